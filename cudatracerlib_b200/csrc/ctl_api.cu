@@ -1,0 +1,503 @@
+// ctl_api.cu -- C ABI (include/ctl_b200.h) over the sm_100a kernels.
+//
+// Host orchestration replaces Tracer<true>::DoPass / UpdateKernel / __internal__IntersectBuffers
+// (Kernel/Tracer.h:209-289, Kernel/TraceHelper.cu:182-217, 736-746): one context per device, one
+// stream, no globals, no per-launch cudaDeviceSynchronize, queue sizes stay on the device.
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include <cstring>
+#include <cstdio>
+#include <cmath>
+#include "../../include/ctl_b200.h"
+#include "scene_builder.h"
+#include "sampler_tables.h"
+#include "wavefront.cuh"
+
+using namespace ctld;
+
+static thread_local std::string g_err;
+static int set_err(const std::string& s) { g_err = s; return 1; }
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { char b_[512]; snprintf(b_, sizeof(b_), "In file %s at line %d : %s", __FILE__, __LINE__, cudaGetErrorString(e_)); return set_err(b_); } } while (0)
+#define CKP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { char b_[512]; snprintf(b_, sizeof(b_), "In file %s at line %d : %s", __FILE__, __LINE__, cudaGetErrorString(e_)); set_err(b_); return nullptr; } } while (0)
+
+struct ctl_scene { ctlb::SceneStorage S; };
+
+namespace {
+const int MAX_BOUNCES = 256;
+const int N_TABLE_SLOTS = 4;
+enum { CTR_Q = 0, CTR_SH = MAX_BOUNCES + 1, CTR_WORK = 2 * (MAX_BOUNCES + 1), CTR_TOTAL = 4 * (MAX_BOUNCES + 1) };
+
+template <typename T> struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    cudaError_t upload(const T* h, size_t count) {
+        cudaError_t e = ensure(count ? count : 1);
+        if (e != cudaSuccess || !count) return e;
+        return cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+} // namespace
+
+struct ctl_ctx {
+    int device = 0, w = 0, h = 0;
+    int n_sm = 148;
+    cudaStream_t stream = nullptr;
+    // parameters (Integrators/PathTracer.h:10-20)
+    int max_path_length = 50, rr_start = 5, direct = 1, regularization = 0, sort_mode = 0, stage_timers = 0, capture_bounce = 0;
+    // scene
+    DevBuf<ctl_bvh_node> d_scene_nodes, d_bvh_nodes; DevBuf<ctl_woop_tri> d_woop; DevBuf<uint32_t> d_tri_index; DevBuf<ctl_tri_data> d_tri_data;
+    DevBuf<ctl_mesh> d_meshes; DevBuf<ctl_node> d_nodes; DevBuf<float> d_xf, d_inv_xf; DevBuf<ctl_material> d_materials; DevBuf<ctl_light> d_lights;
+    DevBuf<ctl_light_tri> d_light_tris; DevBuf<float> d_light_cdf, d_normal_lut;
+    DScene scene; bool has_scene = false;
+    // sampler tables ring
+    DevBuf<float> d_d1[N_TABLE_SLOTS]; DevBuf<float> d_d2[N_TABLE_SLOTS];
+    float* h_d1[N_TABLE_SLOTS] = {nullptr}; float* h_d2[N_TABLE_SLOTS] = {nullptr};
+    cudaEvent_t table_free[N_TABLE_SLOTS] = {nullptr};
+    int table_slot = 0; bool user_tables = false;
+    ctlb::SamplerTableGenerator gen;
+    // wavefront state
+    DevBuf<float4> cf, cl, nor, px, rays_a, rays_b, hit_a, sh_rays, sh_payload, capture;
+    DevBuf<uint32_t> path_a, path_b, hit_node;
+    DevBuf<unsigned> counters;
+    DevBuf<unsigned long long> stats; // [0] rays_last [1] rays_total [2..4] ext visits [5] ext rays [6..8] shadow visits [9] shadow rays
+    DevBuf<float> own_accum; float* accum = nullptr;
+    unsigned captured_n = 0; DevBuf<unsigned> d_captured_n;
+    uint32_t passes_done = 0;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    std::vector<cudaEvent_t> stage_ev; std::vector<int> stage_kind;
+    float stage_ms[5] = {0, 0, 0, 0, 0}; uint32_t n_launches = 0;
+    bool instrumented = false;
+};
+
+extern "C" {
+
+const char* ctl_last_error(void) { return g_err.c_str(); }
+
+// ------------------------------------------------------------------ scenes (host)
+ctl_scene* ctl_scene_create(int kind, int width, int height, uint32_t seed, int n_hint) {
+    try { ctl_scene* s = new ctl_scene(); ctlb::make_scene(kind, width, height, seed, n_hint, s->S); return s; }
+    catch (const std::exception& e) { set_err(e.what()); return nullptr; }
+}
+ctl_scene* ctl_scene_create_from_mesh(const float* verts, uint32_t nv, const uint32_t* indices, uint32_t nt, const uint8_t* mat_index,
+                                      const ctl_material* materials, uint32_t nm, const float* emissive, const float* cam_pos,
+                                      const float* cam_target, const float* cam_up, float fov_deg, int width, int height) {
+    try {
+        ctlb::MeshInput M;
+        for (uint32_t i = 0; i < nv; i++) M.verts.push_back(ctlb::V3(verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]));
+        M.indices.assign(indices, indices + 3 * (size_t)nt);
+        M.mat_index.assign(mat_index, mat_index + nt);
+        M.materials.assign(materials, materials + nm);
+        for (uint32_t i = 0; i < nm; i++) M.emissive.push_back(emissive ? ctlb::V3(emissive[3 * i], emissive[3 * i + 1], emissive[3 * i + 2]) : ctlb::V3(0.0f));
+        ctl_scene* s = new ctl_scene();
+        std::vector<ctlb::MeshInput> meshes = {M};
+        std::vector<ctlb::NodeInput> nodes = {{0, ctlb::M4::identity(), -1}};
+        ctlb::assemble_scene(meshes, nodes, ctlb::V3(cam_pos[0], cam_pos[1], cam_pos[2]), ctlb::V3(cam_target[0], cam_target[1], cam_target[2]),
+                             ctlb::V3(cam_up[0], cam_up[1], cam_up[2]), fov_deg, width, height, s->S);
+        return s;
+    } catch (const std::exception& e) { set_err(e.what()); return nullptr; }
+}
+int ctl_scene_get_view(const ctl_scene* s, ctl_scene_view* out) { if (!s || !out) return set_err("null argument"); s->S.fill_view(out); return 0; }
+void ctl_scene_destroy(ctl_scene* s) { delete s; }
+void ctl_encode_woop(const float v0[3], const float v1[3], const float v2[3], ctl_woop_tri* out) {
+    ctlb::encode_woop(ctlb::V3(v0[0], v0[1], v0[2]), ctlb::V3(v1[0], v1[1], v1[2]), ctlb::V3(v2[0], v2[1], v2[2]), out);
+}
+void ctl_encode_tri_data(const float p[9], const float n[9], const float uv[6], uint32_t mat, ctl_tri_data* out) {
+    ctlb::V3 P[3], N[3];
+    for (int i = 0; i < 3; i++) { P[i] = ctlb::V3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); N[i] = ctlb::V3(n[3 * i], n[3 * i + 1], n[3 * i + 2]); }
+    ctlb::encode_tri_data(P, N, uv, mat, out);
+}
+int ctl_generate_sample_tables(uint32_t pass, float* d1, float* d2) {
+    ctlb::SamplerTableGenerator g;
+    for (uint32_t p = 0; p <= pass; p++) g.next_pass(d1, d2);
+    return 0;
+}
+
+// ------------------------------------------------------------------ context
+static int alloc_image(ctl_ctx* c) {
+    CK(c->own_accum.ensure((size_t)c->w * c->h * 7));
+    c->accum = c->own_accum.p;
+    CK(cudaMemsetAsync(c->accum, 0, (size_t)c->w * c->h * 7 * sizeof(float), c->stream));
+    return 0;
+}
+
+ctl_ctx* ctl_create(int device, int width, int height) {
+    if (width <= 0 || height <= 0) { set_err("invalid resolution"); return nullptr; }
+    int n_dev = 0;
+    CKP(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) { set_err("no such CUDA device"); return nullptr; }
+    CKP(cudaSetDevice(device));
+    ctl_ctx* c = new ctl_ctx();
+    c->device = device; c->w = width; c->h = height;
+    cudaDeviceProp prop;
+    CKP(cudaGetDeviceProperties(&prop, device));
+    c->n_sm = prop.multiProcessorCount;
+    CKP(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CKP(cudaEventCreate(&c->ev_start)); CKP(cudaEventCreate(&c->ev_stop));
+    for (int i = 0; i < N_TABLE_SLOTS; i++) {
+        CKP(c->d_d1[i].ensure((size_t)ctlb::kNumSeq * ctlb::kSeqLen)); CKP(c->d_d2[i].ensure((size_t)ctlb::kNumSeq * ctlb::kSeqLen * 2));
+        CKP(cudaMallocHost((void**)&c->h_d1[i], (size_t)ctlb::kNumSeq * ctlb::kSeqLen * 4)); CKP(cudaMallocHost((void**)&c->h_d2[i], (size_t)ctlb::kNumSeq * ctlb::kSeqLen * 8));
+        CKP(cudaEventCreateWithFlags(&c->table_free[i], cudaEventDisableTiming));
+    }
+    CKP(c->counters.ensure(CTR_TOTAL)); CKP(c->stats.ensure(16)); CKP(c->d_captured_n.ensure(1));
+    CKP(cudaMemset(c->stats.p, 0, 16 * sizeof(unsigned long long)));
+    if (alloc_image(c)) { delete c; return nullptr; }
+    return c;
+}
+
+void ctl_destroy(ctl_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->d_scene_nodes.release(); c->d_bvh_nodes.release(); c->d_woop.release(); c->d_tri_index.release(); c->d_tri_data.release(); c->d_meshes.release();
+    c->d_nodes.release(); c->d_xf.release(); c->d_inv_xf.release(); c->d_materials.release(); c->d_lights.release(); c->d_light_tris.release();
+    c->d_light_cdf.release(); c->d_normal_lut.release();
+    for (int i = 0; i < N_TABLE_SLOTS; i++) { c->d_d1[i].release(); c->d_d2[i].release(); if (c->h_d1[i]) cudaFreeHost(c->h_d1[i]); if (c->h_d2[i]) cudaFreeHost(c->h_d2[i]); if (c->table_free[i]) cudaEventDestroy(c->table_free[i]); }
+    c->cf.release(); c->cl.release(); c->nor.release(); c->px.release(); c->rays_a.release(); c->rays_b.release(); c->hit_a.release(); c->sh_rays.release();
+    c->sh_payload.release(); c->capture.release(); c->path_a.release(); c->path_b.release(); c->hit_node.release(); c->counters.release(); c->stats.release();
+    c->own_accum.release(); c->d_captured_n.release();
+    for (auto e : c->stage_ev) cudaEventDestroy(e);
+    cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_stop);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int ctl_resize(ctl_ctx* c, int width, int height) {
+    if (!c || width <= 0 || height <= 0) return set_err("invalid argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->w = width; c->h = height; c->scene.img_w = width; c->scene.img_h = height;
+    c->passes_done = 0;
+    return alloc_image(c);
+}
+
+int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
+    if (!c || !key) return set_err("null argument");
+    std::string k(key);
+    if (k == "MaxPathLength") { if (v < 1 || v > MAX_BOUNCES) return set_err("MaxPathLength out of range [1,256]"); c->max_path_length = v; }
+    else if (k == "RRStartDepth") { if (v < 0) return set_err("RRStartDepth must be >= 0"); c->rr_start = v; }
+    else if (k == "Direct") c->direct = v != 0;
+    else if (k == "Regularization") { if (v != 0) return set_err("Regularization=true is not implemented (off by default in the reference)"); c->regularization = 0; }
+    else if (k == "SortMode") c->sort_mode = v;
+    else if (k == "StageTimers") c->stage_timers = v != 0;
+    else if (k == "CaptureBounce") c->capture_bounce = v;
+    else return set_err("unknown parameter key: " + k);
+    return 0;
+}
+int ctl_get_param_i(ctl_ctx* c, const char* key, int* v) {
+    if (!c || !key || !v) return set_err("null argument");
+    std::string k(key);
+    if (k == "MaxPathLength") *v = c->max_path_length; else if (k == "RRStartDepth") *v = c->rr_start; else if (k == "Direct") *v = c->direct;
+    else if (k == "Regularization") *v = c->regularization; else if (k == "SortMode") *v = c->sort_mode; else if (k == "StageTimers") *v = c->stage_timers;
+    else if (k == "CaptureBounce") *v = c->capture_bounce; else return set_err("unknown parameter key: " + k);
+    return 0;
+}
+
+int ctl_upload_scene(ctl_ctx* c, const ctl_scene_view* v) {
+    if (!c || !v) return set_err("null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(c->d_scene_nodes.upload(v->scene_bvh_nodes, v->n_scene_bvh_nodes)); CK(c->d_bvh_nodes.upload(v->bvh_nodes, v->n_bvh_nodes));
+    CK(c->d_woop.upload(v->woop, v->n_woop)); CK(c->d_tri_index.upload(v->tri_index, v->n_tri_index)); CK(c->d_tri_data.upload(v->tri_data, v->n_tri_data));
+    CK(c->d_meshes.upload(v->meshes, v->n_meshes)); CK(c->d_nodes.upload(v->nodes, v->n_nodes));
+    CK(c->d_xf.upload(v->node_xf, (size_t)v->n_nodes * 16)); CK(c->d_inv_xf.upload(v->node_inv_xf, (size_t)v->n_nodes * 16));
+    CK(c->d_materials.upload(v->materials, v->n_materials)); CK(c->d_lights.upload(v->lights, v->n_lights_buf));
+    CK(c->d_light_tris.upload(v->light_tris, v->n_light_tris)); CK(c->d_light_cdf.upload(v->light_cdf_data, v->n_light_cdf_data));
+    // sin/cos tables of the 16-bit spherical normal code (Math/Compression.h:20-31), computed with the host libm
+    std::vector<float> lut(1024);
+    for (int i = 0; i < 256; i++) {
+        float th, ph, th2, ph2;
+        ctlb::normal_code_angles((uint16_t)(i << 8), th, ph); ctlb::normal_code_angles((uint16_t)i, th2, ph2);
+        lut[i] = sinf(th); lut[256 + i] = cosf(th); lut[512 + i] = sinf(ph2); lut[768 + i] = cosf(ph2);
+        (void)ph; (void)th2;
+    }
+    CK(c->d_normal_lut.upload(lut.data(), 1024));
+    DScene& S = c->scene;
+    S.scene_nodes = (const float4*)c->d_scene_nodes.p; S.bvh_nodes = (const float4*)c->d_bvh_nodes.p; S.woop = (const float4*)c->d_woop.p;
+    S.tri_index = c->d_tri_index.p; S.tri_data = (const uint4*)c->d_tri_data.p; S.meshes = c->d_meshes.p; S.nodes = c->d_nodes.p;
+    S.node_xf = (const float4*)c->d_xf.p; S.node_inv_xf = (const float4*)c->d_inv_xf.p; S.materials = c->d_materials.p; S.lights = c->d_lights.p;
+    S.light_tris = c->d_light_tris.p; S.light_cdf_data = c->d_light_cdf.p; S.normal_lut = c->d_normal_lut.p;
+    S.d1 = c->d_d1[0].p; S.d2 = (const float2*)c->d_d2[0].p;
+    S.num_lights = v->num_lights;
+    memcpy(S.light_indices, v->light_indices, sizeof(S.light_indices)); memcpy(S.light_cdf, v->light_cdf, sizeof(S.light_cdf));
+    S.camera = v->camera; S.ray_eps = v->ray_eps; S.scene_start = v->scene_start_node; S.n_nodes = v->n_nodes;
+    S.img_w = c->w; S.img_h = c->h;
+    c->has_scene = true;
+    return 0;
+}
+
+int ctl_upload_samples(ctl_ctx* c, const float* d1, const float* d2) {
+    if (!c || !d1 || !d2) return set_err("null argument");
+    CK(cudaSetDevice(c->device));
+    const int s = (c->table_slot + 1) % N_TABLE_SLOTS;
+    CK(cudaEventSynchronize(c->table_free[s]));
+    memcpy(c->h_d1[s], d1, (size_t)ctlb::kNumSeq * ctlb::kSeqLen * 4); memcpy(c->h_d2[s], d2, (size_t)ctlb::kNumSeq * ctlb::kSeqLen * 8);
+    CK(cudaMemcpyAsync(c->d_d1[s].p, c->h_d1[s], (size_t)ctlb::kNumSeq * ctlb::kSeqLen * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_d2[s].p, c->h_d2[s], (size_t)ctlb::kNumSeq * ctlb::kSeqLen * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(c->table_free[s], c->stream));
+    c->table_slot = s; c->user_tables = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------ intersect API
+static int grid_for(const ctl_ctx* c, int per_sm) { return c->n_sm * per_sm; }
+
+int ctl_intersect(ctl_ctx* c, int n, const void* d_rays, void* d_results, int any_hit, void* stream) {
+    if (!c || !c->has_scene) return set_err("no scene uploaded");
+    if (n < 0) return set_err("negative ray count");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    unsigned* work = c->counters.p + CTR_WORK + 2 * MAX_BOUNCES + 1;
+    CK(cudaMemsetAsync(work, 0, sizeof(unsigned), st));
+    const int grid = grid_for(c, 8);
+    if (any_hit) k_intersect<2, true, false><<<grid, 128, 0, st>>>(c->scene, (const float4*)d_rays, nullptr, n, work, nullptr, nullptr, nullptr, nullptr, d_results, nullptr);
+    else k_intersect<2, false, false><<<grid, 128, 0, st>>>(c->scene, (const float4*)d_rays, nullptr, n, work, nullptr, nullptr, nullptr, nullptr, d_results, nullptr);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int ctl_intersect_host(ctl_ctx* c, int n, const ctl_traversal_ray* rays, ctl_traversal_result* results, int any_hit) {
+    if (!c || !c->has_scene) return set_err("no scene uploaded");
+    if (n < 0) return set_err("negative ray count");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    DevBuf<float4> dr, dres;
+    CK(dr.ensure((size_t)n * 2)); CK(dres.ensure((size_t)n));
+    CK(cudaMemcpyAsync(dr.p, rays, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream));
+    int rc = ctl_intersect(c, n, dr.p, dres.p, any_hit, nullptr);
+    if (!rc) { cudaError_t e = cudaMemcpyAsync(results, dres.p, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream); if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) rc = set_err(cudaGetErrorString(e)); }
+    dr.release(); dres.release();
+    return rc;
+}
+
+int ctl_trace_rays_host(ctl_ctx* c, int n, const ctl_traversal_ray* rays, ctl_trace_result* results, uint64_t counts[3]) {
+    if (!c || !c->has_scene) return set_err("no scene uploaded");
+    if (n < 0) return set_err("negative ray count");
+    if (n == 0) { if (counts) counts[0] = counts[1] = counts[2] = 0; return 0; }
+    CK(cudaSetDevice(c->device));
+    DevBuf<float4> dr; DevBuf<float> dres; DevBuf<unsigned long long> dcnt;
+    CK(dr.ensure((size_t)n * 2)); CK(dres.ensure((size_t)n * 5)); CK(dcnt.ensure(4));
+    CK(cudaMemsetAsync(dcnt.p, 0, 32, c->stream));
+    CK(cudaMemcpyAsync(dr.p, rays, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream));
+    unsigned* work = c->counters.p + CTR_WORK + 2 * MAX_BOUNCES + 1;
+    CK(cudaMemsetAsync(work, 0, sizeof(unsigned), c->stream));
+    const int grid = grid_for(c, 8);
+    if (counts) k_intersect<3, false, true><<<grid, 128, 0, c->stream>>>(c->scene, dr.p, nullptr, n, work, nullptr, nullptr, nullptr, nullptr, dres.p, dcnt.p);
+    else k_intersect<3, false, false><<<grid, 128, 0, c->stream>>>(c->scene, dr.p, nullptr, n, work, nullptr, nullptr, nullptr, nullptr, dres.p, nullptr);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(results, dres.p, (size_t)n * 20, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long hc[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(hc, dcnt.p, 32, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (counts) { counts[0] = hc[0]; counts[1] = hc[1]; counts[2] = hc[2]; }
+    dr.release(); dres.release(); dcnt.release();
+    return 0;
+}
+
+// ------------------------------------------------------------------ render pass
+static int ensure_state(ctl_ctx* c, size_t n) {
+    CK(c->cf.ensure(n)); CK(c->cl.ensure(n)); CK(c->nor.ensure(n)); CK(c->px.ensure(n));
+    CK(c->rays_a.ensure(2 * n)); CK(c->rays_b.ensure(2 * n)); CK(c->hit_a.ensure(n)); CK(c->hit_node.ensure(n));
+    CK(c->sh_rays.ensure(2 * n)); CK(c->sh_payload.ensure(n)); CK(c->path_a.ensure(n)); CK(c->path_b.ensure(n));
+    return 0;
+}
+
+static void stage_mark(ctl_ctx* c, int kind) {
+    if (!c->stage_timers) return;
+    size_t i = c->stage_kind.size();
+    if (i >= c->stage_ev.size()) { cudaEvent_t e; cudaEventCreate(&e); c->stage_ev.push_back(e); }
+    cudaEventRecord(c->stage_ev[i], c->stream);
+    c->stage_kind.push_back(kind);
+}
+
+static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
+    if (!c->has_scene) return set_err("no scene uploaded");
+    if (W.n_slots <= 0) return 0;
+    CK(cudaSetDevice(c->device));
+    if (new_trace) {
+        CK(cudaMemsetAsync(c->accum, 0, (size_t)c->w * c->h * 7 * sizeof(float), c->stream));
+        c->passes_done = 0;
+        if (!c->user_tables) c->gen.reset();
+    }
+    // sample tables of this pass (GenerateNewRandomSequences, Kernel/Sampler.h:36-55): host XORWOW, async H2D
+    if (!c->user_tables) {
+        const int s = (c->table_slot + 1) % N_TABLE_SLOTS;
+        CK(cudaEventSynchronize(c->table_free[s]));
+        c->gen.next_pass(c->h_d1[s], c->h_d2[s]);
+        CK(cudaMemcpyAsync(c->d_d1[s].p, c->h_d1[s], (size_t)ctlb::kNumSeq * ctlb::kSeqLen * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_d2[s].p, c->h_d2[s], (size_t)ctlb::kNumSeq * ctlb::kSeqLen * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaEventRecord(c->table_free[s], c->stream));
+        c->table_slot = s;
+    }
+    c->user_tables = false;
+    c->scene.d1 = c->d_d1[c->table_slot].p; c->scene.d2 = (const float2*)c->d_d2[c->table_slot].p;
+    c->scene.img_w = c->w; c->scene.img_h = c->h;
+    if (ensure_state(c, (size_t)W.n_slots)) return 1;
+    if (c->capture_bounce > 0) CK(c->capture.ensure(2 * (size_t)W.n_slots));
+
+    CK(cudaEventRecord(c->ev_start, c->stream));
+    c->stage_kind.clear();
+    CK(cudaMemsetAsync(c->counters.p, 0, CTR_TOTAL * sizeof(unsigned), c->stream));
+    if (c->instrumented) CK(cudaMemsetAsync(c->stats.p + 2, 0, 8 * sizeof(unsigned long long), c->stream));
+    unsigned* ctr = c->counters.p;
+    PathState st = {c->cf.p, c->cl.p, c->nor.p, c->px.p};
+    const int g_light = grid_for(c, 8);
+    const int g_trav = grid_for(c, 8);
+    uint32_t launches = 0;
+    stage_mark(c, 0);
+    k_generate<<<g_light, 256, 0, c->stream>>>(c->scene, W, st, c->rays_a.p, c->path_a.p, ctr + CTR_Q + 0);
+    launches++;
+    ShadeParams P = {c->max_path_length, c->rr_start, c->direct};
+    float4* rin = c->rays_a.p; float4* rout = c->rays_b.p; uint32_t* pin = c->path_a.p; uint32_t* pout = c->path_b.p;
+    for (int b = 0; b < c->max_path_length; b++) {
+        stage_mark(c, 1);
+        if (c->capture_bounce == b + 1) {
+            CK(cudaMemcpyAsync(c->capture.p, rin, 32 * (size_t)W.n_slots, cudaMemcpyDeviceToDevice, c->stream));
+            CK(cudaMemcpyAsync(c->d_captured_n.p, ctr + CTR_Q + b, sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
+        }
+        if (c->instrumented) k_intersect<0, false, true><<<g_trav, 128, 0, c->stream>>>(c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, c->stats.p + 2);
+        else k_intersect<0, false, false><<<g_trav, 128, 0, c->stream>>>(c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, nullptr);
+        stage_mark(c, 2);
+        Queues Q = {rin, pin, rout, pout, c->hit_a.p, c->hit_node.p, c->sh_rays.p, c->sh_payload.p};
+        k_shade<<<g_light, 128, 0, c->stream>>>(c->scene, P, st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b);
+        stage_mark(c, 3);
+        if (c->direct) {
+            if (c->instrumented) k_intersect<1, true, true><<<g_trav, 128, 0, c->stream>>>(c->scene, c->sh_rays.p, ctr + CTR_SH + b, 0, ctr + CTR_WORK + 2 * b + 1, nullptr, nullptr, c->sh_payload.p, c->cl.p, nullptr, c->stats.p + 6);
+            else k_intersect<1, true, false><<<g_trav, 128, 0, c->stream>>>(c->scene, c->sh_rays.p, ctr + CTR_SH + b, 0, ctr + CTR_WORK + 2 * b + 1, nullptr, nullptr, c->sh_payload.p, c->cl.p, nullptr, nullptr);
+            launches++;
+        }
+        launches += 2;
+        std::swap(rin, rout); std::swap(pin, pout);
+    }
+    stage_mark(c, 4);
+    k_finish<<<g_light, 256, 0, c->stream>>>(W.n_slots, st, c->accum, c->w, c->h);
+    k_tally<<<1, 32, 0, c->stream>>>(ctr + CTR_Q, ctr + CTR_SH, c->max_path_length, c->stats.p, c->stats.p + 1);
+    launches += 2;
+    stage_mark(c, 5);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev_stop, c->stream));
+    c->n_launches = launches;
+    c->passes_done++;
+    return 0;
+}
+
+int ctl_render_pass(ctl_ctx* c, int new_trace, int x0, int y0, int x1, int y1) {
+    if (!c) return set_err("null context");
+    if (x0 < 0 || y0 < 0 || x1 > c->w || y1 > c->h || x1 < x0 || y1 < y0) return set_err("pixel window outside the image");
+    Window W; memset(&W, 0, sizeof(W));
+    W.mode = 0; W.x0 = x0; W.y0 = y0; W.x1 = x1; W.y1 = y1; W.n_slots = (x1 - x0) * (y1 - y0);
+    return render_window(c, new_trace, W);
+}
+
+int ctl_render_pass_tiled(ctl_ctx* c, int new_trace, int tile_w, int tile_h, int part, int n_parts) {
+    if (!c) return set_err("null context");
+    if (tile_w <= 0 || tile_h <= 0 || n_parts <= 0 || part < 0 || part >= n_parts) return set_err("invalid tiling");
+    Window W; memset(&W, 0, sizeof(W));
+    W.mode = 1; W.tile_w = tile_w; W.tile_h = tile_h; W.part = part; W.n_parts = n_parts;
+    W.tiles_x = (c->w + tile_w - 1) / tile_w; W.tiles_y = (c->h + tile_h - 1) / tile_h;
+    const int n_tiles = W.tiles_x * W.tiles_y;
+    const int n_local = n_tiles > part ? (n_tiles - part + n_parts - 1) / n_parts : 0;
+    W.n_slots = n_local * tile_w * tile_h;
+    if (W.n_slots == 0 && new_trace) { // still honour the clear
+        CK(cudaSetDevice(c->device));
+        CK(cudaMemsetAsync(c->accum, 0, (size_t)c->w * c->h * 7 * sizeof(float), c->stream));
+    }
+    return render_window(c, new_trace, W);
+}
+
+int ctl_synchronize(ctl_ctx* c) {
+    if (!c) return set_err("null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int ctl_read_accum(ctl_ctx* c, ctl_pixel_data* out) {
+    if (!c || !out) return set_err("null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(out, c->accum, (size_t)c->w * c->h * 7 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+void* ctl_accum_device_ptr(ctl_ctx* c) { return c ? (void*)c->accum : nullptr; }
+int ctl_set_accum_device_ptr(ctl_ctx* c, void* p) {
+    if (!c) return set_err("null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->accum = p ? (float*)p : c->own_accum.p;
+    return 0;
+}
+void* ctl_stream(ctl_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int ctl_stats(ctl_ctx* c, uint64_t* rays_last, float* seconds_last, uint64_t* rays_total, uint32_t* passes_done) {
+    if (!c) return set_err("null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    unsigned long long h[2] = {0, 0};
+    CK(cudaMemcpy(h, c->stats.p, sizeof(h), cudaMemcpyDeviceToHost));
+    float ms = 0.0f;
+    if (c->passes_done) CK(cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop));
+    if (rays_last) *rays_last = h[0];
+    if (rays_total) *rays_total = h[1];
+    if (seconds_last) *seconds_last = ms * 1e-3f;
+    if (passes_done) *passes_done = c->passes_done;
+    return 0;
+}
+
+int ctl_stage_times(ctl_ctx* c, float ms[5], uint32_t* n_launches) {
+    if (!c) return set_err("null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 5; i++) c->stage_ms[i] = 0;
+    for (size_t i = 0; i + 1 < c->stage_kind.size(); i++) {
+        float t = 0; CK(cudaEventElapsedTime(&t, c->stage_ev[i], c->stage_ev[i + 1]));
+        int k = c->stage_kind[i]; if (k >= 0 && k < 5) c->stage_ms[k] += t;
+    }
+    if (ms) memcpy(ms, c->stage_ms, sizeof(c->stage_ms));
+    if (n_launches) *n_launches = c->n_launches;
+    return 0;
+}
+
+int ctl_set_instrumented(ctl_ctx* c, int on) { if (!c) return set_err("null context"); c->instrumented = on != 0; return 0; }
+int ctl_get_visit_counts(ctl_ctx* c, uint64_t ext[4], uint64_t sh[4]) {
+    if (!c) return set_err("null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    unsigned long long h[8]; std::vector<unsigned> ctr(CTR_TOTAL);
+    CK(cudaMemcpy(h, c->stats.p + 2, sizeof(h), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ctr.data(), c->counters.p, CTR_TOTAL * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    unsigned long long ne = 0, ns = 0;
+    for (int b = 0; b < c->max_path_length; b++) { ne += ctr[CTR_Q + b]; ns += ctr[CTR_SH + b]; }
+    if (ext) { ext[0] = h[0]; ext[1] = h[1]; ext[2] = h[2]; ext[3] = ne; }
+    if (sh) { sh[0] = h[4]; sh[1] = h[5]; sh[2] = h[6]; sh[3] = ns; }
+    return 0;
+}
+int ctl_get_queue_sizes(ctl_ctx* c, uint32_t* ext, uint32_t* sh, int n) {
+    if (!c) return set_err("null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    std::vector<unsigned> ctr(CTR_TOTAL);
+    CK(cudaMemcpy(ctr.data(), c->counters.p, CTR_TOTAL * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < n && b < MAX_BOUNCES; b++) { if (ext) ext[b] = ctr[CTR_Q + b]; if (sh) sh[b] = ctr[CTR_SH + b]; }
+    return 0;
+}
+int ctl_get_captured_rays(ctl_ctx* c, ctl_traversal_ray* host_out, int capacity) {
+    if (!c) { set_err("null context"); return -1; }
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) { set_err("cuda error"); return -1; }
+    unsigned n = 0;
+    if (cudaMemcpy(&n, c->d_captured_n.p, sizeof(n), cudaMemcpyDeviceToHost) != cudaSuccess) { set_err("cuda error"); return -1; }
+    int m = (int)n < capacity ? (int)n : capacity;
+    if (m > 0 && host_out && cudaMemcpy(host_out, c->capture.p, (size_t)m * 32, cudaMemcpyDeviceToHost) != cudaSuccess) { set_err("cuda error"); return -1; }
+    return m;
+}
+
+} // extern "C"

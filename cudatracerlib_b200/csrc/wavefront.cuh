@@ -1,0 +1,293 @@
+// wavefront.cuh -- the wavefront stages of the path tracer (device kernels).
+//
+// Replaces the megakernel pathKernel2 -> PathTrace<DIRECT> (Integrators/PathTracer.cu:10-113,182-194)
+// by stages  generate -> [ intersect(ext) -> shade (+NEE emit) -> intersect(shadow, any-hit, adds the
+// pending NEE term) ] x bounces -> finish (Image::AddSample, Engine/Image.cu:22-44),
+// with warp-ballot stream compaction of surviving paths between bounces.  Per-path arithmetic and
+// random-number bookkeeping are those of PathTrace.
+#pragma once
+#include "device/shading.cuh"
+#include <cfloat>
+
+namespace ctld {
+
+struct Window { // which pixels a pass renders
+    int mode;   // 0 = rectangle [x0,x1) x [y0,y1); 1 = interleaved tiles
+    int x0, y0, x1, y1;
+    int tile_w, tile_h, part, n_parts, tiles_x, tiles_y;
+    int n_slots;
+};
+
+// SoA path state, indexed by path id (= window slot)
+struct PathState {
+    float4* cf;   // throughput rgb, brdf_scattering_pdf
+    float4* cl;   // radiance rgb, -
+    float4* nor;  // last_nor xyz, packed (depth | specular<<8 | i1<<9 | i2<<19)
+    float4* px;   // pX, pY, sampler index bits, valid flag
+};
+
+struct Queues {
+    float4* rays_in;  uint32_t* path_in;   // extension rays of this bounce (2 x float4 each) + owning path
+    float4* rays_out; uint32_t* path_out;  // next bounce
+    float4* hit_a;    uint32_t* hit_node;  // (dist,u,v,tri) + node, by queue position
+    float4* sh_rays;  float4* sh_payload;  // shadow rays + (pending radiance rgb, path id)
+};
+
+CTL_DEV unsigned lane_id() { return threadIdx.x & 31; }
+
+// all 32 lanes must call
+CTL_DEV int warp_append(bool pred, unsigned* counter) {
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (!mask) return -1;
+    const int leader = __ffs(mask) - 1;
+    unsigned base = 0;
+    if ((int)lane_id() == leader) base = atomicAdd(counter, (unsigned)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return pred ? (int)(base + __popc(mask & ((1u << lane_id()) - 1u))) : -1;
+}
+
+CTL_DEV uint32_t pack_ctl(int depth, bool spec, unsigned i1, unsigned i2) { return (uint32_t)depth | (spec ? 256u : 0u) | (i1 << 9) | (i2 << 19); }
+
+CTL_DEV bool slot_to_pixel(const Window& W, int s, int img_w, int img_h, int& x, int& y) {
+    if (W.mode == 0) {
+        const int bw = W.x1 - W.x0;
+        x = W.x0 + s % bw; y = W.y0 + s / bw;
+    } else {
+        const int per = W.tile_w * W.tile_h;
+        const int t_local = s / per, r = s % per;
+        const int tile = W.part + t_local * W.n_parts;
+        const int tx = tile % W.tiles_x, ty = tile / W.tiles_x;
+        x = tx * W.tile_w + r % W.tile_w; y = ty * W.tile_h + r / W.tile_w;
+    }
+    return x >= 0 && y >= 0 && x < img_w && y < img_h;
+}
+
+// ---- generate: pathKernel2 prologue (PathTracer.cu:184-190) -------------------
+__global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene S, const __grid_constant__ Window W, PathState st,
+                                                   float4* rays, uint32_t* paths, unsigned* q_count) {
+    const int n_round = (W.n_slots + 31) & ~31;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_round; s += gridDim.x * blockDim.x) {
+        int x = 0, y = 0;
+        const bool in_range = s < W.n_slots;
+        const bool valid = in_range && slot_to_pixel(W, s, S.img_w, S.img_h, x, y);
+        V3 o = mk(0, 0, 0), d = mk(0, 0, 1);
+        if (valid) {
+            Sampler rng; rng.idx = (unsigned)(y * S.img_w + x); rng.i1 = 0; rng.i2 = 0;
+            const float2 j = rng.f2(S);
+            const float pX = (float)x + j.x, pY = (float)y + j.y;
+            rng.f2(S); // aperture sample: drawn, unused by the pinhole camera
+            camera_ray(S, pX, pY, o, d);
+            st.px[s] = make_float4(pX, pY, __uint_as_float(rng.idx), 1.0f);
+            st.cf[s] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+            st.cl[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            st.nor[s] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(pack_ctl(0, false, rng.i1, rng.i2)));
+        } else if (in_range) {
+            st.px[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        const int jq = warp_append(valid, q_count);
+        if (valid) {
+            rays[2 * jq] = make_float4(o.x, o.y, o.z, S.ray_eps);
+            rays[2 * jq + 1] = make_float4(d.x, d.y, d.z, FLT_MAX);
+            paths[jq] = (uint32_t)s;
+        }
+    }
+}
+
+// ---- intersect ------------------------------------------------------------------
+// MODE 0: wavefront extension (closest hit -> hit_a / hit_node)
+// MODE 1: wavefront shadow (any hit; unoccluded => cl[path] += pending)
+// MODE 2: API, 16-byte traversalResult, box/tri lower bound = ray.tmin  (== intersectKernel, TraceHelper.cu:326-734)
+// MODE 3: API, ctl_trace_result, t in (rayEps, FLT_MAX)                  (== traceRay, TraceHelper.cu:174-180)
+template <int MODE, bool ANY_HIT, bool COUNT>
+__global__ void __launch_bounds__(128) k_intersect(const __grid_constant__ DScene S, const float4* __restrict__ rays, const unsigned* __restrict__ n_ptr, int n_fixed,
+                                                    unsigned* work_ctr, float4* __restrict__ hit_a, uint32_t* __restrict__ hit_node,
+                                                    const float4* __restrict__ sh_payload, float4* __restrict__ cl,
+                                                    void* __restrict__ api_out, unsigned long long* visit_out) {
+    const int n = n_ptr ? (int)*n_ptr : n_fixed;
+    VisitCounters<COUNT> cnt;
+    for (;;) {
+        unsigned base = 0;
+        if (lane_id() == 0) base = atomicAdd(work_ctr, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((int)base >= n) break;
+        const int i = (int)base + (int)lane_id();
+        if (i < n) {
+            const float4 ro = __ldg(rays + 2 * i), rd = __ldg(rays + 2 * i + 1);
+            Hit hit; hit.u = hit.v = 0.0f; hit.tri = 0xffffffffu; hit.node = 0xffffffffu;
+            float tri_lo, box_lo;
+            if (MODE == 3) { tri_lo = S.ray_eps; box_lo = 0.0f; hit.dist = FLT_MAX; }
+            else if (MODE == 2) { tri_lo = ro.w; box_lo = ro.w; hit.dist = rd.w; }
+            else { tri_lo = ro.w; box_lo = 0.0f; hit.dist = rd.w; }
+            trace_ray<ANY_HIT, COUNT>(S, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), tri_lo, box_lo, hit, cnt);
+            if (MODE == 0) {
+                hit_a[i] = make_float4(hit.dist, hit.u, hit.v, __uint_as_float(hit.tri));
+                hit_node[i] = hit.node;
+            } else if (MODE == 1) {
+                if (hit.tri == 0xffffffffu) {
+                    const float4 pl = __ldg(sh_payload + i);
+                    const uint32_t p = __float_as_uint(pl.w);
+                    float4 c = cl[p];
+                    c.x = c.x + pl.x; c.y = c.y + pl.y; c.z = c.z + pl.z;
+                    cl[p] = c;
+                }
+            } else if (MODE == 2) {
+                uint4 res = make_uint4(__float_as_uint(hit.dist), 0xffffffffu, 0xffffffffu, 0u);
+                if (hit.tri != 0xffffffffu) {
+                    res.y = hit.node; res.z = hit.tri;
+                    const unsigned short xd = (unsigned short)(hit.u * 65535), yd = (unsigned short)(hit.v * 65535); // TraceHelper.cu:726-727
+                    res.w = ((uint32_t)yd << 16) | (uint32_t)xd;
+                }
+                ((uint4*)api_out)[i] = res;
+            } else {
+                float* out = (float*)api_out + (size_t)i * 5;
+                out[0] = hit.dist; out[1] = hit.u; out[2] = hit.v; out[3] = __uint_as_float(hit.tri); out[4] = __uint_as_float(hit.node);
+            }
+        }
+    }
+    if (COUNT) {
+        VisitCounters<true>& c = (VisitCounters<true>&)cnt;
+        unsigned a = c.inner, b = c.tris, e = c.inst;
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); e += __shfl_xor_sync(0xffffffffu, e, o); }
+        if (lane_id() == 0) { atomicAdd(visit_out, (unsigned long long)a); atomicAdd(visit_out + 1, (unsigned long long)b); atomicAdd(visit_out + 2, (unsigned long long)e); }
+    }
+}
+
+// ---- shade: one path vertex (PathTracer.cu:58-96) ----------------------------------
+struct ShadeParams { int max_path_length, rr_start, direct; };
+
+__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene S, const __grid_constant__ ShadeParams P, PathState st, Queues Q,
+                                                const unsigned* __restrict__ n_in, unsigned* n_out, unsigned* n_shadow) {
+    const int n = (int)*n_in;
+    const int n_round = (n + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        bool alive = false, shadow = false;
+        uint32_t p = 0;
+        V3 no = mk(0, 0, 0), nd = mk(0, 0, 1), sd = mk(0, 0, 1);
+        float sh_tmax = 0.0f;
+        Spec pending = sp(0.0f);
+        if (i < n) {
+            p = Q.path_in[i];
+            const float4 ha = Q.hit_a[i];
+            const uint32_t tri = __float_as_uint(ha.w);
+            if (tri != 0xffffffffu) {
+                const uint32_t node = Q.hit_node[i];
+                const float4 r0 = Q.rays_in[2 * i], r1 = Q.rays_in[2 * i + 1];
+                const V3 ro = mk(r0.x, r0.y, r0.z), rd = mk(r1.x, r1.y, r1.z);
+                const float4 cf4 = st.cf[p], nor4 = st.nor[p];
+                float4 cl4 = st.cl[p];
+                Spec cf = mk_sp(cf4.x, cf4.y, cf4.z), cl = mk_sp(cl4.x, cl4.y, cl4.z);
+                float brdf_pdf = cf4.w;
+                V3 last_nor = mk(nor4.x, nor4.y, nor4.z);
+                const uint32_t ctl = __float_as_uint(nor4.w);
+                const int depth = (int)(ctl & 0xff) + 1; // depth++ at loop entry
+                bool specularBounce = (ctl & 256u) != 0;
+                Sampler rnd; rnd.idx = __float_as_uint(st.px[p].z); rnd.i1 = (ctl >> 9) & 0x3ff; rnd.i2 = ctl >> 19;
+                // getBsdfSample (Kernel/TraceResult.cu:16-43)
+                DG dg; uint32_t mat_local;
+                dg.P = ro + rd * ha.x;
+                fill_dg(S, ha.y, ha.z, tri, node, dg, mat_local);
+                const ctl_node* N = S.nodes + node;
+                const ctl_material mat = S.materials[mat_local + __ldg(&N->material_offset)];
+                BRec bRec; bRec.eta = 1.0f; bRec.sampledType = 0; bRec.typeMask = E_ALL; bRec.wo = mk(0, 0, 1);
+                bRec.wi = to_local(dg.sys, -rd);
+                if ((mat.flags & CTL_MAT_TWO_SIDED) && bRec.wi.z < 0) { dg.n = -dg.n; dg.sys.n = -dg.sys.n; bRec.wi.z *= -1.0f; }
+                // emitter hit with MIS (PathTracer.cu:64-77)
+                if (mat.node_light_index != 0xffffffffu) {
+                    const unsigned li = mat.node_light_index == 0 ? __ldg(&N->lights[0]) : __ldg(&N->lights[1]);
+                    const ctl_light L = S.lights[li];
+                    float misWeight = 1.0f;
+                    if (!(!P.direct || depth == 1 || specularBounce)) {
+                        DRec dRec; dRec.ref = ro; dRec.refN = last_nor; dRec.p = dg.P; dRec.n = dg.n; dRec.d = rd; dRec.dist = ha.x;
+                        const float direct_pdf = light_pdf_direct(L, dRec) * pdf_emitter(S, li);
+                        misWeight = power_heuristic(brdf_pdf, direct_pdf);
+                    }
+                    const Spec Le = dot(dg.sys.n, -rd) <= 0 ? sp(0.0f) : sp3(L.radiance);
+                    cl = cl + (cf * misWeight) * Le;
+                }
+                const float2 bs = rnd.f2(S);
+                const Spec f = bsdf_sample(mat, bRec, brdf_pdf, bs.x, bs.y);
+                last_nor = dg.sys.n;
+                // next-event estimation (TraceAlgorithms.cu:44-101)
+                if (P.direct && (bsdf_combined_type(mat.bsdf_type) & E_SMOOTH) && S.num_lights) {
+                    const float2 ls = rnd.f2(S);
+                    unsigned first = 0, count = S.num_lights; // STL_upper_bound, Base/STL.h:21-38
+                    while (count > 0) { const unsigned c2 = count / 2, mid = first + c2; if (!(ls.x < S.light_cdf[mid])) { first = mid + 1; count -= c2 + 1; } else count = c2; }
+                    unsigned idx = first; if (idx >= S.num_lights) idx = S.num_lights - 1;
+                    const float fU = S.light_cdf[idx], fL = idx > 0 ? S.light_cdf[idx - 1] : 0.0f;
+                    const float emPdf = fU - fL;
+                    const ctl_light L = S.lights[S.light_indices[idx]];
+                    DRec dRec; dRec.ref = dg.P; dRec.refN = dg.sys.n; dRec.p = dg.P; dRec.n = dg.sys.n; dRec.pdf = 0;
+                    const float2 es = rnd.f2(S);
+                    const Spec value = light_sample_direct(S, L, dRec, es.x, es.y);
+                    if (!is_zero(value)) {
+                        BRec b2 = bRec;
+                        b2.wo = to_local(dg.sys, dRec.d);
+                        b2.typeMask = E_ALL & ~E_DELTA;
+                        const Spec bsdfVal = bsdf_f(mat, b2);
+                        if (!is_zero(bsdfVal)) {
+                            const float bsdfPdf = bsdf_pdf(mat, b2);
+                            const float directPdf = dRec.pdf * emPdf;
+                            const float weight = power_heuristic(directPdf, bsdfPdf);
+                            const Spec retVal = (value * bsdfVal) * weight;
+                            pending = cf * (retVal / emPdf);
+                            shadow = true; sd = dRec.d; sh_tmax = dRec.dist - S.ray_eps;
+                        }
+                    }
+                }
+                specularBounce = (bRec.sampledType & E_DELTA) != 0;
+                cf = cf * f;
+                nd = to_world(dg.sys, bRec.wo); no = dg.P;
+                alive = !is_zero(cf);
+                if (alive && depth > P.rr_start && !specularBounce) {
+                    const float q = smax(cf);
+                    if (rnd.f1(S) >= q) alive = false;
+                    else cf = cf / q;
+                }
+                if (depth >= P.max_path_length) alive = false;
+                cl4.x = cl.r; cl4.y = cl.g; cl4.z = cl.b;
+                st.cl[p] = cl4;
+                if (alive) {
+                    st.cf[p] = make_float4(cf.r, cf.g, cf.b, brdf_pdf);
+                    st.nor[p] = make_float4(last_nor.x, last_nor.y, last_nor.z, __uint_as_float(pack_ctl(depth, specularBounce, rnd.i1, rnd.i2)));
+                }
+            }
+        }
+        const int jq = warp_append(alive, n_out);
+        if (alive) {
+            Q.rays_out[2 * jq] = make_float4(no.x, no.y, no.z, S.ray_eps);
+            Q.rays_out[2 * jq + 1] = make_float4(nd.x, nd.y, nd.z, FLT_MAX);
+            Q.path_out[jq] = p;
+        }
+        const int ks = warp_append(shadow, n_shadow);
+        if (shadow) {
+            Q.sh_rays[2 * ks] = make_float4(no.x, no.y, no.z, S.ray_eps);
+            Q.sh_rays[2 * ks + 1] = make_float4(sd.x, sd.y, sd.z, sh_tmax);
+            Q.sh_payload[ks] = make_float4(pending.r, pending.g, pending.b, __uint_as_float(p));
+        }
+    }
+}
+
+// ---- finish: img.AddSample(pX.x, pX.y, imp * L) (PathTracer.cu:191-192, Image.cu:22-44) ----
+__global__ void __launch_bounds__(256) k_finish(int n_slots, PathState st, float* accum, int img_w, int img_h) {
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
+        const float4 px = st.px[s];
+        if (px.w == 0.0f) continue;
+        const float4 c = st.cl[s];
+        const float r = fmaxf(0.0f, c.x), g = fmaxf(0.0f, c.y), b = fmaxf(0.0f, c.z);
+        const int x = (int)floorf(px.x), y = (int)floorf(px.y);
+        if (x < 0 || x >= img_w || y < 0 || y >= img_h || !isfinite(r) || !isfinite(g) || !isfinite(b)) continue;
+        float* dst = accum + ((size_t)y * img_w + x) * 7;
+        atomicAdd(dst + 0, r); atomicAdd(dst + 1, g); atomicAdd(dst + 2, b); atomicAdd(dst + 6, 1.0f);
+    }
+}
+
+// rays of the pass = sum of extension + shadow queue sizes (every traceRay call counts, TraceHelper.cu:176)
+__global__ void k_tally(const unsigned* q_count, const unsigned* sh_count, int n_bounces, unsigned long long* rays_last, unsigned long long* rays_total) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long s = 0;
+        for (int b = 0; b < n_bounces; b++) s += (unsigned long long)q_count[b] + (unsigned long long)sh_count[b];
+        *rays_last = s; *rays_total += s;
+    }
+}
+
+} // namespace ctld

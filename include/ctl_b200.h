@@ -1,0 +1,275 @@
+/*
+ * ctl_b200.h -- C ABI of the B200-native replacement for CudaTracerLib's
+ * ray-traversal + path-tracing hot path.
+ *
+ * Every entry point cites the reference interface (file:line, relative to the
+ * CudaTracerLib tree) that it replaces.  Plain pointers and sizes only; no C++
+ * types, no torch types.  All functions returning int use 0 = ok, non-zero =
+ * error; the message is available from ctl_last_error() (the C++ adapter in
+ * cudatracerlib_b200/csrc/b200_path_tracer.h re-raises it as
+ * std::runtime_error, the reference's ThrowCudaErrors convention,
+ * Defines.cpp:15-29).
+ *
+ * The data surface (ctl_scene_view) mirrors the hot subset of
+ * KernelDynamicScene (Engine/KernelDynamicScene.h:28-57) byte for byte where
+ * the reference layout is on the path (BVH nodes, Woop triangles, leaf index
+ * words, TriangleData, KernelMesh, Node, float4x4, PixelData, traversalRay,
+ * traversalResult) and replaces the 3344-byte tagged-union Material / 592-byte
+ * Light by compact 64-byte records that carry exactly the fields the path
+ * reads.
+ */
+#ifndef CTL_B200_H
+#define CTL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTL_MAX_NUM_LIGHTS 16 /* Engine/KernelDynamicScene.h:26 */
+#define CTL_SENTINEL 0x76543210 /* Kernel/TraceHelper.cu:20 */
+
+/* ---- byte-exact reference layouts ------------------ */
+
+/* Engine/TriIntersectorData.h:42-117; 64 B; children in float4 units */
+typedef struct ctl_bvh_node {
+    float a[4]; /* c0.lo.x c0.hi.x c0.lo.y c0.hi.y */
+    float b[4]; /* c1.lo.x c1.hi.x c1.lo.y c1.hi.y */
+    float c[4]; /* c0.lo.z c0.hi.z c1.lo.z c1.hi.z */
+    int32_t child0, child1;
+    uint32_t parent;
+    uint32_t pad;
+} ctl_bvh_node;
+
+/* Engine/TriIntersectorData.h:30-40; 48 B */
+typedef struct ctl_woop_tri {
+    float a[4], b[4], c[4];
+} ctl_woop_tri;
+
+/* Engine/TriangleData.h:19-35 (EXT_TRI, NUM_UV_SETS 1); 32 B */
+typedef struct ctl_tri_data {
+    uint32_t w[8];
+} ctl_tri_data;
+
+/* Engine/Mesh.h:12-19; 20 B */
+typedef struct ctl_mesh {
+    uint32_t tri_offset;      /* m_uTriangleOffset                     */
+    uint32_t bvh_node_offset; /* m_uBVHNodeOffset, float4 units        */
+    uint32_t bvh_tri_offset;  /* m_uBVHTriangleOffset, float4 units    */
+    uint32_t bvh_idx_offset;  /* m_uBVHIndicesOffset, slots            */
+    uint32_t mat_offset;      /* m_uStdMaterialOffset                  */
+} ctl_mesh;
+
+/* SceneTypes/Node.h:13-20; 24 B */
+typedef struct ctl_node {
+    uint32_t mesh_index;
+    uint32_t material_offset;
+    uint32_t instanciated_material;
+    uint32_t lights[2]; /* 0xffffffff = none */
+    uint32_t n_lights;
+} ctl_node;
+
+/* Kernel/TraceHelper.h:55-59; 32 B */
+typedef struct ctl_traversal_ray {
+    float o[3], tmin;
+    float d[3], tmax;
+} ctl_traversal_ray;
+
+/* Kernel/TraceHelper.h:61-69; 16 B. miss = (dist bits, -1, -1, 0) */
+typedef struct ctl_traversal_result {
+    float dist;
+    int32_t node_idx;
+    int32_t tri_idx;
+    uint32_t bary; /* (u16)(v*65535) << 16 | (u16)(u*65535) */
+} ctl_traversal_result;
+
+/* Kernel/TraceResult.h:17-31 (field order dist,u,v,tri,node); 24 B padded to 32 B
+ * is NOT used on the wire; this 24 B form is what ctl_trace_rays writes. */
+typedef struct ctl_trace_result {
+    float dist;
+    float u, v;
+    uint32_t tri_idx;  /* UINT_MAX = miss */
+    uint32_t node_idx;
+} ctl_trace_result;
+
+/* Engine/Image.h:10-29; 28 B */
+typedef struct ctl_pixel_data {
+    float rgb[3];
+    float rgb_splat[3];
+    float weight_sum;
+} ctl_pixel_data;
+
+/* Engine/ShapeSet.h:16-26; 64 B */
+typedef struct ctl_light_tri {
+    float p[3][3];
+    float n[3];
+    float area;
+    uint32_t i_dat;
+    uint32_t t_dat;
+    uint32_t pad;
+} ctl_light_tri;
+
+/* ---- compact records replacing Material / Light ------------------------ */
+
+enum { CTL_BSDF_DIFFUSE = 0, CTL_BSDF_ROUGHCONDUCTOR = 1, CTL_BSDF_DIELECTRIC = 2 };
+enum { CTL_DISTR_BECKMANN = 0, CTL_DISTR_GGX = 1 };
+#define CTL_MAT_TWO_SIDED 1u
+
+/* Fields read by the path from Material (Engine/Material.h:38-112): NodeLightIndex,
+ * bsdf type + payload (SceneTypes/BSDF_Simple.h), m_enableTwoSided. 64 B. */
+typedef struct ctl_material {
+    uint32_t bsdf_type;        /* CTL_BSDF_*                                      */
+    uint32_t flags;            /* CTL_MAT_TWO_SIDED                               */
+    uint32_t node_light_index; /* Material::NodeLightIndex, 0xffffffff = none     */
+    uint32_t distr_type;       /* CTL_DISTR_* (roughconductor)                    */
+    float reflectance[3];      /* diffuse m_reflectance / specularReflectance     */
+    float alpha_u;
+    float eta[3];              /* conductor eta; eta[0] = dielectric eta(600 nm)  */
+    float alpha_v;
+    float k[3];                /* conductor k                                     */
+    float transmittance;       /* dielectric specular transmittance (grey)        */
+} ctl_material;
+
+/* DiffuseLight (SceneTypes/Light.h:96-142) over a ShapeSet (Engine/ShapeSet.h). 32 B */
+typedef struct ctl_light {
+    float radiance[3];
+    float sum_area;
+    uint32_t tri_offset; /* first ctl_light_tri                              */
+    uint32_t cdf_offset; /* first of count+1 floats in light_cdf_data        */
+    uint32_t count;
+    uint32_t node_idx;
+} ctl_light;
+
+/* PerspectiveSensor (SceneTypes/Sensor.h:189, Sensor.cu:76-144) */
+typedef struct ctl_camera {
+    float sample_to_camera[16]; /* row-major float4x4 */
+    float to_world[16];
+    float inv_resolution[2];
+    float resolution[2];
+} ctl_camera;
+
+/* Flat, read-only view of everything the path reads. Host pointers; copied
+ * by ctl_upload_scene.  == KernelDynamicScene's hot subset
+ * (Engine/KernelDynamicScene.h:28-57, Engine/DynamicScene.cpp:567-589). */
+typedef struct ctl_scene_view {
+    const ctl_bvh_node* bvh_nodes;       uint32_t n_bvh_nodes;       /* m_sBVHNodeData  */
+    const ctl_woop_tri* woop;            uint32_t n_woop;            /* m_sBVHIntData   */
+    const uint32_t*     tri_index;       uint32_t n_tri_index;       /* m_sBVHIndexData */
+    const ctl_tri_data* tri_data;        uint32_t n_tri_data;        /* m_sTriData      */
+    const ctl_mesh*     meshes;          uint32_t n_meshes;          /* m_sMeshData     */
+    const ctl_node*     nodes;           uint32_t n_nodes;           /* m_sNodeData     */
+    const float*        node_xf;         /* n_nodes * 16, m_pNodeTransforms           */
+    const float*        node_inv_xf;     /* n_nodes * 16, m_pInvNodeTransforms        */
+    const ctl_bvh_node* scene_bvh_nodes; uint32_t n_scene_bvh_nodes; /* m_sSceneBVH    */
+    int32_t             scene_start_node;                            /* m_sStartNode   */
+    const ctl_material* materials;       uint32_t n_materials;       /* m_sMatData     */
+    const ctl_light*    lights;          uint32_t n_lights_buf;      /* m_sLightBuf    */
+    const ctl_light_tri* light_tris;     uint32_t n_light_tris;      /* m_sAnimData    */
+    const float*        light_cdf_data;  uint32_t n_light_cdf_data;  /* m_sAnimData    */
+    uint32_t num_lights;                                             /* m_numLights    */
+    uint32_t light_indices[CTL_MAX_NUM_LIGHTS];                      /* m_pLightIndices*/
+    float    light_cdf[CTL_MAX_NUM_LIGHTS];                          /* m_pLightCDF    */
+    ctl_camera camera;                                               /* m_Camera       */
+    float box_min[3], box_max[3];                                    /* m_sBox         */
+    float ray_eps;                                                   /* m_rayTraceEps  */
+} ctl_scene_view;
+
+/* ---- host-side scene construction (replaces DynamicScene + SplitBVHBuilder
+ *      for synthetic scenes; Engine/DynamicScene.cpp, BVHBuilderHelper.cpp) --- */
+
+typedef struct ctl_scene ctl_scene;
+
+/* kind: 0 = Cornell-32 single node, 1 = Cornell-32 split in 7 nodes,
+ *       2 = C2 100K diffuse, 3 = C3 100K microfacet mix,
+ *       4 = C4 1M clustered + foliage (8 meshes/nodes), 5 = C5 (C4 geometry + C3 materials),
+ *       6 = small random "soup" test scene (n_hint triangles).                        */
+ctl_scene* ctl_scene_create(int kind, int width, int height, uint32_t seed, int n_hint);
+/* Build from caller geometry: one mesh, one node, identity transform.
+ * verts: nv*3 floats; indices: nt*3; mat_index: nt bytes; materials: nm records;
+ * emissive[nm*3]: radiance per material (all-zero = not a light). */
+ctl_scene* ctl_scene_create_from_mesh(const float* verts, uint32_t nv, const uint32_t* indices, uint32_t nt,
+                                      const uint8_t* mat_index, const ctl_material* materials, uint32_t nm,
+                                      const float* emissive, const float* cam_pos, const float* cam_target,
+                                      const float* cam_up, float fov_deg, int width, int height);
+int  ctl_scene_get_view(const ctl_scene*, ctl_scene_view* out);
+void ctl_scene_destroy(ctl_scene*);
+/* encoders exposed for known-answer tests */
+void ctl_encode_woop(const float v0[3], const float v1[3], const float v2[3], ctl_woop_tri* out); /* TriIntersectorData.cu:5-18 */
+void ctl_encode_tri_data(const float p[9], const float n[9], const float uv[6], uint32_t mat, ctl_tri_data* out); /* TriangleData.cu:8-65 */
+
+/* ---- sample tables (Kernel/Sampler.h:22-85, Base/CudaRandom.h:108-291) --- */
+/* Fill the 4096x30 1-D and 2-D tables of pass `pass` (0-based) of a fresh
+ * tracer: XORWOW curand_init(1234, 7539414, 0), 4096*(30+60) draws per pass.
+ * d1: n_seq*seq_len floats, d2: n_seq*seq_len*2 floats, element (seq,dim) at dim*n_seq+seq. */
+int ctl_generate_sample_tables(uint32_t pass, float* d1, float* d2);
+
+/* ---- tracer context (Kernel/Tracer.h:67-294, Integrators/PathTracer.h:7-24) --- */
+
+typedef struct ctl_ctx ctl_ctx;
+
+const char* ctl_last_error(void);
+/* == PathTracer ctor + TracerBase::Resize (Kernel/Tracer.h:102-109) */
+ctl_ctx* ctl_create(int device, int width, int height);
+void     ctl_destroy(ctl_ctx*);
+int      ctl_resize(ctl_ctx*, int width, int height);
+/* == m_sParameters: "MaxPathLength" (50), "RRStartDepth" (5), "Direct" (1),
+ *    "Regularization" (0, only 0 supported)  (Integrators/PathTracer.h:10-20);
+ *    extras: "SortMode" (0 none, 1 material), "StageTimers" (0/1), "CaptureBounce" (0 = off). */
+int ctl_set_param_i(ctl_ctx*, const char* key, int value);
+int ctl_get_param_i(ctl_ctx*, const char* key, int* value);
+/* == UpdateKernel scene half (Kernel/TraceHelper.cu:182-217): host view copied to HBM */
+int ctl_upload_scene(ctl_ctx*, const ctl_scene_view*);
+/* == UpdateKernel sampler half / GenerateNewRandomSequences; host tables, async H2D */
+int ctl_upload_samples(ctl_ctx*, const float* d1, const float* d2);
+/* == __internal__IntersectBuffers (Kernel/TraceHelper.cu:736-746). Device pointers,
+ *    n rays of ctl_traversal_ray -> n ctl_traversal_result. Asynchronous on `stream`
+ *    (cudaStream_t, may be NULL = context stream); unlike the reference it does not
+ *    synchronise -- call ctl_synchronize. */
+int ctl_intersect(ctl_ctx*, int n, const void* d_rays, void* d_results, int any_hit, void* stream);
+/* Host-buffer convenience: H2D, intersect, D2H, synchronous. */
+int ctl_intersect_host(ctl_ctx*, int n, const ctl_traversal_ray* rays, ctl_traversal_result* results, int any_hit);
+/* == traceRay (Kernel/TraceHelper.cu:174-180) batched: rays with tmin/tmax ignored
+ *    (t in (rayEps, FLT_MAX)), full-precision barycentrics. Host buffers, synchronous.
+ *    counts (may be NULL): [0]=inner nodes popped, [1]=triangle refs tested,
+ *    [2]=instance leaves entered, summed over rays (instrumented build). */
+int ctl_trace_rays_host(ctl_ctx*, int n, const ctl_traversal_ray* rays, ctl_trace_result* results, uint64_t counts[3]);
+/* == Tracer<true>::DoPass (Kernel/Tracer.h:209-248) restricted to the pixel window
+ *    [x0,x1) x [y0,y1) (full image: 0,0,w,h).  new_trace != 0 clears the accumulator
+ *    and restarts the sample-table stream at pass 0.  Generates this pass's sample
+ *    tables (unless tables were supplied by ctl_upload_samples since the last pass),
+ *    then runs the wavefront stages.  Asynchronous; ctl_synchronize to wait. */
+int ctl_render_pass(ctl_ctx*, int new_trace, int x0, int y0, int x1, int y1);
+/* Interleaved-tile variant for multi-GPU: renders tiles (tile_w x tile_h) whose
+ * index % n_parts == part. */
+int ctl_render_pass_tiled(ctl_ctx*, int new_trace, int tile_w, int tile_h, int part, int n_parts);
+int ctl_synchronize(ctl_ctx*);
+/* == Image accumulator: PixelData[w*h], reference layout. */
+int ctl_read_accum(ctl_ctx*, ctl_pixel_data* host_out);
+/* Device pointer of the accumulator (7*w*h floats) for in-place NCCL reduce. */
+void* ctl_accum_device_ptr(ctl_ctx*);
+/* Use caller-owned device memory (7*w*h floats) as the accumulator (e.g. a torch tensor). */
+int ctl_set_accum_device_ptr(ctl_ctx*, void* d_ptr);
+/* == getRaysInLastPass / getLastTimeSpentRenderingSec (Kernel/Tracer.h:133-148);
+ *    synchronises. rays = extension + shadow queries of the last pass. */
+int ctl_stats(ctl_ctx*, uint64_t* rays_last_pass, float* seconds_last_pass, uint64_t* rays_total, uint32_t* passes_done);
+/* Per-stage device time (ms) of the last pass: [0] generate [1] extension traversal
+ * [2] shade [3] shadow traversal [4] accumulate/compact/sort; and launches. */
+int ctl_stage_times(ctl_ctx*, float ms[5], uint32_t* n_launches);
+/* Instrumented traversal of the NEXT pass: collects visit counts (slower).
+ * counts[0..2] as in ctl_trace_rays_host, [3] = rays; for extension (0) / shadow (1). */
+int ctl_set_instrumented(ctl_ctx*, int on);
+int ctl_get_visit_counts(ctl_ctx*, uint64_t ext_counts[4], uint64_t shadow_counts[4]);
+/* ctl_set_param_i(ctx, "CaptureBounce", b) makes every following pass keep a copy of the extension-ray
+ * queue of bounce b (1-based; 0 = off). Fetch it (32-byte traversalRay records) after the pass; returns the
+ * number of rays copied or -1.  Used for the ray-level micro-benchmark. */
+int ctl_get_captured_rays(ctl_ctx*, ctl_traversal_ray* host_out, int capacity);
+/* Extension / shadow queue sizes per bounce of the last pass (n entries each). */
+int ctl_get_queue_sizes(ctl_ctx*, uint32_t* ext, uint32_t* shadow, int n);
+/* The context's cudaStream_t (so callers can order their own work after the passes). */
+void* ctl_stream(ctl_ctx*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTL_B200_H */

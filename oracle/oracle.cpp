@@ -1,0 +1,971 @@
+// oracle.cpp -- CPU restatement of CudaTracerLib's ray-traversal + path-tracing hot path.
+//
+// TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load this library; the product
+// (cudatracerlib_b200/) never links, imports or calls it.
+//
+// Parity status: the reference ships no tests / golden vectors, so this
+// restatement is pinned against (a) the known-answer values SURVEY Appendix C records from
+// running the reference's own host code (tests/test_oracle_kat.py) and (b) oracle/_ref,
+// a build of the reference's own sources (oracle/build_ref.sh), where that exists.
+//
+// Each function cites the reference file:line (relative to the CudaTracerLib tree) it follows.
+// Independent code: nothing here includes product sources except the public C header for
+// the POD layouts of the data surface it reads.
+//
+// Arithmetic: IEEE fp32, no implicit FMA contraction (-ffp-contract=off).  The reference's
+// GPU build lets nvcc contract a*b+c; the product writes the FMAs that matter explicitly
+// (slab test, Woop test) and this file restates exactly those with fmaf() so that traversal
+// parity is bit-exact.  Everything else is evaluated in the reference's host order.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cfloat>
+#include <climits>
+#include <vector>
+#include <thread>
+#include <atomic>
+#include <algorithm>
+// toolkit XORWOW jump matrices (third-party: CUDA 12.9 cuRAND headers, not vendored)
+#ifndef __device__
+#define __device__
+#define ORC_UNDEF_DEVICE
+#endif
+#include <curand_globals.h>
+#include <curand_precalc.h>
+#ifdef ORC_UNDEF_DEVICE
+#undef __device__
+#endif
+#include "../include/ctl_b200.h"
+
+namespace {
+
+const float PI_F = 3.14159265358979f;             // Math/MathFunc.h:12
+const float INV_PI_F = 1.0f / PI_F;               // :13
+const float DELTA_EPS = 1e-3f;                    // :26
+const unsigned E_DIFFUSE_REFL = 0x2, E_GLOSSY_REFL = 0x8, E_DELTA_REFL = 0x20, E_DELTA_TRANS = 0x40; // SceneTypes/Samples.h:32-71
+const unsigned E_SMOOTH = 0x2 | 0x4 | 0x8 | 0x10, E_DELTA = 0x1 | 0x20 | 0x40, E_ALL = E_SMOOTH | E_DELTA | 0x80 | 0x100; // :73-92
+
+struct V3 { float x, y, z; };
+inline V3 mk(float x, float y, float z) { V3 r = {x, y, z}; return r; }
+inline V3 add(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline V3 sub(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline V3 mul(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+inline V3 divs(V3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
+inline V3 neg(V3 a) { return mk(-a.x, -a.y, -a.z); }
+inline float dot(V3 a, V3 b) { float r = 0.0f; r += a.x * b.x; r += a.y * b.y; r += a.z * b.z; return r; } // Math/Vector.h:97
+inline V3 cross(V3 a, V3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); } // :329
+inline float rcpf(float a) { return a != 0.0f ? 1.0f / a : 0.0f; }                                             // MathFunc.h:399
+inline float length(V3 a) { return sqrtf(dot(a, a)); }
+inline V3 normalize(V3 a) { return mul(a, rcpf(length(a))); } // Vector.h:369-372
+
+struct Spec { float r, g, b; };
+inline Spec sp(float v) { Spec s = {v, v, v}; return s; }
+inline Spec sp3(const float* p) { Spec s = {p[0], p[1], p[2]}; return s; }
+inline Spec smul(Spec a, Spec b) { Spec s = {a.r * b.r, a.g * b.g, a.b * b.b}; return s; }
+inline Spec smulf(Spec a, float f) { Spec s = {a.r * f, a.g * f, a.b * f}; return s; }
+inline Spec sdivf(Spec a, float f) { Spec s = {a.r / f, a.g / f, a.b / f}; return s; }
+inline Spec sadd(Spec a, Spec b) { Spec s = {a.r + b.r, a.g + b.g, a.b + b.b}; return s; }
+inline Spec ssub(Spec a, Spec b) { Spec s = {a.r - b.r, a.g - b.g, a.b - b.b}; return s; }
+inline Spec sdiv(Spec a, Spec b) { Spec s = {a.r / b.r, a.g / b.g, a.b / b.b}; return s; }
+inline bool sis_zero(Spec a) { return a.r == 0.0f && a.g == 0.0f && a.b == 0.0f; }
+inline float smax(Spec a) { float m = a.r; if (a.g > m) m = a.g; if (a.b > m) m = a.b; return m; } // Spectrum.h:247
+inline float savg(Spec a) { float s = 0.0f; s += a.r; s += a.g; s += a.b; return s * (1.0f / 3); }  // :180-190
+inline Spec ssafe_sqrt(Spec a) { Spec s = {sqrtf(fmaxf(0.0f, a.r)), sqrtf(fmaxf(0.0f, a.g)), sqrtf(fmaxf(0.0f, a.b))}; return s; }
+
+// ---- row-major float4x4 (Math/float4x4.h) --------------------------------
+inline float dot4(const float* a, float b0, float b1, float b2, float b3) { float r = 0.0f; r += a[0] * b0; r += a[1] * b1; r += a[2] * b2; r += a[3] * b3; return r; }
+inline V3 xf_point(const float* m, V3 p) { // :398-402
+    float x = dot4(m, p.x, p.y, p.z, 1.0f), y = dot4(m + 4, p.x, p.y, p.z, 1.0f), z = dot4(m + 8, p.x, p.y, p.z, 1.0f), w = dot4(m + 12, p.x, p.y, p.z, 1.0f);
+    return mk(x / w, y / w, z / w);
+}
+inline V3 xf_dir(const float* m, V3 d) { // :404-408
+    return mk(dot4(m, d.x, d.y, d.z, 0.0f), dot4(m + 4, d.x, d.y, d.z, 0.0f), dot4(m + 8, d.x, d.y, d.z, 0.0f));
+}
+void mat_inverse(const float* q, float* out) { // :132-193, cofactor expansion in the reference's evaluation order
+#define Q(i, j) q[(i) * 4 + (j)]
+    float m00 = Q(0, 0), m01 = Q(0, 1), m02 = Q(0, 2), m03 = Q(0, 3), m10 = Q(1, 0), m11 = Q(1, 1), m12 = Q(1, 2), m13 = Q(1, 3);
+    float m20 = Q(2, 0), m21 = Q(2, 1), m22 = Q(2, 2), m23 = Q(2, 3), m30 = Q(3, 0), m31 = Q(3, 1), m32 = Q(3, 2), m33 = Q(3, 3);
+#undef Q
+    float v0 = m20 * m31 - m21 * m30, v1 = m20 * m32 - m22 * m30, v2 = m20 * m33 - m23 * m30, v3 = m21 * m32 - m22 * m31, v4 = m21 * m33 - m23 * m31, v5 = m22 * m33 - m23 * m32;
+    float t00 = +(v5 * m11 - v4 * m12 + v3 * m13), t10 = -(v5 * m10 - v2 * m12 + v1 * m13), t20 = +(v4 * m10 - v2 * m11 + v0 * m13), t30 = -(v3 * m10 - v1 * m11 + v0 * m12);
+    float id = 1 / (t00 * m00 + t10 * m01 + t20 * m02 + t30 * m03);
+    float d00 = t00 * id, d10 = t10 * id, d20 = t20 * id, d30 = t30 * id;
+    float d01 = -(v5 * m01 - v4 * m02 + v3 * m03) * id, d11 = +(v5 * m00 - v2 * m02 + v1 * m03) * id, d21 = -(v4 * m00 - v2 * m01 + v0 * m03) * id, d31 = +(v3 * m00 - v1 * m01 + v0 * m02) * id;
+    v0 = m10 * m31 - m11 * m30; v1 = m10 * m32 - m12 * m30; v2 = m10 * m33 - m13 * m30; v3 = m11 * m32 - m12 * m31; v4 = m11 * m33 - m13 * m31; v5 = m12 * m33 - m13 * m32;
+    float d02 = +(v5 * m01 - v4 * m02 + v3 * m03) * id, d12 = -(v5 * m00 - v2 * m02 + v1 * m03) * id, d22 = +(v4 * m00 - v2 * m01 + v0 * m03) * id, d32 = -(v3 * m00 - v1 * m01 + v0 * m02) * id;
+    v0 = m21 * m10 - m20 * m11; v1 = m22 * m10 - m20 * m12; v2 = m23 * m10 - m20 * m13; v3 = m22 * m11 - m21 * m12; v4 = m23 * m11 - m21 * m13; v5 = m23 * m12 - m22 * m13;
+    float d03 = -(v5 * m01 - v4 * m02 + v3 * m03) * id, d13 = +(v5 * m00 - v2 * m02 + v1 * m03) * id, d23 = -(v4 * m00 - v2 * m01 + v0 * m03) * id, d33 = +(v3 * m00 - v1 * m01 + v0 * m02) * id;
+    float r[16] = {d00, d01, d02, d03, d10, d11, d12, d13, d20, d21, d22, d23, d30, d31, d32, d33};
+    memcpy(out, r, 64);
+}
+
+// ---- half / normal codec (Math/half.h:20-82 IEEE form; Math/Compression.h:12-31) ---
+uint16_t f2h(float f) {
+    uint32_t ia; memcpy(&ia, &f, 4);
+    uint16_t ir = (uint16_t)((ia >> 16) & 0x8000);
+    uint32_t e = ia & 0x7f800000;
+    if (e == 0x7f800000) { if ((ia & 0x7fffffff) == 0x7f800000) ir |= 0x7c00; else ir = 0x7fff; return ir; }
+    if (e < 0x33000000) return ir;
+    int shift = (int)((ia >> 23) & 0xff) - 127;
+    if (shift > 15) return ir | 0x7c00;
+    ia = (ia & 0x007fffff) | 0x00800000;
+    if (shift < -14) { ir |= (uint16_t)(ia >> (-1 - shift)); ia <<= (32 - (-1 - shift)); }
+    else { ir |= (uint16_t)(ia >> 13); ia <<= 19; ir = (uint16_t)(ir + ((14 + shift) << 10)); }
+    if (ia > 0x80000000u || (ia == 0x80000000u && (ir & 1))) ir++;
+    return ir;
+}
+float h2f(uint16_t h) { // IEEE decode = device __half2float
+    int e = (h >> 10) & 31, m = h & 1023;
+    float v;
+    if (e == 0) v = ldexpf((float)m, -24);
+    else if (e == 31) v = m ? NAN : INFINITY;
+    else v = ldexpf((float)(m | 1024), e - 25);
+    return (h & 0x8000) ? -v : v;
+}
+uint16_t enc_normal(V3 v) {
+    float theta = (acosf(v.z) * (255.0f / PI_F));
+    float phi = (atan2f(v.y, v.x) * (255.0f / (2.0f * PI_F)));
+    phi = phi < 0 ? (phi + 255) : phi;
+    return (uint16_t)(((unsigned short)theta << 8) | (unsigned short)phi);
+}
+V3 dec_normal(uint16_t c) {
+    const float PI_4 = PI_F / 4.0f, PI_2 = PI_F / 2.0f;
+    unsigned char x = c >> 8, y = c & 0xff;
+    float theta = x == 63 ? PI_4 : (x == 127 ? PI_2 : (x == 191 ? 3 * PI_4 : float(x) * (1.0f / 255.0f) * PI_F));
+    float phi = y == 63 ? PI_2 : (y == 127 ? PI_F : (y == 191 ? 3 * PI_2 : float(y) * (1.0f / 255.0f) * PI_F * 2.0f));
+    float sp_ = sinf(phi), cp = cosf(phi), st = sinf(theta), ct = cosf(theta); // host sincos = sinf/cosf, MathFunc.h:70-74
+    return mk(st * cp, st * sp_, ct);
+}
+void coordinate_system(V3 a, V3& s, V3& t) { // Math/Frame.h:9-22
+    if (fabsf(a.x) > fabsf(a.y)) { float il = 1.0f / sqrtf(a.x * a.x + a.z * a.z); t = mk(a.z * il, 0.0f, -a.x * il); }
+    else { float il = 1.0f / sqrtf(a.y * a.y + a.z * a.z); t = mk(0.0f, a.z * il, -a.y * il); }
+    s = normalize(cross(t, a));
+}
+
+// ---- XORWOW (Base/CudaRandom.h:108-291, .cu:7-34; curand_kernel.h) ---------
+struct Xorwow {
+    uint32_t v[5], d;
+    uint32_t next() { // CudaRandom.h:112-123
+        uint32_t t = (v[0] ^ (v[0] >> 2));
+        v[0] = v[1]; v[1] = v[2]; v[2] = v[3]; v[3] = v[4];
+        v[4] = (v[4] ^ (v[4] << 4)) ^ (t ^ (t << 1));
+        d += 362437;
+        return v[4] + d;
+    }
+    float random_float() { // :124-127, .cu:7-16
+        float f = next() * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
+        return f * (1 - 1e-5f);
+    }
+};
+void matvec(const uint32_t* vec, const uint32_t* mat, uint32_t* res, int n) {
+    for (int i = 0; i < n; i++) res[i] = 0;
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < 32; j++)
+            if (vec[i] & (1u << j))
+                for (int k = 0; k < n; k++) res[k] ^= mat[n * (i * 32 + j) + k];
+}
+void matmat(uint32_t* A, const uint32_t* B, int n) {
+    uint32_t res[8];
+    for (int i = 0; i < n * 32; i++) { matvec(A + i * n, B, res, n); for (int j = 0; j < n; j++) A[i * n + j] = res[j]; }
+}
+// generic skip-ahead with the toolkit's precalculated matrices (CudaRandom.h:160-242)
+void skipahead(unsigned long long x, Xorwow& st, unsigned int (*precalc)[800], bool is_offset) {
+    const int n = 5;
+    std::vector<uint32_t> matrix(n * n * 32), matrixA(n * n * 32);
+    uint32_t vec[5], res[5];
+    unsigned long long p = x;
+    for (int i = 0; i < n; i++) vec[i] = st.v[i];
+    int mn = 0;
+    while (p && mn < PRECALC_NUM_MATRICES - 1) {
+        for (unsigned t = 0; t < (p & PRECALC_BLOCK_MASK); t++) { matvec(vec, precalc[mn], res, n); memcpy(vec, res, sizeof(res)); }
+        p >>= PRECALC_BLOCK_SIZE; mn++;
+    }
+    if (p) { memcpy(matrix.data(), precalc[PRECALC_NUM_MATRICES - 1], n * n * 32 * 4); matrixA = matrix; }
+    while (p) {
+        for (unsigned t = 0; t < (p & SKIPAHEAD_MASK); t++) { matvec(vec, matrixA.data(), res, n); memcpy(vec, res, sizeof(res)); }
+        p >>= SKIPAHEAD_BLOCKSIZE;
+        if (p) for (int i = 0; i < SKIPAHEAD_BLOCKSIZE; i++) { matmat(matrix.data(), matrixA.data(), n); matrixA = matrix; }
+    }
+    for (int i = 0; i < n; i++) st.v[i] = vec[i];
+    if (is_offset) st.d += 362437 * (unsigned int)x;
+}
+void xorwow_init(unsigned long long seed, unsigned long long subsequence, unsigned long long offset, Xorwow& st) { // :243-262
+    uint32_t s0 = ((uint32_t)seed) ^ 0xaad26b49u, s1 = (uint32_t)(seed >> 32) ^ 0xf7dcefddu;
+    uint32_t t0 = 1099087573u * s0, t1 = 2591861531u * s1;
+    st.d = 6615241 + t1 + t0;
+    st.v[0] = 123456789u + t0; st.v[1] = 362436069u ^ t0; st.v[2] = 521288629u + t1; st.v[3] = 88675123u ^ t1; st.v[4] = 5783321u + t0;
+    skipahead(subsequence, st, precalc_xorwow_matrix_host, false);
+    skipahead(offset, st, precalc_xorwow_offset_matrix_host, true);
+}
+
+const int N_SEQ = 4096, SEQ_LEN = 30; // Kernel/TraceHelper.cu:257
+
+// Kernel/Sampler.h:36-85: per pass, for every sequence: 30 1-D draws then 30 2-D draws.
+// Vec2f(rng.randomFloat(), rng.randomFloat()) evaluates its arguments right-to-left with g++
+// (unspecified order in C++; observed with g++ 13.3 and matches oracle/_ref): the FIRST draw is y.
+void fill_tables(Xorwow& rng, float* d1, float* d2) {
+    for (int s = 0; s < N_SEQ; s++) {
+        for (int i = 0; i < SEQ_LEN; i++) d1[i * N_SEQ + s] = rng.random_float();
+        for (int i = 0; i < SEQ_LEN; i++) {
+            float y = rng.random_float(), x = rng.random_float();
+            d2[(i * N_SEQ + s) * 2 + 0] = x; d2[(i * N_SEQ + s) * 2 + 1] = y;
+        }
+    }
+}
+
+// Kernel/Sampler_device.h:62-107
+struct Sampler {
+    const float *d1, *d2;
+    unsigned idx, i1, i2;
+    float f1() {
+        unsigned a = idx % N_SEQ, b = (idx / N_SEQ) % N_SEQ, e = i1 % SEQ_LEN;
+        float sum = 0.0f; sum += d1[e * N_SEQ + a]; sum += d1[e * N_SEQ + b];
+        i1++;
+        return sum - floorf(sum);
+    }
+    void f2(float& x, float& y) {
+        unsigned a = idx % N_SEQ, b = (idx / N_SEQ) % N_SEQ, e = i2 % SEQ_LEN;
+        float sx = 0.0f, sy = 0.0f;
+        sx += d2[(e * N_SEQ + a) * 2]; sy += d2[(e * N_SEQ + a) * 2 + 1];
+        sx += d2[(e * N_SEQ + b) * 2]; sy += d2[(e * N_SEQ + b) * 2 + 1];
+        i2++;
+        x = sx - floorf(sx); y = sy - floorf(sy);
+    }
+};
+
+// ---- traversal -------------------------------------------------------------
+struct Hit { float dist, u, v; uint32_t tri, node; };
+struct Counters { uint64_t inner, tris, inst; };
+
+inline float guard_inv(float d) { // BVHTraversal.h:16-19
+    const float ooeps = powf(2.0f, -80.0f);
+    return 1.0f / (fabsf(d) > ooeps ? d : copysignf(ooeps, d));
+}
+
+// Generic stack traversal, host semantics of TracerayTemplate (BVHTraversal.h:122-232):
+// both children tested, nearer first (swp = c1min < c0min), far pushed, a found leaf is processed
+// as soon as it is met (host branch: mask = leafAddr >= 0), box entry clamped at tmin_box.
+template <typename LEAF>
+inline bool traverse(const float* nodes4, int node_off4, int start, V3 o, V3 d, float tmin_box, float& rayT, Counters* cnt, LEAF leaf) {
+    const int SENT = CTL_SENTINEL;
+    if (start < 0) return leaf(~start);
+    bool found = false;
+    int stack[64]; int sp_ = 0; stack[0] = SENT;
+    float idx = guard_inv(d.x), idy = guard_inv(d.y), idz = guard_inv(d.z);
+    float oodx = o.x * idx, oody = o.y * idy, oodz = o.z * idz;
+    int leafAddr = 0, nodeAddr = start;
+    while (nodeAddr != SENT) {
+        while ((unsigned)nodeAddr < (unsigned)SENT) {
+            const float* n = nodes4 + (size_t)(node_off4 + nodeAddr) * 4;
+            if (cnt) cnt->inner++;
+            int c0, c1; memcpy(&c0, n + 12, 4); memcpy(&c1, n + 13, 4);
+            float c0lox = fmaf(n[0], idx, -oodx), c0hix = fmaf(n[1], idx, -oodx), c0loy = fmaf(n[2], idy, -oody), c0hiy = fmaf(n[3], idy, -oody);
+            float c0loz = fmaf(n[8], idz, -oodz), c0hiz = fmaf(n[9], idz, -oodz), c1loz = fmaf(n[10], idz, -oodz), c1hiz = fmaf(n[11], idz, -oodz);
+            float c1lox = fmaf(n[4], idx, -oodx), c1hix = fmaf(n[5], idx, -oodx), c1loy = fmaf(n[6], idy, -oody), c1hiy = fmaf(n[7], idy, -oody);
+            // spanBegin/EndKepler (MathFunc.h:443-444) == float min/max for t >= 0
+            float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tmin_box));
+            float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), rayT));
+            float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tmin_box));
+            float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), rayT));
+            bool swp = (c1min < c0min), t0 = (c0max >= c0min), t1 = (c1max >= c1min);
+            if (!t0 && !t1) { nodeAddr = stack[sp_]; sp_--; }
+            else {
+                nodeAddr = t0 ? c0 : c1;
+                if (t0 && t1) { if (swp) { int tmp = nodeAddr; nodeAddr = c1; c1 = tmp; } sp_++; stack[sp_] = c1; }
+            }
+            if (nodeAddr < 0 && leafAddr >= 0) { leafAddr = nodeAddr; nodeAddr = stack[sp_]; sp_--; }
+            if (leafAddr < 0) break;
+        }
+        while (leafAddr < 0) {
+            found |= leaf(~leafAddr);
+            leafAddr = nodeAddr;
+            if (nodeAddr < 0) { nodeAddr = stack[sp_]; sp_--; }
+        }
+    }
+    return found;
+}
+
+// Woop test with the explicit FMA pattern shared with the device kernel (TraceHelper.cu:118-134)
+inline bool woop_test(const float* w, V3 o, V3 d, float tlo, float thi, float& t, float& u, float& v) {
+    float Oz = fmaf(-o.z, w[2], fmaf(-o.y, w[1], fmaf(-o.x, w[0], w[3])));
+    float invDz = 1.0f / fmaf(d.z, w[2], fmaf(d.y, w[1], d.x * w[0]));
+    t = Oz * invDz;
+    if (t > tlo && t < thi) {
+        float Ox = fmaf(o.z, w[6], fmaf(o.y, w[5], fmaf(o.x, w[4], w[7])));
+        float Dx = fmaf(d.z, w[6], fmaf(d.y, w[5], d.x * w[4]));
+        u = fmaf(t, Dx, Ox);
+        if (u >= 0.0f) {
+            float Oy = fmaf(o.z, w[10], fmaf(o.y, w[9], fmaf(o.x, w[8], w[11])));
+            float Dy = fmaf(d.z, w[10], fmaf(d.y, w[9], d.x * w[8]));
+            v = fmaf(t, Dy, Oy);
+            if (v >= 0.0f && u + v <= 1.0f) return true;
+        }
+    }
+    return false;
+}
+
+// two-level closest hit: __traceRay_internal__<false> (TraceHelper.cu:88-172).
+// tri_lo: lower t bound for triangles (rayEps for traceRay, ray.tmin for intersectKernel),
+// box_lo: lower bound for boxes (0 for traceRay, ray.tmin for intersectKernel). any_hit: intersectKernel<true>.
+bool trace(const ctl_scene_view& S, V3 ori, V3 dir, float tri_lo, float box_lo, Hit& hit, Counters* cnt, bool any_hit) {
+    if (!S.n_nodes) return false;
+    bool stop = false;
+    return traverse((const float*)S.scene_bvh_nodes, 0, S.scene_start_node, ori, dir, box_lo, hit.dist, cnt, [&](int nodeIdx) {
+        if (stop) return false;
+        if (cnt) cnt->inst++;
+        const ctl_node& N = S.nodes[nodeIdx];
+        const ctl_mesh& mesh = S.meshes[N.mesh_index];
+        const float* inv = S.node_inv_xf + (size_t)nodeIdx * 16;
+        V3 d = xf_dir(inv, dir), o = xf_point(inv, ori);
+        return traverse((const float*)S.bvh_nodes, (int)mesh.bvh_node_offset, 0, o, d, box_lo, hit.dist, cnt, [&](int triIdx) {
+            bool found = false;
+            if (stop) return false;
+            for (int triAddr = triIdx;; triAddr++) {
+                const float* w = (const float*)S.woop + ((size_t)mesh.bvh_tri_offset + (size_t)triAddr * 3) * 4;
+                uint32_t index = S.tri_index[mesh.bvh_idx_offset + triAddr];
+                if (cnt) cnt->tris++;
+                float t, u, v;
+                if (woop_test(w, o, d, tri_lo, hit.dist, t, u, v)) {
+                    hit.node = (uint32_t)nodeIdx; hit.tri = (index >> 1) + mesh.tri_offset; hit.u = u; hit.v = v; hit.dist = t;
+                    found = true;
+                    if (any_hit) { stop = true; break; }
+                }
+                if (index & 1) break;
+            }
+            return found;
+        });
+    });
+}
+
+// ---- fillDG (TraceHelper.cu:274-307 -> TriangleData.cu:75-103) --------------
+struct Frame { V3 s, t, n; };
+struct DG { V3 P; Frame sys; V3 n; };
+inline V3 to_local(const Frame& f, V3 v) { return mk(dot(v, f.s), dot(v, f.t), dot(v, f.n)); }                  // Frame.h:38-40
+inline V3 to_world(const Frame& f, V3 v) { return add(add(mul(f.s, v.x), mul(f.t, v.y)), mul(f.n, v.z)); }      // :41-43
+
+void fill_dg(const ctl_scene_view& S, float bu, float bv, uint32_t tri, uint32_t node, DG& dg) {
+    const float* l2w = S.node_xf + (size_t)node * 16;
+    const uint32_t* w = S.tri_data[tri].w;
+    V3 na = dec_normal(w[0] & 0xffff), nb = dec_normal(w[0] >> 16), nc = dec_normal(w[1] & 0xffff);
+    float ww = 1.0f - bu - bv, u = bu, v = bv;
+    V3 n = normalize(add(add(mul(na, u), mul(nb, v)), mul(nc, ww)));
+    V3 dpdu = mk(h2f(w[2] & 0xffff), h2f(w[2] >> 16), h2f(w[3] & 0xffff));
+    V3 dpdv = mk(h2f(w[3] >> 16), h2f(w[4] & 0xffff), h2f(w[4] >> 16));
+    V3 s = sub(dpdu, mul(n, dot(n, dpdu)));
+    V3 t = cross(s, n);
+    s = xf_dir(l2w, s); t = xf_dir(l2w, t);
+    dg.sys.s = normalize(s); dg.sys.t = normalize(t); dg.sys.n = normalize(cross(t, s));
+    V3 wdpdu = xf_dir(l2w, dpdu), wdpdv = xf_dir(l2w, dpdv);
+    dg.n = normalize(cross(wdpdu, wdpdv));
+    if (dot(dg.n, dg.sys.n) < 0.0f) dg.n = neg(dg.n);
+}
+
+// ---- warps (Math/Warp.h:61-164) --------------------------------------------
+void concentric_disk(float sx, float sy, float& px, float& py) {
+    float r1 = 2.0f * sx - 1.0f, r2 = 2.0f * sy - 1.0f, phi, r;
+    if (r1 == 0 && r2 == 0) { r = phi = 0; }
+    else if (r1 * r1 > r2 * r2) { r = r1; phi = (PI_F / 4.0f) * (r2 / r1); }
+    else { r = r2; phi = (PI_F / 2.0f) - (r1 / r2) * (PI_F / 4.0f); }
+    float cp = cosf(phi), sp_ = sinf(phi);
+    px = r * cp; py = r * sp_;
+}
+V3 cosine_hemisphere(float sx, float sy) {
+    float px, py; concentric_disk(sx, sy, px, py);
+    float z = sqrtf(1.0f - px * px - py * py);
+    return mk(px, py, z);
+}
+
+// ---- Fresnel (Math/FresnelHelper.h:27-58, 119-147) ---------------------------
+float fresnel_dielectric_ext(float cosThetaI_, float& cosThetaT_, float eta) {
+    if (eta == 1) { cosThetaT_ = -cosThetaI_; return 0.0f; }
+    float scale = (cosThetaI_ > 0) ? 1.0f / eta : eta, cosThetaTSqr = 1.0f - (1.0f - cosThetaI_ * cosThetaI_) * (scale * scale);
+    if (cosThetaTSqr <= 0.0f) { cosThetaT_ = 0.0f; return 1.0f; }
+    float cosThetaI = fabsf(cosThetaI_), cosThetaT = sqrtf(fmaxf(0.0f, cosThetaTSqr));
+    float Rs = (cosThetaI - eta * cosThetaT) / (cosThetaI + eta * cosThetaT);
+    float Rp = (eta * cosThetaI - cosThetaT) / (eta * cosThetaI + cosThetaT);
+    cosThetaT_ = (cosThetaI_ > 0) ? -cosThetaT : cosThetaT;
+    return 0.5f * (Rs * Rs + Rp * Rp);
+}
+Spec fresnel_conductor_exact(float cosThetaI, Spec eta, Spec k) {
+    float c2 = cosThetaI * cosThetaI, s2 = 1 - c2, s4 = s2 * s2;
+    Spec temp1 = ssub(ssub(smul(eta, eta), smul(k, k)), sp(s2));
+    Spec a2pb2 = ssafe_sqrt(sadd(smul(temp1, temp1), smulf(smul(smul(smul(k, k), eta), eta), 4)));
+    Spec a = ssafe_sqrt(smulf(sadd(a2pb2, temp1), 0.5f));
+    Spec term1 = sadd(a2pb2, sp(c2)), term2 = smulf(a, (2 * cosThetaI));
+    Spec Rs2 = sdiv(ssub(term1, term2), sadd(term1, term2));
+    Spec term3 = sadd(smulf(a2pb2, c2), sp(s4)), term4 = smulf(term2, s2);
+    Spec Rp2 = sdiv(smul(Rs2, ssub(term3, term4)), sadd(term3, term4));
+    return smulf(sadd(Rp2, Rs2), 0.5f);
+}
+
+// ---- microfacet distribution (Engine/MicrofacetDistribution.h/.cu), Beckmann + GGX, visible normals
+float m_erfinv(float x) { // MathFunc.h:343-373
+    float w = -logf((1.0f - x) * (1.0f + x)), p;
+    if (w < 5.0f) {
+        w = w - 2.5f;
+        p = 2.81022636e-08f; p = 3.43273939e-07f + p * w; p = -3.5233877e-06f + p * w; p = -4.39150654e-06f + p * w; p = 0.00021858087f + p * w;
+        p = -0.00125372503f + p * w; p = -0.00417768164f + p * w; p = 0.246640727f + p * w; p = 1.50140941f + p * w;
+    } else {
+        w = sqrtf(w) - 3;
+        p = -0.000200214257f; p = 0.000100950558f + p * w; p = 0.00134934322f + p * w; p = -0.00367342844f + p * w; p = 0.00573950773f + p * w;
+        p = -0.0076224613f + p * w; p = 0.00943887047f + p * w; p = 1.00167406f + p * w; p = 2.83297682f + p * w;
+    }
+    return p * x;
+}
+float m_erf(float x) { // :375-393
+    float a1 = 0.254829592f, a2 = -0.284496736f, a3 = 1.421413741f, a4 = -1.453152027f, a5 = 1.061405429f, p = 0.3275911f;
+    float sign = copysignf(1.0f, x); x = fabsf(x);
+    float t = 1.0f / (1.0f + p * x);
+    float y = 1.0f - (((((a5 * t + a4) * t) + a3) * t + a2) * t + a1) * t * expf(-x * x);
+    return sign * y;
+}
+float m_hypot2(float a, float b) { // :326-341
+    float r;
+    if (fabsf(a) > fabsf(b)) { r = b / a; r = fabsf(a) * sqrtf(1.0f + r * r); }
+    else if (b != 0.0f) { r = a / b; r = fabsf(b) * sqrtf(1.0f + r * r); }
+    else r = 0.0f;
+    return r;
+}
+struct Distr {
+    int type; float au, av;
+    Distr(int t, float a, float b) : type(t), au(a > 1e-4f ? a : 1e-4f), av(b > 1e-4f ? b : 1e-4f) {} // .h:37-44
+    float eval(V3 m) const { // .cu:6-42
+        if (m.z <= 0) return 0.0f;
+        float c2 = m.z * m.z;
+        float be = ((m.x * m.x) / (au * au) + (m.y * m.y) / (av * av)) / c2;
+        float result;
+        if (type == CTL_DISTR_BECKMANN) result = expf(-be) / (PI_F * au * av * c2 * c2);
+        else { float root = (1 + be) * c2; result = 1.0f / (PI_F * au * av * root * root); }
+        if (result < 1e-20f) result = 0;
+        return result;
+    }
+    float project_roughness(V3 v) const { // .h:126-136
+        float invSinTheta2 = 1 / (1.0f - v.z * v.z);
+        if (au == av || invSinTheta2 <= 0) return au;
+        float cosPhi2 = v.x * v.x * invSinTheta2, sinPhi2 = v.y * v.y * invSinTheta2;
+        return sqrtf(cosPhi2 * au * au + sinPhi2 * av * av);
+    }
+    float smith_g1(V3 v, V3 m) const { // .cu:306-340
+        if (dot(v, m) * v.z <= 0) return 0.0f;
+        float temp = 1 - v.z * v.z;
+        float tanTheta = fabsf(temp <= 0.0f ? 0.0f : sqrtf(temp) / v.z); // Frame::tanTheta, Frame.h:90-95
+        if (tanTheta == 0.0f) return 1.0f;
+        float alpha = project_roughness(v);
+        if (type == CTL_DISTR_BECKMANN) {
+            float a = 1.0f / (alpha * tanTheta);
+            if (a >= 1.6f) return 1.0f;
+            float aSqr = a * a;
+            return (3.535f * a + 2.181f * aSqr) / (1.0f + 2.276f * a + 2.577f * aSqr);
+        }
+        float root = alpha * tanTheta;
+        return 2.0f / (1.0f + m_hypot2(1.0f, root));
+    }
+    float pdf_visible(V3 wi, V3 m) const { // .h:114-119
+        if (wi.z == 0) return 0.0f;
+        return smith_g1(wi, m) * fabsf(dot(wi, m)) * eval(m) / fabsf(wi.z);
+    }
+    void sample_visible11(float thetaI, float sx, float sy, float& slx, float& sly) const { // .cu:188-304
+        const float SQRT_PI_INV = 1 / sqrtf(PI_F);
+        if (type == CTL_DISTR_BECKMANN) {
+            if (thetaI < 1e-4f) {
+                float r = sqrtf(-logf(1.0f - sx));
+                float sinPhi = sinf(2 * PI_F * sy), cosPhi = cosf(2 * PI_F * sy);
+                slx = r * cosPhi; sly = r * sinPhi; return;
+            }
+            float tanThetaI = tanf(thetaI), cotThetaI = 1 / tanThetaI;
+            float a = -1, c = m_erf(cotThetaI);
+            float sample_x = sx > 1e-6f ? sx : 1e-6f;
+            float fit = 1 + thetaI * (-0.876f + thetaI * (0.4265f - 0.0594f * thetaI));
+            float b = c - (1 + c) * powf(1 - sample_x, fit);
+            float normalization = 1 / (1 + c + SQRT_PI_INV * tanThetaI * expf(-cotThetaI * cotThetaI));
+            int it = 0;
+            while (++it < 10) {
+                if (!(b >= a && b <= c)) b = 0.5f * (a + c);
+                float invErf = m_erfinv(b);
+                float value = normalization * (1 + b + SQRT_PI_INV * tanThetaI * expf(-invErf * invErf)) - sample_x;
+                float derivative = normalization * (1 - invErf * tanThetaI);
+                if (fabsf(value) < 1e-5f) break;
+                if (value > 0) c = b; else a = b;
+                b -= value / derivative;
+            }
+            slx = m_erfinv(b);
+            sly = m_erfinv(2.0f * (sy > 1e-6f ? sy : 1e-6f) - 1.0f);
+            return;
+        }
+        if (thetaI < 1e-4f) {
+            float r = sqrtf(fmaxf(0.0f, sx / (1 - sx)));
+            float sinPhi = sinf(2 * PI_F * sy), cosPhi = cosf(2 * PI_F * sy);
+            slx = r * cosPhi; sly = r * sinPhi; return;
+        }
+        float tanThetaI = tanf(thetaI), a = 1 / tanThetaI;
+        float G1 = 2.0f / (1.0f + sqrtf(fmaxf(0.0f, 1.0f + 1.0f / (a * a))));
+        float A = 2.0f * sx / G1 - 1.0f;
+        if (fabsf(A) == 1) A -= copysignf(1.0f, A) * 1e-7f;
+        float tmp = 1.0f / (A * A - 1.0f), B = tanThetaI;
+        float D = sqrtf(fmaxf(0.0f, B * B * tmp * tmp - (A * A - B * B) * tmp));
+        float s1 = B * tmp - D, s2 = B * tmp + D;
+        slx = (A < 0.0f || s2 > 1.0f / tanThetaI) ? s1 : s2;
+        float Sg;
+        if (sy > 0.5f) { Sg = 1.0f; sy = 2.0f * (sy - 0.5f); } else { Sg = -1.0f; sy = 2.0f * (0.5f - sy); }
+        float z = (sy * (sy * (sy * (-0.365728915865723f) + 0.790235037209296f) - 0.424965825137544f) + 0.000152998850436920f) /
+                  (sy * (sy * (sy * (sy * 0.169507819808272f - 0.397203533833404f) - 0.232500544458471f) + 1.0f) - 0.539825872510702f);
+        sly = Sg * z * sqrtf(1.0f + slx * slx);
+    }
+    V3 sample_visible(V3 _wi, float sx, float sy) const { // .cu:151-186
+        V3 wi = normalize(mk(au * _wi.x, av * _wi.y, _wi.z));
+        float theta = 0, phi = 0;
+        if (wi.z < 0.99999f) { theta = acosf(wi.z); phi = atan2f(wi.y, wi.x); }
+        float sinPhi = sinf(phi), cosPhi = cosf(phi);
+        float slx, sly; sample_visible11(theta, sx, sy, slx, sly);
+        float rx = cosPhi * slx - sinPhi * sly, ry = sinPhi * slx + cosPhi * sly;
+        rx *= au; ry *= av;
+        float nrm = 1.0f / sqrtf(rx * rx + ry * ry + (float)1.0);
+        return mk(-rx * nrm, -ry * nrm, nrm);
+    }
+};
+
+// ---- BSDFs (SceneTypes/BSDF_Simple.cu:7-75 diffuse, 174-277 dielectric, 662-763 roughconductor) ---
+struct BRec { DG dg; V3 wi, wo; float eta; unsigned typeMask, sampledType; };
+
+unsigned bsdf_combined_type(const ctl_material& m) {
+    return m.bsdf_type == CTL_BSDF_DIFFUSE ? E_DIFFUSE_REFL : (m.bsdf_type == CTL_BSDF_ROUGHCONDUCTOR ? E_GLOSSY_REFL : (E_DELTA_REFL | E_DELTA_TRANS));
+}
+float mat_alpha(float a) { return savg(sp(a)); } // m_alphaU.Evaluate(dg).avg(), BSDF_Simple.cu:669-672
+
+Spec bsdf_sample_inner(const ctl_material& m, BRec& b, float& pdf, float sx, float sy) {
+    if (m.bsdf_type == CTL_BSDF_DIFFUSE) {
+        if (!(b.typeMask & E_DIFFUSE_REFL) || b.wi.z <= 0) return sp(0.0f);
+        b.sampledType = E_DIFFUSE_REFL;
+        b.wo = cosine_hemisphere(sx, sy);
+        b.eta = 1.0f;
+        pdf = fabsf(INV_PI_F * b.wo.z) * 1;
+        return smulf(sp3(m.reflectance), 1);
+    }
+    if (m.bsdf_type == CTL_BSDF_ROUGHCONDUCTOR) {
+        if (b.wi.z < 0 || !(b.typeMask & E_GLOSSY_REFL)) return sp(0.0f);
+        Distr distr(m.distr_type, mat_alpha(m.alpha_u), mat_alpha(m.alpha_v));
+        V3 mm = distr.sample_visible(b.wi, sx, sy);
+        pdf = distr.pdf_visible(b.wi, mm);
+        if (pdf == 0) return sp(0.0f);
+        b.wo = normalize(sub(mul(mm, 2 * dot(b.wi, mm)), b.wi)); // FresnelHelper::reflect, FresnelHelper.h:144-147
+        b.eta = 1.0f; b.sampledType = E_GLOSSY_REFL;
+        if (b.wo.z <= 0) return sp(0.0f);
+        Spec F = smul(fresnel_conductor_exact(dot(b.wi, mm), sp3(m.eta), sp3(m.k)), sp3(m.reflectance));
+        float weight = distr.smith_g1(b.wo, mm);
+        pdf /= 4.0f * dot(b.wo, mm);
+        return smulf(F, weight);
+    }
+    // dielectric, no dispersion: eta_pdf = 1, f_o = 1 (SceneTypes/Dispersion.h:125-138)
+    bool sR = (b.typeMask & E_DELTA_REFL) != 0, sT = (b.typeMask & E_DELTA_TRANS) != 0;
+    float cosThetaT, eta = m.eta[0], invEta = 1.0f / eta;
+    float F = fresnel_dielectric_ext(b.wi.z, cosThetaT, eta);
+    auto refract = [&](V3 wi) { float scale = -(cosThetaT < 0 ? invEta : eta); return normalize(mk(scale * wi.x, scale * wi.y, cosThetaT)); }; // Frame.h:143-152
+    if (sT && sR) {
+        if (sx <= F) { b.sampledType = E_DELTA_REFL; b.wo = mk(-b.wi.x, -b.wi.y, b.wi.z); b.eta = 1.0f; pdf = F; return sp3(m.reflectance); }
+        b.sampledType = E_DELTA_TRANS; b.wo = refract(b.wi); b.eta = cosThetaT < 0 ? eta : invEta; pdf = (1 - F) * 1.0f;
+        float factor = cosThetaT < 0 ? invEta : eta;
+        return smulf(smul(sp(1.0f), sp(m.transmittance)), (factor * factor));
+    } else if (sR) { b.sampledType = E_DELTA_REFL; b.wo = mk(-b.wi.x, -b.wi.y, b.wi.z); b.eta = 1.0f; pdf = 1.0f; return sp3(m.reflectance); }
+    else if (sT) {
+        b.sampledType = E_DELTA_TRANS; b.wo = refract(b.wi); b.eta = cosThetaT < 0 ? eta : invEta; pdf = 1.0f;
+        float factor = cosThetaT < 0 ? invEta : eta;
+        return smulf(smul(sp(1.0f), sp(m.transmittance)), (factor * factor * (1 - F)));
+    }
+    return sp(0.0f);
+}
+Spec bsdf_f_inner(const ctl_material& m, const BRec& b) { // measure = ESolidAngle
+    if (m.bsdf_type == CTL_BSDF_DIFFUSE) {
+        if (!(b.typeMask & E_DIFFUSE_REFL)) return sp(0.0f);
+        bool validRefl = b.wi.z > 0 && b.wo.z > 0;
+        Spec s = smulf(sp3(m.reflectance), (INV_PI_F * fabsf(b.wo.z)));
+        return validRefl ? s : sp(0.0f);
+    }
+    if (m.bsdf_type == CTL_BSDF_ROUGHCONDUCTOR) {
+        if (b.wi.z < 0 || b.wo.z < 0 || !(b.typeMask & E_GLOSSY_REFL)) return sp(0.0f);
+        V3 H = normalize(add(b.wo, b.wi));
+        Distr distr(m.distr_type, mat_alpha(m.alpha_u), mat_alpha(m.alpha_v));
+        float D = distr.eval(H);
+        if (D == 0) return sp(0.0f);
+        Spec F = smul(fresnel_conductor_exact(dot(b.wi, H), sp3(m.eta), sp3(m.k)), sp3(m.reflectance));
+        float G = distr.smith_g1(b.wi, H) * distr.smith_g1(b.wo, H);
+        float value = D * G / (4.0f * b.wi.z);
+        return smulf(F, value);
+    }
+    return sp(0.0f); // dielectric: delta lobes have no solid-angle density (BSDF_Simple.cu:227-252)
+}
+float bsdf_pdf_inner(const ctl_material& m, const BRec& b) {
+    if (m.bsdf_type == CTL_BSDF_DIFFUSE) {
+        if (!(b.typeMask & E_DIFFUSE_REFL)) return 0.0f;
+        bool validRefl = b.wi.z > 0 && b.wo.z > 0;
+        return validRefl ? fabsf(INV_PI_F * b.wo.z) : 0.0f;
+    }
+    if (m.bsdf_type == CTL_BSDF_ROUGHCONDUCTOR) {
+        if (b.wi.z < 0 || b.wo.z < 0 || !(b.typeMask & E_GLOSSY_REFL)) return 0.0f;
+        V3 H = normalize(add(b.wo, b.wi));
+        Distr distr(m.distr_type, mat_alpha(m.alpha_u), mat_alpha(m.alpha_v));
+        return distr.eval(H) * distr.smith_g1(b.wi, H) / (4.0f * b.wi.z);
+    }
+    return 0.0f;
+}
+// BSDFALL two-sided wrapper (SceneTypes/BSDF.h:141-207)
+Spec bsdf_sample(const ctl_material& m, BRec& b, float& pdf, float sx, float sy) {
+    bool flip = b.wi.z < 0 && (m.flags & CTL_MAT_TWO_SIDED);
+    if (flip) b.wi.z *= -1.0f;
+    Spec r = bsdf_sample_inner(m, b, pdf, sx, sy);
+    if (flip) { b.wi.z *= -1.0f; b.wo.z *= -1.0f; }
+    return r;
+}
+Spec bsdf_f(const ctl_material& m, BRec& b) {
+    bool flip = b.wi.z < 0 && (m.flags & CTL_MAT_TWO_SIDED);
+    if (flip) b.wi.z *= -1.0f;
+    Spec r = bsdf_f_inner(m, b);
+    if (flip) { b.wi.z *= -1.0f; b.wo.z *= -1.0f; }
+    return r;
+}
+float bsdf_pdf(const ctl_material& m, BRec& b) {
+    bool flip = b.wi.z < 0 && (m.flags & CTL_MAT_TWO_SIDED);
+    if (flip) b.wi.z *= -1.0f;
+    float r = bsdf_pdf_inner(m, b);
+    if (flip) { b.wi.z *= -1.0f; b.wo.z *= -1.0f; }
+    return r;
+}
+
+// ---- area light (SceneTypes/Light.cu:67-155; Engine/ShapeSet.cu:51-69; Math/MonteCarlo.cu:7-14) ---
+struct DRec { V3 p, n; float pdf; V3 ref, refN, d; float dist; };
+
+const float* lower_bound_f(const float* first, const float* last, float val) { // Base/STL.h:40-57
+    unsigned count = (unsigned)(last - first);
+    for (; 0 < count;) { unsigned c2 = count / 2; const float* mid = first + c2; if (*mid < val) { first = ++mid; count -= c2 + 1; } else count = c2; }
+    return first;
+}
+const float* upper_bound_f(const float* first, const float* last, float val) { // :21-38
+    unsigned count = (unsigned)(last - first);
+    for (; 0 < count;) { unsigned c2 = count / 2; const float* mid = first + c2; if (!(val < *mid)) { first = ++mid; count -= c2 + 1; } else count = c2; }
+    return first;
+}
+Spec light_sample_direct(const ctl_scene_view& S, const ctl_light& L, DRec& dRec, float sx, float sy) {
+    const float* cdf = S.light_cdf_data + L.cdf_offset;
+    const float* entry = lower_bound_f(cdf, cdf + L.count + 1, sy);
+    int ii = (int)(entry - cdf) - 1; if (ii < 0) ii = 0; if (ii > (int)L.count - 1) ii = (int)L.count - 1;
+    unsigned index = (unsigned)ii;
+    float pdf = cdf[index + 1] - cdf[index];
+    sy = (sy - cdf[index]) / pdf;
+    const ctl_light_tri& sn = S.light_tris[L.tri_offset + index];
+    float a = sqrtf(1.0f - sx); float b0 = 1 - a, b1 = a * sy; // squareToUniformTriangle, Warp.h:160-164
+    V3 p0 = mk(sn.p[0][0], sn.p[0][1], sn.p[0][2]), p1 = mk(sn.p[1][0], sn.p[1][1], sn.p[1][2]), p2 = mk(sn.p[2][0], sn.p[2][1], sn.p[2][2]);
+    dRec.p = add(add(mul(p0, b0), mul(p1, b1)), mul(p2, (1.f - b0 - b1)));
+    dRec.n = mk(sn.n[0], sn.n[1], sn.n[2]);
+    dRec.pdf = 1.0f / L.sum_area;
+    V3 dir = sub(dRec.p, dRec.ref);
+    float distSquared = dot(dir, dir);
+    dRec.dist = sqrtf(distSquared);
+    dRec.d = divs(dir, dRec.dist);
+    float dp = fabsf(dot(dRec.d, dRec.n));
+    dRec.pdf *= dp != 0 ? (distSquared / dp) : 0.0f;
+    if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0 && dRec.pdf != 0) return sdivf(sp3(L.radiance), dRec.pdf);
+    dRec.pdf = 0.0f;
+    return sp(0.0f);
+}
+float light_pdf_direct(const ctl_light& L, const DRec& dRec) { // Light.cu:137-155, measure ESolidAngle
+    if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0) {
+        float pdfPos = 1.0f / L.sum_area;
+        return pdfPos * (dRec.dist * dRec.dist) / fabsf(dot(dRec.d, dRec.n));
+    }
+    return 0.0f;
+}
+float pdf_emitter(const ctl_scene_view& S, unsigned light_buf_idx) { // KernelDynamicScene.cu:42-46
+    return S.light_cdf[light_buf_idx] - (light_buf_idx == 0 ? 0.0f : S.light_cdf[light_buf_idx - 1]);
+}
+inline float power_heuristic(float fPdf, float gPdf) { float f = 1 * fPdf, g = 1 * gPdf; return (f * f) / (f * f + g * g); } // MonteCarlo.h:29-33
+
+// ---- camera (SceneTypes/Sensor.cu:130-144) -----------------------------------
+void camera_ray(const ctl_camera& C, float px, float py, V3& o, V3& d) {
+    V3 nearP = xf_point(C.sample_to_camera, mk(px * C.inv_resolution[0], py * C.inv_resolution[1], 0.0f));
+    V3 dn = normalize(nearP);
+    o = mk(C.to_world[3], C.to_world[7], C.to_world[11]); // Translation()
+    d = xf_dir(C.to_world, dn);
+}
+
+struct PTParams { int max_path_length, rr_start, direct; };
+
+inline uint32_t mat_index_of(const ctl_scene_view& S, const Hit& h) { // TraceResult.cu:81-84
+    return ((S.tri_data[h.tri].w[1] >> 16) & 0xff) + S.nodes[h.node].material_offset;
+}
+
+// PathTrace<DIRECT> (Integrators/PathTracer.cu:10-113), volumes absent, no environment map.
+// Deviation (documented in DESIGN.md): a path whose throughput becomes exactly zero stops; the
+// reference keeps tracing it with zero weight until Russian roulette ends it (no image effect).
+Spec path_trace(const ctl_scene_view& S, V3 ro, V3 rd, Sampler& rnd, const PTParams& P, uint64_t& rays, Counters* cnt) {
+    Spec cl = sp(0.0f), cf = sp(1.0f);
+    int depth = 0; bool specularBounce = false; float brdf_pdf = 0; V3 last_nor = mk(0, 0, 0);
+    BRec bRec; bRec.wo = mk(0, 0, 1);
+    while (depth++ < P.max_path_length) {
+        Hit r2; r2.dist = FLT_MAX; r2.tri = UINT_MAX; r2.node = UINT_MAX; r2.u = r2.v = 0;
+        rays++;
+        trace(S, ro, rd, S.ray_eps, 0.0f, r2, cnt, false);
+        if (r2.tri == UINT_MAX) break;
+        // getBsdfSample (Kernel/TraceResult.cu:16-43)
+        const ctl_material& mat = S.materials[mat_index_of(S, r2)];
+        bRec.eta = 1.0f; bRec.sampledType = 0; bRec.typeMask = E_ALL;
+        bRec.dg.P = add(ro, mul(rd, r2.dist));
+        fill_dg(S, r2.u, r2.v, r2.tri, r2.node, bRec.dg);
+        bRec.wi = to_local(bRec.dg.sys, neg(rd));
+        if ((mat.flags & CTL_MAT_TWO_SIDED) && bRec.wi.z < 0) { bRec.dg.n = neg(bRec.dg.n); bRec.dg.sys.n = neg(bRec.dg.sys.n); bRec.wi.z *= -1.0f; }
+        // emitter hit (PathTracer.cu:64-77; TraceResult.cu:45-60)
+        if (mat.node_light_index != UINT_MAX) {
+            unsigned li = S.nodes[r2.node].lights[mat.node_light_index];
+            const ctl_light& L = S.lights[li];
+            float misWeight = 1.0f;
+            if (!(!P.direct || depth == 1 || specularBounce)) {
+                DRec dRec; dRec.ref = ro; dRec.refN = last_nor; dRec.p = bRec.dg.P; dRec.n = bRec.dg.n; dRec.d = rd; dRec.dist = r2.dist;
+                float direct_pdf = light_pdf_direct(L, dRec) * pdf_emitter(S, li);
+                misWeight = power_heuristic(brdf_pdf, direct_pdf);
+            }
+            Spec Le = dot(bRec.dg.sys.n, neg(rd)) <= 0 ? sp(0.0f) : sp3(L.radiance); // DiffuseLight::eval, Light.cu:67-70
+            cl = sadd(cl, smul(smulf(cf, misWeight), Le));
+        }
+        float sx, sy; rnd.f2(sx, sy);
+        Spec f = bsdf_sample(mat, bRec, brdf_pdf, sx, sy);
+        last_nor = bRec.dg.sys.n;
+        if (P.direct && (bsdf_combined_type(mat) & E_SMOOTH) && S.num_lights) { // UniformSampleOneLight, TraceAlgorithms.cu:92-101
+            float lx, ly; rnd.f2(lx, ly);
+            unsigned idx = (unsigned)(upper_bound_f(S.light_cdf, S.light_cdf + S.num_lights, lx) - S.light_cdf); // sampleEmitter, KernelDynamicScene.cu:25-40
+            if (idx >= S.num_lights) idx = S.num_lights - 1;
+            float fU = S.light_cdf[idx], fL = idx > 0 ? S.light_cdf[idx - 1] : 0.0f;
+            float emPdf = fU - fL;
+            const ctl_light& L = S.lights[S.light_indices[idx]];
+            // EstimateDirect (TraceAlgorithms.cu:44-73)
+            DRec dRec; dRec.ref = bRec.dg.P; dRec.refN = bRec.dg.sys.n; dRec.p = bRec.dg.P; dRec.n = bRec.dg.sys.n; dRec.pdf = 0;
+            float ex, ey; rnd.f2(ex, ey);
+            Spec value = light_sample_direct(S, L, dRec, ex, ey);
+            Spec retVal = sp(0.0f);
+            if (!sis_zero(value)) {
+                BRec b2 = bRec;
+                b2.wo = to_local(b2.dg.sys, dRec.d);
+                b2.typeMask = E_ALL & ~E_DELTA;
+                Spec bsdfVal = bsdf_f(mat, b2);
+                if (!sis_zero(bsdfVal)) {
+                    Hit sh; sh.dist = FLT_MAX; sh.tri = UINT_MAX; sh.node = UINT_MAX;
+                    rays++;
+                    trace(S, dRec.ref, dRec.d, S.ray_eps, 0.0f, sh, cnt, false); // Occluded = closest hit, KernelDynamicScene.cu:70-80
+                    bool end = sh.dist < dRec.dist - S.ray_eps;
+                    bool occluded = sh.dist > 0 + S.ray_eps && end;
+                    if (!occluded) {
+                        float bsdfPdf = bsdf_pdf(mat, b2);
+                        float directPdf = dRec.pdf * emPdf;
+                        float weight = power_heuristic(directPdf, bsdfPdf);
+                        retVal = smulf(smul(value, bsdfVal), weight);
+                    }
+                }
+            }
+            cl = sadd(cl, smul(cf, sdivf(retVal, emPdf)));
+        }
+        specularBounce = (bRec.sampledType & E_DELTA) != 0;
+        cf = smul(cf, f);
+        rd = to_world(bRec.dg.sys, bRec.wo); ro = bRec.dg.P;
+        if (sis_zero(cf)) break; // see deviation note above
+        if (depth > P.rr_start && !specularBounce) {
+            if (rnd.f1() >= smax(cf)) break;
+            cf = sdivf(cf, smax(cf));
+        }
+    }
+    return cl;
+}
+
+struct PixSample { float sx, sy; Spec L; };
+
+void add_sample(ctl_pixel_data* img, int w, int h, float sx, float sy, Spec L) { // Engine/Image.cu:22-44
+    L.r = fmaxf(0.0f, L.r); L.g = fmaxf(0.0f, L.g); L.b = fmaxf(0.0f, L.b);
+    int x = (int)floorf(sx), y = (int)floorf(sy);
+    if (x < 0 || x >= w || y < 0 || y >= h || std::isnan(L.r) || std::isnan(L.g) || std::isnan(L.b) || !std::isfinite(L.r) || !std::isfinite(L.g) || !std::isfinite(L.b)) return;
+    ctl_pixel_data& p = img[(size_t)y * w + x];
+    p.rgb[0] += L.r; p.rgb[1] += L.g; p.rgb[2] += L.b; p.weight_sum += 1.0f;
+}
+
+} // namespace
+
+// =========================================================================== C interface
+extern "C" {
+
+void orc_xorwow_init(unsigned long long seed, unsigned long long subsequence, unsigned long long offset, uint32_t state[6]) {
+    Xorwow st; xorwow_init(seed, subsequence, offset, st);
+    for (int i = 0; i < 5; i++) state[i] = st.v[i];
+    state[5] = st.d;
+}
+void orc_xorwow_floats(uint32_t state[6], int n, float* out) {
+    Xorwow st; for (int i = 0; i < 5; i++) st.v[i] = state[i]; st.d = state[5];
+    for (int i = 0; i < n; i++) out[i] = st.random_float();
+    for (int i = 0; i < 5; i++) state[i] = st.v[i]; state[5] = st.d;
+}
+// sample tables of pass `pass` of a fresh tracer (IndependantSamplingSequenceGenerator, rng(7539414))
+void orc_sample_tables(uint32_t pass, float* d1, float* d2) {
+    Xorwow st; xorwow_init(1234, 7539414, 0, st);
+    for (uint32_t p = 0; p <= pass; p++) fill_tables(st, d1, d2);
+}
+void orc_sampler_draws(const float* d1, const float* d2, uint32_t idx, int n1, float* out1, int n2, float* out2) {
+    Sampler s = {d1, d2, idx, 0, 0};
+    for (int i = 0; i < n1; i++) out1[i] = s.f1();
+    for (int i = 0; i < n2; i++) s.f2(out2[2 * i], out2[2 * i + 1]);
+}
+void orc_encode_woop(const float* v0, const float* v1, const float* v2, float* out12) { // TriIntersectorData.cu:5-18
+    V3 a = mk(v0[0], v0[1], v0[2]), b = mk(v1[0], v1[1], v1[2]), c = mk(v2[0], v2[1], v2[2]);
+    V3 e0 = sub(a, c), e1 = sub(b, c), n = cross(e0, e1);
+    float m[16] = {e0.x, e1.x, n.x, c.x, e0.y, e1.y, n.y, c.y, e0.z, e1.z, n.z, c.z, 0, 0, 0, 1}, i[16];
+    mat_inverse(m, i);
+    float o[12] = {i[8], i[9], i[10], -i[11], i[0], i[1], i[2], i[3], i[4], i[5], i[6], i[7]};
+    memcpy(out12, o, 48);
+}
+int orc_woop_intersect(const float* woop12, const float* o, const float* d, float tmax, float* tuv) { // TriIntersectorData.cu:34-61 (eps 1e-4)
+    float t, u, v;
+    bool h = woop_test(woop12, mk(o[0], o[1], o[2]), mk(d[0], d[1], d[2]), 0.0001f, tmax, t, u, v);
+    if (h) { tuv[0] = t; tuv[1] = u; tuv[2] = v; }
+    return h;
+}
+uint16_t orc_float_to_half(float f) { return f2h(f); }
+float orc_half_to_float(uint16_t h) { return h2f(h); }
+uint16_t orc_encode_normal(const float* n) { return enc_normal(mk(n[0], n[1], n[2])); }
+void orc_decode_normal(uint16_t c, float* out) { V3 n = dec_normal(c); out[0] = n.x; out[1] = n.y; out[2] = n.z; }
+void orc_encode_tri_data(const float* p9, const float* n9, const float* uv6, uint32_t mat, uint32_t* out8) { // TriangleData.cu:8-65
+    uint16_t h[6]; for (int i = 0; i < 6; i++) h[i] = f2h(uv6[i]);
+    out8[5] = h[0] | ((uint32_t)h[1] << 16); out8[6] = h[2] | ((uint32_t)h[3] << 16); out8[7] = h[4] | ((uint32_t)h[5] << 16);
+    V3 v0 = mk(p9[0], p9[1], p9[2]), v1 = mk(p9[3], p9[4], p9[5]), v2 = mk(p9[6], p9[7], p9[8]);
+    float t0x = h2f(h[0]), t0y = h2f(h[1]), t1x = h2f(h[2]), t1y = h2f(h[3]), t2x = h2f(h[4]), t2y = h2f(h[5]);
+    V3 dP1 = sub(v1, v0), dP2 = sub(v2, v0);
+    float dU1x = t1x - t0x, dU1y = t1y - t0y, dU2x = t2x - t0x, dU2y = t2y - t0y;
+    float det = dU1x * dU2y - dU1y * dU2x;
+    V3 dpdu, dpdv;
+    if (det == 0) { V3 n = normalize(cross(dP1, dP2)); coordinate_system(n, dpdu, dpdv); }
+    else { float id = 1.0f / det; dpdu = mul(sub(mul(dP1, dU2y), mul(dP2, dU1y)), id); dpdv = mul(add(mul(dP1, -dU2x), mul(dP2, dU1x)), id); }
+    out8[0] = enc_normal(mk(n9[0], n9[1], n9[2])) | ((uint32_t)enc_normal(mk(n9[3], n9[4], n9[5])) << 16);
+    out8[1] = enc_normal(mk(n9[6], n9[7], n9[8])) | ((mat & 0xff) << 16);
+    out8[2] = f2h(dpdu.x) | ((uint32_t)f2h(dpdu.y) << 16);
+    out8[3] = f2h(dpdu.z) | ((uint32_t)f2h(dpdv.x) << 16);
+    out8[4] = f2h(dpdv.y) | ((uint32_t)f2h(dpdv.z) << 16);
+}
+void orc_warp(int which, float sx, float sy, float* out3) {
+    if (which == 0) { V3 v = cosine_hemisphere(sx, sy); out3[0] = v.x; out3[1] = v.y; out3[2] = v.z; }
+    else { float a = sqrtf(1.0f - sx); out3[0] = 1 - a; out3[1] = a * sy; out3[2] = 0; }
+}
+float orc_fresnel_dielectric_ext(float cosi, float eta, float* cost) { return fresnel_dielectric_ext(cosi, *cost, eta); }
+void orc_fresnel_conductor_exact(float cosi, const float* eta, const float* k, float* out) { Spec s = fresnel_conductor_exact(cosi, sp3(eta), sp3(k)); out[0] = s.r; out[1] = s.g; out[2] = s.b; }
+// microfacet probe: m = sample(wi, s), pdf, D(m), G1(wi, m)
+void orc_microfacet_sample(int type, float alpha, const float* wi, float sx, float sy, float* out6) {
+    Distr d(type, alpha, alpha); V3 w = mk(wi[0], wi[1], wi[2]);
+    V3 m = d.sample_visible(w, sx, sy);
+    out6[0] = m.x; out6[1] = m.y; out6[2] = m.z; out6[3] = d.pdf_visible(w, m); out6[4] = d.eval(m); out6[5] = d.smith_g1(w, m);
+}
+// BSDF probe with an identity shading frame: out = weight[3], pdf, wo[3], sampledType, eta ; f[3], pdf(wo)
+void orc_bsdf_probe(const ctl_material* m, const float* wi, float sx, float sy, float* out9, float* f3, float* pdf1) {
+    BRec b; memset(&b, 0, sizeof(b)); b.wi = mk(wi[0], wi[1], wi[2]); b.wo = mk(0, 0, 1); b.typeMask = E_ALL; b.eta = 1;
+    float pdf = 0; Spec w = bsdf_sample(*m, b, pdf, sx, sy);
+    out9[0] = w.r; out9[1] = w.g; out9[2] = w.b; out9[3] = pdf; out9[4] = b.wo.x; out9[5] = b.wo.y; out9[6] = b.wo.z; out9[7] = (float)b.sampledType; out9[8] = b.eta;
+    BRec b2 = b; b2.typeMask = E_ALL & ~E_DELTA;
+    Spec f = bsdf_f(*m, b2); f3[0] = f.r; f3[1] = f.g; f3[2] = f.b; *pdf1 = bsdf_pdf(*m, b2);
+}
+void orc_bsdf_eval(const ctl_material* m, const float* wi, const float* wo, float* f3, float* pdf1) {
+    BRec b; memset(&b, 0, sizeof(b)); b.wi = mk(wi[0], wi[1], wi[2]); b.wo = mk(wo[0], wo[1], wo[2]); b.typeMask = E_ALL & ~E_DELTA; b.eta = 1;
+    Spec f = bsdf_f(*m, b); f3[0] = f.r; f3[1] = f.g; f3[2] = f.b; *pdf1 = bsdf_pdf(*m, b);
+}
+// DiffuseLight::sampleDirect probe: out = value[3], pdf, p[3], d[3], dist
+void orc_light_sample_direct(const ctl_scene_view* S, uint32_t light, const float* ref, const float* refN, float sx, float sy, float* out11) {
+    DRec d; d.ref = mk(ref[0], ref[1], ref[2]); d.refN = mk(refN[0], refN[1], refN[2]); d.pdf = 0;
+    Spec v = light_sample_direct(*S, S->lights[light], d, sx, sy);
+    float o[11] = {v.r, v.g, v.b, d.pdf, d.p.x, d.p.y, d.p.z, d.d.x, d.d.y, d.d.z, d.dist};
+    memcpy(out11, o, sizeof(o));
+}
+void orc_fill_dg(const ctl_scene_view* S, float u, float v, uint32_t tri, uint32_t node, float* out12) { // sys.s, sys.t, sys.n, n
+    DG dg; fill_dg(*S, u, v, tri, node, dg);
+    float o[12] = {dg.sys.s.x, dg.sys.s.y, dg.sys.s.z, dg.sys.t.x, dg.sys.t.y, dg.sys.t.z, dg.sys.n.x, dg.sys.n.y, dg.sys.n.z, dg.n.x, dg.n.y, dg.n.z};
+    memcpy(out12, o, sizeof(o));
+}
+void orc_camera_ray(const ctl_scene_view* S, float px, float py, float* o3, float* d3) {
+    V3 o, d; camera_ray(S->camera, px, py, o, d); o3[0] = o.x; o3[1] = o.y; o3[2] = o.z; d3[0] = d.x; d3[1] = d.y; d3[2] = d.z;
+}
+
+// traceRay batched (Kernel/TraceHelper.cu:174-180): ray tmin/tmax ignored; counts may be NULL
+void orc_trace_rays(const ctl_scene_view* S, int n, const ctl_traversal_ray* rays, ctl_trace_result* res, uint64_t* counts) {
+    Counters c = {0, 0, 0};
+    for (int i = 0; i < n; i++) {
+        Hit h; h.dist = FLT_MAX; h.tri = UINT_MAX; h.node = UINT_MAX; h.u = h.v = 0;
+        trace(*S, mk(rays[i].o[0], rays[i].o[1], rays[i].o[2]), mk(rays[i].d[0], rays[i].d[1], rays[i].d[2]), S->ray_eps, 0.0f, h, counts ? &c : 0, false);
+        res[i].dist = h.dist; res[i].u = h.u; res[i].v = h.v; res[i].tri_idx = h.tri; res[i].node_idx = h.node;
+    }
+    if (counts) { counts[0] = c.inner; counts[1] = c.tris; counts[2] = c.inst; }
+}
+// intersectKernel<ANY_HIT> semantics (Kernel/TraceHelper.cu:326-734): tmin/tmax from the ray, 16-byte packed result
+void orc_intersect(const ctl_scene_view* S, int n, const ctl_traversal_ray* rays, ctl_traversal_result* res, int any_hit) {
+    for (int i = 0; i < n; i++) {
+        Hit h; h.dist = rays[i].tmax; h.tri = UINT_MAX; h.node = UINT_MAX; h.u = h.v = 0;
+        trace(*S, mk(rays[i].o[0], rays[i].o[1], rays[i].o[2]), mk(rays[i].d[0], rays[i].d[1], rays[i].d[2]), rays[i].tmin, rays[i].tmin, h, 0, any_hit != 0);
+        res[i].dist = h.dist; res[i].node_idx = -1; res[i].tri_idx = -1; res[i].bary = 0;
+        if (h.tri != UINT_MAX) {
+            res[i].node_idx = (int)h.node; res[i].tri_idx = (int)h.tri;
+            uint16_t xd = (uint16_t)(h.u * 65535), yd = (uint16_t)(h.v * 65535); // :726-727
+            res[i].bary = ((uint32_t)yd << 16) | (uint32_t)xd;
+        }
+    }
+}
+
+// Render passes [pass_first, pass_first + n_passes) of a fresh tracer over the pixel window into `img`
+// (accumulated, not cleared): the loop of pathKernel2's body (PathTracer.cu:184-193) over pixels.
+// Rows are distributed over n_threads; samples are splatted serially in pixel order so the result is
+// independent of the thread count. rays_out: traceRay calls (extension + shadow).
+void orc_render(const ctl_scene_view* S, int w, int h, int x0, int y0, int x1, int y1, int pass_first, int n_passes,
+                int max_path_length, int rr_start, int direct, ctl_pixel_data* img, uint64_t* rays_out, int n_threads, uint64_t* counts) {
+    std::vector<float> d1((size_t)N_SEQ * SEQ_LEN), d2((size_t)N_SEQ * SEQ_LEN * 2);
+    Xorwow st; xorwow_init(1234, 7539414, 0, st);
+    for (int p = 0; p < pass_first; p++) fill_tables(st, d1.data(), d2.data());
+    PTParams P = {max_path_length, rr_start, direct};
+    uint64_t total_rays = 0; Counters total_cnt = {0, 0, 0};
+    if (n_threads < 1) n_threads = 1;
+    int bw = x1 - x0, bh = y1 - y0;
+    std::vector<PixSample> samples((size_t)bw * bh);
+    for (int p = 0; p < n_passes; p++) {
+        fill_tables(st, d1.data(), d2.data());
+        std::atomic<int> next_row(0);
+        std::vector<uint64_t> trays(n_threads, 0); std::vector<Counters> tcnt(n_threads, Counters{0, 0, 0});
+        auto work = [&](int tid) {
+            for (;;) {
+                int ry = next_row.fetch_add(1); if (ry >= bh) break;
+                int y = y0 + ry;
+                for (int x = x0; x < x1; x++) {
+                    Sampler rng = {d1.data(), d2.data(), (unsigned)(y * w + x), 0, 0};
+                    float jx, jy; rng.f2(jx, jy);
+                    float pX = (float)x + jx, pY = (float)y + jy;
+                    float ax, ay; rng.f2(ax, ay); // aperture sample, unused by the pinhole
+                    V3 o, d; camera_ray(S->camera, pX, pY, o, d);
+                    Spec col = path_trace(*S, o, d, rng, P, trays[tid], counts ? &tcnt[tid] : 0);
+                    PixSample ps = {pX, pY, col};
+                    samples[(size_t)ry * bw + (x - x0)] = ps;
+                }
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < n_threads; t++) th.emplace_back(work, t);
+        work(0);
+        for (auto& t : th) t.join();
+        for (auto& s : samples) add_sample(img, w, h, s.sx, s.sy, s.L);
+        for (int t = 0; t < n_threads; t++) { total_rays += trays[t]; total_cnt.inner += tcnt[t].inner; total_cnt.tris += tcnt[t].tris; total_cnt.inst += tcnt[t].inst; }
+    }
+    if (rays_out) *rays_out = total_rays;
+    if (counts) { counts[0] = total_cnt.inner; counts[1] = total_cnt.tris; counts[2] = total_cnt.inst; }
+}
+
+// single path probe (Tracer::Debug / PathTracer::DebugInternal analogue): radiance of pixel (x,y) in pass `pass`
+void orc_path_probe(const ctl_scene_view* S, int w, int x, int y, int pass, int max_path_length, int rr_start, int direct, float* rgb, uint64_t* rays) {
+    std::vector<float> d1((size_t)N_SEQ * SEQ_LEN), d2((size_t)N_SEQ * SEQ_LEN * 2);
+    Xorwow st; xorwow_init(1234, 7539414, 0, st);
+    for (int p = 0; p <= pass; p++) fill_tables(st, d1.data(), d2.data());
+    Sampler rng = {d1.data(), d2.data(), (unsigned)(y * w + x), 0, 0};
+    float jx, jy; rng.f2(jx, jy); float ax, ay; rng.f2(ax, ay);
+    V3 o, d; camera_ray(S->camera, (float)x + jx, (float)y + jy, o, d);
+    PTParams P = {max_path_length, rr_start, direct};
+    uint64_t r = 0; Spec c = path_trace(*S, o, d, rng, P, r, 0);
+    rgb[0] = c.r; rgb[1] = c.g; rgb[2] = c.b; if (rays) *rays = r;
+}
+
+int orc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+} // extern "C"

@@ -1,0 +1,161 @@
+"""ctypes binding of oracle/liboracle.so -- TEST INFRASTRUCTURE (the checker, never the product)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from cudatracerlib_b200.api import SceneView, Material, RAY_DTYPE, RESULT16_DTYPE, TRACE_RESULT_DTYPE, PIXEL_DTYPE
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+_lib = None
+
+
+def build_oracle():
+    src = os.path.join(ORACLE_DIR, "oracle.cpp")
+    if not os.path.exists(ORACLE_LIB) or os.path.getmtime(src) > os.path.getmtime(ORACLE_LIB):
+        subprocess.run(["make", "-C", ORACLE_DIR, "-s"], check=True)
+    return ORACLE_LIB
+
+
+def oracle():
+    global _lib
+    if _lib is None:
+        build_oracle()
+        L = C.CDLL(ORACLE_LIB)
+        L.orc_half_to_float.restype = C.c_float; L.orc_half_to_float.argtypes = [C.c_uint16]
+        L.orc_float_to_half.restype = C.c_uint16; L.orc_float_to_half.argtypes = [C.c_float]
+        L.orc_encode_normal.restype = C.c_uint16
+        L.orc_fresnel_dielectric_ext.restype = C.c_float; L.orc_fresnel_dielectric_ext.argtypes = [C.c_float, C.c_float, C.c_void_p]
+        L.orc_warp.argtypes = [C.c_int, C.c_float, C.c_float, C.c_void_p]
+        L.orc_microfacet_sample.argtypes = [C.c_int, C.c_float, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+        L.orc_bsdf_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_bsdf_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_fresnel_conductor_exact.argtypes = [C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_light_sample_direct.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+        L.orc_fill_dg.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.orc_camera_ray.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        L.orc_woop_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+        L.orc_trace_rays.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_intersect.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_render.argtypes = [C.c_void_p] + [C.c_int] * 11 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_path_probe.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_void_p]
+        L.orc_sample_tables.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p]
+        L.orc_sampler_draws.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_xorwow_init.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, C.c_void_p]
+        L.orc_xorwow_floats.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def xorwow_state(seed, subsequence, offset=0):
+    st = np.zeros(6, np.uint32); oracle().orc_xorwow_init(seed, subsequence, offset, _p(st)); return st
+
+
+def xorwow_floats(state, n):
+    out = np.zeros(n, np.float32); oracle().orc_xorwow_floats(_p(state), n, _p(out)); return out
+
+
+def sample_tables(pass_index):
+    d1 = np.zeros(4096 * 30, np.float32); d2 = np.zeros(4096 * 30 * 2, np.float32)
+    oracle().orc_sample_tables(pass_index, _p(d1), _p(d2)); return d1, d2
+
+
+def sampler_draws(d1, d2, idx, n1, n2):
+    o1 = np.zeros(max(n1, 1), np.float32); o2 = np.zeros(max(n2, 1) * 2, np.float32)
+    oracle().orc_sampler_draws(_p(d1), _p(d2), idx, n1, _p(o1), n2, _p(o2)); return o1[:n1], o2[:2 * n2].reshape(-1, 2)
+
+
+def encode_woop(v0, v1, v2):
+    a, b, c = (np.ascontiguousarray(x, np.float32) for x in (v0, v1, v2))
+    out = np.zeros(12, np.float32); oracle().orc_encode_woop(_p(a), _p(b), _p(c), _p(out)); return out
+
+
+def woop_intersect(woop12, o, d, tmax=3.4e38):
+    w = np.ascontiguousarray(woop12, np.float32); o = np.ascontiguousarray(o, np.float32); d = np.ascontiguousarray(d, np.float32)
+    tuv = np.zeros(3, np.float32)
+    hit = oracle().orc_woop_intersect(_p(w), _p(o), _p(d), tmax, _p(tuv))
+    return bool(hit), tuv
+
+
+def encode_tri_data(p9, n9, uv6, mat):
+    p, n, uv = (np.ascontiguousarray(x, np.float32).ravel() for x in (p9, n9, uv6))
+    out = np.zeros(8, np.uint32); oracle().orc_encode_tri_data(_p(p), _p(n), _p(uv), mat, _p(out)); return out
+
+
+def decode_normal(code):
+    out = np.zeros(3, np.float32); oracle().orc_decode_normal(C.c_uint16(code), _p(out)); return out
+
+
+def encode_normal(n):
+    n = np.ascontiguousarray(n, np.float32); return oracle().orc_encode_normal(_p(n))
+
+
+def warp(which, sx, sy):
+    out = np.zeros(3, np.float32); oracle().orc_warp(which, sx, sy, _p(out)); return out
+
+
+def fresnel_dielectric_ext(cosi, eta):
+    ct = C.c_float(0); F = oracle().orc_fresnel_dielectric_ext(cosi, eta, C.byref(ct)); return F, ct.value
+
+
+def fresnel_conductor_exact(cosi, eta, k):
+    e = np.ascontiguousarray(eta, np.float32); kk = np.ascontiguousarray(k, np.float32); out = np.zeros(3, np.float32)
+    oracle().orc_fresnel_conductor_exact(cosi, _p(e), _p(kk), _p(out)); return out
+
+
+def microfacet_sample(type_, alpha, wi, sx, sy):
+    w = np.ascontiguousarray(wi, np.float32); out = np.zeros(6, np.float32)
+    oracle().orc_microfacet_sample(type_, alpha, _p(w), sx, sy, _p(out)); return out
+
+
+def bsdf_probe(mat, wi, sx, sy):
+    w = np.ascontiguousarray(wi, np.float32); out = np.zeros(9, np.float32); f = np.zeros(3, np.float32); pdf = np.zeros(1, np.float32)
+    oracle().orc_bsdf_probe(C.byref(mat), _p(w), sx, sy, _p(out), _p(f), _p(pdf)); return out, f, pdf[0]
+
+
+def light_sample_direct(view, light, ref, refN, sx, sy):
+    r = np.ascontiguousarray(ref, np.float32); n = np.ascontiguousarray(refN, np.float32); out = np.zeros(11, np.float32)
+    oracle().orc_light_sample_direct(C.byref(view), light, _p(r), _p(n), sx, sy, _p(out)); return out
+
+
+def fill_dg(view, u, v, tri, node):
+    out = np.zeros(12, np.float32); oracle().orc_fill_dg(C.byref(view), u, v, tri, node, _p(out)); return out.reshape(4, 3)
+
+
+def camera_ray(view, px, py):
+    o = np.zeros(3, np.float32); d = np.zeros(3, np.float32); oracle().orc_camera_ray(C.byref(view), px, py, _p(o), _p(d)); return o, d
+
+
+def trace_rays(view, rays, counts=False):
+    rays = np.ascontiguousarray(rays, RAY_DTYPE); out = np.zeros(len(rays), TRACE_RESULT_DTYPE); cnt = np.zeros(3, np.uint64)
+    oracle().orc_trace_rays(C.byref(view), len(rays), _p(rays), _p(out), _p(cnt) if counts else None)
+    return (out, [int(x) for x in cnt]) if counts else out
+
+
+def intersect(view, rays, any_hit=False):
+    rays = np.ascontiguousarray(rays, RAY_DTYPE); out = np.zeros(len(rays), RESULT16_DTYPE)
+    oracle().orc_intersect(C.byref(view), len(rays), _p(rays), _p(out), int(any_hit)); return out
+
+
+def render(view, w, h, n_passes=1, pass_first=0, max_path_length=8, rr_start=5, direct=1, window=None, n_threads=0, counts=False, img=None):
+    if img is None:
+        img = np.zeros((h, w), PIXEL_DTYPE)
+    x0, y0, x1, y1 = window if window else (0, 0, w, h)
+    rays = C.c_uint64(0); cnt = np.zeros(3, np.uint64)
+    if n_threads <= 0:
+        n_threads = os.cpu_count() or 1
+    oracle().orc_render(C.byref(view), w, h, x0, y0, x1, y1, pass_first, n_passes, max_path_length, rr_start, direct, _p(img), C.byref(rays), n_threads,
+                        _p(cnt) if counts else None)
+    return (img, rays.value, [int(x) for x in cnt]) if counts else (img, rays.value)
+
+
+def path_probe(view, w, x, y, pass_index=0, max_path_length=8, rr_start=5, direct=1):
+    rgb = np.zeros(3, np.float32); rays = C.c_uint64(0)
+    oracle().orc_path_probe(C.byref(view), w, x, y, pass_index, max_path_length, rr_start, direct, _p(rgb), C.byref(rays)); return rgb, rays.value
