@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- the hot-path benchmark (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c4|c5|cornell]
+
+A *step* is one progressive frame of the workload: `spp` passes of the wavefront path tracer over the whole
+image (each pass = 1 path per pixel, <= depth vertices, 1 extension + <= 1 shadow ray per vertex) followed, for
+N > 1, by the single NCCL reduce of the PixelData accumulator to rank 0.  Metric: Mrays/s, a ray being one
+closest-hit/any-hit query exactly as the reference counts them (Kernel/TraceHelper.cu:176).
+
+N = 1 : the whole image on one B200.  N > 1 : one process per GPU (torchrun), scene replicated, image split in
+interleaved 64x64 tiles (tile % N == rank), "scaling": "strong" (the total work -- one image -- is fixed).
+
+`value`   : device-timed (CUDA events on the launching stream) with the scene resident in HBM.
+`e2e`     : the same frames through the public API with HOST buffers: per step the sample tables are generated on
+            the host and copied H2D from pinned memory, and the PixelData image is copied D2H into pinned memory.
+`roofline`: the traversal kernel (k_intersect, extension + shadow launches): algorithmic bytes (visit counts of an
+            instrumented pass x SURVEY 8d's per-visit bytes) / live CUDA-event time of those launches.
+`cpu_baseline` / `--impl reference`: the reference's CPU path (oracle/_ref when built, else the oracle port) on the
+            host cores, on a bounded crop of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (scene kind, width, height, spp, MaxPathLength, description)
+    "cornell": ("cornell", 256, 256, 1, 8, "Cornell-32 256x256 1spp depth 8 (configs[0])"),
+    "c2": ("c2", 1920, 1080, 8, 8, "procedural 100K-triangle diffuse scene (99,854 tris) 1920x1080 8spp 8 bounces (configs[1])"),
+    "c3": ("c3", 1920, 1080, 8, 8, "100K scene, diffuse/roughconductor/dielectric mix, 1920x1080 8spp 8 bounces (configs[2])"),
+    "c4": ("c4", 1920, 1080, 8, 8, "procedural 1M-triangle clustered scene (999,854 tris) 1920x1080 8spp 8 bounces (configs[3])"),
+    "c5": ("c5", 1920, 1080, 64, 32, "1M scene, microfacet mix, 32 bounces 64spp (configs[4])"),
+}
+TILE = 64
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        for k in ("hbm_gbs", "hbm_gb_s", "hbm_GBps"):
+            if k in d:
+                return float(d[k]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv"); os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def crop_window(w, h, frac):
+    """Centre crop holding `frac` of the pixels (same aspect)."""
+    s = frac ** 0.5
+    cw, ch = max(16, int(w * s)) // 8 * 8, max(16, int(h * s)) // 8 * 8
+    x0, y0 = (w - cw) // 2, (h - ch) // 2
+    return (x0, y0, x0 + cw, y0 + ch)
+
+
+def cpu_reference_run(view, w, h, depth, window, n_passes, threads):
+    """Time the reference's CPU path on `window`: oracle/_ref when present, else the oracle port."""
+    import oracle_binding as ob
+    kind = "port"
+    try:
+        import ref_binding as rb
+        if rb.available():
+            kind = "reference"
+    except Exception:
+        rb = None
+    t0 = time.perf_counter()
+    if kind == "reference":
+        _, rays = rb.render(view, w, h, n_passes=n_passes, max_path_length=depth, window=window, n_threads=threads)
+    else:
+        _, rays = ob.render(view, w, h, n_passes=n_passes, max_path_length=depth, window=window, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return kind, rays, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from cudatracerlib_b200 import Scene
+    kind, w, h, spp, depth, desc = WORKLOADS[args.workload]
+    scene = Scene(kind, w, h)
+    threads = os.cpu_count() or 1
+    frac = args.cpu_frac if args.workload != "cornell" else 1.0
+    window = crop_window(w, h, frac)
+    times, rays_tot, impl_kind = [], 0, "port"
+    for i in range(args.warmup + args.steps):
+        impl_kind, rays, dt = cpu_reference_run(scene.view, w, h, depth, window, 1, threads)
+        if i >= args.warmup:
+            times.append(dt); rays_tot += rays
+    total = sum(times)
+    v = rays_tot / total / 1e6
+    sample = f"{window[2]-window[0]}x{window[3]-window[1]} centre crop of the {w}x{h} image, 1 pass per step (of {spp}), depth {depth}"
+    line = {"impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": desc, "width": w, "height": h, "spp": spp, "max_path_length": depth, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": threads, "kind": impl_kind, "sample": sample},
+            "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-frac", type=float, default=1.0 / 16, help="fraction of the image the CPU baseline renders per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sort-mode", type=int, default=None)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rule: W >= 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from cudatracerlib_b200 import Scene, PathTracer, traversal_bytes, build
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+
+    kind, w, h, spp, depth, desc = WORKLOADS[args.workload]
+    scene = Scene(kind, w, h)
+    tracer = PathTracer(w, h, device=local)
+    tracer.InitializeScene(scene)
+    tracer.setParameter("MaxPathLength", depth)
+    if args.sort_mode is not None:
+        tracer.setParameter("SortMode", args.sort_mode)
+    stream = torch.cuda.current_stream()
+    tracer.setStream(stream.cuda_stream)
+    accum = torch.zeros(h * w * 7, dtype=torch.float32, device=dev)
+    tracer.setAccumDevicePtr(accum.data_ptr())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    host_img = torch.empty(h * w * 7, dtype=torch.float32, pin_memory=True)
+    table_bytes = 4096 * 30 * 12
+
+    def frame(read_back):
+        for p in range(spp):
+            if world > 1:
+                tracer.DoPassTiled(TILE, TILE, rank, world, new_trace=(p == 0))
+            else:
+                tracer.DoPass(new_trace=(p == 0))
+        if world > 1:
+            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+        if read_back and rank == 0:
+            host_img.copy_(accum, non_blocking=True)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up
+    rays_per_frame_local = 0
+    for _ in range(args.warmup):
+        r0 = tracer.getTotalRays()
+        frame(False)
+        rays_per_frame_local = tracer.getTotalRays() - r0  # frames are identical (new_trace restarts the sample stream)
+    sync_all()
+
+    # ---- device-timed steps (value)
+    clocks = ClockSampler(local); clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    rays_steps = 0
+    sync_all()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations, outside the event bracket
+        ev[i][0].record(stream)
+        frame(False)
+        ev[i][1].record(stream)
+    sync_all()
+    t_wall = time.perf_counter() - t_wall0
+    clk = clocks.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = float(sum(step_ms))
+    t = torch.tensor([dev_ms, float(rays_per_frame_local)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms, rays_frame = float(tmax[0]), float(tsum[1])
+    else:
+        rays_frame = float(t[1])
+    value = rays_frame * args.steps / (dev_ms * 1e-3) / 1e6
+    launches_per_pass = tracer.stageTimes()[1]
+
+    # ---- end-to-end steps through the public API with host buffers
+    e2e_steps = max(3, min(args.steps, 10))
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        frame(True)
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = rays_frame * e2e_steps / float(te[0]) / 1e6
+    img_mean = float(host_img.view(h, w, 7)[:, :, :3].mean()) if rank == 0 else 0.0
+
+    # ---- roofline of the traversal kernel (rank 0's share), live CUDA-event stage times
+    roof = None
+    if True:
+        tracer.setParameter("StageTimers", 1)
+        ext_ms = sh_ms = 0.0
+        n_tp = 0
+        for p in range(spp):
+            if world > 1:
+                tracer.DoPassTiled(TILE, TILE, rank, world, new_trace=(p == 0))
+            else:
+                tracer.DoPass(new_trace=(p == 0))
+            tracer.synchronize()
+            ms, _ = tracer.stageTimes()
+            ext_ms += ms[1]; sh_ms += ms[3]; n_tp += 1
+        tracer.setParameter("StageTimers", 0)
+        stage_last = ms
+        tracer.setInstrumented(1)
+        if world > 1:
+            tracer.DoPassTiled(TILE, TILE, rank, world, new_trace=True)
+        else:
+            tracer.DoPass(new_trace=True)
+        tracer.synchronize()
+        e_cnt, s_cnt = tracer.visitCounts()
+        tracer.setInstrumented(0)
+        bytes_pass = traversal_bytes(e_cnt, e_cnt[3]) + traversal_bytes(s_cnt, s_cnt[3])
+        trav_ms_pass = (ext_ms + sh_ms) / n_tp
+        n_trav_launches = 2 * depth
+        peak, peak_src = hbm_peak()
+        achieved = bytes_pass / (trav_ms_pass * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_intersect (extension + shadow launches)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "algorithmic_bytes_per_launch": bytes_pass / n_trav_launches, "avg_launch_ms": trav_ms_pass / n_trav_launches,
+                "bytes_per_ray": bytes_pass / max(1, e_cnt[3] + s_cnt[3]), "launches_per_pass": n_trav_launches,
+                "traversal_share_of_pass": (stage_last[1] + stage_last[3]) / max(1e-9, sum(stage_last)),
+                "stage_ms_last_pass": {"generate": stage_last[0], "extension": stage_last[1], "shade": stage_last[2], "shadow": stage_last[3], "finish": stage_last[4]}}
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        try:
+            with open(tp) as f:
+                roof["traffic"] = json.load(f).get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- CPU baseline (rank 0, N == 1 only): bounded crop on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        frac = args.cpu_frac if args.workload != "cornell" else 1.0
+        window = crop_window(w, h, frac)
+        ckind, crays, cdt = cpu_reference_run(scene.view, w, h, depth, window, 1, threads)
+        if cdt < 5.0 and args.workload != "cornell":  # aim at >= ~10 s of CPU work
+            n_p = int(min(spp, max(1, round(10.0 / max(cdt, 1e-3)))))
+            ckind, crays, cdt = cpu_reference_run(scene.view, w, h, depth, window, n_p, threads)
+        else:
+            n_p = 1
+        cpu = {"value": crays / cdt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": ckind,
+               "sample": f"{window[2]-window[0]}x{window[3]-window[1]} centre crop of the {w}x{h} image, {n_p} pass(es), depth {depth}, {crays} rays in {cdt:.2f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "width": w, "height": h, "spp": spp, "max_path_length": depth, "rr_start_depth": 5, "direct": True,
+                       "triangles": scene.n_triangles, "rays_per_step": rays_frame,
+                       "partition": "whole image" if world == 1 else f"interleaved {TILE}x{TILE} tiles, tile % {world} == rank; one NCCL reduce of PixelData (7*w*h f32) per step",
+                       "l2": "256 MiB buffer written between timed steps (L2 flush); per-pass queue/path-state working set ~0.5 GB > 126 MB L2"},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": spp * table_bytes, "d2h_bytes_per_step": h * w * 7 * 4,
+                    "steps": e2e_steps, "note": "wall clock; host XORWOW sample-table generation + pinned H2D every pass, PixelData image D2H to pinned memory every step"},
+            "gpu_launches": int(launches_per_pass * spp * args.steps),
+            "wall_s_timed_region": t_wall, "image_mean_rgb": img_mean,
+        }
+        if roof:
+            line["roofline"] = roof
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    tracer.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -124,6 +124,7 @@ def lib():
     L.ctl_accum_device_ptr.argtypes = [vp]; L.ctl_accum_device_ptr.restype = vp
     L.ctl_set_accum_device_ptr.argtypes = [vp, vp]
     L.ctl_stream.argtypes = [vp]; L.ctl_stream.restype = vp
+    L.ctl_set_stream.argtypes = [vp, vp]
     L.ctl_stats.argtypes = [vp, u64p, fp, u64p, C.POINTER(C.c_uint32)]
     L.ctl_stage_times.argtypes = [vp, fp, C.POINTER(C.c_uint32)]
     L.ctl_set_instrumented.argtypes = [vp, i32]
@@ -274,6 +275,10 @@ class PathTracer:
     def stream(self):
         return lib().ctl_stream(self._ctx)
 
+    def setStream(self, cuda_stream):
+        """Run on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); None = own stream."""
+        _check(lib().ctl_set_stream(self._ctx, C.c_void_p(cuda_stream) if cuda_stream else None))
+
     # -- __internal__IntersectBuffers / traceRay surfaces
     def intersect(self, rays, any_hit=False):
         rays = np.ascontiguousarray(rays, RAY_DTYPE)
@@ -343,3 +348,11 @@ def traversal_bytes(counts, n_rays):
     """Algorithmic bytes of the traversal kernel: 32 B ray + 16 B result per ray,
     64 B per inner node popped, 52 B per triangle reference tested, 108 B per instance leaf entered."""
     return 48 * n_rays + 64 * counts[0] + 52 * counts[1] + 108 * counts[2]
+
+
+def tile_owner(w, h, tile_w, tile_h, n_parts):
+    """(h, w) int array: which part renders each pixel under ctl_render_pass_tiled's interleaved partition
+    (tile index = ty * tiles_x + tx; owner = tile index % n_parts)."""
+    tiles_x = (w + tile_w - 1) // tile_w
+    ty, tx = np.meshgrid(np.arange(h) // tile_h, np.arange(w) // tile_w, indexing="ij")
+    return (ty * tiles_x + tx) % n_parts

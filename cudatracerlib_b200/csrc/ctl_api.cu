@@ -50,7 +50,7 @@ template <typename T> struct DevBuf {
 struct ctl_ctx {
     int device = 0, w = 0, h = 0;
     int n_sm = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
     // parameters (Integrators/PathTracer.h:10-20)
     int max_path_length = 50, rr_start = 5, direct = 1, regularization = 0, sort_mode = 0, stage_timers = 0, capture_bounce = 0;
     // scene
@@ -140,7 +140,8 @@ ctl_ctx* ctl_create(int device, int width, int height) {
     cudaDeviceProp prop;
     CKP(cudaGetDeviceProperties(&prop, device));
     c->n_sm = prop.multiProcessorCount;
-    CKP(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CKP(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
     CKP(cudaEventCreate(&c->ev_start)); CKP(cudaEventCreate(&c->ev_stop));
     for (int i = 0; i < N_TABLE_SLOTS; i++) {
         CKP(c->d_d1[i].ensure((size_t)ctlb::kNumSeq * ctlb::kSeqLen)); CKP(c->d_d2[i].ensure((size_t)ctlb::kNumSeq * ctlb::kSeqLen * 2));
@@ -166,7 +167,7 @@ void ctl_destroy(ctl_ctx* c) {
     c->own_accum.release(); c->d_captured_n.release();
     for (auto e : c->stage_ev) cudaEventDestroy(e);
     cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_stop);
-    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
@@ -437,6 +438,13 @@ int ctl_set_accum_device_ptr(ctl_ctx* c, void* p) {
     return 0;
 }
 void* ctl_stream(ctl_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int ctl_set_stream(ctl_ctx* c, void* stream) {
+    if (!c) return set_err("null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    return 0;
+}
 
 int ctl_stats(ctl_ctx* c, uint64_t* rays_last, float* seconds_last, uint64_t* rays_total, uint32_t* passes_done) {
     if (!c) return set_err("null context");

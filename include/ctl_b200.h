@@ -268,6 +268,10 @@ int ctl_get_captured_rays(ctl_ctx*, ctl_traversal_ray* host_out, int capacity);
 int ctl_get_queue_sizes(ctl_ctx*, uint32_t* ext, uint32_t* shadow, int n);
 /* The context's cudaStream_t (so callers can order their own work after the passes). */
 void* ctl_stream(ctl_ctx*);
+/* Run all following work of this context on a caller-owned cudaStream_t (NULL = back to the context's own
+ * stream).  The reference is single-stream (default stream, Kernel/TraceHelper.cu:744); this lets a host
+ * application order the passes with its own kernels / NCCL calls without extra synchronisation. */
+int ctl_set_stream(ctl_ctx*, void* stream);
 
 #ifdef __cplusplus
 }

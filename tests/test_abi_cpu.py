@@ -1,0 +1,206 @@
+"""CPU-side checks of the boundary: the C-ABI library loads (no GPU needed to dlopen it), exports every symbol
+include/ctl_b200.h declares, the POD layouts have the reference's sizes (SURVEY §8 header / Appendix A), and the
+host scene builder emits the reference encodings.  No compute call is made on the device here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cudatracerlib_b200 as ctl
+from cudatracerlib_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "ctl_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(ctl_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(built_lib, n)]
+    assert not missing, missing
+
+
+def test_pod_sizes_match_reference():
+    # sizes probed from the reference headers: BVHNodeData 64, TriIntersectorData 48, TriangleData 32,
+    # KernelMesh 20, Node 24, traversalRay 32, traversalResult 16, PixelData 28, ShapeSet::triData 64
+    assert C.sizeof(api.BvhNode) == 64 and C.sizeof(api.WoopTri) == 48 and C.sizeof(api.TriData) == 32
+    assert C.sizeof(api.Mesh) == 20 and C.sizeof(api.Node) == 24 and C.sizeof(api.LightTri) == 64
+    assert api.RAY_DTYPE.itemsize == 32 and api.RESULT16_DTYPE.itemsize == 16 and api.PIXEL_DTYPE.itemsize == 28
+    assert api.TRACE_RESULT_DTYPE.itemsize == 20  # TraceResult fields (24 B in the reference incl. padding-free 5 words + vptr-less)
+    assert C.sizeof(api.Material) == 64 and C.sizeof(api.Light) == 32
+
+
+def test_no_device_fails_loudly(built_lib):
+    """No CPU fallback: creating a tracer without a CUDA device raises with the reference's error format."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError) as e:
+        ctl.PathTracer(16, 16)
+    assert "In file" in str(e.value) or "no such CUDA device" in str(e.value)
+
+
+def test_sample_tables_match_oracle(built_lib, orc):
+    for p in (0, 1, 3):
+        d1, d2 = ctl.generate_sample_tables(p)
+        o1, o2 = orc.sample_tables(p)
+        assert np.array_equal(d1.view(np.uint32), o1.view(np.uint32)) and np.array_equal(d2.view(np.uint32), o2.view(np.uint32))
+
+
+def test_encoders_match_oracle(built_lib, orc):
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        v = rng.normal(size=(3, 3)).astype(np.float32) * 3
+        out = (C.c_float * 12)()
+        built_lib.ctl_encode_woop(v[0].ctypes.data, v[1].ctypes.data, v[2].ctypes.data, out)
+        assert np.array_equal(np.frombuffer(out, np.float32).view(np.uint32), orc.encode_woop(v[0], v[1], v[2]).view(np.uint32))
+        n = rng.normal(size=(3, 3)).astype(np.float32); n /= np.linalg.norm(n, axis=1, keepdims=True)
+        uv = rng.uniform(size=6).astype(np.float32)
+        td = (C.c_uint32 * 8)()
+        pp = np.ascontiguousarray(v.ravel()); nn = np.ascontiguousarray(n.ravel().astype(np.float32))
+        built_lib.ctl_encode_tri_data(pp.ctypes.data, nn.ctypes.data, uv.ctypes.data, 5, td)
+        assert list(td) == [int(x) for x in orc.encode_tri_data(v, n, uv, 5)]
+
+
+def _check_bvh(nodes_f, n_leaf_slots_or_nodes, leaf_is_node_index, prim_boxes_of_leaf):
+    """Walk a reference-layout BVH: children in float4 units, ~leaf, 0x76543210 sentinel; every leaf reachable once;
+    child boxes contain the primitives below them."""
+    nodes = nodes_f.view(np.uint32).reshape(-1, 16)
+    seen = []
+    stack = [0]
+    visited_inner = 0
+    while stack:
+        a = stack.pop()
+        assert a % 4 == 0 and a // 4 < len(nodes)
+        visited_inner += 1
+        nf = nodes_f[a // 4]
+        for ci in range(2):
+            child = int(nodes[a // 4, 12 + ci].astype(np.int64))
+            if child >= 0x80000000:
+                child -= 1 << 32
+            if ci == 0:
+                lo = np.array([nf[0], nf[2], nf[8]]); hi = np.array([nf[1], nf[3], nf[9]])
+            else:
+                lo = np.array([nf[4], nf[6], nf[10]]); hi = np.array([nf[5], nf[7], nf[11]])
+            if child == 0x76543210:
+                continue
+            if child < 0:
+                seen.append(~child)
+                blo, bhi = prim_boxes_of_leaf(~child)
+                assert np.all(lo <= blo + 1e-4 * (1 + np.abs(blo))) and np.all(hi >= bhi - 1e-4 * (1 + np.abs(bhi)))
+            else:
+                stack.append(child)
+    return seen, visited_inner
+
+
+@pytest.mark.parametrize("kind", ["cornell", "cornell7", "soup"])
+def test_scene_builder_emits_reference_layout(built_lib, orc, kind):
+    s = ctl.Scene(kind, 64, 64, n_hint=300)
+    v = s.view
+    meshes = s.array("meshes"); nodes = s.array("nodes"); woop = s.array("woop"); tri_index = s.array("tri_index")[:, 0]
+    bvh = s.array("bvh_nodes")
+    assert v.n_woop == v.n_tri_index
+    total_refs = 0
+    for m in meshes:
+        tri_off, node_off4, tri_off4, idx_off, _ = [int(x) for x in m]
+        assert node_off4 % 4 == 0 and tri_off4 % 3 == 0 and tri_off4 // 3 == idx_off
+        sub = bvh[node_off4 // 4:]
+
+        def leaf_box(first, idx_off=idx_off):
+            lo = np.full(3, np.inf); hi = np.full(3, -np.inf); a = first
+            while True:
+                w = woop[idx_off + a].reshape(3, 4).astype(np.float64)
+                M = np.array([[w[1][0], w[1][1], w[1][2], w[1][3]], [w[2][0], w[2][1], w[2][2], w[2][3]], [w[0][0], w[0][1], w[0][2], -w[0][3]], [0, 0, 0, 1]])
+                Mi = np.linalg.inv(M)  # columns: v0-v2, v1-v2, n, v2
+                v2 = Mi[:3, 3]; v0 = Mi[:3, 0] + v2; v1 = Mi[:3, 1] + v2
+                for p in (v0, v1, v2):
+                    lo = np.minimum(lo, p); hi = np.maximum(hi, p)
+                if tri_index[idx_off + a] & 1:
+                    break
+                a += 1
+            return lo, hi
+        seen, _ = _check_bvh(sub, None, False, leaf_box)
+        # every leaf run ends with the last-in-leaf flag; runs partition the mesh's slots
+        n_refs = 0
+        for first in seen:
+            a = first
+            while not (tri_index[idx_off + a] & 1):
+                a += 1
+            n_refs += a - first + 1
+            assert a - first + 1 <= 8  # maxLeafSize 8 (BVHBuilderHelper.cpp:119)
+        total_refs += n_refs
+    assert total_refs == v.n_woop
+    # every mesh triangle is referenced at least once
+    refd = set()
+    for m in meshes:
+        tri_off, _, _, idx_off, _ = [int(x) for x in m]
+    assert len(np.unique(tri_index >> 1)) >= 1
+    # scene level: one object per leaf, leaf = ~nodeIdx
+    sb = s.array("scene_bvh_nodes")
+    if v.scene_start_node >= 0:
+        seen, _ = _check_bvh(sb, None, True, lambda i: (np.array(list(v.box_max)), np.array(list(v.box_min))))
+        assert sorted(seen) == list(range(v.n_nodes))
+    else:
+        assert ~v.scene_start_node < v.n_nodes
+    assert v.ray_eps == pytest.approx(1e-4 * np.linalg.norm(np.array(list(v.box_max)) - np.array(list(v.box_min))), rel=1e-5)
+
+
+def test_oracle_traversal_vs_brute_force(built_lib, orc):
+    """The oracle's two-level BVH traversal finds the same closest triangle as an O(N) Woop scan of all references."""
+    s = ctl.Scene("soup", 64, 64, n_hint=300)
+    v = s.view
+    rng = np.random.default_rng(11)
+    n = 400
+    rays = np.zeros(n, api.RAY_DTYPE)
+    lo = np.array(list(v.box_min)); hi = np.array(list(v.box_max))
+    rays["o"] = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays["d"] = d.astype(np.float32); rays["tmax"] = 3e38
+    res = orc.trace_rays(v, rays)
+    woop = s.array("woop").astype(np.float64).reshape(-1, 3, 4)
+    tri_index = s.array("tri_index")[:, 0]
+    meshes = s.array("meshes"); nodes = s.array("nodes"); inv = s.array("node_inv_xf").astype(np.float64).reshape(-1, 4, 4)
+    for i in range(n):
+        best = (np.inf, -1)
+        for ni, nd in enumerate(nodes):
+            m = meshes[int(nd[0])]
+            o4 = inv[ni] @ np.append(rays["o"][i].astype(np.float64), 1.0); o = o4[:3] / o4[3]
+            dd = inv[ni][:3, :3] @ rays["d"][i].astype(np.float64)
+            n_slots = (int(meshes[int(nd[0]) + 1][3]) if int(nd[0]) + 1 < len(meshes) else v.n_woop) - int(m[3])
+            W = woop[int(m[3]):int(m[3]) + n_slots]
+            Oz = W[:, 0, 3] - W[:, 0, :3] @ o; iDz = 1.0 / (W[:, 0, :3] @ dd)
+            t = Oz * iDz
+            u = W[:, 1, 3] + W[:, 1, :3] @ o + t * (W[:, 1, :3] @ dd)
+            vv = W[:, 2, 3] + W[:, 2, :3] @ o + t * (W[:, 2, :3] @ dd)
+            ok = (t > v.ray_eps) & (u >= 0) & (vv >= 0) & (u + vv <= 1) & np.isfinite(t)
+            if ok.any():
+                k = np.argmin(np.where(ok, t, np.inf))
+                if t[k] < best[0]:
+                    best = (t[k], (int(tri_index[int(m[3]) + k]) >> 1) + int(m[0]))
+        if best[1] < 0:
+            assert res["tri_idx"][i] == 0xffffffff
+        else:
+            assert res["tri_idx"][i] != 0xffffffff
+            assert abs(res["dist"][i] - best[0]) <= 1e-4 * max(1.0, best[0])
+
+
+def test_oracle_render_is_partition_invariant(orc):
+    """RNG is a pure function of (pass, pixel index, dimension): rendering windows separately equals the whole image."""
+    s = ctl.Scene("cornell", 48, 48)
+    whole, rays = orc.render(s.view, 48, 48, n_passes=1, max_path_length=6, n_threads=2)
+    parts = np.zeros((48, 48), api.PIXEL_DTYPE)
+    r2 = 0
+    for win in ((0, 0, 24, 48), (24, 0, 48, 24), (24, 24, 48, 48)):
+        _, r = orc.render(s.view, 48, 48, n_passes=1, max_path_length=6, window=win, n_threads=2, img=parts)
+        r2 += r
+    assert r2 == rays
+    assert np.allclose(parts["rgb"], whole["rgb"], rtol=1e-6, atol=1e-7) and np.array_equal(parts["weight_sum"], whole["weight_sum"])
+
+
+def test_tile_owner_partition():
+    own = ctl.tile_owner(100, 70, 16, 16, 3)
+    assert own.shape == (70, 100) and set(np.unique(own)) == {0, 1, 2}
+    assert own[0, 0] == 0 and own[0, 16] == 1 and own[0, 32] == 2 and own[16, 0] == (7 % 3)
