@@ -199,7 +199,9 @@ def main():
     tracer.setParameter("MaxPathLength", depth)
     if args.sort_mode is not None:
         tracer.setParameter("SortMode", args.sort_mode)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # a real (non-default) stream: the tracer, NCCL and the timing events all use it
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     tracer.setStream(stream.cuda_stream)
     accum = torch.zeros(h * w * 7, dtype=torch.float32, device=dev)
     tracer.setAccumDevicePtr(accum.data_ptr())

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libctl_b200.so")
+LIB_PATH = os.environ.get("CTL_B200_LIB") or os.path.join(_HERE, "libctl_b200.so")  # env override: A/B builds only
 
 MAX_NUM_LIGHTS = 16
 

@@ -52,7 +52,7 @@ struct ctl_ctx {
     int n_sm = 148;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     // parameters (Integrators/PathTracer.h:10-20)
-    int max_path_length = 50, rr_start = 5, direct = 1, regularization = 0, sort_mode = 0, stage_timers = 0, capture_bounce = 0;
+    int max_path_length = 50, rr_start = 5, direct = 1, regularization = 0, sort_mode = 0, stage_timers = 0, capture_bounce = 0, trav_kernel = 0, trav_blocks_per_sm = 8;
     // scene
     DevBuf<ctl_bvh_node> d_scene_nodes, d_bvh_nodes; DevBuf<ctl_woop_tri> d_woop; DevBuf<uint32_t> d_tri_index; DevBuf<ctl_tri_data> d_tri_data;
     DevBuf<ctl_mesh> d_meshes; DevBuf<ctl_node> d_nodes; DevBuf<float> d_xf, d_inv_xf; DevBuf<ctl_material> d_materials; DevBuf<ctl_light> d_lights;
@@ -76,7 +76,16 @@ struct ctl_ctx {
     std::vector<cudaEvent_t> stage_ev; std::vector<int> stage_kind;
     float stage_ms[5] = {0, 0, 0, 0, 0}; uint32_t n_launches = 0;
     bool instrumented = false;
+    TravTune tune = {2, 8, 8, 4};
 };
+
+
+// "TraversalKernel": 0 = persistent phase-scheduled kernel (production), 1 = simple ray-batch kernel (A/B baseline)
+template <int MODE, bool ANY_HIT, bool COUNT, typename... Args>
+static void launch_intersect(const ctl_ctx* c, int grid, cudaStream_t st, const DScene& S, Args... args) {
+    if (c->trav_kernel == 1) k_intersect_simple<MODE, ANY_HIT, COUNT><<<grid, 128, 0, st>>>(S, args...);
+    else k_intersect<MODE, ANY_HIT, COUNT><<<grid, 128, 0, st>>>(S, c->tune, args...);
+}
 
 extern "C" {
 
@@ -190,6 +199,10 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "SortMode") c->sort_mode = v;
     else if (k == "StageTimers") c->stage_timers = v != 0;
     else if (k == "CaptureBounce") c->capture_bounce = v;
+    else if (k == "TraversalKernel") { if (v < 0 || v > 1) return set_err("TraversalKernel must be 0 or 1"); c->trav_kernel = v; }
+    else if (k == "TravThT") c->tune.th_t = v; else if (k == "TravThL") c->tune.th_l = v; else if (k == "TravThF") c->tune.th_f = v;
+    else if (k == "TravThNExit") c->tune.th_n_exit = v;
+    else if (k == "TraversalBlocksPerSM") { if (v < 1 || v > 16) return set_err("TraversalBlocksPerSM out of range [1,16]"); c->trav_blocks_per_sm = v; }
     else return set_err("unknown parameter key: " + k);
     return 0;
 }
@@ -198,7 +211,8 @@ int ctl_get_param_i(ctl_ctx* c, const char* key, int* v) {
     std::string k(key);
     if (k == "MaxPathLength") *v = c->max_path_length; else if (k == "RRStartDepth") *v = c->rr_start; else if (k == "Direct") *v = c->direct;
     else if (k == "Regularization") *v = c->regularization; else if (k == "SortMode") *v = c->sort_mode; else if (k == "StageTimers") *v = c->stage_timers;
-    else if (k == "CaptureBounce") *v = c->capture_bounce; else return set_err("unknown parameter key: " + k);
+    else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel;
+    else if (k == "TraversalBlocksPerSM") *v = c->trav_blocks_per_sm; else return set_err("unknown parameter key: " + k);
     return 0;
 }
 
@@ -251,6 +265,7 @@ int ctl_upload_samples(ctl_ctx* c, const float* d1, const float* d2) {
 // ------------------------------------------------------------------ intersect API
 static int grid_for(const ctl_ctx* c, int per_sm) { return c->n_sm * per_sm; }
 
+
 int ctl_intersect(ctl_ctx* c, int n, const void* d_rays, void* d_results, int any_hit, void* stream) {
     if (!c || !c->has_scene) return set_err("no scene uploaded");
     if (n < 0) return set_err("negative ray count");
@@ -259,9 +274,9 @@ int ctl_intersect(ctl_ctx* c, int n, const void* d_rays, void* d_results, int an
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     unsigned* work = c->counters.p + CTR_WORK + 2 * MAX_BOUNCES + 1;
     CK(cudaMemsetAsync(work, 0, sizeof(unsigned), st));
-    const int grid = grid_for(c, 8);
-    if (any_hit) k_intersect<2, true, false><<<grid, 128, 0, st>>>(c->scene, (const float4*)d_rays, nullptr, n, work, nullptr, nullptr, nullptr, nullptr, d_results, nullptr);
-    else k_intersect<2, false, false><<<grid, 128, 0, st>>>(c->scene, (const float4*)d_rays, nullptr, n, work, nullptr, nullptr, nullptr, nullptr, d_results, nullptr);
+    const int grid = grid_for(c, c->trav_blocks_per_sm);
+    if (any_hit) launch_intersect<2, true, false>(c, grid, st, c->scene, (const float4*)d_rays, nullptr, n, work, nullptr, nullptr, nullptr, nullptr, d_results, nullptr);
+    else launch_intersect<2, false, false>(c, grid, st, c->scene, (const float4*)d_rays, nullptr, n, work, nullptr, nullptr, nullptr, nullptr, d_results, nullptr);
     CK(cudaGetLastError());
     return 0;
 }
@@ -291,9 +306,9 @@ int ctl_trace_rays_host(ctl_ctx* c, int n, const ctl_traversal_ray* rays, ctl_tr
     CK(cudaMemcpyAsync(dr.p, rays, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream));
     unsigned* work = c->counters.p + CTR_WORK + 2 * MAX_BOUNCES + 1;
     CK(cudaMemsetAsync(work, 0, sizeof(unsigned), c->stream));
-    const int grid = grid_for(c, 8);
-    if (counts) k_intersect<3, false, true><<<grid, 128, 0, c->stream>>>(c->scene, dr.p, nullptr, n, work, nullptr, nullptr, nullptr, nullptr, dres.p, dcnt.p);
-    else k_intersect<3, false, false><<<grid, 128, 0, c->stream>>>(c->scene, dr.p, nullptr, n, work, nullptr, nullptr, nullptr, nullptr, dres.p, nullptr);
+    const int grid = grid_for(c, c->trav_blocks_per_sm);
+    if (counts) launch_intersect<3, false, true>(c, grid, c->stream, c->scene, dr.p, nullptr, n, work, nullptr, nullptr, nullptr, nullptr, dres.p, dcnt.p);
+    else launch_intersect<3, false, false>(c, grid, c->stream, c->scene, dr.p, nullptr, n, work, nullptr, nullptr, nullptr, nullptr, dres.p, nullptr);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(results, dres.p, (size_t)n * 20, cudaMemcpyDeviceToHost, c->stream));
     unsigned long long hc[4] = {0, 0, 0, 0};
@@ -352,7 +367,7 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
     unsigned* ctr = c->counters.p;
     PathState st = {c->cf.p, c->cl.p, c->nor.p, c->px.p};
     const int g_light = grid_for(c, 8);
-    const int g_trav = grid_for(c, 8);
+    const int g_trav = grid_for(c, c->trav_blocks_per_sm);
     uint32_t launches = 0;
     stage_mark(c, 0);
     k_generate<<<g_light, 256, 0, c->stream>>>(c->scene, W, st, c->rays_a.p, c->path_a.p, ctr + CTR_Q + 0);
@@ -365,15 +380,15 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
             CK(cudaMemcpyAsync(c->capture.p, rin, 32 * (size_t)W.n_slots, cudaMemcpyDeviceToDevice, c->stream));
             CK(cudaMemcpyAsync(c->d_captured_n.p, ctr + CTR_Q + b, sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
         }
-        if (c->instrumented) k_intersect<0, false, true><<<g_trav, 128, 0, c->stream>>>(c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, c->stats.p + 2);
-        else k_intersect<0, false, false><<<g_trav, 128, 0, c->stream>>>(c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, nullptr);
+        if (c->instrumented) launch_intersect<0, false, true>(c, g_trav, c->stream, c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, c->stats.p + 2);
+        else launch_intersect<0, false, false>(c, g_trav, c->stream, c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, nullptr);
         stage_mark(c, 2);
         Queues Q = {rin, pin, rout, pout, c->hit_a.p, c->hit_node.p, c->sh_rays.p, c->sh_payload.p};
         k_shade<<<g_light, 128, 0, c->stream>>>(c->scene, P, st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b);
         stage_mark(c, 3);
         if (c->direct) {
-            if (c->instrumented) k_intersect<1, true, true><<<g_trav, 128, 0, c->stream>>>(c->scene, c->sh_rays.p, ctr + CTR_SH + b, 0, ctr + CTR_WORK + 2 * b + 1, nullptr, nullptr, c->sh_payload.p, c->cl.p, nullptr, c->stats.p + 6);
-            else k_intersect<1, true, false><<<g_trav, 128, 0, c->stream>>>(c->scene, c->sh_rays.p, ctr + CTR_SH + b, 0, ctr + CTR_WORK + 2 * b + 1, nullptr, nullptr, c->sh_payload.p, c->cl.p, nullptr, nullptr);
+            if (c->instrumented) launch_intersect<1, true, true>(c, g_trav, c->stream, c->scene, c->sh_rays.p, ctr + CTR_SH + b, 0, ctr + CTR_WORK + 2 * b + 1, nullptr, nullptr, c->sh_payload.p, c->cl.p, nullptr, c->stats.p + 6);
+            else launch_intersect<1, true, false>(c, g_trav, c->stream, c->scene, c->sh_rays.p, ctr + CTR_SH + b, 0, ctr + CTR_WORK + 2 * b + 1, nullptr, nullptr, c->sh_payload.p, c->cl.p, nullptr, nullptr);
             launches++;
         }
         launches += 2;

@@ -64,6 +64,16 @@ struct Frame { V3 s, t, n; };
 CTL_DEV V3 to_local(const Frame& f, V3 v) { return mk(dot(v, f.s), dot(v, f.t), dot(v, f.n)); }
 CTL_DEV V3 to_world(const Frame& f, V3 v) { return f.s * v.x + f.t * v.y + f.n * v.z; }
 
+// 256-bit read-only global load (sm_100a LDG.E.256): one 64-byte BVH node = 2 of these = 2 L1 wavefronts per lane
+// instead of 4 with float4 loads.  `p` must be 32-byte aligned.
+struct F8 { float4 lo, hi; };
+CTL_DEV F8 ldg256(const void* p) {
+    F8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w) : "l"(p));
+    return r;
+}
+
 CTL_DEV float h2f(uint32_t h) { return __half2float(__ushort_as_half((unsigned short)(h & 0xffff))); }
 
 } // namespace ctld

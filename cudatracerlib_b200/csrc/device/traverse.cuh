@@ -66,10 +66,8 @@ CTL_DEV void traverse_level(const float4* __restrict__ nodes, int start, V3 o, V
     while (nodeAddr != SENT) {
         int leafAddr = 0;
         while ((unsigned)nodeAddr < (unsigned)SENT) {
-            const float4 n0xy = __ldg(nodes + nodeAddr + 0);
-            const float4 n1xy = __ldg(nodes + nodeAddr + 1);
-            const float4 nz = __ldg(nodes + nodeAddr + 2);
-            const float4 cn = __ldg(nodes + nodeAddr + 3);
+            const F8 nA = ldg256(nodes + nodeAddr), nB = ldg256(nodes + nodeAddr + 2);
+                const float4 n0xy = nA.lo, n1xy = nA.hi, nz = nB.lo, cn = nB.hi;
             if (COUNT) ((VisitCounters<true>&)cnt).inner++;
             int c0 = __float_as_int(cn.x), c1 = __float_as_int(cn.y);
             const float c0lox = fmaf(n0xy.x, idx, -oodx), c0hix = fmaf(n0xy.y, idx, -oodx);

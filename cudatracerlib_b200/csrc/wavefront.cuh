@@ -7,6 +7,7 @@
 // random-number bookkeeping are those of PathTrace.
 #pragma once
 #include "device/shading.cuh"
+#include "device/traverse_persistent.cuh"
 #include <cfloat>
 
 namespace ctld {
@@ -98,8 +99,11 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
 // MODE 1: wavefront shadow (any hit; unoccluded => cl[path] += pending)
 // MODE 2: API, 16-byte traversalResult, box/tri lower bound = ray.tmin  (== intersectKernel, TraceHelper.cu:326-734)
 // MODE 3: API, ctl_trace_result, t in (rayEps, FLT_MAX)                  (== traceRay, TraceHelper.cu:174-180)
+#ifndef CTL_SIMPLE_MIN_BLOCKS
+#define CTL_SIMPLE_MIN_BLOCKS 10
+#endif
 template <int MODE, bool ANY_HIT, bool COUNT>
-__global__ void __launch_bounds__(128) k_intersect(const __grid_constant__ DScene S, const float4* __restrict__ rays, const unsigned* __restrict__ n_ptr, int n_fixed,
+__global__ void __launch_bounds__(128, CTL_SIMPLE_MIN_BLOCKS) k_intersect_simple(const __grid_constant__ DScene S, const float4* __restrict__ rays, const unsigned* __restrict__ n_ptr, int n_fixed,
                                                     unsigned* work_ctr, float4* __restrict__ hit_a, uint32_t* __restrict__ hit_node,
                                                     const float4* __restrict__ sh_payload, float4* __restrict__ cl,
                                                     void* __restrict__ api_out, unsigned long long* visit_out) {
@@ -144,6 +148,24 @@ __global__ void __launch_bounds__(128) k_intersect(const __grid_constant__ DScen
             }
         }
     }
+    if (COUNT) {
+        VisitCounters<true>& c = (VisitCounters<true>&)cnt;
+        unsigned a = c.inner, b = c.tris, e = c.inst;
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); e += __shfl_xor_sync(0xffffffffu, e, o); }
+        if (lane_id() == 0) { atomicAdd(visit_out, (unsigned long long)a); atomicAdd(visit_out + 1, (unsigned long long)b); atomicAdd(visit_out + 2, (unsigned long long)e); }
+    }
+}
+
+// Production traversal kernel: persistent warps, phase-scheduled (device/traverse_persistent.cuh). Same MODEs as above.
+template <int MODE, bool ANY_HIT, bool COUNT>
+__global__ void __launch_bounds__(128) k_intersect(const __grid_constant__ DScene S, const __grid_constant__ TravTune tune, const float4* __restrict__ rays, const unsigned* __restrict__ n_ptr, int n_fixed,
+                                                    unsigned* work_ctr, float4* __restrict__ hit_a, uint32_t* __restrict__ hit_node,
+                                                    const float4* __restrict__ sh_payload, float4* __restrict__ cl,
+                                                    void* __restrict__ api_out, unsigned long long* visit_out) {
+    const int n = n_ptr ? (int)*n_ptr : n_fixed;
+    VisitCounters<COUNT> cnt;
+    TravOut out = {hit_a, hit_node, sh_payload, cl, api_out};
+    trace_persistent<MODE, ANY_HIT, COUNT>(S, rays, n, work_ctr, out, tune, cnt);
     if (COUNT) {
         VisitCounters<true>& c = (VisitCounters<true>&)cnt;
         unsigned a = c.inner, b = c.tris, e = c.inst;

@@ -237,7 +237,7 @@ struct Sampler {
 
 // ---- traversal -------------------------------------------------------------
 struct Hit { float dist, u, v; uint32_t tri, node; };
-struct Counters { uint64_t inner, tris, inst; };
+struct Counters { uint64_t inner, tris, inst; std::vector<uint8_t>* ev = nullptr; }; // ev: optional per-ray event string (N/I/T) for scheduling studies
 
 inline float guard_inv(float d) { // BVHTraversal.h:16-19
     const float ooeps = powf(2.0f, -80.0f);
@@ -259,7 +259,7 @@ inline bool traverse(const float* nodes4, int node_off4, int start, V3 o, V3 d, 
     while (nodeAddr != SENT) {
         while ((unsigned)nodeAddr < (unsigned)SENT) {
             const float* n = nodes4 + (size_t)(node_off4 + nodeAddr) * 4;
-            if (cnt) cnt->inner++;
+            if (cnt) { cnt->inner++; if (cnt->ev) cnt->ev->push_back('N'); }
             int c0, c1; memcpy(&c0, n + 12, 4); memcpy(&c1, n + 13, 4);
             float c0lox = fmaf(n[0], idx, -oodx), c0hix = fmaf(n[1], idx, -oodx), c0loy = fmaf(n[2], idy, -oody), c0hiy = fmaf(n[3], idy, -oody);
             float c0loz = fmaf(n[8], idz, -oodz), c0hiz = fmaf(n[9], idz, -oodz), c1loz = fmaf(n[10], idz, -oodz), c1hiz = fmaf(n[11], idz, -oodz);
@@ -314,7 +314,7 @@ bool trace(const ctl_scene_view& S, V3 ori, V3 dir, float tri_lo, float box_lo, 
     bool stop = false;
     return traverse((const float*)S.scene_bvh_nodes, 0, S.scene_start_node, ori, dir, box_lo, hit.dist, cnt, [&](int nodeIdx) {
         if (stop) return false;
-        if (cnt) cnt->inst++;
+        if (cnt) { cnt->inst++; if (cnt->ev) cnt->ev->push_back('I'); }
         const ctl_node& N = S.nodes[nodeIdx];
         const ctl_mesh& mesh = S.meshes[N.mesh_index];
         const float* inv = S.node_inv_xf + (size_t)nodeIdx * 16;
@@ -325,7 +325,7 @@ bool trace(const ctl_scene_view& S, V3 ori, V3 dir, float tri_lo, float box_lo, 
             for (int triAddr = triIdx;; triAddr++) {
                 const float* w = (const float*)S.woop + ((size_t)mesh.bvh_tri_offset + (size_t)triAddr * 3) * 4;
                 uint32_t index = S.tri_index[mesh.bvh_idx_offset + triAddr];
-                if (cnt) cnt->tris++;
+                if (cnt) { cnt->tris++; if (cnt->ev) cnt->ev->push_back('T'); }
                 float t, u, v;
                 if (woop_test(w, o, d, tri_lo, hit.dist, t, u, v)) {
                     hit.node = (uint32_t)nodeIdx; hit.tri = (index >> 1) + mesh.tri_offset; hit.u = u; hit.v = v; hit.dist = t;
@@ -964,6 +964,24 @@ void orc_path_probe(const ctl_scene_view* S, int w, int x, int y, int pass, int 
     PTParams P = {max_path_length, rr_start, direct};
     uint64_t r = 0; Spec c = path_trace(*S, o, d, rng, P, r, 0);
     rgb[0] = c.r; rgb[1] = c.g; rgb[2] = c.b; if (rays) *rays = r;
+}
+
+// Per-ray event strings ('N' inner node popped, 'I' instance leaf entered, 'T' triangle reference tested), in visit order,
+// concatenated; offsets[i]..offsets[i+1] delimit ray i. Returns the total length (call with events == NULL to size).
+// Used by scripts/sim_warp_schedule.py to study warp scheduling policies for the traversal kernel.
+long long orc_trace_events(const ctl_scene_view* S, int n, const ctl_traversal_ray* rays, int any_hit, uint8_t* events, long long capacity, long long* offsets) {
+    std::vector<uint8_t> ev; long long total = 0;
+    for (int i = 0; i < n; i++) {
+        ev.clear();
+        Counters c = {0, 0, 0, &ev};
+        Hit h; h.dist = rays[i].tmax; h.u = h.v = 0; h.tri = h.node = UINT_MAX;
+        trace(*S, mk(rays[i].o[0], rays[i].o[1], rays[i].o[2]), mk(rays[i].d[0], rays[i].d[1], rays[i].d[2]), rays[i].tmin, 0.0f, h, &c, any_hit != 0);
+        if (offsets) offsets[i] = total;
+        if (events && total + (long long)ev.size() <= capacity) memcpy(events + total, ev.data(), ev.size());
+        total += (long long)ev.size();
+    }
+    if (offsets) offsets[n] = total;
+    return total;
 }
 
 int orc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
