@@ -41,7 +41,6 @@ WORKLOADS = {
     "c4": ("c4", 1920, 1080, 8, 8, "procedural 1M-triangle clustered scene (999,854 tris) 1920x1080 8spp 8 bounces (configs[3])"),
     "c5": ("c5", 1920, 1080, 64, 32, "1M scene, microfacet mix, 32 bounces 64spp (configs[4])"),
 }
-TILE = 64
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -176,7 +175,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from cudatracerlib_b200 import Scene, PathTracer, traversal_bytes, build
+    from cudatracerlib_b200 import Scene, PathTracer, DistributedFrame, traversal_bytes, build, TILE
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -209,14 +208,16 @@ def main():
     host_img = torch.empty(h * w * 7, dtype=torch.float32, pin_memory=True)
     table_bytes = 4096 * 30 * 12
 
-    def frame(read_back):
-        for p in range(spp):
-            if world > 1:
-                tracer.DoPassTiled(TILE, TILE, rank, world, new_trace=(p == 0))
-            else:
-                tracer.DoPass(new_trace=(p == 0))
+    def render_pass(p, new_trace):
         if world > 1:
-            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+            tracer.DoPassTiled(TILE, TILE, rank, world, new_trace=new_trace)
+        else:
+            tracer.DoPass(new_trace=new_trace)
+
+    df = DistributedFrame(accum, render_pass, lambda: 0)
+
+    def frame(read_back):
+        df.frame(spp)  # spp passes on this rank's tiles + (N > 1) the one NCCL reduce of the accumulator, all on `stream`
         if read_back and rank == 0:
             host_img.copy_(accum, non_blocking=True)
 

@@ -1,0 +1,95 @@
+// b200_path_tracer.hpp -- header-only C++ adapter over the C ABI (ctl_b200.h), shaped like the reference's
+// `PathTracer : Tracer<true>` (Integrators/PathTracer.h:7-24, Kernel/Tracer.h:67-294) so that an application written
+// against CudaTracerLib's tracer interface can switch this path to the B200 backend:
+//
+//     reference                                   here
+//     ---------                                   ----
+//     PathTracer tracer;                          ctlb200::PathTracer tracer;
+//     tracer.Resize(w, h);                        tracer.Resize(w, h);
+//     tracer.InitializeScene(&scene);             tracer.InitializeScene(view);      // flat ctl_scene_view, see INTEGRATION.md
+//     tracer.getParameters() ... KEY_x()          tracer.setParameter("MaxPathLength", 8);
+//     tracer.DoPass(&image, newTrace);            tracer.DoPass(image, newTrace);    // image: PixelData[w*h] host buffer or nullptr
+//     tracer.getRaysInLastPass() ...              same names
+//
+// Errors: every failing ABI call is re-raised as std::runtime_error carrying the reference's
+// "In file ... at line ... : msg" text (ThrowCudaErrors convention, Defines.cpp:15-29).  No CPU fallback exists.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "ctl_b200.h"
+
+namespace ctlb200 {
+
+inline void check(int rc) { if (rc != 0) throw std::runtime_error(ctl_last_error()); }
+
+// RAII owner of a host scene built by the library's own builder (synthetic scenes / one user mesh).
+class Scene {
+public:
+    Scene(int kind, int width, int height, uint32_t seed = 1234, int n_hint = 0) : h_(ctl_scene_create(kind, width, height, seed, n_hint)) {
+        if (!h_) throw std::runtime_error(ctl_last_error());
+        check(ctl_scene_get_view(h_, &view_));
+    }
+    ~Scene() { ctl_scene_destroy(h_); }
+    Scene(const Scene&) = delete; Scene& operator=(const Scene&) = delete;
+    const ctl_scene_view& view() const { return view_; }
+private:
+    ctl_scene* h_; ctl_scene_view view_;
+};
+
+// == CudaTracerLib::PathTracer (progressive tracer; one DoPass = one path per pixel)
+class PathTracer {
+public:
+    explicit PathTracer(int device = 0) : device_(device) {}
+    ~PathTracer() { if (ctx_) ctl_destroy(ctx_); }
+    PathTracer(const PathTracer&) = delete; PathTracer& operator=(const PathTracer&) = delete;
+
+    // TracerBase::Resize (Kernel/Tracer.h:104-116)
+    void Resize(unsigned w, unsigned h) {
+        if (!ctx_) { ctx_ = ctl_create(device_, (int)w, (int)h); if (!ctx_) throw std::runtime_error(ctl_last_error()); apply_params(); }
+        else check(ctl_resize(ctx_, (int)w, (int)h));
+        w_ = w; h_ = h; new_trace_ = true;
+    }
+    // TracerBase::InitializeScene (Kernel/Tracer.h:100-103) + the scene half of UpdateKernel (Kernel/TraceHelper.cu:182-217)
+    void InitializeScene(const ctl_scene_view& view) { need_ctx(); check(ctl_upload_scene(ctx_, &view)); new_trace_ = true; }
+    // m_sParameters << KEY_Direct() / KEY_MaxPathLength() / KEY_RRStartDepth() / KEY_Regularization() (Integrators/PathTracer.h:10-20)
+    void setParameter(const std::string& key, int value) {
+        for (auto& kv : params_) if (kv.first == key) { kv.second = value; if (ctx_) check(ctl_set_param_i(ctx_, key.c_str(), value)); return; }
+        params_.emplace_back(key, value);
+        if (ctx_) check(ctl_set_param_i(ctx_, key.c_str(), value));
+    }
+    int getParameter(const std::string& key) { need_ctx(); int v = 0; check(ctl_get_param_i(ctx_, key.c_str(), &v)); return v; }
+    // Tracer<true>::DoPass (Kernel/Tracer.h:209-248).  `image` (optional) receives the PixelData accumulator after the pass,
+    // as Image::getPixelData would expose it (Engine/Image.h:10-29, 78-81); pass nullptr to keep it on the device.
+    void DoPass(ctl_pixel_data* image, bool a_NewTrace) {
+        need_ctx();
+        check(ctl_render_pass(ctx_, (a_NewTrace || new_trace_) ? 1 : 0, 0, 0, (int)w_, (int)h_));
+        new_trace_ = false;
+        if (image) check(ctl_read_accum(ctx_, image)); else check(ctl_synchronize(ctx_));
+    }
+    bool isMultiPass() const { return true; }
+    unsigned getNumPassesDone() { uint32_t p = 0; stats(nullptr, nullptr, nullptr, &p); return p; }
+    unsigned long long getRaysInLastPass() { uint64_t r = 0; stats(&r, nullptr, nullptr, nullptr); return r; }
+    float getLastTimeSpentRenderingSec() { float s = 0; stats(nullptr, &s, nullptr, nullptr); return s; }
+    unsigned long long getAccRays() { uint64_t r = 0; stats(nullptr, nullptr, &r, nullptr); return r; }
+    float getSplatScale() const { return 0.0f; } // the path tracer never splats (rgbSplat stays 0)
+    // __internal__IntersectBuffers (Kernel/TraceHelper.cu:736-746): device pointers, asynchronous on `stream`
+    void IntersectBuffers(int n, const ctl_traversal_ray* d_rays, ctl_traversal_result* d_results, bool any_hit, void* stream = nullptr) {
+        need_ctx(); check(ctl_intersect(ctx_, n, d_rays, d_results, any_hit ? 1 : 0, stream));
+    }
+    // TracerBase::TraceSingleRay (Kernel/Tracer.cu:74-78), batched; host buffers
+    std::vector<ctl_trace_result> TraceRays(const std::vector<ctl_traversal_ray>& rays) {
+        need_ctx(); std::vector<ctl_trace_result> out(rays.size());
+        check(ctl_trace_rays_host(ctx_, (int)rays.size(), rays.data(), out.data(), nullptr)); return out;
+    }
+    ctl_ctx* handle() { return ctx_; }
+private:
+    void need_ctx() const { if (!ctx_) throw std::runtime_error("PathTracer: call Resize(w, h) first"); }
+    void apply_params() { for (auto& kv : params_) check(ctl_set_param_i(ctx_, kv.first.c_str(), kv.second)); }
+    void stats(uint64_t* r, float* s, uint64_t* t, uint32_t* p) { need_ctx(); check(ctl_stats(ctx_, r, s, t, p)); }
+    int device_; ctl_ctx* ctx_ = nullptr; unsigned w_ = 0, h_ = 0; bool new_trace_ = true;
+    std::vector<std::pair<std::string, int>> params_;
+};
+
+} // namespace ctlb200

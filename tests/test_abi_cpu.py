@@ -204,3 +204,23 @@ def test_tile_owner_partition():
     own = ctl.tile_owner(100, 70, 16, 16, 3)
     assert own.shape == (70, 100) and set(np.unique(own)) == {0, 1, 2}
     assert own[0, 0] == 0 and own[0, 16] == 1 and own[0, 32] == 2 and own[16, 0] == (7 % 3)
+
+
+def _build_adapter_check(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "adapter_check")
+    libdir = os.path.dirname(api.LIB_PATH)
+    cmd = ["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "adapter_check.cpp"), "-o", exe, "-L" + libdir, "-lctl_b200", "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_cpp_adapter_compiles_and_fails_loudly_without_gpu(built_lib, tmp_path):
+    """include/b200_path_tracer.hpp (the Tracer<true>-shaped C++ adapter) builds against the C ABI with plain g++."""
+    import subprocess, torch
+    exe = _build_adapter_check(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    if not torch.cuda.is_available():
+        assert "no device" in r.stdout

@@ -273,3 +273,12 @@ def test_resize_and_scene_swap(built_lib, orc):
     assert img.shape == (40, 48)
     assert (rel_l2(img["rgb"], ref["rgb"]) <= 1e-3).mean() >= 0.99
     t.close()
+
+
+def test_cpp_adapter_renders(built_lib, tmp_path):
+    import subprocess
+    from test_abi_cpu import _build_adapter_check
+    exe = _build_adapter_check(tmp_path)
+    r = subprocess.run([exe, "gpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "passes 1" in r.stdout and "weight 4096" in r.stdout
