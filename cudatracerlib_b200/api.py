@@ -37,8 +37,8 @@ class Mesh(C.Structure):
 
 
 class Node(C.Structure):
-    _fields_ = [("mesh_index", C.c_uint32), ("material_offset", C.c_uint32), ("instanciated_material", C.c_uint32), ("lights", C.c_uint32 * 2),
-                ("n_lights", C.c_uint32)]
+    _fields_ = [("mesh_index", C.c_uint32), ("material_offset", C.c_uint32), ("instanciated_material", C.c_uint32), ("n_lights", C.c_uint32),
+                ("lights", C.c_uint32 * 2)]
 
 
 class Material(C.Structure):

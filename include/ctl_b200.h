@@ -61,13 +61,14 @@ typedef struct ctl_mesh {
     uint32_t mat_offset;      /* m_uStdMaterialOffset                  */
 } ctl_mesh;
 
-/* SceneTypes/Node.h:13-20; 24 B */
+/* SceneTypes/Node.h:13-20 with FixedSizeArray<unsigned,2,true,0xff> m_uLights = {length, buffer[2]}
+ * (Base/FixedSizeArray.h:107-109); 24 B.  Layout checked against the reference headers by oracle/ref_driver.cpp. */
 typedef struct ctl_node {
     uint32_t mesh_index;
     uint32_t material_offset;
     uint32_t instanciated_material;
-    uint32_t lights[2]; /* 0xffffffff = none */
     uint32_t n_lights;
+    uint32_t lights[2]; /* 0xffffffff = none */
 } ctl_node;
 
 /* Kernel/TraceHelper.h:55-59; 32 B */

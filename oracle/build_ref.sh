@@ -1,0 +1,64 @@
+#!/usr/bin/env bash
+# oracle/build_ref.sh -- builds oracle/_ref/libctl_ref.so: the REFERENCE's OWN host code for the hot path
+# (every hot-path function of CudaTracerLib is `inline __host__ __device__` with #ifndef ISCUDA branches),
+# compiled from the sources where they lie under /root/reference.  TEST INFRASTRUCTURE: used to validate the CPU
+# restatement (oracle/oracle.cpp) and as the "reference" CPU baseline of bench.py.  Outputs only into oracle/_ref/
+# (git-ignored).  Nothing from the reference tree is copied into the repository; a scratch copy under $TMPDIR receives
+# the few mechanical patches the 2017-era sources need with g++ 13 / CUDA 12 headers:
+#   1. Base/VirtualFuncType.h:96-103  `obj->Is<T>()` -> `obj->template Is<T>()` (dependent-name syntax, MSVC-only as shipped)
+#   2. Math/half.h                     missing <cstring> (forced with -include); host ToFloat() decodes per IEEE like the device's __half2float
+#                                      (the shipped host branch maps +-0 to +-2^-15; the GPU path is the parity target)
+#   3. Math/Spectrum.cu:729            cudaMemcpyToSymbol of the static CIE table (device-only) commented out
+#   4. Integrators/PathTracer.cu       lines 1-170 only (PathTrace<DIRECT>; the __global__ kernel and <<<>>> launch are CUDA-only)
+#   5. Engine/Image.cu                 lines 1-86 only (AddSample/Splat/Clear; the luminance kernel is CUDA-only); Image.cpp ctor lines 12-30
+# traceRay / fillDG / the scene globals live in Kernel/TraceHelper.cu between texture<> declarations that CUDA 12 removed;
+# oracle/ref_driver.cpp provides them from the file's host branches on top of the reference's own TracerayTemplate.
+set -euo pipefail
+REF=${CTL_REFERENCE:-/root/reference}
+HERE="$(cd "$(dirname "$0")" && pwd)"
+OUT="$HERE/_ref"
+SCR="${TMPDIR:-/tmp}/ctl_ref_build_$$"
+CUDA_INC=${CUDA_INC:-/usr/local/cuda/include}
+[ -d "$REF/Kernel" ] || { echo "reference tree not found at $REF"; exit 3; }
+if [ -f "$OUT/libctl_ref.so" ] && [ "$OUT/libctl_ref.so" -nt "$HERE/ref_driver.cpp" ] && [ "$OUT/libctl_ref.so" -nt "$HERE/build_ref.sh" ]; then echo "$OUT/libctl_ref.so up to date"; exit 0; fi
+mkdir -p "$OUT" "$SCR/obj"
+trap 'rm -rf "$SCR"' EXIT
+cp -r "$REF"/Base "$REF"/Engine "$REF"/Integrators "$REF"/Kernel "$REF"/Math "$REF"/SceneTypes "$REF"/*.h "$SCR"/
+chmod -R u+w "$SCR"
+cd "$SCR"
+sed -i 's/obj->Is<T>()/obj->template Is<T>()/g; s/obj->As<T>()/obj->template As<T>()/g' Base/VirtualFuncType.h
+python3 - <<'PY'
+import re
+p = "Math/half.h"; s = open(p).read()
+old = """		int fltInt32 = ((val & 0x8000) << 16);
+		fltInt32 |= ((val & 0x7fff) << 13) + 0x38000000;
+
+		float fRet;
+		memcpy(&fRet, &fltInt32, sizeof(float));
+		return fRet;"""
+new = """		/* oracle/build_ref.sh patch 2: IEEE decode (== device __half2float) */
+		int e = (val >> 10) & 31, m = val & 1023; float v;
+		if (e == 0) v = ldexpf((float)m, -24); else if (e == 31) v = m ? NAN : INFINITY; else v = ldexpf((float)(m | 1024), e - 25);
+		return (val & 0x8000) ? -v : v;"""
+assert old in s, "half.h host ToFloat not found"
+open(p, "w").write(s.replace(old, new))
+p = "Math/Spectrum.cu"; s = open(p).read()
+s2 = s.replace("ThrowCudaErrors(cudaMemcpyToSymbol(device, &host, sizeof(staticData)));", "/* device-only upload removed (oracle/build_ref.sh patch 3) */")
+assert s2 != s; open(p, "w").write(s2)
+PY
+sed -n '1,170p' Integrators/PathTracer.cu > Integrators/PathTracer_host.inc; echo "}" >> Integrators/PathTracer_host.inc
+sed -n '1,86p' Engine/Image.cu > Engine/Image_host.cu; echo "}" >> Engine/Image_host.cu
+{ echo '#include "Image.h"'; echo '#include <Base/CudaMemoryManager.h>'; echo 'namespace CudaTracerLib {'; sed -n '12,30p' Engine/Image.cpp; echo '}'; } > Engine/Image_ctor.cpp
+CXXFLAGS="-std=c++17 -x c++ -include cstring -include cmath -fpermissive -w -O2 -fPIC -ffp-contract=off -pthread -I$SCR -I$CUDA_INC -I$HERE/../include"
+TUS="SceneTypes/BSDF_Simple.cu SceneTypes/BSDF_Complex.cu SceneTypes/Light.cu Engine/ShapeSet.cu Kernel/TraceAlgorithms.cu Engine/KernelDynamicScene.cu Kernel/TraceResult.cu SceneTypes/Sensor.cu Engine/MicrofacetDistribution.cu Base/CudaRandom.cu Engine/TriIntersectorData.cu Engine/DifferentialGeometry.cu SceneTypes/Samples.cu Engine/Material.cu SceneTypes/Volumes.cu SceneTypes/PhaseFunction.cu Math/FresnelHelper.cu Base/Platform.cu SceneTypes/Texture.cu Engine/RoughTransmittance.cu Math/MonteCarlo.cu Engine/TriangleData.cu Math/Spectrum.cu Engine/Image_host.cu Engine/Image_ctor.cpp"
+pids=()
+for f in $TUS; do
+  o="obj/$(echo "$f" | tr '/' '_').o"
+  ( g++ $CXXFLAGS -c "$f" -o "$o" ) &
+  pids+=($!)
+  if [ ${#pids[@]} -ge 8 ]; then wait "${pids[0]}"; pids=("${pids[@]:1}"); fi
+done
+for p in "${pids[@]}"; do wait "$p"; done
+g++ $CXXFLAGS -c "$HERE/ref_driver.cpp" -o obj/ref_driver.o
+g++ -shared -pthread -o "$OUT/libctl_ref.so" obj/*.o -Wl,-z,defs -lm
+echo "built $OUT/libctl_ref.so"

@@ -4,10 +4,15 @@
 // cpu_baseline / --impl reference legs may load this library; the product
 // (cudatracerlib_b200/) never links, imports or calls it.
 //
-// Parity status: the reference ships no tests / golden vectors, so this
-// restatement is pinned against (a) the known-answer values SURVEY Appendix C records from
-// running the reference's own host code (tests/test_oracle_kat.py) and (b) oracle/_ref,
-// a build of the reference's own sources (oracle/build_ref.sh), where that exists.
+// Parity status: PINNED.  The reference ships no tests / golden vectors, so this
+// restatement is pinned against outputs of the reference itself run here:
+//  (a) oracle/_ref -- the reference's OWN host code for this path (BVH traversal template, PathTrace<DIRECT>,
+//      BSDFs, light, sensor, sampler, XORWOW, Image::AddSample) compiled from /root/reference by oracle/build_ref.sh;
+//      tests/test_golden_cpu.py::test_oracle_vs_live_reference compares the two live where _ref exists;
+//  (b) tests/golden/reference_golden.npz -- vectors minted from (a) by tests/golden/make_golden.py (committed), checked by
+//      tests/test_golden_cpu.py on every box: RNG / sample tables / Woop encoding bit-exact, traversal indices identical,
+//      BSDF tables to 2e-5, same-seed images to 1e-3;
+//  (c) the known-answer values of SURVEY Appendix C (tests/test_oracle_kat.py).
 //
 // Each function cites the reference file:line (relative to the CudaTracerLib tree) it follows.
 // Independent code: nothing here includes product sources except the public C header for

@@ -1,0 +1,331 @@
+// oracle/ref_driver.cpp -- glue that runs the REFERENCE's own host code (CudaTracerLib, compiled by oracle/build_ref.sh
+// from /root/reference) on the flat scene view of include/ctl_b200.h.
+//
+// TEST INFRASTRUCTURE ONLY (see oracle/oracle.cpp header): loaded by tests/ref_binding.py to validate the CPU restatement
+// and by bench.py's cpu_baseline / --impl reference legs.  The product never links or loads it.
+//
+// What is the reference's code here: TracerayTemplate (BVH traversal), PathTrace<DIRECT> (Integrators/PathTracer.cu:10-113),
+// UniformSampleOneLight/EstimateDirect, TraceResult::getBsdfSample, TriangleData::fillDG, BSDFALL (diffuse, roughconductor,
+// dielectric), MicrofacetDistribution, DiffuseLight, ShapeSet::SamplePosition, PerspectiveSensor::sampleRayDifferential,
+// SequenceSampler + SamplingSequenceGeneratorHost + CudaRNG (XORWOW), Image::AddSample.
+// What is written here (the parts of Kernel/TraceHelper.cu that sit between CUDA-12-removed texture<> declarations):
+// the scene/sampler globals, traceRay's two leaf callbacks (host branch of TraceHelper.cu:88-180) and fillDG's host branch
+// (TraceHelper.cu:274-307), plus the packing of ctl_scene_view into KernelDynamicScene.
+#include <Kernel/TraceHelper.h>
+#include <Kernel/TraceAlgorithms.h>
+#include <Kernel/Sampler.h>
+#include <Engine/Mesh.h>
+#include <Engine/TriangleData.h>
+#include <Engine/Material.h>
+#include <Engine/TriIntersectorData.h>
+#include <Engine/ShapeSet.h>
+#include <Engine/Image.h>
+#include <SceneTypes/Node.h>
+#include <SceneTypes/Light.h>
+#include <SceneTypes/Sensor.h>
+#include <SceneTypes/BSDF.h>
+#include <Engine/SpatialStructures/BVH/BVHTraversal.h>
+#include <Base/CudaMemoryManager.h>
+#include <Base/Platform.h>
+#include <thread>
+#include <vector>
+#include <atomic>
+#include <mutex>
+#include <cstring>
+#include <cstdlib>
+#include <cstddef>
+#include "ctl_b200.h"
+
+// ---- CUDA runtime entry points used by host-side buffers: plain host memory (no GPU involved) -----------------
+extern "C" {
+cudaError_t cudaMemcpy(void* dst, const void* src, size_t n, cudaMemcpyKind) { memcpy(dst, src, n); return cudaSuccess; }
+cudaError_t cudaMemset(void* dst, int v, size_t n) { memset(dst, v, n); return cudaSuccess; }
+const char* cudaGetErrorString(cudaError_t) { return "cuda stub"; }
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n ? n : 1); return cudaSuccess; }
+}
+
+namespace CudaTracerLib {
+
+std::map<void*, CudaMemoryEntry> CudaMemoryManager::alloced_entries;
+std::vector<CudaMemoryEntry> CudaMemoryManager::freed_entries;
+cudaError_t CudaMemoryManager::Cuda_malloc_managed(void** v, size_t i, const std::string&) { *v = malloc(i ? i : 1); return cudaSuccess; }
+cudaError_t CudaMemoryManager::Cuda_free_managed(void* v, const std::string&) { free(v); return cudaSuccess; }
+
+// ---- globals of Kernel/TraceHelper.cu:23-32 --------------------------------------------------------------------
+KernelDynamicScene g_SceneDataHost;
+unsigned int g_RayTracedCounterHost;
+CudaStaticWrapper<SamplerData> g_SamplerDataHost;
+
+// ---- traceRay: host branch of Kernel/TraceHelper.cu:88-180 on the pointer overload of TracerayTemplate -----------
+bool traceRay(const Vec3f& dir, const Vec3f& ori, TraceResult* a_Result)
+{
+	Platform::Increment(&g_RayTracedCounter);
+	if (!g_SceneData.m_sNodeData.UsedCount)
+		return false;
+	float rayEps = g_SceneData.m_rayTraceEps;
+	return TracerayTemplate(Ray(ori, dir), a_Result->m_fDist, [&](int nodeIdx)
+	{
+		Node* N = g_SceneData.m_sNodeData.Data + nodeIdx;
+		KernelMesh mesh = g_SceneData.m_sMeshData[N->m_uMeshIndex];
+		unsigned int meshBvhTriOff = mesh.m_uBVHTriangleOffset, meshBvhIndOff = mesh.m_uBVHIndicesOffset, meshTriOff = mesh.m_uTriangleOffset;
+		float4x4 modl = g_SceneData.m_sSceneBVH.m_pInvNodeTransforms[nodeIdx];
+		Vec3f d = modl.TransformDirection(dir), o = modl.TransformPoint(ori);
+		return TracerayTemplate(Ray(o, d), a_Result->m_fDist, [&](int triIdx)
+		{
+			bool found = false;
+			for (int triAddr = triIdx;; triAddr++)
+			{
+				Vec4f* dat = (Vec4f*)g_SceneData.m_sBVHIntData.Data;
+				const Vec4f v00 = dat[meshBvhTriOff + triAddr * 3 + 0];
+				const Vec4f v11 = dat[meshBvhTriOff + triAddr * 3 + 1];
+				const Vec4f v22 = dat[meshBvhTriOff + triAddr * 3 + 2];
+				unsigned int index = g_SceneData.m_sBVHIndexData.Data[meshBvhIndOff + triAddr].index;
+				float Oz = v00.w - o.x*v00.x - o.y*v00.y - o.z*v00.z;
+				float invDz = 1.0f / (d.x*v00.x + d.y*v00.y + d.z*v00.z);
+				float t = Oz * invDz;
+				if (t > rayEps && t < a_Result->m_fDist)
+				{
+					float Ox = v11.w + o.x*v11.x + o.y*v11.y + o.z*v11.z;
+					float Dx = d.x*v11.x + d.y*v11.y + d.z*v11.z;
+					float u = Ox + t*Dx;
+					if (u >= 0.0f)
+					{
+						float Oy = v22.w + o.x*v22.x + o.y*v22.y + o.z*v22.z;
+						float Dy = d.x*v22.x + d.y*v22.y + d.z*v22.z;
+						float v = Oy + t*Dy;
+						if (v >= 0.0f && u + v <= 1.0f)
+						{
+							a_Result->m_nodeIdx = nodeIdx;
+							a_Result->m_triIdx = (index >> 1) + meshTriOff;
+							a_Result->m_fBaryCoords = Vec2f(u, v);
+							a_Result->m_fDist = t;
+							found = true;
+						}
+					}
+				}
+				if (index & 1)
+					break;
+			}
+			return found;
+		}, g_SceneData.m_sBVHNodeData.Data, (const BVHNodeData*)0, mesh.m_uBVHNodeOffset, 0);
+	}, g_SceneData.m_sSceneBVH.m_pNodes, (const BVHNodeData*)0, 0, g_SceneData.m_sSceneBVH.m_sStartNode);
+}
+
+// ---- fillDG: host branch of Kernel/TraceHelper.cu:274-307 --------------------------------------------------------
+void fillDG(const Vec2f& bary, unsigned int triIdx, unsigned int nodeIdx, DifferentialGeometry& dg)
+{
+	float4x4 localToWorld = g_SceneData.m_sSceneBVH.m_pNodeTransforms[nodeIdx];
+	dg.bary = bary;
+	dg.hasUVPartials = false;
+	g_SceneData.m_sTriData[triIdx].fillDG(localToWorld, dg);
+}
+
+} // namespace CudaTracerLib
+
+// ---- stubs for subsystems off the hot path that the compiled TUs reference ---------------------------
+#include "ref_stubs.inc"
+
+#include <Integrators/PathTracer_host.inc>   // the reference's PathTrace<DIRECT> (Integrators/PathTracer.cu:1-170)
+
+using namespace CudaTracerLib;
+
+namespace {
+
+struct ShapeSetMirror { unsigned int areaIdx, areaLen, triIdx, triLen; float sumArea; unsigned int count; }; // Engine/ShapeSet.h:47-52
+static_assert(sizeof(ShapeSetMirror) == sizeof(ShapeSet), "ShapeSet layout");
+static_assert(sizeof(BVHNodeData) == sizeof(ctl_bvh_node) && sizeof(TriIntersectorData) == sizeof(ctl_woop_tri) && sizeof(TriangleData) == sizeof(ctl_tri_data) &&
+              sizeof(KernelMesh) == sizeof(ctl_mesh) && sizeof(Node) == sizeof(ctl_node) && sizeof(ShapeSet::triData) == sizeof(ctl_light_tri) &&
+              sizeof(PixelData) == sizeof(ctl_pixel_data) && sizeof(float4x4) == 64, "data-surface layouts must be byte-identical");
+static_assert(offsetof(Node, m_uLights) == offsetof(ctl_node, n_lights) && offsetof(KernelMesh, m_uStdMaterialOffset) == offsetof(ctl_mesh, mat_offset) &&
+              offsetof(ShapeSet::triData, area) == offsetof(ctl_light_tri, area) && offsetof(PixelData, weightSum) == offsetof(ctl_pixel_data, weight_sum), "field offsets");
+
+struct RefScene {
+	std::vector<Material> mats; std::vector<Light> lights; std::vector<char> anim; std::vector<float> lightPdf;
+};
+RefScene* g_scene = nullptr;
+SamplingSequenceGeneratorHost<IndependantSamplingSequenceGenerator>* g_gen = nullptr;
+unsigned g_passes_generated = 0;
+std::mutex g_mutex;
+
+void pack_scene(const ctl_scene_view& v)
+{
+	delete g_scene; g_scene = new RefScene();
+	RefScene& R = *g_scene;
+	KernelDynamicScene& K = g_SceneDataHost;
+	memset((void*)&K, 0, sizeof(K));
+	K.m_sTriData = {(TriangleData*)v.tri_data, v.n_tri_data, v.n_tri_data};
+	K.m_sBVHIntData = {(TriIntersectorData*)v.woop, v.n_woop, v.n_woop};
+	K.m_sBVHNodeData = {(BVHNodeData*)v.bvh_nodes, v.n_bvh_nodes, v.n_bvh_nodes};
+	K.m_sBVHIndexData = {(TriIntersectorData2*)v.tri_index, v.n_tri_index, v.n_tri_index};
+	K.m_sMeshData = {(KernelMesh*)v.meshes, v.n_meshes, v.n_meshes};
+	K.m_sNodeData = {(Node*)v.nodes, v.n_nodes, v.n_nodes};
+	K.m_sSceneBVH.m_sStartNode = v.scene_start_node; K.m_sSceneBVH.m_uNumNodes = v.n_scene_bvh_nodes;
+	K.m_sSceneBVH.m_pNodes = (BVHNodeData*)v.scene_bvh_nodes;
+	K.m_sSceneBVH.m_pNodeTransforms = (float4x4*)v.node_xf; K.m_sSceneBVH.m_pInvNodeTransforms = (float4x4*)v.node_inv_xf;
+	K.m_uEnvMapIndex = UINT_MAX;
+	K.m_sBox = AABB(Vec3f(v.box_min[0], v.box_min[1], v.box_min[2]), Vec3f(v.box_max[0], v.box_max[1], v.box_max[2]));
+	K.doAlphaMapping = false;
+	K.m_rayTraceEps = v.ray_eps;
+	// materials: ctl_material -> Material with the reference's own BSDF objects
+	R.mats.resize(v.n_materials);
+	for (unsigned i = 0; i < v.n_materials; i++) {
+		const ctl_material& m = v.materials[i];
+		Material M("m");
+		M.NodeLightIndex = m.node_light_index;
+		Spectrum refl(m.reflectance[0], m.reflectance[1], m.reflectance[2]);
+		if (m.bsdf_type == CTL_BSDF_DIFFUSE) M.bsdf.SetData(diffuse(CreateTexture(refl)));
+		else if (m.bsdf_type == CTL_BSDF_ROUGHCONDUCTOR)
+			M.bsdf.SetData(roughconductor(m.distr_type == CTL_DISTR_GGX ? MicrofacetDistribution::EGGX : MicrofacetDistribution::EBeckmann,
+			                              Spectrum(m.eta[0], m.eta[1], m.eta[2]), Spectrum(m.k[0], m.k[1], m.k[2]),
+			                              CreateTexture(Spectrum(m.alpha_u)), CreateTexture(Spectrum(m.alpha_v)), CreateTexture(refl)));
+		else M.bsdf.SetData(dielectric(m.eta[0], refl, Spectrum(m.transmittance)));
+		M.bsdf.As()->m_enableTwoSided = (m.flags & CTL_MAT_TWO_SIDED) != 0;
+		R.mats[i] = M;
+	}
+	K.m_sMatData = {R.mats.data(), v.n_materials, v.n_materials};
+	// m_sAnimData: per light [area CDF (count+1 floats) | triData[count]] as ShapeSet expects (Engine/ShapeSet.cu:31-34)
+	R.lights.resize(v.n_lights_buf);
+	size_t total = 0;
+	for (unsigned i = 0; i < v.n_lights_buf; i++) total += ((v.lights[i].count + 1) * 4 + 15) / 16 * 16 + (size_t)v.lights[i].count * 64;
+	R.anim.assign(total + 64, 0);
+	char* base = (char*)(((uintptr_t)R.anim.data() + 15) & ~(uintptr_t)15);
+	size_t off = 0;
+	for (unsigned i = 0; i < v.n_lights_buf; i++) {
+		const ctl_light& L = v.lights[i];
+		ShapeSetMirror sm; sm.areaIdx = (unsigned)off; sm.areaLen = (L.count + 1) * 4;
+		memcpy(base + off, v.light_cdf_data + L.cdf_offset, sm.areaLen); off += (sm.areaLen + 15) / 16 * 16;
+		sm.triIdx = (unsigned)off; sm.triLen = L.count * 64;
+		memcpy(base + off, v.light_tris + L.tri_offset, sm.triLen); off += sm.triLen;
+		sm.sumArea = L.sum_area; sm.count = L.count;
+		ShapeSet ss; memcpy((void*)&ss, &sm, sizeof(sm));
+		Light l; l.SetData(DiffuseLight(Spectrum(L.radiance[0], L.radiance[1], L.radiance[2]), ss, L.node_idx));
+		R.lights[i] = l;
+	}
+	K.m_sAnimData = {base, (unsigned)off, (unsigned)off};
+	K.m_sLightBuf = {R.lights.data(), v.n_lights_buf, v.n_lights_buf};
+	K.m_numLights = v.num_lights;
+	R.lightPdf.assign(v.n_lights_buf ? v.n_lights_buf : 1, 0.0f);
+	for (unsigned i = 0; i < v.num_lights; i++) {
+		K.m_pLightIndices[i] = v.light_indices[i]; K.m_pLightCDF[i] = v.light_cdf[i];
+		R.lightPdf[v.light_indices[i]] = v.light_cdf[i] - (i ? v.light_cdf[i - 1] : 0.0f);
+	}
+	K.m_pLightPDF = R.lightPdf.data();
+	// camera: PerspectiveSensor with the matrices of the view (SceneTypes/Sensor.cu:76-96)
+	PerspectiveSensor ps((int)v.camera.resolution[0], (int)v.camera.resolution[1], 60.0f);
+	memcpy((void*)&ps.m_sampleToCamera, v.camera.sample_to_camera, 64);
+	ps.m_cameraToSample = ps.m_sampleToCamera.inverse();
+	memcpy((void*)&ps.toWorld, v.camera.to_world, 64);
+	ps.m_invResolution = Vec2f(v.camera.inv_resolution[0], v.camera.inv_resolution[1]);
+	ps.m_dx = ps.m_sampleToCamera.TransformPoint(Vec3f(ps.m_invResolution.x, 0.0f, 0.0f)) - ps.m_sampleToCamera.TransformPoint(Vec3f(0.0f));
+	ps.m_dy = ps.m_sampleToCamera.TransformPoint(Vec3f(0.0f, ps.m_invResolution.y, 0.0f)) - ps.m_sampleToCamera.TransformPoint(Vec3f(0.0f));
+	K.m_Camera.SetData(ps);
+}
+
+} // namespace
+
+extern "C" {
+
+int ref_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+// Renders passes [pass_first, pass_first + n_passes) of the window into img (PixelData[w*h], accumulated) with the reference's
+// PathTrace<DIRECT>; body of pathKernel2 (Integrators/PathTracer.cu:184-193) looped over the pixels.  Returns the ray count
+// (g_RayTracedCounterHost, every traceRay call).
+unsigned long long ref_render(const ctl_scene_view* view, int w, int h, int x0, int y0, int x1, int y1, int pass_first, int n_passes,
+                              int max_path_length, int rr_start, int direct, ctl_pixel_data* img, int n_threads)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	pack_scene(*view);
+	static bool sampler_init = false;
+	if (!sampler_init) { new (&(*g_SamplerDataHost)) SamplerData(4096, 30); sampler_init = true; } // Kernel/TraceHelper.cu:257
+	// fresh tracer: sample stream restarts; batches before pass_first are generated and discarded
+	delete g_gen; g_gen = new SamplingSequenceGeneratorHost<IndependantSamplingSequenceGenerator>();
+	for (int p = 0; p < pass_first; p++) g_gen->Compute(*g_SamplerDataHost);
+	g_RayTracedCounterHost = 0;
+	Image I(w, h);
+	I.Clear();
+	for (int yy = 0; yy < h; yy++) for (int xx = 0; xx < w; xx++) memcpy((void*)&I.getPixelData(xx, yy), &img[yy * w + xx], sizeof(PixelData));
+	if (n_threads < 1) n_threads = 1;
+	struct Smp { float x, y; Spectrum L; };
+	for (int p = 0; p < n_passes; p++) {
+		g_gen->Compute(*g_SamplerDataHost);
+		std::vector<std::vector<Smp>> per_row((size_t)(y1 - y0));
+		std::atomic<int> next(y0);
+		auto work = [&]() {
+			for (;;) {
+				int y = next.fetch_add(1);
+				if (y >= y1) break;
+				std::vector<Smp>& out = per_row[(size_t)(y - y0)];
+				out.reserve((size_t)(x1 - x0));
+				for (int x = x0; x < x1; x++) {
+					auto rng = g_SamplerData((unsigned)(y * w + x));
+					NormalizedT<Ray> r, rX, rY;
+					Vec2f pX = Vec2f((float)x, (float)y) + rng.randomFloat2();
+					Spectrum imp = g_SceneData.sampleSensorRay(r, rX, rY, pX, rng.randomFloat2());
+					Spectrum col = imp * (direct ? PathTrace<true>(r, rX, rY, rng, max_path_length, rr_start) : PathTrace<false>(r, rX, rY, rng, max_path_length, rr_start));
+					out.push_back({pX.x, pX.y, col});
+				}
+			}
+		};
+		std::vector<std::thread> th;
+		for (int t = 1; t < n_threads; t++) th.emplace_back(work);
+		work();
+		for (auto& t : th) t.join();
+		for (auto& row : per_row) for (auto& s : row) I.AddSample(s.x, s.y, s.L); // the reference's Image::AddSample, in pixel order
+	}
+	for (int yy = 0; yy < h; yy++) for (int xx = 0; xx < w; xx++) memcpy(&img[yy * w + xx], (void*)&I.getPixelData(xx, yy), sizeof(PixelData));
+	I.Free();
+	return g_RayTracedCounterHost;
+}
+
+// traceRay on a batch (t in (rayEps, FLT_MAX)); out: ctl_trace_result
+void ref_trace_rays(const ctl_scene_view* view, int n, const ctl_traversal_ray* rays, ctl_trace_result* out)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	pack_scene(*view);
+	for (int i = 0; i < n; i++) {
+		TraceResult r2 = traceRay(Ray(Vec3f(rays[i].o[0], rays[i].o[1], rays[i].o[2]), Vec3f(rays[i].d[0], rays[i].d[1], rays[i].d[2])));
+		out[i].dist = r2.m_fDist; out[i].u = r2.m_fBaryCoords.x; out[i].v = r2.m_fBaryCoords.y; out[i].tri_idx = r2.m_triIdx; out[i].node_idx = r2.m_nodeIdx;
+	}
+}
+
+// Known-answer probes of the reference's own math (regenerates SURVEY Appendix C)
+void ref_xorwow_floats(unsigned int seed_subsequence, int n, float* out) { CudaRNG rng(seed_subsequence); for (int i = 0; i < n; i++) out[i] = rng.randomFloat(); }
+void ref_woop_setdata(const float* v0, const float* v1, const float* v2, float* out12) {
+	TriIntersectorData T; T.setData(Vec3f(v0[0], v0[1], v0[2]), Vec3f(v1[0], v1[1], v1[2]), Vec3f(v2[0], v2[1], v2[2])); memcpy(out12, &T, 48);
+}
+void ref_sample_tables(unsigned int pass, float* d1, float* d2) {
+	std::lock_guard<std::mutex> lock(g_mutex);
+	static bool sampler_init = false;
+	SamplingSequenceGeneratorHost<IndependantSamplingSequenceGenerator> gen;
+	static SamplerData* data = nullptr;
+	if (!data) data = new SamplerData(4096, 30);
+	for (unsigned p = 0; p <= pass; p++) gen.Compute(*data);
+	for (unsigned s = 0; s < 4096; s++) for (unsigned i = 0; i < 30; i++) {
+		d1[i * 4096 + s] = data->getSequenceElement1(s, i);
+		Vec2f q = data->getSequenceElement2(s, i); d2[(i * 4096 + s) * 2] = q.x; d2[(i * 4096 + s) * 2 + 1] = q.y;
+	}
+	(void)sampler_init;
+}
+// BSDFALL::sample / f / pdf of a ctl_material at a local wi (identity frame): out9 = weight rgb, pdf, wo xyz, sampledType, eta
+void ref_bsdf_probe(const ctl_material* m, const float* wi, float sx, float sy, float* out9, float* f3, float* pdf1) {
+	std::lock_guard<std::mutex> lock(g_mutex);
+	ctl_scene_view v; memset(&v, 0, sizeof(v)); v.materials = m; v.n_materials = 1; v.camera.resolution[0] = v.camera.resolution[1] = 16;
+	v.camera.inv_resolution[0] = v.camera.inv_resolution[1] = 1.0f / 16; for (int i = 0; i < 4; i++) { v.camera.sample_to_camera[i * 5] = 1; v.camera.to_world[i * 5] = 1; }
+	pack_scene(v);
+	BSDFSamplingRecord bRec;
+	DifferentialGeometry& dg = bRec.dg;
+	dg.P = Vec3f(0); dg.sys = Frame(NormalizedT<Vec3f>(1, 0, 0), NormalizedT<Vec3f>(0, 1, 0), NormalizedT<Vec3f>(0, 0, 1)); dg.n = NormalizedT<Vec3f>(0, 0, 1); dg.uv[0] = Vec2f(0);
+	bRec.wi = NormalizedT<Vec3f>(wi[0], wi[1], wi[2]); bRec.mode = ERadiance; bRec.typeMask = EAll; bRec.sampledType = 0; bRec.eta = 1.0f;
+	float pdf = 0;
+	Spectrum w = g_scene->mats[0].bsdf.sample(bRec, pdf, Vec2f(sx, sy));
+	float r, g, b; w.toLinearRGB(r, g, b);
+	out9[0] = r; out9[1] = g; out9[2] = b; out9[3] = pdf; out9[4] = bRec.wo.x; out9[5] = bRec.wo.y; out9[6] = bRec.wo.z; out9[7] = (float)bRec.sampledType; out9[8] = bRec.eta;
+	bRec.typeMask = EAll;
+	Spectrum f = g_scene->mats[0].bsdf.f(bRec); f.toLinearRGB(f3[0], f3[1], f3[2]);
+	*pdf1 = g_scene->mats[0].bsdf.pdf(bRec);
+}
+
+} // extern "C"

@@ -1,0 +1,69 @@
+"""ctypes binding of oracle/_ref/libctl_ref.so -- the REFERENCE's own host code (built by oracle/build_ref.sh where
+/root/reference is mounted; the prebuilt .so travels to the GPU box).  TEST INFRASTRUCTURE, same rules as oracle/."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from cudatracerlib_b200.api import RAY_DTYPE, TRACE_RESULT_DTYPE, PIXEL_DTYPE
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libctl_ref.so")
+_lib = None
+
+
+def available():
+    return os.path.exists(REF_LIB)
+
+
+def ref():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(REF_LIB)
+        L.ref_render.restype = C.c_ulonglong
+        L.ref_render.argtypes = [C.c_void_p] + [C.c_int] * 11 + [C.c_void_p, C.c_int]
+        L.ref_trace_rays.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_xorwow_floats.argtypes = [C.c_uint, C.c_int, C.c_void_p]
+        L.ref_woop_setdata.argtypes = [C.c_void_p] * 4
+        L.ref_sample_tables.argtypes = [C.c_uint, C.c_void_p, C.c_void_p]
+        L.ref_bsdf_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def render(view, w, h, n_passes=1, pass_first=0, max_path_length=8, rr_start=5, direct=1, window=None, n_threads=0, img=None):
+    if img is None:
+        img = np.zeros((h, w), PIXEL_DTYPE)
+    x0, y0, x1, y1 = window if window else (0, 0, w, h)
+    if n_threads <= 0:
+        n_threads = os.cpu_count() or 1
+    rays = ref().ref_render(C.byref(view), w, h, x0, y0, x1, y1, pass_first, n_passes, max_path_length, rr_start, direct, _p(img), n_threads)
+    return img, int(rays)
+
+
+def trace_rays(view, rays):
+    rays = np.ascontiguousarray(rays, RAY_DTYPE); out = np.zeros(len(rays), TRACE_RESULT_DTYPE)
+    ref().ref_trace_rays(C.byref(view), len(rays), _p(rays), _p(out)); return out
+
+
+def xorwow_floats(subsequence, n):
+    out = np.zeros(n, np.float32); ref().ref_xorwow_floats(subsequence, n, _p(out)); return out
+
+
+def woop_setdata(v0, v1, v2):
+    a, b, c = (np.ascontiguousarray(x, np.float32) for x in (v0, v1, v2)); out = np.zeros(12, np.float32)
+    ref().ref_woop_setdata(_p(a), _p(b), _p(c), _p(out)); return out
+
+
+def sample_tables(pass_index):
+    d1 = np.zeros(4096 * 30, np.float32); d2 = np.zeros(4096 * 30 * 2, np.float32)
+    ref().ref_sample_tables(pass_index, _p(d1), _p(d2)); return d1, d2
+
+
+def bsdf_probe(mat, wi, sx, sy):
+    w = np.ascontiguousarray(wi, np.float32); out = np.zeros(9, np.float32); f = np.zeros(3, np.float32); pdf = np.zeros(1, np.float32)
+    ref().ref_bsdf_probe(C.byref(mat), _p(w), sx, sy, _p(out), _p(f), _p(pdf)); return out, f, pdf[0]

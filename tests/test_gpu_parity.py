@@ -282,3 +282,51 @@ def test_cpp_adapter_renders(built_lib, tmp_path):
     r = subprocess.run([exe, "gpu"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "passes 1" in r.stdout and "weight 4096" in r.stdout
+
+
+# ------------------------------------------------------------------ golden vectors minted from the reference's own host code
+import os as _os
+_GOLD = np.load(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "reference_golden.npz"))
+
+
+@pytest.mark.parametrize("kind", ["cornell", "cornell7", "soup"])
+def test_trace_rays_golden(built_lib, kind):
+    """CUDA traversal vs results of the REFERENCE's traceRay (oracle/_ref, tests/golden/make_golden.py)."""
+    s, t = make(kind)
+    rays = np.ascontiguousarray(_GOLD[f"trace_{kind}_rays"]).view(api.RAY_DTYPE).reshape(-1)
+    ref = np.ascontiguousarray(_GOLD[f"trace_{kind}_res"]).view(api.TRACE_RESULT_DTYPE).reshape(-1)
+    got = t.trace_rays(rays)
+    assert np.array_equal(got["tri_idx"], ref["tri_idx"]) and np.array_equal(got["node_idx"], ref["node_idx"])
+    hit = ref["tri_idx"] != 0xffffffff
+    assert np.all(np.abs(got["dist"][hit] - ref["dist"][hit]) <= 4e-6 * np.maximum(1, ref["dist"][hit]))  # explicit FMA vs the reference's uncontracted host build
+    assert np.all(np.abs(got["u"][hit] - ref["u"][hit]) <= 2e-5) and np.all(np.abs(got["v"][hit] - ref["v"][hit]) <= 2e-5)
+    t.close()
+
+
+@pytest.mark.parametrize("key,kind,w,h,spp", [("image_cornell_128x128_1spp", "cornell", 128, 128, 1), ("image_cornell7_96x96_8spp", "cornell7", 96, 96, 8),
+                                              ("image_soup_96x96_1spp", "soup", 96, 96, 1)])
+def test_render_golden(built_lib, key, kind, w, h, spp):
+    """CUDA path tracer vs PixelData images rendered by the REFERENCE's PathTrace<true> on its CPU path, same seed."""
+    ref = np.ascontiguousarray(_GOLD[key]).view(api.PIXEL_DTYPE).reshape(h, w)
+    s, t = make(kind, w, h, 8)
+    for p in range(spp):
+        t.DoPass(p == 0)
+    t.synchronize()
+    img = t.readAccumulator()
+    a, b = img["rgb"], ref["rgb"]
+    assert (rel_l2(a, b) <= 1e-3).mean() >= 0.99
+    assert np.sqrt(((a - b) ** 2).mean()) / np.sqrt((b ** 2).mean()) <= (1e-2 if spp == 1 else 3e-3)
+    assert abs(a.mean() - b.mean()) <= 1e-3 * b.mean()
+    assert np.array_equal(img["weight_sum"], ref["weight_sum"])
+    t.close()
+
+
+def test_config1_cornell_256_golden(built_lib):
+    s, t = make("cornell", 256, 256, 8)
+    t.DoPass(True); t.synchronize()
+    img = t.readAccumulator()
+    st = _GOLD["config1_cornell_256_1spp_stats"]
+    assert abs(img["rgb"].astype(np.float64).mean() - st[0]) <= 1e-3 * st[0]
+    assert img["weight_sum"].sum() == st[2] and abs(t.getRaysInLastPass() - int(st[3])) <= 2e-3 * st[3]
+    assert np.allclose(img["rgb"].astype(np.float64).mean(axis=(1, 2)), _GOLD["config1_cornell_256_1spp_rowmeans"], rtol=2e-3, atol=1e-5)
+    t.close()
