@@ -60,5 +60,6 @@ for f in $TUS; do
 done
 for p in "${pids[@]}"; do wait "$p"; done
 g++ $CXXFLAGS -c "$HERE/ref_driver.cpp" -o obj/ref_driver.o
-g++ -shared -pthread -o "$OUT/libctl_ref.so" obj/*.o -Wl,-z,defs -lm
+printf '{ global: ref_*; local: *; };\n' > export.map   # only the ref_* entry points are visible; the CUDA-runtime stubs stay private
+g++ -shared -pthread -o "$OUT/libctl_ref.so" obj/*.o -Wl,-z,defs -Wl,-Bsymbolic -Wl,--version-script=export.map -lm
 echo "built $OUT/libctl_ref.so"
