@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--cpu-frac", type=float, default=1.0 / 16, help="fraction of the image the CPU baseline renders per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sort-mode", type=int, default=None)
+    ap.add_argument("--batch", type=int, default=8, help="progressive passes fused into one wavefront (must divide spp)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: W >= 3
@@ -208,16 +209,16 @@ def main():
     host_img = torch.empty(h * w * 7, dtype=torch.float32, pin_memory=True)
     table_bytes = 4096 * 30 * 12
 
+    batch = min(spp, args.batch)
+
     def render_pass(p, new_trace):
-        if world > 1:
-            tracer.DoPassTiled(TILE, TILE, rank, world, new_trace=new_trace)
-        else:
-            tracer.DoPass(new_trace=new_trace)
+        # `batch` progressive passes fused into one wavefront (ctl_render_passes_tiled) on this rank's tiles
+        tracer.DoPasses(batch, new_trace=new_trace, tile=(TILE, TILE), part=rank, n_parts=world)
 
     df = DistributedFrame(accum, render_pass, lambda: 0)
 
     def frame(read_back):
-        df.frame(spp)  # spp passes on this rank's tiles + (N > 1) the one NCCL reduce of the accumulator, all on `stream`
+        df.frame(spp // batch)  # spp passes on this rank's tiles + (N > 1) the one NCCL reduce of the accumulator, all on `stream`
         if read_back and rank == 0:
             host_img.copy_(accum, non_blocking=True)
 
@@ -259,63 +260,58 @@ def main():
     else:
         rays_frame = float(t[1])
     value = rays_frame * args.steps / (dev_ms * 1e-3) / 1e6
-    launches_per_pass = tracer.stageTimes()[1]
+    launches_per_batch = tracer.stageTimes()[1]
 
     # ---- end-to-end steps through the public API with host buffers
     e2e_steps = max(3, min(args.steps, 10))
+    tracer.setParameter("DeviceSampleTables", 0)   # e2e: the step's inputs (the pass sample tables) come from the host, like the reference's UpdateKernel
+    frame(True)
     sync_all()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         frame(True)
     sync_all()
     e2e_s = time.perf_counter() - t0
+    tracer.setParameter("DeviceSampleTables", 1)
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = rays_frame * e2e_steps / float(te[0]) / 1e6
     img_mean = float(host_img.view(h, w, 7)[:, :, :3].mean()) if rank == 0 else 0.0
 
-    # ---- roofline of the traversal kernel (rank 0's share), live CUDA-event stage times
-    roof = None
-    if True:
-        tracer.setParameter("StageTimers", 1)
-        ext_ms = sh_ms = 0.0
-        n_tp = 0
-        for p in range(spp):
-            if world > 1:
-                tracer.DoPassTiled(TILE, TILE, rank, world, new_trace=(p == 0))
-            else:
-                tracer.DoPass(new_trace=(p == 0))
-            tracer.synchronize()
-            ms, _ = tracer.stageTimes()
-            ext_ms += ms[1]; sh_ms += ms[3]; n_tp += 1
-        tracer.setParameter("StageTimers", 0)
-        stage_last = ms
-        tracer.setInstrumented(1)
-        if world > 1:
-            tracer.DoPassTiled(TILE, TILE, rank, world, new_trace=True)
-        else:
-            tracer.DoPass(new_trace=True)
+    # ---- roofline of the traversal kernel (this rank's share), live CUDA-event stage times of the same batched frames
+    tracer.setParameter("StageTimers", 1)
+    ext_ms = sh_ms = 0.0
+    n_batches = spp // batch
+    for b_i in range(n_batches):
+        render_pass(b_i, b_i == 0)
         tracer.synchronize()
-        e_cnt, s_cnt = tracer.visitCounts()
-        tracer.setInstrumented(0)
-        bytes_pass = traversal_bytes(e_cnt, e_cnt[3]) + traversal_bytes(s_cnt, s_cnt[3])
-        trav_ms_pass = (ext_ms + sh_ms) / n_tp
-        n_trav_launches = 2 * depth
-        peak, peak_src = hbm_peak()
-        achieved = bytes_pass / (trav_ms_pass * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_intersect (extension + shadow launches)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
-                "algorithmic_bytes_per_launch": bytes_pass / n_trav_launches, "avg_launch_ms": trav_ms_pass / n_trav_launches,
-                "bytes_per_ray": bytes_pass / max(1, e_cnt[3] + s_cnt[3]), "launches_per_pass": n_trav_launches,
-                "traversal_share_of_pass": (stage_last[1] + stage_last[3]) / max(1e-9, sum(stage_last)),
-                "stage_ms_last_pass": {"generate": stage_last[0], "extension": stage_last[1], "shade": stage_last[2], "shadow": stage_last[3], "finish": stage_last[4]}}
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        try:
-            with open(tp) as f:
-                roof["traffic"] = json.load(f).get(args.workload, {}).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+        ms, _ = tracer.stageTimes()
+        ext_ms += ms[1]; sh_ms += ms[3]
+    tracer.setParameter("StageTimers", 0)
+    stage_last = ms
+    tracer.setInstrumented(1)
+    render_pass(0, True)
+    tracer.synchronize()
+    e_cnt, s_cnt = tracer.visitCounts()
+    tracer.setInstrumented(0)
+    bytes_batch = traversal_bytes(e_cnt, e_cnt[3]) + traversal_bytes(s_cnt, s_cnt[3])   # one batch (all batches of a frame are alike up to RNG)
+    trav_ms_batch = (ext_ms + sh_ms) / n_batches
+    n_trav_launches = 2 * depth
+    peak, peak_src = hbm_peak()
+    achieved = bytes_batch / (trav_ms_batch * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "k_intersect (extension + shadow launches)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+            "algorithmic_bytes_per_launch": bytes_batch / n_trav_launches, "avg_launch_ms": trav_ms_batch / n_trav_launches,
+            "bytes_per_ray": bytes_batch / max(1, e_cnt[3] + s_cnt[3]), "launches_per_batch": n_trav_launches, "passes_per_batch": batch,
+            "traversal_share_of_batch": (stage_last[1] + stage_last[3]) / max(1e-9, sum(stage_last)),
+            "stage_ms_last_batch": {"generate": stage_last[0], "extension": stage_last[1], "shade": stage_last[2], "shadow": stage_last[3], "finish": stage_last[4]}}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(tp) as f:
+            roof["traffic"] = json.load(f).get(args.workload, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
 
     # ---- CPU baseline (rank 0, N == 1 only): bounded crop on the host cores
     cpu = None
@@ -336,14 +332,14 @@ def main():
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "width": w, "height": h, "spp": spp, "max_path_length": depth, "rr_start_depth": 5, "direct": True,
+            "config": {"workload": desc, "width": w, "height": h, "spp": spp, "max_path_length": depth, "rr_start_depth": 5, "direct": True, "passes_per_wavefront": batch,
                        "triangles": scene.n_triangles, "rays_per_step": rays_frame,
                        "partition": "whole image" if world == 1 else f"interleaved {TILE}x{TILE} tiles, tile % {world} == rank; one NCCL reduce of PixelData (7*w*h f32) per step",
                        "l2": "256 MiB buffer written between timed steps (L2 flush); per-pass queue/path-state working set ~0.5 GB > 126 MB L2"},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": spp * table_bytes, "d2h_bytes_per_step": h * w * 7 * 4,
-                    "steps": e2e_steps, "note": "wall clock; host XORWOW sample-table generation + pinned H2D every pass, PixelData image D2H to pinned memory every step"},
-            "gpu_launches": int(launches_per_pass * spp * args.steps),
+                    "steps": e2e_steps, "note": "wall clock; DeviceSampleTables=0: sample tables generated by the host XORWOW twin and copied H2D from pinned memory for every pass, PixelData image copied D2H to pinned memory every step"},
+            "gpu_launches": int((launches_per_batch + 1) * (spp // batch) * args.steps),
             "wall_s_timed_region": t_wall, "image_mean_rgb": img_mean,
         }
         if roof:

@@ -119,6 +119,8 @@ def lib():
     L.ctl_trace_rays_host.argtypes = [vp, i32, vp, vp, vp]
     L.ctl_render_pass.argtypes = [vp, i32, i32, i32, i32, i32]
     L.ctl_render_pass_tiled.argtypes = [vp, i32, i32, i32, i32, i32]
+    L.ctl_render_passes_tiled.argtypes = [vp, i32, i32, i32, i32, i32, i32]
+    L.ctl_read_sample_tables.argtypes = [vp, i32, vp, vp]
     L.ctl_synchronize.argtypes = [vp]
     L.ctl_read_accum.argtypes = [vp, vp]
     L.ctl_accum_device_ptr.argtypes = [vp]; L.ctl_accum_device_ptr.restype = vp
@@ -236,6 +238,16 @@ class PathTracer:
     def DoPassTiled(self, tile_w, tile_h, part, n_parts, new_trace=None):
         nt = self._new_trace if new_trace is None else bool(new_trace)
         _check(lib().ctl_render_pass_tiled(self._ctx, int(nt), tile_w, tile_h, part, n_parts)); self._new_trace = False
+
+    def DoPasses(self, n_passes, new_trace=None, tile=(64, 64), part=0, n_parts=1):
+        """n_passes DoPass calls fused into one wavefront (ctl_render_passes_tiled); part/n_parts select interleaved tiles."""
+        nt = self._new_trace if new_trace is None else bool(new_trace)
+        _check(lib().ctl_render_passes_tiled(self._ctx, int(nt), int(n_passes), tile[0], tile[1], part, n_parts)); self._new_trace = False
+
+    def readSampleTables(self, table_set=0):
+        d1 = np.zeros(4096 * 30, np.float32); d2 = np.zeros(4096 * 30 * 2, np.float32)
+        _check(lib().ctl_read_sample_tables(self._ctx, table_set, _ptr(d1), _ptr(d2)))
+        return d1, d2
 
     def StartNewTrace(self):
         self._new_trace = True

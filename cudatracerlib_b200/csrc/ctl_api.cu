@@ -25,7 +25,6 @@ struct ctl_scene { ctlb::SceneStorage S; };
 
 namespace {
 const int MAX_BOUNCES = 256;
-const int N_TABLE_SLOTS = 4;
 enum { CTR_Q = 0, CTR_SH = MAX_BOUNCES + 1, CTR_WORK = 2 * (MAX_BOUNCES + 1), CTR_TOTAL = 4 * (MAX_BOUNCES + 1) };
 
 template <typename T> struct DevBuf {
@@ -58,11 +57,13 @@ struct ctl_ctx {
     DevBuf<ctl_mesh> d_meshes; DevBuf<ctl_node> d_nodes; DevBuf<float> d_xf, d_inv_xf; DevBuf<ctl_material> d_materials; DevBuf<ctl_light> d_lights;
     DevBuf<ctl_light_tri> d_light_tris; DevBuf<float> d_light_cdf, d_normal_lut;
     DScene scene; bool has_scene = false;
-    // sampler tables ring
-    DevBuf<float> d_d1[N_TABLE_SLOTS]; DevBuf<float> d_d2[N_TABLE_SLOTS];
-    float* h_d1[N_TABLE_SLOTS] = {nullptr}; float* h_d2[N_TABLE_SLOTS] = {nullptr};
-    cudaEvent_t table_free[N_TABLE_SLOTS] = {nullptr};
-    int table_slot = 0; bool user_tables = false;
+    // sampler tables: `tab_cap` consecutive table sets (one per pass of a batch) on the device; generated there
+    // (k_gen_tables) or -- "DeviceSampleTables"=0, the reference's UpdateKernel behaviour -- on the host and copied H2D
+    int tab_cap = 0; DevBuf<float> d_tab1, d_tab2;
+    float* h_tab1 = nullptr; float* h_tab2 = nullptr; int h_tab_cap = 0; cudaEvent_t h_tab_free = nullptr;
+    DevBuf<uint32_t> d_states, d_states0, d_jump;
+    bool user_tables = false; int device_tables = 1;
+    uint32_t gen_pos_host = 0, gen_pos_dev = 0;   // index of the next pass each generator would produce
     ctlb::SamplerTableGenerator gen;
     // wavefront state
     DevBuf<float4> cf, cl, nor, px, rays_a, rays_b, hit_a, sh_rays, sh_payload, capture;
@@ -152,10 +153,12 @@ ctl_ctx* ctl_create(int device, int width, int height) {
     CKP(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CKP(cudaEventCreate(&c->ev_start)); CKP(cudaEventCreate(&c->ev_stop));
-    for (int i = 0; i < N_TABLE_SLOTS; i++) {
-        CKP(c->d_d1[i].ensure((size_t)ctlb::kNumSeq * ctlb::kSeqLen)); CKP(c->d_d2[i].ensure((size_t)ctlb::kNumSeq * ctlb::kSeqLen * 2));
-        CKP(cudaMallocHost((void**)&c->h_d1[i], (size_t)ctlb::kNumSeq * ctlb::kSeqLen * 4)); CKP(cudaMallocHost((void**)&c->h_d2[i], (size_t)ctlb::kNumSeq * ctlb::kSeqLen * 8));
-        CKP(cudaEventCreateWithFlags(&c->table_free[i], cudaEventDisableTiming));
+    CKP(cudaEventCreateWithFlags(&c->h_tab_free, cudaEventDisableTiming));
+    {   // device-side table generator: per-sequence start states of pass 0 + the jump matrix to the next pass
+        std::vector<uint32_t> st0((size_t)ctlb::kNumSeq * 6); ctlb::XorwowJump J;
+        ctlb::device_generator_data(st0.data(), &J);
+        CKP(c->d_states0.upload(st0.data(), st0.size())); CKP(c->d_states.upload(st0.data(), st0.size()));
+        CKP(c->d_jump.upload(&J.row[0][0], 160 * 5));
     }
     CKP(c->counters.ensure(CTR_TOTAL)); CKP(c->stats.ensure(16)); CKP(c->d_captured_n.ensure(1));
     CKP(cudaMemset(c->stats.p, 0, 16 * sizeof(unsigned long long)));
@@ -170,7 +173,8 @@ void ctl_destroy(ctl_ctx* c) {
     c->d_scene_nodes.release(); c->d_bvh_nodes.release(); c->d_woop.release(); c->d_tri_index.release(); c->d_tri_data.release(); c->d_meshes.release();
     c->d_nodes.release(); c->d_xf.release(); c->d_inv_xf.release(); c->d_materials.release(); c->d_lights.release(); c->d_light_tris.release();
     c->d_light_cdf.release(); c->d_normal_lut.release();
-    for (int i = 0; i < N_TABLE_SLOTS; i++) { c->d_d1[i].release(); c->d_d2[i].release(); if (c->h_d1[i]) cudaFreeHost(c->h_d1[i]); if (c->h_d2[i]) cudaFreeHost(c->h_d2[i]); if (c->table_free[i]) cudaEventDestroy(c->table_free[i]); }
+    c->d_tab1.release(); c->d_tab2.release(); c->d_states.release(); c->d_states0.release(); c->d_jump.release();
+    if (c->h_tab1) cudaFreeHost(c->h_tab1); if (c->h_tab2) cudaFreeHost(c->h_tab2); if (c->h_tab_free) cudaEventDestroy(c->h_tab_free);
     c->cf.release(); c->cl.release(); c->nor.release(); c->px.release(); c->rays_a.release(); c->rays_b.release(); c->hit_a.release(); c->sh_rays.release();
     c->sh_payload.release(); c->capture.release(); c->path_a.release(); c->path_b.release(); c->hit_node.release(); c->counters.release(); c->stats.release();
     c->own_accum.release(); c->d_captured_n.release();
@@ -199,6 +203,7 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "SortMode") c->sort_mode = v;
     else if (k == "StageTimers") c->stage_timers = v != 0;
     else if (k == "CaptureBounce") c->capture_bounce = v;
+    else if (k == "DeviceSampleTables") c->device_tables = v != 0;
     else if (k == "TraversalKernel") { if (v < 0 || v > 1) return set_err("TraversalKernel must be 0 or 1"); c->trav_kernel = v; }
     else if (k == "TravThT") c->tune.th_t = v; else if (k == "TravThL") c->tune.th_l = v; else if (k == "TravThF") c->tune.th_f = v;
     else if (k == "TravThNExit") c->tune.th_n_exit = v;
@@ -211,7 +216,7 @@ int ctl_get_param_i(ctl_ctx* c, const char* key, int* v) {
     std::string k(key);
     if (k == "MaxPathLength") *v = c->max_path_length; else if (k == "RRStartDepth") *v = c->rr_start; else if (k == "Direct") *v = c->direct;
     else if (k == "Regularization") *v = c->regularization; else if (k == "SortMode") *v = c->sort_mode; else if (k == "StageTimers") *v = c->stage_timers;
-    else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel;
+    else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables;
     else if (k == "TraversalBlocksPerSM") *v = c->trav_blocks_per_sm; else return set_err("unknown parameter key: " + k);
     return 0;
 }
@@ -240,7 +245,7 @@ int ctl_upload_scene(ctl_ctx* c, const ctl_scene_view* v) {
     S.tri_index = c->d_tri_index.p; S.tri_data = (const uint4*)c->d_tri_data.p; S.meshes = c->d_meshes.p; S.nodes = c->d_nodes.p;
     S.node_xf = (const float4*)c->d_xf.p; S.node_inv_xf = (const float4*)c->d_inv_xf.p; S.materials = c->d_materials.p; S.lights = c->d_lights.p;
     S.light_tris = c->d_light_tris.p; S.light_cdf_data = c->d_light_cdf.p; S.normal_lut = c->d_normal_lut.p;
-    S.d1 = c->d_d1[0].p; S.d2 = (const float2*)c->d_d2[0].p;
+    S.d1 = c->d_tab1.p; S.d2 = (const float2*)c->d_tab2.p;
     S.num_lights = v->num_lights;
     memcpy(S.light_indices, v->light_indices, sizeof(S.light_indices)); memcpy(S.light_cdf, v->light_cdf, sizeof(S.light_cdf));
     S.camera = v->camera; S.ray_eps = v->ray_eps; S.scene_start = v->scene_start_node; S.n_nodes = v->n_nodes;
@@ -249,16 +254,69 @@ int ctl_upload_scene(ctl_ctx* c, const ctl_scene_view* v) {
     return 0;
 }
 
+static const size_t TAB1 = (size_t)ctlb::kNumSeq * ctlb::kSeqLen, TAB2 = TAB1 * 2;
+
+static int ensure_tables(ctl_ctx* c, int n_passes) {
+    if (n_passes <= c->tab_cap) return 0;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(c->d_tab1.ensure(TAB1 * n_passes)); CK(c->d_tab2.ensure(TAB2 * n_passes));
+    c->tab_cap = n_passes;
+    return 0;
+}
+static int ensure_host_tables(ctl_ctx* c, int n_passes) {
+    if (n_passes <= c->h_tab_cap) return 0;
+    CK(cudaEventSynchronize(c->h_tab_free));
+    if (c->h_tab1) cudaFreeHost(c->h_tab1); if (c->h_tab2) cudaFreeHost(c->h_tab2);
+    c->h_tab1 = c->h_tab2 = nullptr; c->h_tab_cap = 0;
+    CK(cudaMallocHost((void**)&c->h_tab1, TAB1 * 4 * n_passes)); CK(cudaMallocHost((void**)&c->h_tab2, TAB2 * 4 * n_passes));
+    c->h_tab_cap = n_passes;
+    return 0;
+}
+
 int ctl_upload_samples(ctl_ctx* c, const float* d1, const float* d2) {
     if (!c || !d1 || !d2) return set_err("null argument");
     CK(cudaSetDevice(c->device));
-    const int s = (c->table_slot + 1) % N_TABLE_SLOTS;
-    CK(cudaEventSynchronize(c->table_free[s]));
-    memcpy(c->h_d1[s], d1, (size_t)ctlb::kNumSeq * ctlb::kSeqLen * 4); memcpy(c->h_d2[s], d2, (size_t)ctlb::kNumSeq * ctlb::kSeqLen * 8);
-    CK(cudaMemcpyAsync(c->d_d1[s].p, c->h_d1[s], (size_t)ctlb::kNumSeq * ctlb::kSeqLen * 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_d2[s].p, c->h_d2[s], (size_t)ctlb::kNumSeq * ctlb::kSeqLen * 8, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaEventRecord(c->table_free[s], c->stream));
-    c->table_slot = s; c->user_tables = true;
+    if (ensure_tables(c, 1) || ensure_host_tables(c, 1)) return 1;
+    CK(cudaEventSynchronize(c->h_tab_free));
+    memcpy(c->h_tab1, d1, TAB1 * 4); memcpy(c->h_tab2, d2, TAB2 * 4);
+    CK(cudaMemcpyAsync(c->d_tab1.p, c->h_tab1, TAB1 * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_tab2.p, c->h_tab2, TAB2 * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(c->h_tab_free, c->stream));
+    c->user_tables = true;
+    return 0;
+}
+
+// Tables of passes [first, first + n) into the device table sets 0..n-1 (GenerateNewRandomSequences, Kernel/Sampler.h:36-55)
+static int generate_tables(ctl_ctx* c, uint32_t first, int n) {
+    if (ensure_tables(c, n)) return 1;
+    if (c->device_tables) {
+        if (c->gen_pos_dev != first) { // re-synchronise the device stream position (rare: mode switch / user tables)
+            CK(cudaMemcpyAsync(c->d_states.p, c->d_states0.p, (size_t)ctlb::kNumSeq * 6 * 4, cudaMemcpyDeviceToDevice, c->stream));
+            for (uint32_t p = 0; p < first; p++) k_gen_tables<<<ctlb::kNumSeq / 128, 128, 0, c->stream>>>(c->d_states.p, c->d_jump.p, 1, c->d_tab1.p, (float2*)c->d_tab2.p);
+        }
+        k_gen_tables<<<ctlb::kNumSeq / 128, 128, 0, c->stream>>>(c->d_states.p, c->d_jump.p, n, c->d_tab1.p, (float2*)c->d_tab2.p);
+        CK(cudaGetLastError());
+        c->gen_pos_dev = first + n;
+    } else {
+        if (ensure_host_tables(c, n)) return 1;
+        CK(cudaEventSynchronize(c->h_tab_free));
+        if (c->gen_pos_host != first) { c->gen.reset(); for (uint32_t p = 0; p < first; p++) c->gen.next_pass(c->h_tab1, c->h_tab2); }
+        for (int p = 0; p < n; p++) c->gen.next_pass(c->h_tab1 + TAB1 * p, c->h_tab2 + TAB2 * p);
+        CK(cudaMemcpyAsync(c->d_tab1.p, c->h_tab1, TAB1 * 4 * n, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_tab2.p, c->h_tab2, TAB2 * 4 * n, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaEventRecord(c->h_tab_free, c->stream));
+        c->gen_pos_host = first + n;
+    }
+    return 0;
+}
+
+int ctl_read_sample_tables(ctl_ctx* c, int table_set, float* d1, float* d2) {
+    if (!c || !d1 || !d2) return set_err("null argument");
+    if (table_set < 0 || table_set >= c->tab_cap) return set_err("no such table set");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(d1, c->d_tab1.p + TAB1 * table_set, TAB1 * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(d2, c->d_tab2.p + TAB2 * table_set, TAB2 * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -339,28 +397,21 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
     if (!c->has_scene) return set_err("no scene uploaded");
     if (W.n_slots <= 0) return 0;
     CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->ev_start, c->stream));
     if (new_trace) {
         CK(cudaMemsetAsync(c->accum, 0, (size_t)c->w * c->h * 7 * sizeof(float), c->stream));
         c->passes_done = 0;
-        if (!c->user_tables) c->gen.reset();
     }
-    // sample tables of this pass (GenerateNewRandomSequences, Kernel/Sampler.h:36-55): host XORWOW, async H2D
-    if (!c->user_tables) {
-        const int s = (c->table_slot + 1) % N_TABLE_SLOTS;
-        CK(cudaEventSynchronize(c->table_free[s]));
-        c->gen.next_pass(c->h_d1[s], c->h_d2[s]);
-        CK(cudaMemcpyAsync(c->d_d1[s].p, c->h_d1[s], (size_t)ctlb::kNumSeq * ctlb::kSeqLen * 4, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(c->d_d2[s].p, c->h_d2[s], (size_t)ctlb::kNumSeq * ctlb::kSeqLen * 8, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaEventRecord(c->table_free[s], c->stream));
-        c->table_slot = s;
-    }
+    // sample tables of these passes: caller-supplied (single pass), generated on the device, or host XORWOW + H2D
+    if (c->user_tables) { if (W.n_passes != 1) return set_err("caller-supplied sample tables cover exactly one pass"); }
+    else if (generate_tables(c, c->passes_done, W.n_passes)) return 1;
     c->user_tables = false;
-    c->scene.d1 = c->d_d1[c->table_slot].p; c->scene.d2 = (const float2*)c->d_d2[c->table_slot].p;
+    c->scene.d1 = c->d_tab1.p; c->scene.d2 = (const float2*)c->d_tab2.p;
     c->scene.img_w = c->w; c->scene.img_h = c->h;
-    if (ensure_state(c, (size_t)W.n_slots)) return 1;
-    if (c->capture_bounce > 0) CK(c->capture.ensure(2 * (size_t)W.n_slots));
+    const size_t n_paths = (size_t)W.n_slots * W.n_passes;
+    if (ensure_state(c, n_paths)) return 1;
+    if (c->capture_bounce > 0) CK(c->capture.ensure(2 * n_paths));
 
-    CK(cudaEventRecord(c->ev_start, c->stream));
     c->stage_kind.clear();
     CK(cudaMemsetAsync(c->counters.p, 0, CTR_TOTAL * sizeof(unsigned), c->stream));
     if (c->instrumented) CK(cudaMemsetAsync(c->stats.p + 2, 0, 8 * sizeof(unsigned long long), c->stream));
@@ -377,7 +428,7 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
     for (int b = 0; b < c->max_path_length; b++) {
         stage_mark(c, 1);
         if (c->capture_bounce == b + 1) {
-            CK(cudaMemcpyAsync(c->capture.p, rin, 32 * (size_t)W.n_slots, cudaMemcpyDeviceToDevice, c->stream));
+            CK(cudaMemcpyAsync(c->capture.p, rin, 32 * n_paths, cudaMemcpyDeviceToDevice, c->stream));
             CK(cudaMemcpyAsync(c->d_captured_n.p, ctr + CTR_Q + b, sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
         }
         if (c->instrumented) launch_intersect<0, false, true>(c, g_trav, c->stream, c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, c->stats.p + 2);
@@ -395,14 +446,14 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
         std::swap(rin, rout); std::swap(pin, pout);
     }
     stage_mark(c, 4);
-    k_finish<<<g_light, 256, 0, c->stream>>>(W.n_slots, st, c->accum, c->w, c->h);
+    k_finish<<<g_light, 256, 0, c->stream>>>((int)n_paths, st, c->accum, c->w, c->h);
     k_tally<<<1, 32, 0, c->stream>>>(ctr + CTR_Q, ctr + CTR_SH, c->max_path_length, c->stats.p, c->stats.p + 1);
     launches += 2;
     stage_mark(c, 5);
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev_stop, c->stream));
     c->n_launches = launches;
-    c->passes_done++;
+    c->passes_done += W.n_passes;
     return 0;
 }
 
@@ -410,24 +461,32 @@ int ctl_render_pass(ctl_ctx* c, int new_trace, int x0, int y0, int x1, int y1) {
     if (!c) return set_err("null context");
     if (x0 < 0 || y0 < 0 || x1 > c->w || y1 > c->h || x1 < x0 || y1 < y0) return set_err("pixel window outside the image");
     Window W; memset(&W, 0, sizeof(W));
-    W.mode = 0; W.x0 = x0; W.y0 = y0; W.x1 = x1; W.y1 = y1; W.n_slots = (x1 - x0) * (y1 - y0);
+    W.mode = 0; W.x0 = x0; W.y0 = y0; W.x1 = x1; W.y1 = y1; W.n_slots = (x1 - x0) * (y1 - y0); W.n_passes = 1;
     return render_window(c, new_trace, W);
 }
 
-int ctl_render_pass_tiled(ctl_ctx* c, int new_trace, int tile_w, int tile_h, int part, int n_parts) {
+int ctl_render_passes_tiled(ctl_ctx* c, int new_trace, int n_passes, int tile_w, int tile_h, int part, int n_parts) {
     if (!c) return set_err("null context");
+    if (n_passes < 1 || n_passes > 4096) return set_err("n_passes out of range [1,4096]");
     if (tile_w <= 0 || tile_h <= 0 || n_parts <= 0 || part < 0 || part >= n_parts) return set_err("invalid tiling");
     Window W; memset(&W, 0, sizeof(W));
-    W.mode = 1; W.tile_w = tile_w; W.tile_h = tile_h; W.part = part; W.n_parts = n_parts;
+    W.mode = 1; W.tile_w = tile_w; W.tile_h = tile_h; W.part = part; W.n_parts = n_parts; W.n_passes = n_passes;
     W.tiles_x = (c->w + tile_w - 1) / tile_w; W.tiles_y = (c->h + tile_h - 1) / tile_h;
     const int n_tiles = W.tiles_x * W.tiles_y;
     const int n_local = n_tiles > part ? (n_tiles - part + n_parts - 1) / n_parts : 0;
     W.n_slots = n_local * tile_w * tile_h;
-    if (W.n_slots == 0 && new_trace) { // still honour the clear
+    if ((size_t)W.n_slots * n_passes > 0x7fffffffull / 2) return set_err("batch too large: reduce n_passes");
+    if (W.n_slots == 0) { // nothing to trace on this part: still honour the clear and advance the pass counter / sample stream
         CK(cudaSetDevice(c->device));
-        CK(cudaMemsetAsync(c->accum, 0, (size_t)c->w * c->h * 7 * sizeof(float), c->stream));
+        if (new_trace) { CK(cudaMemsetAsync(c->accum, 0, (size_t)c->w * c->h * 7 * sizeof(float), c->stream)); c->passes_done = 0; }
+        c->passes_done += n_passes;
+        return 0;
     }
     return render_window(c, new_trace, W);
+}
+
+int ctl_render_pass_tiled(ctl_ctx* c, int new_trace, int tile_w, int tile_h, int part, int n_parts) {
+    return ctl_render_passes_tiled(c, new_trace, 1, tile_w, tile_h, part, n_parts);
 }
 
 int ctl_synchronize(ctl_ctx* c) {

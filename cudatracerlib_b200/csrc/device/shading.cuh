@@ -12,16 +12,16 @@ namespace ctld {
 
 constexpr int N_SEQ = 4096, SEQ_LEN = 30;
 
-struct Sampler { // SequenceSampler, Kernel/Sampler_device.h:62-107
-    unsigned idx, i1, i2;
+struct Sampler { // SequenceSampler, Kernel/Sampler_device.h:62-107; `tab` selects the pass's table when several passes share a wavefront
+    unsigned idx, i1, i2, tab;
     CTL_DEV float f1(const DScene& S) {
-        const unsigned a = idx % N_SEQ, b = (idx / N_SEQ) % N_SEQ, e = i1 % SEQ_LEN;
+        const unsigned a = idx % N_SEQ, b = (idx / N_SEQ) % N_SEQ, e = i1 % SEQ_LEN + tab * SEQ_LEN;
         float sum = 0.0f; sum += __ldg(S.d1 + e * N_SEQ + a); sum += __ldg(S.d1 + e * N_SEQ + b);
         i1++;
         return sum - floorf(sum);
     }
     CTL_DEV float2 f2(const DScene& S) {
-        const unsigned a = idx % N_SEQ, b = (idx / N_SEQ) % N_SEQ, e = i2 % SEQ_LEN;
+        const unsigned a = idx % N_SEQ, b = (idx / N_SEQ) % N_SEQ, e = i2 % SEQ_LEN + tab * SEQ_LEN;
         const float2 va = __ldg(S.d2 + e * N_SEQ + a), vb = __ldg(S.d2 + e * N_SEQ + b);
         float sx = 0.0f, sy = 0.0f; sx += va.x; sy += va.y; sx += vb.x; sy += vb.y;
         i2++;

@@ -42,4 +42,47 @@ struct SamplerTableGenerator {
     }
 };
 
+// ---- data for the DEVICE-side generator (k_gen_tables in wavefront.cuh) ---------------------------------------
+// The XORWOW state update is linear over GF(2) on the 160 bits of v[0..4] (the Weyl counter d just adds 362437 per
+// draw), so "skip n draws" is a 160x160 bit matrix.  Sequence s of a pass starts 90*s draws into the pass and the next
+// pass starts 4096*90 draws later; one thread per sequence therefore needs (a) its start state in pass 0 and (b) the
+// jump matrix for 4096*90 - 90 draws to get from the end of its slice to its slice in the next pass.
+struct XorwowJump {
+    // row k = image of basis vector e_k (bit k of the 160-bit state, word k/32, bit k%32)
+    uint32_t row[160][5];
+    static void step_linear(uint32_t v[5]) {
+        uint32_t t = (v[0] ^ (v[0] >> 2));
+        v[0] = v[1]; v[1] = v[2]; v[2] = v[3]; v[3] = v[4];
+        v[4] = (v[4] ^ (v[4] << 4)) ^ (t ^ (t << 1));
+    }
+    void set_one_step() {
+        for (int k = 0; k < 160; k++) { uint32_t v[5] = {0, 0, 0, 0, 0}; v[k / 32] = 1u << (k % 32); step_linear(v); for (int w = 0; w < 5; w++) row[k][w] = v[w]; }
+    }
+    void apply(const uint32_t in[5], uint32_t out[5]) const {
+        uint32_t r[5] = {0, 0, 0, 0, 0};
+        for (int k = 0; k < 160; k++) if ((in[k / 32] >> (k % 32)) & 1u) for (int w = 0; w < 5; w++) r[w] ^= row[k][w];
+        for (int w = 0; w < 5; w++) out[w] = r[w];
+    }
+    // this = this followed by other
+    void then(const XorwowJump& other) { for (int k = 0; k < 160; k++) other.apply(row[k], row[k]); }
+    static XorwowJump power(unsigned long long n) {
+        XorwowJump result; for (int k = 0; k < 160; k++) for (int w = 0; w < 5; w++) result.row[k][w] = (w == k / 32) ? (1u << (k % 32)) : 0u; // identity
+        XorwowJump base; base.set_one_step();
+        while (n) { if (n & 1ull) result.then(base); XorwowJump sq = base; sq.then(base); base = sq; n >>= 1; }
+        return result;
+    }
+};
+constexpr int kDrawsPerSeq = 3 * kSeqLen;                 // 30 one-dimensional + 30 two-dimensional draws
+constexpr int kDrawsPerPass = kNumSeq * kDrawsPerSeq;
+// states0: kNumSeq x 6 words (v[5], d) = state of the stream right before sequence s of pass 0
+inline void device_generator_data(uint32_t* states0, XorwowJump* jump_to_next_pass) {
+    SamplerTableGenerator g;
+    for (int s = 0; s < kNumSeq; s++) {
+        for (int w = 0; w < 5; w++) states0[s * 6 + w] = g.v[w];
+        states0[s * 6 + 5] = g.d;
+        for (int i = 0; i < kDrawsPerSeq; i++) g.next();
+    }
+    *jump_to_next_pass = XorwowJump::power((unsigned long long)(kDrawsPerPass - kDrawsPerSeq));
+}
+
 } // namespace ctlb

@@ -16,7 +16,8 @@ struct Window { // which pixels a pass renders
     int mode;   // 0 = rectangle [x0,x1) x [y0,y1); 1 = interleaved tiles
     int x0, y0, x1, y1;
     int tile_w, tile_h, part, n_parts, tiles_x, tiles_y;
-    int n_slots;
+    int n_slots;   // pixels of the window (paths per pass)
+    int n_passes;  // passes rendered by this wavefront; path slot = pass * n_slots + pixel slot
 };
 
 // SoA path state, indexed by path id (= window slot)
@@ -24,7 +25,7 @@ struct PathState {
     float4* cf;   // throughput rgb, brdf_scattering_pdf
     float4* cl;   // radiance rgb, -
     float4* nor;  // last_nor xyz, packed (depth | specular<<8 | i1<<9 | i2<<19)
-    float4* px;   // pX, pY, sampler index bits, valid flag
+    float4* px;   // pX, pY, sampler index bits, (pass-in-batch + 1) as uint bits (0 = no path)
 };
 
 struct Queues {
@@ -63,22 +64,59 @@ CTL_DEV bool slot_to_pixel(const Window& W, int s, int img_w, int img_h, int& x,
     return x >= 0 && y >= 0 && x < img_w && y < img_h;
 }
 
+// ---- sample tables on the device: SamplingSequenceGeneratorHost<IndependantSamplingSequenceGenerator>::Compute
+// (Kernel/Sampler.h:36-85) + CudaRNG host twin (Base/CudaRandom.h:108-127), bit-identical, one thread per sequence.
+// states: kNumSeq x 6 words, the stream state right before this thread's slice of the NEXT pass to generate (updated);
+// jump: 160 x 5 words = skip (4096*90 - 90) draws (csrc/sampler_tables.h).  Fills n_passes consecutive table sets.
+__global__ void __launch_bounds__(128) k_gen_tables(uint32_t* __restrict__ states, const uint32_t* __restrict__ jump, int n_passes, float* __restrict__ d1, float2* __restrict__ d2) {
+    __shared__ uint32_t sj[160 * 5];
+    for (int i = threadIdx.x; i < 160 * 5; i += blockDim.x) sj[i] = jump[i];
+    __syncthreads();
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N_SEQ) return;
+    uint32_t v0 = states[s * 6], v1 = states[s * 6 + 1], v2 = states[s * 6 + 2], v3 = states[s * 6 + 3], v4 = states[s * 6 + 4], d = states[s * 6 + 5];
+    auto next_float = [&]() {
+        const uint32_t t = v0 ^ (v0 >> 2);
+        v0 = v1; v1 = v2; v2 = v3; v3 = v4;
+        v4 = (v4 ^ (v4 << 4)) ^ (t ^ (t << 1));
+        d += 362437u;
+        const float f = __uint2float_rn(v4 + d) * 2.3283064e-10f + (2.3283064e-10f / 2.0f); // curand_uniform, no FMA contraction (-fmad=false)
+        return f * (1 - 1e-5f);
+    };
+    for (int p = 0; p < n_passes; p++) {
+        float* t1 = d1 + (size_t)p * N_SEQ * SEQ_LEN; float2* t2 = d2 + (size_t)p * N_SEQ * SEQ_LEN;
+        for (int i = 0; i < SEQ_LEN; i++) t1[i * N_SEQ + s] = next_float();
+        for (int i = 0; i < SEQ_LEN; i++) { const float y = next_float(), x = next_float(); t2[i * N_SEQ + s] = make_float2(x, y); } // y is drawn first (sampler_tables.h)
+        // jump to this sequence's slice of the next pass
+        uint32_t in[5] = {v0, v1, v2, v3, v4}, r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0;
+#pragma unroll
+        for (int w = 0; w < 5; w++)
+            for (int b = 0; b < 32; b++)
+                if ((in[w] >> b) & 1u) { const uint32_t* row = sj + (w * 32 + b) * 5; r0 ^= row[0]; r1 ^= row[1]; r2 ^= row[2]; r3 ^= row[3]; r4 ^= row[4]; }
+        v0 = r0; v1 = r1; v2 = r2; v3 = r3; v4 = r4;
+        d += 362437u * (uint32_t)(N_SEQ * 3 * SEQ_LEN - 3 * SEQ_LEN);
+    }
+    states[s * 6] = v0; states[s * 6 + 1] = v1; states[s * 6 + 2] = v2; states[s * 6 + 3] = v3; states[s * 6 + 4] = v4; states[s * 6 + 5] = d;
+}
+
 // ---- generate: pathKernel2 prologue (PathTracer.cu:184-190) -------------------
 __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene S, const __grid_constant__ Window W, PathState st,
                                                    float4* rays, uint32_t* paths, unsigned* q_count) {
-    const int n_round = (W.n_slots + 31) & ~31;
+    const int n_total = W.n_slots * W.n_passes;
+    const int n_round = (n_total + 31) & ~31;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_round; s += gridDim.x * blockDim.x) {
         int x = 0, y = 0;
-        const bool in_range = s < W.n_slots;
-        const bool valid = in_range && slot_to_pixel(W, s, S.img_w, S.img_h, x, y);
+        const bool in_range = s < n_total;
+        const unsigned pass = (unsigned)(s / W.n_slots);
+        const bool valid = in_range && slot_to_pixel(W, s % W.n_slots, S.img_w, S.img_h, x, y);
         V3 o = mk(0, 0, 0), d = mk(0, 0, 1);
         if (valid) {
-            Sampler rng; rng.idx = (unsigned)(y * S.img_w + x); rng.i1 = 0; rng.i2 = 0;
+            Sampler rng; rng.idx = (unsigned)(y * S.img_w + x); rng.i1 = 0; rng.i2 = 0; rng.tab = pass;
             const float2 j = rng.f2(S);
             const float pX = (float)x + j.x, pY = (float)y + j.y;
             rng.f2(S); // aperture sample: drawn, unused by the pinhole camera
             camera_ray(S, pX, pY, o, d);
-            st.px[s] = make_float4(pX, pY, __uint_as_float(rng.idx), 1.0f);
+            st.px[s] = make_float4(pX, pY, __uint_as_float(rng.idx), __uint_as_float(pass + 1u));
             st.cf[s] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
             st.cl[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             st.nor[s] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(pack_ctl(0, false, rng.i1, rng.i2)));
@@ -203,7 +241,8 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene S,
                 const uint32_t ctl = __float_as_uint(nor4.w);
                 const int depth = (int)(ctl & 0xff) + 1; // depth++ at loop entry
                 bool specularBounce = (ctl & 256u) != 0;
-                Sampler rnd; rnd.idx = __float_as_uint(st.px[p].z); rnd.i1 = (ctl >> 9) & 0x3ff; rnd.i2 = ctl >> 19;
+                const float4 px4 = st.px[p];
+                Sampler rnd; rnd.idx = __float_as_uint(px4.z); rnd.tab = __float_as_uint(px4.w) - 1u; rnd.i1 = (ctl >> 9) & 0x3ff; rnd.i2 = ctl >> 19;
                 // getBsdfSample (Kernel/TraceResult.cu:16-43)
                 DG dg; uint32_t mat_local;
                 dg.P = ro + rd * ha.x;
@@ -290,10 +329,10 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene S,
 }
 
 // ---- finish: img.AddSample(pX.x, pX.y, imp * L) (PathTracer.cu:191-192, Image.cu:22-44) ----
-__global__ void __launch_bounds__(256) k_finish(int n_slots, PathState st, float* accum, int img_w, int img_h) {
+__global__ void __launch_bounds__(256) k_finish(int n_slots /* all passes */, PathState st, float* accum, int img_w, int img_h) {
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
         const float4 px = st.px[s];
-        if (px.w == 0.0f) continue;
+        if (__float_as_uint(px.w) == 0u) continue;
         const float4 c = st.cl[s];
         const float r = fmaxf(0.0f, c.x), g = fmaxf(0.0f, c.y), b = fmaxf(0.0f, c.z);
         const int x = (int)floorf(px.x), y = (int)floorf(px.y);

@@ -216,7 +216,10 @@ void     ctl_destroy(ctl_ctx*);
 int      ctl_resize(ctl_ctx*, int width, int height);
 /* == m_sParameters: "MaxPathLength" (50), "RRStartDepth" (5), "Direct" (1),
  *    "Regularization" (0, only 0 supported)  (Integrators/PathTracer.h:10-20);
- *    extras: "SortMode" (0 none, 1 material), "StageTimers" (0/1), "CaptureBounce" (0 = off). */
+ *    extras: "SortMode" (0 none, 1 material), "StageTimers" (0/1), "CaptureBounce" (0 = off),
+ *    "DeviceSampleTables" (1 = tables generated by a CUDA kernel, bit-identical to the host XORWOW generator; 0 = generated on the
+ *    host and copied H2D every pass like the reference's UpdateKernel), "TraversalKernel" (0 persistent, 1 simple A/B baseline),
+ *    "TraversalBlocksPerSM", "TravThT/L/F", "TravThNExit" (tuning). */
 int ctl_set_param_i(ctl_ctx*, const char* key, int value);
 int ctl_get_param_i(ctl_ctx*, const char* key, int* value);
 /* == UpdateKernel scene half (Kernel/TraceHelper.cu:182-217): host view copied to HBM */
@@ -244,6 +247,13 @@ int ctl_render_pass(ctl_ctx*, int new_trace, int x0, int y0, int x1, int y1);
 /* Interleaved-tile variant for multi-GPU: renders tiles (tile_w x tile_h) whose
  * index % n_parts == part. */
 int ctl_render_pass_tiled(ctl_ctx*, int new_trace, int tile_w, int tile_h, int part, int n_parts);
+/* n_passes consecutive DoPass calls fused into ONE wavefront (paths = pixels x passes; every path uses the sample tables
+ * of its own pass, so each path is identical to the one the sequential passes would trace; only the order of the float
+ * atomics into PixelData differs).  Keeps launches large when the image is split over many GPUs and amortises launch
+ * overhead; path state is ~230 B x pixels x n_passes of HBM.  part=0, n_parts=1 renders the whole image. */
+int ctl_render_passes_tiled(ctl_ctx*, int new_trace, int n_passes, int tile_w, int tile_h, int part, int n_parts);
+/* Device copy-back of sample-table set `table_set` (0 .. passes of the last batch - 1) for verification. */
+int ctl_read_sample_tables(ctl_ctx*, int table_set, float* d1, float* d2);
 int ctl_synchronize(ctl_ctx*);
 /* == Image accumulator: PixelData[w*h], reference layout. */
 int ctl_read_accum(ctl_ctx*, ctl_pixel_data* host_out);

@@ -330,3 +330,49 @@ def test_config1_cornell_256_golden(built_lib):
     assert img["weight_sum"].sum() == st[2] and abs(t.getRaysInLastPass() - int(st[3])) <= 2e-3 * st[3]
     assert np.allclose(img["rgb"].astype(np.float64).mean(axis=(1, 2)), _GOLD["config1_cornell_256_1spp_rowmeans"], rtol=2e-3, atol=1e-5)
     t.close()
+
+
+# ------------------------------------------------------------------ device-side sample tables, fused passes
+def test_device_sample_tables_bit_exact(built_lib):
+    """k_gen_tables (XORWOW with GF(2) jump-ahead, one thread per sequence) == the host generator == the reference (golden)."""
+    s, t = make("cornell", 32, 32, 4)
+    t.DoPasses(3, new_trace=True); t.synchronize()
+    for k in range(3):
+        d1, d2 = t.readSampleTables(k)
+        h1, h2 = ctl.generate_sample_tables(k)
+        assert np.array_equal(d1.view(np.uint32), h1.view(np.uint32)) and np.array_equal(d2.view(np.uint32), h2.view(np.uint32))
+    t.DoPasses(2); t.synchronize()            # continues the stream: passes 3, 4
+    d1, d2 = t.readSampleTables(1)
+    h1, h2 = ctl.generate_sample_tables(4)
+    assert np.array_equal(d1.view(np.uint32), h1.view(np.uint32)) and np.array_equal(d2.view(np.uint32), h2.view(np.uint32))
+    t.DoPass(False); t.synchronize()           # pass 5
+    assert np.array_equal(t.readSampleTables(0)[0][:8192].view(np.uint32), _GOLD["tables_p5_d1_head"].view(np.uint32))
+    # host-generated tables (reference UpdateKernel behaviour) give the same tables
+    t.setParameter("DeviceSampleTables", 0)
+    t.DoPasses(2, new_trace=True); t.synchronize()
+    assert np.array_equal(t.readSampleTables(1)[1].view(np.uint32), ctl.generate_sample_tables(1)[1].view(np.uint32))
+    t.close()
+
+
+def test_fused_passes_equal_sequential_passes(built_lib, orc):
+    w, h = 160, 96
+    s, t = make("soup", w, h, 8)
+    for p in range(6):
+        t.DoPass(p == 0)
+    t.synchronize(); seq = t.readAccumulator().copy(); rays_seq = t.getTotalRays()
+    r0 = t.getTotalRays()
+    t.DoPasses(6, new_trace=True); t.synchronize(); fused = t.readAccumulator().copy()
+    assert t.getTotalRays() - r0 == rays_seq and t.getNumPassesDone() == 6
+    assert np.array_equal(fused["weight_sum"], seq["weight_sum"])
+    assert np.allclose(fused["rgb"], seq["rgb"], rtol=2e-6, atol=1e-6)        # same paths; only the float-atomic order differs
+    # 2 + 4 split with host-generated tables (the reference's UpdateKernel behaviour): still the same image
+    t.setParameter("DeviceSampleTables", 0)
+    t.DoPasses(2, new_trace=True); t.DoPasses(4); t.synchronize(); split = t.readAccumulator()
+    assert np.array_equal(split["weight_sum"], seq["weight_sum"]) and np.allclose(split["rgb"], seq["rgb"], rtol=2e-6, atol=1e-6)
+    t.close()
+    s2, t2 = make("cornell7", 96, 96, 8)
+    t2.DoPasses(8, new_trace=True); t2.synchronize()
+    img = t2.readAccumulator()
+    ref = np.ascontiguousarray(_GOLD["image_cornell7_96x96_8spp"]).view(api.PIXEL_DTYPE).reshape(96, 96)
+    assert (rel_l2(img["rgb"], ref["rgb"]) <= 1e-3).mean() >= 0.99 and np.array_equal(img["weight_sum"], ref["weight_sum"])
+    t2.close()
