@@ -67,7 +67,7 @@ struct ctl_ctx {
     ctlb::SamplerTableGenerator gen;
     // wavefront state
     DevBuf<float4> cf, cl, nor, px, rays_a, rays_b, hit_a, sh_rays, sh_payload, capture;
-    DevBuf<uint32_t> path_a, path_b, hit_node;
+    DevBuf<uint32_t> path_a, path_b, path_c, hit_node, sort_keys; DevBuf<float4> rays_c; DevBuf<unsigned> sort_hist, sort_offsets;
     DevBuf<unsigned> counters;
     DevBuf<unsigned long long> stats; // [0] rays_last [1] rays_total [2..4] ext visits [5] ext rays [6..8] shadow visits [9] shadow rays
     DevBuf<float> own_accum; float* accum = nullptr;
@@ -176,7 +176,7 @@ void ctl_destroy(ctl_ctx* c) {
     c->d_tab1.release(); c->d_tab2.release(); c->d_states.release(); c->d_states0.release(); c->d_jump.release();
     if (c->h_tab1) cudaFreeHost(c->h_tab1); if (c->h_tab2) cudaFreeHost(c->h_tab2); if (c->h_tab_free) cudaEventDestroy(c->h_tab_free);
     c->cf.release(); c->cl.release(); c->nor.release(); c->px.release(); c->rays_a.release(); c->rays_b.release(); c->hit_a.release(); c->sh_rays.release();
-    c->sh_payload.release(); c->capture.release(); c->path_a.release(); c->path_b.release(); c->hit_node.release(); c->counters.release(); c->stats.release();
+    c->sh_payload.release(); c->capture.release(); c->path_a.release(); c->path_b.release(); c->path_c.release(); c->rays_c.release(); c->sort_keys.release(); c->sort_hist.release(); c->sort_offsets.release(); c->hit_node.release(); c->counters.release(); c->stats.release();
     c->own_accum.release(); c->d_captured_n.release();
     for (auto e : c->stage_ev) cudaEventDestroy(e);
     cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_stop);
@@ -248,6 +248,7 @@ int ctl_upload_scene(ctl_ctx* c, const ctl_scene_view* v) {
     S.d1 = c->d_tab1.p; S.d2 = (const float2*)c->d_tab2.p;
     S.num_lights = v->num_lights;
     memcpy(S.light_indices, v->light_indices, sizeof(S.light_indices)); memcpy(S.light_cdf, v->light_cdf, sizeof(S.light_cdf));
+    for (int k = 0; k < 3; k++) { S.box_min[k] = v->box_min[k]; const float e = v->box_max[k] - v->box_min[k]; S.box_inv_extent[k] = e > 0 ? 1.0f / e : 0.0f; }
     S.camera = v->camera; S.ray_eps = v->ray_eps; S.scene_start = v->scene_start_node; S.n_nodes = v->n_nodes;
     S.img_w = c->w; S.img_h = c->h;
     c->has_scene = true;
@@ -382,6 +383,10 @@ static int ensure_state(ctl_ctx* c, size_t n) {
     CK(c->cf.ensure(n)); CK(c->cl.ensure(n)); CK(c->nor.ensure(n)); CK(c->px.ensure(n));
     CK(c->rays_a.ensure(2 * n)); CK(c->rays_b.ensure(2 * n)); CK(c->hit_a.ensure(n)); CK(c->hit_node.ensure(n));
     CK(c->sh_rays.ensure(2 * n)); CK(c->sh_payload.ensure(n)); CK(c->path_a.ensure(n)); CK(c->path_b.ensure(n));
+    if (c->sort_mode) {
+        CK(c->rays_c.ensure(2 * n)); CK(c->path_c.ensure(n)); CK(c->sort_keys.ensure(n));
+        if (!c->sort_hist.p) { CK(c->sort_hist.ensure(SORT_BUCKETS)); CK(c->sort_offsets.ensure(SORT_BUCKETS)); CK(cudaMemsetAsync(c->sort_hist.p, 0, SORT_BUCKETS * sizeof(unsigned), c->stream)); }
+    }
     return 0;
 }
 
@@ -425,6 +430,7 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
     launches++;
     ShadeParams P = {c->max_path_length, c->rr_start, c->direct};
     float4* rin = c->rays_a.p; float4* rout = c->rays_b.p; uint32_t* pin = c->path_a.p; uint32_t* pout = c->path_b.p;
+    float4* rspare = c->rays_c.p; uint32_t* pspare = c->path_c.p;
     for (int b = 0; b < c->max_path_length; b++) {
         stage_mark(c, 1);
         if (c->capture_bounce == b + 1) {
@@ -434,8 +440,16 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
         if (c->instrumented) launch_intersect<0, false, true>(c, g_trav, c->stream, c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, c->stats.p + 2);
         else launch_intersect<0, false, false>(c, g_trav, c->stream, c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, nullptr);
         stage_mark(c, 2);
-        Queues Q = {rin, pin, rout, pout, c->hit_a.p, c->hit_node.p, c->sh_rays.p, c->sh_payload.p};
+        const bool sort_next = c->sort_mode == 1 && b + 1 < c->max_path_length;
+        Queues Q = {rin, pin, rout, pout, c->hit_a.p, c->hit_node.p, c->sh_rays.p, c->sh_payload.p, sort_next ? c->sort_keys.p : nullptr, sort_next ? c->sort_hist.p : nullptr};
         k_shade<<<g_light, 128, 0, c->stream>>>(c->scene, P, st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b);
+        if (sort_next) { // counting sort of the next bounce's extension queue by (octant, origin cell)
+            stage_mark(c, 4);
+            k_sort_scan<<<1, 1024, 0, c->stream>>>(c->sort_hist.p, c->sort_offsets.p);
+            k_sort_scatter<<<g_light, 256, 0, c->stream>>>(ctr + CTR_Q + b + 1, c->sort_keys.p, rout, pout, c->sort_offsets.p, rspare, pspare);
+            std::swap(rout, rspare); std::swap(pout, pspare);
+            launches += 2;
+        }
         stage_mark(c, 3);
         if (c->direct) {
             if (c->instrumented) launch_intersect<1, true, true>(c, g_trav, c->stream, c->scene, c->sh_rays.p, ctr + CTR_SH + b, 0, ctr + CTR_WORK + 2 * b + 1, nullptr, nullptr, c->sh_payload.p, c->cl.p, nullptr, c->stats.p + 6);

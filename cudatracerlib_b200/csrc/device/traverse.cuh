@@ -34,6 +34,7 @@ struct DScene {
     float light_cdf[CTL_MAX_NUM_LIGHTS];
     ctl_camera camera;
     float ray_eps;
+    float box_min[3], box_inv_extent[3]; // scene box (m_sBox) for the ray-sort keys: cell = (o - min) * inv_extent
     int scene_start;
     uint32_t n_nodes;
     int img_w, img_h;

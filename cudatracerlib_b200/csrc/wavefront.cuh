@@ -33,6 +33,7 @@ struct Queues {
     float4* rays_out; uint32_t* path_out;  // next bounce
     float4* hit_a;    uint32_t* hit_node;  // (dist,u,v,tri) + node, by queue position
     float4* sh_rays;  float4* sh_payload;  // shadow rays + (pending radiance rgb, path id)
+    uint32_t* keys_out; unsigned* hist;    // SortMode 1: sort key of every emitted extension ray + bucket histogram (else null)
 };
 
 CTL_DEV unsigned lane_id() { return threadIdx.x & 31; }
@@ -212,6 +213,45 @@ __global__ void __launch_bounds__(128) k_intersect(const __grid_constant__ DScen
     }
 }
 
+// ---- ray sorting between bounces (the wavefront scheduler's coherence step) -----------------------------------------
+// key = direction octant (3 bits, major) | 15-bit Morton code of the origin's cell in a 32^3 grid over the scene box:
+// rays that start in the same cell and head into the same octant take near-identical top-of-tree paths, so a warp of
+// the traversal kernel stays converged longer and its node fetches hit the same L1 lines.  Counting sort: histogram
+// (atomics in k_shade) -> exclusive scan (one block) -> scatter of the 36-byte (ray, path id) records.
+constexpr int SORT_BUCKETS = 1 << 18;
+CTL_DEV uint32_t spread5(uint32_t x) { x &= 31u; x = (x | (x << 8)) & 0x100fu; x = (x | (x << 4)) & 0x10c3u; x = (x | (x << 2)) & 0x1249u; return x; }
+CTL_DEV uint32_t ray_sort_key(const DScene& S, V3 o, V3 d) {
+    const float fx = (o.x - S.box_min[0]) * S.box_inv_extent[0], fy = (o.y - S.box_min[1]) * S.box_inv_extent[1], fz = (o.z - S.box_min[2]) * S.box_inv_extent[2];
+    const uint32_t cx = (uint32_t)fminf(fmaxf(fx * 32.0f, 0.0f), 31.0f), cy = (uint32_t)fminf(fmaxf(fy * 32.0f, 0.0f), 31.0f), cz = (uint32_t)fminf(fmaxf(fz * 32.0f, 0.0f), 31.0f);
+    const uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+    return (oct << 15) | spread5(cx) | (spread5(cy) << 1) | (spread5(cz) << 2);
+}
+// exclusive scan of hist[SORT_BUCKETS] into offsets; hist is zeroed for the next bounce.  One block of 1024 threads.
+__global__ void __launch_bounds__(1024) k_sort_scan(unsigned* __restrict__ hist, unsigned* __restrict__ offsets) {
+    __shared__ unsigned warp_sums[32];
+    constexpr int PER = SORT_BUCKETS / 1024;
+    const int t = threadIdx.x;
+    unsigned local = 0;
+    for (int i = 0; i < PER; i++) local += hist[t * PER + i];
+    unsigned incl = local;
+    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if ((t & 31) >= o) incl += v; }
+    if ((t & 31) == 31) warp_sums[t >> 5] = incl;
+    __syncthreads();
+    if (t < 32) { unsigned w = warp_sums[t], wi = w; for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, wi, o); if (t >= o) wi += v; } warp_sums[t] = wi - w; }
+    __syncthreads();
+    unsigned run = warp_sums[t >> 5] + incl - local;
+    for (int i = 0; i < PER; i++) { const unsigned h = hist[t * PER + i]; offsets[t * PER + i] = run; run += h; hist[t * PER + i] = 0; }
+}
+__global__ void __launch_bounds__(256) k_sort_scatter(const unsigned* __restrict__ n_ptr, const uint32_t* __restrict__ keys, const float4* __restrict__ rays_in, const uint32_t* __restrict__ path_in,
+                                                       unsigned* __restrict__ offsets, float4* __restrict__ rays_out, uint32_t* __restrict__ path_out) {
+    const int n = (int)*n_ptr;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned pos = atomicAdd(offsets + __ldg(keys + i), 1u);
+        rays_out[2 * pos] = __ldg(rays_in + 2 * i); rays_out[2 * pos + 1] = __ldg(rays_in + 2 * i + 1);
+        path_out[pos] = __ldg(path_in + i);
+    }
+}
+
 // ---- shade: one path vertex (PathTracer.cu:58-96) ----------------------------------
 struct ShadeParams { int max_path_length, rr_start, direct; };
 
@@ -318,6 +358,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene S,
             Q.rays_out[2 * jq] = make_float4(no.x, no.y, no.z, S.ray_eps);
             Q.rays_out[2 * jq + 1] = make_float4(nd.x, nd.y, nd.z, FLT_MAX);
             Q.path_out[jq] = p;
+            if (Q.keys_out) { const uint32_t key = ray_sort_key(S, no, nd); Q.keys_out[jq] = key; atomicAdd(Q.hist + key, 1u); }
         }
         const int ks = warp_append(shadow, n_shadow);
         if (shadow) {

@@ -1,4 +1,5 @@
-"""Small fixed target for ncu: N passes of one workload (default c2 @1080p, depth 8). Usage: profile_target.py [workload] [passes]"""
+"""Small fixed target for ncu: N fused-pass wavefronts of one workload (default c2 @1080p, depth 8, 8 passes per wavefront).
+Usage: profile_target.py [workload] [wavefronts] [passes_per_wavefront]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cudatracerlib_b200 import Scene, PathTracer
@@ -6,10 +7,11 @@ from bench import WORKLOADS
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+batch = int(sys.argv[3]) if len(sys.argv) > 3 else 8
 kind, w, h, spp, depth, _ = WORKLOADS[wl]
 s = Scene(kind, w, h)
 t = PathTracer(w, h); t.InitializeScene(s); t.setParameter("MaxPathLength", depth)
 for i in range(n):
-    t.DoPass(i == 0)
+    t.DoPasses(batch, new_trace=(i == 0))
 t.synchronize()
-print(wl, "rays last pass", t.getRaysInLastPass(), "sec", t.getLastTimeSpentRenderingSec())
+print(wl, "rays last wavefront", t.getRaysInLastPass(), "sec", t.getLastTimeSpentRenderingSec())

@@ -376,3 +376,31 @@ def test_fused_passes_equal_sequential_passes(built_lib, orc):
     ref = np.ascontiguousarray(_GOLD["image_cornell7_96x96_8spp"]).view(api.PIXEL_DTYPE).reshape(96, 96)
     assert (rel_l2(img["rgb"], ref["rgb"]) <= 1e-3).mean() >= 0.99 and np.array_equal(img["weight_sum"], ref["weight_sum"])
     t2.close()
+
+
+def test_ray_sorting_preserves_results(built_lib):
+    """SortMode=1 (counting sort of every bounce's extension queue by direction octant + origin cell) reorders work only."""
+    w, h = 192, 108
+    for kind in ("soup", "c3"):
+        s, t = make(kind, w, h, 8)
+        t.DoPasses(2, new_trace=True); t.synchronize(); a = t.readAccumulator().copy(); ra = t.getRaysInLastPass(); qa = t.queueSizes(8)
+        t.setParameter("SortMode", 1)
+        t.DoPasses(2, new_trace=True); t.synchronize(); b = t.readAccumulator().copy(); rb = t.getRaysInLastPass(); qb = t.queueSizes(8)
+        assert ra == rb and np.array_equal(qa[0], qb[0]) and np.array_equal(qa[1], qb[1])
+        assert np.array_equal(a["weight_sum"], b["weight_sum"])
+        assert np.allclose(a["rgb"], b["rgb"], rtol=2e-6, atol=1e-6)
+        # the sorted queue really is sorted: capture bounce 3 and check the keys are non-decreasing
+        t.setParameter("CaptureBounce", 3)
+        t.DoPass(True); t.synchronize()
+        rays = t.capturedRays(w * h)
+        t.setParameter("CaptureBounce", 0)
+        lo = np.array(list(s.view.box_min), np.float32); hi = np.array(list(s.view.box_max), np.float32)
+        inv = (np.float32(1) / (hi - lo)).astype(np.float32)
+        c = np.clip(((rays["o"] - lo) * inv * np.float32(32)), 0, 31).astype(np.uint32)
+
+        def spread(x):
+            x = x & 31; x = (x | (x << 8)) & 0x100f; x = (x | (x << 4)) & 0x10c3; x = (x | (x << 2)) & 0x1249; return x
+        octant = (rays["d"][:, 0] < 0).astype(np.uint32) | ((rays["d"][:, 1] < 0).astype(np.uint32) << 1) | ((rays["d"][:, 2] < 0).astype(np.uint32) << 2)
+        key = (octant << 15) | spread(c[:, 0]) | (spread(c[:, 1]) << 1) | (spread(c[:, 2]) << 2)
+        assert len(rays) > 1000 and np.all(np.diff(key.astype(np.int64)) >= 0)
+        t.close()
