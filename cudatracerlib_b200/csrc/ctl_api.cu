@@ -51,7 +51,7 @@ struct ctl_ctx {
     int n_sm = 148;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     // parameters (Integrators/PathTracer.h:10-20)
-    int max_path_length = 50, rr_start = 5, direct = 1, regularization = 0, sort_mode = 0, stage_timers = 0, capture_bounce = 0, trav_kernel = 0, trav_blocks_per_sm = 8;
+    int max_path_length = 50, rr_start = 5, direct = 1, regularization = 0, sort_mode = 0, stage_timers = 0, capture_bounce = 0, trav_kernel = 0, trav_blocks_per_sm = 8, shade_blocks_per_sm = 8, smem_carveout = -1;
     // scene
     DevBuf<ctl_bvh_node> d_scene_nodes, d_bvh_nodes; DevBuf<ctl_woop_tri> d_woop; DevBuf<uint32_t> d_tri_index; DevBuf<ctl_tri_data> d_tri_data;
     DevBuf<ctl_mesh> d_meshes; DevBuf<ctl_node> d_nodes; DevBuf<float> d_xf, d_inv_xf; DevBuf<ctl_material> d_materials; DevBuf<ctl_light> d_lights;
@@ -207,6 +207,12 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "TraversalKernel") { if (v < 0 || v > 1) return set_err("TraversalKernel must be 0 or 1"); c->trav_kernel = v; }
     else if (k == "TravThT") c->tune.th_t = v; else if (k == "TravThL") c->tune.th_l = v; else if (k == "TravThF") c->tune.th_f = v;
     else if (k == "TravThNExit") c->tune.th_n_exit = v;
+    else if (k == "ShadeBlocksPerSM") { if (v < 1 || v > 16) return set_err("ShadeBlocksPerSM out of range [1,16]"); c->shade_blocks_per_sm = v; }
+    else if (k == "TravSmemCarveout") { // experiment: shared-memory carve-out (percent) of the traversal kernels = how much L1 they lose
+        c->smem_carveout = v;
+        CK(cudaFuncSetAttribute(k_intersect<0, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, v));
+        CK(cudaFuncSetAttribute(k_intersect<1, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, v));
+    }
     else if (k == "TraversalBlocksPerSM") { if (v < 1 || v > 16) return set_err("TraversalBlocksPerSM out of range [1,16]"); c->trav_blocks_per_sm = v; }
     else return set_err("unknown parameter key: " + k);
     return 0;
@@ -422,7 +428,7 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
     if (c->instrumented) CK(cudaMemsetAsync(c->stats.p + 2, 0, 8 * sizeof(unsigned long long), c->stream));
     unsigned* ctr = c->counters.p;
     PathState st = {c->cf.p, c->cl.p, c->nor.p, c->px.p};
-    const int g_light = grid_for(c, 8);
+    const int g_light = grid_for(c, c->shade_blocks_per_sm);
     const int g_trav = grid_for(c, c->trav_blocks_per_sm);
     uint32_t launches = 0;
     stage_mark(c, 0);
