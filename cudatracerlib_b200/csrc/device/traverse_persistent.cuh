@@ -18,7 +18,7 @@
 
 namespace ctld {
 
-constexpr int TP_CHUNK = 128;    // rays a warp claims per global atomic
+constexpr int TP_CHUNK = 128;    // rays a warp claims per global atomic (large queues; small queues use smaller chunks, see chunk below)
 constexpr int TP_STACK = 64;     // BVHTraversal.h: int traversalStack[64]
 
 struct TravOut { // where results go (MODE-dependent, see k_intersect)
@@ -47,7 +47,10 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, const float4* 
     const float4* nbase = S.scene_nodes;
     const float4* wbase = S.woop; const uint32_t* ibase = S.tri_index; uint32_t tri_base = 0;
 
-    // warp-uniform pool of claimed rays
+    // warp-uniform pool of claimed rays.  Chunk size: ~1/8 of a warp's fair share, 32..TP_CHUNK, so that small queues
+    // (late bounces, image split over many GPUs) still balance across the grid's warps.
+    const int n_warps = (int)(gridDim.x * (blockDim.x >> 5));
+    const int chunk = max(32, min(TP_CHUNK, (n / (n_warps * 8)) & ~31));
     int pool_next = 0, pool_end = 0;
     bool exhausted = (n <= 0);
 
@@ -108,10 +111,10 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, const float4* 
                 while (need > 0) {
                     if (pool_next >= pool_end) {
                         unsigned base = 0;
-                        if (lane == 0) base = atomicAdd(work_ctr, (unsigned)TP_CHUNK);
+                        if (lane == 0) base = atomicAdd(work_ctr, (unsigned)chunk);
                         base = __shfl_sync(0xffffffffu, base, 0);
                         if ((int)base >= n) { exhausted = true; break; }
-                        pool_next = (int)base; pool_end = min((int)base + TP_CHUNK, n);
+                        pool_next = (int)base; pool_end = min((int)base + chunk, n);
                     }
                     const int take = min(need, pool_end - pool_next);
                     const int r = my_rank - got_before;
