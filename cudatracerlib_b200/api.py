@@ -124,6 +124,7 @@ def lib():
     L.ctl_synchronize.argtypes = [vp]
     L.ctl_read_accum.argtypes = [vp, vp]
     L.ctl_accum_device_ptr.argtypes = [vp]; L.ctl_accum_device_ptr.restype = vp
+    L.ctl_resolve_srgb8.argtypes = [vp, C.c_float, vp, vp]
     L.ctl_set_accum_device_ptr.argtypes = [vp, vp]
     L.ctl_stream.argtypes = [vp]; L.ctl_stream.restype = vp
     L.ctl_set_stream.argtypes = [vp, vp]
@@ -277,6 +278,12 @@ class PathTracer:
         out = np.zeros(self.w * self.h, PIXEL_DTYPE)
         _check(lib().ctl_read_accum(self._ctx, _ptr(out)))
         return out.reshape(self.h, self.w)
+
+    def resolveSRGB8(self, splat_scale=0.0):
+        """applyImagePipeline(tracer, img) with no filter / post-process: (h, w, 4) uint8 sRGB image."""
+        out = np.zeros((self.h, self.w, 4), np.uint8)
+        _check(lib().ctl_resolve_srgb8(self._ctx, float(splat_scale), None, _ptr(out)))
+        return out
 
     def accumDevicePtr(self):
         return lib().ctl_accum_device_ptr(self._ctx)

@@ -70,7 +70,7 @@ struct ctl_ctx {
     DevBuf<uint32_t> path_a, path_b, path_c, hit_node, sort_keys; DevBuf<float4> rays_c; DevBuf<unsigned> sort_hist, sort_offsets;
     DevBuf<unsigned> counters;
     DevBuf<unsigned long long> stats; // [0] rays_last [1] rays_total [2..4] ext visits [5] ext rays [6..8] shadow visits [9] shadow rays
-    DevBuf<float> own_accum; float* accum = nullptr;
+    DevBuf<float> own_accum; float* accum = nullptr; DevBuf<uchar4> resolve_tmp;
     unsigned captured_n = 0; DevBuf<unsigned> d_captured_n;
     uint32_t passes_done = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
@@ -177,7 +177,7 @@ void ctl_destroy(ctl_ctx* c) {
     if (c->h_tab1) cudaFreeHost(c->h_tab1); if (c->h_tab2) cudaFreeHost(c->h_tab2); if (c->h_tab_free) cudaEventDestroy(c->h_tab_free);
     c->cf.release(); c->cl.release(); c->nor.release(); c->px.release(); c->rays_a.release(); c->rays_b.release(); c->hit_a.release(); c->sh_rays.release();
     c->sh_payload.release(); c->capture.release(); c->path_a.release(); c->path_b.release(); c->path_c.release(); c->rays_c.release(); c->sort_keys.release(); c->sort_hist.release(); c->sort_offsets.release(); c->hit_node.release(); c->counters.release(); c->stats.release();
-    c->own_accum.release(); c->d_captured_n.release();
+    c->own_accum.release(); c->d_captured_n.release(); c->resolve_tmp.release();
     for (auto e : c->stage_ev) cudaEventDestroy(e);
     cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_stop);
     cudaStreamDestroy(c->own_stream);
@@ -521,6 +521,18 @@ int ctl_read_accum(ctl_ctx* c, ctl_pixel_data* out) {
     CK(cudaSetDevice(c->device));
     CK(cudaMemcpyAsync(out, c->accum, (size_t)c->w * c->h * 7 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+// == applyImagePipeline(tracer, img, filter = 0, process = 0) (Kernel/ImagePipeline/ImagePipeline.cu:54-63): PixelData -> sRGB RGBA8
+int ctl_resolve_srgb8(ctl_ctx* c, float splat_scale, void* d_rgba8, void* host_rgba8) {
+    if (!c || (!d_rgba8 && !host_rgba8)) return set_err("null argument");
+    CK(cudaSetDevice(c->device));
+    const int n = c->w * c->h;
+    uchar4* dst = (uchar4*)d_rgba8;
+    if (!dst) { CK(c->resolve_tmp.ensure((size_t)n)); dst = c->resolve_tmp.p; }
+    k_resolve_srgb8<<<grid_for(c, 8), 256, 0, c->stream>>>(c->accum, n, splat_scale, dst);
+    CK(cudaGetLastError());
+    if (host_rgba8) { CK(cudaMemcpyAsync(host_rgba8, dst, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
     return 0;
 }
 void* ctl_accum_device_ptr(ctl_ctx* c) { return c ? (void*)c->accum : nullptr; }

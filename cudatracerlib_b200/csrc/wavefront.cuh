@@ -386,6 +386,22 @@ __global__ void __launch_bounds__(256) k_finish(int n_slots /* all passes */, Pa
     }
 }
 
+// ---- resolve: the default image pipeline (no filter, no post-process): copySamplesToOutput
+// (Kernel/ImagePipeline/ImagePipeline.cu:14-21) = PixelData::toSpectrum(splatScale) (Engine/Image.h:20-27) -> toSRGB
+// (Math/Spectrum.cu:229-250) -> Float3ToCOLORREF (Math/Spectrum.h:521-526).  One thread per pixel, 28 B in, 4 B out.
+CTL_DEV float to_srgb_component(float v) { return v <= 0.0031308f ? 12.92f * v : 1.055f * powf(v, (float)(1.0 / 2.4)) - 0.055f; }
+CTL_DEV unsigned to_u8(float x) { return (unsigned)(unsigned char)(fminf(fmaxf(x, 0.0f), 1.0f) * 255.0f); }
+__global__ void __launch_bounds__(256) k_resolve_srgb8(const float* __restrict__ accum, int n_pixels, float splat_scale, uchar4* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pixels; i += gridDim.x * blockDim.x) {
+        const float* p = accum + (size_t)i * 7;
+        const float ws = __ldg(p + 6), weight = ws != 0.0f ? ws : 1.0f;
+        float c[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) c[k] = to_srgb_component(__ldg(p + k) / weight + __ldg(p + 3 + k) * splat_scale);
+        out[i] = make_uchar4((unsigned char)to_u8(c[0]), (unsigned char)to_u8(c[1]), (unsigned char)to_u8(c[2]), 255);
+    }
+}
+
 // rays of the pass = sum of extension + shadow queue sizes (every traceRay call counts, TraceHelper.cu:176)
 __global__ void k_tally(const unsigned* q_count, const unsigned* sh_count, int n_bounces, unsigned long long* rays_last, unsigned long long* rays_total) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {

@@ -257,6 +257,10 @@ int ctl_read_sample_tables(ctl_ctx*, int table_set, float* d1, float* d2);
 int ctl_synchronize(ctl_ctx*);
 /* == Image accumulator: PixelData[w*h], reference layout. */
 int ctl_read_accum(ctl_ctx*, ctl_pixel_data* host_out);
+/* == applyImagePipeline(tracer, img, 0, 0) (Kernel/ImagePipeline/ImagePipeline.cu:14-21, 54-63): the default resolve
+ * PixelData -> toSpectrum(splatScale) -> sRGB -> RGBA8 (uchar4, a = 255).  Writes w*h*4 bytes to d_rgba8 (device,
+ * asynchronous) and/or host_rgba8 (synchronous); either may be NULL.  First row of SURVEY 8f3 ("next"). */
+int ctl_resolve_srgb8(ctl_ctx*, float splat_scale, void* d_rgba8, void* host_rgba8);
 /* Device pointer of the accumulator (7*w*h floats) for in-place NCCL reduce. */
 void* ctl_accum_device_ptr(ctl_ctx*);
 /* Use caller-owned device memory (7*w*h floats) as the accumulator (e.g. a torch tensor). */

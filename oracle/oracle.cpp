@@ -989,6 +989,21 @@ long long orc_trace_events(const ctl_scene_view* S, int n, const ctl_traversal_r
     return total;
 }
 
+// Default image pipeline: copySamplesToOutput (Kernel/ImagePipeline/ImagePipeline.cu:14-21) = PixelData::toSpectrum
+// (Engine/Image.h:20-27) -> toSRGBComponent (Math/Spectrum.cu:229-235) -> Float3ToCOLORREF (Math/Spectrum.h:521-526)
+void orc_resolve_srgb8(const ctl_pixel_data* img, int n, float splat_scale, uint8_t* rgba) {
+    for (int i = 0; i < n; i++) {
+        float weight = img[i].weight_sum != 0 ? img[i].weight_sum : 1;
+        for (int k = 0; k < 3; k++) {
+            float v = img[i].rgb[k] / weight + img[i].rgb_splat[k] * splat_scale;
+            float s = v <= (float)0.0031308 ? (float)12.92 * v : (float)1.055 * powf(v, (float)(1.0 / 2.4)) - (float)0.055;
+            float cl = s < 0.0f ? 0.0f : (s > 1.0f ? 1.0f : s); // math::clamp01
+            rgba[4 * i + k] = (unsigned char)(cl * 255.0f);
+        }
+        rgba[4 * i + 3] = 255;
+    }
+}
+
 int orc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 
 } // extern "C"

@@ -291,6 +291,17 @@ void ref_trace_rays(const ctl_scene_view* view, int n, const ctl_traversal_ray* 
 	}
 }
 
+// copySamplesToOutput (Kernel/ImagePipeline/ImagePipeline.cu:7-21) with the reference's PixelData::toSpectrum / toSRGB / toRGBCOL
+void ref_resolve_srgb8(const ctl_pixel_data* img, int n, float splat_scale, unsigned char* rgba) {
+	for (int i = 0; i < n; i++) {
+		PixelData pd; memcpy((void*)&pd, &img[i], sizeof(pd));
+		Spectrum c = pd.toSpectrum(splat_scale), c2;
+		c.toSRGB(c2[0], c2[1], c2[2]);
+		RGBCOL o = Spectrum(c2).toRGBCOL();
+		rgba[4 * i] = o.x; rgba[4 * i + 1] = o.y; rgba[4 * i + 2] = o.z; rgba[4 * i + 3] = o.w;
+	}
+}
+
 // Known-answer probes of the reference's own math (regenerates SURVEY Appendix C)
 void ref_xorwow_floats(unsigned int seed_subsequence, int n, float* out) { CudaRNG rng(seed_subsequence); for (int i = 0; i < n; i++) out[i] = rng.randomFloat(); }
 void ref_woop_setdata(const float* v0, const float* v1, const float* v2, float* out12) {

@@ -156,6 +156,12 @@ def render(view, w, h, n_passes=1, pass_first=0, max_path_length=8, rr_start=5, 
     return (img, rays.value, [int(x) for x in cnt]) if counts else (img, rays.value)
 
 
+def resolve_srgb8(img, splat_scale=0.0):
+    img = np.ascontiguousarray(img); out = np.zeros(img.shape + (4,), np.uint8)
+    oracle().orc_resolve_srgb8.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p]
+    oracle().orc_resolve_srgb8(_p(img), img.size, splat_scale, _p(out)); return out
+
+
 def path_probe(view, w, x, y, pass_index=0, max_path_length=8, rr_start=5, direct=1):
     rgb = np.zeros(3, np.float32); rays = C.c_uint64(0)
     oracle().orc_path_probe(C.byref(view), w, x, y, pass_index, max_path_length, rr_start, direct, _p(rgb), C.byref(rays)); return rgb, rays.value

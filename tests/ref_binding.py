@@ -64,6 +64,12 @@ def sample_tables(pass_index):
     ref().ref_sample_tables(pass_index, _p(d1), _p(d2)); return d1, d2
 
 
+def resolve_srgb8(img, splat_scale=0.0):
+    img = np.ascontiguousarray(img); out = np.zeros(img.shape + (4,), np.uint8)
+    ref().ref_resolve_srgb8.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p]
+    ref().ref_resolve_srgb8(_p(img), img.size, splat_scale, _p(out)); return out
+
+
 def bsdf_probe(mat, wi, sx, sy):
     w = np.ascontiguousarray(wi, np.float32); out = np.zeros(9, np.float32); f = np.zeros(3, np.float32); pdf = np.zeros(1, np.float32)
     ref().ref_bsdf_probe(C.byref(mat), _p(w), sx, sy, _p(out), _p(f), _p(pdf)); return out, f, pdf[0]

@@ -129,3 +129,22 @@ def test_oracle_vs_live_reference(orc):
     rel = np.linalg.norm(ia["rgb"] - ib["rgb"], axis=2) / (np.linalg.norm(ib["rgb"], axis=2) + 1e-3)
     assert (rel <= 1e-3).mean() >= 0.99 and np.array_equal(ia["weight_sum"], ib["weight_sum"])
     assert abs(rbb - ra) <= 0.02 * ra
+
+
+def test_resolve_srgb8_matches_reference(orc):
+    """Default image pipeline (copySamplesToOutput): the oracle's restatement is byte-identical to the reference's own
+    PixelData::toSpectrum -> toSRGB -> toRGBCOL where oracle/_ref is available; known answers otherwise."""
+    px = np.zeros(6, api.PIXEL_DTYPE)
+    px["rgb"] = [(0, 0, 0), (0.002, 0.5, 1.0), (4.0, 8.0, 2.0), (0.2, 0.2, 0.2), (1e-4, 5.0, -1.0), (0.18, 0.18, 0.18)]
+    px["weight_sum"] = [0, 1, 8, 1, 1, 1]
+    px["rgb_splat"][3] = (0.5, 0.0, 0.25)
+    got = orc.resolve_srgb8(px, splat_scale=0.5)
+    assert got[0].tolist() == [0, 0, 0, 255] and got[1].tolist() == [6, 187, 254, 255] and got[2].tolist() == [187, 254, 136, 255]  # 1.0 -> 254: 1.055f*1 - 0.055f < 1 in fp32
+    assert got[3].tolist() == [178, 123, 154, 255] and got[4].tolist() == [0, 255, 0, 255]
+    assert got[5].tolist() == [117, 117, 117, 255]      # 18 % grey -> sRGB 0.4614 -> 117
+    import ref_binding as rb
+    if rb.available():
+        assert np.array_equal(got, rb.resolve_srgb8(px, splat_scale=0.5))
+        s = ctl.Scene("cornell", 64, 64)
+        img, _ = orc.render(s.view, 64, 64, n_passes=3, max_path_length=6)
+        assert np.array_equal(orc.resolve_srgb8(img), rb.resolve_srgb8(img))

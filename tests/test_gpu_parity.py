@@ -404,3 +404,19 @@ def test_ray_sorting_preserves_results(built_lib):
         key = (octant << 15) | spread(c[:, 0]) | (spread(c[:, 1]) << 1) | (spread(c[:, 2]) << 2)
         assert len(rays) > 1000 and np.all(np.diff(key.astype(np.int64)) >= 0)
         t.close()
+
+
+def test_resolve_srgb8(built_lib, orc):
+    """ctl_resolve_srgb8 (== applyImagePipeline without filter / post-process) vs the oracle on the SAME accumulator:
+    identical bytes except where CUDA powf and libm powf straddle a 1/255 step (<= 1 LSB, < 0.5 % of the channels)."""
+    w, h = 160, 120
+    s, t = make("cornell7", w, h, 8)
+    t.DoPasses(4, new_trace=True); t.synchronize()
+    acc = t.readAccumulator()
+    got = t.resolveSRGB8()
+    ref = orc.resolve_srgb8(acc)
+    assert got.shape == (h, w, 4) and np.all(got[:, :, 3] == 255)
+    d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 0.005
+    assert got[:, :, :3].mean() > 20          # a lit image, not black
+    t.close()
