@@ -74,6 +74,30 @@ CTL_DEV F8 ldg256(const void* p) {
     return r;
 }
 
+// Streaming (touch-once) data must not evict the BVH nodes and per-lane stacks the traversal kernel keeps in L1:
+// triangles and queue records are loaded with L1::no_allocate.  (Storing the results with .cs was measured and rejected:
+// evict-first partial-sector writes cost +66 % extension-traversal time, profiles/r01i_cache_hint_variants.log.)
+#ifndef CTL_STREAM_HINTS
+#define CTL_STREAM_HINTS 0 // measured: L1::no_allocate on triangle/queue loads = -1 % on C4 but +66 % on C2 extension rays (coherent rays re-use triangles through L1)
+#endif
+CTL_DEV float4 ldg_stream(const float4* p) {
+#if CTL_STREAM_HINTS
+    float4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+#else
+    return __ldg(p);
+#endif
+}
+CTL_DEV uint32_t ldg_stream(const uint32_t* p) {
+#if CTL_STREAM_HINTS
+    uint32_t r;
+    asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+#else
+    return __ldg(p);
+#endif
+}
 CTL_DEV float h2f(uint32_t h) { return __half2float(__ushort_as_half((unsigned short)(h & 0xffff))); }
 
 } // namespace ctld

@@ -82,7 +82,7 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, const float4* 
                     out.hit_node[i] = hit.node;
                 } else if (MODE == 1) {
                     if (hit.tri == 0xffffffffu) { // unoccluded: add the pending NEE term (each path has <= 1 shadow ray per bounce)
-                        const float4 pl = __ldg(out.sh_payload + i);
+                        const float4 pl = ldg_stream(out.sh_payload + i);
                         const uint32_t p = __float_as_uint(pl.w);
                         float4 c = out.cl[p];
                         c.x = c.x + pl.x; c.y = c.y + pl.y; c.z = c.z + pl.z;
@@ -120,7 +120,7 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, const float4* 
                     const int r = my_rank - got_before;
                     if (is_free && r >= 0 && r < take) {
                         const int i = pool_next + r;
-                        const float4 ro = __ldg(rays + 2 * i), rd = __ldg(rays + 2 * i + 1);
+                        const float4 ro = ldg_stream(rays + 2 * i), rd = ldg_stream(rays + 2 * i + 1);
                         ray_i = i;
                         ox = ro.x; oy = ro.y; oz = ro.z; dx = rd.x; dy = rd.y; dz = rd.z;
                         hit.u = hit.v = 0.0f; hit.tri = 0xffffffffu; hit.node = 0xffffffffu;
@@ -206,10 +206,10 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, const float4* 
         const unsigned mT2 = __ballot_sync(0xffffffffu, state == 1);
         if (mT2 && (__popc(mT2) >= TH_T || (mT2 | b1) == 0xffffffffu)) { // enough T lanes, or no lane can take a node step
             if (state == 1) {
-                const float4 v00 = __ldg(wbase + triAddr * 3 + 0);
-                const float4 v11 = __ldg(wbase + triAddr * 3 + 1);
-                const float4 v22 = __ldg(wbase + triAddr * 3 + 2);
-                const uint32_t index = __ldg(ibase + triAddr);
+                const float4 v00 = ldg_stream(wbase + triAddr * 3 + 0);
+                const float4 v11 = ldg_stream(wbase + triAddr * 3 + 1);
+                const float4 v22 = ldg_stream(wbase + triAddr * 3 + 2);
+                const uint32_t index = ldg_stream(ibase + triAddr);
                 if (COUNT) ((VisitCounters<true>&)cnt).tris++;
                 float t, u, v;
                 bool done = false;

@@ -196,8 +196,11 @@ __global__ void __launch_bounds__(128, CTL_SIMPLE_MIN_BLOCKS) k_intersect_simple
 }
 
 // Production traversal kernel: persistent warps, phase-scheduled (device/traverse_persistent.cuh). Same MODEs as above.
+#ifndef CTL_TRAV_MIN_BLOCKS
+#define CTL_TRAV_MIN_BLOCKS 1
+#endif
 template <int MODE, bool ANY_HIT, bool COUNT>
-__global__ void __launch_bounds__(128) k_intersect(const __grid_constant__ DScene S, const __grid_constant__ TravTune tune, const float4* __restrict__ rays, const unsigned* __restrict__ n_ptr, int n_fixed,
+__global__ void __launch_bounds__(128, CTL_TRAV_MIN_BLOCKS) k_intersect(const __grid_constant__ DScene S, const __grid_constant__ TravTune tune, const float4* __restrict__ rays, const unsigned* __restrict__ n_ptr, int n_fixed,
                                                     unsigned* work_ctr, float4* __restrict__ hit_a, uint32_t* __restrict__ hit_node,
                                                     const float4* __restrict__ sh_payload, float4* __restrict__ cl,
                                                     void* __restrict__ api_out, unsigned long long* visit_out) {
