@@ -51,7 +51,7 @@ struct ctl_ctx {
     int n_sm = 148;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     // parameters (Integrators/PathTracer.h:10-20)
-    int max_path_length = 50, rr_start = 5, direct = 1, regularization = 0, sort_mode = 0, stage_timers = 0, capture_bounce = 0, trav_kernel = 0, trav_blocks_per_sm = 8, shade_blocks_per_sm = 8, smem_carveout = -1;
+    int max_path_length = 50, rr_start = 5, direct = 1, regularization = 0, sort_mode = 0, stage_timers = 0, capture_bounce = 0, trav_kernel = 0, trav_blocks_per_sm = 8, shade_blocks_per_sm = 8, smem_carveout = -1, fuse_traversal = 1;
     // scene
     DevBuf<ctl_bvh_node> d_scene_nodes, d_bvh_nodes; DevBuf<ctl_woop_tri> d_woop; DevBuf<uint32_t> d_tri_index; DevBuf<ctl_tri_data> d_tri_data;
     DevBuf<ctl_mesh> d_meshes; DevBuf<ctl_node> d_nodes; DevBuf<float> d_xf, d_inv_xf; DevBuf<ctl_material> d_materials; DevBuf<ctl_light> d_lights;
@@ -204,6 +204,7 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "StageTimers") c->stage_timers = v != 0;
     else if (k == "CaptureBounce") c->capture_bounce = v;
     else if (k == "DeviceSampleTables") c->device_tables = v != 0;
+    else if (k == "FuseTraversal") c->fuse_traversal = v != 0;
     else if (k == "TraversalKernel") { if (v < 0 || v > 1) return set_err("TraversalKernel must be 0 or 1"); c->trav_kernel = v; }
     else if (k == "TravThT") c->tune.th_t = v; else if (k == "TravThL") c->tune.th_l = v; else if (k == "TravThF") c->tune.th_f = v;
     else if (k == "TravThNExit") c->tune.th_n_exit = v;
@@ -222,7 +223,7 @@ int ctl_get_param_i(ctl_ctx* c, const char* key, int* v) {
     std::string k(key);
     if (k == "MaxPathLength") *v = c->max_path_length; else if (k == "RRStartDepth") *v = c->rr_start; else if (k == "Direct") *v = c->direct;
     else if (k == "Regularization") *v = c->regularization; else if (k == "SortMode") *v = c->sort_mode; else if (k == "StageTimers") *v = c->stage_timers;
-    else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables;
+    else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables; else if (k == "FuseTraversal") *v = c->fuse_traversal;
     else if (k == "TraversalBlocksPerSM") *v = c->trav_blocks_per_sm; else return set_err("unknown parameter key: " + k);
     return 0;
 }
@@ -437,13 +438,18 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
     ShadeParams P = {c->max_path_length, c->rr_start, c->direct};
     float4* rin = c->rays_a.p; float4* rout = c->rays_b.p; uint32_t* pin = c->path_a.p; uint32_t* pout = c->path_b.p;
     float4* rspare = c->rays_c.p; uint32_t* pspare = c->path_c.p;
+    const bool fuse = c->fuse_traversal && c->direct && !c->instrumented && c->trav_kernel == 0;
     for (int b = 0; b < c->max_path_length; b++) {
         stage_mark(c, 1);
         if (c->capture_bounce == b + 1) {
             CK(cudaMemcpyAsync(c->capture.p, rin, 32 * n_paths, cudaMemcpyDeviceToDevice, c->stream));
             CK(cudaMemcpyAsync(c->d_captured_n.p, ctr + CTR_Q + b, sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
         }
-        if (c->instrumented) launch_intersect<0, false, true>(c, g_trav, c->stream, c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, c->stats.p + 2);
+        if (fuse && b > 0) { // shadow rays of bounce b-1 + extension rays of bounce b in one persistent launch
+            k_intersect_fused<<<g_trav, 128, 0, c->stream>>>(c->scene, c->tune, rin, ctr + CTR_Q + b, c->sh_rays.p, ctr + CTR_SH + b - 1, ctr + CTR_WORK + 2 * b,
+                                                              c->hit_a.p, c->hit_node.p, c->sh_payload.p, c->cl.p);
+        }
+        else if (c->instrumented) launch_intersect<0, false, true>(c, g_trav, c->stream, c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, c->stats.p + 2);
         else launch_intersect<0, false, false>(c, g_trav, c->stream, c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, nullptr);
         stage_mark(c, 2);
         const bool sort_next = c->sort_mode == 1 && b + 1 < c->max_path_length;
@@ -457,7 +463,7 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
             launches += 2;
         }
         stage_mark(c, 3);
-        if (c->direct) {
+        if (c->direct && (!fuse || b + 1 == c->max_path_length)) {
             if (c->instrumented) launch_intersect<1, true, true>(c, g_trav, c->stream, c->scene, c->sh_rays.p, ctr + CTR_SH + b, 0, ctr + CTR_WORK + 2 * b + 1, nullptr, nullptr, c->sh_payload.p, c->cl.p, nullptr, c->stats.p + 6);
             else launch_intersect<1, true, false>(c, g_trav, c->stream, c->scene, c->sh_rays.p, ctr + CTR_SH + b, 0, ctr + CTR_WORK + 2 * b + 1, nullptr, nullptr, c->sh_payload.p, c->cl.p, nullptr, nullptr);
             launches++;

@@ -23,6 +23,9 @@ constexpr int TP_STACK = 64;     // BVHTraversal.h: int traversalStack[64]
 
 struct TravOut { // where results go (MODE-dependent, see k_intersect)
     float4* hit_a; uint32_t* hit_node; const float4* sh_payload; float4* cl; void* api_out;
+    // MODE 4 (fused launch): work items [0, n_ext) are extension rays (closest hit, results as MODE 0) taken from `rays`,
+    // items [n_ext, n) are shadow rays (any hit, results as MODE 1) taken from `sh_rays`
+    const float4* sh_rays; int n_ext;
 };
 
 struct TravTune { int th_t, th_l, th_f, th_n_exit; }; // lane thresholds of the T / L / F blocks; th_n_exit = node steps per iteration
@@ -44,6 +47,8 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, const float4* 
     float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1, idx = 0, idy = 0, idz = 0, oodx = 0, oody = 0, oodz = 0;
     float tri_lo = 0, box_lo = 0;
     Hit hit; hit.dist = 0; hit.u = hit.v = 0; hit.tri = hit.node = 0xffffffffu;
+    bool lane_any = ANY_HIT;        // MODE 4: per-lane any-hit flag (shadow rays)
+    const float4* my_rays = rays;   // MODE 4: queue this lane's ray came from (for the world-space reload at instance exit)
     const float4* nbase = S.scene_nodes;
     const float4* wbase = S.woop; const uint32_t* ibase = S.tri_index; uint32_t tri_base = 0;
 
@@ -77,10 +82,10 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, const float4* 
         if (runF) {
             if (state == 3 && ray_i >= 0) {
                 const int i = ray_i;
-                if (MODE == 0) {
+                if (MODE == 0 || (MODE == 4 && !lane_any)) {
                     out.hit_a[i] = make_float4(hit.dist, hit.u, hit.v, __uint_as_float(hit.tri));
                     out.hit_node[i] = hit.node;
-                } else if (MODE == 1) {
+                } else if (MODE == 1 || MODE == 4) {
                     if (hit.tri == 0xffffffffu) { // unoccluded: add the pending NEE term (each path has <= 1 shadow ray per bounce)
                         const float4 pl = ldg_stream(out.sh_payload + i);
                         const uint32_t p = __float_as_uint(pl.w);
@@ -119,8 +124,9 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, const float4* 
                     const int take = min(need, pool_end - pool_next);
                     const int r = my_rank - got_before;
                     if (is_free && r >= 0 && r < take) {
-                        const int i = pool_next + r;
-                        const float4 ro = ldg_stream(rays + 2 * i), rd = ldg_stream(rays + 2 * i + 1);
+                        int i = pool_next + r;
+                        if (MODE == 4) { lane_any = i >= out.n_ext; my_rays = lane_any ? out.sh_rays : rays; if (lane_any) i -= out.n_ext; }
+                        const float4 ro = ldg_stream(my_rays + 2 * i), rd = ldg_stream(my_rays + 2 * i + 1);
                         ray_i = i;
                         ox = ro.x; oy = ro.y; oz = ro.z; dx = rd.x; dy = rd.y; dz = rd.z;
                         hit.u = hit.v = 0.0f; hit.tri = 0xffffffffu; hit.node = 0xffffffffu;
@@ -159,7 +165,7 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, const float4* 
                     sp++; stack[sp] = SENT; // marker: popping it ends the mesh level
                     nodeAddr = 0;
                 } else { // mesh level exhausted: back to the scene level with the world-space ray
-                    const float4 ro = __ldg(rays + 2 * ray_i), rd = __ldg(rays + 2 * ray_i + 1);
+                    const float4 ro = __ldg(my_rays + 2 * ray_i), rd = __ldg(my_rays + 2 * ray_i + 1);
                     ox = ro.x; oy = ro.y; oz = ro.z; dx = rd.x; dy = rd.y; dz = rd.z;
                     nbase = S.scene_nodes;
                     inst = -1;
@@ -215,7 +221,7 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, const float4* 
                 bool done = false;
                 if (woop_test(v00, v11, v22, mk(ox, oy, oz), mk(dx, dy, dz), tri_lo, hit.dist, t, u, v)) {
                     hit.node = (uint32_t)inst; hit.tri = (index >> 1) + tri_base; hit.u = u; hit.v = v; hit.dist = t;
-                    if (ANY_HIT) { done = true; nodeAddr = SENT; inst = -1; } // first hit terminates the ray (TraceHelper.cu:675-679)
+                    if (MODE == 4 ? lane_any : ANY_HIT) { done = true; nodeAddr = SENT; inst = -1; } // first hit terminates the ray (TraceHelper.cu:675-679)
                 }
                 if (!done) {
                     if (index & 1) { nodeAddr = stack[sp]; sp--; if (nodeAddr < 0) triAddr = ~nodeAddr; }

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(128, CTL_TRAV_MIN_BLOCKS) k_intersect(const __
                                                     void* __restrict__ api_out, unsigned long long* visit_out) {
     const int n = n_ptr ? (int)*n_ptr : n_fixed;
     VisitCounters<COUNT> cnt;
-    TravOut out = {hit_a, hit_node, sh_payload, cl, api_out};
+    TravOut out = {hit_a, hit_node, sh_payload, cl, api_out, nullptr, 0};
     trace_persistent<MODE, ANY_HIT, COUNT>(S, rays, n, work_ctr, out, tune, cnt);
     if (COUNT) {
         VisitCounters<true>& c = (VisitCounters<true>&)cnt;
@@ -253,6 +253,18 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const unsigned* __restrict
         rays_out[2 * pos] = __ldg(rays_in + 2 * i); rays_out[2 * pos + 1] = __ldg(rays_in + 2 * i + 1);
         path_out[pos] = __ldg(path_in + i);
     }
+}
+
+// Fused traversal launch: the shadow rays of bounce b (any hit -> cl += pending) and the extension rays of bounce b+1
+// (closest hit -> hit records) share one persistent kernel, so each bounce has ONE traversal tail instead of two and small
+// queues (late bounces, 8-GPU tiles) fill the machine together.  Lane-level any-hit flag; same arithmetic as MODE 0 / 1.
+__global__ void __launch_bounds__(128, 8) k_intersect_fused(const __grid_constant__ DScene S, const __grid_constant__ TravTune tune,
+        const float4* __restrict__ ext_rays, const unsigned* __restrict__ n_ext_ptr, const float4* __restrict__ sh_rays, const unsigned* __restrict__ n_sh_ptr,
+        unsigned* work_ctr, float4* __restrict__ hit_a, uint32_t* __restrict__ hit_node, const float4* __restrict__ sh_payload, float4* __restrict__ cl) {
+    const int n_ext = (int)*n_ext_ptr, n_sh = (int)*n_sh_ptr;
+    VisitCounters<false> cnt;
+    TravOut out = {hit_a, hit_node, sh_payload, cl, nullptr, sh_rays, n_ext};
+    trace_persistent<4, false, false>(S, ext_rays, n_ext + n_sh, work_ctr, out, tune, cnt);
 }
 
 // ---- shade: one path vertex (PathTracer.cu:58-96) ----------------------------------

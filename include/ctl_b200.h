@@ -218,7 +218,8 @@ int      ctl_resize(ctl_ctx*, int width, int height);
  *    "Regularization" (0, only 0 supported)  (Integrators/PathTracer.h:10-20);
  *    extras: "SortMode" (0 none, 1 material), "StageTimers" (0/1), "CaptureBounce" (0 = off),
  *    "DeviceSampleTables" (1 = tables generated by a CUDA kernel, bit-identical to the host XORWOW generator; 0 = generated on the
- *    host and copied H2D every pass like the reference's UpdateKernel), "TraversalKernel" (0 persistent, 1 simple A/B baseline),
+ *    host and copied H2D every pass like the reference's UpdateKernel), "TraversalKernel" (0 persistent, 1 simple A/B baseline), "FuseTraversal" (1 = shadow rays of bounce b and
+ *    extension rays of bounce b+1 share one traversal launch),
  *    "TraversalBlocksPerSM", "TravThT/L/F", "TravThNExit" (tuning). */
 int ctl_set_param_i(ctl_ctx*, const char* key, int value);
 int ctl_get_param_i(ctl_ctx*, const char* key, int* value);
