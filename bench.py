@@ -297,10 +297,11 @@ def main():
     tracer.setInstrumented(0)
     bytes_batch = traversal_bytes(e_cnt, e_cnt[3]) + traversal_bytes(s_cnt, s_cnt[3])   # one batch (all batches of a frame are alike up to RNG)
     trav_ms_batch = (ext_ms + sh_ms) / n_batches
-    n_trav_launches = 2 * depth
+    fused = bool(tracer.getParameter("FuseTraversal"))
+    n_trav_launches = depth + 1 if fused else 2 * depth   # fused: ext(0), [shadow(b-1)+ext(b)] x (depth-1), shadow(depth-1)
     peak, peak_src = hbm_peak()
     achieved = bytes_batch / (trav_ms_batch * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "k_intersect (extension + shadow launches)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roof = {"bound": "hbm", "kernel": "k_intersect / k_intersect_fused (all traversal launches of a wavefront)", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
             "algorithmic_bytes_per_launch": bytes_batch / n_trav_launches, "avg_launch_ms": trav_ms_batch / n_trav_launches,
             "bytes_per_ray": bytes_batch / max(1, e_cnt[3] + s_cnt[3]), "launches_per_batch": n_trav_launches, "passes_per_batch": batch,
