@@ -102,6 +102,21 @@ def test_images(orc, key, kind, w, h, spp):
     assert abs(rays - ref_rays) <= 0.01 * ref_rays   # fp-contraction flips a few discrete decisions; the oracle also stops zero-throughput paths
 
 
+def test_two_light_scene(orc):
+    """Hand-made scene through ctl_scene_create_from_mesh: two area lights (light-selection CDF, pdfEmitter), a two-sided
+    card, a GGX block, back-facing one-sided walls (zero-throughput paths) -- vs the reference's own PathTrace."""
+    from scene_fixtures import two_light_room
+    s = two_light_room(96, 96)
+    assert s.view.num_lights == 2 and s.view.light_cdf[0] == 0.5 and s.view.light_cdf[1] == 1.0
+    ref = np.ascontiguousarray(GOLD["image_two_light_96x96_4spp"]).view(api.PIXEL_DTYPE).reshape(96, 96)
+    img, rays = orc.render(s.view, 96, 96, n_passes=4, max_path_length=6)
+    rel = np.linalg.norm(img["rgb"] - ref["rgb"], axis=2) / (np.linalg.norm(ref["rgb"], axis=2) + 1e-3)
+    assert (rel <= 1e-3).mean() >= 0.99 and np.array_equal(img["weight_sum"], ref["weight_sum"])
+    assert abs(img["rgb"].mean() - ref["rgb"].mean()) <= 1e-4 * ref["rgb"].mean()
+    # the oracle stops zero-throughput paths (here: hits on the back of one-sided walls), the reference traces them on
+    assert rays < int(GOLD["image_two_light_96x96_4spp_rays"][0])
+
+
 def test_config1_cornell_256(orc):
     """BASELINE config 1 (Cornell-32, 256x256, 1 spp) against the reference's own CPU path."""
     s = ctl.Scene("cornell", 256, 256)

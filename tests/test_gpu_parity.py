@@ -433,3 +433,24 @@ def test_fused_traversal_launch_is_exact(built_lib):
         assert np.allclose(a["rgb"], b["rgb"], rtol=2e-6, atol=1e-6)
         assert (a["rgb"] == b["rgb"]).all(axis=2).mean() > 0.99   # per-path arithmetic is identical; only atomics into spill pixels reorder
         t.close()
+
+
+def test_two_light_scene_from_mesh(built_lib, orc):
+    """ctl_scene_create_from_mesh scene with two area lights / two-sided card / GGX block: CUDA vs oracle and vs the
+    image rendered by the reference's own PathTrace<true> (golden)."""
+    from scene_fixtures import two_light_room
+    w = h = 96
+    s = two_light_room(w, h)
+    t = ctl.PathTracer(w, h); t.InitializeScene(s); t.setParameter("MaxPathLength", 6)
+    t.DoPasses(4, new_trace=True); t.synchronize()
+    img = t.readAccumulator()
+    o, orays = orc.render(s.view, w, h, n_passes=4, max_path_length=6)
+    ref = np.ascontiguousarray(_GOLD["image_two_light_96x96_4spp"]).view(api.PIXEL_DTYPE).reshape(h, w)
+    for other in (o, ref):
+        assert (rel_l2(img["rgb"], other["rgb"]) <= 1e-3).mean() >= 0.99
+        assert np.array_equal(img["weight_sum"], other["weight_sum"])
+    assert abs(t.getRaysInLastPass() - orays) <= 2e-3 * orays      # the 4-pass wavefront traced what the oracle traced
+    rays = random_rays(s, 3000, seed=4)
+    g = t.trace_rays(rays); oo = orc.trace_rays(s.view, rays)
+    assert np.array_equal(g["tri_idx"], oo["tri_idx"]) and np.array_equal(g["dist"].view(np.uint32), oo["dist"].view(np.uint32))
+    t.close()
