@@ -104,6 +104,8 @@ def lib():
     L.ctl_scene_create_from_mesh.argtypes = [vp, u32, vp, u32, vp, vp, u32, vp, vp, vp, vp, C.c_float, i32, i32]
     L.ctl_scene_get_view.argtypes = [vp, C.POINTER(SceneView)]
     L.ctl_scene_destroy.argtypes = [vp]; L.ctl_scene_destroy.restype = None
+    L.ctl_bvh_build_gpu.argtypes = [i32, vp, u32, vp, vp, vp, vp, vp]
+    L.ctl_scene_rebuild_bvh_gpu.argtypes = [vp, i32, vp]
     L.ctl_encode_woop.argtypes = [vp, vp, vp, vp]; L.ctl_encode_woop.restype = None
     L.ctl_encode_tri_data.argtypes = [vp, vp, vp, u32, vp]; L.ctl_encode_tri_data.restype = None
     L.ctl_generate_sample_tables.argtypes = [u32, vp, vp]
@@ -176,6 +178,13 @@ class Scene:
         self.view = SceneView()
         _check(lib().ctl_scene_get_view(self._h, C.byref(self.view)))
         return self
+
+    def rebuildBVHOnGPU(self, device=0):
+        """Replace every mesh BVH by one built on the GPU (ctl_scene_rebuild_bvh_gpu); returns the device build time in ms."""
+        ms = C.c_float(0)
+        _check(lib().ctl_scene_rebuild_bvh_gpu(self._h, device, C.byref(ms)))
+        _check(lib().ctl_scene_get_view(self._h, C.byref(self.view)))
+        return ms.value
 
     @property
     def n_triangles(self):

@@ -6,8 +6,14 @@
 //   Math/float4x4.h:132-193 (cofactor inverse), 398-408 (TransformPoint divides by w),
 //   Math/Compression.h:12-31 (16-bit spherical normal codec),
 //   Math/half.h:20-82 (IEEE binary16 round-to-nearest-even; decode per IEEE).
-// Host only (no CUDA). Not used by oracle/ (which carries its own restatement).
+// Host code; the vector / matrix-inverse helpers are also callable from device code (CTLB_HD) so that the GPU BVH builder
+// encodes Woop triangles with the very same expressions.  Not used by oracle/ (which carries its own restatement).
 #pragma once
+#ifdef __CUDACC__
+#define CTLB_HD __host__ __device__
+#else
+#define CTLB_HD
+#endif
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -16,26 +22,26 @@ namespace ctlb {
 
 struct V3 {
     float x, y, z;
-    V3() : x(0), y(0), z(0) {}
-    V3(float a, float b, float c) : x(a), y(b), z(c) {}
-    explicit V3(float a) : x(a), y(a), z(a) {}
+    CTLB_HD V3() : x(0), y(0), z(0) {}
+    CTLB_HD V3(float a, float b, float c) : x(a), y(b), z(c) {}
+    CTLB_HD explicit V3(float a) : x(a), y(a), z(a) {}
     float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
     float& operator[](int i) { return i == 0 ? x : (i == 1 ? y : z); }
 };
-inline V3 operator+(V3 a, V3 b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
-inline V3 operator-(V3 a, V3 b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
-inline V3 operator-(V3 a) { return V3(-a.x, -a.y, -a.z); }
-inline V3 operator*(V3 a, float s) { return V3(a.x * s, a.y * s, a.z * s); }
-inline V3 operator*(float s, V3 a) { return V3(a.x * s, a.y * s, a.z * s); }
-inline V3 operator/(V3 a, float s) { return V3(a.x / s, a.y / s, a.z / s); }
-inline float dot(V3 a, V3 b) { float r = 0.0f; r += a.x * b.x; r += a.y * b.y; r += a.z * b.z; return r; }
-inline V3 cross(V3 a, V3 b) { return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+CTLB_HD inline V3 operator+(V3 a, V3 b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+CTLB_HD inline V3 operator-(V3 a, V3 b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
+CTLB_HD inline V3 operator-(V3 a) { return V3(-a.x, -a.y, -a.z); }
+CTLB_HD inline V3 operator*(V3 a, float s) { return V3(a.x * s, a.y * s, a.z * s); }
+CTLB_HD inline V3 operator*(float s, V3 a) { return V3(a.x * s, a.y * s, a.z * s); }
+CTLB_HD inline V3 operator/(V3 a, float s) { return V3(a.x / s, a.y / s, a.z / s); }
+CTLB_HD inline float dot(V3 a, V3 b) { float r = 0.0f; r += a.x * b.x; r += a.y * b.y; r += a.z * b.z; return r; }
+CTLB_HD inline V3 cross(V3 a, V3 b) { return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 inline float len_sqr(V3 a) { return dot(a, a); }
 inline float length(V3 a) { return sqrtf(len_sqr(a)); }
 inline float rcp(float a) { return a != 0.0f ? 1.0f / a : 0.0f; }
 inline V3 normalize(V3 a) { return a * rcp(length(a)); }
-inline V3 vmin(V3 a, V3 b) { return V3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
-inline V3 vmax(V3 a, V3 b) { return V3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
+CTLB_HD inline V3 vmin(V3 a, V3 b) { return V3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
+CTLB_HD inline V3 vmax(V3 a, V3 b) { return V3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
 
 struct Box {
     V3 lo, hi;
@@ -54,8 +60,8 @@ struct Box {
 // Row-major 4x4, column-vector convention (M * v), Math/float4x4.h:12-18.
 struct M4 {
     float m[16];
-    float operator()(int r, int c) const { return m[r * 4 + c]; }
-    float& operator()(int r, int c) { return m[r * 4 + c]; }
+    CTLB_HD float operator()(int r, int c) const { return m[r * 4 + c]; }
+    CTLB_HD float& operator()(int r, int c) { return m[r * 4 + c]; }
     static M4 identity() {
         M4 r; for (int i = 0; i < 16; i++) r.m[i] = (i % 5 == 0) ? 1.0f : 0.0f; return r;
     }
@@ -103,7 +109,7 @@ struct M4 {
         return V3(dot4(&m[0], d.x, d.y, d.z, 0.0f), dot4(&m[4], d.x, d.y, d.z, 0.0f), dot4(&m[8], d.x, d.y, d.z, 0.0f));
     }
     // Adjugate / determinant inverse, evaluation order of Math/float4x4.h:132-193.
-    M4 inverse() const {
+    CTLB_HD M4 inverse() const {
         const M4& Q = *this;
         float a00 = Q(0, 0), a01 = Q(0, 1), a02 = Q(0, 2), a03 = Q(0, 3);
         float a10 = Q(1, 0), a11 = Q(1, 1), a12 = Q(1, 2), a13 = Q(1, 3);

@@ -8,19 +8,6 @@ namespace ctlb {
 
 // ------------------------------------------------------------------ encoders
 
-void encode_woop(V3 v0, V3 v1, V3 v2, ctl_woop_tri* out) {
-    // M = [v0-v2 | v1-v2 | (v0-v2)x(v1-v2) | v2] (columns), inverted; store row2 (w negated), row0, row1.
-    V3 e0 = v0 - v2, e1 = v1 - v2, nn = cross(e0, e1);
-    M4 m;
-    m(0, 0) = e0.x; m(1, 0) = e0.y; m(2, 0) = e0.z; m(3, 0) = 0;
-    m(0, 1) = e1.x; m(1, 1) = e1.y; m(2, 1) = e1.z; m(3, 1) = 0;
-    m(0, 2) = nn.x; m(1, 2) = nn.y; m(2, 2) = nn.z; m(3, 2) = 0;
-    m(0, 3) = v2.x; m(1, 3) = v2.y; m(2, 3) = v2.z; m(3, 3) = 1;
-    M4 i = m.inverse();
-    out->a[0] = i(2, 0); out->a[1] = i(2, 1); out->a[2] = i(2, 2); out->a[3] = -i(2, 3);
-    for (int k = 0; k < 4; k++) { out->b[k] = i(0, k); out->c[k] = i(1, k); }
-}
-
 void decode_woop(const ctl_woop_tri& w, V3& v0, V3& v1, V3& v2) { // TriIntersectorData.cu:20-32
     M4 m = M4::identity();
     for (int k = 0; k < 4; k++) { m(0, k) = w.b[k]; m(1, k) = w.c[k]; m(2, k) = w.a[k]; }
@@ -232,9 +219,10 @@ void assemble_scene(const std::vector<MeshInput>& meshes, const std::vector<Node
         std::vector<V3> vn;
         compute_vertex_normals(M.verts, M.indices, vn);
         std::vector<Box> pb(nt);
+        S.mesh_verts9.emplace_back(); S.mesh_verts9.back().reserve((size_t)nt * 9);
         for (uint32_t t = 0; t < nt; t++) {
             V3 p[3], n[3];
-            for (int k = 0; k < 3; k++) { p[k] = M.verts[M.indices[t * 3 + k]]; n[k] = vn[M.indices[t * 3 + k]]; pb[t].grow(p[k]); }
+            for (int k = 0; k < 3; k++) { p[k] = M.verts[M.indices[t * 3 + k]]; n[k] = vn[M.indices[t * 3 + k]]; pb[t].grow(p[k]); S.mesh_verts9.back().insert(S.mesh_verts9.back().end(), {p[k].x, p[k].y, p[k].z}); }
             float uv[6] = {0, 0, 0, 0, 0, 0};
             ctl_tri_data td;
             encode_tri_data(p, n, uv, M.mat_index[t], &td);

@@ -39,6 +39,7 @@ struct SceneStorage {
     std::vector<uint32_t> tri_index;
     std::vector<ctl_tri_data> tri_data;
     std::vector<ctl_mesh> meshes;
+    std::vector<std::vector<float>> mesh_verts9;   // per mesh: 9 floats per triangle (for BVH rebuilds, e.g. on the GPU)
     std::vector<ctl_node> nodes;
     std::vector<float> node_xf, node_inv_xf;
     std::vector<ctl_bvh_node> scene_bvh;
@@ -62,7 +63,19 @@ struct BvhBuildResult { std::vector<ctl_bvh_node> nodes; std::vector<uint32_t> l
 void build_bvh(const std::vector<Box>& prim_boxes, int max_leaf, std::vector<ctl_bvh_node>& nodes_out,
                std::vector<uint32_t>& ordered_prims_out, std::vector<uint8_t>& last_in_leaf_out);
 
-void encode_woop(V3 v0, V3 v1, V3 v2, ctl_woop_tri* out);
+// Woop unit-triangle transform (Engine/TriIntersectorData.cu:5-18); host + device (GPU BVH builder), same expressions
+CTLB_HD inline void encode_woop(V3 v0, V3 v1, V3 v2, ctl_woop_tri* out) {
+    // M = [v0-v2 | v1-v2 | (v0-v2)x(v1-v2) | v2] (columns), inverted; store row2 (w negated), row0, row1.
+    V3 e0 = v0 - v2, e1 = v1 - v2, nn = cross(e0, e1);
+    M4 m;
+    m(0, 0) = e0.x; m(1, 0) = e0.y; m(2, 0) = e0.z; m(3, 0) = 0;
+    m(0, 1) = e1.x; m(1, 1) = e1.y; m(2, 1) = e1.z; m(3, 1) = 0;
+    m(0, 2) = nn.x; m(1, 2) = nn.y; m(2, 2) = nn.z; m(3, 2) = 0;
+    m(0, 3) = v2.x; m(1, 3) = v2.y; m(2, 3) = v2.z; m(3, 3) = 1;
+    M4 i = m.inverse();
+    out->a[0] = i(2, 0); out->a[1] = i(2, 1); out->a[2] = i(2, 2); out->a[3] = -i(2, 3);
+    for (int k = 0; k < 4; k++) { out->b[k] = i(0, k); out->c[k] = i(1, k); }
+}
 void decode_woop(const ctl_woop_tri& w, V3& v0, V3& v1, V3& v2);
 void encode_tri_data(const V3 p[3], const V3 n[3], const float uv[6], uint32_t mat, ctl_tri_data* out);
 void compute_vertex_normals(const std::vector<V3>& verts, const std::vector<uint32_t>& idx, std::vector<V3>& normals);

@@ -195,6 +195,14 @@ ctl_scene* ctl_scene_create_from_mesh(const float* verts, uint32_t nv, const uin
                                       const float* cam_up, float fov_deg, int width, int height);
 int  ctl_scene_get_view(const ctl_scene*, ctl_scene_view* out);
 void ctl_scene_destroy(ctl_scene*);
+/* GPU construction of one mesh BVH in the reference layout (LBVH: Morton codes, hand-written radix sort, Karras radix tree,
+ * bottom-up fit, <= 8-triangle leaves) -- replaces the CPU pre-process SplitBVHBuilder.cpp / BVHBuilderHelper.cpp:119 for
+ * meshes that need (re)building at run time.  verts9: n_tris * 9 floats (host).  Outputs (host): nodes_out
+ * (capacity max(1, n_tris)), woop_out / index_out (n_tris each, leaf order), *n_nodes_out, optional device build time. */
+int ctl_bvh_build_gpu(int device, const float* verts9, uint32_t n_tris, ctl_bvh_node* nodes_out, uint32_t* n_nodes_out,
+                      ctl_woop_tri* woop_out, uint32_t* index_out, float* build_ms);
+/* Rebuild all mesh BVHs of a host scene with ctl_bvh_build_gpu (views obtained before the call are invalidated). */
+int ctl_scene_rebuild_bvh_gpu(ctl_scene*, int device, float* build_ms_total);
 /* encoders exposed for known-answer tests */
 void ctl_encode_woop(const float v0[3], const float v1[3], const float v2[3], ctl_woop_tri* out); /* TriIntersectorData.cu:5-18 */
 void ctl_encode_tri_data(const float p[9], const float n[9], const float uv[6], uint32_t mat, ctl_tri_data* out); /* TriangleData.cu:8-65 */

@@ -1,0 +1,21 @@
+"""GPU LBVH build vs CPU binned-SAH build: build time and traversal cost of the resulting trees."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cudatracerlib_b200 import Scene, PathTracer
+for kind in ("c2", "c4"):
+    t0 = time.time(); s = Scene(kind, 1920, 1080); t_cpu = time.time() - t0
+    res = {}
+    for tag in ("cpu-sah", "gpu-lbvh"):
+        if tag == "gpu-lbvh":
+            t0 = time.time(); ms = s.rebuildBVHOnGPU(); wall = time.time() - t0
+        t = PathTracer(1920, 1080); t.InitializeScene(s); t.setParameter("MaxPathLength", 8); t.setParameter("StageTimers", 1)
+        best = None
+        for i in range(3):
+            t.DoPasses(2, new_trace=True); t.synchronize(); m, _ = t.stageTimes()
+            if best is None or m[1] + m[3] < best: best = m[1] + m[3]
+        t.setInstrumented(1); t.DoPass(True); t.synchronize(); e, sh = t.visitCounts(); t.setInstrumented(0)
+        res[tag] = (best, e[0] / e[3], e[1] / e[3], s.view.n_bvh_nodes)
+        t.close()
+    print(kind, "tris", s.n_triangles, "CPU scene build (all meshes, SAH + encoders) %.2f s" % t_cpu, "| GPU LBVH build %.2f ms device, %.2f s wall incl. copies" % (ms, wall))
+    for tag, (trav, ni, nt, nn) in res.items():
+        print("   ", tag, "traversal ms / 2-pass wavefront %.2f" % trav, "inner nodes/ray %.1f tris/ray %.1f" % (ni, nt), "nodes", nn)

@@ -454,3 +454,78 @@ def test_two_light_scene_from_mesh(built_lib, orc):
     g = t.trace_rays(rays); oo = orc.trace_rays(s.view, rays)
     assert np.array_equal(g["tri_idx"], oo["tri_idx"]) and np.array_equal(g["dist"].view(np.uint32), oo["dist"].view(np.uint32))
     t.close()
+
+
+# ------------------------------------------------------------------ GPU BVH build
+def _walk_reference_bvh(nodes_f32, tri_index, n_slots):
+    """Walk a reference-layout mesh BVH; returns (#inner nodes, leaf runs [(first, count)])."""
+    nodes_u = nodes_f32.view(np.uint32).reshape(-1, 16)
+    leaves, inner, stack = [], 0, [0]
+    while stack:
+        a = stack.pop(); assert a % 4 == 0
+        inner += 1
+        for ci in range(2):
+            child = int(nodes_u[a // 4, 12 + ci]); child = child - (1 << 32) if child >= 0x80000000 else child
+            if child == 0x76543210:
+                continue
+            if child < 0:
+                first = ~child; k = first
+                while not (tri_index[k] & 1):
+                    k += 1
+                leaves.append((first, k - first + 1))
+            else:
+                stack.append(child)
+    return inner, leaves
+
+
+@pytest.mark.parametrize("kind", ["cornell7", "soup", "c2"])
+def test_gpu_bvh_build_matches_cpu_bvh_results(built_lib, orc, kind):
+    """ctl_scene_rebuild_bvh_gpu: LBVH built on the device in the reference layout.  Different tree, same data surface:
+    every triangle referenced exactly once, leaves <= 8, and closest hits / images identical to the CPU-built (SAH) tree."""
+    w, h = 192, 108
+    s_cpu = ctl.Scene(kind, w, h); s_gpu = ctl.Scene(kind, w, h)
+    ms = s_gpu.rebuildBVHOnGPU()
+    assert ms > 0 and s_gpu.view.n_woop == s_cpu.view.n_woop == s_gpu.view.n_tri_index
+    meshes = s_gpu.array("meshes"); tri_index = s_gpu.array("tri_index")[:, 0]; bvh = s_gpu.array("bvh_nodes")
+    for mi, m in enumerate(meshes):
+        node_off4, idx_off = int(m[1]), int(m[3])
+        n_slots = (int(meshes[mi + 1][3]) if mi + 1 < len(meshes) else s_gpu.view.n_tri_index) - idx_off
+        inner, leaves = _walk_reference_bvh(bvh[node_off4 // 4:], tri_index[idx_off:idx_off + n_slots], n_slots)
+        covered = np.zeros(n_slots, np.int32)
+        for first, cnt in leaves:
+            assert 1 <= cnt <= 8
+            covered[first:first + cnt] += 1
+        assert np.all(covered == 1)                                                   # slots partitioned by the leaves
+        assert sorted((tri_index[idx_off:idx_off + n_slots] >> 1).tolist()) == list(range(n_slots))   # every triangle exactly once
+    # the oracle traverses the GPU-built tree and the CPU-built tree to the same hits
+    rays = random_rays(s_cpu, 6000, seed=21)
+    a = orc.trace_rays(s_cpu.view, rays); b = orc.trace_rays(s_gpu.view, rays)
+    same = (a["tri_idx"] == b["tri_idx"]) & (a["dist"].view(np.uint32) == b["dist"].view(np.uint32))
+    assert same.mean() >= 0.9995                                                      # exact ties may pick the other triangle
+    # and so does the CUDA path, including the light sampling that points into the re-ordered Woop slots
+    t1 = ctl.PathTracer(w, h); t1.InitializeScene(s_cpu); t1.setParameter("MaxPathLength", 6); t1.DoPasses(2, new_trace=True); t1.synchronize()
+    t2 = ctl.PathTracer(w, h); t2.InitializeScene(s_gpu); t2.setParameter("MaxPathLength", 6); t2.DoPasses(2, new_trace=True); t2.synchronize()
+    g = t2.trace_rays(rays)
+    assert np.array_equal(g["tri_idx"], b["tri_idx"]) and np.array_equal(g["dist"].view(np.uint32), b["dist"].view(np.uint32))
+    i1, i2 = t1.readAccumulator(), t2.readAccumulator()
+    assert np.array_equal(i1["weight_sum"], i2["weight_sum"])
+    assert (rel_l2(i2["rgb"], i1["rgb"]) <= 1e-4).mean() >= 0.999
+    t1.close(); t2.close()
+
+
+def test_gpu_bvh_build_api_edge_cases(built_lib, orc):
+    L = built_lib
+    for n in (1, 2, 8, 9, 300):
+        rng = np.random.default_rng(n)
+        verts = rng.uniform(-1, 1, size=(n, 9)).astype(np.float32)
+        nodes = np.zeros((max(n, 1), 16), np.float32); woop = np.zeros((n, 12), np.float32); index = np.zeros(n, np.uint32)
+        nn = C.c_uint32(0); ms = C.c_float(0)
+        assert L.ctl_bvh_build_gpu(0, verts.ctypes.data, n, nodes.ctypes.data, C.byref(nn), woop.ctypes.data, index.ctypes.data, C.byref(ms)) == 0
+        inner, leaves = _walk_reference_bvh(nodes[:nn.value], index, n)
+        assert inner == nn.value and sum(c for _, c in leaves) == n and all(c <= 8 for _, c in leaves)
+        if n <= 8:   # single-leaf mesh: root = {~0, sentinel} (SplitBVHBuilder.cpp:176-189)
+            assert nn.value == 1 and nodes.view(np.uint32)[0, 12] == 0xffffffff and nodes.view(np.uint32)[0, 13] == 0x76543210
+        for s_ in range(n):  # Woop data of every slot == the host encoder on that triangle's vertices, bit for bit
+            t = index[s_] >> 1
+            assert np.array_equal(woop[s_].view(np.uint32), orc.encode_woop(verts[t, 0:3], verts[t, 3:6], verts[t, 6:9]).view(np.uint32))
+    assert L.ctl_bvh_build_gpu(0, None, 0, None, None, None, None, None) != 0
