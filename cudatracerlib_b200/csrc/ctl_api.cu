@@ -68,7 +68,7 @@ struct ctl_ctx {
     ctlb::SamplerTableGenerator gen;
     // wavefront state
     DevBuf<float4> cf, cl, nor, px, rays_a, rays_b, hit_a, sh_rays, sh_payload, capture;
-    DevBuf<uint32_t> path_a, path_b, path_c, hit_node, sort_keys; DevBuf<float4> rays_c; DevBuf<unsigned> sort_hist, sort_offsets;
+    DevBuf<uint32_t> path_a, path_b, path_c, hit_node, sort_keys; DevBuf<float4> rays_c; DevBuf<unsigned> sort_hist, sort_offsets, mat_hist; DevBuf<unsigned char> mat_cls; DevBuf<uint32_t> mat_order;
     DevBuf<unsigned> counters;
     DevBuf<unsigned long long> stats; // [0] rays_last [1] rays_total [2..4] ext visits [5] ext rays [6..8] shadow visits [9] shadow rays
     DevBuf<float> own_accum; float* accum = nullptr; DevBuf<uchar4> resolve_tmp;
@@ -274,7 +274,7 @@ void ctl_destroy(ctl_ctx* c) {
     c->d_tab1.release(); c->d_tab2.release(); c->d_states.release(); c->d_states0.release(); c->d_jump.release();
     if (c->h_tab1) cudaFreeHost(c->h_tab1); if (c->h_tab2) cudaFreeHost(c->h_tab2); if (c->h_tab_free) cudaEventDestroy(c->h_tab_free);
     c->cf.release(); c->cl.release(); c->nor.release(); c->px.release(); c->rays_a.release(); c->rays_b.release(); c->hit_a.release(); c->sh_rays.release();
-    c->sh_payload.release(); c->capture.release(); c->path_a.release(); c->path_b.release(); c->path_c.release(); c->rays_c.release(); c->sort_keys.release(); c->sort_hist.release(); c->sort_offsets.release(); c->hit_node.release(); c->counters.release(); c->stats.release();
+    c->sh_payload.release(); c->capture.release(); c->path_a.release(); c->path_b.release(); c->path_c.release(); c->rays_c.release(); c->sort_keys.release(); c->sort_hist.release(); c->sort_offsets.release(); c->mat_hist.release(); c->mat_cls.release(); c->mat_order.release(); c->hit_node.release(); c->counters.release(); c->stats.release();
     c->own_accum.release(); c->d_captured_n.release(); c->resolve_tmp.release();
     for (auto e : c->stage_ev) cudaEventDestroy(e);
     cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_stop);
@@ -488,7 +488,8 @@ static int ensure_state(ctl_ctx* c, size_t n) {
     CK(c->cf.ensure(n)); CK(c->cl.ensure(n)); CK(c->nor.ensure(n)); CK(c->px.ensure(n));
     CK(c->rays_a.ensure(2 * n)); CK(c->rays_b.ensure(2 * n)); CK(c->hit_a.ensure(n)); CK(c->hit_node.ensure(n));
     CK(c->sh_rays.ensure(2 * n)); CK(c->sh_payload.ensure(n)); CK(c->path_a.ensure(n)); CK(c->path_b.ensure(n));
-    if (c->sort_mode) {
+    if (c->sort_mode == 2) { CK(c->mat_cls.ensure(n)); CK(c->mat_order.ensure(n)); CK(c->mat_hist.ensure(2 * MAT_CLASSES * (MAX_BOUNCES + 1))); }
+    if (c->sort_mode == 1) {
         CK(c->rays_c.ensure(2 * n)); CK(c->path_c.ensure(n)); CK(c->sort_keys.ensure(n));
         if (!c->sort_hist.p) { CK(c->sort_hist.ensure(SORT_BUCKETS)); CK(c->sort_offsets.ensure(SORT_BUCKETS)); CK(cudaMemsetAsync(c->sort_hist.p, 0, SORT_BUCKETS * sizeof(unsigned), c->stream)); }
     }
@@ -524,6 +525,7 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
 
     c->stage_kind.clear();
     CK(cudaMemsetAsync(c->counters.p, 0, CTR_TOTAL * sizeof(unsigned), c->stream));
+    if (c->sort_mode == 2) CK(cudaMemsetAsync(c->mat_hist.p, 0, 2 * MAT_CLASSES * (MAX_BOUNCES + 1) * sizeof(unsigned), c->stream));
     if (c->instrumented) CK(cudaMemsetAsync(c->stats.p + 2, 0, 8 * sizeof(unsigned long long), c->stream));
     unsigned* ctr = c->counters.p;
     PathState st = {c->cf.p, c->cl.p, c->nor.p, c->px.p};
@@ -551,7 +553,14 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
         else launch_intersect<0, false, false>(c, g_trav, c->stream, c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, nullptr);
         stage_mark(c, 2);
         const bool sort_next = c->sort_mode == 1 && b + 1 < c->max_path_length;
-        Queues Q = {rin, pin, rout, pout, c->hit_a.p, c->hit_node.p, c->sh_rays.p, c->sh_payload.p, sort_next ? c->sort_keys.p : nullptr, sort_next ? c->sort_hist.p : nullptr};
+        const uint32_t* order = nullptr;
+        if (c->sort_mode == 2) { // group this bounce's hits by material class before shading
+            unsigned* hist = c->mat_hist.p + 2 * MAT_CLASSES * b;
+            k_matsort_classify<<<g_light, 256, 0, c->stream>>>(c->scene, ctr + CTR_Q + b, c->hit_a.p, c->hit_node.p, c->mat_cls.p, hist);
+            k_matsort_scatter<<<g_light, 256, 0, c->stream>>>(ctr + CTR_Q + b, c->mat_cls.p, hist, hist + MAT_CLASSES, c->mat_order.p);
+            order = c->mat_order.p; launches += 2;
+        }
+        Queues Q = {rin, pin, rout, pout, c->hit_a.p, c->hit_node.p, c->sh_rays.p, c->sh_payload.p, sort_next ? c->sort_keys.p : nullptr, sort_next ? c->sort_hist.p : nullptr, order};
         k_shade<<<g_light, 128, 0, c->stream>>>(c->scene, P, st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b);
         if (sort_next) { // counting sort of the next bounce's extension queue by (octant, origin cell)
             stage_mark(c, 4);

@@ -34,6 +34,7 @@ struct Queues {
     float4* hit_a;    uint32_t* hit_node;  // (dist,u,v,tri) + node, by queue position
     float4* sh_rays;  float4* sh_payload;  // shadow rays + (pending radiance rgb, path id)
     uint32_t* keys_out; unsigned* hist;    // SortMode 1: sort key of every emitted extension ray + bucket histogram (else null)
+    const uint32_t* order;                 // SortMode 2: queue positions grouped by material class (else null = identity)
 };
 
 CTL_DEV unsigned lane_id() { return threadIdx.x & 31; }
@@ -267,6 +268,53 @@ __global__ void __launch_bounds__(128, 8) k_intersect_fused(const __grid_constan
     trace_persistent<4, false, false>(S, ext_rays, n_ext + n_sh, work_ctr, out, tune, cnt);
 }
 
+// ---- material sort before shading (SortMode 2) ----------------------------------------------------------------------
+// The BSDF dispatch of the reference is a 15-way if-chain inside one thread (Base/VirtualFuncType.h:90-111); a warp that
+// holds diffuse, rough-conductor and dielectric hits executes all three bodies.  Grouping the hit queue by material class
+// (bsdf type, microfacet distribution; misses last) lets each warp of k_shade run one body.  8 buckets: warp-aggregated
+// histogram -> 8-entry scan (done by every block of the scatter) -> index scatter; only 4-byte indices move.
+constexpr int MAT_CLASSES = 8;
+CTL_DEV unsigned material_class(const DScene& S, float4 ha, uint32_t node) {
+    const uint32_t tri = __float_as_uint(ha.w);
+    if (tri == 0xffffffffu) return MAT_CLASSES - 1;
+    const uint32_t w1 = __ldg(&S.tri_data[(size_t)tri * 2].y);
+    const ctl_material* m = S.materials + ((w1 >> 16) & 0xff) + __ldg(&S.nodes[node].material_offset);
+    const uint32_t bt = __ldg(&m->bsdf_type);
+    return bt == CTL_BSDF_ROUGHCONDUCTOR ? 1u + (__ldg(&m->distr_type) & 1u) : (bt == CTL_BSDF_DIELECTRIC ? 3u : 0u);
+}
+__global__ void __launch_bounds__(256) k_matsort_classify(const __grid_constant__ DScene S, const unsigned* __restrict__ n_ptr, const float4* __restrict__ hit_a, const uint32_t* __restrict__ hit_node,
+                                                           unsigned char* __restrict__ cls, unsigned* __restrict__ hist /* MAT_CLASSES, zeroed */) {
+    const int n = (int)*n_ptr;
+    const int n_round = (n + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        unsigned c = MAT_CLASSES; // out of range lanes: no class
+        if (i < n) { c = material_class(S, __ldg(hit_a + i), __ldg(hit_node + i)); cls[i] = (unsigned char)c; }
+        for (unsigned b = 0; b < MAT_CLASSES; b++) {
+            const unsigned m = __ballot_sync(0xffffffffu, c == b);
+            if (m && lane_id() == 0) atomicAdd(hist + b, (unsigned)__popc(m));
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_matsort_scatter(const unsigned* __restrict__ n_ptr, const unsigned char* __restrict__ cls, const unsigned* __restrict__ hist, unsigned* __restrict__ cursor /* MAT_CLASSES, zeroed */,
+                                                          uint32_t* __restrict__ order) {
+    const int n = (int)*n_ptr;
+    unsigned start[MAT_CLASSES]; unsigned run = 0;
+    for (int b = 0; b < MAT_CLASSES; b++) { start[b] = run; run += hist[b]; }
+    const int n_round = (n + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const unsigned c = i < n ? cls[i] : MAT_CLASSES;
+        for (unsigned b = 0; b < MAT_CLASSES; b++) {
+            const unsigned m = __ballot_sync(0xffffffffu, c == b);
+            if (!m) continue;
+            unsigned base = 0;
+            const int leader = __ffs(m) - 1;
+            if ((int)lane_id() == leader) base = atomicAdd(cursor + b, (unsigned)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (c == b) order[start[b] + base + __popc(m & ((1u << lane_id()) - 1u))] = (uint32_t)i;
+        }
+    }
+}
+
 // ---- shade: one path vertex (PathTracer.cu:58-96) ----------------------------------
 struct ShadeParams { int max_path_length, rr_start, direct; };
 
@@ -284,6 +332,8 @@ __global__ void __launch_bounds__(128, CTL_SHADE_MIN_BLOCKS) k_shade(const __gri
         float sh_tmax = 0.0f;
         Spec pending = sp(0.0f);
         if (i < n) {
+            const int i_unsorted = i;
+            const int i = Q.order ? (int)__ldg(Q.order + i_unsorted) : i_unsorted; // material-sorted shading: same work items, grouped
             p = Q.path_in[i];
             const float4 ha = Q.hit_a[i];
             const uint32_t tri = __float_as_uint(ha.w);

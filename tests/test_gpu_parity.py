@@ -529,3 +529,17 @@ def test_gpu_bvh_build_api_edge_cases(built_lib, orc):
             t = index[s_] >> 1
             assert np.array_equal(woop[s_].view(np.uint32), orc.encode_woop(verts[t, 0:3], verts[t, 3:6], verts[t, 6:9]).view(np.uint32))
     assert L.ctl_bvh_build_gpu(0, None, 0, None, None, None, None, None) != 0
+
+
+def test_material_sort_preserves_results(built_lib):
+    """SortMode=2 (hit queue grouped by material class before shading) reorders work only."""
+    w, h = 192, 108
+    for kind in ("soup", "c3", "cornell"):
+        s, t = make(kind, w, h, 8)
+        t.DoPasses(2, new_trace=True); t.synchronize(); a = t.readAccumulator().copy(); ra = t.getRaysInLastPass(); qa = t.queueSizes(8)
+        t.setParameter("SortMode", 2)
+        t.DoPasses(2, new_trace=True); t.synchronize(); b = t.readAccumulator().copy(); rb = t.getRaysInLastPass(); qb = t.queueSizes(8)
+        assert ra == rb and np.array_equal(qa[0], qb[0]) and np.array_equal(qa[1], qb[1])
+        assert np.array_equal(a["weight_sum"], b["weight_sum"])
+        assert np.allclose(a["rgb"], b["rgb"], rtol=2e-6, atol=1e-6)
+        t.close()
