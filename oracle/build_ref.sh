@@ -11,8 +11,11 @@
 #   3. Math/Spectrum.cu:729            cudaMemcpyToSymbol of the static CIE table (device-only) commented out
 #   4. Integrators/PathTracer.cu       lines 1-170 only (PathTrace<DIRECT>; the __global__ kernel and <<<>>> launch are CUDA-only)
 #   5. Engine/Image.cu                 lines 1-86 only (AddSample/Splat/Clear; the luminance kernel is CUDA-only); Image.cpp ctor lines 12-30
-# traceRay / fillDG / the scene globals live in Kernel/TraceHelper.cu between texture<> declarations that CUDA 12 removed;
-# oracle/ref_driver.cpp provides them from the file's host branches on top of the reference's own TracerayTemplate.
+#   6. Kernel/TraceHelper.cu          lines 62-180 (loadModl/loadInvModl, __traceRay_internal__, traceRay) and 274-307 (fillDG) only --
+#                                      the rest of the file is texture<> declarations and kernels that CUDA 12 / g++ cannot compile;
+#                                      the two TracerayTemplate calls get the host node pointers instead of the texture references
+#                                      (the texture overload exists only under __CUDACC__, BVHTraversal.h:7,121)
+# oracle/ref_driver.cpp only defines the scene globals and packs ctl_scene_view into KernelDynamicScene.
 set -euo pipefail
 REF=${CTL_REFERENCE:-/root/reference}
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -46,6 +49,9 @@ p = "Math/Spectrum.cu"; s = open(p).read()
 s2 = s.replace("ThrowCudaErrors(cudaMemcpyToSymbol(device, &host, sizeof(staticData)));", "/* device-only upload removed (oracle/build_ref.sh patch 3) */")
 assert s2 != s; open(p, "w").write(s2)
 PY
+{ sed -n '62,180p' Kernel/TraceHelper.cu; sed -n '274,307p' Kernel/TraceHelper.cu; } \
+  | sed 's/t_nodesA, g_SceneData.m_sBVHNodeData.Data,/g_SceneData.m_sBVHNodeData.Data, (const BVHNodeData*)0,/; s/t_SceneNodes, g_SceneData.m_sSceneBVH.m_pNodes,/g_SceneData.m_sSceneBVH.m_pNodes, (const BVHNodeData*)0,/' > Kernel/TraceHelper_host.inc
+grep -q '(const BVHNodeData\*)0, mesh.m_uBVHNodeOffset' Kernel/TraceHelper_host.inc || { echo "TraceHelper.cu patch 6 did not apply"; exit 4; }
 sed -n '1,170p' Integrators/PathTracer.cu > Integrators/PathTracer_host.inc; echo "}" >> Integrators/PathTracer_host.inc
 sed -n '1,86p' Engine/Image.cu > Engine/Image_host.cu; echo "}" >> Engine/Image_host.cu
 { echo '#include "Image.h"'; echo '#include <Base/CudaMemoryManager.h>'; echo 'namespace CudaTracerLib {'; sed -n '12,30p' Engine/Image.cpp; echo '}'; } > Engine/Image_ctor.cpp

@@ -8,9 +8,10 @@
 // UniformSampleOneLight/EstimateDirect, TraceResult::getBsdfSample, TriangleData::fillDG, BSDFALL (diffuse, roughconductor,
 // dielectric), MicrofacetDistribution, DiffuseLight, ShapeSet::SamplePosition, PerspectiveSensor::sampleRayDifferential,
 // SequenceSampler + SamplingSequenceGeneratorHost + CudaRNG (XORWOW), Image::AddSample.
-// What is written here (the parts of Kernel/TraceHelper.cu that sit between CUDA-12-removed texture<> declarations):
-// the scene/sampler globals, traceRay's two leaf callbacks (host branch of TraceHelper.cu:88-180) and fillDG's host branch
-// (TraceHelper.cu:274-307), plus the packing of ctl_scene_view into KernelDynamicScene.
+// traceRay / __traceRay_internal__ / fillDG are the reference's own lines too (Kernel/TraceHelper.cu:62-180, 274-307, cut out
+// of the file by oracle/build_ref.sh because the rest of it is CUDA-12-removed texture<> declarations and kernels).
+// What is written here: the scene/sampler globals (TraceHelper.cu:23-32), CUDA-runtime stubs backed by host memory, and
+// the packing of ctl_scene_view into KernelDynamicScene.
 #include <Kernel/TraceHelper.h>
 #include <Kernel/TraceAlgorithms.h>
 #include <Kernel/Sampler.h>
@@ -59,69 +60,8 @@ KernelDynamicScene g_SceneDataHost;
 unsigned int g_RayTracedCounterHost;
 CudaStaticWrapper<SamplerData> g_SamplerDataHost;
 
-// ---- traceRay: host branch of Kernel/TraceHelper.cu:88-180 on the pointer overload of TracerayTemplate -----------
-bool traceRay(const Vec3f& dir, const Vec3f& ori, TraceResult* a_Result)
-{
-	Platform::Increment(&g_RayTracedCounter);
-	if (!g_SceneData.m_sNodeData.UsedCount)
-		return false;
-	float rayEps = g_SceneData.m_rayTraceEps;
-	return TracerayTemplate(Ray(ori, dir), a_Result->m_fDist, [&](int nodeIdx)
-	{
-		Node* N = g_SceneData.m_sNodeData.Data + nodeIdx;
-		KernelMesh mesh = g_SceneData.m_sMeshData[N->m_uMeshIndex];
-		unsigned int meshBvhTriOff = mesh.m_uBVHTriangleOffset, meshBvhIndOff = mesh.m_uBVHIndicesOffset, meshTriOff = mesh.m_uTriangleOffset;
-		float4x4 modl = g_SceneData.m_sSceneBVH.m_pInvNodeTransforms[nodeIdx];
-		Vec3f d = modl.TransformDirection(dir), o = modl.TransformPoint(ori);
-		return TracerayTemplate(Ray(o, d), a_Result->m_fDist, [&](int triIdx)
-		{
-			bool found = false;
-			for (int triAddr = triIdx;; triAddr++)
-			{
-				Vec4f* dat = (Vec4f*)g_SceneData.m_sBVHIntData.Data;
-				const Vec4f v00 = dat[meshBvhTriOff + triAddr * 3 + 0];
-				const Vec4f v11 = dat[meshBvhTriOff + triAddr * 3 + 1];
-				const Vec4f v22 = dat[meshBvhTriOff + triAddr * 3 + 2];
-				unsigned int index = g_SceneData.m_sBVHIndexData.Data[meshBvhIndOff + triAddr].index;
-				float Oz = v00.w - o.x*v00.x - o.y*v00.y - o.z*v00.z;
-				float invDz = 1.0f / (d.x*v00.x + d.y*v00.y + d.z*v00.z);
-				float t = Oz * invDz;
-				if (t > rayEps && t < a_Result->m_fDist)
-				{
-					float Ox = v11.w + o.x*v11.x + o.y*v11.y + o.z*v11.z;
-					float Dx = d.x*v11.x + d.y*v11.y + d.z*v11.z;
-					float u = Ox + t*Dx;
-					if (u >= 0.0f)
-					{
-						float Oy = v22.w + o.x*v22.x + o.y*v22.y + o.z*v22.z;
-						float Dy = d.x*v22.x + d.y*v22.y + d.z*v22.z;
-						float v = Oy + t*Dy;
-						if (v >= 0.0f && u + v <= 1.0f)
-						{
-							a_Result->m_nodeIdx = nodeIdx;
-							a_Result->m_triIdx = (index >> 1) + meshTriOff;
-							a_Result->m_fBaryCoords = Vec2f(u, v);
-							a_Result->m_fDist = t;
-							found = true;
-						}
-					}
-				}
-				if (index & 1)
-					break;
-			}
-			return found;
-		}, g_SceneData.m_sBVHNodeData.Data, (const BVHNodeData*)0, mesh.m_uBVHNodeOffset, 0);
-	}, g_SceneData.m_sSceneBVH.m_pNodes, (const BVHNodeData*)0, 0, g_SceneData.m_sSceneBVH.m_sStartNode);
-}
-
-// ---- fillDG: host branch of Kernel/TraceHelper.cu:274-307 --------------------------------------------------------
-void fillDG(const Vec2f& bary, unsigned int triIdx, unsigned int nodeIdx, DifferentialGeometry& dg)
-{
-	float4x4 localToWorld = g_SceneData.m_sSceneBVH.m_pNodeTransforms[nodeIdx];
-	dg.bary = bary;
-	dg.hasUVPartials = false;
-	g_SceneData.m_sTriData[triIdx].fillDG(localToWorld, dg);
-}
+// ---- traceRay / fillDG: the reference's own text (Kernel/TraceHelper.cu:62-180, 274-307), extracted by oracle/build_ref.sh
+#include <Kernel/TraceHelper_host.inc>
 
 } // namespace CudaTracerLib
 
