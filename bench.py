@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--cpu-frac", type=float, default=1.0 / 16, help="fraction of the image the CPU baseline renders per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sort-mode", type=int, default=None)
+    ap.add_argument("--tile", type=int, default=0, help="tile edge for the multi-GPU partition (0 = package default)")
     ap.add_argument("--batch", type=int, default=8, help="progressive passes fused into one wavefront (must divide spp)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -193,6 +194,8 @@ def main():
         dist.barrier()
 
     kind, w, h, spp, depth, desc = WORKLOADS[args.workload]
+    if args.tile > 0:
+        TILE = args.tile
     scene = Scene(kind, w, h)
     tracer = PathTracer(w, h, device=local)
     tracer.InitializeScene(scene)

@@ -5,8 +5,8 @@
 // handleNode SplitBVHBuilder.cpp:163-203, maxLeafSize 8 BVHBuilderHelper.cpp:119) by an LBVH:
 //   triangle boxes + scene box -> 30-bit Morton codes of the centroids -> LSD radix sort (4 x 8 bit, hand-written:
 //   per-block digit histograms, one scan, stable scatter with warp match/ballot ranking) -> Karras 2012 radix tree
-//   (one thread per internal node) -> bottom-up box fit (atomic arrival flags) -> collapse subtrees of <= 8 triangles
-//   into leaves -> emit 64-byte nodes (children in float4 units, ~first-slot leaves, parent links, 0x76543210 sentinel
+//   (one thread per internal node) -> bottom-up box fit + SAH leaf decision (atomic arrival flags) -> subtrees of <= 8 triangles whose leaf
+//   cost beats their split cost become leaves -> emit 64-byte nodes (children in float4 units, ~first-slot leaves, parent links, 0x76543210 sentinel
 //   for a single-leaf mesh), Woop triangles in Morton order and (triIdx << 1 | lastInLeaf) index words.
 // No spatial splits (every triangle is referenced exactly once), so the tree is not the SBVH the reference builds, but any
 // tree in this layout is traversed by the same kernels with identical hit results.  All device-side, one stream.
@@ -154,8 +154,12 @@ __global__ void k_radix_tree(const uint32_t* __restrict__ keys, int n, int* __re
 }
 
 // bottom-up boxes: node_box[2i], node_box[2i+1] for internal nodes; leaves read the sorted triangle boxes
+// Also decides, bottom-up, which subtrees become leaves: SAH with C_inner = 1.2, C_tri = 1 (leaf cost = N * area, split cost =
+// 1.2 * area + cost of the children); a subtree of <= MAX_LEAF triangles collapses when the leaf is not more expensive.
+__device__ __forceinline__ float box_area(float4 lo, float4 hi) { const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z; return 2.0f * (dx * dy + dy * dz + dz * dx); }
 __global__ void k_fit_boxes(const float4* __restrict__ tri_boxes, const uint32_t* __restrict__ vals, int n, const int* __restrict__ left, const int* __restrict__ right,
-                            const int* __restrict__ parent_int, const int* __restrict__ parent_leaf, unsigned* __restrict__ flags, float4* __restrict__ node_box) {
+                            const int* __restrict__ parent_int, const int* __restrict__ parent_leaf, const int* __restrict__ first, const int* __restrict__ last,
+                            unsigned* __restrict__ flags, float4* __restrict__ node_box, float* __restrict__ cost, unsigned char* __restrict__ collapse) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     int node = parent_leaf[s];
@@ -164,32 +168,43 @@ __global__ void k_fit_boxes(const float4* __restrict__ tri_boxes, const uint32_t
         if (atomicAdd(flags + node, 1u) == 0u) return;   // first child to arrive: the sibling will finish this node
         float4 lo = make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0), hi = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, 0);
         const int ch[2] = {left[node], right[node]};
+        float child_cost = 0.0f;
         for (int k = 0; k < 2; k++) {
             float4 a, b;
-            if (ch[k] < 0) { const uint32_t p = vals[~ch[k]]; a = tri_boxes[2 * p]; b = tri_boxes[2 * p + 1]; }
-            else { a = __ldcg(node_box + 2 * ch[k]); b = __ldcg(node_box + 2 * ch[k] + 1); }
+            if (ch[k] < 0) { const uint32_t p = vals[~ch[k]]; a = tri_boxes[2 * p]; b = tri_boxes[2 * p + 1]; child_cost += box_area(a, b); }
+            else { a = __ldcg(node_box + 2 * ch[k]); b = __ldcg(node_box + 2 * ch[k] + 1); child_cost += __ldcg(cost + ch[k]); }
             lo.x = fminf(lo.x, a.x); lo.y = fminf(lo.y, a.y); lo.z = fminf(lo.z, a.z);
             hi.x = fmaxf(hi.x, b.x); hi.y = fmaxf(hi.y, b.y); hi.z = fmaxf(hi.z, b.z);
         }
+        const float area = box_area(lo, hi);
+        const int count = last[node] - first[node] + 1;
+        const float split_cost = 1.2f * area + child_cost, leaf_cost = count <= MAX_LEAF ? (float)count * area : 3.0e38f;
+        collapse[node] = leaf_cost <= split_cost ? 1 : 0;
+        __stcg(cost + node, fminf(leaf_cost, split_cost));
         __stcg(node_box + 2 * node, lo); __stcg(node_box + 2 * node + 1, hi);
         node = parent_int[node];
     }
 }
 
-// emitted[i] = 1 iff internal node i covers more than MAX_LEAF triangles (it becomes a BVHNodeData; smaller subtrees become leaves)
-__global__ void k_mark_emitted(int n, const int* __restrict__ first, const int* __restrict__ last, unsigned* __restrict__ emitted) {
+// An internal node becomes a BVHNodeData iff neither it nor any ancestor collapsed into a leaf (only subtrees of <= MAX_LEAF
+// triangles can collapse, so the upward walk is at most a few steps).
+__device__ __forceinline__ bool node_emitted(int i, const int* __restrict__ parent_int, const int* __restrict__ first, const int* __restrict__ last, const unsigned char* __restrict__ collapse) {
+    for (int a = i; a >= 0 && (last[a] - first[a] + 1) <= MAX_LEAF; a = parent_int[a]) if (collapse[a]) return false;
+    return true;
+}
+__global__ void k_mark_emitted(int n, const int* __restrict__ parent_int, const int* __restrict__ first, const int* __restrict__ last, const unsigned char* __restrict__ collapse, unsigned* __restrict__ emitted) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n - 1) emitted[i] = (last[i] - first[i] + 1) > MAX_LEAF ? 1u : 0u;
+    if (i < n - 1) emitted[i] = node_emitted(i, parent_int, first, last, collapse) ? 1u : 0u;
     else if (i == n - 1) emitted[i] = 0u;   // slot n-1 receives the total after the exclusive scan
 }
 
 // one thread per internal node: write its BVHNodeData if emitted; mark the last slot of every leaf it creates
 __global__ void k_emit_nodes(int n, const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ parent_int, const int* __restrict__ first, const int* __restrict__ last,
                              const unsigned* __restrict__ new_index /* exclusive scan of emitted */, const float4* __restrict__ tri_boxes, const uint32_t* __restrict__ vals,
-                             const float4* __restrict__ node_box, ctl_bvh_node* __restrict__ nodes, unsigned char* __restrict__ last_flag) {
+                             const float4* __restrict__ node_box, const unsigned char* __restrict__ collapse, ctl_bvh_node* __restrict__ nodes, unsigned char* __restrict__ last_flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
-    if ((last[i] - first[i] + 1) <= MAX_LEAF) return;
+    if (!node_emitted(i, parent_int, first, last, collapse)) return;
     ctl_bvh_node out;
     const int ch[2] = {left[i], right[i]};
     int addr[2];
@@ -198,7 +213,7 @@ __global__ void k_emit_nodes(int n, const int* __restrict__ left, const int* __r
         if (c < 0) { const uint32_t p = vals[~c]; lo = tri_boxes[2 * p]; hi = tri_boxes[2 * p + 1]; addr[k] = c; last_flag[~c] = 1; }   // single triangle: leaf ~slot
         else {
             lo = node_box[2 * c]; hi = node_box[2 * c + 1];
-            if ((last[c] - first[c] + 1) <= MAX_LEAF) { addr[k] = ~first[c]; last_flag[last[c]] = 1; }   // collapsed subtree = leaf over slots first..last
+            if (collapse[c]) { addr[k] = ~first[c]; last_flag[last[c]] = 1; }   // collapsed subtree = leaf over slots first..last
             else addr[k] = (int)(new_index[c] * 4u);
         }
         if (k == 0) { out.a[0] = lo.x; out.a[1] = hi.x; out.a[2] = lo.y; out.a[3] = hi.y; out.c[0] = lo.z; out.c[1] = hi.z; }

@@ -143,13 +143,13 @@ int ctl_bvh_build_gpu(int device, const float* verts9, uint32_t n_tris, ctl_bvh_
     const int n = (int)n_tris;
     const int nb_sort = (n + SORT_TILE - 1) / SORT_TILE;
     DevBuf<float> d_verts; DevBuf<float4> d_boxes, d_nbox; DevBuf<unsigned> d_sbox, d_counts, d_flags, d_emit; DevBuf<uint32_t> d_k0, d_k1, d_v0, d_v1, d_index;
-    DevBuf<int> d_left, d_right, d_pint, d_pleaf, d_first, d_last; DevBuf<ctl_bvh_node> d_nodes; DevBuf<ctl_woop_tri> d_woop; DevBuf<unsigned char> d_lastflag;
+    DevBuf<int> d_left, d_right, d_pint, d_pleaf, d_first, d_last; DevBuf<ctl_bvh_node> d_nodes; DevBuf<ctl_woop_tri> d_woop; DevBuf<unsigned char> d_lastflag, d_collapse; DevBuf<float> d_cost;
     auto free_all = [&]() { d_verts.release(); d_boxes.release(); d_nbox.release(); d_sbox.release(); d_counts.release(); d_flags.release(); d_emit.release(); d_k0.release(); d_k1.release(); d_v0.release(); d_v1.release();
-                            d_index.release(); d_left.release(); d_right.release(); d_pint.release(); d_pleaf.release(); d_first.release(); d_last.release(); d_nodes.release(); d_woop.release(); d_lastflag.release(); };
+                            d_index.release(); d_left.release(); d_right.release(); d_pint.release(); d_pleaf.release(); d_first.release(); d_last.release(); d_nodes.release(); d_woop.release(); d_lastflag.release(); d_collapse.release(); d_cost.release(); };
 #define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { free_all(); char b_[512]; snprintf(b_, sizeof(b_), "In file %s at line %d : %s", __FILE__, __LINE__, cudaGetErrorString(e_)); return set_err(b_); } } while (0)
     CKF(d_verts.upload(verts9, (size_t)n * 9)); CKF(d_boxes.ensure((size_t)n * 2)); CKF(d_nbox.ensure((size_t)n * 2)); CKF(d_sbox.ensure(6)); CKF(d_counts.ensure((size_t)256 * nb_sort));
     CKF(d_flags.ensure((size_t)n)); CKF(d_emit.ensure((size_t)n + 1)); CKF(d_k0.ensure(n)); CKF(d_k1.ensure(n)); CKF(d_v0.ensure(n)); CKF(d_v1.ensure(n)); CKF(d_index.ensure(n));
-    CKF(d_left.ensure(n)); CKF(d_right.ensure(n)); CKF(d_pint.ensure(n)); CKF(d_pleaf.ensure(n)); CKF(d_first.ensure(n)); CKF(d_last.ensure(n)); CKF(d_nodes.ensure((size_t)n)); CKF(d_woop.ensure(n)); CKF(d_lastflag.ensure(n));
+    CKF(d_left.ensure(n)); CKF(d_right.ensure(n)); CKF(d_pint.ensure(n)); CKF(d_pleaf.ensure(n)); CKF(d_first.ensure(n)); CKF(d_last.ensure(n)); CKF(d_nodes.ensure((size_t)n)); CKF(d_woop.ensure(n)); CKF(d_lastflag.ensure(n)); CKF(d_collapse.ensure(n)); CKF(d_cost.ensure(n));
     cudaEvent_t e0, e1; CKF(cudaEventCreate(&e0)); CKF(cudaEventCreate(&e1));
     cudaStream_t st = nullptr;
     CKF(cudaEventRecord(e0, st));
@@ -169,10 +169,10 @@ int ctl_bvh_build_gpu(int device, const float* verts9, uint32_t n_tris, ctl_bvh_
     uint32_t n_nodes = 1;
     if (n > MAX_LEAF) {
         k_radix_tree<<<g, 256, 0, st>>>(kin, n, d_left.p, d_right.p, d_pint.p, d_pleaf.p, d_first.p, d_last.p);
-        k_fit_boxes<<<g, 256, 0, st>>>(d_boxes.p, vin, n, d_left.p, d_right.p, d_pint.p, d_pleaf.p, d_flags.p, d_nbox.p);
-        k_mark_emitted<<<g, 256, 0, st>>>(n, d_first.p, d_last.p, d_emit.p);
+        k_fit_boxes<<<g, 256, 0, st>>>(d_boxes.p, vin, n, d_left.p, d_right.p, d_pint.p, d_pleaf.p, d_first.p, d_last.p, d_flags.p, d_nbox.p, d_cost.p, d_collapse.p);
+        k_mark_emitted<<<g, 256, 0, st>>>(n, d_pint.p, d_first.p, d_last.p, d_collapse.p, d_emit.p);
         k_scan_exclusive<<<1, 1024, 0, st>>>(d_emit.p, (uint32_t)n);
-        k_emit_nodes<<<g, 256, 0, st>>>(n, d_left.p, d_right.p, d_pint.p, d_first.p, d_last.p, d_emit.p, d_boxes.p, vin, d_nbox.p, d_nodes.p, d_lastflag.p);
+        k_emit_nodes<<<g, 256, 0, st>>>(n, d_left.p, d_right.p, d_pint.p, d_first.p, d_last.p, d_emit.p, d_boxes.p, vin, d_nbox.p, d_collapse.p, d_nodes.p, d_lastflag.p);
         CKF(cudaMemcpyAsync(&n_nodes, d_emit.p + (n - 1), 4, cudaMemcpyDeviceToHost, st));
     } else {
         k_single_leaf_root<<<1, 32, 0, st>>>(d_sbox.p, n, d_nodes.p, d_lastflag.p);
