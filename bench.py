@@ -45,13 +45,33 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
 def hbm_peak():
+    """Measured HBM copy bandwidth (GB/s) from the driver-written MEASURED_PEAKS.json, else the profiling guide's fallback."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
         with open(p) as f:
             d = json.load(f)
-        for k in ("hbm_gbs", "hbm_gb_s", "hbm_GBps"):
-            if k in d:
-                return float(d[k]), "measured (MEASURED_PEAKS.json)"
+
+        def find(o):
+            if isinstance(o, dict):
+                for k in ("hbm_gbs", "hbm_gb_s", "hbm_GBps", "hbm_gbps"):
+                    if k in o and isinstance(o[k], (int, float)):
+                        return float(o[k])
+                for k, v in o.items():
+                    if isinstance(v, (int, float)) and "hbm" in k.lower() and 500.0 < float(v) < 20000.0:
+                        return float(v)
+                for v in o.values():
+                    r = find(v)
+                    if r:
+                        return r
+            elif isinstance(o, list):
+                for v in o:
+                    r = find(v)
+                    if r:
+                        return r
+            return None
+        v = find(d)
+        if v:
+            return v, "measured (MEASURED_PEAKS.json)"
     except Exception:
         pass
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
