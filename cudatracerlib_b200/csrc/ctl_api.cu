@@ -237,6 +237,25 @@ static int alloc_image(ctl_ctx* c) {
     return 0;
 }
 
+static int init_ctx(ctl_ctx* c) { // everything of ctl_create that can fail after the context object exists
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c->device));
+    c->n_sm = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CK(cudaEventCreate(&c->ev_start)); CK(cudaEventCreate(&c->ev_stop));
+    CK(cudaEventCreateWithFlags(&c->h_tab_free, cudaEventDisableTiming));
+    {   // device-side table generator: per-sequence start states of pass 0 + the jump matrix to the next pass
+        std::vector<uint32_t> st0((size_t)ctlb::kNumSeq * 6); ctlb::XorwowJump J;
+        ctlb::device_generator_data(st0.data(), &J);
+        CK(c->d_states0.upload(st0.data(), st0.size())); CK(c->d_states.upload(st0.data(), st0.size()));
+        CK(c->d_jump.upload(&J.row[0][0], 160 * 5));
+    }
+    CK(c->counters.ensure(CTR_TOTAL)); CK(c->stats.ensure(16)); CK(c->d_captured_n.ensure(1));
+    CK(cudaMemset(c->stats.p, 0, 16 * sizeof(unsigned long long)));
+    return alloc_image(c);
+}
+
 ctl_ctx* ctl_create(int device, int width, int height) {
     if (width <= 0 || height <= 0) { set_err("invalid resolution"); return nullptr; }
     int n_dev = 0;
@@ -245,29 +264,14 @@ ctl_ctx* ctl_create(int device, int width, int height) {
     CKP(cudaSetDevice(device));
     ctl_ctx* c = new ctl_ctx();
     c->device = device; c->w = width; c->h = height;
-    cudaDeviceProp prop;
-    CKP(cudaGetDeviceProperties(&prop, device));
-    c->n_sm = prop.multiProcessorCount;
-    CKP(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-    c->stream = c->own_stream;
-    CKP(cudaEventCreate(&c->ev_start)); CKP(cudaEventCreate(&c->ev_stop));
-    CKP(cudaEventCreateWithFlags(&c->h_tab_free, cudaEventDisableTiming));
-    {   // device-side table generator: per-sequence start states of pass 0 + the jump matrix to the next pass
-        std::vector<uint32_t> st0((size_t)ctlb::kNumSeq * 6); ctlb::XorwowJump J;
-        ctlb::device_generator_data(st0.data(), &J);
-        CKP(c->d_states0.upload(st0.data(), st0.size())); CKP(c->d_states.upload(st0.data(), st0.size()));
-        CKP(c->d_jump.upload(&J.row[0][0], 160 * 5));
-    }
-    CKP(c->counters.ensure(CTR_TOTAL)); CKP(c->stats.ensure(16)); CKP(c->d_captured_n.ensure(1));
-    CKP(cudaMemset(c->stats.p, 0, 16 * sizeof(unsigned long long)));
-    if (alloc_image(c)) { delete c; return nullptr; }
+    if (init_ctx(c)) { const std::string keep = g_err; ctl_destroy(c); g_err = keep; return nullptr; }
     return c;
 }
 
 void ctl_destroy(ctl_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     c->d_scene_nodes.release(); c->d_bvh_nodes.release(); c->d_woop.release(); c->d_tri_index.release(); c->d_tri_data.release(); c->d_meshes.release();
     c->d_nodes.release(); c->d_xf.release(); c->d_inv_xf.release(); c->d_materials.release(); c->d_lights.release(); c->d_light_tris.release();
     c->d_light_cdf.release(); c->d_normal_lut.release();
@@ -277,8 +281,8 @@ void ctl_destroy(ctl_ctx* c) {
     c->sh_payload.release(); c->capture.release(); c->path_a.release(); c->path_b.release(); c->path_c.release(); c->rays_c.release(); c->sort_keys.release(); c->sort_hist.release(); c->sort_offsets.release(); c->mat_hist.release(); c->mat_cls.release(); c->mat_order.release(); c->hit_node.release(); c->counters.release(); c->stats.release();
     c->own_accum.release(); c->d_captured_n.release(); c->resolve_tmp.release();
     for (auto e : c->stage_ev) cudaEventDestroy(e);
-    cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_stop);
-    cudaStreamDestroy(c->own_stream);
+    if (c->ev_start) cudaEventDestroy(c->ev_start); if (c->ev_stop) cudaEventDestroy(c->ev_stop);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
