@@ -12,8 +12,9 @@ N = 1 : the whole image on one B200.  N > 1 : one process per GPU (torchrun), sc
 interleaved 64x64 tiles (tile % N == rank), "scaling": "strong" (the total work -- one image -- is fixed).
 
 `value`   : device-timed (CUDA events on the launching stream) with the scene resident in HBM.
-`e2e`     : the same frames through the public API with HOST buffers: per step the sample tables are generated on
-            the host and copied H2D from pinned memory, and the PixelData image is copied D2H into pinned memory.
+`e2e`     : the same frames through the public API with HOST buffers: per step the sample tables of every pass are
+            generated on the host (DeviceSampleTables=0, the reference's UpdateKernel behaviour) and copied H2D from pinned
+            memory, and the frame is resolved (default image pipeline) and the RGBA8 image copied D2H into pinned memory.
 `roofline`: the traversal kernel (k_intersect, extension + shadow launches): algorithmic bytes (visit counts of an
             instrumented pass x SURVEY 8d's per-visit bytes) / live CUDA-event time of those launches.
 `cpu_baseline` / `--impl reference`: the reference's CPU path (oracle/_ref when built, else the oracle port) on the
@@ -229,7 +230,8 @@ def main():
     accum = torch.zeros(h * w * 7, dtype=torch.float32, device=dev)
     tracer.setAccumDevicePtr(accum.data_ptr())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    host_img = torch.empty(h * w * 7, dtype=torch.float32, pin_memory=True)
+    d_rgba = torch.empty(h * w * 4, dtype=torch.uint8, device=dev)
+    host_rgba = torch.empty(h * w * 4, dtype=torch.uint8, pin_memory=True)
     table_bytes = 4096 * 30 * 12
 
     batch = min(spp, args.batch)
@@ -243,7 +245,10 @@ def main():
     def frame(read_back):
         df.frame(spp // batch)  # spp passes on this rank's tiles + (N > 1) the one NCCL reduce of the accumulator, all on `stream`
         if read_back and rank == 0:
-            host_img.copy_(accum, non_blocking=True)
+            # what an application reads per frame: the image after the (default) image pipeline, as in the reference's
+            # applyImagePipeline -> RGBCOL (Kernel/ImagePipeline/ImagePipeline.cu:54-63); PixelData stays on the device
+            tracer.resolveSRGB8Device(d_rgba.data_ptr())
+            host_rgba.copy_(d_rgba, non_blocking=True)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -300,7 +305,7 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = rays_frame * e2e_steps / float(te[0]) / 1e6
-    img_mean = float(host_img.view(h, w, 7)[:, :, :3].mean()) if rank == 0 else 0.0
+    img_mean = float(host_rgba.view(h, w, 4)[:, :, :3].float().mean()) if rank == 0 else 0.0
 
     # ---- roofline of the traversal kernel (this rank's share), live CUDA-event stage times of the same batched frames
     tracer.setParameter("StageTimers", 1)
@@ -361,10 +366,10 @@ def main():
                        "partition": "whole image" if world == 1 else f"interleaved {TILE}x{TILE} tiles, tile % {world} == rank; one NCCL reduce of PixelData (7*w*h f32) per step",
                        "l2": "256 MiB buffer written between timed steps (L2 flush); per-pass queue/path-state working set ~0.5 GB > 126 MB L2"},
             "clocks": clk,
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": spp * table_bytes, "d2h_bytes_per_step": h * w * 7 * 4,
-                    "steps": e2e_steps, "note": "wall clock; DeviceSampleTables=0: sample tables generated by the host XORWOW twin and copied H2D from pinned memory for every pass, PixelData image copied D2H to pinned memory every step"},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": spp * table_bytes, "d2h_bytes_per_step": h * w * 4,
+                    "steps": e2e_steps, "note": "wall clock; DeviceSampleTables=0: sample tables generated by the host XORWOW twin and copied H2D from pinned memory for every pass, the frame resolved by ctl_resolve_srgb8 (default image pipeline) and the RGBA8 image copied D2H to pinned memory every step"},
             "gpu_launches": int((launches_per_batch + 1) * (spp // batch) * args.steps),
-            "wall_s_timed_region": t_wall, "image_mean_rgb": img_mean,
+            "wall_s_timed_region": t_wall, "image_mean_srgb8": img_mean,
         }
         if roof:
             line["roofline"] = roof

@@ -294,6 +294,10 @@ class PathTracer:
         _check(lib().ctl_resolve_srgb8(self._ctx, float(splat_scale), None, _ptr(out)))
         return out
 
+    def resolveSRGB8Device(self, d_rgba8, splat_scale=0.0):
+        """Same, into caller-owned device memory (w*h*4 bytes), asynchronous on the tracer's stream."""
+        _check(lib().ctl_resolve_srgb8(self._ctx, float(splat_scale), C.c_void_p(d_rgba8), None))
+
     def accumDevicePtr(self):
         return lib().ctl_accum_device_ptr(self._ctx)
 
