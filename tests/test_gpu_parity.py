@@ -543,3 +543,35 @@ def test_material_sort_preserves_results(built_lib):
         assert np.array_equal(a["weight_sum"], b["weight_sum"])
         assert np.allclose(a["rgb"], b["rgb"], rtol=2e-6, atol=1e-6)
         t.close()
+
+
+def test_edge_cases_small_and_degenerate(built_lib, orc):
+    """1x1 and odd-sized images, MaxPathLength 1, zero-area windows, a scene without lights, rays that miss everything."""
+    # odd sizes, depth 1 (camera ray + one NEE only)
+    for (w, h, depth) in ((1, 1, 8), (33, 7, 1), (65, 3, 2)):
+        s, t = make("cornell", w, h, depth)
+        t.DoPass(True); t.synchronize()
+        img = t.readAccumulator()
+        ref, rays = orc.render(s.view, w, h, n_passes=1, max_path_length=depth)
+        assert np.array_equal(img["weight_sum"], ref["weight_sum"])
+        assert np.allclose(img["rgb"], ref["rgb"], rtol=2e-3, atol=1e-5)
+        assert t.getRaysInLastPass() == rays
+        t.DoPass(False, window=(0, 0, 0, 0)); t.synchronize()          # zero-area window: nothing happens, no error
+        assert np.array_equal(t.readAccumulator()["weight_sum"], ref["weight_sum"])
+        t.close()
+    # no lights: every path contributes exactly zero, weights still accumulate
+    from scene_fixtures import _mat
+    V = np.array([(-1, 0, -1), (1, 0, -1), (1, 0, 1), (-1, 0, 1)], np.float32)
+    s = ctl.Scene.from_mesh(V, np.array([0, 2, 1, 0, 3, 2], np.uint32), np.array([0, 0], np.uint8), [_mat()], np.zeros((1, 3), np.float32),
+                            (0, 1.5, -2.0), (0, 0, 0), (0, 1, 0), 60.0, 40, 30)
+    assert s.view.num_lights == 0
+    t = ctl.PathTracer(40, 30); t.InitializeScene(s); t.setParameter("MaxPathLength", 4)
+    t.DoPasses(2, new_trace=True); t.synchronize()
+    img = t.readAccumulator()
+    assert np.all(img["rgb"] == 0) and img["weight_sum"].sum() == 2 * 40 * 30
+    ref, rays = orc.render(s.view, 40, 30, n_passes=2, max_path_length=4)
+    assert t.getRaysInLastPass() == rays and np.array_equal(img["weight_sum"], ref["weight_sum"])
+    # rays that start outside and point away: all miss, API returns the miss encoding
+    r = np.zeros(64, api.RAY_DTYPE); r["o"] = (0, 50, 0); r["d"] = (0, 1, 0); r["tmax"] = 1e30
+    assert np.all(t.intersect(r)["tri_idx"] == -1) and np.all(t.trace_rays(r)["tri_idx"] == 0xffffffff)
+    t.close()
