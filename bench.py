@@ -357,12 +357,17 @@ def main():
         threads = os.cpu_count() or 1
         frac = args.cpu_frac if args.workload != "cornell" else 1.0
         window = crop_window(w, h, frac)
-        ckind, crays, cdt = cpu_reference_run(scene.view, w, h, depth, window, 1, threads)
-        if cdt < 5.0 and args.workload != "cornell":  # aim at >= ~10 s of CPU work
-            n_p = int(min(spp, max(1, round(10.0 / max(cdt, 1e-3)))))
+        ckind, crays, cdt = cpu_reference_run(scene.view, w, h, depth, window, 1, threads)   # probe: 1 pass on the small crop
+        n_p = 1
+        if args.workload != "cornell" and cdt < 8.0:
+            # size the sample for ~12 s of CPU work: all spp passes on a centre crop of the matching size
+            target_rays = 12.0 * crays / max(cdt, 1e-3)
+            frac2 = min(1.0, target_rays / (crays / frac * spp))
+            if frac2 > frac:
+                window, n_p = crop_window(w, h, frac2), spp
+            else:
+                n_p = int(min(spp, max(1, round(target_rays / crays))))
             ckind, crays, cdt = cpu_reference_run(scene.view, w, h, depth, window, n_p, threads)
-        else:
-            n_p = 1
         cpu = {"value": crays / cdt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": ckind,
                "sample": f"{window[2]-window[0]}x{window[3]-window[1]} centre crop of the {w}x{h} image, {n_p} pass(es), depth {depth}, {crays} rays in {cdt:.2f} s"}
 
