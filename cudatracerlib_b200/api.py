@@ -127,6 +127,7 @@ def lib():
     L.ctl_read_accum.argtypes = [vp, vp]
     L.ctl_accum_device_ptr.argtypes = [vp]; L.ctl_accum_device_ptr.restype = vp
     L.ctl_resolve_srgb8.argtypes = [vp, C.c_float, vp, vp]
+    L.ctl_resolve_filtered_srgb8.argtypes = [vp, C.c_float, i32, C.c_float, C.c_float, C.c_float, vp, vp]
     L.ctl_set_accum_device_ptr.argtypes = [vp, vp]
     L.ctl_stream.argtypes = [vp]; L.ctl_stream.restype = vp
     L.ctl_set_stream.argtypes = [vp, vp]
@@ -292,6 +293,14 @@ class PathTracer:
         """applyImagePipeline(tracer, img) with no filter / post-process: (h, w, 4) uint8 sRGB image."""
         out = np.zeros((self.h, self.w, 4), np.uint8)
         _check(lib().ctl_resolve_srgb8(self._ctx, float(splat_scale), None, _ptr(out)))
+        return out
+
+    FILTERS = {"box": 0, "gaussian": 1, "triangle": 2}
+
+    def resolveFilteredSRGB8(self, filter="box", x_width=0.5, y_width=0.5, alpha=2.0, splat_scale=0.0):
+        """applyImagePipeline(tracer, img, filter): CanonicalFilter reconstruction -> RGBE stage -> sRGB RGBA8."""
+        out = np.zeros((self.h, self.w, 4), np.uint8)
+        _check(lib().ctl_resolve_filtered_srgb8(self._ctx, float(splat_scale), self.FILTERS[filter], float(x_width), float(y_width), float(alpha), None, _ptr(out)))
         return out
 
     def resolveSRGB8Device(self, d_rgba8, splat_scale=0.0):

@@ -652,6 +652,21 @@ int ctl_resolve_srgb8(ctl_ctx* c, float splat_scale, void* d_rgba8, void* host_r
     if (host_rgba8) { CK(cudaMemcpyAsync(host_rgba8, dst, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
     return 0;
 }
+// == applyImagePipeline(tracer, img, filter, process = 0) (ImagePipeline.cu:70-74): CanonicalFilter + RGBE stage + gamma
+int ctl_resolve_filtered_srgb8(ctl_ctx* c, float splat_scale, int filter_type, float x_width, float y_width, float alpha, void* d_rgba8, void* host_rgba8) {
+    if (!c || (!d_rgba8 && !host_rgba8)) return set_err("null argument");
+    if (filter_type < 0 || filter_type > 2) return set_err("filter_type must be 0 (box), 1 (Gaussian) or 2 (triangle)");
+    if (!(x_width > 0) || !(y_width > 0) || x_width > 16 || y_width > 16) return set_err("filter widths out of range (0, 16]");
+    CK(cudaSetDevice(c->device));
+    const int n = c->w * c->h;
+    uchar4* dst = (uchar4*)d_rgba8;
+    if (!dst) { CK(c->resolve_tmp.ensure((size_t)n)); dst = c->resolve_tmp.p; }
+    ResolveFilter F = {filter_type, x_width, y_width, alpha, expf(-alpha * x_width * x_width), expf(-alpha * y_width * y_width)}; // GaussianFilter::Update, SceneTypes/Filter.h:68-72
+    k_resolve_filtered_srgb8<<<grid_for(c, 8), 256, 0, c->stream>>>(c->accum, c->w, c->h, splat_scale, F, dst);
+    CK(cudaGetLastError());
+    if (host_rgba8) { CK(cudaMemcpyAsync(host_rgba8, dst, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+    return 0;
+}
 void* ctl_accum_device_ptr(ctl_ctx* c) { return c ? (void*)c->accum : nullptr; }
 int ctl_set_accum_device_ptr(ctl_ctx* c, void* p) {
     if (!c) return set_err("null context");

@@ -270,6 +270,10 @@ int ctl_read_accum(ctl_ctx*, ctl_pixel_data* host_out);
  * PixelData -> toSpectrum(splatScale) -> sRGB -> RGBA8 (uchar4, a = 255).  Writes w*h*4 bytes to d_rgba8 (device,
  * asynchronous) and/or host_rgba8 (synchronous); either may be NULL.  First row of SURVEY 8f3 ("next"). */
 int ctl_resolve_srgb8(ctl_ctx*, float splat_scale, void* d_rgba8, void* host_rgba8);
+/* == applyImagePipeline(tracer, img, filter) (ImagePipeline.cu:70-74; the call the reference's example main makes with
+ * BoxFilter(0.5, 0.5), main.cpp:172): CanonicalFilter reconstruction (Kernel/ImagePipeline/Filter/CanonicalFilter.cu:6-36) into the
+ * RGBE stage, then gamma.  filter_type 0 = BoxFilter, 1 = GaussianFilter(alpha), 2 = TriangleFilter (SceneTypes/Filter.h). */
+int ctl_resolve_filtered_srgb8(ctl_ctx*, float splat_scale, int filter_type, float x_width, float y_width, float alpha, void* d_rgba8, void* host_rgba8);
 /* Device pointer of the accumulator (7*w*h floats) for in-place NCCL reduce. */
 void* ctl_accum_device_ptr(ctl_ctx*);
 /* Use caller-owned device memory (7*w*h floats) as the accumulator (e.g. a torch tensor). */

@@ -11,6 +11,7 @@
 #   3. Math/Spectrum.cu:729            cudaMemcpyToSymbol of the static CIE table (device-only) commented out
 #   4. Integrators/PathTracer.cu       lines 1-170 only (PathTrace<DIRECT>; the __global__ kernel and <<<>>> launch are CUDA-only)
 #   5. Engine/Image.cu                 lines 1-86 only (AddSample/Splat/Clear; the luminance kernel is CUDA-only); Image.cpp ctor lines 12-30
+#   7. Kernel/ImagePipeline/Filter/CanonicalFilter.cu lines 6-27 only (evalFilter)
 #   6. Kernel/TraceHelper.cu          lines 62-180 (loadModl/loadInvModl, __traceRay_internal__, traceRay) and 274-307 (fillDG) only --
 #                                      the rest of the file is texture<> declarations and kernels that CUDA 12 / g++ cannot compile;
 #                                      the two TracerayTemplate calls get the host node pointers instead of the texture references
@@ -26,7 +27,7 @@ CUDA_INC=${CUDA_INC:-/usr/local/cuda/include}
 if [ -f "$OUT/libctl_ref.so" ] && [ "$OUT/libctl_ref.so" -nt "$HERE/ref_driver.cpp" ] && [ "$OUT/libctl_ref.so" -nt "$HERE/build_ref.sh" ]; then echo "$OUT/libctl_ref.so up to date"; exit 0; fi
 mkdir -p "$OUT" "$SCR/obj"
 trap 'rm -rf "$SCR"' EXIT
-cp -r "$REF"/Base "$REF"/Engine "$REF"/Integrators "$REF"/Kernel "$REF"/Math "$REF"/SceneTypes "$REF"/*.h "$SCR"/
+cp -r "$REF"/Base "$REF"/Engine "$REF"/Integrators "$REF"/Kernel "$REF"/Math "$REF"/SceneTypes "$REF"/*.h "$SCR"/   # scratch copy only
 chmod -R u+w "$SCR"
 cd "$SCR"
 sed -i 's/obj->Is<T>()/obj->template Is<T>()/g; s/obj->As<T>()/obj->template As<T>()/g' Base/VirtualFuncType.h
@@ -52,6 +53,7 @@ PY
 { sed -n '62,180p' Kernel/TraceHelper.cu; sed -n '274,307p' Kernel/TraceHelper.cu; } \
   | sed 's/t_nodesA, g_SceneData.m_sBVHNodeData.Data,/g_SceneData.m_sBVHNodeData.Data, (const BVHNodeData*)0,/; s/t_SceneNodes, g_SceneData.m_sSceneBVH.m_pNodes,/g_SceneData.m_sSceneBVH.m_pNodes, (const BVHNodeData*)0,/' > Kernel/TraceHelper_host.inc
 grep -q '(const BVHNodeData\*)0, mesh.m_uBVHNodeOffset' Kernel/TraceHelper_host.inc || { echo "TraceHelper.cu patch 6 did not apply"; exit 4; }
+sed -n '6,27p' Kernel/ImagePipeline/Filter/CanonicalFilter.cu > Kernel/ImagePipeline/Filter/evalFilter_host.inc   # evalFilter() only; the rest of the file is a kernel + launch
 sed -n '1,170p' Integrators/PathTracer.cu > Integrators/PathTracer_host.inc; echo "}" >> Integrators/PathTracer_host.inc
 sed -n '1,86p' Engine/Image.cu > Engine/Image_host.cu; echo "}" >> Engine/Image_host.cu
 { echo '#include "Image.h"'; echo '#include <Base/CudaMemoryManager.h>'; echo 'namespace CudaTracerLib {'; sed -n '12,30p' Engine/Image.cpp; echo '}'; } > Engine/Image_ctor.cpp

@@ -1004,6 +1004,48 @@ void orc_resolve_srgb8(const ctl_pixel_data* img, int n, float splat_scale, uint
     }
 }
 
+// applyImagePipeline(tracer, img, filter): CanonicalFilter::Apply / evalFilter (Kernel/ImagePipeline/Filter/CanonicalFilter.cu:6-36),
+// filters of SceneTypes/Filter.h (0 box :28-48, 1 Gaussian :50-82, 2 triangle :151-171), RGBE stage (Math/Spectrum.h:534-565),
+// copyFilteredToOutput (ImagePipeline.cu:32-41)
+void orc_resolve_filtered_srgb8(const ctl_pixel_data* img, int w, int h, float splat_scale, int type, float xw, float yw, float alpha, uint8_t* rgba) {
+    const float expx = expf(-alpha * xw * xw), expy = expf(-alpha * yw * yw);
+    auto eval = [&](float x, float y) {
+        if (type == 0) return 1.0f;
+        if (type == 1) return fmaxf(0.f, float(expf(-alpha * x * x) - expx)) * fmaxf(0.f, float(expf(-alpha * y * y) - expy));
+        return fmaxf(0.f, xw - fabsf(x)) * fmaxf(0.f, yw - fabsf(y));
+    };
+    for (int _y = 0; _y < h; _y++) for (int _x = 0; _x < w; _x++) {
+        int x0 = std::max(0, (int)ceilf(_x - xw)), x1 = std::min(w - 1, (int)floorf(_x + xw));
+        int y0 = std::max(0, (int)ceilf(_y - yw)), y1 = std::min(h - 1, (int)floorf(_y + yw));
+        float c[3] = {0, 0, 0};
+        if ((x1 - x0) >= 0 && (y1 - y0) >= 0) {
+            float acc[3] = {0, 0, 0}, accw = 0;
+            for (int y = y0; y <= y1; ++y) for (int x = x0; x <= x1; ++x) {
+                float wt = eval((float)abs(x - _x), (float)abs(y - _y));
+                const ctl_pixel_data& P = img[y * w + x];
+                float weight = P.weight_sum != 0 ? P.weight_sum : 1;
+                for (int k = 0; k < 3; k++) acc[k] += (P.rgb[k] / weight + P.rgb_splat[k] * splat_scale) * wt;
+                accw += wt;
+            }
+            for (int k = 0; k < 3; k++) c[k] = acc[k] / accw;
+        }
+        float mx = std::max(c[0], std::max(c[1], c[2]));
+        if (mx < 1e-32) c[0] = c[1] = c[2] = 0;
+        else {
+            int e; float scale = (float)frexp((double)mx, &e) * 256.0f / mx;
+            unsigned char eb = (unsigned char)(e + 128);
+            float ex = ldexpf(1.0f, int(eb) - (128 + 8));
+            for (int k = 0; k < 3; k++) c[k] = (float)(unsigned char)(c[k] * scale) * ex;
+        }
+        for (int k = 0; k < 3; k++) {
+            float v = c[k], s2 = v <= (float)0.0031308 ? (float)12.92 * v : (float)1.055 * powf(v, (float)(1.0 / 2.4)) - (float)0.055;
+            float cl = s2 < 0.0f ? 0.0f : (s2 > 1.0f ? 1.0f : s2);
+            rgba[4 * (_y * w + _x) + k] = (unsigned char)(cl * 255.0f);
+        }
+        rgba[4 * (_y * w + _x) + 3] = 255;
+    }
+}
+
 int orc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 
 } // extern "C"

@@ -69,6 +69,10 @@ CudaStaticWrapper<SamplerData> g_SamplerDataHost;
 #include "ref_stubs.inc"
 
 #include <Integrators/PathTracer_host.inc>   // the reference's PathTrace<DIRECT> (Integrators/PathTracer.cu:1-170)
+#include <SceneTypes/Filter.h>
+namespace CudaTracerLib {
+#include <Kernel/ImagePipeline/Filter/evalFilter_host.inc>   // the reference's evalFilter (CanonicalFilter.cu:6-27)
+}
 
 using namespace CudaTracerLib;
 
@@ -238,6 +242,24 @@ void ref_resolve_srgb8(const ctl_pixel_data* img, int n, float splat_scale, unsi
 		Spectrum c = pd.toSpectrum(splat_scale), c2;
 		c.toSRGB(c2[0], c2[1], c2[2]);
 		RGBCOL o = Spectrum(c2).toRGBCOL();
+		rgba[4 * i] = o.x; rgba[4 * i + 1] = o.y; rgba[4 * i + 2] = o.z; rgba[4 * i + 3] = o.w;
+	}
+}
+
+// applyImagePipeline(tracer, img, filter): rtm_Copy (CanonicalFilter.cu:29-36) + copyFilteredToOutput (ImagePipeline.cu:32-41)
+// with the reference's evalFilter, Filter aggregate, toRGBE / fromRGBE / toSRGB / toRGBCOL
+void ref_resolve_filtered_srgb8(const ctl_pixel_data* img, int w, int h, float splat_scale, int type, float xw, float yw, float alpha, unsigned char* rgba) {
+	std::vector<PixelData> P((size_t)w * h);
+	memcpy((void*)P.data(), img, (size_t)w * h * sizeof(PixelData));
+	Filter filter;
+	if (type == 0) filter.SetData(BoxFilter(xw, yw)); else if (type == 1) filter.SetData(GaussianFilter(xw, yw, alpha)); else filter.SetData(TriangleFilter(xw, yw));
+	for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+		Spectrum c = evalFilter(filter, P.data(), splat_scale, x, y, w, h);
+		RGBE e = c.toRGBE();
+		Spectrum s; s.fromRGBE(e);
+		Spectrum c2; s.toSRGB(c2[0], c2[1], c2[2]);
+		RGBCOL o = Spectrum(c2).toRGBCOL();
+		int i = y * w + x;
 		rgba[4 * i] = o.x; rgba[4 * i + 1] = o.y; rgba[4 * i + 2] = o.z; rgba[4 * i + 3] = o.w;
 	}
 }

@@ -162,6 +162,12 @@ def resolve_srgb8(img, splat_scale=0.0):
     oracle().orc_resolve_srgb8(_p(img), img.size, splat_scale, _p(out)); return out
 
 
+def resolve_filtered_srgb8(img, filter_type=0, xw=0.5, yw=0.5, alpha=2.0, splat_scale=0.0):
+    img = np.ascontiguousarray(img); h, w = img.shape; out = np.zeros((h, w, 4), np.uint8)
+    oracle().orc_resolve_filtered_srgb8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    oracle().orc_resolve_filtered_srgb8(_p(img), w, h, splat_scale, filter_type, xw, yw, alpha, _p(out)); return out
+
+
 def path_probe(view, w, x, y, pass_index=0, max_path_length=8, rr_start=5, direct=1):
     rgb = np.zeros(3, np.float32); rays = C.c_uint64(0)
     oracle().orc_path_probe(C.byref(view), w, x, y, pass_index, max_path_length, rr_start, direct, _p(rgb), C.byref(rays)); return rgb, rays.value

@@ -73,3 +73,9 @@ def resolve_srgb8(img, splat_scale=0.0):
 def bsdf_probe(mat, wi, sx, sy):
     w = np.ascontiguousarray(wi, np.float32); out = np.zeros(9, np.float32); f = np.zeros(3, np.float32); pdf = np.zeros(1, np.float32)
     ref().ref_bsdf_probe(C.byref(mat), _p(w), sx, sy, _p(out), _p(f), _p(pdf)); return out, f, pdf[0]
+
+
+def resolve_filtered_srgb8(img, filter_type=0, xw=0.5, yw=0.5, alpha=2.0, splat_scale=0.0):
+    img = np.ascontiguousarray(img); h, w = img.shape; out = np.zeros((h, w, 4), np.uint8)
+    ref().ref_resolve_filtered_srgb8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    ref().ref_resolve_filtered_srgb8(_p(img), w, h, splat_scale, filter_type, xw, yw, alpha, _p(out)); return out

@@ -163,3 +163,12 @@ def test_resolve_srgb8_matches_reference(orc):
         s = ctl.Scene("cornell", 64, 64)
         img, _ = orc.render(s.view, 64, 64, n_passes=3, max_path_length=6)
         assert np.array_equal(orc.resolve_srgb8(img), rb.resolve_srgb8(img))
+
+
+def test_image_pipeline_goldens(orc):
+    """Default resolve and CanonicalFilter (box / Gaussian / triangle) + RGBE stage: oracle == bytes produced by the
+    reference's own evalFilter / toRGBE / fromRGBE / toSRGB / toRGBCOL (minted from oracle/_ref)."""
+    acc = np.ascontiguousarray(GOLD["pipeline_accum_cornell_80x64_4spp"]).view(api.PIXEL_DTYPE).reshape(64, 80)
+    assert np.array_equal(orc.resolve_srgb8(acc), GOLD["pipeline_resolve_default"])
+    for k, (t, xw, yw, a) in enumerate(GOLD["pipeline_filter_cases"]):
+        assert np.array_equal(orc.resolve_filtered_srgb8(acc, int(t), float(xw), float(yw), float(a)), GOLD[f"pipeline_resolve_filter{k}"])

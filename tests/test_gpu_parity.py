@@ -575,3 +575,27 @@ def test_edge_cases_small_and_degenerate(built_lib, orc):
     r = np.zeros(64, api.RAY_DTYPE); r["o"] = (0, 50, 0); r["d"] = (0, 1, 0); r["tmax"] = 1e30
     assert np.all(t.intersect(r)["tri_idx"] == -1) and np.all(t.trace_rays(r)["tri_idx"] == 0xffffffff)
     t.close()
+
+
+def test_filtered_resolve_golden(built_lib, orc):
+    """ctl_resolve_filtered_srgb8 (applyImagePipeline with a reconstruction filter, the call of the reference's example main) on
+    the reference-rendered accumulator: bytes equal to the reference's own pipeline except <= 1 LSB where CUDA powf/expf and libm
+    straddle a quantisation step."""
+    import torch
+    acc = np.ascontiguousarray(_GOLD["pipeline_accum_cornell_80x64_4spp"])
+    t = ctl.PathTracer(80, 64)
+    d_acc = torch.from_numpy(acc.reshape(-1).copy()).cuda()
+    t.setAccumDevicePtr(d_acc.data_ptr())
+    got = t.resolveSRGB8()
+    d = np.abs(got.astype(np.int32) - _GOLD["pipeline_resolve_default"].astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 0.005
+    names = {0: "box", 1: "gaussian", 2: "triangle"}
+    for k, (ft, xw, yw, a) in enumerate(_GOLD["pipeline_filter_cases"]):
+        got = t.resolveFilteredSRGB8(names[int(ft)], float(xw), float(yw), float(a))
+        ref = _GOLD[f"pipeline_resolve_filter{k}"]
+        d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+        assert d.max() <= 2 and (d > 0).mean() < 0.01, (k, d.max(), (d > 0).mean())   # RGBE mantissa step +- sRGB step
+    with pytest.raises(RuntimeError):
+        t.resolveFilteredSRGB8("box", 0.0, 0.5)
+    t.setAccumDevicePtr(0)
+    t.close()
