@@ -41,7 +41,7 @@ def rel_l2(a, b):
 
 
 # ------------------------------------------------------------------ traversal
-@pytest.mark.parametrize("kind,n", [("cornell", 4096), ("cornell7", 4096), ("soup", 4096), ("c2", 8192), ("c3", 2048)])
+@pytest.mark.parametrize("kind,n", [("cornell", 4096), ("cornell7", 4096), ("soup", 4096), ("c2", 8192), ("c3", 2048), ("c4", 2048)])
 def test_trace_rays_bit_exact(built_lib, orc, kind, n):
     s, t = make(kind)
     for inside in (True, False):
@@ -104,7 +104,8 @@ def test_intersect_device_pointers_async(built_lib, orc):
 
 
 # ------------------------------------------------------------------ radiance
-@pytest.mark.parametrize("kind,w,h,depth", [("cornell", 256, 256, 8), ("cornell7", 128, 128, 8), ("soup", 128, 128, 8), ("c3", 160, 90, 8), ("cornell", 64, 64, 32)])
+@pytest.mark.parametrize("kind,w,h,depth", [("cornell", 256, 256, 8), ("cornell7", 128, 128, 8), ("soup", 128, 128, 8), ("c3", 160, 90, 8), ("cornell", 64, 64, 32),
+                                              ("c4", 96, 54, 8), ("c5", 64, 36, 32)])
 def test_render_pass_matches_oracle(built_lib, orc, kind, w, h, depth):
     s, t = make(kind, w, h, depth)
     t.DoPass(True); t.synchronize()
@@ -599,3 +600,20 @@ def test_filtered_resolve_golden(built_lib, orc):
         t.resolveFilteredSRGB8("box", 0.0, 0.5)
     t.setAccumDevicePtr(0)
     t.close()
+
+
+def test_cpp_example_driver(built_lib, tmp_path):
+    """examples/main.cpp (the reference's example main on this backend) builds with plain g++ and renders."""
+    import subprocess
+    root = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+    libdir = _os.path.dirname(api.LIB_PATH)
+    exe = str(tmp_path / "ctl_render"); out = str(tmp_path / "r.ppm")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", _os.path.join(root, "examples", "main.cpp"), "-I" + _os.path.join(root, "include"), "-L" + libdir, "-lctl_b200",
+                        "-Wl,-rpath," + libdir, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, "1", "4", "96", "64", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    data = open(out, "rb").read()
+    assert data.startswith(b"P6\n96 64\n255\n") and len(data) == len(b"P6\n96 64\n255\n") + 96 * 64 * 3
+    px = np.frombuffer(data[len(b"P6\n96 64\n255\n"):], np.uint8)
+    assert px.mean() > 20 and "4 passes" in r.stdout
