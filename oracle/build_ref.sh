@@ -12,10 +12,18 @@
 #   4. Integrators/PathTracer.cu       lines 1-170 only (PathTrace<DIRECT>; the __global__ kernel and <<<>>> launch are CUDA-only)
 #   5. Engine/Image.cu                 lines 1-86 only (AddSample/Splat/Clear; the luminance kernel is CUDA-only); Image.cpp ctor lines 12-30
 #   7. Kernel/ImagePipeline/Filter/CanonicalFilter.cu lines 6-27 only (evalFilter)
-#   6. Kernel/TraceHelper.cu          lines 62-180 (loadModl/loadInvModl, __traceRay_internal__, traceRay) and 274-307 (fillDG) only --
+#   6. Kernel/TraceHelper.cu          lines 44-60 (traversalResult::toResult/fromResult), 62-180 (loadModl/loadInvModl, __traceRay_internal__, traceRay) and 274-307 (fillDG) only --
 #                                      the rest of the file is texture<> declarations and kernels that CUDA 12 / g++ cannot compile;
 #                                      the two TracerayTemplate calls get the host node pointers instead of the texture references
 #                                      (the texture overload exists only under __CUDACC__, BVHTraversal.h:7,121)
+#   8. Integrators/PseudoRealtime/WavefrontPathTracer.h lines 11-24 (WavefrontPTRayData + buffer typedef) and WavefrontPathTracer.cu lines 51-164
+#                                      (pathIterateKernel<NEE>, compiled as a host function: `__global__` is an ignored attribute for g++);
+#                                      the rest (Tracer<true> subclass, <<<>>> launches, pathCreateKernelWPT's threadIdx/atomics) is CUDA-only.
+#                                      Kernel/DoubleRayBuffer.h is the reference's own header, unpatched (atomicInc is supplied by the driver).
+#   9. (flag, not a source patch) ref_driver.cpp -- the TU that instantiates PathTrace / pathIterateKernel -- is compiled with
+#                                      -ftrivial-auto-var-init=zero: a failed BSDF sample leaves BSDFSamplingRecord::wo unset (Samples.h:181 initialises only
+#                                      f_i), and WavefrontPathTracer still pushes a ray along it (cu:113,139).  Zero-filling defines that read; nothing else
+#                                      depends on it (PathTrace images are bit-identical with and without the flag).
 # oracle/ref_driver.cpp only defines the scene globals and packs ctl_scene_view into KernelDynamicScene.
 set -euo pipefail
 REF=${CTL_REFERENCE:-/root/reference}
@@ -50,11 +58,14 @@ p = "Math/Spectrum.cu"; s = open(p).read()
 s2 = s.replace("ThrowCudaErrors(cudaMemcpyToSymbol(device, &host, sizeof(staticData)));", "/* device-only upload removed (oracle/build_ref.sh patch 3) */")
 assert s2 != s; open(p, "w").write(s2)
 PY
-{ sed -n '62,180p' Kernel/TraceHelper.cu; sed -n '274,307p' Kernel/TraceHelper.cu; } \
+{ sed -n '44,60p' Kernel/TraceHelper.cu; sed -n '62,180p' Kernel/TraceHelper.cu; sed -n '274,307p' Kernel/TraceHelper.cu; } \
   | sed 's/t_nodesA, g_SceneData.m_sBVHNodeData.Data,/g_SceneData.m_sBVHNodeData.Data, (const BVHNodeData*)0,/; s/t_SceneNodes, g_SceneData.m_sSceneBVH.m_pNodes,/g_SceneData.m_sSceneBVH.m_pNodes, (const BVHNodeData*)0,/' > Kernel/TraceHelper_host.inc
 grep -q '(const BVHNodeData\*)0, mesh.m_uBVHNodeOffset' Kernel/TraceHelper_host.inc || { echo "TraceHelper.cu patch 6 did not apply"; exit 4; }
 sed -n '6,27p' Kernel/ImagePipeline/Filter/CanonicalFilter.cu > Kernel/ImagePipeline/Filter/evalFilter_host.inc   # evalFilter() only; the rest of the file is a kernel + launch
 sed -n '1,170p' Integrators/PathTracer.cu > Integrators/PathTracer_host.inc; echo "}" >> Integrators/PathTracer_host.inc
+sed -n '11,24p' Integrators/PseudoRealtime/WavefrontPathTracer.h > Integrators/PseudoRealtime/WavefrontPT_payload_host.inc   # struct WavefrontPTRayData
+sed -n '51,164p' Integrators/PseudoRealtime/WavefrontPathTracer.cu > Integrators/PseudoRealtime/WavefrontPT_iterate_host.inc   # pathIterateKernel<NEXT_EVENT_EST>
+grep -q 'struct WavefrontPTRayData' Integrators/PseudoRealtime/WavefrontPT_payload_host.inc && grep -q 'void pathIterateKernel' Integrators/PseudoRealtime/WavefrontPT_iterate_host.inc || { echo "WavefrontPathTracer extraction (patch 8) did not apply"; exit 4; }
 sed -n '1,86p' Engine/Image.cu > Engine/Image_host.cu; echo "}" >> Engine/Image_host.cu
 { echo '#include "Image.h"'; echo '#include <Base/CudaMemoryManager.h>'; echo 'namespace CudaTracerLib {'; sed -n '12,30p' Engine/Image.cpp; echo '}'; } > Engine/Image_ctor.cpp
 CXXFLAGS="-std=c++17 -x c++ -include cstring -include cmath -fpermissive -w -O2 -fPIC -ffp-contract=off -pthread -I$SCR -I$CUDA_INC -I$HERE/../include"
@@ -67,7 +78,7 @@ for f in $TUS; do
   if [ ${#pids[@]} -ge 8 ]; then wait "${pids[0]}"; pids=("${pids[@]:1}"); fi
 done
 for p in "${pids[@]}"; do wait "$p"; done
-g++ $CXXFLAGS -c "$HERE/ref_driver.cpp" -o obj/ref_driver.o
+g++ $CXXFLAGS -ftrivial-auto-var-init=zero -c "$HERE/ref_driver.cpp" -o obj/ref_driver.o   # note 9
 printf '{ global: ref_*; local: *; };\n' > export.map   # only the ref_* entry points are visible; the CUDA-runtime stubs stay private
 g++ -shared -pthread -o "$OUT/libctl_ref.so" obj/*.o -Wl,-z,defs -Wl,-Bsymbolic -Wl,--version-script=export.map -lm
 echo "built $OUT/libctl_ref.so"

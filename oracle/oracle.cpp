@@ -24,6 +24,14 @@
 // parity is bit-exact.  Everything else is evaluated in the reference's host order.
 #include <cmath>
 #include <cstdint>
+// -DORC_NO_FMA builds liboracle_nofma.so: the same restatement with a*b+c in two roundings, i.e. the arithmetic of the reference's HOST build
+// (g++, no contraction).  tests/test_golden_cpu.py requires that variant to be bit-identical to oracle/_ref, which pins every line of this file;
+// the default build differs from it only in the explicit FMAs below (what nvcc emits for the reference's GPU build and what the product computes).
+#ifdef ORC_NO_FMA
+#define ORC_FMA(a, b, c) ((a) * (b) + (c))
+#else
+#define ORC_FMA(a, b, c) fmaf((a), (b), (c))
+#endif
 #include <cstdio>
 #include <cstring>
 #include <cfloat>
@@ -70,7 +78,7 @@ inline Spec sp(float v) { Spec s = {v, v, v}; return s; }
 inline Spec sp3(const float* p) { Spec s = {p[0], p[1], p[2]}; return s; }
 inline Spec smul(Spec a, Spec b) { Spec s = {a.r * b.r, a.g * b.g, a.b * b.b}; return s; }
 inline Spec smulf(Spec a, float f) { Spec s = {a.r * f, a.g * f, a.b * f}; return s; }
-inline Spec sdivf(Spec a, float f) { Spec s = {a.r / f, a.g / f, a.b / f}; return s; }
+inline Spec sdivf(Spec a, float f) { const float recip = 1.0f / f; Spec s = {a.r * recip, a.g * recip, a.b * recip}; return s; } // Spectrum.h:122-128,150-155: reciprocal multiply
 inline Spec sadd(Spec a, Spec b) { Spec s = {a.r + b.r, a.g + b.g, a.b + b.b}; return s; }
 inline Spec ssub(Spec a, Spec b) { Spec s = {a.r - b.r, a.g - b.g, a.b - b.b}; return s; }
 inline Spec sdiv(Spec a, Spec b) { Spec s = {a.r / b.r, a.g / b.g, a.b / b.b}; return s; }
@@ -266,9 +274,9 @@ inline bool traverse(const float* nodes4, int node_off4, int start, V3 o, V3 d, 
             const float* n = nodes4 + (size_t)(node_off4 + nodeAddr) * 4;
             if (cnt) { cnt->inner++; if (cnt->ev) cnt->ev->push_back('N'); }
             int c0, c1; memcpy(&c0, n + 12, 4); memcpy(&c1, n + 13, 4);
-            float c0lox = fmaf(n[0], idx, -oodx), c0hix = fmaf(n[1], idx, -oodx), c0loy = fmaf(n[2], idy, -oody), c0hiy = fmaf(n[3], idy, -oody);
-            float c0loz = fmaf(n[8], idz, -oodz), c0hiz = fmaf(n[9], idz, -oodz), c1loz = fmaf(n[10], idz, -oodz), c1hiz = fmaf(n[11], idz, -oodz);
-            float c1lox = fmaf(n[4], idx, -oodx), c1hix = fmaf(n[5], idx, -oodx), c1loy = fmaf(n[6], idy, -oody), c1hiy = fmaf(n[7], idy, -oody);
+            float c0lox = ORC_FMA(n[0], idx, -oodx), c0hix = ORC_FMA(n[1], idx, -oodx), c0loy = ORC_FMA(n[2], idy, -oody), c0hiy = ORC_FMA(n[3], idy, -oody);
+            float c0loz = ORC_FMA(n[8], idz, -oodz), c0hiz = ORC_FMA(n[9], idz, -oodz), c1loz = ORC_FMA(n[10], idz, -oodz), c1hiz = ORC_FMA(n[11], idz, -oodz);
+            float c1lox = ORC_FMA(n[4], idx, -oodx), c1hix = ORC_FMA(n[5], idx, -oodx), c1loy = ORC_FMA(n[6], idy, -oody), c1hiy = ORC_FMA(n[7], idy, -oody);
             // spanBegin/EndKepler (MathFunc.h:443-444) == float min/max for t >= 0
             float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tmin_box));
             float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), rayT));
@@ -294,17 +302,17 @@ inline bool traverse(const float* nodes4, int node_off4, int start, V3 o, V3 d, 
 
 // Woop test with the explicit FMA pattern shared with the device kernel (TraceHelper.cu:118-134)
 inline bool woop_test(const float* w, V3 o, V3 d, float tlo, float thi, float& t, float& u, float& v) {
-    float Oz = fmaf(-o.z, w[2], fmaf(-o.y, w[1], fmaf(-o.x, w[0], w[3])));
-    float invDz = 1.0f / fmaf(d.z, w[2], fmaf(d.y, w[1], d.x * w[0]));
+    float Oz = ORC_FMA(-o.z, w[2], ORC_FMA(-o.y, w[1], ORC_FMA(-o.x, w[0], w[3])));
+    float invDz = 1.0f / ORC_FMA(d.z, w[2], ORC_FMA(d.y, w[1], d.x * w[0]));
     t = Oz * invDz;
     if (t > tlo && t < thi) {
-        float Ox = fmaf(o.z, w[6], fmaf(o.y, w[5], fmaf(o.x, w[4], w[7])));
-        float Dx = fmaf(d.z, w[6], fmaf(d.y, w[5], d.x * w[4]));
-        u = fmaf(t, Dx, Ox);
+        float Ox = ORC_FMA(o.z, w[6], ORC_FMA(o.y, w[5], ORC_FMA(o.x, w[4], w[7])));
+        float Dx = ORC_FMA(d.z, w[6], ORC_FMA(d.y, w[5], d.x * w[4]));
+        u = ORC_FMA(t, Dx, Ox);
         if (u >= 0.0f) {
-            float Oy = fmaf(o.z, w[10], fmaf(o.y, w[9], fmaf(o.x, w[8], w[11])));
-            float Dy = fmaf(d.z, w[10], fmaf(d.y, w[9], d.x * w[8]));
-            v = fmaf(t, Dy, Oy);
+            float Oy = ORC_FMA(o.z, w[10], ORC_FMA(o.y, w[9], ORC_FMA(o.x, w[8], w[11])));
+            float Dy = ORC_FMA(d.z, w[10], ORC_FMA(d.y, w[9], d.x * w[8]));
+            v = ORC_FMA(t, Dy, Oy);
             if (v >= 0.0f && u + v <= 1.0f) return true;
         }
     }
@@ -956,6 +964,133 @@ void orc_render(const ctl_scene_view* S, int w, int h, int x0, int y0, int x1, i
     }
     if (rays_out) *rays_out = total_rays;
     if (counts) { counts[0] = total_cnt.inner; counts[1] = total_cnt.tris; counts[2] = total_cnt.inst; }
+}
+
+// WavefrontPathTracer::DoRender (Integrators/PseudoRealtime/WavefrontPathTracer.cu:17-191) over DoubleRayBuffer (Kernel/DoubleRayBuffer.h),
+// restated in the SERIAL schedule of its queue atomics (fetch index i = 0, 1, 2, ...; the k-th insertion lands in slot k): the reference's GPU
+// order depends on the hardware scheduler, and the random numbers of a path are a function of its queue slot (cu:59-60), so the serial order is
+// the one deterministic member of the reference's possible outputs.  It is also what oracle/_ref executes (the reference's own kernel text on one
+// host thread).  Quirks kept: the sampler is keyed by the queue slot and re-skipped to dimension passesDone + 2 at EVERY bounce
+// (cu:59-60); Russian roulette before the BSDF sample, from pathDepth >= RRStartDepth (cu:102-109); one 2-D sample re-used for light selection
+// and light position (KernelDynamicScene.cu:98-117); shadow rays are closest-hit queries compared with dDist * (1 - eps) (cu:68); hits arrive
+// through the 16-byte traversalResult, i.e. with 16-bit barycentrics (TraceHelper.cu:44-60); the previous normal is the 16-bit spherical
+// code (cu:94,137); the sample is splatted at the un-jittered half-precision pixel coordinate (cu:40-41,161).
+// queue_sizes (may be NULL): [2*i] primary, [2*i+1] secondary rays intersected before iteration i of the last pass.
+void orc_render_wavefront(const ctl_scene_view* Sp, int w, int h, int pass_first, int n_passes, int max_path_length, int rr_start, int direct,
+                          ctl_pixel_data* img, uint64_t* rays_out, uint32_t* queue_sizes) {
+    const ctl_scene_view& S = *Sp;
+    struct Payload { Spec throughput; uint16_t x, y; Spec L, directF; float dDist; uint32_t dIdx; bool specular_bounce; float bsdf_pdf; uint32_t prev_normal; }; // WavefrontPathTracer.h:11-22
+    const size_t N = (size_t)w * h;
+    std::vector<Payload> pay(N); std::vector<ctl_traversal_ray> ray(N), sec_in(N), sec_out(N); std::vector<ctl_traversal_result> res(N), sec_res(N);
+    std::vector<float> d1((size_t)N_SEQ * SEQ_LEN), d2((size_t)N_SEQ * SEQ_LEN * 2);
+    Xorwow st; xorwow_init(1234, 7539414, 0, st);
+    for (int p = 0; p < pass_first; p++) fill_tables(st, d1.data(), d2.data());
+    uint64_t rays = 0;
+    auto mk_ray = [&](V3 o, V3 d) { ctl_traversal_ray r; r.o[0] = o.x; r.o[1] = o.y; r.o[2] = o.z; r.tmin = S.ray_eps; r.d[0] = d.x; r.d[1] = d.y; r.d[2] = d.z; r.tmax = FLT_MAX; return r; }; // DoubleRayBuffer.h:234-237
+    for (int p = 0; p < n_passes; p++) {
+        fill_tables(st, d1.data(), d2.data());
+        const unsigned iterationIdx = (unsigned)(pass_first + p + 1); // m_uPassesDone++ precedes DoRender (Kernel/Tracer.h:231-232)
+        // pathCreateKernelWPT (cu:17-49), one sample per pixel
+        uint32_t n_pay = 0, n_sec = 0;
+        for (uint32_t rayidx = 0; rayidx < (uint32_t)N; rayidx++) {
+            int x = (int)(rayidx % (uint32_t)w), y = (int)(rayidx / (uint32_t)w);
+            Sampler rng = {d1.data(), d2.data(), rayidx, 0, 0};
+            float jx, jy; rng.f2(jx, jy); float ax, ay; rng.f2(ax, ay);
+            V3 o, d; camera_ray(S.camera, (float)x + jx, (float)y + jy, o, d);
+            Payload dat; dat.x = f2h((float)x); dat.y = f2h((float)y); dat.throughput = sp(1.0f); dat.L = sp(0.0f); dat.directF = sp(0.0f); dat.dDist = 0; dat.dIdx = UINT_MAX;
+            dat.specular_bounce = true; dat.bsdf_pdf = 0; dat.prev_normal = 0;
+            pay[n_pay] = dat; ray[n_pay] = mk_ray(o, d); n_pay++;
+        }
+        int pathDepth = 0;
+        do {
+            // FinishIteration (DoubleRayBuffer.h:84-112): intersect the primaries and the new secondaries, swap the secondary buffers
+            orc_intersect(Sp, (int)n_pay, ray.data(), res.data(), 0);
+            if (n_sec) orc_intersect(Sp, (int)n_sec, sec_out.data(), sec_res.data(), 0);
+            rays += (uint64_t)n_pay + n_sec;
+            if (queue_sizes && p == n_passes - 1) { queue_sizes[2 * pathDepth] = n_pay; queue_sizes[2 * pathDepth + 1] = n_sec; }
+            const uint32_t n_fetch = n_pay; n_pay = 0; n_sec = 0;
+            sec_in.swap(sec_out); // sec_in + sec_res: what accessSecondaryRay reads; sec_out: what insertSecondaryRay fills
+            // pathIterateKernel<NEXT_EVENT_EST> (cu:51-164)
+            for (uint32_t rayIdx = 0; rayIdx < n_fetch; rayIdx++) {
+                Payload payload = pay[rayIdx];
+                const V3 ro = mk(ray[rayIdx].o[0], ray[rayIdx].o[1], ray[rayIdx].o[2]), rd = mk(ray[rayIdx].d[0], ray[rayIdx].d[1], ray[rayIdx].d[2]);
+                Hit r2; r2.dist = res[rayIdx].dist; r2.node = (uint32_t)res[rayIdx].node_idx; r2.tri = (uint32_t)res[rayIdx].tri_idx; // toResult, TraceHelper.cu:44-51
+                { uint16_t xd = (uint16_t)(res[rayIdx].bary & 0xffff), yd = (uint16_t)(res[rayIdx].bary >> 16); r2.u = (float)xd / 65535.0f; r2.v = (float)yd / 65535.0f; }
+                Sampler rng = {d1.data(), d2.data(), rayIdx, iterationIdx + 2, iterationIdx + 2};
+                if (direct && pathDepth > 0 && payload.dIdx != UINT_MAX) {
+                    if (sec_res[payload.dIdx].dist >= payload.dDist * (1 - S.ray_eps)) payload.L = sadd(payload.L, payload.directF);
+                    payload.dIdx = UINT_MAX; payload.directF = sp(0.0f);
+                }
+                bool path_terminated = (pathDepth + 1 == max_path_length);
+                if (r2.tri != UINT_MAX) {
+                    const ctl_material& mat = S.materials[mat_index_of(S, r2)];
+                    BRec bRec; bRec.wo = mk(0, 0, 0); // unset in the reference; a failed sample still launches a ray along it: defined as zero (oracle/build_ref.sh note 9)
+                     bRec.eta = 1.0f; bRec.sampledType = 0; bRec.typeMask = E_ALL;
+                    bRec.dg.P = add(ro, mul(rd, r2.dist));
+                    fill_dg(S, r2.u, r2.v, r2.tri, r2.node, bRec.dg);
+                    bRec.wi = to_local(bRec.dg.sys, neg(rd));
+                    if ((mat.flags & CTL_MAT_TWO_SIDED) && bRec.wi.z < 0) { bRec.dg.n = neg(bRec.dg.n); bRec.dg.sys.n = neg(bRec.dg.sys.n); bRec.wi.z *= -1.0f; }
+                    if (mat.node_light_index != UINT_MAX) { // cu:84-99
+                        unsigned li = S.nodes[r2.node].lights[mat.node_light_index];
+                        const ctl_light& L = S.lights[li];
+                        float misWeight = 1.0f;
+                        if (!(!direct || pathDepth == 0 || payload.specular_bounce)) {
+                            DRec dRec; dRec.ref = ro; dRec.refN = dec_normal((uint16_t)payload.prev_normal); dRec.p = bRec.dg.P; dRec.n = bRec.dg.n; dRec.d = rd; dRec.dist = r2.dist;
+                            float direct_pdf = light_pdf_direct(L, dRec) * pdf_emitter(S, li);
+                            misWeight = power_heuristic(payload.bsdf_pdf, direct_pdf);
+                        }
+                        Spec Le = dot(bRec.dg.sys.n, neg(rd)) <= 0 ? sp(0.0f) : sp3(L.radiance);
+                        payload.L = sadd(payload.L, smul(smulf(Le, misWeight), payload.throughput)); // misWeight * Le * throughput
+                    }
+                    bool surviveRR = true;
+                    if (pathDepth >= rr_start) { // cu:102-109
+                        if (rng.f1() < smax(payload.throughput)) payload.throughput = sdivf(payload.throughput, smax(payload.throughput));
+                        else surviveRR = false;
+                    }
+                    if (pathDepth + 1 != max_path_length && surviveRR) {
+                        float sx, sy; rng.f2(sx, sy);
+                        Spec f = bsdf_sample(mat, bRec, payload.bsdf_pdf, sx, sy);
+                        payload.specular_bounce = (bRec.sampledType & E_DELTA) != 0;
+                        const V3 refl_d = to_world(bRec.dg.sys, bRec.wo);
+                        payload.dIdx = UINT_MAX;
+                        if (direct && (bsdf_combined_type(mat) & E_SMOOTH)) { // cu:118-135
+                            DRec dRec; dRec.ref = bRec.dg.P; dRec.refN = bRec.dg.sys.n; dRec.p = bRec.dg.P; dRec.n = bRec.dg.sys.n; dRec.pdf = 0;
+                            float lx, ly; rng.f2(lx, ly);
+                            Spec value = sp(0.0f);
+                            if (S.num_lights) { // sampleEmitterDirect / sampleEmitter with sample re-use (KernelDynamicScene.cu:25-40, 98-117)
+                                unsigned idx = (unsigned)(upper_bound_f(S.light_cdf, S.light_cdf + S.num_lights, lx) - S.light_cdf);
+                                if (idx >= S.num_lights) idx = S.num_lights - 1;
+                                float fU = S.light_cdf[idx], fL = idx > 0 ? S.light_cdf[idx - 1] : 0.0f;
+                                lx = (lx - fL) / (fU - fL);
+                                float emPdf = fU - fL;
+                                value = light_sample_direct(S, S.lights[S.light_indices[idx]], dRec, lx, ly);
+                                if (dRec.pdf != 0) { dRec.pdf *= emPdf; value = sdivf(value, emPdf); } else value = sp(0.0f);
+                            }
+                            if (!sis_zero(value)) {
+                                bRec.typeMask = E_ALL & ~E_DELTA;
+                                bRec.wo = to_local(bRec.dg.sys, dRec.d);
+                                Spec bsdfVal = bsdf_f(mat, bRec);
+                                const float bsdfPdf = bsdf_pdf(mat, bRec);
+                                const float directPdf = dRec.pdf; // DiffuseLight::sampleDirect reports ESolidAngle (Light.cu:84-135)
+                                const float weight = power_heuristic(directPdf, bsdfPdf);
+                                payload.directF = smulf(smul(smul(payload.throughput, value), bsdfVal), weight);
+                                payload.dDist = dRec.dist;
+                                if (n_sec < (uint32_t)N) { payload.dIdx = n_sec; sec_out[n_sec] = mk_ray(bRec.dg.P, dRec.d); n_sec++; } // insertSecondaryRay, DoubleRayBuffer.h:166-177
+                            }
+                        }
+                        payload.prev_normal = enc_normal(bRec.dg.sys.n);
+                        payload.throughput = smul(payload.throughput, f);
+                        pay[n_pay] = payload; ray[n_pay] = mk_ray(bRec.dg.P, refl_d); n_pay++;
+                    } else path_terminated = true;
+                } else {
+                    path_terminated = true; // no environment map: the miss adds misWeight * throughput * 0 (cu:143-156)
+                    payload.L = sadd(payload.L, smulf(smul(payload.throughput, sp(0.0f)), 1.0f));
+                }
+                if (path_terminated) add_sample(img, w, h, h2f(payload.x), h2f(payload.y), payload.L);
+            }
+        } while (n_pay != 0 && ++pathDepth < max_path_length);
+    }
+    if (rays_out) *rays_out = rays;
 }
 
 // single path probe (Tracer::Debug / PathTracer::DebugInternal analogue): radiance of pixel (x,y) in pass `pass`

@@ -74,6 +74,45 @@ namespace CudaTracerLib {
 #include <Kernel/ImagePipeline/Filter/evalFilter_host.inc>   // the reference's evalFilter (CanonicalFilter.cu:6-27)
 }
 
+// ---- WavefrontPathTracer: the reference's own pathIterateKernel<NEE> (Integrators/PseudoRealtime/WavefrontPathTracer.cu:51-164)
+// over the reference's own DoubleRayBuffer (Kernel/DoubleRayBuffer.h, unpatched), run by one host thread = the serial schedule of its atomics.
+namespace CudaTracerLib {
+static inline unsigned int atomicInc(unsigned int* a, unsigned int limit) { unsigned int o = *a; *a = (o >= limit) ? 0u : o + 1u; return o; } // CUDA semantics, one thread
+static int g_wpt_threads = 1;
+static std::vector<int> g_wpt_calls;   // N of every __internal__IntersectBuffers call since the last clear
+// __internal__IntersectBuffers (Kernel/TraceHelper.cu:736-746) on the host: the reference's traceRay (t in (rayEps, FLT_MAX), what the queue's
+// rays carry: DoubleRayBuffer.h:236-237) + the reference's traversalResult::fromResult (16-bit barycentrics); a miss is (FLT_MAX, -1, -1, 0)
+// like the kernel's store (TraceHelper.cu:722-731).  Closest hit only (WavefrontPathTracer never asks for any-hit).
+void __internal__IntersectBuffers(int N, traversalRay* rays, traversalResult* res, bool, bool)
+{
+	g_wpt_calls.push_back(N);
+	std::atomic<int> next(0);
+	auto work = [&]() {
+		for (;;) {
+			int i0 = next.fetch_add(256); if (i0 >= N) break;
+			for (int i = i0; i < N && i < i0 + 256; i++) {
+				TraceResult r2 = traceRay(Ray(rays[i].a.getXYZ(), rays[i].b.getXYZ()));
+				if (r2.hasHit()) res[i].fromResult(&r2, g_SceneDataHost);
+				else { res[i].dist = r2.m_fDist; res[i].nodeIdx = -1; res[i].triIdx = -1; res[i].bCoords = 0; }
+			}
+		}
+	};
+	std::vector<std::thread> th;
+	for (int t = 1; t < g_wpt_threads; t++) th.emplace_back(work);
+	work();
+	for (auto& t : th) t.join();
+}
+}
+#include <Kernel/DoubleRayBuffer.h>
+#include <Math/half.h>
+#include <Math/Compression.h>
+namespace CudaTracerLib {
+#include <Integrators/PseudoRealtime/WavefrontPT_payload_host.inc>   // struct WavefrontPTRayData, WavefrontPathTracerBuffer (WavefrontPathTracer.h:11-24)
+CudaStaticWrapper<WavefrontPathTracerBuffer> g_ray_buffer;             // WavefrontPathTracer.cu:14-15
+DeviceDepthImage g_DepthImageWPT;                                      // Kernel/Tracer.h:16-32; never stored to (depthImage = false)
+#include <Integrators/PseudoRealtime/WavefrontPT_iterate_host.inc>   // the reference's pathIterateKernel<NEXT_EVENT_EST> (WavefrontPathTracer.cu:51-164)
+}
+
 using namespace CudaTracerLib;
 
 namespace {
@@ -222,6 +261,62 @@ unsigned long long ref_render(const ctl_scene_view* view, int w, int h, int x0, 
 	for (int yy = 0; yy < h; yy++) for (int xx = 0; xx < w; xx++) memcpy(&img[yy * w + xx], (void*)&I.getPixelData(xx, yy), sizeof(PixelData));
 	I.Free();
 	return g_RayTracedCounterHost;
+}
+
+// WavefrontPathTracer::DoRender (Integrators/PseudoRealtime/WavefrontPathTracer.cu:166-191) for passes [pass_first, pass_first + n_passes) of a
+// fresh tracer, one host thread for the queue kernels (the deterministic serial order of the queue atomics), n_threads for the intersections.
+// pathCreateKernelWPT (cu:17-49) is restated here in its serial order (threadIdx / shared memory / atomicAdd make its text CUDA-only); one sample
+// per pixel (the default uniform block sampler visits every block once per pass, BlockSamplerBuffer.h:38-46).  C++ leaves the evaluation order of
+// the two randomFloat2() arguments of sampleSensorRay unspecified; device code evaluates left to right (jitter = 2-D dimension 0, aperture = 1),
+// which is also PathTracer's explicit order (PathTracer.cu:186-188).  Returns the ray count (N per __internal__IntersectBuffers call).
+unsigned long long ref_render_wavefront(const ctl_scene_view* view, int w, int h, int pass_first, int n_passes,
+                                        int max_path_length, int rr_start, int direct, ctl_pixel_data* img, int n_threads, unsigned int* queue_sizes /* 2 * max_path_length or NULL: last pass */)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	pack_scene(*view);
+	static bool sampler_init = false;
+	if (!sampler_init) { new (&(*g_SamplerDataHost)) SamplerData(4096, 30); sampler_init = true; }
+	delete g_gen; g_gen = new SamplingSequenceGeneratorHost<IndependantSamplingSequenceGenerator>();
+	for (int p = 0; p < pass_first; p++) g_gen->Compute(*g_SamplerDataHost);
+	g_wpt_threads = n_threads < 1 ? 1 : n_threads;
+	Image I(w, h);
+	I.Clear();
+	for (int yy = 0; yy < h; yy++) for (int xx = 0; xx < w; xx++) memcpy((void*)&I.getPixelData(xx, yy), &img[yy * w + xx], sizeof(PixelData));
+	WavefrontPathTracerBuffer* buf = new WavefrontPathTracerBuffer((unsigned)(w * h), (unsigned)(w * h));
+	unsigned long long rays = 0;
+	for (int p = 0; p < n_passes; p++) {
+		g_gen->Compute(*g_SamplerDataHost);
+		const int passes_done = pass_first + p + 1;      // m_uPassesDone++ precedes DoRender (Kernel/Tracer.h:231-232)
+		buf->StartFrame(g_SceneData.m_rayTraceEps);
+		memcpy((void*)&g_ray_buffer.As(), (void*)buf, sizeof(*buf));
+		for (int rayidx = 0; rayidx < w * h; rayidx++) {
+			int x = rayidx % w, y = rayidx / w;
+			auto rng = g_SamplerData((unsigned)rayidx);
+			NormalizedT<Ray> r;
+			Vec2f jitter = rng.randomFloat2(), aperture = rng.randomFloat2();
+			Spectrum W = g_SceneData.sampleSensorRay(r, Vec2f((float)x, (float)y) + jitter, aperture);
+			WavefrontPTRayData dat;
+			dat.x = half((float)x); dat.y = half((float)y); dat.throughput = W; dat.L = Spectrum(0.0f); dat.dIdx = UINT_MAX; dat.specular_bounce = true;
+			dat.directF = Spectrum(0.0f); dat.dDist = 0; dat.bsdf_pdf = 0; dat.prev_normal = 0;   // left uninitialised by the reference; never read before written
+			g_ray_buffer->insertPayloadElement(dat, r);
+		}
+		memcpy((void*)buf, (void*)&g_ray_buffer.As(), sizeof(*buf));
+		int pass = 0;
+		do {
+			g_wpt_calls.clear();
+			buf->FinishIteration();   // primary batch, then the secondary batch if there is one (DoubleRayBuffer.h:84-112)
+			for (int n : g_wpt_calls) rays += (unsigned long long)n;   // g_RayTracedCounterHost += N per call (TraceHelper.cu:745)
+			if (queue_sizes && p == n_passes - 1) { queue_sizes[2 * pass] = (unsigned)g_wpt_calls[0]; queue_sizes[2 * pass + 1] = g_wpt_calls.size() > 1 ? (unsigned)g_wpt_calls[1] : 0u; }
+			memcpy((void*)&g_ray_buffer.As(), (void*)buf, sizeof(*buf));
+			if (direct) pathIterateKernel<true>(I, pass, passes_done, max_path_length, rr_start, false);
+			else pathIterateKernel<false>(I, pass, passes_done, max_path_length, rr_start, false);
+			memcpy((void*)buf, (void*)&g_ray_buffer.As(), sizeof(*buf));
+		} while (!buf->isEmpty() && ++pass < max_path_length);
+	}
+	buf->Free(); delete buf;
+	for (int yy = 0; yy < h; yy++) for (int xx = 0; xx < w; xx++) memcpy(&img[yy * w + xx], (void*)&I.getPixelData(xx, yy), sizeof(PixelData));
+	I.Free();
+	return rays;
 }
 
 // traceRay on a batch (t in (rayEps, FLT_MAX)); out: ctl_trace_result

@@ -10,21 +10,32 @@ from cudatracerlib_b200.api import SceneView, Material, RAY_DTYPE, RESULT16_DTYP
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
-_lib = None
+ORACLE_LIB_NOFMA = os.path.join(ORACLE_DIR, "liboracle_nofma.so")   # host arithmetic (no FMA): the variant pinned bit-for-bit against oracle/_ref
+_libs = {}
+_variant = "fma"
+
+
+class host_arithmetic:
+    """with host_arithmetic(): every oracle call runs the -DORC_NO_FMA build (the reference's host-build arithmetic)."""
+    def __enter__(self):
+        global _variant
+        self.prev = _variant; _variant = "nofma"
+    def __exit__(self, *a):
+        global _variant
+        _variant = self.prev
 
 
 def build_oracle():
     src = os.path.join(ORACLE_DIR, "oracle.cpp")
-    if not os.path.exists(ORACLE_LIB) or os.path.getmtime(src) > os.path.getmtime(ORACLE_LIB):
+    if any(not os.path.exists(l) or os.path.getmtime(src) > os.path.getmtime(l) for l in (ORACLE_LIB, ORACLE_LIB_NOFMA)):
         subprocess.run(["make", "-C", ORACLE_DIR, "-s"], check=True)
     return ORACLE_LIB
 
 
 def oracle():
-    global _lib
-    if _lib is None:
+    if _variant not in _libs:
         build_oracle()
-        L = C.CDLL(ORACLE_LIB)
+        L = C.CDLL(ORACLE_LIB if _variant == "fma" else ORACLE_LIB_NOFMA)
         L.orc_half_to_float.restype = C.c_float; L.orc_half_to_float.argtypes = [C.c_uint16]
         L.orc_float_to_half.restype = C.c_uint16; L.orc_float_to_half.argtypes = [C.c_float]
         L.orc_encode_normal.restype = C.c_uint16
@@ -46,8 +57,9 @@ def oracle():
         L.orc_sampler_draws.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.orc_xorwow_init.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, C.c_void_p]
         L.orc_xorwow_floats.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-        _lib = L
-    return _lib
+        L.orc_render_wavefront.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_void_p, C.c_void_p]
+        _libs[_variant] = L
+    return _libs[_variant]
 
 
 def _p(a):
@@ -171,3 +183,12 @@ def resolve_filtered_srgb8(img, filter_type=0, xw=0.5, yw=0.5, alpha=2.0, splat_
 def path_probe(view, w, x, y, pass_index=0, max_path_length=8, rr_start=5, direct=1):
     rgb = np.zeros(3, np.float32); rays = C.c_uint64(0)
     oracle().orc_path_probe(C.byref(view), w, x, y, pass_index, max_path_length, rr_start, direct, _p(rgb), C.byref(rays)); return rgb, rays.value
+
+
+def render_wavefront(view, w, h, n_passes=1, pass_first=0, max_path_length=8, rr_start=5, direct=1, img=None):
+    """WavefrontPathTracer restatement (serial queue order).  Returns (image, rays, queue sizes [max_path_length, 2] of the last pass)."""
+    if img is None:
+        img = np.zeros((h, w), PIXEL_DTYPE)
+    rays = np.zeros(1, np.uint64); q = np.zeros((max_path_length, 2), np.uint32)
+    oracle().orc_render_wavefront(C.byref(view), w, h, pass_first, n_passes, max_path_length, rr_start, direct, _p(img), _p(rays), _p(q))
+    return img, int(rays[0]), q

@@ -79,3 +79,18 @@ def resolve_filtered_srgb8(img, filter_type=0, xw=0.5, yw=0.5, alpha=2.0, splat_
     img = np.ascontiguousarray(img); h, w = img.shape; out = np.zeros((h, w, 4), np.uint8)
     ref().ref_resolve_filtered_srgb8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
     ref().ref_resolve_filtered_srgb8(_p(img), w, h, splat_scale, filter_type, xw, yw, alpha, _p(out)); return out
+
+
+def render_wavefront(view, w, h, n_passes=1, pass_first=0, max_path_length=8, rr_start=5, direct=1, n_threads=0, img=None):
+    """The reference's WavefrontPathTracer (pathIterateKernel + DoubleRayBuffer, serial queue order).  Returns (image, rays, queue sizes
+    [max_path_length, 2] of the last pass: primary / secondary rays intersected per iteration)."""
+    if img is None:
+        img = np.zeros((h, w), PIXEL_DTYPE)
+    if n_threads <= 0:
+        n_threads = os.cpu_count() or 1
+    q = np.zeros((max_path_length, 2), np.uint32)
+    f = ref().ref_render_wavefront
+    f.restype = C.c_ulonglong
+    f.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_int, C.c_void_p]
+    rays = f(C.byref(view), w, h, pass_first, n_passes, max_path_length, rr_start, direct, _p(img), n_threads, _p(q))
+    return img, int(rays), q
