@@ -122,6 +122,7 @@ def lib():
     L.ctl_render_pass.argtypes = [vp, i32, i32, i32, i32, i32]
     L.ctl_render_pass_tiled.argtypes = [vp, i32, i32, i32, i32, i32]
     L.ctl_render_passes_tiled.argtypes = [vp, i32, i32, i32, i32, i32, i32]
+    L.ctl_wavefront_pass.argtypes = [vp, i32]
     L.ctl_read_sample_tables.argtypes = [vp, i32, vp, vp]
     L.ctl_synchronize.argtypes = [vp]
     L.ctl_read_accum.argtypes = [vp, vp]
@@ -377,6 +378,30 @@ class PathTracer:
             self.close()
         except Exception:
             pass
+
+
+class WavefrontPathTracer(PathTracer):
+    """Mirror of CudaTracerLib::WavefrontPathTracer : Tracer<true> (Integrators/PseudoRealtime/WavefrontPathTracer.h:28-66): the
+    reference's own wavefront integrator over DoubleRayBuffer, SURVEY 8 f1.  Same parameter keys ("Direct", "MaxPathLength",
+    "RRStartDepth"); DoPass renders one path per pixel; results equal the reference's algorithm run in the serial order of its
+    queue atomics (csrc/wavefront_pt.cuh)."""
+
+    def __init__(self, width, height, device=0):
+        super().__init__(width, height, device)
+        self.setParameter("MaxPathLength", 50)   # WavefrontPathTracer.h:38-42 defaults
+        self.setParameter("RRStartDepth", 5)
+        self.setParameter("Direct", 1)
+
+    def DoPass(self, new_trace=None, window=None):
+        if window is not None:
+            raise ValueError("WavefrontPathTracer renders whole frames (its queue slots are pixel indices)")
+        nt = self._new_trace if new_trace is None else bool(new_trace)
+        _check(lib().ctl_wavefront_pass(self._ctx, int(nt))); self._new_trace = False
+
+    def DoPassTiled(self, *a, **k):
+        raise NotImplementedError("WavefrontPathTracer renders whole frames")
+
+    DoPasses = DoPassTiled
 
 
 def generate_sample_tables(pass_index):

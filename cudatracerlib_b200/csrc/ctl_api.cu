@@ -13,6 +13,7 @@
 #include "scene_builder.h"
 #include "sampler_tables.h"
 #include "wavefront.cuh"
+#include "wavefront_pt.cuh"
 #include "bvh_build.cuh"
 
 using namespace ctld;
@@ -70,6 +71,8 @@ struct ctl_ctx {
     DevBuf<float4> cf, cl, nor, px, rays_a, rays_b, hit_a, sh_rays, sh_payload, capture;
     DevBuf<uint32_t> path_a, path_b, path_c, hit_node, sort_keys; DevBuf<float4> rays_c; DevBuf<unsigned> sort_hist, sort_offsets, mat_hist; DevBuf<unsigned char> mat_cls; DevBuf<uint32_t> mat_order;
     DevBuf<unsigned> counters;
+    // WavefrontPathTracer queue (DoubleRayBuffer<WavefrontPTRayData>)
+    DevBuf<float4> w_thr, w_lxy, w_df, w_ray, w_sec[2]; DevBuf<uint2> w_misc; DevBuf<uint4> w_res, w_sres[2]; DevBuf<unsigned long long> w_desc;
     DevBuf<unsigned long long> stats; // [0] rays_last [1] rays_total [2..4] ext visits [5] ext rays [6..8] shadow visits [9] shadow rays
     DevBuf<float> own_accum; float* accum = nullptr; DevBuf<uchar4> resolve_tmp;
     unsigned captured_n = 0; DevBuf<unsigned> d_captured_n;
@@ -280,6 +283,8 @@ void ctl_destroy(ctl_ctx* c) {
     c->cf.release(); c->cl.release(); c->nor.release(); c->px.release(); c->rays_a.release(); c->rays_b.release(); c->hit_a.release(); c->sh_rays.release();
     c->sh_payload.release(); c->capture.release(); c->path_a.release(); c->path_b.release(); c->path_c.release(); c->rays_c.release(); c->sort_keys.release(); c->sort_hist.release(); c->sort_offsets.release(); c->mat_hist.release(); c->mat_cls.release(); c->mat_order.release(); c->hit_node.release(); c->counters.release(); c->stats.release();
     c->own_accum.release(); c->d_captured_n.release(); c->resolve_tmp.release();
+    c->w_thr.release(); c->w_lxy.release(); c->w_df.release(); c->w_ray.release(); c->w_misc.release(); c->w_res.release(); c->w_desc.release();
+    for (int k = 0; k < 2; k++) { c->w_sec[k].release(); c->w_sres[k].release(); }
     for (auto e : c->stage_ev) cudaEventDestroy(e);
     if (c->ev_start) cudaEventDestroy(c->ev_start); if (c->ev_stop) cudaEventDestroy(c->ev_stop);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -624,6 +629,70 @@ int ctl_render_passes_tiled(ctl_ctx* c, int new_trace, int n_passes, int tile_w,
 
 int ctl_render_pass_tiled(ctl_ctx* c, int new_trace, int tile_w, int tile_h, int part, int n_parts) {
     return ctl_render_passes_tiled(c, new_trace, 1, tile_w, tile_h, part, n_parts);
+}
+
+// ------------------------------------------------------------------ WavefrontPathTracer
+__global__ void k_set_u32(unsigned* p, unsigned v) { *p = v; }
+
+// == Tracer<true>::DoPass + WavefrontPathTracer::DoRender (Kernel/Tracer.h:209-248, Integrators/PseudoRealtime/WavefrontPathTracer.cu:166-191).
+// One pass = one path per pixel through the DoubleRayBuffer-shaped queue: create -> { intersect primaries (+ last iteration's secondaries),
+// iterate } x MaxPathLength.  Unlike the reference nothing crosses the host per bounce (it copies the queue struct to and from the device
+// around every kernel, cu:175-188): the queue sizes stay in device counters and an empty iteration costs three empty launches.
+int ctl_wavefront_pass(ctl_ctx* c, int new_trace) {
+    if (!c) return set_err("null context");
+    if (!c->has_scene) return set_err("no scene uploaded");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->ev_start, c->stream));
+    if (new_trace) { CK(cudaMemsetAsync(c->accum, 0, (size_t)c->w * c->h * 7 * sizeof(float), c->stream)); c->passes_done = 0; }
+    if (c->user_tables) c->user_tables = false;
+    else if (generate_tables(c, c->passes_done, 1)) return 1;
+    c->scene.d1 = c->d_tab1.p; c->scene.d2 = (const float2*)c->d_tab2.p;
+    c->scene.img_w = c->w; c->scene.img_h = c->h;
+    const size_t n = (size_t)c->w * c->h;
+    if (n > 0x3fffffffull) return set_err("image too large for the wavefront queue");
+    const int n_tiles = (int)((n + WPT_TILE - 1) / WPT_TILE);
+    const int mpl = c->max_path_length;
+    CK(c->w_thr.ensure(n)); CK(c->w_lxy.ensure(n)); CK(c->w_df.ensure(n)); CK(c->w_misc.ensure(n)); CK(c->w_ray.ensure(2 * n)); CK(c->w_res.ensure(n));
+    for (int k = 0; k < 2; k++) { CK(c->w_sec[k].ensure(2 * n)); CK(c->w_sres[k].ensure(n)); }
+    CK(c->w_desc.ensure((size_t)mpl * (n_tiles + 1)));
+    c->stage_kind.clear();
+    unsigned* ctr = c->counters.p;
+    CK(cudaMemsetAsync(ctr, 0, CTR_TOTAL * sizeof(unsigned), c->stream));
+    CK(cudaMemsetAsync(c->w_desc.p, 0, (size_t)mpl * (n_tiles + 1) * sizeof(unsigned long long), c->stream));
+    const int g_light = grid_for(c, c->shade_blocks_per_sm), g_trav = grid_for(c, c->trav_blocks_per_sm);
+    uint32_t launches = 0;
+    stage_mark(c, 0);
+    k_set_u32<<<1, 1, 0, c->stream>>>(ctr + CTR_Q, (unsigned)n);
+    WptBuf B = {c->w_thr.p, c->w_lxy.p, c->w_df.p, c->w_misc.p, c->w_ray.p, c->w_res.p, nullptr, nullptr};
+    k_wpt_create<<<g_light, 256, 0, c->stream>>>(c->scene, B, (int)n);
+    launches += 2;
+    for (int d = 0; d < mpl; d++) {
+        stage_mark(c, 1);
+        launch_intersect<2, false, false>(c, g_trav, c->stream, c->scene, (const float4*)c->w_ray.p, ctr + CTR_Q + d, 0, ctr + CTR_WORK + 2 * d, nullptr, nullptr, nullptr, nullptr, (void*)c->w_res.p, nullptr);
+        launches++;
+        if (d > 0 && c->direct) { // closest-hit queries for the secondary rays pushed by iteration d-1 (FinishIteration, DoubleRayBuffer.h:84-112)
+            stage_mark(c, 3);
+            launch_intersect<2, false, false>(c, g_trav, c->stream, c->scene, (const float4*)c->w_sec[(d - 1) & 1].p, ctr + CTR_SH + d - 1, 0, ctr + CTR_WORK + 2 * d + 1, nullptr, nullptr, nullptr, nullptr,
+                                              (void*)c->w_sres[(d - 1) & 1].p, nullptr);
+            launches++;
+        }
+        stage_mark(c, 2);
+        B.sec_out = c->w_sec[d & 1].p; B.sec_res = c->w_sres[(d - 1) & 1].p;
+        const WptParams P = {d, (int)c->passes_done + 1, mpl, c->rr_start}; // m_uPassesDone++ precedes DoRender (Kernel/Tracer.h:231-232)
+        unsigned long long* desc = c->w_desc.p + (size_t)d * (n_tiles + 1);
+        if (c->direct) k_wpt_iterate<true><<<n_tiles, WPT_TILE, 0, c->stream>>>(c->scene, P, B, ctr + CTR_Q + d, ctr + CTR_Q + d + 1, ctr + CTR_SH + d, desc, n_tiles, c->accum);
+        else k_wpt_iterate<false><<<n_tiles, WPT_TILE, 0, c->stream>>>(c->scene, P, B, ctr + CTR_Q + d, ctr + CTR_Q + d + 1, ctr + CTR_SH + d, desc, n_tiles, c->accum);
+        launches++;
+    }
+    stage_mark(c, 4);
+    k_tally<<<1, 32, 0, c->stream>>>(ctr + CTR_Q, ctr + CTR_SH, mpl, c->stats.p, c->stats.p + 1);
+    launches++;
+    stage_mark(c, 5);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev_stop, c->stream));
+    c->n_launches = launches;
+    c->passes_done += 1;
+    return 0;
 }
 
 int ctl_synchronize(ctl_ctx* c) {

@@ -39,7 +39,7 @@ CTL_DEV Spec sp3(const float* p) { Spec s; s.r = p[0]; s.g = p[1]; s.b = p[2]; r
 CTL_DEV Spec mk_sp(float r, float g, float b) { Spec s; s.r = r; s.g = g; s.b = b; return s; }
 CTL_DEV Spec operator*(Spec a, Spec b) { return mk_sp(a.r * b.r, a.g * b.g, a.b * b.b); }
 CTL_DEV Spec operator*(Spec a, float f) { return mk_sp(a.r * f, a.g * f, a.b * f); }
-CTL_DEV Spec operator/(Spec a, float f) { return mk_sp(a.r / f, a.g / f, a.b / f); }
+CTL_DEV Spec operator/(Spec a, float f) { const float recip = 1.0f / f; return mk_sp(a.r * recip, a.g * recip, a.b * recip); } // Math/Spectrum.h:122-128, 150-155: reciprocal multiply
 CTL_DEV Spec operator/(Spec a, Spec b) { return mk_sp(a.r / b.r, a.g / b.g, a.b / b.b); }
 CTL_DEV Spec operator+(Spec a, Spec b) { return mk_sp(a.r + b.r, a.g + b.g, a.b + b.b); }
 CTL_DEV Spec operator-(Spec a, Spec b) { return mk_sp(a.r - b.r, a.g - b.g, a.b - b.b); }

@@ -84,12 +84,31 @@ public:
         check(ctl_trace_rays_host(ctx_, (int)rays.size(), rays.data(), out.data(), nullptr)); return out;
     }
     ctl_ctx* handle() { return ctx_; }
+protected:
+    bool take_new_trace(bool a_NewTrace) { const bool nt = a_NewTrace || new_trace_; new_trace_ = false; return nt; }
+    void finish_pass(ctl_pixel_data* image) { if (image) check(ctl_read_accum(ctx_, image)); else check(ctl_synchronize(ctx_)); }
+    void require_ctx() const { need_ctx(); }
 private:
     void need_ctx() const { if (!ctx_) throw std::runtime_error("PathTracer: call Resize(w, h) first"); }
     void apply_params() { for (auto& kv : params_) check(ctl_set_param_i(ctx_, kv.first.c_str(), kv.second)); }
     void stats(uint64_t* r, float* s, uint64_t* t, uint32_t* p) { need_ctx(); check(ctl_stats(ctx_, r, s, t, p)); }
     int device_; ctl_ctx* ctx_ = nullptr; unsigned w_ = 0, h_ = 0; bool new_trace_ = true;
     std::vector<std::pair<std::string, int>> params_;
+};
+
+// == CudaTracerLib::WavefrontPathTracer (Integrators/PseudoRealtime/WavefrontPathTracer.h:28-66): the reference's own wavefront
+// integrator over DoubleRayBuffer -- same parameter keys, same DoPass contract; one pass = one path per pixel.
+class WavefrontPathTracer : public PathTracer {
+public:
+    explicit WavefrontPathTracer(int device = 0) : PathTracer(device) {
+        setParameter("Direct", 1); setParameter("MaxPathLength", 50); setParameter("RRStartDepth", 5); // WavefrontPathTracer.h:38-42
+    }
+    // Tracer<true>::DoPass -> WavefrontPathTracer::DoRender (WavefrontPathTracer.cu:166-191)
+    void DoPass(ctl_pixel_data* image, bool a_NewTrace) {
+        require_ctx();
+        check(ctl_wavefront_pass(handle(), take_new_trace(a_NewTrace) ? 1 : 0));
+        finish_pass(image);
+    }
 };
 
 } // namespace ctlb200

@@ -261,6 +261,13 @@ int ctl_render_pass_tiled(ctl_ctx*, int new_trace, int tile_w, int tile_h, int p
  * atomics into PixelData differs).  Keeps launches large when the image is split over many GPUs and amortises launch
  * overhead; path state is ~230 B x pixels x n_passes of HBM.  part=0, n_parts=1 renders the whole image. */
 int ctl_render_passes_tiled(ctl_ctx*, int new_trace, int n_passes, int tile_w, int tile_h, int part, int n_parts);
+/* == WavefrontPathTracer: Tracer<true>::DoPass + WavefrontPathTracer::DoRender (Kernel/Tracer.h:209-248,
+ *    Integrators/PseudoRealtime/WavefrontPathTracer.cu:166-191) over a DoubleRayBuffer-shaped device queue (Kernel/DoubleRayBuffer.h):
+ *    the reference's own wavefront integrator, second consumer of the intersect kernel.  Same parameters as the reference
+ *    class ("Direct", "MaxPathLength", "RRStartDepth", WavefrontPathTracer.h:32-42).  One pass = one path per pixel; results equal the
+ *    reference's algorithm run in the serial order of its queue atomics (see csrc/wavefront_pt.cuh).  Asynchronous.
+ *    ctl_get_queue_sizes afterwards: ext[i] = primary rays intersected before iteration i, shadow[i] = secondary rays pushed by iteration i. */
+int ctl_wavefront_pass(ctl_ctx*, int new_trace);
 /* Device copy-back of sample-table set `table_set` (0 .. passes of the last batch - 1) for verification. */
 int ctl_read_sample_tables(ctl_ctx*, int table_set, float* d1, float* d2);
 int ctl_synchronize(ctl_ctx*);

@@ -1,0 +1,47 @@
+"""WavefrontPathTracer timing on one GPU: Mrays/s per pass, stage split, vs the PathTracer wavefront on the same scene."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import cudatracerlib_b200 as ctl
+
+kind = sys.argv[1] if len(sys.argv) > 1 else "c2"
+w, h, mpl, spp = 1920, 1080, 8, 8
+s = ctl.Scene(kind, w, h)
+out = {"scene": kind, "w": w, "h": h, "max_path_length": mpl, "spp": spp}
+t = ctl.WavefrontPathTracer(w, h); t.InitializeScene(s); t.setParameter("MaxPathLength", mpl)
+for rep in range(3):   # warm-up frames
+    for p in range(spp):
+        t.DoPass(p == 0)
+t.synchronize()
+import torch
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+st = torch.cuda.Stream(); t.setStream(st.cuda_stream)
+frames = 5
+with torch.cuda.stream(st):
+    e0.record(st)
+    for f in range(frames):
+        for p in range(spp):
+            t.DoPass(p == 0)
+    e1.record(st)
+st.synchronize()
+ms = e0.elapsed_time(e1) / frames
+rays = t.getTotalRays() // (frames + 3)
+out["wavefront_pt"] = {"ms_per_frame": ms, "rays_per_frame": int(rays), "mrays_s": rays / ms / 1e3}
+t.setParameter("StageTimers", 1); t.DoPass(True); t.synchronize()
+sm, nl = t.stageTimes(); out["wavefront_pt"]["stage_ms_one_pass"] = dict(zip(["create", "primary_trav", "iterate", "secondary_trav", "tally"], [round(x, 3) for x in sm])); out["wavefront_pt"]["launches_per_pass"] = nl
+e, sh = t.queueSizes(mpl); out["wavefront_pt"]["queues"] = [e.tolist(), sh.tolist()]
+t.close()
+p = ctl.PathTracer(w, h); p.InitializeScene(s); p.setParameter("MaxPathLength", mpl); p.setStream(st.cuda_stream)
+for rep in range(3):
+    p.DoPasses(spp, new_trace=True)
+p.synchronize()
+with torch.cuda.stream(st):
+    e0.record(st)
+    for f in range(frames):
+        p.DoPasses(spp, new_trace=True)
+    e1.record(st)
+st.synchronize()
+ms = e0.elapsed_time(e1) / frames
+out["path_tracer"] = {"ms_per_frame": ms, "rays_per_frame": int(p.getRaysInLastPass()), "mrays_s": p.getRaysInLastPass() / ms / 1e3}
+p.close()
+print(json.dumps(out))
