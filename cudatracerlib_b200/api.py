@@ -60,6 +60,19 @@ class Camera(C.Structure):
     _fields_ = [("sample_to_camera", C.c_float * 16), ("to_world", C.c_float * 16), ("inv_resolution", C.c_float * 2), ("resolution", C.c_float * 2)]
 
 
+class ImagePipeline(C.Structure):
+    """ctl_image_pipeline: filter_type -1 none / 0 box / 1 gaussian / 2 triangle / 3 mitchell / 4 lanczos; tonemap 0 none / 1 Reinhard05."""
+    _fields_ = [("filter_type", C.c_int32), ("x_width", C.c_float), ("y_width", C.c_float), ("param0", C.c_float), ("param1", C.c_float),
+                ("tonemap", C.c_int32), ("key", C.c_float), ("burn", C.c_float)]
+
+    def __init__(self, filter_type=-1, x_width=0.5, y_width=0.5, param0=0.0, param1=0.0, tonemap=0, key=0.18, burn=0.0):
+        super().__init__(filter_type, x_width, y_width, param0, param1, tonemap, key, burn)
+
+
+VARIANCE_DTYPE = np.dtype([("prev_I", np.float32, 3), ("half_buffer", np.float32, 3), ("iterations_done", np.int32), ("weight", np.float32),
+                           ("sum_x", np.float32), ("sum_x2", np.float32), ("num_samples_var", np.int32)])
+
+
 class SceneView(C.Structure):
     _fields_ = [
         ("bvh_nodes", C.POINTER(BvhNode)), ("n_bvh_nodes", C.c_uint32),
@@ -130,6 +143,8 @@ def lib():
     L.ctl_resolve_srgb8.argtypes = [vp, C.c_float, vp, vp]
     L.ctl_resolve_filtered_srgb8.argtypes = [vp, C.c_float, i32, C.c_float, C.c_float, C.c_float, vp, vp]
     L.ctl_set_accum_device_ptr.argtypes = [vp, vp]
+    L.ctl_apply_image_pipeline.argtypes = [vp, C.c_float, C.POINTER(ImagePipeline), vp, vp, vp]
+    L.ctl_read_variance.argtypes = [vp, vp]
     L.ctl_stream.argtypes = [vp]; L.ctl_stream.restype = vp
     L.ctl_set_stream.argtypes = [vp, vp]
     L.ctl_stats.argtypes = [vp, u64p, fp, u64p, C.POINTER(C.c_uint32)]
@@ -303,6 +318,19 @@ class PathTracer:
         out = np.zeros((self.h, self.w, 4), np.uint8)
         _check(lib().ctl_resolve_filtered_srgb8(self._ctx, float(splat_scale), self.FILTERS[filter], float(x_width), float(y_width), float(alpha), None, _ptr(out)))
         return out
+
+    def applyImagePipeline(self, pipeline, splat_scale=0.0, lum_info=False):
+        """applyImagePipeline(tracer, img, filter, process) (Kernel/ImagePipeline/ImagePipeline.cu:54-84): (h, w, 4) uint8 image
+        [+ (min, max, avg, log-avg luminance, scale, invWp2) of the tone-mapping stage]."""
+        out = np.zeros((self.h, self.w, 4), np.uint8); lum = np.zeros(6, np.float32)
+        _check(lib().ctl_apply_image_pipeline(self._ctx, float(splat_scale), C.byref(pipeline), None, _ptr(out), _ptr(lum) if lum_info else None))
+        return (out, lum) if lum_info else out
+
+    def readVarianceBuffer(self):
+        """PixelVarianceBuffer contents (needs setParameter("PixelVarianceBuffer", 1) before the passes)."""
+        out = np.zeros(self.w * self.h, VARIANCE_DTYPE)
+        _check(lib().ctl_read_variance(self._ctx, _ptr(out)))
+        return out.reshape(self.h, self.w)
 
     def resolveSRGB8Device(self, d_rgba8, splat_scale=0.0):
         """Same, into caller-owned device memory (w*h*4 bytes), asynchronous on the tracer's stream."""

@@ -14,6 +14,7 @@
 #include "sampler_tables.h"
 #include "wavefront.cuh"
 #include "wavefront_pt.cuh"
+#include "image_pipeline.cuh"
 #include "bvh_build.cuh"
 
 using namespace ctld;
@@ -74,7 +75,8 @@ struct ctl_ctx {
     // WavefrontPathTracer queue (DoubleRayBuffer<WavefrontPTRayData>)
     DevBuf<float4> w_thr, w_lxy, w_df, w_ray, w_sec[2]; DevBuf<uint2> w_misc; DevBuf<uint4> w_res, w_sres[2]; DevBuf<unsigned long long> w_desc;
     DevBuf<unsigned long long> stats; // [0] rays_last [1] rays_total [2..4] ext visits [5] ext rays [6..8] shadow visits [9] shadow rays
-    DevBuf<float> own_accum; float* accum = nullptr; DevBuf<uchar4> resolve_tmp;
+    DevBuf<float> own_accum; float* accum = nullptr; DevBuf<uchar4> resolve_tmp, pipe_rgbe; DevBuf<float4> pipe_partial; DevBuf<float> pipe_lum;
+    DevBuf<ctl_pixel_variance_info> d_var; int variance_buffer = 0;
     unsigned captured_n = 0; DevBuf<unsigned> d_captured_n;
     uint32_t passes_done = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
@@ -282,7 +284,7 @@ void ctl_destroy(ctl_ctx* c) {
     if (c->h_tab1) cudaFreeHost(c->h_tab1); if (c->h_tab2) cudaFreeHost(c->h_tab2); if (c->h_tab_free) cudaEventDestroy(c->h_tab_free);
     c->cf.release(); c->cl.release(); c->nor.release(); c->px.release(); c->rays_a.release(); c->rays_b.release(); c->hit_a.release(); c->sh_rays.release();
     c->sh_payload.release(); c->capture.release(); c->path_a.release(); c->path_b.release(); c->path_c.release(); c->rays_c.release(); c->sort_keys.release(); c->sort_hist.release(); c->sort_offsets.release(); c->mat_hist.release(); c->mat_cls.release(); c->mat_order.release(); c->hit_node.release(); c->counters.release(); c->stats.release();
-    c->own_accum.release(); c->d_captured_n.release(); c->resolve_tmp.release();
+    c->own_accum.release(); c->d_captured_n.release(); c->resolve_tmp.release(); c->pipe_rgbe.release(); c->pipe_partial.release(); c->pipe_lum.release(); c->d_var.release();
     c->w_thr.release(); c->w_lxy.release(); c->w_df.release(); c->w_ray.release(); c->w_misc.release(); c->w_res.release(); c->w_desc.release();
     for (int k = 0; k < 2; k++) { c->w_sec[k].release(); c->w_sres[k].release(); }
     for (auto e : c->stage_ev) cudaEventDestroy(e);
@@ -312,6 +314,7 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "CaptureBounce") c->capture_bounce = v;
     else if (k == "DeviceSampleTables") c->device_tables = v != 0;
     else if (k == "FuseTraversal") c->fuse_traversal = v != 0;
+    else if (k == "PixelVarianceBuffer") c->variance_buffer = v != 0;
     else if (k == "TraversalKernel") { if (v < 0 || v > 1) return set_err("TraversalKernel must be 0 or 1"); c->trav_kernel = v; }
     else if (k == "TravThT") c->tune.th_t = v; else if (k == "TravThL") c->tune.th_l = v; else if (k == "TravThF") c->tune.th_f = v;
     else if (k == "TravThNExit") c->tune.th_n_exit = v;
@@ -330,7 +333,7 @@ int ctl_get_param_i(ctl_ctx* c, const char* key, int* v) {
     std::string k(key);
     if (k == "MaxPathLength") *v = c->max_path_length; else if (k == "RRStartDepth") *v = c->rr_start; else if (k == "Direct") *v = c->direct;
     else if (k == "Regularization") *v = c->regularization; else if (k == "SortMode") *v = c->sort_mode; else if (k == "StageTimers") *v = c->stage_timers;
-    else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables; else if (k == "FuseTraversal") *v = c->fuse_traversal;
+    else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables; else if (k == "FuseTraversal") *v = c->fuse_traversal; else if (k == "PixelVarianceBuffer") *v = c->variance_buffer;
     else if (k == "TraversalBlocksPerSM") *v = c->trav_blocks_per_sm; else return set_err("unknown parameter key: " + k);
     return 0;
 }
@@ -513,8 +516,12 @@ static void stage_mark(ctl_ctx* c, int kind) {
     c->stage_kind.push_back(kind);
 }
 
+static int variance_after_pass(ctl_ctx* c, bool new_trace);
+
 static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
     if (!c->has_scene) return set_err("no scene uploaded");
+    if (c->variance_buffer && (W.n_passes != 1 || W.mode != 0 || W.n_slots != c->w * c->h))
+        return set_err("PixelVarianceBuffer=1 needs whole-image single-pass renders (ctl_render_pass with the full window, ctl_wavefront_pass)");
     if (W.n_slots <= 0) return 0;
     CK(cudaSetDevice(c->device));
     CK(cudaEventRecord(c->ev_start, c->stream));
@@ -593,6 +600,7 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
     launches += 2;
     stage_mark(c, 5);
     CK(cudaGetLastError());
+    if (variance_after_pass(c, new_trace != 0)) return 1;
     CK(cudaEventRecord(c->ev_stop, c->stream));
     c->n_launches = launches;
     c->passes_done += W.n_passes;
@@ -689,6 +697,7 @@ int ctl_wavefront_pass(ctl_ctx* c, int new_trace) {
     launches++;
     stage_mark(c, 5);
     CK(cudaGetLastError());
+    if (variance_after_pass(c, new_trace != 0)) return 1;
     CK(cudaEventRecord(c->ev_stop, c->stream));
     c->n_launches = launches;
     c->passes_done += 1;
@@ -709,31 +718,63 @@ int ctl_read_accum(ctl_ctx* c, ctl_pixel_data* out) {
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
-// == applyImagePipeline(tracer, img, filter = 0, process = 0) (Kernel/ImagePipeline/ImagePipeline.cu:54-63): PixelData -> sRGB RGBA8
-int ctl_resolve_srgb8(ctl_ctx* c, float splat_scale, void* d_rgba8, void* host_rgba8) {
-    if (!c || (!d_rgba8 && !host_rgba8)) return set_err("null argument");
+// == applyImagePipeline (Kernel/ImagePipeline/ImagePipeline.cu:54-84): optional reconstruction filter, optional tone mapper, gamma
+int ctl_apply_image_pipeline(ctl_ctx* c, float splat_scale, const ctl_image_pipeline* P, void* d_rgba8, void* host_rgba8, float lum_info[6]) {
+    if (!c || !P || (!d_rgba8 && !host_rgba8)) return set_err("null argument");
+    if (P->filter_type < -1 || P->filter_type > 4) return set_err("filter_type must be -1 (none), 0 (box), 1 (Gaussian), 2 (triangle), 3 (Mitchell) or 4 (Lanczos-sinc)");
+    if (P->filter_type >= 0 && (!(P->x_width > 0) || !(P->y_width > 0) || P->x_width > 16 || P->y_width > 16)) return set_err("filter widths out of range (0, 16]");
+    if (P->tonemap < 0 || P->tonemap > 1) return set_err("tonemap must be 0 (none) or 1 (Reinhard05)");
     CK(cudaSetDevice(c->device));
     const int n = c->w * c->h;
     uchar4* dst = (uchar4*)d_rgba8;
     if (!dst) { CK(c->resolve_tmp.ensure((size_t)n)); dst = c->resolve_tmp.p; }
-    k_resolve_srgb8<<<grid_for(c, 8), 256, 0, c->stream>>>(c->accum, n, splat_scale, dst);
+    const int grid = grid_for(c, 8);
+    PipeFilter F = {P->filter_type, P->x_width, P->y_width, P->param0, P->param1, 1.f / P->x_width, 1.f / P->y_width,
+                    expf(-P->param0 * P->x_width * P->x_width), expf(-P->param0 * P->y_width * P->y_width)}; // FilterBase / GaussianFilter ctor, SceneTypes/Filter.h:15-19, 60-66
+    if (P->filter_type < 0 && !P->tonemap) k_pipe_direct<<<grid, 256, 0, c->stream>>>(c->accum, n, splat_scale, dst);
+    else if (!P->tonemap) k_pipe_stage2<true, true><<<grid, 256, 0, c->stream>>>(c->accum, c->w, c->h, splat_scale, F, dst);
+    else {
+        const int bx = (c->w + 15) / 16, by = (c->h + 15) / 16;
+        CK(c->pipe_rgbe.ensure((size_t)n)); CK(c->pipe_partial.ensure((size_t)bx * by)); CK(c->pipe_lum.ensure(8));
+        if (P->filter_type >= 0) k_pipe_stage2<true, false><<<grid, 256, 0, c->stream>>>(c->accum, c->w, c->h, splat_scale, F, c->pipe_rgbe.p);
+        else k_pipe_stage2<false, false><<<grid, 256, 0, c->stream>>>(c->accum, c->w, c->h, splat_scale, F, c->pipe_rgbe.p);
+        k_lum_blocks<<<bx * by, 256, 0, c->stream>>>(c->pipe_rgbe.p, c->w, c->h, bx, c->pipe_partial.p);
+        k_lum_final<<<1, 32, 0, c->stream>>>(c->pipe_partial.p, bx * by, n, P->key, P->burn, c->pipe_lum.p);
+        k_reinhard<<<grid, 256, 0, c->stream>>>(c->pipe_rgbe.p, n, c->pipe_lum.p, dst);
+        if (lum_info) { CK(cudaMemcpyAsync(lum_info, c->pipe_lum.p, 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+    }
     CK(cudaGetLastError());
     if (host_rgba8) { CK(cudaMemcpyAsync(host_rgba8, dst, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
     return 0;
 }
-// == applyImagePipeline(tracer, img, filter, process = 0) (ImagePipeline.cu:70-74): CanonicalFilter + RGBE stage + gamma
+// == applyImagePipeline(tracer, img, 0, 0): the default resolve
+int ctl_resolve_srgb8(ctl_ctx* c, float splat_scale, void* d_rgba8, void* host_rgba8) {
+    ctl_image_pipeline P; memset(&P, 0, sizeof(P)); P.filter_type = -1;
+    return ctl_apply_image_pipeline(c, splat_scale, &P, d_rgba8, host_rgba8, nullptr);
+}
+// == applyImagePipeline(tracer, img, filter, 0) with box / Gaussian / triangle (kept for callers of the first f3 slice)
 int ctl_resolve_filtered_srgb8(ctl_ctx* c, float splat_scale, int filter_type, float x_width, float y_width, float alpha, void* d_rgba8, void* host_rgba8) {
-    if (!c || (!d_rgba8 && !host_rgba8)) return set_err("null argument");
     if (filter_type < 0 || filter_type > 2) return set_err("filter_type must be 0 (box), 1 (Gaussian) or 2 (triangle)");
-    if (!(x_width > 0) || !(y_width > 0) || x_width > 16 || y_width > 16) return set_err("filter widths out of range (0, 16]");
-    CK(cudaSetDevice(c->device));
-    const int n = c->w * c->h;
-    uchar4* dst = (uchar4*)d_rgba8;
-    if (!dst) { CK(c->resolve_tmp.ensure((size_t)n)); dst = c->resolve_tmp.p; }
-    ResolveFilter F = {filter_type, x_width, y_width, alpha, expf(-alpha * x_width * x_width), expf(-alpha * y_width * y_width)}; // GaussianFilter::Update, SceneTypes/Filter.h:68-72
-    k_resolve_filtered_srgb8<<<grid_for(c, 8), 256, 0, c->stream>>>(c->accum, c->w, c->h, splat_scale, F, dst);
+    ctl_image_pipeline P; memset(&P, 0, sizeof(P)); P.filter_type = filter_type; P.x_width = x_width; P.y_width = y_width; P.param0 = alpha;
+    return ctl_apply_image_pipeline(c, splat_scale, &P, d_rgba8, host_rgba8, nullptr);
+}
+// == PixelVarianceBuffer (Kernel/PixelVarianceBuffer.h)
+static int variance_after_pass(ctl_ctx* c, bool new_trace) { // Tracer<true>::DoPass: Clear on a new trace (Tracer.h:222-226), AddPass after DoRender (:233-237)
+    if (!c->variance_buffer) return 0;
+    const size_t n = (size_t)c->w * c->h;
+    const bool fresh = c->d_var.n < n;
+    CK(c->d_var.ensure(n));
+    if (new_trace || fresh) CK(cudaMemsetAsync(c->d_var.p, 0, n * sizeof(ctl_pixel_variance_info), c->stream));
+    k_variance_update<<<grid_for(c, 8), 256, 0, c->stream>>>(c->d_var.p, c->accum, (int)n, 0.0f /* getSplatScale(): the path tracers never splat */);
     CK(cudaGetLastError());
-    if (host_rgba8) { CK(cudaMemcpyAsync(host_rgba8, dst, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+    return 0;
+}
+int ctl_read_variance(ctl_ctx* c, ctl_pixel_variance_info* out) {
+    if (!c || !out) return set_err("null argument");
+    if (!c->variance_buffer || !c->d_var.p) return set_err("PixelVarianceBuffer is off: ctl_set_param_i(ctx, \"PixelVarianceBuffer\", 1) before the passes");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(out, c->d_var.p, (size_t)c->w * c->h * sizeof(ctl_pixel_variance_info), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 void* ctl_accum_device_ptr(ctl_ctx* c) { return c ? (void*)c->accum : nullptr; }

@@ -451,63 +451,6 @@ __global__ void __launch_bounds__(256) k_finish(int n_slots /* all passes */, Pa
     }
 }
 
-// ---- resolve: the default image pipeline (no filter, no post-process): copySamplesToOutput
-// (Kernel/ImagePipeline/ImagePipeline.cu:14-21) = PixelData::toSpectrum(splatScale) (Engine/Image.h:20-27) -> toSRGB
-// (Math/Spectrum.cu:229-250) -> Float3ToCOLORREF (Math/Spectrum.h:521-526).  One thread per pixel, 28 B in, 4 B out.
-CTL_DEV float to_srgb_component(float v) { return v <= 0.0031308f ? 12.92f * v : 1.055f * powf(v, (float)(1.0 / 2.4)) - 0.055f; }
-CTL_DEV unsigned to_u8(float x) { return (unsigned)(unsigned char)(fminf(fmaxf(x, 0.0f), 1.0f) * 255.0f); }
-__global__ void __launch_bounds__(256) k_resolve_srgb8(const float* __restrict__ accum, int n_pixels, float splat_scale, uchar4* __restrict__ out) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pixels; i += gridDim.x * blockDim.x) {
-        const float* p = accum + (size_t)i * 7;
-        const float ws = __ldg(p + 6), weight = ws != 0.0f ? ws : 1.0f;
-        float c[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) c[k] = to_srgb_component(__ldg(p + k) / weight + __ldg(p + 3 + k) * splat_scale);
-        out[i] = make_uchar4((unsigned char)to_u8(c[0]), (unsigned char)to_u8(c[1]), (unsigned char)to_u8(c[2]), 255);
-    }
-}
-
-// ---- resolve through a reconstruction filter: applyImagePipeline(tracer, img, filter) (ImagePipeline.cu:70-74) =
-// CanonicalFilter::Apply -> rtm_Copy / evalFilter (Kernel/ImagePipeline/Filter/CanonicalFilter.cu:6-36; filters SceneTypes/Filter.h:
-// Box 28-48, Gaussian 50-82, Triangle 151-171) -> Spectrum::toRGBE (Math/Spectrum.h:534-555) -> copyFilteredToOutput: fromRGBE
-// (557-565) -> sRGB -> RGBA8.  filter: 0 box, 1 Gaussian (alpha), 2 triangle.
-struct ResolveFilter { int type; float xw, yw, alpha, expx, expy; };
-CTL_DEV float filter_eval(const ResolveFilter& f, float x, float y) {
-    if (f.type == 0) return 1.0f;
-    if (f.type == 1) return fmaxf(0.0f, expf(-f.alpha * x * x) - f.expx) * fmaxf(0.0f, expf(-f.alpha * y * y) - f.expy);
-    return fmaxf(0.0f, f.xw - fabsf(x)) * fmaxf(0.0f, f.yw - fabsf(y));
-}
-__global__ void __launch_bounds__(256) k_resolve_filtered_srgb8(const float* __restrict__ accum, int w, int h, float splat_scale, const __grid_constant__ ResolveFilter F, uchar4* __restrict__ out) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w * h; i += gridDim.x * blockDim.x) {
-        const int _x = i % w, _y = i / w;
-        const int x0 = max(0, (int)ceilf((float)_x - F.xw)), x1 = min(w - 1, (int)floorf((float)_x + F.xw));
-        const int y0 = max(0, (int)ceilf((float)_y - F.yw)), y1 = min(h - 1, (int)floorf((float)_y + F.yw));
-        float c[3] = {0.0f, 0.0f, 0.0f};
-        if ((x1 - x0) >= 0 && (y1 - y0) >= 0) {
-            float acc[3] = {0.0f, 0.0f, 0.0f}, acc_w = 0.0f;
-            for (int y = y0; y <= y1; ++y)
-                for (int x = x0; x <= x1; ++x) {
-                    const float wt = filter_eval(F, (float)abs(x - _x), (float)abs(y - _y));
-                    const float* p = accum + ((size_t)y * w + x) * 7;
-                    const float ws = __ldg(p + 6), weight = ws != 0.0f ? ws : 1.0f;
-                    for (int k = 0; k < 3; k++) acc[k] += (__ldg(p + k) / weight + __ldg(p + 3 + k) * splat_scale) * wt;
-                    acc_w += wt;
-                }
-            for (int k = 0; k < 3; k++) c[k] = acc[k] / acc_w;
-        }
-        // RGBE round trip (Stage 2 of the reference Image is an RGBE buffer)
-        float mx = fmaxf(c[0], fmaxf(c[1], c[2]));
-        if (mx < 1e-32f) { c[0] = c[1] = c[2] = 0.0f; }
-        else {
-            int e;
-            const float scale = (float)frexp((double)mx, &e) * 256.0f / mx;
-            const float ex = ldexpf(1.0f, (int)(unsigned char)(e + 128) - (128 + 8));
-            for (int k = 0; k < 3; k++) c[k] = (float)(unsigned char)(c[k] * scale) * ex;
-        }
-        out[i] = make_uchar4((unsigned char)to_u8(to_srgb_component(c[0])), (unsigned char)to_u8(to_srgb_component(c[1])), (unsigned char)to_u8(to_srgb_component(c[2])), 255);
-    }
-}
-
 // rays of the pass = sum of extension + shadow queue sizes (every traceRay call counts, TraceHelper.cu:176)
 __global__ void k_tally(const unsigned* q_count, const unsigned* sh_count, int n_bounces, unsigned long long* rays_last, unsigned long long* rays_total) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {

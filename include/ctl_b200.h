@@ -111,6 +111,27 @@ typedef struct ctl_light_tri {
     uint32_t pad;
 } ctl_light_tri;
 
+/* Kernel/PixelVarianceBuffer.h:10-67 (PixelVarianceInfo: prev_I, half_buffer, iterations_done, weight, VarAccumulator<float> I,
+ * num_samples_var); 44 B */
+typedef struct ctl_pixel_variance_info {
+    float prev_I[3];
+    float half_buffer[3];
+    int32_t iterations_done;
+    float weight;
+    float sum_x, sum_x2;
+    int32_t num_samples_var;
+} ctl_pixel_variance_info;
+
+/* applyImagePipeline's two optional stages (Kernel/ImagePipeline/ImagePipeline.h): an ImageSamplesFilter (CanonicalFilter over one of
+ * the five filters of SceneTypes/Filter.h) and a PostProcess (ToneMapPostProcess = Reinhard05). */
+typedef struct ctl_image_pipeline {
+    int32_t filter_type; /* -1 none; 0 BoxFilter, 1 GaussianFilter, 2 TriangleFilter, 3 MitchellFilter, 4 LanczosSincFilter */
+    float x_width, y_width;
+    float param0, param1; /* Gaussian: alpha; Mitchell: B, C; LanczosSinc: tau */
+    int32_t tonemap;     /* 0 none; 1 ToneMapPostProcess (Kernel/ImagePipeline/PostProcess/ToneMapPostProcess.h) */
+    float key, burn;     /* m_key (0.18), m_burn (0) */
+} ctl_image_pipeline;
+
 /* ---- compact records replacing Material / Light ------------------------ */
 
 enum { CTL_BSDF_DIFFUSE = 0, CTL_BSDF_ROUGHCONDUCTOR = 1, CTL_BSDF_DIELECTRIC = 2 };
@@ -281,6 +302,16 @@ int ctl_resolve_srgb8(ctl_ctx*, float splat_scale, void* d_rgba8, void* host_rgb
  * BoxFilter(0.5, 0.5), main.cpp:172): CanonicalFilter reconstruction (Kernel/ImagePipeline/Filter/CanonicalFilter.cu:6-36) into the
  * RGBE stage, then gamma.  filter_type 0 = BoxFilter, 1 = GaussianFilter(alpha), 2 = TriangleFilter (SceneTypes/Filter.h). */
 int ctl_resolve_filtered_srgb8(ctl_ctx*, float splat_scale, int filter_type, float x_width, float y_width, float alpha, void* d_rgba8, void* host_rgba8);
+/* == applyImagePipeline(tracer, img, filter, process) in full (ImagePipeline.cu:54-84): optional CanonicalFilter (Box / Gaussian /
+ * Triangle / Mitchell / LanczosSinc) into the RGBE stage, optional ToneMapPostProcess (Image::ComputeLuminanceInfo, Engine/Image.cu:88-173,
+ * + Reinhard05Kernel, ToneMapPostProcess.cu:6-39) and the gamma stage.  lum_info (may be NULL, filled when tonemap != 0, synchronises):
+ * [0] min [1] max [2] average luminance, [3] log-average luminance, [4] scale, [5] invWp2. */
+int ctl_apply_image_pipeline(ctl_ctx*, float splat_scale, const ctl_image_pipeline*, void* d_rgba8, void* host_rgba8, float lum_info[6]);
+/* == PixelVarianceBuffer (Kernel/PixelVarianceBuffer.h, .cu:10-36; owned by TracerBase, updated after every pass of a progressive tracer,
+ * Kernel/Tracer.h:233-237): "PixelVarianceBuffer"=1 (ctl_set_param_i) makes every single-pass render call (ctl_render_pass with the full
+ * window, ctl_wavefront_pass) run PixelVarianceInfo::updateMoments on all pixels after the pass and clear the buffer on a new trace.
+ * ctl_read_variance copies the w*h records to the host. */
+int ctl_read_variance(ctl_ctx*, ctl_pixel_variance_info* host_out);
 /* Device pointer of the accumulator (7*w*h floats) for in-place NCCL reduce. */
 void* ctl_accum_device_ptr(ctl_ctx*);
 /* Use caller-owned device memory (7*w*h floats) as the accumulator (e.g. a torch tensor). */

@@ -1124,60 +1124,159 @@ long long orc_trace_events(const ctl_scene_view* S, int n, const ctl_traversal_r
     return total;
 }
 
-// Default image pipeline: copySamplesToOutput (Kernel/ImagePipeline/ImagePipeline.cu:14-21) = PixelData::toSpectrum
-// (Engine/Image.h:20-27) -> toSRGBComponent (Math/Spectrum.cu:229-235) -> Float3ToCOLORREF (Math/Spectrum.h:521-526)
-void orc_resolve_srgb8(const ctl_pixel_data* img, int n, float splat_scale, uint8_t* rgba) {
-    for (int i = 0; i < n; i++) {
-        float weight = img[i].weight_sum != 0 ? img[i].weight_sum : 1;
-        for (int k = 0; k < 3; k++) {
-            float v = img[i].rgb[k] / weight + img[i].rgb_splat[k] * splat_scale;
-            float s = v <= (float)0.0031308 ? (float)12.92 * v : (float)1.055 * powf(v, (float)(1.0 / 2.4)) - (float)0.055;
-            float cl = s < 0.0f ? 0.0f : (s > 1.0f ? 1.0f : s); // math::clamp01
-            rgba[4 * i + k] = (unsigned char)(cl * 255.0f);
-        }
-        rgba[4 * i + 3] = 255;
+// ---- image pipeline: applyImagePipeline (Kernel/ImagePipeline/ImagePipeline.cu:54-84) ---------------------------
+// PixelData::toSpectrum (Engine/Image.h:20-27; Spectrum / float multiplies by the reciprocal, Math/Spectrum.h:122-128)
+static inline void px_to_spectrum(const ctl_pixel_data& P, float splat_scale, float c[3]) {
+    const float weight = P.weight_sum != 0 ? P.weight_sum : 1, recip = 1.0f / weight;
+    for (int k = 0; k < 3; k++) c[k] = P.rgb[k] * recip + P.rgb_splat[k] * splat_scale;
+}
+// gammaCorrecture (ImagePipeline.cu:7-12): toSRGBComponent (Math/Spectrum.cu:229-235) -> Float3ToCOLORREF (Math/Spectrum.h:521-526)
+static inline void gamma_to_rgba8(const float c[3], uint8_t* out) {
+    for (int k = 0; k < 3; k++) {
+        float v = c[k], s2 = v <= (float)0.0031308 ? (float)12.92 * v : (float)1.055 * powf(v, (float)(1.0 / 2.4)) - (float)0.055;
+        float cl = s2 < 0.0f ? 0.0f : (s2 > 1.0f ? 1.0f : s2); // math::clamp01
+        out[k] = (unsigned char)(cl * 255.0f);
     }
+    out[3] = 255;
+}
+// Spectrum::toRGBE / fromRGBE (Math/Spectrum.h:534-565)
+static inline void to_rgbe(const float c[3], uint8_t e4[4]) {
+    float mx = std::max(c[0], std::max(c[1], c[2]));
+    if (mx < 1e-32) { e4[0] = e4[1] = e4[2] = e4[3] = 0; return; }
+    int e; float scale = (float)frexp((double)mx, &e) * 256.0f / mx;
+    for (int k = 0; k < 3; k++) e4[k] = (unsigned char)(c[k] * scale);
+    e4[3] = (unsigned char)(e + 128);
+}
+static inline void from_rgbe(const uint8_t e4[4], float c[3]) {
+    if (!e4[3]) { c[0] = c[1] = c[2] = 0; return; }
+    float ex = ldexpf(1.0f, int(e4[3]) - (128 + 8));
+    for (int k = 0; k < 3; k++) c[k] = e4[k] * ex;
+}
+// the five reconstruction filters of SceneTypes/Filter.h (Box :28-48, Gaussian :50-82, Mitchell :84-116, LanczosSinc :118-148, Triangle :151-171)
+struct FilterEval {
+    int type; float xw, yw, p0, p1, ix, iy, expx, expy;
+    FilterEval(const ctl_image_pipeline& P) : type(P.filter_type), xw(P.x_width), yw(P.y_width), p0(P.param0), p1(P.param1), ix(1.f / P.x_width), iy(1.f / P.y_width),
+        expx(expf(-P.param0 * P.x_width * P.x_width)), expy(expf(-P.param0 * P.y_width * P.y_width)) {}
+    float mitchell1d(float x) const {
+        const float B = p0, C = p1;
+        x = fabsf(2.f * x);
+        if (x > 1.f) return ((-B - 6 * C) * x * x * x + (6 * B + 30 * C) * x * x + (-12 * B - 48 * C) * x + (8 * B + 24 * C)) * (1.f / 6.f);
+        return ((12 - 9 * B - 6 * C) * x * x * x + (-18 + 12 * B + 6 * C) * x * x + (6 - 2 * B)) * (1.f / 6.f);
+    }
+    float sinc1d(float x) const {
+        x = fabsf(x);
+        if (x < 1e-5) return 1.f;
+        if (x > 1.) return 0.f;
+        x *= PI_F;
+        float sinc = sinf(x) / x, lanczos = sinf(x * p0) / (x * p0);
+        return sinc * lanczos;
+    }
+    float operator()(float x, float y) const {
+        switch (type) {
+        case 0: return 1.0f;
+        case 1: return fmaxf(0.f, float(expf(-p0 * x * x) - expx)) * fmaxf(0.f, float(expf(-p0 * y * y) - expy));
+        case 2: return fmaxf(0.f, xw - fabsf(x)) * fmaxf(0.f, yw - fabsf(y));
+        case 3: return mitchell1d(x * ix) * mitchell1d(y * iy);
+        default: return sinc1d(x * ix) * sinc1d(y * iy);
+        }
+    }
+};
+// evalFilter (Kernel/ImagePipeline/Filter/CanonicalFilter.cu:6-27)
+static void eval_filter(const FilterEval& F, const ctl_pixel_data* img, float splat_scale, int _x, int _y, int w, int h, float c[3]) {
+    int x0 = std::max(0, (int)ceilf(_x - F.xw)), x1 = std::min(w - 1, (int)floorf(_x + F.xw));
+    int y0 = std::max(0, (int)ceilf(_y - F.yw)), y1 = std::min(h - 1, (int)floorf(_y + F.yw));
+    c[0] = c[1] = c[2] = 0;
+    if ((x1 - x0) < 0 || (y1 - y0) < 0) return;
+    float acc[3] = {0, 0, 0}, accw = 0;
+    for (int y = y0; y <= y1; ++y) for (int x = x0; x <= x1; ++x) {
+        float wt = F((float)abs(x - _x), (float)abs(y - _y));
+        float pc[3]; px_to_spectrum(img[y * w + x], splat_scale, pc);
+        for (int k = 0; k < 3; k++) acc[k] += pc[k] * wt;
+        accw += wt;
+    }
+    const float recip = 1.0f / accw; // Spectrum / float
+    for (int k = 0; k < 3; k++) c[k] = acc[k] * recip;
+}
+// Image::ComputeLuminanceInfo (Engine/Image.cu:88-173) over the RGBE stage.  The reference sums with float atomics (16x16 blocks into shared
+// memory, then into globals): the order is the scheduler's.  Restated in the deterministic order block by block, row-major inside a block.
+// lum: [0] min, [1] max, [2] avg, [3] exp(avg log(2.3e-5 + Y))
+static void luminance_info(const uint8_t* rgbe, int w, int h, float lum[4]) {
+    float mn = FLT_MAX, mx = 0.0f, sum = 0.0f, sumlog = 0.0f;
+    for (int by = 0; by < h; by += 16) for (int bx = 0; bx < w; bx += 16) {
+        float s = 0.0f, sl = 0.0f;
+        for (int y = by; y < std::min(h, by + 16); y++) for (int x = bx; x < std::min(w, bx + 16); x++) {
+            float c[3]; from_rgbe(rgbe + 4 * ((size_t)y * w + x), c);
+            float Y = c[0] * 0.212671f + c[1] * 0.715160f + c[2] * 0.072169f; // Spectrum::getLuminance, Math/Spectrum.cu:174-177
+            mn = std::min(mn, Y); mx = std::max(mx, Y);
+            s += Y; sl += logf(2.3e-5f + Y);
+        }
+        sum += s; sumlog += sl;
+    }
+    lum[0] = mn; lum[1] = mx; lum[2] = sum / (float)(w * h); lum[3] = expf(sumlog / (float)(w * h));
+}
+// Reinhard05Kernel (Kernel/ImagePipeline/PostProcess/ToneMapPostProcess.cu:6-25) with toYxy / fromYxy (Math/Spectrum.cu:286-302), then
+// applyGammaCorrectureToOutput (ImagePipeline.cu:43-52): the processed RGBA8 value is read back, gamma-corrected and quantised again
+static void reinhard_pixel(const uint8_t e4[4], float scale, float invWp2, uint8_t* out) {
+    float c[3]; from_rgbe(e4, c);
+    float X = c[0] * 0.412453f + c[1] * 0.357580f + c[2] * 0.180423f, Y = c[0] * 0.212671f + c[1] * 0.715160f + c[2] * 0.072169f, Z = c[0] * 0.019334f + c[1] * 0.119193f + c[2] * 0.950227f;
+    float sxyz = X + Y + Z; sxyz = sxyz < 0.001f ? 0.001f : (sxyz > 100000.0f ? 100000.0f : sxyz);
+    float x = X / sxyz, y = Y / sxyz;
+    float Lp = scale * Y;
+    Y = Lp * (1.0f + Lp * invWp2) / (1.0f + Lp);
+    float yc = y < 0.001f ? 0.001f : (y > 100000.0f ? 100000.0f : y);
+    X = Y / yc * x; Z = Y / yc * (1 - x - y);
+    float r[3] = {3.240479f * X + -1.537150f * Y + -0.498535f * Z, -0.969256f * X + 1.875991f * Y + 0.041556f * Z, 0.055648f * X + -0.204043f * Y + 1.057311f * Z};
+    uint8_t q[3];
+    for (int k = 0; k < 3; k++) { float cl = r[k] < 0.0f ? 0.0f : (r[k] > 1.0f ? 1.0f : r[k]); q[k] = (unsigned char)(cl * 255.0f); } // toRGBCOL
+    float lin[3] = {float(q[0]) / 255.0f, float(q[1]) / 255.0f, float(q[2]) / 255.0f};                                              // fromRGBCOL
+    gamma_to_rgba8(lin, out);
 }
 
-// applyImagePipeline(tracer, img, filter): CanonicalFilter::Apply / evalFilter (Kernel/ImagePipeline/Filter/CanonicalFilter.cu:6-36),
-// filters of SceneTypes/Filter.h (0 box :28-48, 1 Gaussian :50-82, 2 triangle :151-171), RGBE stage (Math/Spectrum.h:534-565),
-// copyFilteredToOutput (ImagePipeline.cu:32-41)
+void orc_apply_image_pipeline(const ctl_pixel_data* img, int w, int h, float splat_scale, const ctl_image_pipeline* P, uint8_t* rgba, float* lum_out) {
+    const size_t n = (size_t)w * h;
+    if (P->filter_type < 0 && !P->tonemap) { // copySamplesToOutput
+        for (size_t i = 0; i < n; i++) { float c[3]; px_to_spectrum(img[i], splat_scale, c); gamma_to_rgba8(c, rgba + 4 * i); }
+        return;
+    }
+    std::vector<uint8_t> rgbe(4 * n); // Stage 2 of the reference Image: the RGBE buffer
+    if (P->filter_type >= 0) {
+        FilterEval F(*P);
+        for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) { float c[3]; eval_filter(F, img, splat_scale, x, y, w, h, c); to_rgbe(c, &rgbe[4 * ((size_t)y * w + x)]); }
+    } else {
+        for (size_t i = 0; i < n; i++) { float c[3]; px_to_spectrum(img[i], splat_scale, c); to_rgbe(c, &rgbe[4 * i]); } // copySamplesToFiltered
+    }
+    if (!P->tonemap) { // copyFilteredToOutput
+        for (size_t i = 0; i < n; i++) { float c[3]; from_rgbe(&rgbe[4 * i], c); gamma_to_rgba8(c, rgba + 4 * i); }
+        return;
+    }
+    float lum[4]; luminance_info(rgbe.data(), w, h, lum); // ToneMapPostProcess::Apply (ToneMapPostProcess.cu:27-39)
+    const float scale = P->key / lum[3], Lwhite = lum[1] * scale;
+    const float burn = std::min(1.0f, std::max(1e-8f, 1.0f - P->burn));
+    const float invWp2 = 1 / (Lwhite * Lwhite * std::pow(burn, 4.0f));
+    if (lum_out) { memcpy(lum_out, lum, sizeof(lum)); lum_out[4] = scale; lum_out[5] = invWp2; }
+    for (size_t i = 0; i < n; i++) reinhard_pixel(&rgbe[4 * i], scale, invWp2, rgba + 4 * i);
+}
+void orc_resolve_srgb8(const ctl_pixel_data* img, int n, float splat_scale, uint8_t* rgba) {
+    ctl_image_pipeline P; memset(&P, 0, sizeof(P)); P.filter_type = -1;
+    orc_apply_image_pipeline(img, n, 1, splat_scale, &P, rgba, nullptr);
+}
 void orc_resolve_filtered_srgb8(const ctl_pixel_data* img, int w, int h, float splat_scale, int type, float xw, float yw, float alpha, uint8_t* rgba) {
-    const float expx = expf(-alpha * xw * xw), expy = expf(-alpha * yw * yw);
-    auto eval = [&](float x, float y) {
-        if (type == 0) return 1.0f;
-        if (type == 1) return fmaxf(0.f, float(expf(-alpha * x * x) - expx)) * fmaxf(0.f, float(expf(-alpha * y * y) - expy));
-        return fmaxf(0.f, xw - fabsf(x)) * fmaxf(0.f, yw - fabsf(y));
-    };
-    for (int _y = 0; _y < h; _y++) for (int _x = 0; _x < w; _x++) {
-        int x0 = std::max(0, (int)ceilf(_x - xw)), x1 = std::min(w - 1, (int)floorf(_x + xw));
-        int y0 = std::max(0, (int)ceilf(_y - yw)), y1 = std::min(h - 1, (int)floorf(_y + yw));
-        float c[3] = {0, 0, 0};
-        if ((x1 - x0) >= 0 && (y1 - y0) >= 0) {
-            float acc[3] = {0, 0, 0}, accw = 0;
-            for (int y = y0; y <= y1; ++y) for (int x = x0; x <= x1; ++x) {
-                float wt = eval((float)abs(x - _x), (float)abs(y - _y));
-                const ctl_pixel_data& P = img[y * w + x];
-                float weight = P.weight_sum != 0 ? P.weight_sum : 1;
-                for (int k = 0; k < 3; k++) acc[k] += (P.rgb[k] / weight + P.rgb_splat[k] * splat_scale) * wt;
-                accw += wt;
-            }
-            for (int k = 0; k < 3; k++) c[k] = acc[k] / accw;
-        }
-        float mx = std::max(c[0], std::max(c[1], c[2]));
-        if (mx < 1e-32) c[0] = c[1] = c[2] = 0;
-        else {
-            int e; float scale = (float)frexp((double)mx, &e) * 256.0f / mx;
-            unsigned char eb = (unsigned char)(e + 128);
-            float ex = ldexpf(1.0f, int(eb) - (128 + 8));
-            for (int k = 0; k < 3; k++) c[k] = (float)(unsigned char)(c[k] * scale) * ex;
-        }
-        for (int k = 0; k < 3; k++) {
-            float v = c[k], s2 = v <= (float)0.0031308 ? (float)12.92 * v : (float)1.055 * powf(v, (float)(1.0 / 2.4)) - (float)0.055;
-            float cl = s2 < 0.0f ? 0.0f : (s2 > 1.0f ? 1.0f : s2);
-            rgba[4 * (_y * w + _x) + k] = (unsigned char)(cl * 255.0f);
-        }
-        rgba[4 * (_y * w + _x) + 3] = 255;
+    ctl_image_pipeline P; memset(&P, 0, sizeof(P)); P.filter_type = type; P.x_width = xw; P.y_width = yw; P.param0 = alpha;
+    orc_apply_image_pipeline(img, w, h, splat_scale, &P, rgba, nullptr);
+}
+
+// PixelVarianceInfo::updateMoments over the image = PixelVarianceBuffer::AddPass with the uniform block sampler (every block sampled once per
+// pass: samplerPerformed = 1) (Kernel/PixelVarianceBuffer.h:19-42, .cu:10-36)
+void orc_variance_add_pass(ctl_pixel_variance_info* var, const ctl_pixel_data* img, int n, float splat_scale) {
+    for (int i = 0; i < n; i++) {
+        ctl_pixel_variance_info& V = var[i]; const ctl_pixel_data& P = img[i];
+        const float samplerPerformed = 1.0f, recip = 1.0f / samplerPerformed;
+        float est[3];
+        for (int k = 0; k < 3; k++) { float nps = P.rgb[k] + P.rgb_splat[k] * splat_scale; est[k] = (nps - V.prev_I[k]) * recip; V.prev_I[k] = nps; }
+        V.weight = P.weight_sum;
+        if (V.iterations_done++ % 2 == 1) for (int k = 0; k < 3; k++) V.half_buffer[k] += est[k];
+        const float Y = est[0] * 0.212671f + est[1] * 0.715160f + est[2] * 0.072169f;
+        V.sum_x += Y; V.sum_x2 += Y * Y; V.num_samples_var++;
     }
 }
 

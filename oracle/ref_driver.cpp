@@ -70,6 +70,8 @@ CudaStaticWrapper<SamplerData> g_SamplerDataHost;
 
 #include <Integrators/PathTracer_host.inc>   // the reference's PathTrace<DIRECT> (Integrators/PathTracer.cu:1-170)
 #include <SceneTypes/Filter.h>
+#include <Kernel/PixelVarianceBuffer.h>
+#include <Kernel/ImagePipeline/PostProcess/ToneMapPostProcess.h>
 namespace CudaTracerLib {
 #include <Kernel/ImagePipeline/Filter/evalFilter_host.inc>   // the reference's evalFilter (CanonicalFilter.cu:6-27)
 }
@@ -356,6 +358,71 @@ void ref_resolve_filtered_srgb8(const ctl_pixel_data* img, int w, int h, float s
 		RGBCOL o = Spectrum(c2).toRGBCOL();
 		int i = y * w + x;
 		rgba[4 * i] = o.x; rgba[4 * i + 1] = o.y; rgba[4 * i + 2] = o.z; rgba[4 * i + 3] = o.w;
+	}
+}
+
+// applyImagePipeline(tracer, img, filter, process) in full (ImagePipeline.cu:54-84) with the reference's own per-pixel code: evalFilter over the
+// Filter aggregate (all five filters), toRGBE / fromRGBE, getLuminance, toYxy / fromYxy, toRGBCOL / fromRGBCOL, toSRGB.  The two kernels that
+// are CUDA-only text (computeLuminanceInfo's atomics, Reinhard05Kernel's thread indexing) are looped here: block by block, row-major inside a
+// 16x16 block for the luminance sums (the reference's order is the scheduler's).
+void ref_apply_image_pipeline(const ctl_pixel_data* img, int w, int h, float splat_scale, const ctl_image_pipeline* P, unsigned char* rgba, float* lum_out) {
+	std::vector<PixelData> px((size_t)w * h);
+	memcpy((void*)px.data(), img, (size_t)w * h * sizeof(PixelData));
+	auto gamma_out = [&](const Spectrum& c, int i) {
+		Spectrum c2; c.toSRGB(c2[0], c2[1], c2[2]);
+		RGBCOL o = Spectrum(c2).toRGBCOL();
+		rgba[4 * i] = o.x; rgba[4 * i + 1] = o.y; rgba[4 * i + 2] = o.z; rgba[4 * i + 3] = o.w;
+	};
+	if (P->filter_type < 0 && !P->tonemap) { for (int i = 0; i < w * h; i++) gamma_out(px[i].toSpectrum(splat_scale), i); return; }
+	std::vector<RGBE> stage2((size_t)w * h);
+	if (P->filter_type >= 0) {
+		Filter filter;
+		switch (P->filter_type) {
+		case 0: filter.SetData(BoxFilter(P->x_width, P->y_width)); break;
+		case 1: filter.SetData(GaussianFilter(P->x_width, P->y_width, P->param0)); break;
+		case 2: filter.SetData(TriangleFilter(P->x_width, P->y_width)); break;
+		case 3: filter.SetData(MitchellFilter(P->param0, P->param1, P->x_width, P->y_width)); break;
+		default: filter.SetData(LanczosSincFilter(P->x_width, P->y_width, P->param0)); break;
+		}
+		for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) stage2[(size_t)y * w + x] = evalFilter(filter, px.data(), splat_scale, x, y, w, h).toRGBE();
+	} else for (int i = 0; i < w * h; i++) stage2[i] = px[i].toSpectrum(splat_scale).toRGBE();
+	if (!P->tonemap) { for (int i = 0; i < w * h; i++) { Spectrum s; s.fromRGBE(stage2[i]); gamma_out(s, i); } return; }
+	float mn = FLT_MAX, mx = 0.0f, sum = 0.0f, sumlog = 0.0f;
+	for (int by = 0; by < h; by += 16) for (int bx = 0; bx < w; bx += 16) {
+		float sb = 0.0f, sl = 0.0f;
+		for (int y = by; y < std::min(h, by + 16); y++) for (int x = bx; x < std::min(w, bx + 16); x++) {
+			Spectrum L_w; L_w.fromRGBE(stage2[(size_t)y * w + x]);
+			float Y = L_w.getLuminance();
+			mn = std::min(mn, Y); mx = std::max(mx, Y); sb += Y; sl += math::log(2.3e-5f + Y);
+		}
+		sum += sb; sumlog += sl;
+	}
+	float avgLum = sum / (w * h), logAvgLuminance = math::exp(sumlog / (w * h));
+	ToneMapPostProcess tm; tm.m_key = P->key; tm.m_burn = P->burn;
+	float scale = tm.m_key / logAvgLuminance, Lwhite = mx * scale;               // ToneMapPostProcess.cu:33-36
+	auto burn = min(1.0f, max(1e-8f, 1.0f - tm.m_burn));
+	float invWp2 = 1 / (Lwhite * Lwhite * std::pow(burn, 4.0f));
+	if (lum_out) { lum_out[0] = mn; lum_out[1] = mx; lum_out[2] = avgLum; lum_out[3] = logAvgLuminance; lum_out[4] = scale; lum_out[5] = invWp2; }
+	for (int i = 0; i < w * h; i++) {
+		Spectrum color; color.fromRGBE(stage2[i]);                                 // Reinhard05Kernel body, ToneMapPostProcess.cu:11-22
+		float x, y, Y; color.toYxy(Y, x, y);
+		float Lp = scale * Y;
+		Y = Lp * (1.0f + Lp * invWp2) / (1.0f + Lp);
+		color.fromYxy(Y, x, y);
+		RGBCOL processed = color.toRGBCOL();
+		Spectrum s; s.fromRGBCOL(processed);                                       // applyGammaCorrectureToOutput, ImagePipeline.cu:43-52
+		gamma_out(s, i);
+	}
+}
+
+// PixelVarianceBuffer::AddPass with the uniform block sampler (every block flag = 1): the reference's own PixelVarianceInfo::updateMoments
+void ref_variance_add_pass(ctl_pixel_variance_info* var, const ctl_pixel_data* img, int n, float splat_scale) {
+	static_assert(sizeof(PixelVarianceInfo) == sizeof(ctl_pixel_variance_info), "PixelVarianceInfo layout");
+	for (int i = 0; i < n; i++) {
+		PixelVarianceInfo V; memcpy((void*)&V, &var[i], sizeof(V));
+		PixelData pd; memcpy((void*)&pd, &img[i], sizeof(pd));
+		V.updateMoments(pd, splat_scale, 1.0f);
+		memcpy(&var[i], (void*)&V, sizeof(V));
 	}
 }
 

@@ -192,3 +192,15 @@ def render_wavefront(view, w, h, n_passes=1, pass_first=0, max_path_length=8, rr
     rays = np.zeros(1, np.uint64); q = np.zeros((max_path_length, 2), np.uint32)
     oracle().orc_render_wavefront(C.byref(view), w, h, pass_first, n_passes, max_path_length, rr_start, direct, _p(img), _p(rays), _p(q))
     return img, int(rays[0]), q
+
+
+def apply_image_pipeline(img, pipeline, splat_scale=0.0):
+    """applyImagePipeline restatement; returns (rgba8 image, lum info[6])."""
+    img = np.ascontiguousarray(img); h, w = img.shape; out = np.zeros((h, w, 4), np.uint8); lum = np.zeros(6, np.float32)
+    f = oracle().orc_apply_image_pipeline; f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    f(_p(img), w, h, splat_scale, C.byref(pipeline), _p(out), _p(lum)); return out, lum
+
+
+def variance_add_pass(var, img, splat_scale=0.0):
+    f = oracle().orc_variance_add_pass; f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float]
+    f(_p(var), _p(np.ascontiguousarray(img)), img.size, splat_scale); return var

@@ -241,3 +241,28 @@ def test_wavefront_converges_to_pathtracer(orc):
     b, _ = orc.render(s.view, 32, 32, n_passes=64, max_path_length=8)
     ma, mb = a["rgb"].astype(np.float64).mean(axis=(0, 1)) / 64, b["rgb"].astype(np.float64).mean(axis=(0, 1)) / 64
     assert np.allclose(ma, mb, rtol=0.03), (ma, mb)
+
+
+# ---- full image pipeline + variance buffer ----------------------------------------------------------------------
+def test_full_image_pipeline_goldens(orc):
+    """applyImagePipeline with Mitchell / Lanczos-sinc filters, ToneMapPostProcess (Reinhard05) and both: the restatement's bytes and
+    luminance statistics equal those of the reference's own evalFilter / toRGBE / getLuminance / toYxy / fromYxy / toRGBCOL / toSRGB."""
+    from cudatracerlib_b200 import ImagePipeline
+    acc = np.ascontiguousarray(GOLD["pipeline_accum_cornell_80x64_4spp"]).view(api.PIXEL_DTYPE).reshape(64, 80)
+    for k, (ft, xw, yw, p0, p1, tm, key, burn) in enumerate(GOLD["pipeline_full_cases"]):
+        rgba, lum = orc.apply_image_pipeline(acc, ImagePipeline(int(ft), float(xw), float(yw), float(p0), float(p1), int(tm), float(key), float(burn)))
+        assert np.array_equal(rgba, GOLD[f"pipeline_full_{k}"]), k
+        assert np.array_equal(lum.view(np.uint32), GOLD[f"pipeline_full_{k}_lum"].view(np.uint32)), k
+    # the tone mapper must actually change the image, and the burn parameter must matter
+    assert not np.array_equal(GOLD["pipeline_full_3"], GOLD["pipeline_resolve_default"]) and not np.array_equal(GOLD["pipeline_full_3"], GOLD["pipeline_full_4"])
+
+
+def test_pixel_variance_buffer_golden(orc):
+    """PixelVarianceBuffer::AddPass after each of 4 passes: the restatement of updateMoments is bit-identical to the reference's own."""
+    accs = GOLD["variance_accums_cornell_32x24"]
+    var = np.zeros(32 * 24, ctl.VARIANCE_DTYPE)
+    for a in accs:
+        orc.variance_add_pass(var, np.ascontiguousarray(a).view(api.PIXEL_DTYPE).reshape(24, 32))
+    assert np.array_equal(var.view(np.uint32).reshape(-1, 11), GOLD["variance_info_cornell_32x24"])
+    assert (var["iterations_done"] == 4).all() and (var["num_samples_var"] == 4).all() and (var["weight"] == 4).all()
+    assert np.allclose(var["sum_x"], (accs[-1][..., :3].reshape(-1, 3) * [0.212671, 0.715160, 0.072169]).sum(axis=1), rtol=1e-4, atol=1e-6)  # telescoping sum of the per-pass luminances
