@@ -24,6 +24,9 @@
 #                                      -ftrivial-auto-var-init=zero: a failed BSDF sample leaves BSDFSamplingRecord::wo unset (Samples.h:181 initialises only
 #                                      f_i), and WavefrontPathTracer still pushes a ray along it (cu:113,139).  Zero-filling defines that read; nothing else
 #                                      depends on it (PathTrace images are bit-identical with and without the flag).
+#  10. Math/Spectrum.h:549-551       Float3ToRGBE casts a possibly NEGATIVE float (negative filter lobes of Mitchell / Lanczos) to unsigned char: undefined in
+#                                      C++ (x86 wraps modulo 256); the device code the reference ships converts with cvt.rzi.u32.f32 (negative -> 0).
+#                                      The three casts take the device's conversion so that the host build reproduces the GPU's RGBE bytes.
 # oracle/ref_driver.cpp only defines the scene globals and packs ctl_scene_view into KernelDynamicScene.
 set -euo pipefail
 REF=${CTL_REFERENCE:-/root/reference}
@@ -54,6 +57,11 @@ new = """		/* oracle/build_ref.sh patch 2: IEEE decode (== device __half2float) 
 		return (val & 0x8000) ? -v : v;"""
 assert old in s, "half.h host ToFloat not found"
 open(p, "w").write(s.replace(old, new))
+p = "Math/Spectrum.h"; s = open(p).read()
+s2 = re.sub(r"\(unsigned char\)\(c\.([xyz]) \* max_\)", r"CTL_DEVICE_F2U8(c.\1 * max_)", s)
+assert s2.count("CTL_DEVICE_F2U8") == 3, "Float3ToRGBE casts not found (patch 10)"
+s2 = s2.replace("#pragma once", "#pragma once\n/* oracle/build_ref.sh patch 10: float -> unsigned char as the device converts (cvt.rzi.u32.f32 + low byte: negative -> 0) */\n#define CTL_DEVICE_F2U8(v) ((unsigned char)(unsigned int)((v) > 0.0f ? (v) : 0.0f))", 1)
+open(p, "w").write(s2)
 p = "Math/Spectrum.cu"; s = open(p).read()
 s2 = s.replace("ThrowCudaErrors(cudaMemcpyToSymbol(device, &host, sizeof(staticData)));", "/* device-only upload removed (oracle/build_ref.sh patch 3) */")
 assert s2 != s; open(p, "w").write(s2)

@@ -1144,7 +1144,7 @@ static inline void to_rgbe(const float c[3], uint8_t e4[4]) {
     float mx = std::max(c[0], std::max(c[1], c[2]));
     if (mx < 1e-32) { e4[0] = e4[1] = e4[2] = e4[3] = 0; return; }
     int e; float scale = (float)frexp((double)mx, &e) * 256.0f / mx;
-    for (int k = 0; k < 3; k++) e4[k] = (unsigned char)(c[k] * scale);
+    for (int k = 0; k < 3; k++) { const float v = c[k] * scale; e4[k] = (unsigned char)(unsigned int)(v > 0.0f ? v : 0.0f); } // device conversion (cvt.rzi.u32.f32): negative lobes -> 0
     e4[3] = (unsigned char)(e + 128);
 }
 static inline void from_rgbe(const uint8_t e4[4], float c[3]) {
