@@ -116,6 +116,9 @@ def lib():
     L.ctl_scene_create_from_mesh.restype = vp
     L.ctl_scene_create_from_mesh.argtypes = [vp, u32, vp, u32, vp, vp, u32, vp, vp, vp, vp, C.c_float, i32, i32]
     L.ctl_scene_get_view.argtypes = [vp, C.POINTER(SceneView)]
+    L.ctl_scene_create_from_xmsh.restype = vp
+    L.ctl_scene_create_from_xmsh.argtypes = [C.POINTER(C.c_char_p), u32, vp, vp, vp, vp, C.c_float, i32, i32]
+    L.ctl_scene_write_xmsh.argtypes = [vp, u32, C.c_char_p]
     L.ctl_scene_destroy.argtypes = [vp]; L.ctl_scene_destroy.restype = None
     L.ctl_bvh_build_gpu.argtypes = [i32, vp, u32, vp, vp, vp, vp, vp]
     L.ctl_scene_rebuild_bvh_gpu.argtypes = [vp, i32, vp]
@@ -195,6 +198,26 @@ class Scene:
         self.view = SceneView()
         _check(lib().ctl_scene_get_view(self._h, C.byref(self.view)))
         return self
+
+    @classmethod
+    def from_xmsh(cls, paths, cam_pos, cam_target, cam_up, fov_deg, width, height, node_xforms=None):
+        """Flat scene import from the reference's compiled-mesh files (ctl_scene_create_from_xmsh): one mesh + node per file."""
+        self = cls.__new__(cls)
+        paths = [paths] if isinstance(paths, (str, bytes, os.PathLike)) else list(paths)
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+        xf = np.ascontiguousarray(node_xforms, np.float32).reshape(len(paths), 16) if node_xforms is not None else None
+        cp, ct, cu = (np.ascontiguousarray(x, np.float32) for x in (cam_pos, cam_target, cam_up))
+        self._h = lib().ctl_scene_create_from_xmsh(arr, len(paths), _ptr(xf) if xf is not None else None, _ptr(cp), _ptr(ct), _ptr(cu), fov_deg, width, height)
+        if not self._h:
+            raise RuntimeError(lib().ctl_last_error().decode())
+        self.width, self.height = width, height
+        self.view = SceneView()
+        _check(lib().ctl_scene_get_view(self._h, C.byref(self.view)))
+        return self
+
+    def write_xmsh(self, path, mesh=0):
+        """Mesh `mesh` as an .xmsh file (the output sequence of the reference's Mesh::CompileMesh)."""
+        _check(lib().ctl_scene_write_xmsh(self._h, mesh, os.fsencode(path)))
 
     def rebuildBVHOnGPU(self, device=0):
         """Replace every mesh BVH by one built on the GPU (ctl_scene_rebuild_bvh_gpu); returns the device build time in ms."""

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <cstdio>
 #include <cmath>
+#include <stdexcept>
 #include "../../include/ctl_b200.h"
 #include "scene_builder.h"
 #include "sampler_tables.h"
@@ -120,6 +121,33 @@ ctl_scene* ctl_scene_create_from_mesh(const float* verts, uint32_t nv, const uin
                              ctlb::V3(cam_up[0], cam_up[1], cam_up[2]), fov_deg, width, height, s->S);
         return s;
     } catch (const std::exception& e) { set_err(e.what()); return nullptr; }
+}
+// == DynamicScene::CreateNode(compiled mesh file) per file + the camera (Engine/DynamicScene.cpp:283-345; reader Engine/Mesh.cpp:46-98): SURVEY 8 f4
+ctl_scene* ctl_scene_create_from_xmsh(const char* const* paths, uint32_t n_files, const float* node_xforms, const float* cam_pos, const float* cam_target,
+                                      const float* cam_up, float fov_deg, int width, int height) {
+    if (!paths || !n_files || !cam_pos || !cam_target || !cam_up) { set_err("null / empty argument"); return nullptr; }
+    try {
+        std::vector<ctlb::MeshInput> meshes(n_files); std::vector<ctlb::NodeInput> nodes;
+        for (uint32_t i = 0; i < n_files; i++) {
+            if (!paths[i]) throw std::runtime_error("null path");
+            ctlb::read_xmsh(paths[i], meshes[i]);
+            ctlb::M4 xf = ctlb::M4::identity();
+            if (node_xforms) memcpy(xf.m, node_xforms + 16 * (size_t)i, 64);
+            nodes.push_back({i, xf, -1});
+        }
+        ctl_scene* s = new ctl_scene();
+        try {
+            ctlb::assemble_scene(meshes, nodes, ctlb::V3(cam_pos[0], cam_pos[1], cam_pos[2]), ctlb::V3(cam_target[0], cam_target[1], cam_target[2]),
+                                 ctlb::V3(cam_up[0], cam_up[1], cam_up[2]), fov_deg, width, height, s->S);
+        } catch (...) { delete s; throw; }
+        return s;
+    } catch (const std::exception& e) { set_err(e.what()); return nullptr; }
+}
+// == the output sequence of Mesh::CompileMesh (Engine/Mesh.cpp:278-289) for mesh `mesh` of a host scene
+int ctl_scene_write_xmsh(const ctl_scene* s, uint32_t mesh, const char* path) {
+    if (!s || !path) return set_err("null argument");
+    try { ctlb::write_xmsh(path, s->S, mesh); return 0; }
+    catch (const std::exception& e) { return set_err(e.what()); }
 }
 int ctl_scene_get_view(const ctl_scene* s, ctl_scene_view* out) { if (!s || !out) return set_err("null argument"); s->S.fill_view(out); return 0; }
 void ctl_scene_destroy(ctl_scene* s) { delete s; }

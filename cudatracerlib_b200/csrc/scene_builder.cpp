@@ -207,6 +207,20 @@ void assemble_scene(const std::vector<MeshInput>& meshes, const std::vector<Node
     std::vector<Box> mesh_box(meshes.size());
     for (size_t mi = 0; mi < meshes.size(); mi++) {
         const MeshInput& M = meshes[mi];
+        if (!M.pre_tri_data.empty()) { // pre-compiled mesh (.xmsh): reference-layout arrays appended as they are
+            ctl_mesh km;
+            km.tri_offset = (uint32_t)S.tri_data.size(); km.bvh_node_offset = (uint32_t)S.bvh_nodes.size() * 4; km.bvh_tri_offset = (uint32_t)S.woop.size() * 3;
+            km.bvh_idx_offset = (uint32_t)S.tri_index.size(); km.mat_offset = (uint32_t)S.materials.size();
+            for (auto m : M.materials) { m.node_light_index = 0xffffffffu; S.materials.push_back(m); }
+            S.tri_data.insert(S.tri_data.end(), M.pre_tri_data.begin(), M.pre_tri_data.end());
+            S.bvh_nodes.insert(S.bvh_nodes.end(), M.pre_nodes.begin(), M.pre_nodes.end());
+            S.woop.insert(S.woop.end(), M.pre_woop.begin(), M.pre_woop.end());
+            S.tri_index.insert(S.tri_index.end(), M.pre_index.begin(), M.pre_index.end());
+            S.mesh_verts9.emplace_back(); // no source vertices: GPU BVH rebuilds are not available for imported meshes
+            mesh_box[mi] = M.pre_box;
+            S.meshes.push_back(km);
+            continue;
+        }
         uint32_t nt = (uint32_t)M.indices.size() / 3;
         if (M.materials.size() > 255) throw std::runtime_error("more than 255 materials in one mesh (8-bit index, TriangleData.h:24)");
         ctl_mesh km;
@@ -241,6 +255,7 @@ void assemble_scene(const std::vector<MeshInput>& meshes, const std::vector<Node
         }
         S.meshes.push_back(km);
     }
+    S.mesh_boxes = mesh_box;
     // nodes
     std::vector<Box> node_box(nodes.size());
     for (size_t ni = 0; ni < nodes.size(); ni++) {
@@ -286,10 +301,12 @@ void assemble_scene(const std::vector<MeshInput>& meshes, const std::vector<Node
             lt.cdf_offset = (uint32_t)S.light_cdf_data.size();
             lt.node_idx = (uint32_t)ni;
             lt.count = 0;
-            uint32_t nt = (uint32_t)M.indices.size() / 3;
+            const bool pre = !M.pre_tri_data.empty();
+            uint32_t nt = pre ? (uint32_t)M.pre_tri_data.size() : (uint32_t)M.indices.size() / 3;
             M4 xf = nodes[ni].xf;
             for (uint32_t t = 0; t < nt; t++) {
-                if (M.mat_index[t] != m) continue;
+                const uint32_t tm = pre ? ((M.pre_tri_data[t].w[1] >> 16) & 0xffu) : M.mat_index[t]; // TriangleData::getMatIndex, TriangleData.h:40-44
+                if (tm != m) continue;
                 ctl_light_tri lt3; memset(&lt3, 0, sizeof(lt3));
                 // first woop slot referencing this triangle
                 uint32_t slot_end = (nodes[ni].mesh + 1 < S.meshes.size()) ? S.meshes[nodes[ni].mesh + 1].bvh_idx_offset : (uint32_t)S.tri_index.size();

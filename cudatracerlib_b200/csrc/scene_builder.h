@@ -25,7 +25,18 @@ struct MeshInput {
     std::vector<uint8_t> mat_index;  // per triangle, local to the mesh's material block
     std::vector<ctl_material> materials;
     std::vector<V3> emissive;        // per material; non-zero => area light
+    // pre-compiled mesh (.xmsh import, xmsh.cpp): when pre_tri_data is non-empty the arrays below are taken as they are (reference layouts)
+    // instead of being built from verts / indices; mat_index is then derived from the TriangleData words
+    std::vector<ctl_tri_data> pre_tri_data;
+    std::vector<ctl_bvh_node> pre_nodes;
+    std::vector<ctl_woop_tri> pre_woop;
+    std::vector<uint32_t> pre_index;
+    Box pre_box;
 };
+
+// .xmsh (the reference's compiled-mesh format: Engine/Mesh.cpp:46-98 reader, :199-290 writer, Engine/MeshLoader/BVHBuilderHelper.cpp:129-147)
+void read_xmsh(const char* path, MeshInput& out);                                  // throws std::runtime_error
+void write_xmsh(const char* path, const struct SceneStorage& S, uint32_t mesh);    // mesh `mesh` of an assembled scene
 
 struct NodeInput {
     uint32_t mesh;
@@ -39,6 +50,7 @@ struct SceneStorage {
     std::vector<uint32_t> tri_index;
     std::vector<ctl_tri_data> tri_data;
     std::vector<ctl_mesh> meshes;
+    std::vector<Box> mesh_boxes;                   // per mesh: local AABB (Mesh::m_sLocalBox)
     std::vector<std::vector<float>> mesh_verts9;   // per mesh: 9 floats per triangle (for BVH rebuilds, e.g. on the GPU)
     std::vector<ctl_node> nodes;
     std::vector<float> node_xf, node_inv_xf;

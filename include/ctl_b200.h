@@ -214,6 +214,15 @@ ctl_scene* ctl_scene_create_from_mesh(const float* verts, uint32_t nv, const uin
                                       const uint8_t* mat_index, const ctl_material* materials, uint32_t nm,
                                       const float* emissive, const float* cam_pos, const float* cam_target,
                                       const float* cam_up, float fov_deg, int width, int height);
+/* Flat scene import from the reference's compiled-mesh files (.xmsh; format in csrc/xmsh.cpp): one mesh + one node per file, == the static-mesh
+ * branch of DynamicScene::CreateNode (Engine/DynamicScene.cpp:283-345) over Mesh::Mesh(IInStream&) (Engine/Mesh.cpp:46-98).  The file's BVH
+ * nodes / Woop triangles / leaf words / TriangleData are used as they are (reference layouts); its Material blobs are decoded to ctl_material
+ * (diffuse, roughconductor, dielectric with constant textures; anything else fails with a message naming the material); MeshPartLight entries
+ * become area lights.  node_xforms: n_files row-major float4x4 local-to-world matrices, or NULL = identity. */
+ctl_scene* ctl_scene_create_from_xmsh(const char* const* paths, uint32_t n_files, const float* node_xforms, const float* cam_pos,
+                                      const float* cam_target, const float* cam_up, float fov_deg, int width, int height);
+/* Mesh `mesh` of a host scene as an .xmsh file: the output sequence of Mesh::CompileMesh (Engine/Mesh.cpp:278-289). */
+int  ctl_scene_write_xmsh(const ctl_scene*, uint32_t mesh, const char* path);
 int  ctl_scene_get_view(const ctl_scene*, ctl_scene_view* out);
 void ctl_scene_destroy(ctl_scene*);
 /* GPU construction of one mesh BVH in the reference layout (LBVH: Morton codes, hand-written radix sort, Karras radix tree,

@@ -27,6 +27,11 @@
 #  10. Math/Spectrum.h:549-551       Float3ToRGBE casts a possibly NEGATIVE float (negative filter lobes of Mitchell / Lanczos) to unsigned char: undefined in
 #                                      C++ (x86 wraps modulo 256); the device code the reference ships converts with cvt.rzi.u32.f32 (negative -> 0).
 #                                      The three casts take the device's conversion so that the host build reproduces the GPU's RGBE bytes.
+#  11. Engine/Mesh.cpp                lines 151-290 only (Mesh::ComputeVertexNormals, Mesh::CompileMesh = the .xmsh WRITER); the rest of the file
+#                                      (the reader's Stream<> plumbing) needs boost, an empty submodule.  Base/FileStream.cpp, SplitBVHBuilder.cpp and
+#                                      BVHBuilderHelper.cpp compile unpatched.  One line patched: `TriangleData tri;` (Mesh.cpp:232) is zero-filled -- its
+#                                      constructor sets nothing (TriangleData.h:37) and setData reads the UV words, which a mesh without texture
+#                                      coordinates never writes (uninitialised read; zero UVs take setData's determinant == 0 branch).
 # oracle/ref_driver.cpp only defines the scene globals and packs ctl_scene_view into KernelDynamicScene.
 set -euo pipefail
 REF=${CTL_REFERENCE:-/root/reference}
@@ -74,10 +79,13 @@ sed -n '1,170p' Integrators/PathTracer.cu > Integrators/PathTracer_host.inc; ech
 sed -n '11,24p' Integrators/PseudoRealtime/WavefrontPathTracer.h > Integrators/PseudoRealtime/WavefrontPT_payload_host.inc   # struct WavefrontPTRayData
 sed -n '51,164p' Integrators/PseudoRealtime/WavefrontPathTracer.cu > Integrators/PseudoRealtime/WavefrontPT_iterate_host.inc   # pathIterateKernel<NEXT_EVENT_EST>
 grep -q 'struct WavefrontPTRayData' Integrators/PseudoRealtime/WavefrontPT_payload_host.inc && grep -q 'void pathIterateKernel' Integrators/PseudoRealtime/WavefrontPT_iterate_host.inc || { echo "WavefrontPathTracer extraction (patch 8) did not apply"; exit 4; }
+{ echo '#include <Engine/Mesh.h>'; echo '#include <Engine/MeshLoader/BVHBuilderHelper.h>'; echo '#include <Base/FileStream.h>'; echo '#include <Engine/TriangleData.h>'; echo '#include <Engine/Material.h>'; echo '#include <SceneTypes/Light.h>'
+  echo 'namespace CudaTracerLib {'; sed -n '151,290p' Engine/Mesh.cpp | sed 's/^\t\tTriangleData tri;$/\t\tTriangleData tri; memset((void*)\&tri, 0, sizeof(tri)); \/* patch 11 *\//'; echo '}'; } > Engine/Mesh_compile_host.cpp   # the reference's .xmsh writer
+grep -q 'void Mesh::CompileMesh' Engine/Mesh_compile_host.cpp && grep -q 'patch 11' Engine/Mesh_compile_host.cpp || { echo "Mesh.cpp extraction (patch 11) did not apply"; exit 4; }
 sed -n '1,86p' Engine/Image.cu > Engine/Image_host.cu; echo "}" >> Engine/Image_host.cu
 { echo '#include "Image.h"'; echo '#include <Base/CudaMemoryManager.h>'; echo 'namespace CudaTracerLib {'; sed -n '12,30p' Engine/Image.cpp; echo '}'; } > Engine/Image_ctor.cpp
 CXXFLAGS="-std=c++17 -x c++ -include cstring -include cmath -fpermissive -w -O2 -fPIC -ffp-contract=off -pthread -I$SCR -I$CUDA_INC -I$HERE/../include"
-TUS="SceneTypes/BSDF_Simple.cu SceneTypes/BSDF_Complex.cu SceneTypes/Light.cu Engine/ShapeSet.cu Kernel/TraceAlgorithms.cu Engine/KernelDynamicScene.cu Kernel/TraceResult.cu SceneTypes/Sensor.cu Engine/MicrofacetDistribution.cu Base/CudaRandom.cu Engine/TriIntersectorData.cu Engine/DifferentialGeometry.cu SceneTypes/Samples.cu Engine/Material.cu SceneTypes/Volumes.cu SceneTypes/PhaseFunction.cu Math/FresnelHelper.cu Base/Platform.cu SceneTypes/Texture.cu Engine/RoughTransmittance.cu Math/MonteCarlo.cu Engine/TriangleData.cu Math/Spectrum.cu Engine/Image_host.cu Engine/Image_ctor.cpp"
+TUS="SceneTypes/BSDF_Simple.cu SceneTypes/BSDF_Complex.cu SceneTypes/Light.cu Engine/ShapeSet.cu Kernel/TraceAlgorithms.cu Engine/KernelDynamicScene.cu Kernel/TraceResult.cu SceneTypes/Sensor.cu Engine/MicrofacetDistribution.cu Base/CudaRandom.cu Engine/TriIntersectorData.cu Engine/DifferentialGeometry.cu SceneTypes/Samples.cu Engine/Material.cu SceneTypes/Volumes.cu SceneTypes/PhaseFunction.cu Math/FresnelHelper.cu Base/Platform.cu SceneTypes/Texture.cu Engine/RoughTransmittance.cu Math/MonteCarlo.cu Engine/TriangleData.cu Math/Spectrum.cu Engine/Image_host.cu Engine/Image_ctor.cpp Engine/Mesh_compile_host.cpp Base/FileStream.cpp Engine/SpatialStructures/BVH/SplitBVHBuilder.cpp Engine/MeshLoader/BVHBuilderHelper.cpp"
 pids=()
 for f in $TUS; do
   o="obj/$(echo "$f" | tr '/' '_').o"
@@ -88,5 +96,5 @@ done
 for p in "${pids[@]}"; do wait "$p"; done
 g++ $CXXFLAGS -ftrivial-auto-var-init=zero -c "$HERE/ref_driver.cpp" -o obj/ref_driver.o   # note 9
 printf '{ global: ref_*; local: *; };\n' > export.map   # only the ref_* entry points are visible; the CUDA-runtime stubs stay private
-g++ -shared -pthread -o "$OUT/libctl_ref.so" obj/*.o -Wl,-z,defs -Wl,-Bsymbolic -Wl,--version-script=export.map -lm
+g++ -shared -pthread -o "$OUT/libctl_ref.so" obj/*.o -Wl,-z,defs -Wl,-Bsymbolic -Wl,--version-script=export.map -lstdc++fs -lm
 echo "built $OUT/libctl_ref.so"

@@ -70,6 +70,10 @@ CudaStaticWrapper<SamplerData> g_SamplerDataHost;
 
 #include <Integrators/PathTracer_host.inc>   // the reference's PathTrace<DIRECT> (Integrators/PathTracer.cu:1-170)
 #include <SceneTypes/Filter.h>
+#include <SceneTypes/Dispersion.h>
+#include <Engine/Mesh.h>
+#include <Engine/MeshLoader/MeshCompiler.h>
+#include <Base/FileStream.h>
 #include <Kernel/PixelVarianceBuffer.h>
 #include <Kernel/ImagePipeline/PostProcess/ToneMapPostProcess.h>
 namespace CudaTracerLib {
@@ -425,6 +429,41 @@ void ref_variance_add_pass(ctl_pixel_variance_info* var, const ctl_pixel_data* i
 		memcpy(&var[i], (void*)&V, sizeof(V));
 	}
 }
+
+// .xmsh WRITER: the reference's own Mesh::CompileMesh (Engine/Mesh.cpp:199-290: TriangleData encoding, vertex normals, MeshPartLight list,
+// Material blobs, SplitBVHBuilder via ConstructBVH) behind the MeshCompileType token the scene loader expects first (Engine/DynamicScene.cpp:313-319,
+// Engine/MeshLoader/MeshCompiler.cpp:94).  sub_tris[k] = triangles of sub-mesh k (consecutive); materials / emissive per sub-mesh.
+int ref_write_xmsh(const char* path, const float* verts, unsigned nv, const unsigned* indices, unsigned n_indices, const unsigned* sub_tris, unsigned n_sub,
+                   const ctl_material* mats, const float* emissive)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	try {
+		ctl_scene_view v; memset(&v, 0, sizeof(v)); v.materials = mats; v.n_materials = n_sub; v.camera.resolution[0] = v.camera.resolution[1] = 16;
+		v.camera.inv_resolution[0] = v.camera.inv_resolution[1] = 1.0f / 16; for (int i = 0; i < 4; i++) { v.camera.sample_to_camera[i * 5] = 1; v.camera.to_world[i * 5] = 1; }
+		pack_scene(v);   // builds the reference Material objects (g_scene->mats) from the compact records
+		std::vector<Material> M = g_scene->mats; std::vector<Spectrum> Le(n_sub);
+		for (unsigned k = 0; k < n_sub; k++) {
+			M[k].Name = FixedString<64>(format("material_%u", k)); M[k].NodeLightIndex = UINT_MAX;
+			Le[k] = emissive ? Spectrum(emissive[3 * k], emissive[3 * k + 1], emissive[3 * k + 2]) : Spectrum(0.0f);
+		}
+		FileOutputStream out(path);
+		out << (unsigned int)MeshCompileType::Static;
+		Mesh::CompileMesh((const Vec3f*)verts, nv, 0, 0, 0, indices, n_indices, M.data(), Le.data(), sub_tris, 0, out, false, false, 0.0f);
+		out.Close();
+	} catch (const std::exception& e) { fprintf(stderr, "ref_write_xmsh: %s\n", e.what()); return 1; }
+	return 0;
+}
+
+// layout facts the product's .xmsh reader hard-codes (cudatracerlib_b200/csrc/xmsh.cpp), checked against the reference headers
+static_assert(sizeof(Material) == 3344 && offsetof(Material, NodeLightIndex) == 68 && offsetof(Material, bsdf) == 512 && sizeof(FixedString<64>) == 68, "Material layout");
+static_assert(sizeof(MeshPartLight) == 48 && offsetof(MeshPartLight, L) == 36 && sizeof(Texture) == 208 && sizeof(AABB) == 24 && sizeof(BSDF) == 56, "xmsh record layout");
+static_assert(offsetof(BSDF, m_enableTwoSided) == 52 && offsetof(diffuse, m_reflectance) == 64 && offsetof(ConstantTexture, val) == 8, "BSDF layout");
+static_assert(offsetof(roughconductor, m_specularReflectance) == 64 && offsetof(roughconductor, m_alphaU) == 272 && offsetof(roughconductor, m_alphaV) == 480 &&
+              offsetof(roughconductor, m_eta) == 688 && offsetof(roughconductor, m_k) == 700 && offsetof(roughconductor, m_type) == 716, "roughconductor layout");
+static_assert(offsetof(dielectric, eta_f) == 64 && offsetof(dielectric, m_specularTransmittance) == 128 && offsetof(dielectric, m_specularReflectance) == 336 &&
+              offsetof(DispersionCauchy, B) == 8 && offsetof(DispersionCauchy, C) == 12 && sizeof(Dispersion) == 64, "dielectric layout");
+static_assert(diffuse::TYPE() == 1 && dielectric::TYPE() == 3 && roughconductor::TYPE() == 7 && ConstantTexture::TYPE() == 2 && DispersionCauchy::TYPE() == 1 &&
+              (unsigned)MeshCompileType::Static == 0, "type tags");
 
 // Known-answer probes of the reference's own math (regenerates SURVEY Appendix C)
 void ref_xorwow_floats(unsigned int seed_subsequence, int n, float* out) { CudaRNG rng(seed_subsequence); for (int i = 0; i < n; i++) out[i] = rng.randomFloat(); }

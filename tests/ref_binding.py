@@ -105,3 +105,16 @@ def apply_image_pipeline(img, pipeline, splat_scale=0.0):
 def variance_add_pass(var, img, splat_scale=0.0):
     f = ref().ref_variance_add_pass; f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float]
     f(_p(var), _p(np.ascontiguousarray(img)), img.size, splat_scale); return var
+
+
+def write_xmsh(path, verts, indices, sub_tris, mats, emissive=None):
+    """The reference's own .xmsh writer (Mesh::CompileMesh): verts (nv, 3) f32, indices (3 * nt) u32 with the triangles of sub-mesh k
+    consecutive, sub_tris[k] triangles each, mats = list of Material (one per sub-mesh), emissive (n_sub, 3) or None."""
+    from cudatracerlib_b200 import Material
+    v = np.ascontiguousarray(verts, np.float32); i = np.ascontiguousarray(indices, np.uint32); st = np.ascontiguousarray(sub_tris, np.uint32)
+    arr = (Material * len(mats))(*mats)
+    e = np.ascontiguousarray(emissive, np.float32) if emissive is not None else None
+    f = ref().ref_write_xmsh; f.argtypes = [C.c_char_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p]
+    rc = f(str(path).encode(), _p(v), len(v), _p(i), len(i), _p(st), len(st), C.cast(arr, C.c_void_p), _p(e) if e is not None else None)
+    if rc:
+        raise RuntimeError("ref_write_xmsh failed")

@@ -11,9 +11,18 @@ def _mat(bsdf=0, refl=(0.7, 0.7, 0.7), two_sided=False, distr=0, alpha=0.2, eta=
     return m
 
 
+TWO_LIGHT_CAMERA = ((0, 0, -0.95), (0, -0.1, 0.5), (0, 1, 0), 80.0)
+
+
 def two_light_room(w, h):
     """Closed box [-1,1]^3 with TWO area lights of different radiance and size (exercises the light-selection CDF,
     pdfEmitter and per-light area CDFs), a two-sided diffuse quad floating in the middle, a GGX conductor block."""
+    V, I, M, mats, emissive = two_light_room_arrays()
+    return ctl.Scene.from_mesh(V, I, M, mats, emissive, *TWO_LIGHT_CAMERA, w, h)
+
+
+def two_light_room_arrays():
+    """(verts (nv, 3) f32, indices (3 nt) u32, material index per triangle u8, materials, emissive (nm, 3))."""
     V, I, M = [], [], []
 
     def quad(a, b, c, d, mat):
@@ -38,5 +47,4 @@ def two_light_room(w, h):
     mats = [_mat(refl=(0.73, 0.73, 0.73)), _mat(refl=(0.63, 0.065, 0.05)), _mat(refl=(0.14, 0.45, 0.091)), _mat(refl=(0.78, 0.78, 0.78)), _mat(refl=(0.78, 0.78, 0.78)),
             _mat(refl=(0.3, 0.4, 0.8), two_sided=True), _mat(bsdf=1, distr=1, alpha=0.25, refl=(1, 1, 1), eta=(0.2, 0.924, 1.102), k=(3.912, 2.452, 2.142))]
     emissive = np.zeros((7, 3), np.float32); emissive[3] = (30, 26, 20); emissive[4] = (2, 3, 5)
-    return ctl.Scene.from_mesh(np.array(V, np.float32), np.array(I, np.uint32).ravel(), np.array(M, np.uint8), mats, emissive,
-                               (0, 0, -0.95), (0, -0.1, 0.5), (0, 1, 0), 80.0, w, h)
+    return np.array(V, np.float32), np.array(I, np.uint32).ravel(), np.array(M, np.uint8), mats, emissive

@@ -1,0 +1,39 @@
+"""GPU side of the .xmsh import: a scene read from the file the reference's own writer produced (its SplitBVHBuilder tree,
+its TriangleData, its Material blobs) renders through the CUDA path like the oracle and like the reference's own PathTrace."""
+import os
+
+import numpy as np
+import pytest
+
+import cudatracerlib_b200 as ctl
+from cudatracerlib_b200 import api
+from scene_fixtures import TWO_LIGHT_CAMERA
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+XMSH = os.path.join(HERE, "golden", "two_light_room.xmsh")
+GOLD = np.load(os.path.join(HERE, "golden", "reference_golden.npz"))
+
+
+def rel_l2(a, b):
+    return np.linalg.norm(a - b, axis=-1) / (np.linalg.norm(b, axis=-1) + 1e-3)
+
+
+def test_imported_scene_on_gpu(built_lib, orc):
+    s = ctl.Scene.from_xmsh(XMSH, *TWO_LIGHT_CAMERA, 64, 64)
+    t = ctl.PathTracer(64, 64); t.InitializeScene(s); t.setParameter("MaxPathLength", 6)
+    rng = np.random.default_rng(11)
+    rays = np.zeros(8192, api.RAY_DTYPE); rays["o"] = rng.uniform(-0.99, 0.99, (8192, 3)); d = rng.normal(size=(8192, 3)); rays["d"] = d / np.linalg.norm(d, axis=1, keepdims=True); rays["tmax"] = 3e38
+    g, gc = t.trace_rays(rays, counts=True); o, oc = orc.trace_rays(s.view, rays, counts=True)
+    assert np.array_equal(g["tri_idx"], o["tri_idx"]) and np.array_equal(g["dist"].view(np.uint32), o["dist"].view(np.uint32)) and gc == oc   # the reference's SBVH, bit-exact
+    t.DoPass(True); t.DoPass(False)
+    img = t.readAccumulator()
+    ref = np.ascontiguousarray(GOLD["xmsh_two_light_image_64x64_2spp"]).view(api.PIXEL_DTYPE).reshape(64, 64)   # the reference's PathTrace on its own file
+    assert (rel_l2(img["rgb"], ref["rgb"]) <= 1e-3).mean() >= 0.99 and np.array_equal(img["weight_sum"], ref["weight_sum"])
+    orc_img, _ = orc.render(s.view, 64, 64, n_passes=2, max_path_length=6)
+    assert (rel_l2(img["rgb"], orc_img["rgb"]) <= 1e-3).mean() >= 0.99
+    w = ctl.WavefrontPathTracer(64, 64); w.InitializeScene(s); w.setParameter("MaxPathLength", 6)
+    w.DoPass(True)
+    wref, wrays, _ = orc.render_wavefront(s.view, 64, 64, n_passes=1, max_path_length=6)
+    assert (rel_l2(w.readAccumulator()["rgb"], wref["rgb"]) <= 1e-3).mean() >= 0.99 and w.getRaysInLastPass() == wrays
+    t.close(); w.close()

@@ -1,0 +1,118 @@
+"""`.xmsh` import / export, CPU side.  tests/golden/two_light_room.xmsh was written by the reference's OWN writer
+(Mesh::CompileMesh + SplitBVHBuilder, compiled into oracle/_ref; tests/golden/make_golden.py); the product's reader must turn it into a
+scene view that renders exactly like the scene built from the same triangles here."""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import cudatracerlib_b200 as ctl
+from cudatracerlib_b200 import api
+from scene_fixtures import two_light_room, two_light_room_arrays, TWO_LIGHT_CAMERA
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+XMSH = os.path.join(HERE, "golden", "two_light_room.xmsh")
+GOLD = np.load(os.path.join(HERE, "golden", "reference_golden.npz"))
+
+
+def _materials(s):
+    raw = bytes((C.c_char * (64 * s.view.n_materials)).from_address(C.addressof(s.view.materials.contents)))
+    return [struct.unpack("4I12f", raw[64 * i:64 * i + 64]) for i in range(s.view.n_materials)]
+
+
+def _relevant(m):
+    """fields of ctl_material the BSDF of that type reads"""
+    t = m[0]
+    if t == 0:
+        return (t, m[1], m[2], m[4:7])
+    if t == 1:
+        return (t, m[1], m[2], m[3], m[4:8], m[8:11], m[11], m[12:15])
+    return (t, m[1], m[2], m[4:7], m[8], m[15])
+
+
+def _grouped_scene(w, h):
+    V, I, M, mats, emissive = two_light_room_arrays()
+    order = np.argsort(M, kind="stable")
+    return ctl.Scene.from_mesh(V, I.reshape(-1, 3)[order].ravel(), M[order], mats, emissive, *TWO_LIGHT_CAMERA, w, h)
+
+
+def test_reader_reproduces_the_scene(built_lib, orc):
+    s1 = ctl.Scene.from_xmsh(XMSH, *TWO_LIGHT_CAMERA, 64, 64)
+    s2 = _grouped_scene(64, 64)
+    assert s1.n_triangles == s2.n_triangles == 26 and s1.view.n_materials == 7 and s1.view.num_lights == 2 and s1.view.n_nodes == 1
+    # TriangleData written by the reference's Mesh::CompileMesh (vertex normals, dpdu/dpdv, material index) == this repo's encoder, bit for bit
+    assert np.array_equal(s1.array("tri_data"), s2.array("tri_data"))
+    assert [_relevant(m) for m in _materials(s1)] == [_relevant(m) for m in _materials(s2)]
+    assert list(s1.view.box_min) == list(s2.view.box_min) and list(s1.view.box_max) == list(s2.view.box_max) and s1.view.ray_eps == s2.view.ray_eps
+    for name in ("light_tris", "light_cdf_data"):   # ShapeSets of the two area lights: same triangles; Woop slots differ with the BVH
+        a, b = s1.array(name), s2.array(name)
+        assert a.shape == b.shape and np.allclose(a[:, :13], b[:, :13], rtol=1e-5, atol=1e-6) if name == "light_tris" else np.array_equal(a, b)
+    # the reference's SBVH: every triangle referenced, leaves of <= 8, sentinel-terminated leaves
+    idx = s1.array("tri_index").ravel()
+    assert set((idx >> 1).tolist()) == set(range(26)) and s1.view.n_woop == len(idx) >= 26
+    run = 0
+    for wd in idx:
+        run += 1
+        if wd & 1:
+            assert run <= 8; run = 0
+    assert run == 0
+    # same closest hits and the same images with the reference's tree and with ours
+    rng = np.random.default_rng(3)
+    rays = np.zeros(4000, api.RAY_DTYPE); rays["o"] = rng.uniform(-0.99, 0.99, (4000, 3)); d = rng.normal(size=(4000, 3)); rays["d"] = d / np.linalg.norm(d, axis=1, keepdims=True); rays["tmax"] = 3e38
+    h1, h2 = orc.trace_rays(s1.view, rays), orc.trace_rays(s2.view, rays)
+    assert np.array_equal(h1["tri_idx"], h2["tri_idx"]) and np.array_equal(h1["dist"].view(np.uint32), h2["dist"].view(np.uint32))
+    a, ra = orc.render(s1.view, 64, 64, n_passes=2, max_path_length=6)
+    b, rb_ = orc.render(s2.view, 64, 64, n_passes=2, max_path_length=6)
+    assert np.array_equal(a["rgb"].view(np.uint32), b["rgb"].view(np.uint32)) and ra == rb_
+
+
+def test_imported_scene_vs_reference_image(built_lib, orc):
+    """The reference's own PathTrace on the scene imported from its own file (golden) == the host-arithmetic oracle, bit for bit."""
+    s = ctl.Scene.from_xmsh(XMSH, *TWO_LIGHT_CAMERA, 64, 64)
+    ref = np.ascontiguousarray(GOLD["xmsh_two_light_image_64x64_2spp"]).view(api.PIXEL_DTYPE).reshape(64, 64)
+    with orc.host_arithmetic():
+        img, rays = orc.render(s.view, 64, 64, n_passes=2, max_path_length=6)
+    assert np.array_equal(img["rgb"].view(np.uint32), ref["rgb"].view(np.uint32)) and rays <= int(GOLD["xmsh_two_light_rays"][0])
+
+
+def test_writer_round_trip_and_multi_file_import(built_lib, orc, tmp_path):
+    s2 = two_light_room(32, 32)
+    p = tmp_path / "rt.xmsh"
+    s2.write_xmsh(p)
+    s3 = ctl.Scene.from_xmsh(p, *TWO_LIGHT_CAMERA, 32, 32)
+    for name in ("bvh_nodes", "woop", "tri_index", "tri_data", "light_tris", "light_cdf_data", "meshes", "nodes"):
+        assert np.array_equal(s3.array(name).view(np.uint32), s2.array(name).view(np.uint32)), name
+    assert [_relevant(m) for m in _materials(s3)] == [_relevant(m) for m in _materials(s2)]
+    # same header layout as the reference-written file
+    a, b = open(XMSH, "rb").read(64), open(p, "rb").read(64)
+    assert a[:4] == b[:4] == bytes(4) and a[4:28] == b[4:28] and a[28:32] == b[28:32] == struct.pack("I", 2)
+    # two instances of the file with different transforms: two nodes, a real scene-level BVH, lights of both
+    xf = np.stack([np.eye(4, dtype=np.float32), np.eye(4, dtype=np.float32)]); xf[1, 0, 3] = 2.5; xf[1, 1, 1] = 0.5
+    s4 = ctl.Scene.from_xmsh([XMSH, p], (1.2, 0, -4.0), (1.2, 0, 0), (0, 1, 0), 60.0, 48, 32, node_xforms=xf)
+    assert s4.view.n_nodes == 2 and s4.view.n_meshes == 2 and s4.view.num_lights == 4 and s4.view.scene_start_node == 0
+    img, rays = orc.render(s4.view, 48, 32, n_passes=1, max_path_length=4)
+    assert (img["weight_sum"] == 1).all() and img["rgb"].mean() > 0 and rays > 48 * 32
+
+
+def test_reader_error_paths(built_lib, tmp_path):
+    good = open(XMSH, "rb").read()
+    def expect(data, text):
+        p = tmp_path / "bad.xmsh"; p.write_bytes(data)
+        with pytest.raises(RuntimeError, match=text):
+            ctl.Scene.from_xmsh(p, *TWO_LIGHT_CAMERA, 16, 16)
+    with pytest.raises(RuntimeError, match="Could not open file"):
+        ctl.Scene.from_xmsh(tmp_path / "missing.xmsh", *TWO_LIGHT_CAMERA, 16, 16)
+    expect(good[:1000], "Passed end of file")
+    expect(struct.pack("I", 7) + good[4:], "Mesh file parser error")
+    expect(struct.pack("I", 1) + good[4:], "animated meshes")
+    expect(b"", "Passed end of file")
+    # first material blob starts after: token, box, light count, 2 lights, triangle count, 26 triangles, material count
+    m0 = 4 + 24 + 4 + 2 * 48 + 4 + 26 * 32 + 4
+    bad = bytearray(good); bad[m0 + 512:m0 + 516] = struct.pack("I", 9)          # roughplastic
+    expect(bytes(bad), "BSDF type 9 is not supported")
+    bad = bytearray(good); bad[m0 + 528 + 64:m0 + 528 + 68] = struct.pack("I", 3)   # ImageTexture as the diffuse reflectance
+    expect(bytes(bad), "not a ConstantTexture")
+    bad = bytearray(good); bad[4 + 24 + 4 + 4:4 + 24 + 4 + 4 + 10] = b"nosuchmat" + bytes(1)
+    expect(bytes(bad), "unknown material")
