@@ -149,6 +149,16 @@ int ctl_scene_write_xmsh(const ctl_scene* s, uint32_t mesh, const char* path) {
     try { ctlb::write_xmsh(path, s->S, mesh); return 0; }
     catch (const std::exception& e) { return set_err(e.what()); }
 }
+// Source triangles of mesh `mesh` (9 floats each, TriangleData order) for export / rebuild tooling; *n_tris receives the count (verts9_out may be NULL to size).
+int ctl_scene_get_mesh_triangles(const ctl_scene* s, uint32_t mesh, float* verts9_out, uint32_t* n_tris) {
+    if (!s || !n_tris) return set_err("null argument");
+    if (mesh >= s->S.mesh_verts9.size()) return set_err("no such mesh");
+    const std::vector<float>& v = s->S.mesh_verts9[mesh];
+    if (v.empty()) return set_err("mesh has no source triangles (imported from a compiled file)");
+    *n_tris = (uint32_t)(v.size() / 9);
+    if (verts9_out) memcpy(verts9_out, v.data(), v.size() * sizeof(float));
+    return 0;
+}
 int ctl_scene_get_view(const ctl_scene* s, ctl_scene_view* out) { if (!s || !out) return set_err("null argument"); s->S.fill_view(out); return 0; }
 void ctl_scene_destroy(ctl_scene* s) { delete s; }
 void ctl_encode_woop(const float v0[3], const float v1[3], const float v2[3], ctl_woop_tri* out) {
@@ -704,13 +714,21 @@ int ctl_wavefront_pass(ctl_ctx* c, int new_trace) {
     launches += 2;
     for (int d = 0; d < mpl; d++) {
         stage_mark(c, 1);
-        launch_intersect<2, false, false>(c, g_trav, c->stream, c->scene, (const float4*)c->w_ray.p, ctr + CTR_Q + d, 0, ctr + CTR_WORK + 2 * d, nullptr, nullptr, nullptr, nullptr, (void*)c->w_res.p, nullptr);
-        launches++;
-        if (d > 0 && c->direct) { // closest-hit queries for the secondary rays pushed by iteration d-1 (FinishIteration, DoubleRayBuffer.h:84-112)
-            stage_mark(c, 3);
-            launch_intersect<2, false, false>(c, g_trav, c->stream, c->scene, (const float4*)c->w_sec[(d - 1) & 1].p, ctr + CTR_SH + d - 1, 0, ctr + CTR_WORK + 2 * d + 1, nullptr, nullptr, nullptr, nullptr,
-                                              (void*)c->w_sres[(d - 1) & 1].p, nullptr);
+        // FinishIteration (DoubleRayBuffer.h:84-112): the primaries and the secondary rays pushed by iteration d-1
+        const bool have_sec = d > 0 && c->direct;
+        if (have_sec && c->fuse_traversal && c->trav_kernel == 0) {
+            k_intersect_fused_api<<<g_trav, 128, 0, c->stream>>>(c->scene, c->tune, (const float4*)c->w_ray.p, ctr + CTR_Q + d, (const float4*)c->w_sec[(d - 1) & 1].p, ctr + CTR_SH + d - 1,
+                                                                  ctr + CTR_WORK + 2 * d, (void*)c->w_res.p, (void*)c->w_sres[(d - 1) & 1].p);
             launches++;
+        } else {
+            launch_intersect<2, false, false>(c, g_trav, c->stream, c->scene, (const float4*)c->w_ray.p, ctr + CTR_Q + d, 0, ctr + CTR_WORK + 2 * d, nullptr, nullptr, nullptr, nullptr, (void*)c->w_res.p, nullptr);
+            launches++;
+            if (have_sec) {
+                stage_mark(c, 3);
+                launch_intersect<2, true, false>(c, g_trav, c->stream, c->scene, (const float4*)c->w_sec[(d - 1) & 1].p, ctr + CTR_SH + d - 1, 0, ctr + CTR_WORK + 2 * d + 1, nullptr, nullptr, nullptr, nullptr,
+                                                 (void*)c->w_sres[(d - 1) & 1].p, nullptr);
+                launches++;
+            }
         }
         stage_mark(c, 2);
         B.sec_out = c->w_sec[d & 1].p; B.sec_res = c->w_sres[(d - 1) & 1].p;

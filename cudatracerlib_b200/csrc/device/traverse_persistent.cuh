@@ -26,6 +26,9 @@ struct TravOut { // where results go (MODE-dependent, see k_intersect)
     // MODE 4 (fused launch): work items [0, n_ext) are extension rays (closest hit, results as MODE 0) taken from `rays`,
     // items [n_ext, n) are shadow rays (any hit, results as MODE 1) taken from `sh_rays`
     const float4* sh_rays; int n_ext;
+    // MODE 5 (fused API launch, WavefrontPathTracer): items [0, n_ext) are closest-hit queries from `rays` -> api_out, items [n_ext, n) are
+    // any-hit queries from `sh_rays` -> api_out2; both with intersectKernel semantics (MODE 2: tmin / tmax from the ray, 16-byte results)
+    void* api_out2;
 };
 
 struct TravTune { int th_t, th_l, th_f, th_n_exit; }; // lane thresholds of the T / L / F blocks; th_n_exit = node steps per iteration
@@ -93,14 +96,14 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, const float4* 
                         c.x = c.x + pl.x; c.y = c.y + pl.y; c.z = c.z + pl.z;
                         out.cl[p] = c;
                     }
-                } else if (MODE == 2) {
+                } else if (MODE == 2 || MODE == 5) {
                     uint4 res = make_uint4(__float_as_uint(hit.dist), 0xffffffffu, 0xffffffffu, 0u);
                     if (hit.tri != 0xffffffffu) {
                         res.y = hit.node; res.z = hit.tri;
                         const unsigned short xd = (unsigned short)(hit.u * 65535), yd = (unsigned short)(hit.v * 65535); // TraceHelper.cu:726-727
                         res.w = ((uint32_t)yd << 16) | (uint32_t)xd;
                     }
-                    ((uint4*)out.api_out)[i] = res;
+                    ((uint4*)((MODE == 5 && lane_any) ? out.api_out2 : out.api_out))[i] = res;
                 } else {
                     float* o5 = (float*)out.api_out + (size_t)i * 5;
                     o5[0] = hit.dist; o5[1] = hit.u; o5[2] = hit.v; o5[3] = __uint_as_float(hit.tri); o5[4] = __uint_as_float(hit.node);
@@ -125,13 +128,13 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, const float4* 
                     const int r = my_rank - got_before;
                     if (is_free && r >= 0 && r < take) {
                         int i = pool_next + r;
-                        if (MODE == 4) { lane_any = i >= out.n_ext; my_rays = lane_any ? out.sh_rays : rays; if (lane_any) i -= out.n_ext; }
+                        if (MODE == 4 || MODE == 5) { lane_any = i >= out.n_ext; my_rays = lane_any ? out.sh_rays : rays; if (lane_any) i -= out.n_ext; }
                         const float4 ro = ldg_stream(my_rays + 2 * i), rd = ldg_stream(my_rays + 2 * i + 1);
                         ray_i = i;
                         ox = ro.x; oy = ro.y; oz = ro.z; dx = rd.x; dy = rd.y; dz = rd.z;
                         hit.u = hit.v = 0.0f; hit.tri = 0xffffffffu; hit.node = 0xffffffffu;
                         if (MODE == 3) { tri_lo = S.ray_eps; box_lo = 0.0f; hit.dist = FLT_MAX; }
-                        else if (MODE == 2) { tri_lo = ro.w; box_lo = ro.w; hit.dist = rd.w; }
+                        else if (MODE == 2 || MODE == 5) { tri_lo = ro.w; box_lo = ro.w; hit.dist = rd.w; }
                         else { tri_lo = ro.w; box_lo = 0.0f; hit.dist = rd.w; }
                         sp = 0; stack[0] = SENT;
                         inst = -1; nbase = S.scene_nodes;
@@ -221,7 +224,7 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, const float4* 
                 bool done = false;
                 if (woop_test(v00, v11, v22, mk(ox, oy, oz), mk(dx, dy, dz), tri_lo, hit.dist, t, u, v)) {
                     hit.node = (uint32_t)inst; hit.tri = (index >> 1) + tri_base; hit.u = u; hit.v = v; hit.dist = t;
-                    if (MODE == 4 ? lane_any : ANY_HIT) { done = true; nodeAddr = SENT; inst = -1; } // first hit terminates the ray (TraceHelper.cu:675-679)
+                    if ((MODE == 4 || MODE == 5) ? lane_any : ANY_HIT) { done = true; nodeAddr = SENT; inst = -1; } // first hit terminates the ray (TraceHelper.cu:675-679)
                 }
                 if (!done) {
                     if (index & 1) { nodeAddr = stack[sp]; sp--; if (nodeAddr < 0) triAddr = ~nodeAddr; }

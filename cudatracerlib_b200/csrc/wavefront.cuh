@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(128, CTL_TRAV_MIN_BLOCKS) k_intersect(const __
                                                     void* __restrict__ api_out, unsigned long long* visit_out) {
     const int n = n_ptr ? (int)*n_ptr : n_fixed;
     VisitCounters<COUNT> cnt;
-    TravOut out = {hit_a, hit_node, sh_payload, cl, api_out, nullptr, 0};
+    TravOut out = {hit_a, hit_node, sh_payload, cl, api_out, nullptr, 0, nullptr};
     trace_persistent<MODE, ANY_HIT, COUNT>(S, rays, n, work_ctr, out, tune, cnt);
     if (COUNT) {
         VisitCounters<true>& c = (VisitCounters<true>&)cnt;
@@ -264,8 +264,19 @@ __global__ void __launch_bounds__(128, 8) k_intersect_fused(const __grid_constan
         unsigned* work_ctr, float4* __restrict__ hit_a, uint32_t* __restrict__ hit_node, const float4* __restrict__ sh_payload, float4* __restrict__ cl) {
     const int n_ext = (int)*n_ext_ptr, n_sh = (int)*n_sh_ptr;
     VisitCounters<false> cnt;
-    TravOut out = {hit_a, hit_node, sh_payload, cl, nullptr, sh_rays, n_ext};
+    TravOut out = {hit_a, hit_node, sh_payload, cl, nullptr, sh_rays, n_ext, nullptr};
     trace_persistent<4, false, false>(S, ext_rays, n_ext + n_sh, work_ctr, out, tune, cnt);
+}
+
+// Fused API launch (WavefrontPathTracer's FinishIteration): the primary queue (closest hit) and the secondary queue (any hit against the
+// ray's own tmax) of one iteration share one persistent kernel; 16-byte traversalResult records into two result buffers.
+__global__ void __launch_bounds__(128, 8) k_intersect_fused_api(const __grid_constant__ DScene S, const __grid_constant__ TravTune tune,
+        const float4* __restrict__ rays, const unsigned* __restrict__ n_ptr, const float4* __restrict__ sec_rays, const unsigned* __restrict__ n_sec_ptr,
+        unsigned* work_ctr, void* __restrict__ res, void* __restrict__ sec_res) {
+    const int n_ext = (int)*n_ptr, n_sec = (int)*n_sec_ptr;
+    VisitCounters<false> cnt;
+    TravOut out = {nullptr, nullptr, nullptr, nullptr, res, sec_rays, n_ext, sec_res};
+    trace_persistent<5, false, false>(S, rays, n_ext + n_sec, work_ctr, out, tune, cnt);
 }
 
 // ---- material sort before shading (SortMode 2) ----------------------------------------------------------------------

@@ -13,7 +13,7 @@
 //
 // Quirks of the reference kept on purpose (oracle/oracle.cpp orc_render_wavefront): sampler keyed by queue slot and re-skipped to
 // dimension passesDone + 2 at every bounce; Russian roulette before the BSDF sample from pathDepth >= RRStartDepth; one 2-D sample re-used for
-// light selection and position; shadow rays are closest-hit queries compared with dDist * (1 - eps); 16-bit barycentrics (traversalResult);
+// light selection and position; 16-bit barycentrics (traversalResult);
 // 16-bit spherical previous normal; half-precision un-jittered splat position; a failed BSDF sample still launches a ray (zero direction).
 #pragma once
 #include "wavefront.cuh"
@@ -94,8 +94,9 @@ __global__ void __launch_bounds__(WPT_TILE, 6) k_wpt_iterate(const __grid_consta
         bool specular = (misc.y >> 16) != 0;
         Sampler rng; rng.idx = (unsigned)i; rng.tab = 0; rng.i1 = rng.i2 = (unsigned)P.iterationIdx + 2u; // cu:59-60
         if (NEE && P.pathDepth > 0 && dIdx != 0xffffffffu) { // cu:62-73
-            const float sdist = __uint_as_float(B.sec_res[dIdx].x);
-            if (sdist >= dDist * (1 - S.ray_eps)) L = L + directF;
+            // reference: closest hit of the secondary ray, then `dist >= dDist * (1 - eps)`.  Here the ray carries tmax = dDist * (1 - eps) and is
+            // traced as an any-hit query: "no hit below tmax" is the same predicate (same strict t < tmax test), at a fraction of the traversal
+            if (B.sec_res[dIdx].z == 0xffffffffu) L = L + directF;
             dIdx = 0xffffffffu; directF = sp(0.0f);
         }
         terminated = (P.pathDepth + 1 == P.maxPathDepth);
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(WPT_TILE, 6) k_wpt_iterate(const __grid_consta
     if (shadow) { // insertSecondaryRay (DoubleRayBuffer.h:166-177)
         const unsigned k = excl_sec + pre_sec + __popc(m_sec & lt);
         B.sec_out[2 * k] = make_float4(no.x, no.y, no.z, S.ray_eps);
-        B.sec_out[2 * k + 1] = make_float4(sd.x, sd.y, sd.z, FLT_MAX);
+        B.sec_out[2 * k + 1] = make_float4(sd.x, sd.y, sd.z, df4.w * (1 - S.ray_eps)); // tmax = dDist * (1 - eps), see the occlusion test above
         misc.x = k;
     }
     if (alive) { // insertPayloadElement (DoubleRayBuffer.h:139-152)

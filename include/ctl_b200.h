@@ -223,6 +223,9 @@ ctl_scene* ctl_scene_create_from_xmsh(const char* const* paths, uint32_t n_files
                                       const float* cam_target, const float* cam_up, float fov_deg, int width, int height);
 /* Mesh `mesh` of a host scene as an .xmsh file: the output sequence of Mesh::CompileMesh (Engine/Mesh.cpp:278-289). */
 int  ctl_scene_write_xmsh(const ctl_scene*, uint32_t mesh, const char* path);
+/* Source triangles of mesh `mesh` of a host scene built here (9 floats per triangle, in TriangleData order); verts9_out may be NULL to query
+ * *n_tris.  For export / BVH-rebuild tooling (the reference keeps them only inside its mesh compilers, Engine/Mesh.cpp:199-290). */
+int  ctl_scene_get_mesh_triangles(const ctl_scene*, uint32_t mesh, float* verts9_out, uint32_t* n_tris);
 int  ctl_scene_get_view(const ctl_scene*, ctl_scene_view* out);
 void ctl_scene_destroy(ctl_scene*);
 /* GPU construction of one mesh BVH in the reference layout (LBVH: Morton codes, hand-written radix sort, Karras radix tree,
