@@ -1,5 +1,7 @@
 // scene_builder.cpp -- see scene_builder.h for the reference citations.
 #include "scene_builder.h"
+#include <cstdlib>
+#include <string>
 #include <algorithm>
 #include <cstdio>
 #include <stdexcept>
@@ -244,7 +246,9 @@ void assemble_scene(const std::vector<MeshInput>& meshes, const std::vector<Node
             mesh_box[mi].grow(pb[t]);
         }
         std::vector<ctl_bvh_node> bn; std::vector<uint32_t> ord; std::vector<uint8_t> last;
-        build_bvh(pb, 8, bn, ord, last);
+        const char* which = getenv("CTL_BVH_BUILDER");
+        if (which && std::string(which) == "sah") build_bvh(pb, 8, bn, ord, last);
+        else build_sbvh(S.mesh_verts9.back().data(), nt, 8, bn, ord, last); // maxLeafSize 8: BVHBuilderHelper.cpp:119
         S.bvh_nodes.insert(S.bvh_nodes.end(), bn.begin(), bn.end());
         for (size_t s = 0; s < ord.size(); s++) {
             uint32_t t = ord[s];
