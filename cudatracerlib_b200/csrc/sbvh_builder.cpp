@@ -15,6 +15,9 @@
 #include "scene_builder.h"
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
+#include <cmath>
+#include <cstdio>
 #include <thread>
 
 namespace ctlb {
@@ -30,7 +33,8 @@ struct Sbvh {
     int max_leaf;
     std::vector<ctl_bvh_node>& nodes; std::vector<uint32_t>& ordered; std::vector<uint8_t>& last;
     float root_area = 0.0f;
-    static constexpr float ALPHA = 1e-5f;       // the published default (and the reference's BuildParams::splitAlpha)
+    float CT = 1.0f;                            // cost of a triangle test relative to a node step (CTL_SBVH_CT overrides)
+    float ALPHA = 1e-5f;                        // overlap threshold for trying a spatial split, relative to the root area
     static constexpr int OBJ_BINS = 32, SPATIAL_BINS = 64, SWEEP_BELOW = 4096, MAX_DEPTH = 48, PARALLEL_ABOVE = 8192, PARALLEL_DEPTH = 4;
 
     V3 vert(uint32_t t, int k) const { const float* p = v9 + (size_t)t * 9 + 3 * k; return V3(p[0], p[1], p[2]); }
@@ -183,7 +187,7 @@ struct Sbvh {
             return (int)(node_idx * 4);
         }
         const float area = half_area(bounds);
-        const float leaf_cost = (float)n;
+        const float leaf_cost = CT * (float)n;
         ObjSplit os; SpatialSplit ss;
         if (depth < MAX_DEPTH) {
             os = find_object_split(refs);
@@ -192,8 +196,8 @@ struct Sbvh {
                 if (overlap >= ALPHA * root_area && n > (uint32_t)max_leaf) ss = find_spatial_split(refs, bounds); // leaf-sized nodes: object splits only
             } else if (area > 0 && n > (uint32_t)max_leaf) ss = find_spatial_split(refs, bounds);
         }
-        const float obj_cost = (os.axis >= 0 && area > 0) ? 1.0f + os.cost / area : 3.0e38f;
-        const float spa_cost = (ss.axis >= 0 && area > 0) ? 1.0f + ss.cost / area : 3.0e38f;
+        const float obj_cost = (os.axis >= 0 && area > 0) ? 1.0f + CT * os.cost / area : 3.0e38f;
+        const float spa_cost = (ss.axis >= 0 && area > 0) ? 1.0f + CT * ss.cost / area : 3.0e38f;
         const float split_cost = obj_cost < spa_cost ? obj_cost : spa_cost;
         if (!is_root && (int)n <= max_leaf && (leaf_cost <= split_cost || depth >= MAX_DEPTH)) return emit_leaf(refs);
 
@@ -251,7 +255,7 @@ struct Sbvh {
             // slots in depth-first order) is exactly the sequential one, so the tree does not depend on the thread count
             std::vector<ctl_bvh_node> ln, rn; std::vector<uint32_t> lo_, ro_; std::vector<uint8_t> ll, rl;
             Sbvh SL{v9, max_leaf, ln, lo_, ll}, SR{v9, max_leaf, rn, ro_, rl};
-            SL.root_area = SR.root_area = root_area;
+            SL.root_area = SR.root_area = root_area; SL.ALPHA = SR.ALPHA = ALPHA; SL.CT = SR.CT = CT;
             int la = 0, ra = 0;
             std::thread th([&]() { la = SL.build(left, lb, 0xfffffffeu, false, depth + 1); });
             ra = SR.build(right, rb, 0xfffffffeu, false, depth + 1);
@@ -271,10 +275,109 @@ struct Sbvh {
 
 } // namespace
 
+// ---- which tree serves path rays better?  Measured, not assumed: spatial splits pay off massively on meshes with long thin triangles (config 4:
+// -32 % inner-node visits per path ray) but cost ~10 % on config 2, whose 14 room-sized triangles get chopped into 1 500 references that every
+// path -- all of which end on a wall -- has to dig for (GPU A/B in profiles/r01u_builder_ab.log).  The SAH's uniform-ray model cannot see that,
+// so the mesh builder builds both candidates and keeps the one that a sample of random-walk rays (the population a path tracer sends through the
+// mesh) traverses with fewer steps.
+namespace {
+struct SampleRay { V3 o, d; };
+
+inline bool ray_tri(const float* t, V3 o, V3 d, float tmin, float& tmax) { // Moeller-Trumbore; only used to shrink tmax like the real traversal does
+    const V3 v0(t[0], t[1], t[2]), e1 = V3(t[3], t[4], t[5]) - v0, e2 = V3(t[6], t[7], t[8]) - v0;
+    const V3 p = cross(d, e2); const float det = dot(e1, p);
+    if (fabsf(det) < 1e-20f) return false;
+    const float inv = 1.0f / det; const V3 s = o - v0; const float u = dot(s, p) * inv;
+    if (u < 0.0f || u > 1.0f) return false;
+    const V3 q = cross(s, e1); const float v = dot(d, q) * inv;
+    if (v < 0.0f || u + v > 1.0f) return false;
+    const float tt = dot(e2, q) * inv;
+    if (tt <= tmin || tt >= tmax) return false;
+    tmax = tt; return true;
+}
+
+// closest-hit query through a reference-layout tree (same child-order rule as the device kernel); counts inner pops and triangle tests
+struct Tree { const float* v9; const std::vector<ctl_bvh_node>& nodes; const std::vector<uint32_t>& ordered; const std::vector<uint8_t>& last; };
+int trace_tree(const Tree& T, const SampleRay& r, float& t_hit, double& inner, double& tris) {
+    const V3 id(1.0f / (fabsf(r.d.x) > 1e-20f ? r.d.x : 1e-20f), 1.0f / (fabsf(r.d.y) > 1e-20f ? r.d.y : 1e-20f), 1.0f / (fabsf(r.d.z) > 1e-20f ? r.d.z : 1e-20f));
+    float tmax = 3.0e38f; const float tmin = 1e-4f;
+    int hit = -1, stack[128], sp = 0, cur = 0;
+    for (;;) {
+        if (cur >= 0) {
+            if (cur == CTL_SENTINEL) { if (!sp) break; cur = stack[--sp]; continue; }
+            const ctl_bvh_node& n = T.nodes[(size_t)cur / 4]; inner += 1;
+            auto slab = [&](float lx, float hx, float ly, float hy, float lz, float hz, float& t0) {
+                const float ax = (lx - r.o.x) * id.x, bx = (hx - r.o.x) * id.x, ay = (ly - r.o.y) * id.y, by = (hy - r.o.y) * id.y, az = (lz - r.o.z) * id.z, bz = (hz - r.o.z) * id.z;
+                t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+                const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+                return t1 >= t0;
+            };
+            float t0a = 0, t0b = 0;
+            const bool ha = slab(n.a[0], n.a[1], n.a[2], n.a[3], n.c[0], n.c[1], t0a);
+            const bool hb = n.child1 != CTL_SENTINEL && slab(n.b[0], n.b[1], n.b[2], n.b[3], n.c[2], n.c[3], t0b);
+            if (!ha && !hb) { if (!sp) break; cur = stack[--sp]; continue; }
+            if (ha && hb) { const bool swp = t0b < t0a; cur = swp ? n.child1 : n.child0; if (sp < 127) stack[sp++] = swp ? n.child0 : n.child1; }
+            else cur = ha ? n.child0 : n.child1;
+        } else {
+            for (uint32_t slot = (uint32_t)~cur;; slot++) { tris += 1; if (ray_tri(T.v9 + (size_t)T.ordered[slot] * 9, r.o, r.d, tmin, tmax)) hit = (int)T.ordered[slot]; if (T.last[slot]) break; }
+            if (!sp) break; cur = stack[--sp];
+        }
+    }
+    t_hit = tmax;
+    return hit;
+}
+
+// a small random walk through the mesh: origins inside its box, then up to 4 diffuse-like bounces off whatever is hit -- the population of
+// extension and shadow rays a path tracer sends through this mesh (every walk ray is kept as a sample)
+std::vector<SampleRay> walk_rays(const Tree& T, const Box& box, int n_walks) {
+    uint64_t state = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&]() { state = state * 6364136223846793005ull + 1442695040888963407ull; return (float)((state >> 40) * (1.0 / 16777216.0)); };
+    auto dir = [&]() { const float z = 2.0f * rnd() - 1.0f, ph = 6.2831853f * rnd(), rr = sqrtf(fmaxf(0.0f, 1.0f - z * z)); return V3(rr * cosf(ph), rr * sinf(ph), z); };
+    std::vector<SampleRay> rays;
+    for (int i = 0; i < n_walks; i++) {
+        SampleRay r{V3(box.lo.x + (box.hi.x - box.lo.x) * rnd(), box.lo.y + (box.hi.y - box.lo.y) * rnd(), box.lo.z + (box.hi.z - box.lo.z) * rnd()), dir()};
+        for (int depth = 0; depth < 5; depth++) {
+            rays.push_back(r);
+            float t; double a = 0, b = 0;
+            const int tri = trace_tree(T, r, t, a, b);
+            if (tri < 0) break;
+            const float* p = T.v9 + (size_t)tri * 9;
+            V3 n = normalize(cross(V3(p[3], p[4], p[5]) - V3(p[0], p[1], p[2]), V3(p[6], p[7], p[8]) - V3(p[0], p[1], p[2])));
+            if (dot(n, r.d) > 0) n = -n;
+            V3 d = dir(); if (dot(d, n) < 0) d = -d;
+            r = SampleRay{r.o + r.d * t + n * 1e-4f, d};
+        }
+    }
+    return rays;
+}
+double traversal_cost(const Tree& T, const std::vector<SampleRay>& rays) {
+    double inner = 0, tris = 0; float t;
+    for (const SampleRay& r : rays) trace_tree(T, r, t, inner, tris);
+    return inner + 0.8 * tris;
+}
+} // namespace
+
+static void build_sbvh_alpha(const float* verts9, uint32_t n_tris, int max_leaf, float alpha, std::vector<ctl_bvh_node>& nodes_out, std::vector<uint32_t>& ordered, std::vector<uint8_t>& last);
+
 void build_sbvh(const float* verts9, uint32_t n_tris, int max_leaf, std::vector<ctl_bvh_node>& nodes_out, std::vector<uint32_t>& ordered, std::vector<uint8_t>& last) {
+    if (getenv("CTL_SBVH_ALPHA")) { build_sbvh_alpha(verts9, n_tris, max_leaf, (float)atof(getenv("CTL_SBVH_ALPHA")), nodes_out, ordered, last); return; } // experiments: no selection
+    build_sbvh_alpha(verts9, n_tris, max_leaf, 1e-5f, nodes_out, ordered, last);   // the published default (and the reference's BuildParams::splitAlpha)
+    if (ordered.size() == n_tris || n_tris < 64) return;                           // no reference was split: nothing to choose
+    std::vector<ctl_bvh_node> n2; std::vector<uint32_t> o2; std::vector<uint8_t> l2;
+    build_sbvh_alpha(verts9, n_tris, max_leaf, 3.0e38f, n2, o2, l2);               // object splits only
+    const Tree split{verts9, nodes_out, ordered, last}, plain{verts9, n2, o2, l2};
+    Box box; for (size_t i = 0; i < (size_t)n_tris * 3; i++) box.grow(V3(verts9[3 * i], verts9[3 * i + 1], verts9[3 * i + 2]));
+    const std::vector<SampleRay> rays = walk_rays(plain, box, 4096);
+    const double c_split = traversal_cost(split, rays), c_plain = traversal_cost(plain, rays);
+    if (getenv("CTL_SBVH_VERBOSE")) fprintf(stderr, "mesh %u tris: split tree %zu refs cost %.0f, plain tree cost %.0f over %zu walk rays -> %s\n", n_tris, ordered.size(), c_split, c_plain, rays.size(), c_plain < c_split ? "plain" : "split");
+    if (c_plain < c_split) { nodes_out.swap(n2); ordered.swap(o2); last.swap(l2); }
+}
+
+static void build_sbvh_alpha(const float* verts9, uint32_t n_tris, int max_leaf, float alpha, std::vector<ctl_bvh_node>& nodes_out, std::vector<uint32_t>& ordered, std::vector<uint8_t>& last) {
     nodes_out.clear(); ordered.clear(); last.clear();
     if (!n_tris) return;
     Sbvh S{verts9, max_leaf, nodes_out, ordered, last};
+    S.ALPHA = alpha;
     std::vector<Ref> refs(n_tris); Box all;
     for (uint32_t t = 0; t < n_tris; t++) {
         refs[t].tri = t;
@@ -282,6 +385,7 @@ void build_sbvh(const float* verts9, uint32_t n_tris, int max_leaf, std::vector<
         all.grow(refs[t].b);
     }
     S.root_area = half_area(all);
+    if (const char* a = getenv("CTL_SBVH_CT")) S.CT = (float)atof(a);
     S.build(refs, all, 0xffffffffu, true, 0);
 }
 

@@ -231,27 +231,35 @@ def test_cpp_adapter_compiles_and_fails_loudly_without_gpu(built_lib, tmp_path):
 
 
 def test_split_bvh_builder_vs_plain_sah(built_lib, orc, monkeypatch):
-    """The mesh builder is a split BVH (csrc/sbvh_builder.cpp; the reference's meshes come from SplitBVHBuilder).  Against the plain binned-SAH
-    builder kept for A/B (CTL_BVH_BUILDER=sah): identical closest hits, bit for bit, on a scene with long thin triangles (the config-4
-    generator at a small size), references duplicated only moderately, and fewer inner-node visits per ray.  The build is deterministic."""
+    """The mesh builder is a split BVH (csrc/sbvh_builder.cpp; the reference's meshes come from SplitBVHBuilder) that keeps, per mesh, the
+    better of the tree with spatial splits and the tree without, judged by random-walk sample rays.  Against the plain binned-SAH builder kept
+    for A/B (CTL_BVH_BUILDER=sah): identical closest hits, bit for bit, on a scene with long thin triangles (the config-4 generator at a small
+    size); the spatially split tree (forced with CTL_SBVH_ALPHA) duplicates references moderately and needs fewer triangle tests and node pops."""
     from cudatracerlib_b200 import api
     s1 = ctl.Scene("c4", 64, 64, n_hint=24)
     s1b = ctl.Scene("c4", 64, 64, n_hint=24)
     monkeypatch.setenv("CTL_BVH_BUILDER", "sah")
     s0 = ctl.Scene("c4", 64, 64, n_hint=24)
     monkeypatch.delenv("CTL_BVH_BUILDER")
-    assert s0.view.n_woop == s0.n_triangles == s1.n_triangles and s1.n_triangles <= s1.view.n_woop <= 1.35 * s1.n_triangles
+    monkeypatch.setenv("CTL_SBVH_ALPHA", "1e-5")
+    s2 = ctl.Scene("c4", 64, 64, n_hint=24)
+    monkeypatch.delenv("CTL_SBVH_ALPHA")
+    assert s0.view.n_woop == s0.n_triangles == s1.n_triangles and s1.n_triangles <= s1.view.n_woop <= s2.view.n_woop
+    assert s2.n_triangles < s2.view.n_woop <= 1.35 * s2.n_triangles
     for name in ("bvh_nodes", "woop", "tri_index"):
         assert np.array_equal(s1.array(name).view(np.uint32), s1b.array(name).view(np.uint32))       # deterministic (threads only change the schedule)
     assert np.array_equal(s0.array("tri_data"), s1.array("tri_data"))
     rng = np.random.default_rng(8)
     lo = np.array(list(s1.view.box_min)); hi = np.array(list(s1.view.box_max))
     rays = np.zeros(6000, api.RAY_DTYPE); rays["o"] = rng.uniform(lo, hi, (6000, 3)); d = rng.normal(size=(6000, 3)); rays["d"] = d / np.linalg.norm(d, axis=1, keepdims=True); rays["tmax"] = 3e38
-    a, ca = orc.trace_rays(s0.view, rays, counts=True); b, cb = orc.trace_rays(s1.view, rays, counts=True)
-    assert np.array_equal(a["tri_idx"], b["tri_idx"]) and np.array_equal(a["node_idx"], b["node_idx"])
-    for f in ("dist", "u", "v"):
-        assert np.array_equal(a[f].view(np.uint32), b[f].view(np.uint32)), f
-    # fewer node pops and triangle tests -- modest at this size (24 spheres + 3.4 K foliage triangles); on the full 1 M-triangle config 4 the
-    # oracle measures 95 vs 140 inner nodes and 12 vs 25 triangle tests per ray (profiles/r01u_sbvh_builder.log)
+    a, ca = orc.trace_rays(s0.view, rays, counts=True)
+    for s in (s1, s2):
+        b, cb = orc.trace_rays(s.view, rays, counts=True)
+        assert np.array_equal(a["tri_idx"], b["tri_idx"]) and np.array_equal(a["node_idx"], b["node_idx"])
+        for f in ("dist", "u", "v"):
+            assert np.array_equal(a[f].view(np.uint32), b[f].view(np.uint32)), f
+        assert cb[0] <= ca[0]
+    # spatial splits: fewer node pops and triangle tests -- modest at this size (24 spheres + 3.4 K foliage triangles); on the full 1 M-triangle
+    # config 4 the oracle measures 95 vs 140 inner nodes and 12 vs 25 triangle tests per ray (profiles/r01u_sbvh_builder.log)
     assert cb[0] < 0.95 * ca[0] and cb[1] < 0.85 * ca[1], (ca, cb)
     assert api.traversal_bytes(cb, len(rays)) < 0.95 * api.traversal_bytes(ca, len(rays))

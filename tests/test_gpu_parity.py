@@ -494,7 +494,7 @@ def test_gpu_bvh_build_matches_cpu_bvh_results(built_lib, orc, kind):
     w, h = 192, 108
     s_cpu = ctl.Scene(kind, w, h); s_gpu = ctl.Scene(kind, w, h)
     ms = s_gpu.rebuildBVHOnGPU()
-    assert ms > 0 and s_gpu.view.n_woop == s_cpu.view.n_woop == s_gpu.view.n_tri_index
+    assert ms > 0 and s_gpu.view.n_woop == s_gpu.n_triangles == s_gpu.view.n_tri_index and s_cpu.view.n_woop >= s_cpu.n_triangles   # the CPU split BVH may duplicate references
     meshes = s_gpu.array("meshes"); tri_index = s_gpu.array("tri_index")[:, 0]; bvh = s_gpu.array("bvh_nodes")
     for mi, m in enumerate(meshes):
         node_off4, idx_off = int(m[1]), int(m[3])
