@@ -35,6 +35,9 @@ struct WptBuf {
 struct WptParams { int pathDepth, iterationIdx, maxPathDepth, rrStart; };
 
 constexpr int WPT_TILE = 128;
+#ifndef WPT_MIN_BLOCKS
+#define WPT_MIN_BLOCKS 8 // 64 registers, 8 blocks per SM: measured +2 % over 6 (80 registers) on C2, profiles/r01v_wpt_occupancy_ab.log
+#endif
 
 CTL_DEV unsigned short enc_normal_dev(V3 v) { // NormalizedFloat3ToUchar2_Spherical, Math/Compression.h:12-18
     const float theta = acosf(v.z) * (255.0f / PI_F);
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(256) k_wpt_create(const __grid_constant__ DSce
 // desc: one 64-bit descriptor per tile: [63:62] status (0 = not ready, 1 = tile aggregate, 2 = inclusive prefix), [61:31] secondary count,
 // [30:0] payload count; desc[n_tiles_max] is the tile ticket.  All zero at launch.
 template <bool NEE>
-__global__ void __launch_bounds__(WPT_TILE, 6) k_wpt_iterate(const __grid_constant__ DScene S, const __grid_constant__ WptParams P, WptBuf B, const unsigned* __restrict__ n_in,
+__global__ void __launch_bounds__(WPT_TILE, WPT_MIN_BLOCKS) k_wpt_iterate(const __grid_constant__ DScene S, const __grid_constant__ WptParams P, WptBuf B, const unsigned* __restrict__ n_in,
                                                              unsigned* __restrict__ n_pay_out, unsigned* __restrict__ n_sec_out, unsigned long long* desc, int n_tiles_max, float* accum) {
     __shared__ unsigned s_tile;
     __shared__ unsigned s_warp_pay[WPT_TILE / 32], s_warp_sec[WPT_TILE / 32];
