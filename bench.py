@@ -197,6 +197,7 @@ def main():
     ap.add_argument("--cpu-frac", type=float, default=1.0 / 16, help="fraction of the image the CPU baseline renders per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sort-mode", type=int, default=None)
+    ap.add_argument("--set", action="append", default=[], metavar="KEY=INT", help="extra tracer parameter (ctl_set_param_i), for A/B runs")
     ap.add_argument("--tile", type=int, default=0, help="tile edge for the multi-GPU partition (0 = package default)")
     ap.add_argument("--batch", type=int, default=8, help="progressive passes fused into one wavefront (must divide spp)")
     args = ap.parse_args()
@@ -232,6 +233,8 @@ def main():
     tracer.setParameter("MaxPathLength", depth)
     if args.sort_mode is not None:
         tracer.setParameter("SortMode", args.sort_mode)
+    for kv in args.set:
+        k, v = kv.split("="); tracer.setParameter(k, int(v))
     stream = torch.cuda.Stream(device=dev)  # a real (non-default) stream: the tracer, NCCL and the timing events all use it
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0

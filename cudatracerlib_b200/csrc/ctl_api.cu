@@ -55,7 +55,7 @@ struct ctl_ctx {
     int n_sm = 148;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     // parameters (Integrators/PathTracer.h:10-20)
-    int max_path_length = 50, rr_start = 5, direct = 1, regularization = 0, sort_mode = 0, stage_timers = 0, capture_bounce = 0, trav_kernel = 0, trav_blocks_per_sm = 8, shade_blocks_per_sm = 8, smem_carveout = -1, fuse_traversal = 1;
+    int max_path_length = 50, rr_start = 5, direct = 1, regularization = 0, sort_mode = 0, stage_timers = 0, capture_bounce = 0, trav_kernel = 0, trav_blocks_per_sm = 8, shade_blocks_per_sm = 8, smem_carveout = -1, fuse_traversal = 1, warp_blocks = 0;
     // scene
     DevBuf<ctl_bvh_node> d_scene_nodes, d_bvh_nodes; DevBuf<ctl_woop_tri> d_woop; DevBuf<uint32_t> d_tri_index; DevBuf<ctl_tri_data> d_tri_data;
     DevBuf<ctl_mesh> d_meshes; DevBuf<ctl_node> d_nodes; DevBuf<float> d_xf, d_inv_xf; DevBuf<ctl_material> d_materials; DevBuf<ctl_light> d_lights;
@@ -353,6 +353,7 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "DeviceSampleTables") c->device_tables = v != 0;
     else if (k == "FuseTraversal") c->fuse_traversal = v != 0;
     else if (k == "PixelVarianceBuffer") c->variance_buffer = v != 0;
+    else if (k == "WarpPixelBlocks") c->warp_blocks = v != 0;
     else if (k == "TraversalKernel") { if (v < 0 || v > 1) return set_err("TraversalKernel must be 0 or 1"); c->trav_kernel = v; }
     else if (k == "TravThT") c->tune.th_t = v; else if (k == "TravThL") c->tune.th_l = v; else if (k == "TravThF") c->tune.th_f = v;
     else if (k == "TravThNExit") c->tune.th_n_exit = v;
@@ -660,6 +661,7 @@ int ctl_render_passes_tiled(ctl_ctx* c, int new_trace, int n_passes, int tile_w,
     Window W; memset(&W, 0, sizeof(W));
     W.mode = 1; W.tile_w = tile_w; W.tile_h = tile_h; W.part = part; W.n_parts = n_parts; W.n_passes = n_passes;
     W.tiles_x = (c->w + tile_w - 1) / tile_w; W.tiles_y = (c->h + tile_h - 1) / tile_h;
+    W.warp_blocks = c->warp_blocks && tile_w % 8 == 0 && tile_h % 4 == 0;
     const int n_tiles = W.tiles_x * W.tiles_y;
     const int n_local = n_tiles > part ? (n_tiles - part + n_parts - 1) / n_parts : 0;
     W.n_slots = n_local * tile_w * tile_h;

@@ -18,6 +18,7 @@ struct Window { // which pixels a pass renders
     int tile_w, tile_h, part, n_parts, tiles_x, tiles_y;
     int n_slots;   // pixels of the window (paths per pass)
     int n_passes;  // passes rendered by this wavefront; path slot = pass * n_slots + pixel slot
+    int warp_blocks; // mode 1: slots inside a tile run over 8x4 pixel blocks (tile_w % 8 == 0 and tile_h % 4 == 0) instead of rows
 };
 
 // SoA path state, indexed by path id (= window slot)
@@ -61,7 +62,11 @@ CTL_DEV bool slot_to_pixel(const Window& W, int s, int img_w, int img_h, int& x,
         const int t_local = s / per, r = s % per;
         const int tile = W.part + t_local * W.n_parts;
         const int tx = tile % W.tiles_x, ty = tile / W.tiles_x;
-        x = tx * W.tile_w + r % W.tile_w; y = ty * W.tile_h + r / W.tile_w;
+        if (W.warp_blocks) { // a warp = an 8x4 pixel block instead of 32 pixels of one row: tighter ray bundles at bounce 0 and, because compaction
+                             // keeps the queue order, neighbouring origins at the later bounces (pixels, samples and results are unchanged)
+            const int b = r >> 5, l = r & 31, bpr = W.tile_w >> 3;
+            x = tx * W.tile_w + (b % bpr) * 8 + (l & 7); y = ty * W.tile_h + (b / bpr) * 4 + (l >> 3);
+        } else { x = tx * W.tile_w + r % W.tile_w; y = ty * W.tile_h + r / W.tile_w; }
     }
     return x >= 0 && y >= 0 && x < img_w && y < img_h;
 }
