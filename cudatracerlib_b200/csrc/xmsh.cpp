@@ -41,6 +41,11 @@ struct File {
     File(const char* p, const char* mode) : f(fopen(p, mode)), path(p) { if (!f) throw std::runtime_error("Could not open file: " + path); }
     ~File() { if (f) fclose(f); }
     void read(void* dst, size_t n) { if (n && fread(dst, 1, n, f) != n) throw std::runtime_error("Passed end of file: " + path); }
+    // refuse to allocate for a record count the rest of the file cannot hold (corrupt / truncated headers)
+    void need(uint64_t count, size_t record) {
+        const long pos = ftell(f); fseek(f, 0, SEEK_END); const long end = ftell(f); fseek(f, pos, SEEK_SET);
+        if (pos < 0 || end < pos || count > (uint64_t)(end - pos) / record) throw std::runtime_error("Passed end of file: " + path);
+    }
     void write(const void* src, size_t n) { if (n && fwrite(src, 1, n, f) != n) throw std::runtime_error("Could not write to file: " + path); }
     template <typename T> T get() { T v; read(&v, sizeof(T)); return v; }
     template <typename T> void put(const T& v) { write(&v, sizeof(T)); }
@@ -150,6 +155,7 @@ void read_xmsh(const char* path, MeshInput& M) {
     }
     const uint32_t n_tris = in.get<uint32_t>();
     if (n_tris == 0 || n_tris > 0x3fffffffu) throw std::runtime_error(std::string("Mesh file parser error (triangle count). ") + path);
+    in.need(n_tris, sizeof(ctl_tri_data));
     M.pre_tri_data.resize(n_tris); in.read(M.pre_tri_data.data(), (size_t)n_tris * sizeof(ctl_tri_data));
     const uint32_t n_mats = in.get<uint32_t>();
     if (n_mats == 0 || n_mats > 256) throw std::runtime_error(std::string("Mesh file parser error (material count). ") + path);
@@ -164,12 +170,15 @@ void read_xmsh(const char* path, MeshInput& M) {
     }
     const uint64_t n_nodes = in.get<uint64_t>();
     if (n_nodes == 0 || n_nodes > 0x7fffffffull / 4) throw std::runtime_error(std::string("Mesh file parser error (node count). ") + path);
+    in.need(n_nodes, sizeof(ctl_bvh_node));
     M.pre_nodes.resize((size_t)n_nodes); in.read(M.pre_nodes.data(), (size_t)n_nodes * sizeof(ctl_bvh_node));
     const uint64_t n_refs = in.get<uint64_t>();
     if (n_refs == 0 || n_refs > 0x7fffffffull) throw std::runtime_error(std::string("Mesh file parser error (triangle reference count). ") + path);
+    in.need(n_refs, sizeof(ctl_woop_tri));
     M.pre_woop.resize((size_t)n_refs); in.read(M.pre_woop.data(), (size_t)n_refs * sizeof(ctl_woop_tri));
     const uint64_t n_idx = in.get<uint64_t>();
     if (n_idx != n_refs) throw std::runtime_error(std::string("Mesh file parser error (index count != reference count). ") + path);
+    in.need(n_idx, 4);
     M.pre_index.resize((size_t)n_idx); in.read(M.pre_index.data(), (size_t)n_idx * 4);
     for (uint32_t w : M.pre_index) if ((w >> 1) >= n_tris) throw std::runtime_error(std::string("Mesh file parser error (leaf references a triangle out of range). ") + path);
     for (const ctl_tri_data& t : M.pre_tri_data) if (((t.w[1] >> 16) & 0xffu) >= n_mats) throw std::runtime_error(std::string("Mesh file parser error (triangle references a material out of range). ") + path);

@@ -108,6 +108,8 @@ def test_reader_error_paths(built_lib, tmp_path):
     expect(struct.pack("I", 7) + good[4:], "Mesh file parser error")
     expect(struct.pack("I", 1) + good[4:], "animated meshes")
     expect(b"", "Passed end of file")
+    bad = bytearray(good); bad[4 + 24 + 4 + 2 * 48:4 + 24 + 4 + 2 * 48 + 4] = struct.pack("I", 0x30000000)   # absurd triangle count: refused before allocating
+    expect(bytes(bad), "Passed end of file")
     # first material blob starts after: token, box, light count, 2 lights, triangle count, 26 triangles, material count
     m0 = 4 + 24 + 4 + 2 * 48 + 4 + 26 * 32 + 4
     bad = bytearray(good); bad[m0 + 512:m0 + 516] = struct.pack("I", 9)          # roughplastic
