@@ -223,6 +223,8 @@ __global__ void __launch_bounds__(WPT_TILE, WPT_MIN_BLOCKS) k_wpt_iterate(const 
                 if (incl) break;
                 look -= 32;
             }
+            __threadfence(); // acquire side of the hand-over: the reads of the predecessor tiles (ordered before their descriptors by their barrier + fence)
+                             // happen before this tile's writes into their slots
             if (lane == 0) vdesc[tile] = (2ull << 62) | (excl + aggregate);
         }
         if (lane == 0) {
