@@ -13,7 +13,7 @@ __global__ void create(Buffer::Device B, int w, int h, float ox, float oy, float
     if (i >= w * h) return;
     const int x = i % w, y = i / w;
     float dx = (x + 0.5f) / w - 0.5f, dy = (y + 0.5f) / h - 0.5f, dz = 1.0f;
-    const float il = rsqrtf(dx * dx + dy * dy + dz * dz); dx *= il; dy *= il; dz *= il;
+    const float il = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz); dx *= il; dy *= il; dz *= il;   // compiled with -fmad=false: reproducible on the host
     Payload p; p.pixel = i; p.throughput = 1.0f; p.sec_idx = 0xffffffffu;
     B.insertPayloadElement(p, B.makeRay(ox, oy, oz, dx, dy, dz));
 }
@@ -30,7 +30,7 @@ __global__ void iterate(Buffer::Device B, int depth, float* out, float lx, float
         }
         if (depth == 0 && res.tri_idx >= 0) {
             const float px = ray.o[0] + ray.d[0] * res.dist, py = ray.o[1] + ray.d[1] * res.dist, pz = ray.o[2] + ray.d[2] * res.dist;
-            float sx = lx - px, sy = ly - py, sz = lz - pz; const float il = rsqrtf(sx * sx + sy * sy + sz * sz); sx *= il; sy *= il; sz *= il;
+            float sx = lx - px, sy = ly - py, sz = lz - pz; const float il = 1.0f / sqrtf(sx * sx + sy * sy + sz * sz); sx *= il; sy *= il; sz *= il;
             unsigned k = 0xffffffffu;
             if (!B.insertSecondaryRay(B.makeRay(px, py, pz, sx, sy, sz), k)) k = 0xffffffffu;
             p.sec_idx = k; p.throughput *= 0.5f;
