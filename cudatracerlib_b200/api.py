@@ -119,6 +119,8 @@ def lib():
     L.ctl_scene_create_from_xmsh.restype = vp
     L.ctl_scene_create_from_xmsh.argtypes = [C.POINTER(C.c_char_p), u32, vp, vp, vp, vp, C.c_float, i32, i32]
     L.ctl_scene_write_xmsh.argtypes = [vp, u32, C.c_char_p]
+    L.ctl_scene_create_from_files.restype = vp
+    L.ctl_scene_create_from_files.argtypes = [C.POINTER(C.c_char_p), u32, vp, vp, vp, vp, C.c_float, i32, i32]
     L.ctl_scene_get_mesh_triangles.argtypes = [vp, u32, vp, C.POINTER(C.c_uint32)]
     L.ctl_scene_destroy.argtypes = [vp]; L.ctl_scene_destroy.restype = None
     L.ctl_bvh_build_gpu.argtypes = [i32, vp, u32, vp, vp, vp, vp, vp]
@@ -223,6 +225,8 @@ class Scene:
         out = np.zeros((n.value, 3, 3), np.float32)
         _check(lib().ctl_scene_get_mesh_triangles(self._h, mesh, _ptr(out), C.byref(n)))
         return out
+
+    from_files = from_xmsh   # .xmsh and .obj files, chosen by extension (ctl_scene_create_from_files)
 
     def write_xmsh(self, path, mesh=0):
         """Mesh `mesh` as an .xmsh file (the output sequence of the reference's Mesh::CompileMesh)."""

@@ -130,7 +130,9 @@ ctl_scene* ctl_scene_create_from_xmsh(const char* const* paths, uint32_t n_files
         std::vector<ctlb::MeshInput> meshes(n_files); std::vector<ctlb::NodeInput> nodes;
         for (uint32_t i = 0; i < n_files; i++) {
             if (!paths[i]) throw std::runtime_error("null path");
-            ctlb::read_xmsh(paths[i], meshes[i]);
+            const std::string pth(paths[i]);
+            if (pth.size() > 4 && (pth.substr(pth.size() - 4) == ".obj" || pth.substr(pth.size() - 4) == ".OBJ")) ctlb::read_obj(paths[i], meshes[i]); // MeshCompilerManager picks the compiler by extension (MeshCompiler.cpp:21-27)
+            else ctlb::read_xmsh(paths[i], meshes[i]);
             ctlb::M4 xf = ctlb::M4::identity();
             if (node_xforms) memcpy(xf.m, node_xforms + 16 * (size_t)i, 64);
             nodes.push_back({i, xf, -1});
@@ -142,6 +144,10 @@ ctl_scene* ctl_scene_create_from_xmsh(const char* const* paths, uint32_t n_files
         } catch (...) { delete s; throw; }
         return s;
     } catch (const std::exception& e) { set_err(e.what()); return nullptr; }
+}
+ctl_scene* ctl_scene_create_from_files(const char* const* paths, uint32_t n_files, const float* node_xforms, const float* cam_pos, const float* cam_target,
+                                       const float* cam_up, float fov_deg, int width, int height) {
+    return ctl_scene_create_from_xmsh(paths, n_files, node_xforms, cam_pos, cam_target, cam_up, fov_deg, width, height);
 }
 // == the output sequence of Mesh::CompileMesh (Engine/Mesh.cpp:278-289) for mesh `mesh` of a host scene
 int ctl_scene_write_xmsh(const ctl_scene* s, uint32_t mesh, const char* path) {

@@ -238,8 +238,13 @@ void assemble_scene(const std::vector<MeshInput>& meshes, const std::vector<Node
         S.mesh_verts9.emplace_back(); S.mesh_verts9.back().reserve((size_t)nt * 9);
         for (uint32_t t = 0; t < nt; t++) {
             V3 p[3], n[3];
-            for (int k = 0; k < 3; k++) { p[k] = M.verts[M.indices[t * 3 + k]]; n[k] = vn[M.indices[t * 3 + k]]; pb[t].grow(p[k]); S.mesh_verts9.back().insert(S.mesh_verts9.back().end(), {p[k].x, p[k].y, p[k].z}); }
             float uv[6] = {0, 0, 0, 0, 0, 0};
+            for (int k = 0; k < 3; k++) {
+                const uint32_t vi = M.indices[t * 3 + k];
+                p[k] = M.verts[vi]; n[k] = M.normals.empty() ? vn[vi] : normalize(M.normals[vi]); pb[t].grow(p[k]);
+                if (!M.uvs.empty()) { uv[2 * k] = M.uvs[2 * vi]; uv[2 * k + 1] = M.uvs[2 * vi + 1]; }
+                S.mesh_verts9.back().insert(S.mesh_verts9.back().end(), {p[k].x, p[k].y, p[k].z});
+            }
             ctl_tri_data td;
             encode_tri_data(p, n, uv, M.mat_index[t], &td);
             S.tri_data.push_back(td);

@@ -25,6 +25,8 @@ struct MeshInput {
     std::vector<uint8_t> mat_index;  // per triangle, local to the mesh's material block
     std::vector<ctl_material> materials;
     std::vector<V3> emissive;        // per material; non-zero => area light
+    std::vector<V3> normals;         // optional, per vertex: used (normalised) instead of computed vertex normals (Mesh::CompileMesh a_normals)
+    std::vector<float> uvs;          // optional, 2 per vertex: UV set 0 (drives dpdu / dpdv, TriangleData.cu:37-57)
     // pre-compiled mesh (.xmsh import, xmsh.cpp): when pre_tri_data is non-empty the arrays below are taken as they are (reference layouts)
     // instead of being built from verts / indices; mat_index is then derived from the TriangleData words
     std::vector<ctl_tri_data> pre_tri_data;
@@ -36,6 +38,7 @@ struct MeshInput {
 
 // .xmsh (the reference's compiled-mesh format: Engine/Mesh.cpp:46-98 reader, :199-290 writer, Engine/MeshLoader/BVHBuilderHelper.cpp:129-147)
 void read_xmsh(const char* path, MeshInput& out);                                  // throws std::runtime_error
+void read_obj(const char* path, MeshInput& out);                                   // Wavefront OBJ + MTL (obj_import.cpp), == the reference's compileobj front end
 void write_xmsh(const char* path, const struct SceneStorage& S, uint32_t mesh);    // mesh `mesh` of an assembled scene
 
 struct NodeInput {

@@ -221,6 +221,13 @@ ctl_scene* ctl_scene_create_from_mesh(const float* verts, uint32_t nv, const uin
  * become area lights.  node_xforms: n_files row-major float4x4 local-to-world matrices, or NULL = identity. */
 ctl_scene* ctl_scene_create_from_xmsh(const char* const* paths, uint32_t n_files, const float* node_xforms, const float* cam_pos,
                                       const float* cam_target, const float* cam_up, float fov_deg, int width, int height);
+/* Same import for any mix of mesh files, chosen by extension like the reference's MeshCompilerManager (Engine/MeshLoader/MeshCompiler.cpp):
+ * .xmsh as above; .obj (+ the .mtl it names) through this library's own OBJ front end, which reproduces what the reference's
+ * compileobj -> Mesh::CompileMesh writes for the same file (vertex de-duplication order, fan triangulation, reversed winding, its
+ * single-precision number reader, vertex normals, UV-driven dpdu / dpdv) for materials of the hot path: illum 2 with Ks = 0 (diffuse),
+ * illum 7 / 9 (dielectric), Ke (area light).  ctl_scene_create_from_xmsh accepts the same mix (it is this function). */
+ctl_scene* ctl_scene_create_from_files(const char* const* paths, uint32_t n_files, const float* node_xforms, const float* cam_pos,
+                                       const float* cam_target, const float* cam_up, float fov_deg, int width, int height);
 /* Mesh `mesh` of a host scene as an .xmsh file: the output sequence of Mesh::CompileMesh (Engine/Mesh.cpp:278-289). */
 int  ctl_scene_write_xmsh(const ctl_scene*, uint32_t mesh, const char* path);
 /* Source triangles of mesh `mesh` of a host scene built here (9 floats per triangle, in TriangleData order); verts9_out may be NULL to query

@@ -32,6 +32,10 @@
 #                                      BVHBuilderHelper.cpp compile unpatched.  One line patched: `TriangleData tri;` (Mesh.cpp:232) is zero-filled -- its
 #                                      constructor sets nothing (TriangleData.h:37) and setData reads the UV words, which a mesh without texture
 #                                      coordinates never writes (uninitialised read; zero UVs take setData's determinant == 0 branch).
+#                                      Engine/MeshLoader/ObjParser.cpp and PlyParser.cpp (compileobj / compileply, the OBJ / PLY -> .xmsh compilers) compile unpatched.
+#  12. Engine/MeshLoader/ObjParser.cpp:648  `Vec3i ptn;` (empty constructor, Math/Vector.h:186) is read for the vt / vn slots a face vertex does not give
+#                                      (`f 1 2 3`, `f 1//2 ...`): uninitialised.  Zero-initialised = "slot absent" (index 0 -> -1 after the decrement), the
+#                                      evident intent.
 # oracle/ref_driver.cpp only defines the scene globals and packs ctl_scene_view into KernelDynamicScene.
 set -euo pipefail
 REF=${CTL_REFERENCE:-/root/reference}
@@ -47,6 +51,8 @@ cp -r "$REF"/Base "$REF"/Engine "$REF"/Integrators "$REF"/Kernel "$REF"/Math "$R
 chmod -R u+w "$SCR"
 cd "$SCR"
 sed -i 's/obj->Is<T>()/obj->template Is<T>()/g; s/obj->As<T>()/obj->template As<T>()/g' Base/VirtualFuncType.h
+sed -i 's/^\t\t\t\tVec3i ptn;$/\t\t\t\tVec3i ptn(0, 0, 0); \/* patch 12 *\//' Engine/MeshLoader/ObjParser.cpp
+grep -q 'patch 12' Engine/MeshLoader/ObjParser.cpp || { echo "ObjParser.cpp patch 12 did not apply"; exit 4; }
 python3 - <<'PY'
 import re
 p = "Math/half.h"; s = open(p).read()
@@ -85,7 +91,7 @@ grep -q 'void Mesh::CompileMesh' Engine/Mesh_compile_host.cpp && grep -q 'patch 
 sed -n '1,86p' Engine/Image.cu > Engine/Image_host.cu; echo "}" >> Engine/Image_host.cu
 { echo '#include "Image.h"'; echo '#include <Base/CudaMemoryManager.h>'; echo 'namespace CudaTracerLib {'; sed -n '12,30p' Engine/Image.cpp; echo '}'; } > Engine/Image_ctor.cpp
 CXXFLAGS="-std=c++17 -x c++ -include cstring -include cmath -fpermissive -w -O2 -fPIC -ffp-contract=off -pthread -I$SCR -I$CUDA_INC -I$HERE/../include"
-TUS="SceneTypes/BSDF_Simple.cu SceneTypes/BSDF_Complex.cu SceneTypes/Light.cu Engine/ShapeSet.cu Kernel/TraceAlgorithms.cu Engine/KernelDynamicScene.cu Kernel/TraceResult.cu SceneTypes/Sensor.cu Engine/MicrofacetDistribution.cu Base/CudaRandom.cu Engine/TriIntersectorData.cu Engine/DifferentialGeometry.cu SceneTypes/Samples.cu Engine/Material.cu SceneTypes/Volumes.cu SceneTypes/PhaseFunction.cu Math/FresnelHelper.cu Base/Platform.cu SceneTypes/Texture.cu Engine/RoughTransmittance.cu Math/MonteCarlo.cu Engine/TriangleData.cu Math/Spectrum.cu Engine/Image_host.cu Engine/Image_ctor.cpp Engine/Mesh_compile_host.cpp Base/FileStream.cpp Engine/SpatialStructures/BVH/SplitBVHBuilder.cpp Engine/MeshLoader/BVHBuilderHelper.cpp"
+TUS="SceneTypes/BSDF_Simple.cu SceneTypes/BSDF_Complex.cu SceneTypes/Light.cu Engine/ShapeSet.cu Kernel/TraceAlgorithms.cu Engine/KernelDynamicScene.cu Kernel/TraceResult.cu SceneTypes/Sensor.cu Engine/MicrofacetDistribution.cu Base/CudaRandom.cu Engine/TriIntersectorData.cu Engine/DifferentialGeometry.cu SceneTypes/Samples.cu Engine/Material.cu SceneTypes/Volumes.cu SceneTypes/PhaseFunction.cu Math/FresnelHelper.cu Base/Platform.cu SceneTypes/Texture.cu Engine/RoughTransmittance.cu Math/MonteCarlo.cu Engine/TriangleData.cu Math/Spectrum.cu Engine/Image_host.cu Engine/Image_ctor.cpp Engine/Mesh_compile_host.cpp Base/FileStream.cpp Engine/SpatialStructures/BVH/SplitBVHBuilder.cpp Engine/MeshLoader/BVHBuilderHelper.cpp Engine/MeshLoader/ObjParser.cpp Engine/MeshLoader/PlyParser.cpp"
 pids=()
 for f in $TUS; do
   o="obj/$(echo "$f" | tr '/' '_').o"

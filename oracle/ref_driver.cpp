@@ -454,6 +454,25 @@ int ref_write_xmsh(const char* path, const float* verts, unsigned nv, const unsi
 	return 0;
 }
 
+// OBJ / PLY -> .xmsh with the reference's OWN mesh compilers (Engine/MeshLoader/ObjParser.cpp compileobj, PlyParser.cpp compileply), framed like
+// MeshCompilerManager::Compile (Engine/MeshLoader/MeshCompiler.cpp:82-99: the MeshCompileType token first)
+int ref_compile_mesh(const char* in_path, const char* xmsh_path)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	try {
+		std::string p(in_path);
+		const bool obj = p.size() > 4 && p.substr(p.size() - 4) == ".obj", ply = p.size() > 4 && p.substr(p.size() - 4) == ".ply";
+		if (!obj && !ply) throw std::runtime_error("ref_compile_mesh: .obj or .ply expected");
+		IInStream* in = OpenFile(p);
+		FileOutputStream out(xmsh_path);
+		out << (unsigned int)MeshCompileType::Static;
+		if (obj) compileobj(*in, out); else compileply(*in, out);
+		out.Close();
+		delete in;
+	} catch (const std::exception& e) { fprintf(stderr, "ref_compile_mesh: %s\n", e.what()); return 1; }
+	return 0;
+}
+
 // layout facts the product's .xmsh reader hard-codes (cudatracerlib_b200/csrc/xmsh.cpp), checked against the reference headers
 static_assert(sizeof(Material) == 3344 && offsetof(Material, NodeLightIndex) == 68 && offsetof(Material, bsdf) == 512 && sizeof(FixedString<64>) == 68, "Material layout");
 static_assert(sizeof(MeshPartLight) == 48 && offsetof(MeshPartLight, L) == 36 && sizeof(Texture) == 208 && sizeof(AABB) == 24 && sizeof(BSDF) == 56, "xmsh record layout");

@@ -118,3 +118,10 @@ def write_xmsh(path, verts, indices, sub_tris, mats, emissive=None):
     rc = f(str(path).encode(), _p(v), len(v), _p(i), len(i), _p(st), len(st), C.cast(arr, C.c_void_p), _p(e) if e is not None else None)
     if rc:
         raise RuntimeError("ref_write_xmsh failed")
+
+
+def compile_mesh(in_path, xmsh_path):
+    """OBJ / PLY -> .xmsh with the reference's own compilers (compileobj / compileply)."""
+    f = ref().ref_compile_mesh; f.argtypes = [C.c_char_p, C.c_char_p]
+    if f(os.fsencode(str(in_path)), os.fsencode(str(xmsh_path))):
+        raise RuntimeError("ref_compile_mesh failed")

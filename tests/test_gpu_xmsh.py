@@ -37,3 +37,16 @@ def test_imported_scene_on_gpu(built_lib, orc):
     wref, wrays, _ = orc.render_wavefront(s.view, 64, 64, n_passes=1, max_path_length=6)
     assert (rel_l2(w.readAccumulator()["rgb"], wref["rgb"]) <= 1e-3).mean() >= 0.99 and w.getRaysInLastPass() == wrays
     t.close(); w.close()
+
+
+def test_obj_scene_on_gpu(built_lib, orc):
+    """The OBJ front end feeding the CUDA path: same image as the oracle, and as the reference's own PathTrace on the reference-compiled file."""
+    s = ctl.Scene.from_files(os.path.join(HERE, "golden", "obj", "room.obj"), *TWO_LIGHT_CAMERA, 64, 64)
+    t = ctl.PathTracer(64, 64); t.InitializeScene(s); t.setParameter("MaxPathLength", 6)
+    t.DoPass(True); t.DoPass(False)
+    img = t.readAccumulator()
+    ref = np.ascontiguousarray(GOLD["obj_room_image_64x64_2spp"]).view(api.PIXEL_DTYPE).reshape(64, 64)
+    assert (rel_l2(img["rgb"], ref["rgb"]) <= 1e-3).mean() >= 0.99 and np.array_equal(img["weight_sum"], ref["weight_sum"])
+    o, rays = orc.render(s.view, 64, 64, n_passes=2, max_path_length=6)
+    assert (rel_l2(img["rgb"], o["rgb"]) <= 1e-3).mean() >= 0.99 and abs(t.getTotalRays() - rays) <= 2e-3 * rays
+    t.close()

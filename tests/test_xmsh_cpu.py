@@ -118,3 +118,58 @@ def test_reader_error_paths(built_lib, tmp_path):
     expect(bytes(bad), "not a ConstantTexture")
     bad = bytearray(good); bad[4 + 24 + 4 + 4:4 + 24 + 4 + 4 + 10] = b"nosuchmat" + bytes(1)
     expect(bytes(bad), "unknown material")
+
+
+# ---- OBJ front end ---------------------------------------------------------------------------------------------------------------
+OBJ = os.path.join(HERE, "golden", "obj", "room.obj")
+OBJ_REF_XMSH = os.path.join(HERE, "golden", "obj", "room_ref.xmsh")    # the same file compiled by the reference's own compileobj
+
+
+def test_obj_import_equals_reference_compiler_output(built_lib, orc):
+    """ctl_scene_create_from_files on an .obj == reading the .xmsh that the reference's compileobj -> Mesh::CompileMesh wrote for the same
+    file: vertex de-duplication order, fan triangulation, reversed winding, the single-precision number reader (Kd 0.065 becomes
+    0.06500000507), (u, 1 - v), the file's normals, UV-driven dpdu / dpdv, material mapping, the area light -- TriangleData bit-identical,
+    images bit-identical (the trees differ: the reference's SplitBVHBuilder vs this repo's)."""
+    a = ctl.Scene.from_xmsh(OBJ_REF_XMSH, *TWO_LIGHT_CAMERA, 64, 64)
+    b = ctl.Scene.from_files(OBJ, *TWO_LIGHT_CAMERA, 64, 64)
+    assert a.n_triangles == b.n_triangles == 25 and a.view.n_materials == b.view.n_materials == 4 and a.view.num_lights == b.view.num_lights == 1
+    assert np.array_equal(a.array("tri_data"), b.array("tri_data"))
+    assert (a.array("tri_data")[:2, 5:] != 0).any() and (a.array("tri_data")[2:, 5:] == 0).all()      # only the floor carries texture coordinates
+    assert [_relevant(m) for m in _materials(a)] == [_relevant(m) for m in _materials(b)]
+    assert _materials(b)[1][4:7] == pytest.approx((0.63, 0.065, 0.05)) and _materials(b)[1][5] != np.float32(0.065)   # the reference's digit-accumulating reader, reproduced
+    assert _materials(b)[3][0] == 2 and _materials(b)[3][8] == pytest.approx(1.45) and _materials(b)[3][15] == pytest.approx(0.8)
+    assert list(a.view.box_min) == list(b.view.box_min) and list(a.view.box_max) == list(b.view.box_max)
+    assert np.allclose(a.array("light_tris")[:, :13], b.array("light_tris")[:, :13]) and np.array_equal(a.array("light_cdf_data"), b.array("light_cdf_data"))
+    ia, ra = orc.render(a.view, 64, 64, n_passes=2, max_path_length=6)
+    ib, rb_ = orc.render(b.view, 64, 64, n_passes=2, max_path_length=6)
+    assert np.array_equal(ia["rgb"].view(np.uint32), ib["rgb"].view(np.uint32)) and ra == rb_ and ia["rgb"].mean() > 0.1
+    ref = np.ascontiguousarray(GOLD["obj_room_image_64x64_2spp"]).view(api.PIXEL_DTYPE).reshape(64, 64)   # the reference's own PathTrace
+    with orc.host_arithmetic():
+        ih, _ = orc.render(b.view, 64, 64, n_passes=2, max_path_length=6)
+    assert np.array_equal(ih["rgb"].view(np.uint32), ref["rgb"].view(np.uint32))
+
+
+def test_obj_import_error_paths(built_lib, tmp_path):
+    def scene(obj_text, mtl_text=None):
+        (tmp_path / "t.obj").write_text(obj_text)
+        if mtl_text is not None:
+            (tmp_path / "t.mtl").write_text(mtl_text)
+        return ctl.Scene.from_files(tmp_path / "t.obj", *TWO_LIGHT_CAMERA, 16, 16)
+    tri = "v 0 0 0\nv 1 0 0\nv 0 1 0\n"
+    diffuse = "newmtl m\nKd 0.5 0.5 0.5\nKs 0 0 0\nillum 2\n"
+    s = scene("mtllib t.mtl\n" + tri + "usemtl m\nf 1 2 3\nf -3 -2 -1\n", diffuse)
+    assert s.n_triangles == 2 and s.view.n_materials == 1 and s.view.num_lights == 0
+    with pytest.raises(RuntimeError, match="phong"):               # the reference's default material has Ks = 0.5 -> phong, not on the hot path
+        scene(tri + "f 1 2 3\n")
+    with pytest.raises(RuntimeError, match="phong"):
+        scene("mtllib t.mtl\n" + tri + "usemtl m\nf 1 2 3\n", "newmtl m\nKd 0.5 0.5 0.5\nKs 0.2 0.2 0.2\nillum 2\n")
+    with pytest.raises(RuntimeError, match="illum 5"):
+        scene("mtllib t.mtl\n" + tri + "usemtl m\nf 1 2 3\n", "newmtl m\nillum 5\n")
+    with pytest.raises(RuntimeError, match="texture maps"):
+        scene("mtllib t.mtl\n" + tri + "usemtl m\nf 1 2 3\n", diffuse + "map_Kd wood.png\n")
+    with pytest.raises(RuntimeError, match="did not find submeshes"):
+        scene(tri)
+    with pytest.raises(RuntimeError, match="Could not open file"):
+        scene("mtllib missing.mtl\n" + tri + "f 1 2 3\n")
+    with pytest.raises(RuntimeError, match="Could not open file"):
+        ctl.Scene.from_files(tmp_path / "nope.obj", *TWO_LIGHT_CAMERA, 16, 16)
