@@ -713,6 +713,7 @@ int ctl_wavefront_pass(ctl_ctx* c, int new_trace) {
     unsigned* ctr = c->counters.p;
     CK(cudaMemsetAsync(ctr, 0, CTR_TOTAL * sizeof(unsigned), c->stream));
     CK(cudaMemsetAsync(c->w_desc.p, 0, (size_t)mpl * (n_tiles + 1) * sizeof(unsigned long long), c->stream));
+    if (c->instrumented) CK(cudaMemsetAsync(c->stats.p + 2, 0, 8 * sizeof(unsigned long long), c->stream));
     const int g_light = grid_for(c, c->shade_blocks_per_sm), g_trav = grid_for(c, c->trav_blocks_per_sm);
     uint32_t launches = 0;
     stage_mark(c, 0);
@@ -724,7 +725,16 @@ int ctl_wavefront_pass(ctl_ctx* c, int new_trace) {
         stage_mark(c, 1);
         // FinishIteration (DoubleRayBuffer.h:84-112): the primaries and the secondary rays pushed by iteration d-1
         const bool have_sec = d > 0 && c->direct;
-        if (have_sec && c->fuse_traversal && c->trav_kernel == 0) {
+        if (c->instrumented) { // visit counts for the roofline (ctl_get_visit_counts: "extension" = primaries, "shadow" = secondaries): unfused, counting builds
+            launch_intersect<2, false, true>(c, g_trav, c->stream, c->scene, (const float4*)c->w_ray.p, ctr + CTR_Q + d, 0, ctr + CTR_WORK + 2 * d, nullptr, nullptr, nullptr, nullptr, (void*)c->w_res.p, c->stats.p + 2);
+            launches++;
+            if (have_sec) {
+                stage_mark(c, 3);
+                launch_intersect<2, true, true>(c, g_trav, c->stream, c->scene, (const float4*)c->w_sec[(d - 1) & 1].p, ctr + CTR_SH + d - 1, 0, ctr + CTR_WORK + 2 * d + 1, nullptr, nullptr, nullptr, nullptr,
+                                                (void*)c->w_sres[(d - 1) & 1].p, c->stats.p + 6);
+                launches++;
+            }
+        } else if (have_sec && c->fuse_traversal && c->trav_kernel == 0) {
             k_intersect_fused_api<<<g_trav, 128, 0, c->stream>>>(c->scene, c->tune, (const float4*)c->w_ray.p, ctr + CTR_Q + d, (const float4*)c->w_sec[(d - 1) & 1].p, ctr + CTR_SH + d - 1,
                                                                   ctr + CTR_WORK + 2 * d, (void*)c->w_res.p, (void*)c->w_sres[(d - 1) & 1].p);
             launches++;

@@ -35,7 +35,8 @@ struct Sbvh {
     float root_area = 0.0f;
     float CT = 1.0f;                            // cost of a triangle test relative to a node step (CTL_SBVH_CT overrides)
     float ALPHA = 1e-5f;                        // overlap threshold for trying a spatial split, relative to the root area
-    static constexpr int OBJ_BINS = 32, SPATIAL_BINS = 64, SWEEP_BELOW = 4096, MAX_DEPTH = 48, PARALLEL_ABOVE = 8192, PARALLEL_DEPTH = 4;
+    static constexpr int OBJ_BINS = 32, SPATIAL_BINS = 64, MAX_DEPTH = 48, PARALLEL_ABOVE = 8192, PARALLEL_DEPTH = 4;
+    int SWEEP_BELOW = 4096;   // exact SAH sweep below this many references, binned above (CTL_SBVH_SWEEP overrides, experiments)
 
     V3 vert(uint32_t t, int k) const { const float* p = v9 + (size_t)t * 9 + 3 * k; return V3(p[0], p[1], p[2]); }
 
@@ -255,7 +256,7 @@ struct Sbvh {
             // slots in depth-first order) is exactly the sequential one, so the tree does not depend on the thread count
             std::vector<ctl_bvh_node> ln, rn; std::vector<uint32_t> lo_, ro_; std::vector<uint8_t> ll, rl;
             Sbvh SL{v9, max_leaf, ln, lo_, ll}, SR{v9, max_leaf, rn, ro_, rl};
-            SL.root_area = SR.root_area = root_area; SL.ALPHA = SR.ALPHA = ALPHA; SL.CT = SR.CT = CT;
+            SL.root_area = SR.root_area = root_area; SL.ALPHA = SR.ALPHA = ALPHA; SL.CT = SR.CT = CT; SL.SWEEP_BELOW = SR.SWEEP_BELOW = SWEEP_BELOW;
             int la = 0, ra = 0;
             std::thread th([&]() { la = SL.build(left, lb, 0xfffffffeu, false, depth + 1); });
             ra = SR.build(right, rb, 0xfffffffeu, false, depth + 1);
@@ -386,6 +387,7 @@ static void build_sbvh_alpha(const float* verts9, uint32_t n_tris, int max_leaf,
     }
     S.root_area = half_area(all);
     if (const char* a = getenv("CTL_SBVH_CT")) S.CT = (float)atof(a);
+    if (const char* a = getenv("CTL_SBVH_SWEEP")) S.SWEEP_BELOW = atoi(a);
     S.build(refs, all, 0xffffffffu, true, 0);
 }
 

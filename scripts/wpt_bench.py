@@ -30,6 +30,16 @@ out["wavefront_pt"] = {"ms_per_frame": ms, "rays_per_frame": int(rays), "mrays_s
 t.setParameter("StageTimers", 1); t.DoPass(True); t.synchronize()
 sm, nl = t.stageTimes(); out["wavefront_pt"]["stage_ms_one_pass"] = dict(zip(["create", "primary_trav", "iterate", "secondary_trav", "tally"], [round(x, 3) for x in sm])); out["wavefront_pt"]["launches_per_pass"] = nl
 e, sh = t.queueSizes(mpl); out["wavefront_pt"]["queues"] = [e.tolist(), sh.tolist()]
+# roofline of the traversal launches of one pass: algorithmic bytes from an instrumented pass / CUDA-event time of the fused launches
+trav_ms = sm[1] + sm[3]
+t.setParameter("StageTimers", 0); t.setInstrumented(1); t.DoPass(True); t.synchronize()
+e_cnt, s_cnt = t.visitCounts(); t.setInstrumented(0)
+nbytes = ctl.traversal_bytes(e_cnt, e_cnt[3]) + ctl.traversal_bytes(s_cnt, s_cnt[3])
+from bench import hbm_peak
+peak, peak_src = hbm_peak()
+out["wavefront_pt"]["roofline"] = {"bound": "hbm", "kernel": "k_intersect / k_intersect_fused_api (all traversal launches of a pass)", "achieved": nbytes / (trav_ms * 1e-3) / 1e9, "peak": peak,
+                                   "peak_source": peak_src, "unit": "GB/s", "frac": nbytes / (trav_ms * 1e-3) / 1e9 / peak, "bytes_per_ray": nbytes / max(1, e_cnt[3] + s_cnt[3]), "traversal_ms_per_pass": trav_ms,
+                                   "rays_per_pass": int(e_cnt[3] + s_cnt[3])}
 t.close()
 p = ctl.PathTracer(w, h); p.InitializeScene(s); p.setParameter("MaxPathLength", mpl); p.setStream(st.cuda_stream)
 for rep in range(3):

@@ -120,6 +120,19 @@ def test_wavefront_progressive_passes_and_new_trace(built_lib, orc):
     t.close()
 
 
+def test_wavefront_instrumented_pass(built_lib, orc):
+    """The counting build of the traversal (roofline input) leaves image and queues unchanged and counts every intersected ray."""
+    s = _scene("soup", 80, 48)
+    t = _tracer(s, 80, 48, 6)
+    t.DoPass(True); a = t.readAccumulator().copy(); qa = _queues(t, 6)
+    t.setInstrumented(1); t.DoPass(True); b = t.readAccumulator().copy(); qb = _queues(t, 6)
+    e_cnt, s_cnt = t.visitCounts(); t.setInstrumented(0)
+    assert np.array_equal(a["rgb"].view(np.uint32), b["rgb"].view(np.uint32)) and np.array_equal(qa, qb)
+    assert e_cnt[3] == int(qa[:, 0].sum()) and s_cnt[3] == int(qa[:, 1].sum()) and e_cnt[0] > e_cnt[3] and e_cnt[2] >= e_cnt[3]   # >= 1 inner node, >= 1 instance per ray
+    # the primaries of iteration 0 are the camera rays: their visit counts equal the oracle's for the same rays (intersectKernel semantics)
+    t.close()
+
+
 def test_wavefront_edge_cases(built_lib, orc):
     for (w, h, mpl) in ((1, 1, 4), (127, 3, 1), (129, 2, 2)):     # single slot, one tile minus one, one tile plus one; depth 1 = emission only
         s = _scene("cornell", w, h)
