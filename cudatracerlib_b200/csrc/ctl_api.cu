@@ -132,6 +132,7 @@ ctl_scene* ctl_scene_create_from_xmsh(const char* const* paths, uint32_t n_files
             if (!paths[i]) throw std::runtime_error("null path");
             const std::string pth(paths[i]);
             if (pth.size() > 4 && (pth.substr(pth.size() - 4) == ".obj" || pth.substr(pth.size() - 4) == ".OBJ")) ctlb::read_obj(paths[i], meshes[i]); // MeshCompilerManager picks the compiler by extension (MeshCompiler.cpp:21-27)
+            else if (pth.size() > 4 && (pth.substr(pth.size() - 4) == ".ply" || pth.substr(pth.size() - 4) == ".PLY")) ctlb::read_ply(paths[i], meshes[i]);
             else ctlb::read_xmsh(paths[i], meshes[i]);
             ctlb::M4 xf = ctlb::M4::identity();
             if (node_xforms) memcpy(xf.m, node_xforms + 16 * (size_t)i, 64);

@@ -183,4 +183,91 @@ void read_obj(const char* path_c, MeshInput& M) {
     if (M.indices.empty()) throw std::runtime_error("Invalid obj file, no faces: " + path);
 }
 
+// ---- PLY (Engine/MeshLoader/PlyParser.cpp compileply): ascii and binary (little / big endian) files with float x y z vertices and triangle or
+// quad faces; one red diffuse default material (PlyParser.cpp:364-368), vertex normals computed.  Kept quirks of the reference reader, needed for
+// identical output: triangles are emitted with reversed winding but quads as (2,3,0),(0,1,2); a `u` property is used for both texture
+// coordinates (:283); the binary branch reads the vertex block as consecutive x y z floats, i.e. it supports position-only vertices;
+// binary indices beyond the vertex count become 0.
+void read_ply(const char* path_c, MeshInput& M) {
+    const std::string path(path_c);
+    FILE* f = fopen(path.c_str(), "rb"); if (!f) throw std::runtime_error("Could not open file: " + path);
+    std::vector<unsigned char> data; { unsigned char buf[65536]; size_t n; while ((n = fread(buf, 1, sizeof(buf), f)) > 0) data.insert(data.end(), buf, buf + n); }
+    fclose(f);
+    size_t pos = 0;
+    auto getline = [&](std::string& line) { if (pos >= data.size()) return false; line.clear(); while (pos < data.size() && data[pos] != '\n') line.push_back((char)data[pos++]); if (pos < data.size()) pos++; if (!line.empty() && line.back() == '\r') line.pop_back(); return true; };
+    auto words = [](const std::string& line) { std::vector<std::string> w; size_t i = 0; while (i < line.size()) { while (i < line.size() && isspace((unsigned char)line[i])) i++; size_t j = i; while (j < line.size() && !isspace((unsigned char)line[j])) j++; if (j > i) w.push_back(line.substr(i, j - i)); i = j; } return w; };
+    std::string line;
+    if (!getline(line) || line.substr(0, 3) != "ply") throw std::runtime_error("not a ply file: " + path);
+    int format = -1, vertex_count = -1, face_count = -1, n_props = 0, pos_start = -1, uv_start = -1, has_pos = 0; bool has_uv = false, in_vertex = false;
+    while (getline(line)) {
+        const std::vector<std::string> w = words(line);
+        if (w.empty()) continue;
+        if (w[0] == "format" && w.size() >= 2) format = w[1] == "ascii" ? 2 : (w[1] == "binary_big_endian" ? 1 : (w[1] == "binary_little_endian" ? 0 : -1));
+        else if (w[0] == "element" && w.size() >= 3) { in_vertex = false; if (w[1] == "vertex") { vertex_count = atoi(w[2].c_str()); in_vertex = true; n_props = 0; } else if (w[1] == "face") face_count = atoi(w[2].c_str()); }
+        else if (w[0] == "property" && in_vertex) {
+            if (w.size() < 3 || w[1] == "list") throw std::runtime_error("compileply: unsupported vertex property: " + path);
+            const std::string &type = w[1], &name = w[2];
+            const bool real = type == "float" || type == "double";
+            if (name.size() == 1 && name[0] >= 'x' && name[0] <= 'z' && real) { has_pos |= 1 << (name[0] - 'x'); if (name[0] == 'x') pos_start = n_props; }
+            else if (name[0] == 'u' || (name[0] == 'v' && name.size() == 1 && real)) { has_uv = true; if (name[0] == 'u') uv_start = n_props; }
+            else if (name.find("material") != std::string::npos) throw std::runtime_error("compileply: per-vertex materials are not supported: " + path);
+            n_props++;
+        }
+        else if (w[0] == "end_header") break;
+    }
+    if (has_pos != 7 || vertex_count <= 0 || face_count <= 0 || format < 0) throw std::runtime_error("compileply: header without float x y z vertices and faces: " + path);
+    M = MeshInput();
+    M.verts.resize(vertex_count);
+    if (has_uv) M.uvs.assign((size_t)vertex_count * 2, 0.0f);
+    auto emit = [&](const uint32_t* v, int n) {
+        if (n == 3) { M.indices.push_back(v[2]); M.indices.push_back(v[1]); M.indices.push_back(v[0]); }
+        else if (n == 4) { for (int i = 2; i < 5; i++) M.indices.push_back(v[i % 4]); for (int i = 0; i < 3; i++) M.indices.push_back(v[i]); }
+        else throw std::runtime_error("compileply: faces must be triangles or quads: " + path);
+    };
+    if (format == 2) {
+        for (int v = 0; v < vertex_count; v++) {
+            if (!getline(line)) throw std::runtime_error("Passed end of file: " + path);
+            const std::vector<std::string> w = words(line);
+            if ((int)w.size() < n_props) throw std::runtime_error("compileply: short vertex line: " + path);
+            auto val = [&](int i) { return (float)atof(w[i].c_str()); };
+            M.verts[v] = V3(val(pos_start), val(pos_start + 1), val(pos_start + 2));
+            if (has_uv && uv_start >= 0) { M.uvs[2 * v] = val(uv_start); M.uvs[2 * v + 1] = val(uv_start); }
+        }
+        for (int fc = 0; fc < face_count; fc++) {
+            if (!getline(line)) throw std::runtime_error("Passed end of file: " + path);
+            const std::vector<std::string> w = words(line);
+            const int n = w.empty() ? 0 : atoi(w[0].c_str());
+            if ((int)w.size() < n + 1 || n > 4) throw std::runtime_error("compileply: faces must be triangles or quads: " + path);
+            uint32_t idx[4] = {0, 0, 0, 0}; for (int i = 0; i < n; i++) idx[i] = (uint32_t)atoi(w[1 + i].c_str());
+            emit(idx, n);
+        }
+    } else {
+        auto swap32 = [](uint32_t i) { return (i << 24) | ((i << 8) & 0xff0000u) | ((i >> 8) & 0xff00u) | (i >> 24); };
+        if (pos + (size_t)vertex_count * 12 > data.size()) throw std::runtime_error("Passed end of file: " + path);
+        for (int v = 0; v < vertex_count; v++) {
+            uint32_t b[3]; memcpy(b, &data[pos + (size_t)v * 12], 12);
+            if (format == 1) for (int k = 0; k < 3; k++) b[k] = swap32(b[k]);
+            float xyz[3]; memcpy(xyz, b, 12); M.verts[v] = V3(xyz[0], xyz[1], xyz[2]);
+        }
+        pos += (size_t)vertex_count * 12;
+        for (int fc = 0; fc < face_count; fc++) {
+            if (pos >= data.size()) throw std::runtime_error("Passed end of file: " + path);
+            const int n = data[pos];
+            if ((n != 3 && n != 4) || pos + 1 + 4 * (size_t)n > data.size()) throw std::runtime_error("compileply: faces must be triangles or quads: " + path);
+            uint32_t idx[4] = {0, 0, 0, 0};
+            for (int i = 0; i < n; i++) { memcpy(&idx[i], &data[pos + 1 + 4 * i], 4); if (format == 1) idx[i] = swap32(idx[i]); }
+            const size_t first = M.indices.size();
+            emit(idx, n);
+            for (size_t i = M.indices.size() - n; i < M.indices.size(); i++) if (M.indices[i] > (uint32_t)vertex_count) M.indices[i] = 0;   // PlyParser.cpp:349-350 (the last n indices)
+            (void)first;
+            pos += 4 * (size_t)n + 1;
+        }
+    }
+    for (uint32_t i : M.indices) if (i >= (uint32_t)vertex_count) throw std::runtime_error("compileply: vertex index out of range: " + path);
+    M.mat_index.assign(M.indices.size() / 3, 0);
+    ctl_material cm; memset(&cm, 0, sizeof(cm));
+    cm.bsdf_type = CTL_BSDF_DIFFUSE; cm.node_light_index = 0xffffffffu; cm.reflectance[0] = 1.0f; cm.alpha_u = cm.alpha_v = 0.1f; cm.eta[0] = cm.eta[1] = cm.eta[2] = 1.5f; cm.transmittance = 1.0f;
+    M.materials.push_back(cm); M.emissive.push_back(V3(0.0f));
+}
+
 } // namespace ctlb

@@ -38,6 +38,7 @@ struct MeshInput {
 
 // .xmsh (the reference's compiled-mesh format: Engine/Mesh.cpp:46-98 reader, :199-290 writer, Engine/MeshLoader/BVHBuilderHelper.cpp:129-147)
 void read_xmsh(const char* path, MeshInput& out);                                  // throws std::runtime_error
+void read_ply(const char* path, MeshInput& out);                                   // PLY (obj_import.cpp), == the reference's compileply front end
 void read_obj(const char* path, MeshInput& out);                                   // Wavefront OBJ + MTL (obj_import.cpp), == the reference's compileobj front end
 void write_xmsh(const char* path, const struct SceneStorage& S, uint32_t mesh);    // mesh `mesh` of an assembled scene
 

@@ -225,7 +225,8 @@ ctl_scene* ctl_scene_create_from_xmsh(const char* const* paths, uint32_t n_files
  * .xmsh as above; .obj (+ the .mtl it names) through this library's own OBJ front end, which reproduces what the reference's
  * compileobj -> Mesh::CompileMesh writes for the same file (vertex de-duplication order, fan triangulation, reversed winding, its
  * single-precision number reader, vertex normals, UV-driven dpdu / dpdv) for materials of the hot path: illum 2 with Ks = 0 (diffuse),
- * illum 7 / 9 (dielectric), Ke (area light).  ctl_scene_create_from_xmsh accepts the same mix (it is this function). */
+ * illum 7 / 9 (dielectric), Ke (area light); .ply (ascii, binary little / big endian; float x y z vertices, triangle / quad faces) likewise
+ * reproduces compileply (Engine/MeshLoader/PlyParser.cpp:182-371).  ctl_scene_create_from_xmsh accepts the same mix (it is this function). */
 ctl_scene* ctl_scene_create_from_files(const char* const* paths, uint32_t n_files, const float* node_xforms, const float* cam_pos,
                                        const float* cam_target, const float* cam_up, float fov_deg, int width, int height);
 /* Mesh `mesh` of a host scene as an .xmsh file: the output sequence of Mesh::CompileMesh (Engine/Mesh.cpp:278-289). */

@@ -173,3 +173,32 @@ def test_obj_import_error_paths(built_lib, tmp_path):
         scene("mtllib missing.mtl\n" + tri + "f 1 2 3\n")
     with pytest.raises(RuntimeError, match="Could not open file"):
         ctl.Scene.from_files(tmp_path / "nope.obj", *TWO_LIGHT_CAMERA, 16, 16)
+
+
+@pytest.mark.parametrize("name", ["terrain_ascii", "octa_le", "octa_be"])
+def test_ply_import_equals_reference_compiler_output(built_lib, orc, name):
+    """PLY front end (ascii with u / v properties and quads, binary little / big endian) == the .xmsh the reference's own compileply wrote for
+    the same file: TriangleData bit-identical (incl. its quad winding and u-for-both-coordinates quirks), red default material, same hits."""
+    cam = ((0, 0.3, -2.5), (0, -0.2, 0), (0, 1, 0), 50.0)
+    a = ctl.Scene.from_xmsh(os.path.join(HERE, "golden", "obj", name + "_ref.xmsh"), *cam, 32, 32)
+    b = ctl.Scene.from_files(os.path.join(HERE, "golden", "obj", name + ".ply"), *cam, 32, 32)
+    assert a.n_triangles == b.n_triangles > 0 and np.array_equal(a.array("tri_data"), b.array("tri_data"))
+    assert [_relevant(m) for m in _materials(a)] == [_relevant(m) for m in _materials(b)] == [(0, 0, 0xffffffff, (1.0, 0.0, 0.0))]
+    assert list(a.view.box_min) == list(b.view.box_min) and list(a.view.box_max) == list(b.view.box_max) and b.view.num_lights == 0
+    rng = np.random.default_rng(2)
+    rays = np.zeros(3000, api.RAY_DTYPE); rays["o"] = rng.uniform(-1, 1, (3000, 3)) + np.array([0, 1.5, 0]); d = rng.normal(size=(3000, 3)); d[:, 1] = -abs(d[:, 1])
+    rays["d"] = d / np.linalg.norm(d, axis=1, keepdims=True); rays["tmax"] = 3e38
+    ha, hb = orc.trace_rays(a.view, rays), orc.trace_rays(b.view, rays)
+    assert np.array_equal(ha["tri_idx"], hb["tri_idx"]) and np.array_equal(ha["dist"].view(np.uint32), hb["dist"].view(np.uint32)) and (ha["tri_idx"] != 0xffffffff).mean() > 0.05
+
+
+def test_ply_import_error_paths(built_lib, tmp_path):
+    def expect(data, text):
+        p = tmp_path / "bad.ply"; p.write_bytes(data)
+        with pytest.raises(RuntimeError, match=text):
+            ctl.Scene.from_files(p, (0, 0, -3), (0, 0, 0), (0, 1, 0), 50.0, 8, 8)
+    good = open(os.path.join(HERE, "golden", "obj", "octa_le.ply"), "rb").read()
+    expect(b"plx\n", "not a ply file")
+    expect(good[:200], "Passed end of file|triangles or quads")
+    expect(good.replace(b"property float z\n", b"property int z\n"), "float x y z")
+    expect(b"ply\nformat ascii 1.0\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\nelement face 1\nproperty list uchar int vertex_indices\nend_header\n0 0 0\n1 0 0\n0 1 0\n5 0 1 2 0 1\n", "triangles or quads")
