@@ -67,8 +67,16 @@ CTL_DEV V3 to_world(const Frame& f, V3 v) { return f.s * v.x + f.t * v.y + f.n *
 // 256-bit read-only global load (sm_100a LDG.E.256): one 64-byte BVH node = 2 of these = 2 L1 wavefronts per lane
 // instead of 4 with float4 loads.  `p` must be 32-byte aligned.
 struct F8 { float4 lo, hi; };
+#ifndef CTL_NODE_EVICT_LAST
+#define CTL_NODE_EVICT_LAST 0 // experiment: L1::evict_last on the BVH node loads (keep the top of the tree resident against the ray / triangle streams)
+#endif
 CTL_DEV F8 ldg256(const void* p) {
     F8 r;
+#if CTL_NODE_EVICT_LAST
+    asm("ld.global.nc.L1::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w) : "l"(p));
+    return r;
+#endif
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w) : "l"(p));
     return r;
@@ -81,7 +89,11 @@ CTL_DEV F8 ldg256(const void* p) {
 #define CTL_STREAM_HINTS 0 // measured: L1::no_allocate on triangle/queue loads = -1 % on C4 but +66 % on C2 extension rays (coherent rays re-use triangles through L1)
 #endif
 CTL_DEV float4 ldg_stream(const float4* p) {
-#if CTL_STREAM_HINTS
+#if CTL_STREAM_HINTS == 2
+    float4 r;
+    asm("ld.global.nc.L1::evict_first.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+#elif CTL_STREAM_HINTS
     float4 r;
     asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
@@ -90,7 +102,11 @@ CTL_DEV float4 ldg_stream(const float4* p) {
 #endif
 }
 CTL_DEV uint32_t ldg_stream(const uint32_t* p) {
-#if CTL_STREAM_HINTS
+#if CTL_STREAM_HINTS == 2
+    uint32_t r;
+    asm("ld.global.nc.L1::evict_first.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+#elif CTL_STREAM_HINTS
     uint32_t r;
     asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
     return r;
