@@ -263,3 +263,17 @@ def test_split_bvh_builder_vs_plain_sah(built_lib, orc, monkeypatch):
     # config 4 the oracle measures 95 vs 140 inner nodes and 12 vs 25 triangle tests per ray (profiles/r01u_sbvh_builder.log)
     assert cb[0] < 0.95 * ca[0] and cb[1] < 0.85 * ca[1], (ca, cb)
     assert api.traversal_bytes(cb, len(rays)) < 0.95 * api.traversal_bytes(ca, len(rays))
+
+
+def test_double_ray_buffer_header_compiles_for_sm100a(built_lib, tmp_path):
+    """include/b200_double_ray_buffer.cuh + its test application cross-compile for sm_100a without a GPU (the run is in tests/test_gpu_wavefront_pt.py)."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not found")
+    obj = tmp_path / "drb_check.o"
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-fmad=false", "-I", os.path.join(root, "include"), "-c",
+                    os.path.join(root, "tests", "drb_check.cu"), "-o", str(obj)], check=True)
+    sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", str(obj)], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass and "ATOM" in sass.upper()   # the queue counters are device atomics
