@@ -145,6 +145,24 @@ def test_wavefront_edge_cases(built_lib, orc):
         t.close()
 
 
+def test_wavefront_degenerate_scenes(built_lib, orc):
+    """No lights (every path contributes zero, queues still evolve like the oracle's) and a camera that sees nothing (every primary misses:
+    one iteration, then an empty queue through all remaining launches)."""
+    from scene_fixtures import _mat
+    V = np.array([(-1, 0, -1), (1, 0, -1), (1, 0, 1), (-1, 0, 1)], np.float32)
+    I = np.array([0, 2, 1, 0, 3, 2], np.uint32)
+    for cam, sees in ((((0, 1.5, -2.0), (0, 0, 0), (0, 1, 0), 60.0), True), (((0, 1.5, -2.0), (0, 3.0, -4.0), (0, 1, 0), 30.0), False)):
+        s = ctl.Scene.from_mesh(V, I, np.array([0, 0], np.uint8), [_mat()], np.zeros((1, 3), np.float32), *cam, 40, 30)
+        assert s.view.num_lights == 0
+        t = _tracer(s, 40, 30, 5, rr=1)
+        t.DoPass(True); t.DoPass(False)
+        img = t.readAccumulator()
+        ref, rays, q = orc.render_wavefront(s.view, 40, 30, n_passes=2, max_path_length=5, rr_start=1)
+        assert np.all(img["rgb"] == 0) and (img["weight_sum"] == 2).all() and np.array_equal(_queues(t, 5), q) and t.getTotalRays() == rays
+        assert (q[1, 0] > 0) == sees and q[:, 1].sum() == 0
+        t.close()
+
+
 def test_cpp_adapter_wavefront(built_lib, tmp_path):
     """ctlb200::WavefrontPathTracer (include/b200_path_tracer.hpp) renders through the same entry point."""
     import subprocess
