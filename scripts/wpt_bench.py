@@ -54,4 +54,18 @@ st.synchronize()
 ms = e0.elapsed_time(e1) / frames
 out["path_tracer"] = {"ms_per_frame": ms, "rays_per_frame": int(p.getRaysInLastPass()), "mrays_s": p.getRaysInLastPass() / ms / 1e3}
 p.close()
+# the reference's own WavefrontPathTracer code on the host cores (oracle/_ref: its pathIterateKernel + DoubleRayBuffer on one thread, the
+# intersections on all threads) on a bounded sample: the same scene at 1/16 of the pixels, one pass
+try:
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    import time
+    import ref_binding as rb
+    if rb.available():
+        sw, sh_ = w // 4, h // 4
+        s_small = ctl.Scene(kind, sw, sh_)
+        t0 = time.perf_counter(); _, crays, _ = rb.render_wavefront(s_small.view, sw, sh_, n_passes=4, max_path_length=mpl); dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": crays / dt / 1e6, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "reference",
+                               "sample": f"{sw}x{sh_} frame of the same scene, 4 passes, depth {mpl}, {crays} rays in {dt:.2f} s (queue kernels on one thread, intersections on all)"}
+except Exception as e:   # the baseline is optional here
+    out["cpu_baseline"] = {"unavailable": str(e)}
 print(json.dumps(out))
