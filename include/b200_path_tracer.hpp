@@ -31,6 +31,14 @@ public:
         if (!h_) throw std::runtime_error(ctl_last_error());
         check(ctl_scene_get_view(h_, &view_));
     }
+    // flat import of compiled / source mesh files (.xmsh, .obj, .ply), one node per file: ctl_scene_create_from_files
+    Scene(const std::vector<std::string>& paths, const float cam_pos[3], const float cam_target[3], const float cam_up[3], float fov_deg, int width, int height,
+          const float* node_xforms = nullptr) {
+        std::vector<const char*> p; for (auto& s : paths) p.push_back(s.c_str());
+        h_ = ctl_scene_create_from_files(p.data(), (uint32_t)p.size(), node_xforms, cam_pos, cam_target, cam_up, fov_deg, width, height);
+        if (!h_) throw std::runtime_error(ctl_last_error());
+        check(ctl_scene_get_view(h_, &view_));
+    }
     ~Scene() { ctl_scene_destroy(h_); }
     Scene(const Scene&) = delete; Scene& operator=(const Scene&) = delete;
     const ctl_scene_view& view() const { return view_; }

@@ -619,9 +619,12 @@ def test_cpp_example_driver(built_lib, tmp_path):
     r = subprocess.run(["g++", "-std=c++17", "-O1", _os.path.join(root, "examples", "main.cpp"), "-I" + _os.path.join(root, "include"), "-L" + libdir, "-lctl_b200",
                         "-Wl,-rpath," + libdir, "-o", exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    r = subprocess.run([exe, "1", "4", "96", "64", out], capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout + r.stderr
-    data = open(out, "rb").read()
-    assert data.startswith(b"P6\n96 64\n255\n") and len(data) == len(b"P6\n96 64\n255\n") + 96 * 64 * 3
-    px = np.frombuffer(data[len(b"P6\n96 64\n255\n"):], np.uint8)
-    assert px.mean() > 20 and "4 passes" in r.stdout
+    obj = _os.path.join(root, "tests", "golden", "obj", "room.obj")
+    for args, tag in ((["cornell7", "4", "96x64", out], "PT, 4 passes"), ([obj, "3", "PT_Wave", "tonemap", "96x64", out], "PT_Wave, 3 passes")):
+        r = subprocess.run([exe] + args, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        data = open(out, "rb").read()
+        assert data.startswith(b"P6\n96 64\n255\n") and len(data) == len(b"P6\n96 64\n255\n") + 96 * 64 * 3
+        px = np.frombuffer(data[len(b"P6\n96 64\n255\n"):], np.uint8)
+        assert px.mean() > 20 and tag in r.stdout, r.stdout
+    assert subprocess.run([exe, "no_such_thing"], capture_output=True, text=True).returncode == 2
