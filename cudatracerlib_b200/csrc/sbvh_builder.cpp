@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdio>
 #include <thread>
+#include <exception>
 
 namespace ctlb {
 namespace {
@@ -258,9 +259,11 @@ struct Sbvh {
             Sbvh SL{v9, max_leaf, ln, lo_, ll}, SR{v9, max_leaf, rn, ro_, rl};
             SL.root_area = SR.root_area = root_area; SL.ALPHA = SR.ALPHA = ALPHA; SL.CT = SR.CT = CT; SL.SWEEP_BELOW = SR.SWEEP_BELOW = SWEEP_BELOW;
             int la = 0, ra = 0;
-            std::thread th([&]() { la = SL.build(left, lb, 0xfffffffeu, false, depth + 1); });
-            ra = SR.build(right, rb, 0xfffffffeu, false, depth + 1);
+            std::exception_ptr err;   // an exception in the helper thread (e.g. bad_alloc) is re-thrown here instead of terminating the process
+            std::thread th([&]() { try { la = SL.build(left, lb, 0xfffffffeu, false, depth + 1); } catch (...) { err = std::current_exception(); } });
+            try { ra = SR.build(right, rb, 0xfffffffeu, false, depth + 1); } catch (...) { th.join(); throw; }
             th.join();
+            if (err) std::rethrow_exception(err);
             a = append(ln, lo_, ll, la, node_idx);
             b = append(rn, ro_, rl, ra, node_idx);
         } else {
