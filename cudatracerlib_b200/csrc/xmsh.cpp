@@ -35,6 +35,7 @@ constexpr size_t RC_REFL = 64, RC_ALPHA_U = 272, RC_ALPHA_V = 480, RC_ETA = 688,
 constexpr size_t DI_DISPERSION = 64, DI_TRANS = 128, DI_REFL = 336, DISP_PAYLOAD = 16, CAUCHY_B = 8, CAUCHY_C = 12;
 constexpr uint32_t TAG_DIFFUSE = 1, TAG_DIELECTRIC = 3, TAG_ROUGHCONDUCTOR = 7, TAG_CONST_TEX = 2, TAG_CAUCHY = 1;
 constexpr size_t LIGHT_SIZE = 48, LIGHT_L = 36;
+constexpr size_t MAT_USED_BSSRDF = 88, MAT_NORMAL_MAP_USED = 2656, MAT_HEIGHT_MAP_USED = 2880, MAT_ALPHA_STATE = 3104; // the other things the path reads
 
 struct File {
     FILE* f; std::string path;
@@ -82,6 +83,11 @@ ctl_material decode_material(const unsigned char* m, std::string& name) {
     out.node_light_index = 0xffffffffu;
     const unsigned char* b = m + MAT_BSDF;
     out.flags = b[BSDF_TWO_SIDED] ? CTL_MAT_TWO_SIDED : 0u;
+    // features of the reference's getBsdfSample / traceRay that the B200 path does not have must not be dropped silently
+    if (u32_at(m, MAT_NORMAL_MAP_USED)) throw std::runtime_error("material '" + name + "': normal maps are outside the B200 path");
+    if (u32_at(m, MAT_HEIGHT_MAP_USED)) throw std::runtime_error("material '" + name + "': height maps are outside the B200 path");
+    if (u32_at(m, MAT_ALPHA_STATE)) throw std::runtime_error("material '" + name + "': alpha maps are outside the B200 path");
+    if (u32_at(m, MAT_USED_BSSRDF)) throw std::runtime_error("material '" + name + "': subsurface scattering (bssrdf) is outside the B200 path");
     const uint32_t tag = u32_at(m, MAT_BSDF_TAG);
     out.transmittance = 1.0f; out.alpha_u = out.alpha_v = 0.1f; out.eta[0] = out.eta[1] = out.eta[2] = 1.5f;
     if (tag == TAG_DIFFUSE) {

@@ -475,6 +475,8 @@ int ref_compile_mesh(const char* in_path, const char* xmsh_path)
 
 // layout facts the product's .xmsh reader hard-codes (cudatracerlib_b200/csrc/xmsh.cpp), checked against the reference headers
 static_assert(sizeof(Material) == 3344 && offsetof(Material, NodeLightIndex) == 68 && offsetof(Material, bsdf) == 512 && sizeof(FixedString<64>) == 68, "Material layout");
+static_assert(offsetof(Material, usedBssrdf) == 88 && offsetof(Material, NormalMap) == 2656 && offsetof(Material, HeightMap) == 2880 && offsetof(Material, AlphaMap) == 3104 &&
+              offsetof(AlphaBlendData, state) == 0 && offsetof(Material::mpHlp, used) == 0, "Material map-usage fields");
 static_assert(sizeof(MeshPartLight) == 48 && offsetof(MeshPartLight, L) == 36 && sizeof(Texture) == 208 && sizeof(AABB) == 24 && sizeof(BSDF) == 56, "xmsh record layout");
 static_assert(offsetof(BSDF, m_enableTwoSided) == 52 && offsetof(diffuse, m_reflectance) == 64 && offsetof(ConstantTexture, val) == 8, "BSDF layout");
 static_assert(offsetof(roughconductor, m_specularReflectance) == 64 && offsetof(roughconductor, m_alphaU) == 272 && offsetof(roughconductor, m_alphaV) == 480 &&

@@ -116,6 +116,9 @@ def test_reader_error_paths(built_lib, tmp_path):
     expect(bytes(bad), "BSDF type 9 is not supported")
     bad = bytearray(good); bad[m0 + 528 + 64:m0 + 528 + 68] = struct.pack("I", 3)   # ImageTexture as the diffuse reflectance
     expect(bytes(bad), "not a ConstantTexture")
+    for off, text in ((2656, "normal maps"), (2880, "height maps"), (3104, "alpha maps"), (88, "bssrdf")):
+        bad = bytearray(good); bad[m0 + off:m0 + off + 4] = struct.pack("I", 1)
+        expect(bytes(bad), text)
     bad = bytearray(good); bad[4 + 24 + 4 + 4:4 + 24 + 4 + 4 + 10] = b"nosuchmat" + bytes(1)
     expect(bytes(bad), "unknown material")
 
