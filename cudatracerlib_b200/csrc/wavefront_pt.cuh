@@ -6,7 +6,7 @@
 // in slot k).  The reference's GPU order depends on the hardware scheduler and a path's random numbers are keyed by its queue slot
 // (cu:59-60), so its output is not reproducible run to run; the serial order is the deterministic member of its possible outputs, and is what
 // the reference's own kernel text produces on one host thread (oracle/_ref).  Here that order is produced IN PARALLEL: the iterate kernel
-// compacts with a single-pass chained scan (decoupled look-back over 128-slot tiles, tile ids handed out by an atomic ticket so a tile only
+// compacts with a single-pass chained scan (decoupled look-back over 256-slot tiles, tile ids handed out by an atomic ticket so a tile only
 // waits on tiles that already run), so slot ranks -- and with them every random number, the secondary-ray indices and the image -- equal the
 // serial schedule's.  The queue is compacted in place like the reference's (one payload / ray / result buffer + two secondary buffers): a tile
 // writes only into slots of tiles <= itself, all of which have been read before its look-back completes.
@@ -34,9 +34,10 @@ struct WptBuf {
 
 struct WptParams { int pathDepth, iterationIdx, maxPathDepth, rrStart; };
 
-constexpr int WPT_TILE = 128;
+constexpr int WPT_TILE = 256;
 #ifndef WPT_MIN_BLOCKS
-#define WPT_MIN_BLOCKS 8 // 64 registers, 8 blocks per SM: measured +2 % over 6 (80 registers) on C2, profiles/r01v_wpt_occupancy_ab.log
+#define WPT_MIN_BLOCKS 4 // 256-slot tiles x 4 blocks per SM at 64 registers: measured +2 % (occupancy) and +1.3 % (half as many tiles to look back over) over
+                         // 128 x 6 at 80 registers on C2, profiles/r01v_wpt_occupancy_ab.log
 #endif
 
 CTL_DEV unsigned short enc_normal_dev(V3 v) { // NormalizedFloat3ToUchar2_Spherical, Math/Compression.h:12-18

@@ -134,7 +134,7 @@ def test_wavefront_instrumented_pass(built_lib, orc):
 
 
 def test_wavefront_edge_cases(built_lib, orc):
-    for (w, h, mpl) in ((1, 1, 4), (127, 3, 1), (129, 2, 2)):     # single slot, one tile minus one, one tile plus one; depth 1 = emission only
+    for (w, h, mpl) in ((1, 1, 4), (127, 3, 1), (129, 2, 2), (255, 1, 3), (257, 1, 3)):     # single slot, around the 256-slot tile size; depth 1 = emission only
         s = _scene("cornell", w, h)
         t = _tracer(s, w, h, mpl)
         t.DoPass(True)
