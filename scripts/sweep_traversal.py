@@ -17,7 +17,8 @@ def run():
 t.setParameter("TraversalKernel", 1); print("simple", run())
 t.setParameter("TraversalKernel", 0)
 res = []
-for thT, thL, thF, ns in itertools.product((2, 4, 8), (4, 8), (8, 12, 16), (3, 4, 6, 8, 12)):
+grid = ((1, 2, 4), (4, 8, 16), (4, 8, 16), (2, 4, 6, 8)) if len(sys.argv) > 2 and sys.argv[2] == "wide" else ((2, 4, 8), (4, 8), (8, 12, 16), (3, 4, 6, 8, 12))
+for thT, thL, thF, ns in itertools.product(*grid):
     for k, v in (("TravThT", thT), ("TravThL", thL), ("TravThF", thF), ("TravThNExit", ns)): t.setParameter(k, v)
     r = run(); res.append((r, thT, thL, thF, ns))
 res.sort()
