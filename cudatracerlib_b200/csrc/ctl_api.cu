@@ -55,7 +55,7 @@ struct ctl_ctx {
     int n_sm = 148;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     // parameters (Integrators/PathTracer.h:10-20)
-    int max_path_length = 50, rr_start = 5, direct = 1, regularization = 0, sort_mode = 0, stage_timers = 0, capture_bounce = 0, trav_kernel = 0, trav_blocks_per_sm = 8, shade_blocks_per_sm = 8, smem_carveout = -1, fuse_traversal = 1, warp_blocks = 0;
+    int max_path_length = 50, rr_start = 5, direct = 1, regularization = 0, sort_mode = 0, stage_timers = 0, capture_bounce = 0, trav_kernel = 0, trav_blocks_per_sm = 8, shade_blocks_per_sm = 8, smem_carveout = -1, fuse_traversal = 1, warp_blocks = 0, pass_stride = 1, pass_phase = 0;
     // scene
     DevBuf<ctl_bvh_node> d_scene_nodes, d_bvh_nodes; DevBuf<ctl_woop_tri> d_woop; DevBuf<uint32_t> d_tri_index; DevBuf<ctl_tri_data> d_tri_data;
     DevBuf<ctl_mesh> d_meshes; DevBuf<ctl_node> d_nodes; DevBuf<float> d_xf, d_inv_xf; DevBuf<ctl_material> d_materials; DevBuf<ctl_light> d_lights;
@@ -361,6 +361,8 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "FuseTraversal") c->fuse_traversal = v != 0;
     else if (k == "PixelVarianceBuffer") c->variance_buffer = v != 0;
     else if (k == "WarpPixelBlocks") c->warp_blocks = v != 0;
+    else if (k == "PassStride") { if (v < 1) return set_err("PassStride must be >= 1"); c->pass_stride = v; }   // multi-GPU by pass: this context renders passes PassPhase + k * PassStride
+    else if (k == "PassPhase") { if (v < 0) return set_err("PassPhase must be >= 0"); c->pass_phase = v; }
     else if (k == "TraversalKernel") { if (v < 0 || v > 1) return set_err("TraversalKernel must be 0 or 1"); c->trav_kernel = v; }
     else if (k == "TravThT") c->tune.th_t = v; else if (k == "TravThL") c->tune.th_l = v; else if (k == "TravThF") c->tune.th_f = v;
     else if (k == "TravThNExit") c->tune.th_n_exit = v;
@@ -379,7 +381,7 @@ int ctl_get_param_i(ctl_ctx* c, const char* key, int* v) {
     std::string k(key);
     if (k == "MaxPathLength") *v = c->max_path_length; else if (k == "RRStartDepth") *v = c->rr_start; else if (k == "Direct") *v = c->direct;
     else if (k == "Regularization") *v = c->regularization; else if (k == "SortMode") *v = c->sort_mode; else if (k == "StageTimers") *v = c->stage_timers;
-    else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables; else if (k == "FuseTraversal") *v = c->fuse_traversal; else if (k == "PixelVarianceBuffer") *v = c->variance_buffer;
+    else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables; else if (k == "FuseTraversal") *v = c->fuse_traversal; else if (k == "PixelVarianceBuffer") *v = c->variance_buffer; else if (k == "PassStride") *v = c->pass_stride; else if (k == "PassPhase") *v = c->pass_phase;
     else if (k == "TraversalBlocksPerSM") *v = c->trav_blocks_per_sm; else return set_err("unknown parameter key: " + k);
     return 0;
 }
@@ -454,9 +456,10 @@ int ctl_upload_samples(ctl_ctx* c, const float* d1, const float* d2) {
 static int generate_tables(ctl_ctx* c, uint32_t first, int n) {
     if (ensure_tables(c, n)) return 1;
     if (c->device_tables) {
-        if (c->gen_pos_dev != first) { // re-synchronise the device stream position (rare: mode switch / user tables)
-            CK(cudaMemcpyAsync(c->d_states.p, c->d_states0.p, (size_t)ctlb::kNumSeq * 6 * 4, cudaMemcpyDeviceToDevice, c->stream));
-            for (uint32_t p = 0; p < first; p++) k_gen_tables<<<ctlb::kNumSeq / 128, 128, 0, c->stream>>>(c->d_states.p, c->d_jump.p, 1, c->d_tab1.p, (float2*)c->d_tab2.p);
+        if (c->gen_pos_dev != first) { // re-synchronise the device stream position (mode switch / user tables / strided passes): skip forward, or restart
+            uint32_t from = c->gen_pos_dev;
+            if (from > first) { CK(cudaMemcpyAsync(c->d_states.p, c->d_states0.p, (size_t)ctlb::kNumSeq * 6 * 4, cudaMemcpyDeviceToDevice, c->stream)); from = 0; }
+            for (uint32_t p = from; p < first; p++) k_gen_tables<<<ctlb::kNumSeq / 128, 128, 0, c->stream>>>(c->d_states.p, c->d_jump.p, 1, c->d_tab1.p, (float2*)c->d_tab2.p);
         }
         k_gen_tables<<<ctlb::kNumSeq / 128, 128, 0, c->stream>>>(c->d_states.p, c->d_jump.p, n, c->d_tab1.p, (float2*)c->d_tab2.p);
         CK(cudaGetLastError());
@@ -464,7 +467,7 @@ static int generate_tables(ctl_ctx* c, uint32_t first, int n) {
     } else {
         if (ensure_host_tables(c, n)) return 1;
         CK(cudaEventSynchronize(c->h_tab_free));
-        if (c->gen_pos_host != first) { c->gen.reset(); for (uint32_t p = 0; p < first; p++) c->gen.next_pass(c->h_tab1, c->h_tab2); }
+        if (c->gen_pos_host != first) { uint32_t from = c->gen_pos_host; if (from > first) { c->gen.reset(); from = 0; } for (uint32_t p = from; p < first; p++) c->gen.next_pass(c->h_tab1, c->h_tab2); }
         for (int p = 0; p < n; p++) c->gen.next_pass(c->h_tab1 + TAB1 * p, c->h_tab2 + TAB2 * p);
         CK(cudaMemcpyAsync(c->d_tab1.p, c->h_tab1, TAB1 * 4 * n, cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemcpyAsync(c->d_tab2.p, c->h_tab2, TAB2 * 4 * n, cudaMemcpyHostToDevice, c->stream));
@@ -699,8 +702,9 @@ int ctl_wavefront_pass(ctl_ctx* c, int new_trace) {
     CK(cudaSetDevice(c->device));
     CK(cudaEventRecord(c->ev_start, c->stream));
     if (new_trace) { CK(cudaMemsetAsync(c->accum, 0, (size_t)c->w * c->h * 7 * sizeof(float), c->stream)); c->passes_done = 0; }
+    const uint32_t pass_index = (uint32_t)c->pass_phase + (uint32_t)c->pass_stride * c->passes_done;   // which pass of the (possibly shared) frame this is
     if (c->user_tables) c->user_tables = false;
-    else if (generate_tables(c, c->passes_done, 1)) return 1;
+    else if (generate_tables(c, pass_index, 1)) return 1;
     c->scene.d1 = c->d_tab1.p; c->scene.d2 = (const float2*)c->d_tab2.p;
     c->scene.img_w = c->w; c->scene.img_h = c->h;
     const size_t n = (size_t)c->w * c->h;
@@ -751,7 +755,7 @@ int ctl_wavefront_pass(ctl_ctx* c, int new_trace) {
         }
         stage_mark(c, 2);
         B.sec_out = c->w_sec[d & 1].p; B.sec_res = c->w_sres[(d - 1) & 1].p;
-        const WptParams P = {d, (int)c->passes_done + 1, mpl, c->rr_start}; // m_uPassesDone++ precedes DoRender (Kernel/Tracer.h:231-232)
+        const WptParams P = {d, (int)pass_index + 1, mpl, c->rr_start}; // m_uPassesDone++ precedes DoRender (Kernel/Tracer.h:231-232)
         unsigned long long* desc = c->w_desc.p + (size_t)d * (n_tiles + 1);
         if (c->direct) k_wpt_iterate<true><<<n_tiles, WPT_TILE, 0, c->stream>>>(c->scene, P, B, ctr + CTR_Q + d, ctr + CTR_Q + d + 1, ctr + CTR_SH + d, desc, n_tiles, c->accum);
         else k_wpt_iterate<false><<<n_tiles, WPT_TILE, 0, c->stream>>>(c->scene, P, B, ctr + CTR_Q + d, ctr + CTR_Q + d + 1, ctr + CTR_SH + d, desc, n_tiles, c->accum);

@@ -46,3 +46,33 @@ class DistributedFrame:
         if self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return int(t.item())
+
+
+class DistributedPasses:
+    """Frames of a whole-frame integrator (WavefrontPathTracer: its queue slots are pixel indices, so the image cannot be tiled) shared by PASS
+    index: rank r renders passes r, r + world, r + 2 world, ... of the frame into its own accumulator, then the same single reduce.  Passes are
+    independent given their index (sample tables and the sampler skip are functions of it), so every pass is exactly the one a single GPU
+    would render; only the order of the per-pixel additions differs.  On the GPU: `tracer.setParameter("PassStride", world);
+    tracer.setParameter("PassPhase", rank)` and `render_pass = lambda p, new_trace: tracer.DoPass(new_trace)`; in the CPU tests the oracle
+    renders pass `p`."""
+
+    def __init__(self, accum, render_pass, rays_of_last_frame, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.accum, self.render_pass, self.rays_of_last_frame, self.group = accum, render_pass, rays_of_last_frame, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def passes_of_rank(self, spp):
+        return list(range(self.rank, spp, self.world))
+
+    def frame(self, spp, reduce=True):
+        mine = self.passes_of_rank(spp)
+        if not mine:
+            self.accum.zero_()          # fewer passes than ranks: this rank contributes zeros
+        for k, p in enumerate(mine):
+            self.render_pass(p, k == 0)
+        if reduce and self.world > 1:
+            self.dist.reduce(self.accum, dst=0, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    total_rays = DistributedFrame.total_rays

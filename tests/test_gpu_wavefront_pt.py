@@ -163,6 +163,36 @@ def test_wavefront_degenerate_scenes(built_lib, orc):
         t.close()
 
 
+def test_wavefront_pass_stride_and_phase(built_lib, orc):
+    """Multi-GPU by pass index on one device: contexts with PassStride = 2 and PassPhase = 0 / 1 render passes {0, 2} and {1, 3} of the frame that
+    a third context renders alone; every strided pass is bit-identical to the same pass of the plain sequence, the summed accumulators equal the
+    4-pass frame, ray counts add up (cudatracerlib_b200.DistributedPasses does this across ranks, tests/test_multirank_cpu.py)."""
+    w, h, mpl = 72, 48, 6
+    s = _scene("cornell7", w, h)
+    a = _tracer(s, w, h, mpl)
+    per_pass = []
+    prev = np.zeros((h, w, 3), np.float32)
+    for p in range(4):
+        a.DoPass(p == 0); acc = a.readAccumulator()["rgb"].copy(); per_pass.append(acc - prev); prev = acc
+    full = a.readAccumulator().copy(); rays_full = a.getTotalRays()
+    parts, rays = [], 0
+    for phase in (0, 1):
+        t = _tracer(s, w, h, mpl); t.setParameter("PassStride", 2); t.setParameter("PassPhase", phase)
+        t.DoPass(True); first = t.readAccumulator()["rgb"].copy()
+        ref, _, _ = orc.render_wavefront(s.view, w, h, n_passes=1, pass_first=phase, max_path_length=mpl)
+        assert (rel_l2(first, ref["rgb"]) <= 1e-3).mean() >= 0.99
+        if phase == 0:
+            assert np.array_equal(first.view(np.uint32), per_pass[0].view(np.uint32))       # pass 0 is pass 0
+        t.DoPass(False)
+        parts.append(t.readAccumulator().copy()); rays += t.getTotalRays()
+        assert t.getNumPassesDone() == 2
+        t.close()
+    total = parts[0]["rgb"] + parts[1]["rgb"]
+    assert np.allclose(total, full["rgb"], rtol=1e-5, atol=1e-6) and np.array_equal(parts[0]["weight_sum"] + parts[1]["weight_sum"], full["weight_sum"])
+    assert rays == rays_full
+    a.close()
+
+
 def test_cpp_adapter_wavefront(built_lib, tmp_path):
     """ctlb200::WavefrontPathTracer (include/b200_path_tracer.hpp) renders through the same entry point."""
     import subprocess
