@@ -307,7 +307,9 @@ int ctl_render_passes_tiled(ctl_ctx*, int new_trace, int n_passes, int tile_w, i
  *    the reference's own wavefront integrator, second consumer of the intersect kernel.  Same parameters as the reference
  *    class ("Direct", "MaxPathLength", "RRStartDepth", WavefrontPathTracer.h:32-42).  One pass = one path per pixel; results equal the
  *    reference's algorithm run in the serial order of its queue atomics (see csrc/wavefront_pt.cuh).  Asynchronous.
- *    ctl_get_queue_sizes afterwards: ext[i] = primary rays intersected before iteration i, shadow[i] = secondary rays pushed by iteration i. */
+ *    ctl_get_queue_sizes afterwards: ext[i] = primary rays intersected before iteration i, shadow[i] = secondary rays pushed by iteration i.
+ *    "PassStride" / "PassPhase" (ctl_set_param_i, default 1 / 0): the k-th pass since the last new trace is pass PassPhase + k * PassStride
+ *    of the frame (sample tables, sampler skip) -- several devices share a frame by pass index and sum their accumulators. */
 int ctl_wavefront_pass(ctl_ctx*, int new_trace);
 /* Device copy-back of sample-table set `table_set` (0 .. passes of the last batch - 1) for verification. */
 int ctl_read_sample_tables(ctl_ctx*, int table_set, float* d1, float* d2);
