@@ -119,6 +119,8 @@ def lib():
     L.ctl_scene_create_from_xmsh.restype = vp
     L.ctl_scene_create_from_xmsh.argtypes = [C.POINTER(C.c_char_p), u32, vp, vp, vp, vp, C.c_float, i32, i32]
     L.ctl_scene_write_xmsh.argtypes = [vp, u32, C.c_char_p]
+    L.ctl_scene_set_node_transform.argtypes = [vp, u32, vp]
+    L.ctl_update_scene_nodes.argtypes = [vp, C.POINTER(SceneView)]
     L.ctl_scene_create_from_files.restype = vp
     L.ctl_scene_create_from_files.argtypes = [C.POINTER(C.c_char_p), u32, vp, vp, vp, vp, C.c_float, i32, i32]
     L.ctl_scene_get_mesh_triangles.argtypes = [vp, u32, vp, C.POINTER(C.c_uint32)]
@@ -218,6 +220,12 @@ class Scene:
         _check(lib().ctl_scene_get_view(self._h, C.byref(self.view)))
         return self
 
+    def setNodeTransform(self, node, xf):
+        """DynamicScene::SetNodeTransform: new row-major 4x4 local-to-world matrix of instance `node`; refreshes `self.view`."""
+        m = np.ascontiguousarray(xf, np.float32).reshape(16)
+        _check(lib().ctl_scene_set_node_transform(self._h, int(node), _ptr(m)))
+        _check(lib().ctl_scene_get_view(self._h, C.byref(self.view)))
+
     def mesh_triangles(self, mesh=0):
         """(nt, 3, 3) float32 source triangles of one mesh, in TriangleData order."""
         n = C.c_uint32(0)
@@ -285,6 +293,11 @@ class PathTracer:
     def InitializeScene(self, scene):
         self._scene = scene
         _check(lib().ctl_upload_scene(self._ctx, C.byref(scene.view))); self._new_trace = True
+
+    def UpdateSceneNodes(self, scene):
+        """After Scene.setNodeTransform: re-upload only the node level (ctl_update_scene_nodes)."""
+        self._scene = scene
+        _check(lib().ctl_update_scene_nodes(self._ctx, C.byref(scene.view)))
 
     def setParameter(self, key, value):
         _check(lib().ctl_set_param_i(self._ctx, key.encode(), int(value)))

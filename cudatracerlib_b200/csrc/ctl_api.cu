@@ -166,6 +166,15 @@ int ctl_scene_get_mesh_triangles(const ctl_scene* s, uint32_t mesh, float* verts
     if (verts9_out) memcpy(verts9_out, v.data(), v.size() * sizeof(float));
     return 0;
 }
+// == DynamicScene::SetNodeTransform (Engine/DynamicScene.cpp:433-443): new local-to-world matrix of one instance; the node level is re-assembled (scene-level
+// BVH = BVHRebuilder's job, inverse matrix, the node's area lights -> RecomputeShape, scene box, ray epsilon).  Mesh BVHs, Woop triangles and TriangleData are
+// untouched.  Views obtained before are invalidated: call ctl_scene_get_view and ctl_upload_scene (or ctl_update_scene_nodes) again.
+int ctl_scene_set_node_transform(ctl_scene* s, uint32_t node, const float* xf16) {
+    if (!s || !xf16) return set_err("null argument");
+    if (node >= s->S.node_inputs.size()) return set_err("no such node");
+    try { memcpy(s->S.node_inputs[node].xf.m, xf16, 64); ctlb::assemble_nodes(s->S); return 0; }
+    catch (const std::exception& e) { return set_err(e.what()); }
+}
 int ctl_scene_get_view(const ctl_scene* s, ctl_scene_view* out) { if (!s || !out) return set_err("null argument"); s->S.fill_view(out); return 0; }
 void ctl_scene_destroy(ctl_scene* s) { delete s; }
 void ctl_encode_woop(const float v0[3], const float v1[3], const float v2[3], ctl_woop_tri* out) {
@@ -417,6 +426,28 @@ int ctl_upload_scene(ctl_ctx* c, const ctl_scene_view* v) {
     S.camera = v->camera; S.ray_eps = v->ray_eps; S.scene_start = v->scene_start_node; S.n_nodes = v->n_nodes;
     S.img_w = c->w; S.img_h = c->h;
     c->has_scene = true;
+    return 0;
+}
+
+// Node-level half of ctl_upload_scene for a view whose meshes are the ones already uploaded: nodes, transforms, scene-level BVH, lights, box, epsilon,
+// camera -- what changes when instances move (a few KB instead of the whole scene; the reference re-uploads through Stream<T>::UpdateInvalidated).
+int ctl_update_scene_nodes(ctl_ctx* c, const ctl_scene_view* v) {
+    if (!c || !v) return set_err("null argument");
+    if (!c->has_scene) return set_err("no scene uploaded");
+    if (v->n_bvh_nodes != c->d_bvh_nodes.n && v->n_bvh_nodes > c->d_bvh_nodes.n) return set_err("the view has other meshes than the uploaded scene: use ctl_upload_scene");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(c->d_scene_nodes.upload(v->scene_bvh_nodes, v->n_scene_bvh_nodes)); CK(c->d_nodes.upload(v->nodes, v->n_nodes));
+    CK(c->d_xf.upload(v->node_xf, (size_t)v->n_nodes * 16)); CK(c->d_inv_xf.upload(v->node_inv_xf, (size_t)v->n_nodes * 16));
+    CK(c->d_materials.upload(v->materials, v->n_materials)); CK(c->d_lights.upload(v->lights, v->n_lights_buf));
+    CK(c->d_light_tris.upload(v->light_tris, v->n_light_tris)); CK(c->d_light_cdf.upload(v->light_cdf_data, v->n_light_cdf_data));
+    DScene& S = c->scene;
+    S.scene_nodes = (const float4*)c->d_scene_nodes.p; S.nodes = c->d_nodes.p; S.node_xf = (const float4*)c->d_xf.p; S.node_inv_xf = (const float4*)c->d_inv_xf.p;
+    S.materials = c->d_materials.p; S.lights = c->d_lights.p; S.light_tris = c->d_light_tris.p; S.light_cdf_data = c->d_light_cdf.p;
+    S.num_lights = v->num_lights;
+    memcpy(S.light_indices, v->light_indices, sizeof(S.light_indices)); memcpy(S.light_cdf, v->light_cdf, sizeof(S.light_cdf));
+    for (int k = 0; k < 3; k++) { S.box_min[k] = v->box_min[k]; const float e = v->box_max[k] - v->box_min[k]; S.box_inv_extent[k] = e > 0 ? 1.0f / e : 0.0f; }
+    S.camera = v->camera; S.ray_eps = v->ray_eps; S.scene_start = v->scene_start_node; S.n_nodes = v->n_nodes;
     return 0;
 }
 

@@ -265,6 +265,18 @@ void assemble_scene(const std::vector<MeshInput>& meshes, const std::vector<Node
         S.meshes.push_back(km);
     }
     S.mesh_boxes = mesh_box;
+    S.node_inputs = nodes;
+    for (const MeshInput& M : meshes) { S.mesh_n_materials.push_back((uint32_t)M.materials.size()); S.mesh_emissive.push_back(M.emissive); }
+    S.cam_pos = cam_pos; S.cam_target = cam_target; S.cam_up = cam_up; S.cam_fov = fov_deg; S.cam_w = width; S.cam_h = height;
+    assemble_nodes(S);
+}
+
+void assemble_nodes(SceneStorage& S) {
+    const std::vector<NodeInput>& nodes = S.node_inputs;
+    const std::vector<Box>& mesh_box = S.mesh_boxes;
+    S.nodes.clear(); S.node_xf.clear(); S.node_inv_xf.clear(); S.scene_bvh.clear(); S.lights.clear(); S.light_tris.clear(); S.light_cdf_data.clear();
+    S.box = Box();
+    for (ctl_material& m : S.materials) m.node_light_index = 0xffffffffu;
     // nodes
     std::vector<Box> node_box(nodes.size());
     for (size_t ni = 0; ni < nodes.size(); ni++) {
@@ -296,10 +308,11 @@ void assemble_scene(const std::vector<MeshInput>& meshes, const std::vector<Node
     }
     // area lights: one DiffuseLight per (node, emissive material), DynamicScene.cpp:689-711
     for (size_t ni = 0; ni < nodes.size(); ni++) {
-        const MeshInput& M = meshes[nodes[ni].mesh];
-        const ctl_mesh& km = S.meshes[nodes[ni].mesh];
-        for (size_t m = 0; m < M.materials.size(); m++) {
-            V3 L = m < M.emissive.size() ? M.emissive[m] : V3(0.0f);
+        const uint32_t mesh_id = nodes[ni].mesh;
+        const ctl_mesh& km = S.meshes[mesh_id];
+        const std::vector<V3>& emissive = S.mesh_emissive[mesh_id];
+        for (size_t m = 0; m < S.mesh_n_materials[mesh_id]; m++) {
+            V3 L = m < emissive.size() ? emissive[m] : V3(0.0f);
             if (L.x == 0 && L.y == 0 && L.z == 0) continue;
             ctl_node& kn = S.nodes[ni];
             if (kn.n_lights >= 2) throw std::runtime_error("Node already has maximum number of area lights!");
@@ -310,11 +323,10 @@ void assemble_scene(const std::vector<MeshInput>& meshes, const std::vector<Node
             lt.cdf_offset = (uint32_t)S.light_cdf_data.size();
             lt.node_idx = (uint32_t)ni;
             lt.count = 0;
-            const bool pre = !M.pre_tri_data.empty();
-            uint32_t nt = pre ? (uint32_t)M.pre_tri_data.size() : (uint32_t)M.indices.size() / 3;
+            const uint32_t nt = (mesh_id + 1 < S.meshes.size() ? S.meshes[mesh_id + 1].tri_offset : (uint32_t)S.tri_data.size()) - km.tri_offset;
             M4 xf = nodes[ni].xf;
             for (uint32_t t = 0; t < nt; t++) {
-                const uint32_t tm = pre ? ((M.pre_tri_data[t].w[1] >> 16) & 0xffu) : M.mat_index[t]; // TriangleData::getMatIndex, TriangleData.h:40-44
+                const uint32_t tm = (S.tri_data[km.tri_offset + t].w[1] >> 16) & 0xffu; // TriangleData::getMatIndex, TriangleData.h:40-44
                 if (tm != m) continue;
                 ctl_light_tri lt3; memset(&lt3, 0, sizeof(lt3));
                 // first woop slot referencing this triangle
@@ -354,7 +366,7 @@ void assemble_scene(const std::vector<MeshInput>& meshes, const std::vector<Node
         float pdf = 1.0f / accum;
         S.light_cdf[i] = (i > 0 ? S.light_cdf[i - 1] : 0.0f) + pdf;
     }
-    make_camera(cam_pos, cam_target, cam_up, fov_deg, width, height, &S.camera);
+    make_camera(S.cam_pos, S.cam_target, S.cam_up, S.cam_fov, S.cam_w, S.cam_h, &S.camera);
     S.ray_eps = 1e-4f * length(S.box.hi - S.box.lo); // DynamicScene.cpp:587
 }
 

@@ -55,6 +55,11 @@ struct SceneStorage {
     std::vector<ctl_tri_data> tri_data;
     std::vector<ctl_mesh> meshes;
     std::vector<Box> mesh_boxes;                   // per mesh: local AABB (Mesh::m_sLocalBox)
+    // what the node level is (re)assembled from (assemble_nodes): instances, per-mesh material counts / emission, camera
+    std::vector<NodeInput> node_inputs;
+    std::vector<uint32_t> mesh_n_materials;
+    std::vector<std::vector<V3>> mesh_emissive;
+    V3 cam_pos, cam_target, cam_up; float cam_fov = 60.0f; int cam_w = 0, cam_h = 0;
     std::vector<std::vector<float>> mesh_verts9;   // per mesh: 9 floats per triangle (for BVH rebuilds, e.g. on the GPU)
     std::vector<ctl_node> nodes;
     std::vector<float> node_xf, node_inv_xf;
@@ -106,6 +111,10 @@ V3 shading_normal_at(const ctl_tri_data& td, const M4& local_to_world, float u, 
 void assemble_scene(const std::vector<MeshInput>& meshes, const std::vector<NodeInput>& nodes, V3 cam_pos, V3 cam_target,
                     V3 cam_up, float fov_deg, int width, int height, SceneStorage& out);
 void make_camera(V3 pos, V3 target, V3 up, float fov_deg, int w, int h, ctl_camera* cam);
+// Node level of a scene whose meshes are assembled: nodes, transforms, scene-level BVH, area lights (world-space ShapeSets), light CDF, scene box,
+// ray epsilon, camera -- everything that changes when an instance moves (DynamicScene::SetNodeTransform + BVHRebuilder, Engine/DynamicScene.cpp:433-443).
+// Re-runnable: ctl_scene_set_node_transform edits S.node_inputs and calls it again.
+void assemble_nodes(SceneStorage& S);
 
 // synthetic scenes
 void make_scene(int kind, int width, int height, uint32_t seed, int n_hint, SceneStorage& out);

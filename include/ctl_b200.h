@@ -234,6 +234,10 @@ int  ctl_scene_write_xmsh(const ctl_scene*, uint32_t mesh, const char* path);
 /* Source triangles of mesh `mesh` of a host scene built here (9 floats per triangle, in TriangleData order); verts9_out may be NULL to query
  * *n_tris.  For export / BVH-rebuild tooling (the reference keeps them only inside its mesh compilers, Engine/Mesh.cpp:199-290). */
 int  ctl_scene_get_mesh_triangles(const ctl_scene*, uint32_t mesh, float* verts9_out, uint32_t* n_tris);
+/* == DynamicScene::SetNodeTransform (Engine/DynamicScene.cpp:433-443) on a host scene: new row-major local-to-world float4x4 of instance `node`.  The
+ * node level is re-assembled (scene-level BVH as BVHRebuilder would, inverse matrices, the node's area lights as RecomputeShape would, scene box,
+ * ray epsilon); mesh BVHs / Woop triangles / TriangleData are untouched.  Views obtained before the call are invalidated. */
+int  ctl_scene_set_node_transform(ctl_scene*, uint32_t node, const float* xf16);
 int  ctl_scene_get_view(const ctl_scene*, ctl_scene_view* out);
 void ctl_scene_destroy(ctl_scene*);
 /* GPU construction of one mesh BVH in the reference layout (LBVH: Morton codes, hand-written radix sort, Karras radix tree,
@@ -274,6 +278,9 @@ int ctl_set_param_i(ctl_ctx*, const char* key, int value);
 int ctl_get_param_i(ctl_ctx*, const char* key, int* value);
 /* == UpdateKernel scene half (Kernel/TraceHelper.cu:182-217): host view copied to HBM */
 int ctl_upload_scene(ctl_ctx*, const ctl_scene_view*);
+/* Node-level half of ctl_upload_scene, for a view that differs from the uploaded one only above the meshes (instance transforms, scene-level BVH,
+ * lights, box, epsilon, camera): what DynamicScene's Stream<T>::UpdateInvalidated re-uploads after SetNodeTransform.  Synchronises the stream. */
+int ctl_update_scene_nodes(ctl_ctx*, const ctl_scene_view*);
 /* == UpdateKernel sampler half / GenerateNewRandomSequences; host tables, async H2D */
 int ctl_upload_samples(ctl_ctx*, const float* d1, const float* d2);
 /* == __internal__IntersectBuffers (Kernel/TraceHelper.cu:736-746). Device pointers,

@@ -50,3 +50,23 @@ def test_obj_scene_on_gpu(built_lib, orc):
     o, rays = orc.render(s.view, 64, 64, n_passes=2, max_path_length=6)
     assert (rel_l2(img["rgb"], o["rgb"]) <= 1e-3).mean() >= 0.99 and abs(t.getTotalRays() - rays) <= 2e-3 * rays
     t.close()
+
+
+def test_node_transform_update_on_gpu(built_lib, orc):
+    """Moving an instance and re-uploading only the node level (ctl_update_scene_nodes) renders like a full upload of the moved scene."""
+    files = [XMSH, os.path.join(HERE, "golden", "obj", "room.obj")]
+    cam = ((1.2, 0, -4.0), (1.2, 0, 0), (0, 1, 0), 60.0)
+    x0 = np.stack([np.eye(4, dtype=np.float32)] * 2); x0[1, 0, 3] = 2.5
+    x1 = x0.copy(); x1[1] = np.array([[0.8, 0, 0.6, 2.7], [0, 1, 0, 0.2], [-0.6, 0, 0.8, 0.3], [0, 0, 0, 1]], np.float32)
+    moved = ctl.Scene.from_files(files, *cam, 64, 40, node_xforms=x1)
+    s = ctl.Scene.from_files(files, *cam, 64, 40, node_xforms=x0)
+    t = ctl.PathTracer(64, 40); t.InitializeScene(s); t.setParameter("MaxPathLength", 5)
+    t.DoPass(True); before = t.readAccumulator().copy()
+    s.setNodeTransform(1, x1[1]); t.UpdateSceneNodes(s)
+    t.DoPass(True); after = t.readAccumulator().copy()
+    full = ctl.PathTracer(64, 40); full.InitializeScene(moved); full.setParameter("MaxPathLength", 5)
+    full.DoPass(True); ref = full.readAccumulator()
+    assert np.array_equal(after["rgb"].view(np.uint32), ref["rgb"].view(np.uint32)) and not np.array_equal(before["rgb"], after["rgb"])
+    o, _ = orc.render(moved.view, 64, 40, n_passes=1, max_path_length=5)
+    assert (rel_l2(after["rgb"], o["rgb"]) <= 1e-3).mean() >= 0.99
+    t.close(); full.close()

@@ -205,3 +205,30 @@ def test_ply_import_error_paths(built_lib, tmp_path):
     expect(good[:200], "Passed end of file|triangles or quads")
     expect(good.replace(b"property float z\n", b"property int z\n"), "float x y z")
     expect(b"ply\nformat ascii 1.0\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\nelement face 1\nproperty list uchar int vertex_indices\nend_header\n0 0 0\n1 0 0\n0 1 0\n5 0 1 2 0 1\n", "triangles or quads")
+
+
+def test_set_node_transform_equals_building_with_that_transform(built_lib, orc, tmp_path):
+    """ctl_scene_set_node_transform (DynamicScene::SetNodeTransform): moving an instance re-assembles the node level -- scene-level BVH, inverse
+    matrices, the node's area-light ShapeSets, scene box, ray epsilon -- exactly as if the scene had been imported with that transform; the mesh
+    level is untouched."""
+    cam = ((1.2, 0, -4.0), (1.2, 0, 0), (0, 1, 0), 60.0)
+    x0 = np.stack([np.eye(4, dtype=np.float32)] * 3); x0[1, 0, 3] = 2.5; x0[2, 1, 3] = 2.2
+    x1 = x0.copy()
+    a = 0.6
+    x1[1] = np.array([[np.cos(a), 0, np.sin(a), 2.8], [0, 0.7, 0, -0.3], [-np.sin(a), 0, np.cos(a), 0.4], [0, 0, 0, 1]], np.float32)
+    files = [XMSH, OBJ, XMSH]
+    A = ctl.Scene.from_files(files, *cam, 48, 32, node_xforms=x1)
+    B = ctl.Scene.from_files(files, *cam, 48, 32, node_xforms=x0)
+    before = {n: B.array(n).copy() for n in ("bvh_nodes", "woop", "tri_index", "tri_data", "meshes")}
+    assert not np.array_equal(A.array("node_xf"), B.array("node_xf"))
+    B.setNodeTransform(1, x1[1])
+    for n in ("scene_bvh_nodes", "nodes", "node_xf", "node_inv_xf", "light_tris", "light_cdf_data", "bvh_nodes", "woop", "tri_index", "tri_data", "meshes"):
+        assert np.array_equal(A.array(n).view(np.uint32), B.array(n).view(np.uint32)), n
+    for n, v in before.items():
+        assert np.array_equal(B.array(n).view(np.uint32), v.view(np.uint32)), n                     # mesh level untouched
+    assert list(A.view.box_min) == list(B.view.box_min) and list(A.view.box_max) == list(B.view.box_max) and A.view.ray_eps == B.view.ray_eps
+    assert A.view.scene_start_node == B.view.scene_start_node and A.view.num_lights == B.view.num_lights == 5
+    ia, ra = orc.render(A.view, 48, 32, n_passes=1, max_path_length=4); ib, rb_ = orc.render(B.view, 48, 32, n_passes=1, max_path_length=4)
+    assert np.array_equal(ia["rgb"].view(np.uint32), ib["rgb"].view(np.uint32)) and ra == rb_
+    with pytest.raises(RuntimeError, match="no such node"):
+        B.setNodeTransform(7, np.eye(4))
