@@ -976,13 +976,22 @@ void orc_render(const ctl_scene_view* S, int w, int h, int x0, int y0, int x1, i
 // through the 16-byte traversalResult, i.e. with 16-bit barycentrics (TraceHelper.cu:44-60); the previous normal is the 16-bit spherical
 // code (cu:94,137); the sample is splatted at the un-jittered half-precision pixel coordinate (cu:40-41,161).
 // queue_sizes (may be NULL): [2*i] primary, [2*i+1] secondary rays intersected before iteration i of the last pass.
+// visit_counts (may be NULL; summed over all passes): [0..2] inner nodes / triangle tests / instance leaves of the primary queries, [3] primary rays,
+// [4..7] the same for the secondary rays traced the way the CUDA path traces them (any hit against tmax = dDist (1 - eps): the same occlusion
+// predicate as the reference's closest-hit test, see csrc/wavefront_pt.cuh) -- the roofline's algorithmic bytes for this integrator.
+void orc_render_wavefront_counted(const ctl_scene_view* Sp, int w, int h, int pass_first, int n_passes, int max_path_length, int rr_start, int direct,
+                                  ctl_pixel_data* img, uint64_t* rays_out, uint32_t* queue_sizes, uint64_t* visit_counts);
 void orc_render_wavefront(const ctl_scene_view* Sp, int w, int h, int pass_first, int n_passes, int max_path_length, int rr_start, int direct,
                           ctl_pixel_data* img, uint64_t* rays_out, uint32_t* queue_sizes) {
+    orc_render_wavefront_counted(Sp, w, h, pass_first, n_passes, max_path_length, rr_start, direct, img, rays_out, queue_sizes, nullptr);
+}
+void orc_render_wavefront_counted(const ctl_scene_view* Sp, int w, int h, int pass_first, int n_passes, int max_path_length, int rr_start, int direct,
+                                  ctl_pixel_data* img, uint64_t* rays_out, uint32_t* queue_sizes, uint64_t* visit_counts) {
     const ctl_scene_view& S = *Sp;
     struct Payload { Spec throughput; uint16_t x, y; Spec L, directF; float dDist; uint32_t dIdx; bool specular_bounce; float bsdf_pdf; uint32_t prev_normal; }; // WavefrontPathTracer.h:11-22
     const size_t N = (size_t)w * h;
     std::vector<Payload> pay(N); std::vector<ctl_traversal_ray> ray(N), sec_in(N), sec_out(N); std::vector<ctl_traversal_result> res(N), sec_res(N);
-    std::vector<float> d1((size_t)N_SEQ * SEQ_LEN), d2((size_t)N_SEQ * SEQ_LEN * 2);
+    std::vector<float> d1((size_t)N_SEQ * SEQ_LEN), d2((size_t)N_SEQ * SEQ_LEN * 2), sec_tmax(N);
     Xorwow st; xorwow_init(1234, 7539414, 0, st);
     for (int p = 0; p < pass_first; p++) fill_tables(st, d1.data(), d2.data());
     uint64_t rays = 0;
@@ -1006,6 +1015,15 @@ void orc_render_wavefront(const ctl_scene_view* Sp, int w, int h, int pass_first
             // FinishIteration (DoubleRayBuffer.h:84-112): intersect the primaries and the new secondaries, swap the secondary buffers
             orc_intersect(Sp, (int)n_pay, ray.data(), res.data(), 0);
             if (n_sec) orc_intersect(Sp, (int)n_sec, sec_out.data(), sec_res.data(), 0);
+            if (visit_counts) { // counting replay of the same queries (primaries as they are; secondaries in the CUDA path's any-hit form)
+                Counters cp = {0, 0, 0}, cs = {0, 0, 0};
+                for (uint32_t i = 0; i < n_pay; i++) { Hit hh; hh.dist = ray[i].tmax; hh.u = hh.v = 0; hh.tri = hh.node = UINT_MAX;
+                    trace(S, mk(ray[i].o[0], ray[i].o[1], ray[i].o[2]), mk(ray[i].d[0], ray[i].d[1], ray[i].d[2]), ray[i].tmin, ray[i].tmin, hh, &cp, false); }
+                for (uint32_t i = 0; i < n_sec; i++) { Hit hh; hh.dist = sec_tmax[i]; hh.u = hh.v = 0; hh.tri = hh.node = UINT_MAX;
+                    trace(S, mk(sec_out[i].o[0], sec_out[i].o[1], sec_out[i].o[2]), mk(sec_out[i].d[0], sec_out[i].d[1], sec_out[i].d[2]), sec_out[i].tmin, sec_out[i].tmin, hh, &cs, true); }
+                visit_counts[0] += cp.inner; visit_counts[1] += cp.tris; visit_counts[2] += cp.inst; visit_counts[3] += n_pay;
+                visit_counts[4] += cs.inner; visit_counts[5] += cs.tris; visit_counts[6] += cs.inst; visit_counts[7] += n_sec;
+            }
             rays += (uint64_t)n_pay + n_sec;
             if (queue_sizes && p == n_passes - 1) { queue_sizes[2 * pathDepth] = n_pay; queue_sizes[2 * pathDepth + 1] = n_sec; }
             const uint32_t n_fetch = n_pay; n_pay = 0; n_sec = 0;
@@ -1075,7 +1093,7 @@ void orc_render_wavefront(const ctl_scene_view* Sp, int w, int h, int pass_first
                                 const float weight = power_heuristic(directPdf, bsdfPdf);
                                 payload.directF = smulf(smul(smul(payload.throughput, value), bsdfVal), weight);
                                 payload.dDist = dRec.dist;
-                                if (n_sec < (uint32_t)N) { payload.dIdx = n_sec; sec_out[n_sec] = mk_ray(bRec.dg.P, dRec.d); n_sec++; } // insertSecondaryRay, DoubleRayBuffer.h:166-177
+                                if (n_sec < (uint32_t)N) { payload.dIdx = n_sec; sec_out[n_sec] = mk_ray(bRec.dg.P, dRec.d); sec_tmax[n_sec] = payload.dDist * (1 - S.ray_eps); n_sec++; } // insertSecondaryRay, DoubleRayBuffer.h:166-177
                             }
                         }
                         payload.prev_normal = enc_normal(bRec.dg.sys.n);

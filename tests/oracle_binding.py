@@ -185,13 +185,16 @@ def path_probe(view, w, x, y, pass_index=0, max_path_length=8, rr_start=5, direc
     oracle().orc_path_probe(C.byref(view), w, x, y, pass_index, max_path_length, rr_start, direct, _p(rgb), C.byref(rays)); return rgb, rays.value
 
 
-def render_wavefront(view, w, h, n_passes=1, pass_first=0, max_path_length=8, rr_start=5, direct=1, img=None):
-    """WavefrontPathTracer restatement (serial queue order).  Returns (image, rays, queue sizes [max_path_length, 2] of the last pass)."""
+def render_wavefront(view, w, h, n_passes=1, pass_first=0, max_path_length=8, rr_start=5, direct=1, img=None, counts=False):
+    """WavefrontPathTracer restatement (serial queue order).  Returns (image, rays, queue sizes [max_path_length, 2] of the last pass
+    [, visit counts: primary inner / tris / inst / rays, secondary (any-hit form) inner / tris / inst / rays])."""
     if img is None:
         img = np.zeros((h, w), PIXEL_DTYPE)
-    rays = np.zeros(1, np.uint64); q = np.zeros((max_path_length, 2), np.uint32)
-    oracle().orc_render_wavefront(C.byref(view), w, h, pass_first, n_passes, max_path_length, rr_start, direct, _p(img), _p(rays), _p(q))
-    return img, int(rays[0]), q
+    rays = np.zeros(1, np.uint64); q = np.zeros((max_path_length, 2), np.uint32); cnt = np.zeros(8, np.uint64)
+    f = oracle().orc_render_wavefront_counted
+    f.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    f(C.byref(view), w, h, pass_first, n_passes, max_path_length, rr_start, direct, _p(img), _p(rays), _p(q), _p(cnt) if counts else None)
+    return (img, int(rays[0]), q, [int(x) for x in cnt]) if counts else (img, int(rays[0]), q)
 
 
 def apply_image_pipeline(img, pipeline, splat_scale=0.0):

@@ -129,7 +129,9 @@ def test_wavefront_instrumented_pass(built_lib, orc):
     e_cnt, s_cnt = t.visitCounts(); t.setInstrumented(0)
     assert np.array_equal(a["rgb"].view(np.uint32), b["rgb"].view(np.uint32)) and np.array_equal(qa, qb)
     assert e_cnt[3] == int(qa[:, 0].sum()) and s_cnt[3] == int(qa[:, 1].sum()) and e_cnt[0] > e_cnt[3] and e_cnt[2] >= e_cnt[3]   # >= 1 inner node, >= 1 instance per ray
-    # the primaries of iteration 0 are the camera rays: their visit counts equal the oracle's for the same rays (intersectKernel semantics)
+    # and the counts are the oracle's for the same queues: primaries as closest-hit queries, secondaries in their any-hit form
+    _, _, qo, cnt = orc.render_wavefront(s.view, 80, 48, n_passes=1, max_path_length=6, counts=True)
+    assert np.array_equal(qo, qa) and list(e_cnt) == cnt[:4] and list(s_cnt) == cnt[4:]
     t.close()
 
 
