@@ -261,7 +261,7 @@ inline float guard_inv(float d) { // BVHTraversal.h:16-19
 // both children tested, nearer first (swp = c1min < c0min), far pushed, a found leaf is processed
 // as soon as it is met (host branch: mask = leafAddr >= 0), box entry clamped at tmin_box.
 template <typename LEAF>
-inline bool traverse(const float* nodes4, int node_off4, int start, V3 o, V3 d, float tmin_box, float& rayT, Counters* cnt, LEAF leaf) {
+inline bool traverse(const float* nodes4, int node_off4, int start, V3 o, V3 d, float tmin_box, float& rayT, Counters* cnt, LEAF leaf, const bool* stop = nullptr) {
     const int SENT = CTL_SENTINEL;
     if (start < 0) return leaf(~start);
     bool found = false;
@@ -269,7 +269,7 @@ inline bool traverse(const float* nodes4, int node_off4, int start, V3 o, V3 d, 
     float idx = guard_inv(d.x), idy = guard_inv(d.y), idz = guard_inv(d.z);
     float oodx = o.x * idx, oody = o.y * idy, oodz = o.z * idz;
     int leafAddr = 0, nodeAddr = start;
-    while (nodeAddr != SENT) {
+    while (nodeAddr != SENT && !(stop && *stop)) { // any-hit: the first hit ends the ray at once (TraceHelper.cu:675-679), no further node is popped
         while ((unsigned)nodeAddr < (unsigned)SENT) {
             const float* n = nodes4 + (size_t)(node_off4 + nodeAddr) * 4;
             if (cnt) { cnt->inner++; if (cnt->ev) cnt->ev->push_back('N'); }
@@ -293,6 +293,7 @@ inline bool traverse(const float* nodes4, int node_off4, int start, V3 o, V3 d, 
         }
         while (leafAddr < 0) {
             found |= leaf(~leafAddr);
+            if (stop && *stop) break;
             leafAddr = nodeAddr;
             if (nodeAddr < 0) { nodeAddr = stack[sp_]; sp_--; }
         }
@@ -348,8 +349,8 @@ bool trace(const ctl_scene_view& S, V3 ori, V3 dir, float tri_lo, float box_lo, 
                 if (index & 1) break;
             }
             return found;
-        });
-    });
+        }, &stop);
+    }, &stop);
 }
 
 // ---- fillDG (TraceHelper.cu:274-307 -> TriangleData.cu:75-103) --------------
