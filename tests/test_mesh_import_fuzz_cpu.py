@@ -101,9 +101,29 @@ def test_obj_front_end_vs_reference_compiler_fuzz(built_lib, tmp_path, seed):
     rng = np.random.default_rng(1000 + seed)
     obj = str(tmp_path / "fuzz.obj")
     _random_obj(rng, obj, with_vt=seed % 3 == 1, with_vn=seed % 2 == 0)
+    txt = open(obj).read()
+    if seed % 4 == 1:
+        txt = txt.replace("\n", "\r\n")                         # CRLF line ends
+    if seed % 4 == 3:
+        txt = txt.replace(" ", "  ").replace("\n", " \n\n")      # runs of blanks, trailing blanks, empty lines
+    open(obj, "w").write(txt)
     xm = str(tmp_path / "fuzz_ref.xmsh")
     rb.compile_mesh(obj, xm)
     _same_scene(ctl.Scene.from_xmsh(xm, *CAM, 16, 16), ctl.Scene.from_files(obj, *CAM, 16, 16))
+
+
+def test_obj_tab_separated_is_rejected_like_the_reference(built_lib, tmp_path):
+    """The reference's tokenizer only knows blanks: a tab-separated file yields no submesh and is refused; same here, same message."""
+    import ref_binding as rb
+    if not rb.available():
+        pytest.skip("oracle/_ref not built")
+    obj = str(tmp_path / "fuzz.obj")
+    _random_obj(np.random.default_rng(5), obj, False, True)
+    open(obj, "w").write(open(obj).read().replace(" ", "\t"))
+    with pytest.raises(RuntimeError):
+        rb.compile_mesh(obj, str(tmp_path / "r.xmsh"))
+    with pytest.raises(RuntimeError, match="did not find submeshes"):
+        ctl.Scene.from_files(obj, *CAM, 16, 16)
 
 
 @pytest.mark.parametrize("seed", range(6))
