@@ -238,7 +238,9 @@ int  ctl_scene_get_mesh_triangles(const ctl_scene*, uint32_t mesh, float* verts9
  * node level is re-assembled (scene-level BVH as BVHRebuilder would, inverse matrices, the node's area lights as RecomputeShape would, scene box,
  * ray epsilon); mesh BVHs / Woop triangles / TriangleData are untouched.  Views obtained before the call are invalidated. */
 int  ctl_scene_set_node_transform(ctl_scene*, uint32_t node, const float* xf16);
+/* == DynamicScene::getKernelSceneData(false) (Engine/DynamicScene.cpp:567-589): the flat view of the host arrays; valid until the scene is changed or destroyed */
 int  ctl_scene_get_view(const ctl_scene*, ctl_scene_view* out);
+/* == DynamicScene::~DynamicScene (Engine/DynamicScene.cpp:219) */
 void ctl_scene_destroy(ctl_scene*);
 /* GPU construction of one mesh BVH in the reference layout (LBVH: Morton codes, hand-written radix sort, Karras radix tree,
  * bottom-up fit, <= 8-triangle leaves) -- replaces the CPU pre-process SplitBVHBuilder.cpp / BVHBuilderHelper.cpp:119 for
@@ -265,8 +267,8 @@ typedef struct ctl_ctx ctl_ctx;
 const char* ctl_last_error(void);
 /* == PathTracer ctor + TracerBase::Resize (Kernel/Tracer.h:102-109) */
 ctl_ctx* ctl_create(int device, int width, int height);
-void     ctl_destroy(ctl_ctx*);
-int      ctl_resize(ctl_ctx*, int width, int height);
+void     ctl_destroy(ctl_ctx*);                          /* == TracerBase::~TracerBase (Kernel/Tracer.h:101) + Image::Free (Engine/Image.cpp:25) */
+int      ctl_resize(ctl_ctx*, int width, int height);    /* == Tracer<true>::Resize (Kernel/Tracer.h:196-207): new PixelData / variance / queue storage, starts a new trace */
 /* == m_sParameters: "MaxPathLength" (50), "RRStartDepth" (5), "Direct" (1),
  *    "Regularization" (0, only 0 supported)  (Integrators/PathTracer.h:10-20);
  *    extras: "SortMode" (0 none, 1 material), "StageTimers" (0/1), "CaptureBounce" (0 = off),
@@ -274,8 +276,8 @@ int      ctl_resize(ctl_ctx*, int width, int height);
  *    host and copied H2D every pass like the reference's UpdateKernel), "TraversalKernel" (0 persistent, 1 simple A/B baseline), "FuseTraversal" (1 = shadow rays of bounce b and
  *    extension rays of bounce b+1 share one traversal launch),
  *    "TraversalBlocksPerSM", "TravThT/L/F", "TravThNExit" (tuning). */
-int ctl_set_param_i(ctl_ctx*, const char* key, int value);
-int ctl_get_param_i(ctl_ctx*, const char* key, int* value);
+int ctl_set_param_i(ctl_ctx*, const char* key, int value);   /* == TracerParameterCollection::setValue<int> (Kernel/TracerSettings.h:277-283) */
+int ctl_get_param_i(ctl_ctx*, const char* key, int* value);  /* == getValue<int> (Kernel/TracerSettings.h:266-272) */
 /* == UpdateKernel scene half (Kernel/TraceHelper.cu:182-217): host view copied to HBM */
 int ctl_upload_scene(ctl_ctx*, const ctl_scene_view*);
 /* Node-level half of ctl_upload_scene, for a view that differs from the uploaded one only above the meshes (instance transforms, scene-level BVH,
@@ -320,8 +322,9 @@ int ctl_render_passes_tiled(ctl_ctx*, int new_trace, int n_passes, int tile_w, i
 int ctl_wavefront_pass(ctl_ctx*, int new_trace);
 /* Device copy-back of sample-table set `table_set` (0 .. passes of the last batch - 1) for verification. */
 int ctl_read_sample_tables(ctl_ctx*, int table_set, float* d1, float* d2);
+/* == the ThrowCudaErrors(cudaDeviceSynchronize()) the reference ends every launch with (Kernel/TraceHelper.cu:745), on this context's stream only */
 int ctl_synchronize(ctl_ctx*);
-/* == Image accumulator: PixelData[w*h], reference layout. */
+/* == Image accumulator: PixelData[w*h], reference layout (Engine/Image.h:10-29, getPixelData Image.h:64). */
 int ctl_read_accum(ctl_ctx*, ctl_pixel_data* host_out);
 /* == applyImagePipeline(tracer, img, 0, 0) (Kernel/ImagePipeline/ImagePipeline.cu:14-21, 54-63): the default resolve
  * PixelData -> toSpectrum(splatScale) -> sRGB -> RGBA8 (uchar4, a = 255).  Writes w*h*4 bytes to d_rgba8 (device,
