@@ -125,6 +125,7 @@ def lib():
     L.ctl_scene_create_from_files.argtypes = [C.POINTER(C.c_char_p), u32, vp, vp, vp, vp, C.c_float, i32, i32]
     L.ctl_scene_get_mesh_triangles.argtypes = [vp, u32, vp, C.POINTER(C.c_uint32)]
     L.ctl_scene_destroy.argtypes = [vp]; L.ctl_scene_destroy.restype = None
+    L.ctl_validate_scene_view.argtypes = [C.POINTER(SceneView)]; L.ctl_validate_scene_view.restype = C.c_int
     L.ctl_bvh_build_gpu.argtypes = [i32, vp, u32, vp, vp, vp, vp, vp]
     L.ctl_scene_rebuild_bvh_gpu.argtypes = [vp, i32, vp]
     L.ctl_encode_woop.argtypes = [vp, vp, vp, vp]; L.ctl_encode_woop.restype = None
@@ -239,6 +240,10 @@ class Scene:
     def write_xmsh(self, path, mesh=0):
         """Mesh `mesh` as an .xmsh file (the output sequence of the reference's Mesh::CompileMesh)."""
         _check(lib().ctl_scene_write_xmsh(self._h, mesh, os.fsencode(path)))
+
+    def validate(self):
+        """ctl_validate_scene_view: raises RuntimeError naming the first structural problem of the view (index ranges, tree shape, stack depth)."""
+        _check(lib().ctl_validate_scene_view(C.byref(self.view)))
 
     def rebuildBVHOnGPU(self, device=0):
         """Replace every mesh BVH by one built on the GPU (ctl_scene_rebuild_bvh_gpu); returns the device build time in ms."""

@@ -107,6 +107,11 @@ ctl_scene* ctl_scene_create(int kind, int width, int height, uint32_t seed, int 
 ctl_scene* ctl_scene_create_from_mesh(const float* verts, uint32_t nv, const uint32_t* indices, uint32_t nt, const uint8_t* mat_index,
                                       const ctl_material* materials, uint32_t nm, const float* emissive, const float* cam_pos,
                                       const float* cam_target, const float* cam_up, float fov_deg, int width, int height) {
+    if (!verts || !indices || !mat_index || !materials || !cam_pos || !cam_target || !cam_up) { set_err("null argument"); return nullptr; }
+    if (!nv || !nt || !nm) { set_err("empty mesh (no vertices, triangles or materials)"); return nullptr; }
+    if (width <= 0 || height <= 0) { set_err("bad image size"); return nullptr; }
+    for (size_t i = 0; i < 3 * (size_t)nt; i++) if (indices[i] >= nv) { set_err("triangle " + std::to_string(i / 3) + ": vertex index " + std::to_string(indices[i]) + " out of range (" + std::to_string(nv) + " vertices)"); return nullptr; }
+    for (uint32_t i = 0; i < nt; i++) if (mat_index[i] >= nm) { set_err("triangle " + std::to_string(i) + ": material index " + std::to_string((unsigned)mat_index[i]) + " out of range (" + std::to_string(nm) + " materials)"); return nullptr; }
     try {
         ctlb::MeshInput M;
         for (uint32_t i = 0; i < nv; i++) M.verts.push_back(ctlb::V3(verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]));
@@ -177,6 +182,10 @@ int ctl_scene_set_node_transform(ctl_scene* s, uint32_t node, const float* xf16)
 }
 int ctl_scene_get_view(const ctl_scene* s, ctl_scene_view* out) { if (!s || !out) return set_err("null argument"); s->S.fill_view(out); return 0; }
 void ctl_scene_destroy(ctl_scene* s) { delete s; }
+int ctl_validate_scene_view(const ctl_scene_view* v) {
+    if (!v) return set_err("null argument");
+    try { ctlb::validate_view(*v); return 0; } catch (const std::exception& e) { return set_err(e.what()); }
+}
 void ctl_encode_woop(const float v0[3], const float v1[3], const float v2[3], ctl_woop_tri* out) {
     ctlb::encode_woop(ctlb::V3(v0[0], v0[1], v0[2]), ctlb::V3(v1[0], v1[1], v1[2]), ctlb::V3(v2[0], v2[1], v2[2]), out);
 }

@@ -15,6 +15,7 @@
 #include <vector>
 #include <cstdint>
 #include "../../include/ctl_b200.h"
+#include <string>
 #include "host_math.h"
 
 namespace ctlb {
@@ -115,6 +116,10 @@ void make_camera(V3 pos, V3 target, V3 up, float fov_deg, int w, int h, ctl_came
 // ray epsilon, camera -- everything that changes when an instance moves (DynamicScene::SetNodeTransform + BVHRebuilder, Engine/DynamicScene.cpp:433-443).
 // Re-runnable: ctl_scene_set_node_transform edits S.node_inputs and calls it again.
 void assemble_nodes(SceneStorage& S);
+
+// csrc/validate.cpp: structural checks of externally supplied BVHs / views (index ranges, tree shape, leaf-run end flags, stack depth); throw std::runtime_error
+int validate_mesh_bvh(const ctl_bvh_node* nodes, uint32_t n_nodes, const uint32_t* index, uint32_t n_refs, uint32_t n_tris, const std::string& what);
+void validate_view(const ctl_scene_view& v);
 
 // synthetic scenes
 void make_scene(int kind, int width, int height, uint32_t seed, int n_hint, SceneStorage& out);

@@ -1,0 +1,113 @@
+// validate.cpp -- structural check of a scene view before it reaches the GPU.
+//
+// The reference trusts its own builders and file writers: a damaged .xmsh (a child index past the node array, a leaf run without its end flag, a
+// cycle) makes its traversal (Kernel/TraceHelper.cu:88-172, Kernel/BVHTraversal.h:122-232) read out of bounds or spin.  On a GPU that is a hung
+// device, so everything that comes from outside this library (files, caller-built views) can be checked here first.  What is checked is exactly what
+// the traversal kernels rely on (csrc/device/traverse_persistent.cuh):
+//   * every inner child reference is a multiple of 4 (float4 units) inside the mesh's / the scene's node array, every node is reached at most once
+//     (the structure is a tree, so the walk terminates), no node is its own ancestor;
+//   * every leaf reference of a mesh tree points inside the mesh's reference array and its run ends (bit 0 of a leaf word) inside that array;
+//     every leaf word names a triangle of the mesh; every leaf of the scene-level tree names an existing instance;
+//   * depth(scene tree) + 1 + depth(mesh tree) + 1 fits the 64-entry traversal stack for every instance;
+//   * mesh / material / light indices of nodes, triangles and lights are in range.
+// Box planes are not examined: NaN or inverted boxes only make rays miss.
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "scene_builder.h"
+
+namespace ctlb {
+
+namespace {
+struct TreeInfo { int depth = 0; uint32_t nodes_reached = 0; };
+
+// Walks one tree of `n_nodes` nodes; leaf(ref) validates a leaf reference (already complemented).  Iterative: damaged files may be deep.
+template <typename LEAF> TreeInfo walk_tree(const ctl_bvh_node* nodes, uint32_t n_nodes, int start, const std::string& what, LEAF leaf) {
+    TreeInfo info;
+    if (start < 0) { leaf((uint32_t)~start); return info; }
+    if (start == CTL_SENTINEL) return info;
+    std::vector<unsigned char> seen(n_nodes, 0);
+    std::vector<std::pair<uint32_t, int>> todo;
+    auto enter = [&](int ref, int depth) {
+        if (ref < 0) { leaf((uint32_t)~ref); return; }
+        if (ref == CTL_SENTINEL) return;   // single-primitive root: the second child is the sentinel (SplitBVHBuilder.cpp:176-189)
+        if ((ref & 3) || (uint32_t)ref / 4 >= n_nodes) throw std::runtime_error(what + ": child reference " + std::to_string(ref) + " outside the node array (" + std::to_string(n_nodes) + " nodes)");
+        const uint32_t i = (uint32_t)ref / 4;
+        if (seen[i]) throw std::runtime_error(what + ": node " + std::to_string(i) + " is referenced twice (not a tree)");
+        seen[i] = 1; info.nodes_reached++;
+        todo.emplace_back(i, depth);
+    };
+    enter(start, 1);
+    while (!todo.empty()) {
+        const auto cur = todo.back(); todo.pop_back();
+        if (cur.second > info.depth) info.depth = cur.second;
+        enter(nodes[cur.first].child0, cur.second + 1);
+        enter(nodes[cur.first].child1, cur.second + 1);
+    }
+    return info;
+}
+} // namespace
+
+// Mesh level of one mesh: nodes [0, n_nodes), leaf words [0, n_refs) with triangle ids < n_tris.  Returns the tree depth.
+int validate_mesh_bvh(const ctl_bvh_node* nodes, uint32_t n_nodes, const uint32_t* index, uint32_t n_refs, uint32_t n_tris, const std::string& what) {
+    if (!n_nodes || !n_refs) throw std::runtime_error(what + ": empty BVH");
+    // end_after[i]: a run starting at i meets an end flag before the array ends  <=>  some word in [i, n_refs) has bit 0; true for all i iff the last has
+    if (!(index[n_refs - 1] & 1u)) throw std::runtime_error(what + ": the last leaf run has no end flag");
+    for (uint32_t i = 0; i < n_refs; i++) if ((index[i] >> 1) >= n_tris) throw std::runtime_error(what + ": leaf word " + std::to_string(i) + " references triangle " + std::to_string(index[i] >> 1) + " of " + std::to_string(n_tris));
+    const TreeInfo t = walk_tree(nodes, n_nodes, 0, what, [&](uint32_t ref) {
+        if (ref >= n_refs) throw std::runtime_error(what + ": leaf reference " + std::to_string(ref) + " outside the reference array (" + std::to_string(n_refs) + ")");
+    });
+    return t.depth;
+}
+
+void validate_view(const ctl_scene_view& v) {
+    if (!v.n_nodes) return; // empty scene: every ray misses (TraceHelper.cu:92)
+    if (!v.bvh_nodes || !v.woop || !v.tri_index || !v.tri_data || !v.meshes || !v.nodes || !v.node_xf || !v.node_inv_xf || !v.materials)
+        throw std::runtime_error("scene view: null array");
+    if (v.n_woop != v.n_tri_index) throw std::runtime_error("scene view: woop / index arrays differ in length");
+    std::vector<int> mesh_depth(v.n_meshes, -1);
+    auto mesh_extent = [&](uint32_t m, uint32_t& node0, uint32_t& n_nodes, uint32_t& ref0, uint32_t& n_refs, uint32_t& n_tris) {
+        const ctl_mesh& K = v.meshes[m];
+        // arrays of a mesh end where the next mesh (in array order of its offsets) begins; meshes are appended in order by every builder here
+        uint32_t node_end = v.n_bvh_nodes, ref_end = v.n_tri_index, tri_end = v.n_tri_data;
+        for (uint32_t o = 0; o < v.n_meshes; o++) {
+            const ctl_mesh& O = v.meshes[o];
+            if (O.bvh_node_offset / 4 > K.bvh_node_offset / 4 && O.bvh_node_offset / 4 < node_end) node_end = O.bvh_node_offset / 4;
+            if (O.bvh_idx_offset > K.bvh_idx_offset && O.bvh_idx_offset < ref_end) ref_end = O.bvh_idx_offset;
+            if (O.tri_offset > K.tri_offset && O.tri_offset < tri_end) tri_end = O.tri_offset;
+        }
+        if ((K.bvh_node_offset & 3) || K.bvh_node_offset / 4 >= v.n_bvh_nodes || K.bvh_idx_offset >= v.n_tri_index || K.tri_offset >= v.n_tri_data)
+            throw std::runtime_error("scene view: mesh " + std::to_string(m) + " offsets outside the arrays");
+        if ((uint64_t)K.bvh_tri_offset != (uint64_t)K.bvh_idx_offset * 3) throw std::runtime_error("scene view: mesh " + std::to_string(m) + " woop offset is not 3 x its index offset");
+        node0 = K.bvh_node_offset / 4; n_nodes = node_end - node0; ref0 = K.bvh_idx_offset; n_refs = ref_end - ref0; n_tris = tri_end - K.tri_offset;
+    };
+    for (uint32_t m = 0; m < v.n_meshes; m++) {
+        uint32_t node0, n_nodes, ref0, n_refs, n_tris;
+        mesh_extent(m, node0, n_nodes, ref0, n_refs, n_tris);
+        mesh_depth[m] = validate_mesh_bvh(v.bvh_nodes + node0, n_nodes, v.tri_index + ref0, n_refs, n_tris, "mesh " + std::to_string(m));
+        const ctl_mesh& K = v.meshes[m];
+        if (K.mat_offset > v.n_materials) throw std::runtime_error("scene view: mesh " + std::to_string(m) + " material offset out of range");
+    }
+    std::vector<unsigned char> node_in_tree(v.n_nodes, 0);
+    const TreeInfo top = walk_tree(v.scene_bvh_nodes, v.n_scene_bvh_nodes, v.scene_start_node, "scene-level BVH", [&](uint32_t ref) {
+        if (ref >= v.n_nodes) throw std::runtime_error("scene-level BVH: leaf names instance " + std::to_string(ref) + " of " + std::to_string(v.n_nodes));
+        node_in_tree[ref] = 1;
+    });
+    for (uint32_t n = 0; n < v.n_nodes; n++) {
+        const ctl_node& N = v.nodes[n];
+        if (N.mesh_index >= v.n_meshes) throw std::runtime_error("scene view: node " + std::to_string(n) + " names mesh " + std::to_string(N.mesh_index) + " of " + std::to_string(v.n_meshes));
+        if (N.material_offset > v.n_materials) throw std::runtime_error("scene view: node " + std::to_string(n) + " material offset out of range");
+        if (node_in_tree[n] && top.depth + 1 + mesh_depth[N.mesh_index] + 1 > 64)
+            throw std::runtime_error("scene view: node " + std::to_string(n) + ": tree depths " + std::to_string(top.depth) + " + " + std::to_string(mesh_depth[N.mesh_index]) + " exceed the 64-entry traversal stack");
+    }
+    if (v.num_lights > CTL_MAX_NUM_LIGHTS) throw std::runtime_error("scene view: too many lights");
+    for (uint32_t i = 0; i < v.num_lights; i++) {
+        if (v.light_indices[i] >= v.n_lights_buf) throw std::runtime_error("scene view: light index out of range");
+        const ctl_light& L = v.lights[v.light_indices[i]];
+        if ((uint64_t)L.tri_offset + L.count > v.n_light_tris || (uint64_t)L.cdf_offset + L.count + 1 > v.n_light_cdf_data || L.node_idx >= v.n_nodes)
+            throw std::runtime_error("scene view: light " + std::to_string(i) + " ranges outside the light arrays");
+    }
+}
+
+} // namespace ctlb

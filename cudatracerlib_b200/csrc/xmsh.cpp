@@ -187,6 +187,7 @@ void read_xmsh(const char* path, MeshInput& M) {
     in.need(n_idx, 4);
     M.pre_index.resize((size_t)n_idx); in.read(M.pre_index.data(), (size_t)n_idx * 4);
     for (uint32_t w : M.pre_index) if ((w >> 1) >= n_tris) throw std::runtime_error(std::string("Mesh file parser error (leaf references a triangle out of range). ") + path);
+    validate_mesh_bvh(M.pre_nodes.data(), (uint32_t)n_nodes, M.pre_index.data(), (uint32_t)n_refs, n_tris, std::string("Mesh file parser error: ") + path); // a damaged tree must not reach the GPU
     for (const ctl_tri_data& t : M.pre_tri_data) if (((t.w[1] >> 16) & 0xffu) >= n_mats) throw std::runtime_error(std::string("Mesh file parser error (triangle references a material out of range). ") + path);
 }
 

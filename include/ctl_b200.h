@@ -242,6 +242,11 @@ int  ctl_scene_set_node_transform(ctl_scene*, uint32_t node, const float* xf16);
 int  ctl_scene_get_view(const ctl_scene*, ctl_scene_view* out);
 /* == DynamicScene::~DynamicScene (Engine/DynamicScene.cpp:219) */
 void ctl_scene_destroy(ctl_scene*);
+/* Structural check of a view that was not built by this library (hand-filled arrays, data read from elsewhere) before ctl_upload_scene: child / leaf
+ * references inside their arrays, each BVH a tree, every leaf run terminated, triangle / mesh / material / light indices in range, tree depths within the
+ * 64-entry traversal stack.  The reference trusts its builders and would read out of bounds or spin in __traceRay_internal__ (Kernel/TraceHelper.cu:88-172)
+ * on such data; the .xmsh reader runs the mesh part of this check on every file.  0 = consistent; otherwise ctl_last_error names the first problem. */
+int  ctl_validate_scene_view(const ctl_scene_view*);
 /* GPU construction of one mesh BVH in the reference layout (LBVH: Morton codes, hand-written radix sort, Karras radix tree,
  * bottom-up fit, <= 8-triangle leaves) -- replaces the CPU pre-process SplitBVHBuilder.cpp / BVHBuilderHelper.cpp:119 for
  * meshes that need (re)building at run time.  verts9: n_tris * 9 floats (host).  Outputs (host): nodes_out

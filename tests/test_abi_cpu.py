@@ -277,3 +277,87 @@ def test_double_ray_buffer_header_compiles_for_sm100a(built_lib, tmp_path):
                     os.path.join(root, "tests", "drb_check.cu"), "-o", str(obj)], check=True)
     sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", str(obj)], capture_output=True, text=True).stdout
     assert "sm_100a" in sass and "ATOM" in sass.upper()   # the queue counters are device atomics
+
+
+def test_scene_from_mesh_validates_and_survives_degenerate_geometry(built_lib, orc):
+    """ctl_scene_create_from_mesh refuses indices outside the vertex / material arrays (the reference's Mesh::CompileMesh trusts its compilers;
+    a C ABI cannot), and the mesh builder terminates with a valid tree on geometry SAH cannot separate: coincident, collinear and point
+    triangles, one far outlier, sticks through one point."""
+    mat = api.Material(); mat.type = 1
+    cam = ((0, 0, -5.0), (0, 0, 0), (0, 1, 0), 60.0, 16, 16)
+    tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    z1 = np.zeros((1, 3), np.float32)
+    for idx, mi, msg in (([0, 1, 5], [0], "vertex index 5 out of range"), ([0, 1, 2], [3], "material index 3 out of range")):
+        with pytest.raises(RuntimeError, match=msg):
+            ctl.Scene.from_mesh(tri, np.array(idx, np.uint32), np.array(mi, np.uint8), [mat], z1, *cam)
+    with pytest.raises(RuntimeError, match="empty mesh"):
+        ctl.Scene.from_mesh(tri, np.zeros(0, np.uint32), np.zeros(0, np.uint8), [mat], z1, *cam)
+    rng = np.random.default_rng(0)
+    sticks = []
+    for _ in range(600):
+        a = rng.normal(size=3) * 10
+        sticks += [a, -a + rng.normal(size=3) * 0.01, a + rng.normal(size=3) * 0.001]
+    outlier = rng.normal(size=(900, 3)); outlier[:3] *= 1e18
+    cases = {"identical": np.tile(tri, (300, 1)), "collinear": np.tile(np.array([[0, 0, 0], [1, 1, 1], [2, 2, 2]], np.float32), (60, 1)),
+             "points": np.zeros((180, 3), np.float32), "outlier": outlier, "sticks": np.array(sticks)}
+    for name, V in cases.items():
+        nt = len(V) // 3
+        s = ctl.Scene.from_mesh(V.astype(np.float32), np.arange(3 * nt, dtype=np.uint32), np.zeros(nt, np.uint8), [mat], z1, *cam)
+        v = s.view
+        assert s.n_triangles == nt and v.n_woop >= nt and 1 <= v.n_bvh_nodes <= 2 * v.n_woop, name
+        refs = s.array("tri_index")[:, 0]
+        assert set((refs >> 1).tolist()) == set(range(nt)), name            # every triangle is referenced
+        assert np.bincount(refs & 1)[1] >= 1                                # leaf terminators present
+        # a ray through the middle of every (non-degenerate) triangle finds something at or before it
+        if name in ("identical", "sticks"):
+            P = V.reshape(-1, 3, 3).astype(np.float64); c = P.mean(axis=1); n = np.cross(P[:, 1] - P[:, 0], P[:, 2] - P[:, 0])
+            ok = np.linalg.norm(n, axis=1) > 1e-12
+            n = n[ok] / np.linalg.norm(n[ok], axis=1, keepdims=True); c = c[ok]
+            rays = np.zeros(len(c), api.RAY_DTYPE); rays["o"] = c + n * 0.5; rays["d"] = -n; rays["tmax"] = 3e38
+            r = orc.trace_rays(v, rays)
+            hit = r["tri_idx"] != 0xffffffff
+            assert hit.mean() > 0.98 and (r["dist"][hit] <= 0.5 * (1 + 1e-3)).all(), (name, hit.mean())
+
+
+def test_validate_scene_view_names_the_first_problem(built_lib):
+    """ctl_validate_scene_view on views a caller filled by hand: each damaged array is reported, the untouched view passes."""
+    import ctypes as C
+    s = ctl.Scene("cornell7", 32, 32)
+    L = api.lib()
+
+    def check(field, arr, ctype, expect):
+        v = api.SceneView.from_buffer_copy(s.view)
+        keep = np.ascontiguousarray(arr)
+        setattr(v, field, C.cast(keep.ctypes.data, C.POINTER(ctype)))
+        rc = L.ctl_validate_scene_view(C.byref(v))
+        if expect is None:
+            assert rc == 0, L.ctl_last_error()
+        else:
+            assert rc != 0 and expect in L.ctl_last_error().decode(), L.ctl_last_error()
+
+    nodes = s.array("nodes")
+    check("nodes", nodes, api.Node, None)
+    bad = nodes.copy(); bad[3, 0] = 99
+    check("nodes", bad, api.Node, "node 3 names mesh 99")
+    top = s.array("scene_bvh_nodes").view(np.int32)
+    bad = top.copy(); bad[0, 12] = ~np.int32(7)                 # 7 instances: 0..6
+    check("scene_bvh_nodes", bad, api.BvhNode, "leaf names instance 7")
+    bad = top.copy(); bad[0, 13] = 0
+    check("scene_bvh_nodes", bad, api.BvhNode, "referenced twice")
+    meshes = s.array("meshes")
+    bad = meshes.copy(); bad[1, 1] += 2
+    check("meshes", bad, api.Mesh, "offsets outside the arrays")
+    bad = meshes.copy(); bad[1, 2] += 3
+    check("meshes", bad, api.Mesh, "woop offset")
+    idx = s.array("tri_index")
+    bad = idx.copy(); bad[-1, 0] &= ~np.uint32(1)
+    check("tri_index", bad, C.c_uint32, "no end flag")
+    # a chain deeper than the traversal stack: 70 inner nodes, each with a leaf and the next node
+    deep = np.zeros((70, 16), np.int32)
+    for i in range(70):
+        deep[i, 12] = ~0; deep[i, 13] = 4 * (i + 1) if i < 69 else ~0
+    v = api.SceneView.from_buffer_copy(s.view)
+    keep = np.ascontiguousarray(deep)
+    v.scene_bvh_nodes = C.cast(keep.ctypes.data, C.POINTER(api.BvhNode)); v.n_scene_bvh_nodes = 70; v.scene_start_node = 0
+    assert L.ctl_validate_scene_view(C.byref(v)) != 0 and "traversal stack" in L.ctl_last_error().decode()
+    assert L.ctl_validate_scene_view(None) != 0

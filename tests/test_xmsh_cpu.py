@@ -232,3 +232,43 @@ def test_set_node_transform_equals_building_with_that_transform(built_lib, orc, 
     assert np.array_equal(ia["rgb"].view(np.uint32), ib["rgb"].view(np.uint32)) and ra == rb_
     with pytest.raises(RuntimeError, match="no such node"):
         B.setNodeTransform(7, np.eye(4))
+
+
+def test_structural_validation_of_imported_trees(built_lib, tmp_path):
+    """A tree that would make the traversal kernel read out of bounds or spin never reaches the GPU: the .xmsh reader checks child / leaf references,
+    tree shape and leaf-run end flags (csrc/validate.cpp), and ctl_validate_scene_view does the same for whole views."""
+    import struct
+    for kind in ("cornell", "cornell7", "soup", "c4"):
+        ctl.Scene(kind, 32, 32, n_hint=40).validate()
+    src = ctl.Scene("soup", 32, 32, n_hint=200)
+    good_path = tmp_path / "good.xmsh"
+    src.write_xmsh(good_path)
+    good = good_path.read_bytes()
+    ctl.Scene.from_xmsh(good_path, *TWO_LIGHT_CAMERA, 16, 16).validate()
+    nodes = src.array("bvh_nodes")
+    at = good.find(nodes.tobytes()[:64])
+    assert at > 0
+    n_nodes = struct.unpack_from("<Q", good, at - 8)[0]         # mesh 0 of the scene
+    n_refs = struct.unpack_from("<Q", good, at + 64 * n_nodes)[0]
+    idx_at = len(good) - 4 * n_refs
+    assert 0 < n_nodes <= src.view.n_bvh_nodes and good[idx_at - 8:idx_at] == struct.pack("<Q", n_refs)
+    n_tris = len(src.mesh_triangles(0))
+
+    def damaged(offset, word, match):
+        p = tmp_path / "bad.xmsh"
+        p.write_bytes(good[:offset] + struct.pack("<i", word) + good[offset + 4:])
+        with pytest.raises(RuntimeError, match=match):
+            ctl.Scene.from_xmsh(p, *TWO_LIGHT_CAMERA, 16, 16)
+
+    child0 = at + 48                                            # BVHNodeData: three float4 of planes, then (child0, child1, parent, pad)
+    damaged(child0, 4 * n_nodes, "outside the node array")      # one past the last node
+    damaged(child0, 6, "outside the node array")                # not a node boundary
+    damaged(child0, 0, "referenced twice")                      # the root as its own child: a cycle
+    damaged(child0, ~int(n_refs), "outside the reference array")
+    second = struct.unpack_from("<i", good, at + 52)[0]
+    assert second >= 0
+    damaged(child0, second, "referenced twice")                 # a DAG: both children the same subtree
+    last_word = struct.unpack_from("<I", good, len(good) - 4)[0]
+    assert last_word & 1
+    damaged(len(good) - 4, last_word & ~1, "no end flag")
+    damaged(idx_at, (n_tris << 1) | 1, "out of range|references triangle")
