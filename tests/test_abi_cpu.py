@@ -305,6 +305,7 @@ def test_scene_from_mesh_validates_and_survives_degenerate_geometry(built_lib, o
         s = ctl.Scene.from_mesh(V.astype(np.float32), np.arange(3 * nt, dtype=np.uint32), np.zeros(nt, np.uint8), [mat], z1, *cam)
         v = s.view
         assert s.n_triangles == nt and v.n_woop >= nt and 1 <= v.n_bvh_nodes <= 2 * v.n_woop, name
+        s.validate()                                                        # tree shape, leaf runs, depth within the traversal stack
         refs = s.array("tri_index")[:, 0]
         assert set((refs >> 1).tolist()) == set(range(nt)), name            # every triangle is referenced
         assert np.bincount(refs & 1)[1] >= 1                                # leaf terminators present
