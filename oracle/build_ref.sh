@@ -36,6 +36,12 @@
 #  12. Engine/MeshLoader/ObjParser.cpp:648  `Vec3i ptn;` (empty constructor, Math/Vector.h:186) is read for the vt / vn slots a face vertex does not give
 #                                      (`f 1 2 3`, `f 1//2 ...`): uninitialised.  Zero-initialised = "slot absent" (index 0 -> -1 after the decrement), the
 #                                      evident intent.
+#  13. Kernel/ImagePipeline/Filter/NonLocalMeansFilter.cu lines 9-159 only (copyToShared, loadFromShared, patchDistance, weight and the kernels computeWeights,
+#                                      applyWeights, copyToCached), unpatched, compiled as host functions: `__global__` / `__shared__` are empty macros for g++
+#                                      (Defines.h:49-52), threadIdx / blockIdx / blockDim / __syncthreads are supplied by ref_driver.cpp, which runs every block's
+#                                      threads twice (first sweep fills the block's tile cache, second sweep computes from the complete cache; outputs are plain
+#                                      overwrites).  initializeFeatureBuffer (feature buffer: filled, never read -- its uses are commented out in the reference)
+#                                      and Apply's <<<>>> launches stay out.
 # oracle/ref_driver.cpp only defines the scene globals and packs ctl_scene_view into KernelDynamicScene.
 set -euo pipefail
 REF=${CTL_REFERENCE:-/root/reference}
@@ -81,6 +87,8 @@ PY
   | sed 's/t_nodesA, g_SceneData.m_sBVHNodeData.Data,/g_SceneData.m_sBVHNodeData.Data, (const BVHNodeData*)0,/; s/t_SceneNodes, g_SceneData.m_sSceneBVH.m_pNodes,/g_SceneData.m_sSceneBVH.m_pNodes, (const BVHNodeData*)0,/' > Kernel/TraceHelper_host.inc
 grep -q '(const BVHNodeData\*)0, mesh.m_uBVHNodeOffset' Kernel/TraceHelper_host.inc || { echo "TraceHelper.cu patch 6 did not apply"; exit 4; }
 sed -n '6,27p' Kernel/ImagePipeline/Filter/CanonicalFilter.cu > Kernel/ImagePipeline/Filter/evalFilter_host.inc   # evalFilter() only; the rest of the file is a kernel + launch
+sed -n '9,159p' Kernel/ImagePipeline/Filter/NonLocalMeansFilter.cu > Kernel/ImagePipeline/Filter/NonLocalMeans_host.inc   # note 13: the filter's kernels as host functions
+grep -q 'void computeWeights' Kernel/ImagePipeline/Filter/NonLocalMeans_host.inc && grep -q 'void copyToCached' Kernel/ImagePipeline/Filter/NonLocalMeans_host.inc && ! grep -q 'initializeFeatureBuffer' Kernel/ImagePipeline/Filter/NonLocalMeans_host.inc || { echo "NonLocalMeansFilter.cu extraction (note 13) did not apply"; exit 4; }
 sed -n '1,170p' Integrators/PathTracer.cu > Integrators/PathTracer_host.inc; echo "}" >> Integrators/PathTracer_host.inc
 sed -n '11,24p' Integrators/PseudoRealtime/WavefrontPathTracer.h > Integrators/PseudoRealtime/WavefrontPT_payload_host.inc   # struct WavefrontPTRayData
 sed -n '51,164p' Integrators/PseudoRealtime/WavefrontPathTracer.cu > Integrators/PseudoRealtime/WavefrontPT_iterate_host.inc   # pathIterateKernel<NEXT_EVENT_EST>

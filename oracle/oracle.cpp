@@ -1251,6 +1251,88 @@ static void reinhard_pixel(const uint8_t e4[4], float scale, float invWp2, uint8
     gamma_to_rgba8(lin, out);
 }
 
+// What applyImagePipeline does after the filter has written the RGBE stage (ImagePipeline.cu:71-82): copyFilteredToOutput, or ToneMapPostProcess + gamma
+void orc_pipeline_from_stage2(const uint8_t* rgbe, int w, int h, const ctl_image_pipeline* P, uint8_t* rgba, float* lum_out) {
+    const size_t n = (size_t)w * h;
+    if (!P->tonemap) { // copyFilteredToOutput
+        for (size_t i = 0; i < n; i++) { float c[3]; from_rgbe(&rgbe[4 * i], c); gamma_to_rgba8(c, rgba + 4 * i); }
+        return;
+    }
+    float lum[4]; luminance_info(rgbe, w, h, lum); // ToneMapPostProcess::Apply (ToneMapPostProcess.cu:27-39)
+    const float scale = P->key / lum[3], Lwhite = lum[1] * scale;
+    const float burn = std::min(1.0f, std::max(1e-8f, 1.0f - P->burn));
+    const float invWp2 = 1 / (Lwhite * Lwhite * std::pow(burn, 4.0f));
+    if (lum_out) { memcpy(lum_out, lum, sizeof(lum)); lum_out[4] = scale; lum_out[5] = invWp2; }
+    for (size_t i = 0; i < n; i++) reinhard_pixel(&rgbe[4 * i], scale, invWp2, rgba + 4 * i);
+}
+
+// NonLocalMeansFilter::Apply (Kernel/ImagePipeline/Filter/NonLocalMeansFilter.cu:184-228) without its tile cache: R = 6 search window, F = 3 patch
+// radius.  Stage 1 copyToCached (:150-158): PixelData -> RGBE.  Stage 2 computeWeights (:100-121) when asked: for every pixel p and every q of its
+// 13x13 window inside the image, weight(p, q) (:91-98) = exp(-max(0, patchDistance)) cut to 0 below 0.05, patchDistance (:67-89) = mean over the
+// 7x7 patch offsets that are inside the image around both p and q of
+//     (avg((c_p - c_q)^2) - (var_p + min(var_p, var_q))) / (1e-10 + k^2 (var_p + var_q)),
+// colours decoded from the RGBE cache, variances = PixelVarianceInfo::computeVariance() rounded to half precision (the shared-memory cache holds
+// halves, :14,32) times sigma2Scale.  Stage 3 applyWeights (:123-148): weighted mean of the window's colours (NaN weights skipped), the pixel itself
+// when the weights sum to <= 1e-4, written to the RGBE stage.  weights: w*h*169 floats, slot (yo + 6) * 13 + (xo + 6) of pixel y*w + x
+// (NonLocalMeansFilter.h:13-31, 63-66), kept by the filter between calls: compute_weights = 0 applies them as they are.
+void orc_nlm_filter(const ctl_pixel_data* img, const ctl_pixel_variance_info* var, int w, int h, float splat_scale, float k, float sigma2Scale,
+                    float* weights, int compute_weights, uint8_t* rgbe_out) {
+    const int R = 6, F = 3, NW = (2 * R + 1) * (2 * R + 1);
+    const size_t n = (size_t)w * h;
+    std::vector<uint8_t> cached(4 * n);
+    std::vector<float> col(3 * n), varh(n);
+    for (size_t i = 0; i < n; i++) {
+        float c[3]; px_to_spectrum(img[i], splat_scale, c); to_rgbe(c, &cached[4 * i]); from_rgbe(&cached[4 * i], &col[3 * i]);
+        const float invN = 1.0f / (float)var[i].num_samples_var;                                     // VarianceFromMoments, Math/VarAccumulator.h:7-11
+        const float v = (var[i].sum_x2 - (var[i].sum_x * var[i].sum_x) * invN) * invN;
+        varh[i] = (float)(_Float16)v;                                                                 // half(float): round to nearest even (Math/half.h:21-66)
+    }
+    if (compute_weights) {
+        memset(weights, 0, n * NW * sizeof(float));
+        const float eps = 1e-10f, alpha = 1.0f;
+        auto work = [&](int y0, int y1) {
+            for (int y = y0; y < y1; y++) for (int x = 0; x < w; x++) for (int xo = -R; xo <= R; xo++) for (int yo = -R; yo <= R; yo++) {
+                const int qx = x + xo, qy = y + yo;
+                if (qx < 0 || qx >= w || qy < 0 || qy >= h) continue;
+                float d_range = 0, cnt = 0;
+                for (int dx = -F; dx <= F; dx++) for (int dy = -F; dy <= F; dy++) {
+                    if (x + dx < 0 || x + dx >= w || y + dy < 0 || y + dy >= h || qx + dx < 0 || qx + dx >= w || qy + dy < 0 || qy + dy >= h) continue;
+                    const size_t ip = (size_t)(y + dy) * w + (x + dx), iq = (size_t)(qy + dy) * w + (qx + dx);
+                    float var_p = varh[ip], var_q = varh[iq];
+                    var_p *= sigma2Scale; var_q *= sigma2Scale;
+                    float e[3]; for (int c = 0; c < 3; c++) { const float t = col[3 * ip + c] - col[3 * iq + c]; e[c] = t * t; }
+                    const float u_diff = (((0.0f + e[0]) + e[1]) + e[2]) * (1.0f / 3);
+                    const float d = (u_diff - alpha * (var_p + std::min(var_p, var_q))) / (eps + k * k * (var_p + var_q));
+                    d_range += d; cnt++;
+                }
+                const float dist = cnt != 0 ? d_range / cnt : 0;
+                const float we = expf(-std::max(0.0f, dist));
+                weights[((size_t)y * w + x) * NW + (size_t)(yo + R) * (2 * R + 1) + (xo + R)] = we < 0.05f ? 0.0f : we;
+            }
+        };
+        const int nt = std::max(1, std::min((int)std::thread::hardware_concurrency(), h));
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back(work, (int)((long long)h * t / nt), (int)((long long)h * (t + 1) / nt));
+        for (auto& t : th) t.join();
+    }
+    for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+        float acc[3] = {0, 0, 0}, C_p = 0;
+        for (int xo = -R; xo <= R; xo++) for (int yo = -R; yo <= R; yo++) {
+            const int qx = x + xo, qy = y + yo;
+            if (qx < 0 || qx >= w || qy < 0 || qy >= h) continue;
+            const float we = weights[((size_t)y * w + x) * NW + (size_t)(yo + R) * (2 * R + 1) + (xo + R)];
+            if (we != we) continue;
+            const float* cq = &col[3 * ((size_t)qy * w + qx)];
+            C_p += we;
+            for (int c = 0; c < 3; c++) acc[c] += we * cq[c];
+        }
+        float out[3];
+        if (C_p > 1e-4f) { const float r = 1.0f / C_p; for (int c = 0; c < 3; c++) out[c] = acc[c] * r; }   // Spectrum / float multiplies by the reciprocal
+        else for (int c = 0; c < 3; c++) out[c] = col[3 * ((size_t)y * w + x) + c];
+        to_rgbe(out, &rgbe_out[4 * ((size_t)y * w + x)]);
+    }
+}
+
 void orc_apply_image_pipeline(const ctl_pixel_data* img, int w, int h, float splat_scale, const ctl_image_pipeline* P, uint8_t* rgba, float* lum_out) {
     const size_t n = (size_t)w * h;
     if (P->filter_type < 0 && !P->tonemap) { // copySamplesToOutput
@@ -1264,16 +1346,7 @@ void orc_apply_image_pipeline(const ctl_pixel_data* img, int w, int h, float spl
     } else {
         for (size_t i = 0; i < n; i++) { float c[3]; px_to_spectrum(img[i], splat_scale, c); to_rgbe(c, &rgbe[4 * i]); } // copySamplesToFiltered
     }
-    if (!P->tonemap) { // copyFilteredToOutput
-        for (size_t i = 0; i < n; i++) { float c[3]; from_rgbe(&rgbe[4 * i], c); gamma_to_rgba8(c, rgba + 4 * i); }
-        return;
-    }
-    float lum[4]; luminance_info(rgbe.data(), w, h, lum); // ToneMapPostProcess::Apply (ToneMapPostProcess.cu:27-39)
-    const float scale = P->key / lum[3], Lwhite = lum[1] * scale;
-    const float burn = std::min(1.0f, std::max(1e-8f, 1.0f - P->burn));
-    const float invWp2 = 1 / (Lwhite * Lwhite * std::pow(burn, 4.0f));
-    if (lum_out) { memcpy(lum_out, lum, sizeof(lum)); lum_out[4] = scale; lum_out[5] = invWp2; }
-    for (size_t i = 0; i < n; i++) reinhard_pixel(&rgbe[4 * i], scale, invWp2, rgba + 4 * i);
+    orc_pipeline_from_stage2(rgbe.data(), w, h, P, rgba, lum_out);
 }
 void orc_resolve_srgb8(const ctl_pixel_data* img, int n, float splat_scale, uint8_t* rgba) {
     ctl_image_pipeline P; memset(&P, 0, sizeof(P)); P.filter_type = -1;

@@ -119,6 +119,33 @@ DeviceDepthImage g_DepthImageWPT;                                      // Kernel
 #include <Integrators/PseudoRealtime/WavefrontPT_iterate_host.inc>   // the reference's pathIterateKernel<NEXT_EVENT_EST> (WavefrontPathTracer.cu:51-164)
 }
 
+// NonLocalMeansFilter kernels as host functions (build_ref.sh note 13)
+#include <Kernel/ImagePipeline/Filter/NonLocalMeansFilter.h>
+namespace CudaTracerLib {
+namespace nlm_host {
+struct U3 { unsigned x, y, z; };
+static U3 h_threadIdx, h_blockIdx, h_blockDim;
+static inline void h_syncthreads() {}
+#define threadIdx nlm_host::h_threadIdx
+#define blockIdx nlm_host::h_blockIdx
+#define blockDim nlm_host::h_blockDim
+#define __syncthreads nlm_host::h_syncthreads
+}
+#include <Kernel/ImagePipeline/Filter/NonLocalMeans_host.inc>
+template <typename K> static void nlm_launch(unsigned gx, unsigned gy, K kernel) {
+	nlm_host::h_blockDim = {16, 16, 1};
+	for (unsigned by = 0; by < gy; by++) for (unsigned bx = 0; bx < gx; bx++) {
+		nlm_host::h_blockIdx = {bx, by, 0};
+		for (int sweep = 0; sweep < 2; sweep++)
+			for (unsigned ty = 0; ty < 16; ty++) for (unsigned tx = 0; tx < 16; tx++) { nlm_host::h_threadIdx = {tx, ty, 0}; kernel(); }
+	}
+}
+#undef threadIdx
+#undef blockIdx
+#undef blockDim
+#undef __syncthreads
+} // namespace CudaTracerLib
+
 using namespace CudaTracerLib;
 
 namespace {
@@ -428,6 +455,39 @@ void ref_variance_add_pass(ctl_pixel_variance_info* var, const ctl_pixel_data* i
 		V.updateMoments(pd, splat_scale, 1.0f);
 		memcpy(&var[i], (void*)&V, sizeof(V));
 	}
+}
+
+// NonLocalMeansFilter::Apply (Kernel/ImagePipeline/Filter/NonLocalMeansFilter.cu:184-228) with the reference's OWN kernels (lines 9-159 of that file, compiled
+// as host functions, build_ref.sh note 13).  The launch geometry is the reference's: copyToCached and applyWeights over (w/16+1, h/16+1) blocks of 16x16,
+// computeWeights in 200-pixel super-blocks of 13x13 blocks with (x_off, y_off).  A block's threads run twice: the first sweep completes the block's 64x64
+// tile cache (copyToShared is per thread), the second computes from the complete cache -- what __syncthreads guarantees on the device; outputs are overwrites.
+// weights: w*h*169 floats owned by the caller (the filter's m_weightBuffer); recomputed when compute_weights != 0, else applied as they are.
+void ref_nlm_filter(const ctl_pixel_data* img, const ctl_pixel_variance_info* var, int w, int h, float splat_scale, float k, float sigma2Scale,
+                               float* weights, int compute_weights, unsigned char* rgbe_out)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	const int R = 6, F = 3;
+	Image I(w, h);
+	PixelVarianceBuffer vb(w, h);
+	for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+		memcpy((void*)&I.getPixelData(x, y), &img[y * w + x], sizeof(PixelData));
+		memcpy((void*)&vb(x, y), &var[y * w + x], sizeof(PixelVarianceInfo));
+	}
+	std::vector<RGBE> cached((size_t)w * h);
+	NonLocalMeansFilter::FilterWeightBuffer wb;
+	wb.R = R; wb.F = F; wb.w = w; wb.h = h; wb.n_weights_per_pixel = (2 * R + 1) * (2 * R + 1); wb.deviceWeightBuffer = weights;
+	nlm_launch(w / 16 + 1, h / 16 + 1, [&]() { copyToCached(I, cached.data(), splat_scale); });
+	if (compute_weights) {
+		memset(weights, 0, (size_t)w * h * wb.n_weights_per_pixel * sizeof(float));   // m_weightBuffer.ClearBuffer()
+		const int block_width = 200;
+		const int n_blocks_x = (w + block_width - 1) / block_width, n_blocks_y = (h + block_width - 1) / block_width, n_cuda_blocks = (block_width + 16 - 1) / 16;
+		for (int i = 0; i < n_blocks_x; i++) for (int j = 0; j < n_blocks_y; j++)
+			nlm_launch(n_cuda_blocks, n_cuda_blocks, [&]() { computeWeights(I, cached.data(), 0, R, F, k, sigma2Scale, vb, wb, i * block_width, j * block_width); });
+	}
+	nlm_launch(w / 16 + 1, h / 16 + 1, [&]() { applyWeights(I, cached.data(), wb, R, F); });
+	for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) memcpy(rgbe_out + 4 * ((size_t)y * w + x), (void*)&I.getFilteredData(x, y), 4);
+	wb.deviceWeightBuffer = 0;
+	vb.Free(); I.Free();
 }
 
 // .xmsh WRITER: the reference's own Mesh::CompileMesh (Engine/Mesh.cpp:199-290: TriangleData encoding, vertex normals, MeshPartLight list,

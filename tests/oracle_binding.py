@@ -204,6 +204,22 @@ def apply_image_pipeline(img, pipeline, splat_scale=0.0):
     f(_p(img), w, h, splat_scale, C.byref(pipeline), _p(out), _p(lum)); return out, lum
 
 
+def nlm_filter(img, var, k=0.45, sigma2_scale=0.005, splat_scale=0.0, weights=None):
+    """NonLocalMeansFilter restatement; same contract as ref_binding.nlm_filter."""
+    img = np.ascontiguousarray(img); h, w = img.shape; out = np.zeros((h, w, 4), np.uint8)
+    compute = weights is None
+    wts = np.zeros((h * w, 169), np.float32) if compute else np.ascontiguousarray(weights, np.float32)
+    f = oracle().orc_nlm_filter; f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p]; f.restype = None
+    f(_p(img), _p(np.ascontiguousarray(var)), w, h, splat_scale, k, sigma2_scale, _p(wts), int(compute), _p(out)); return out, wts
+
+
+def pipeline_from_stage2(rgbe, pipeline):
+    """Tail of applyImagePipeline after a filter wrote the RGBE stage: (rgba8, lum info[6])."""
+    rgbe = np.ascontiguousarray(rgbe, np.uint8); h, w = rgbe.shape[:2]; out = np.zeros((h, w, 4), np.uint8); lum = np.zeros(6, np.float32)
+    f = oracle().orc_pipeline_from_stage2; f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]; f.restype = None
+    f(_p(rgbe), w, h, C.byref(pipeline), _p(out), _p(lum)); return out, lum
+
+
 def variance_add_pass(var, img, splat_scale=0.0):
     f = oracle().orc_variance_add_pass; f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float]
     f(_p(var), _p(np.ascontiguousarray(img)), img.size, splat_scale); return var

@@ -107,6 +107,16 @@ def variance_add_pass(var, img, splat_scale=0.0):
     f(_p(var), _p(np.ascontiguousarray(img)), img.size, splat_scale); return var
 
 
+def nlm_filter(img, var, k=0.45, sigma2_scale=0.005, splat_scale=0.0, weights=None):
+    """NonLocalMeansFilter::Apply with the reference's own kernels run on the host.  weights=None: computed (and returned); else applied as given.
+    Returns (RGBE stage (h, w, 4) u8, weights (h*w, 169) f32)."""
+    img = np.ascontiguousarray(img); h, w = img.shape; out = np.zeros((h, w, 4), np.uint8)
+    compute = weights is None
+    wts = np.zeros((h * w, 169), np.float32) if compute else np.ascontiguousarray(weights, np.float32)
+    f = ref().ref_nlm_filter; f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p]; f.restype = None
+    f(_p(img), _p(np.ascontiguousarray(var)), w, h, splat_scale, k, sigma2_scale, _p(wts), int(compute), _p(out)); return out, wts
+
+
 def write_xmsh(path, verts, indices, sub_tris, mats, emissive=None):
     """The reference's own .xmsh writer (Mesh::CompileMesh): verts (nv, 3) f32, indices (3 * nt) u32 with the triangles of sub-mesh k
     consecutive, sub_tris[k] triangles each, mats = list of Material (one per sub-mesh), emissive (n_sub, 3) or None."""

@@ -266,3 +266,62 @@ def test_pixel_variance_buffer_golden(orc):
     assert np.array_equal(var.view(np.uint32).reshape(-1, 11), GOLD["variance_info_cornell_32x24"])
     assert (var["iterations_done"] == 4).all() and (var["num_samples_var"] == 4).all() and (var["weight"] == 4).all()
     assert np.allclose(var["sum_x"], (accs[-1][..., :3].reshape(-1, 3) * [0.212671, 0.715160, 0.072169]).sum(axis=1), rtol=1e-4, atol=1e-6)  # telescoping sum of the per-pass luminances
+
+
+NLM_GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nlm_golden.npz"))
+NLM_CASES = {"a": (0.45, 1.0), "b": (1.0, 5.0), "wide": (0.45, 1.0), "default": (0.45, 0.005)}
+
+
+def _nlm_inputs(name, suffix=""):
+    img = np.ascontiguousarray(NLM_GOLD[name + "_img" + suffix]).view(api.PIXEL_DTYPE).reshape(NLM_GOLD[name + "_img" + suffix].shape[:2])
+    return img, np.ascontiguousarray(NLM_GOLD[name + "_var" + suffix]).view(ctl.VARIANCE_DTYPE).reshape(-1)
+
+
+@pytest.mark.parametrize("name", sorted(NLM_CASES))
+def test_non_local_means_filter_golden(orc, name):
+    """NonLocalMeansFilter restatement against the reference's OWN kernels (computeWeights / applyWeights run on the host, tests/golden/make_nlm_golden.py):
+    RGBE stage and all 169 weights per pixel bit-identical.  `wide` crosses the 200-pixel super-block boundary of the reference's launch loop;
+    `default` (sigma2Scale 0.005 after 2 passes) is the regime where only the self-weight survives and the filter is the identity on the RGBE stage."""
+    import hashlib
+    k, s2 = NLM_CASES[name]
+    img, var = _nlm_inputs(name)
+    rgbe, wts = orc.nlm_filter(img, var, k, s2)
+    assert np.array_equal(rgbe, NLM_GOLD[name + "_rgbe"])
+    assert hashlib.sha256(wts.tobytes()).digest() == NLM_GOLD[name + "_weights_sha256"].tobytes()
+    frac = float((wts > 0).mean())
+    unfiltered = orc.nlm_filter(img, var, 0.45, 0.0)[0]                      # zero variance scale: distances explode, only w(p, p) = 1 is left
+    if name == "default":
+        assert frac == pytest.approx(1 / 169, abs=1e-9) and np.array_equal(rgbe, unfiltered)
+    else:
+        lit = unfiltered[..., :3].any(axis=2)                                 # `wide` is a 204x10 strip, mostly background
+        assert 0.2 < frac < 0.95 and (rgbe != unfiltered).any(axis=2)[lit].mean() > (0.5 if name == "wide" else 0.9)   # 3 passes only in `wide`: many zero variances
+    assert ((wts == 0) | (wts >= 0.05)).all() and wts.max() <= 1.0 and (wts.reshape(-1, 13, 13)[:, 6, 6] == 1.0).all()
+
+
+def test_non_local_means_stale_weights_golden(orc):
+    """UpdateWeightPeriodicity > 1: weights computed on an earlier frame are applied to the current one (NonLocalMeansFilter.cu:207-224)."""
+    img0, var0 = _nlm_inputs("a", "_early")
+    img, var = _nlm_inputs("a")
+    _, w0 = orc.nlm_filter(img0, var0, 0.45, 1.0)
+    stale = orc.nlm_filter(img, var, 0.45, 1.0, weights=w0)[0]
+    assert np.array_equal(stale, NLM_GOLD["a_rgbe_stale"]) and not np.array_equal(stale, NLM_GOLD["a_rgbe"])
+
+
+def test_non_local_means_live_reference(orc):
+    """Fresh inputs (not in the goldens) through oracle/_ref when it is built."""
+    import ref_binding as rb
+    if not rb.available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(3)
+    w, h = 37, 23
+    img = np.zeros((h, w), api.PIXEL_DTYPE); var = np.zeros(w * h, ctl.VARIANCE_DTYPE)
+    base = rng.uniform(0, 2, (h // 14 + 1, w // 14 + 1, 3)).repeat(14, 0).repeat(14, 1)[:h, :w]   # flat regions + noise: weights in every regime
+    n = 5
+    samples = base[None] + rng.normal(0, 0.15, (n, h, w, 3))
+    img["rgb"] = samples.sum(0).astype(np.float32); img["weight_sum"] = n
+    lum = (samples * [0.212671, 0.715160, 0.072169]).sum(-1).reshape(n, -1)
+    var["sum_x"] = lum.sum(0); var["sum_x2"] = (lum ** 2).sum(0); var["num_samples_var"] = n; var["iterations_done"] = n
+    for k, s2 in ((0.45, 1.0), (0.7, 0.3)):
+        a, wa = orc.nlm_filter(img, var, k, s2); b, wb = rb.nlm_filter(img, var, k, s2)
+        assert np.array_equal(a, b) and np.array_equal(wa.view(np.uint32), wb.view(np.uint32))
+        assert 0.05 < (wa > 0).mean() < 0.99
