@@ -154,6 +154,7 @@ def lib():
     L.ctl_set_accum_device_ptr.argtypes = [vp, vp]
     L.ctl_apply_image_pipeline.argtypes = [vp, C.c_float, C.POINTER(ImagePipeline), vp, vp, vp]
     L.ctl_read_variance.argtypes = [vp, vp]
+    L.ctl_read_nlm_weights.argtypes = [vp, vp]
     L.ctl_stream.argtypes = [vp]; L.ctl_stream.restype = vp
     L.ctl_set_stream.argtypes = [vp, vp]
     L.ctl_stats.argtypes = [vp, u64p, fp, u64p, C.POINTER(C.c_uint32)]
@@ -379,6 +380,12 @@ class PathTracer:
         out = np.zeros((self.h, self.w, 4), np.uint8); lum = np.zeros(6, np.float32)
         _check(lib().ctl_apply_image_pipeline(self._ctx, float(splat_scale), C.byref(pipeline), None, _ptr(out), _ptr(lum) if lum_info else None))
         return (out, lum) if lum_info else out
+
+    def readNlmWeights(self):
+        """Weights of the last NonLocalMeansFilter application, reference layout (w*h, 169)."""
+        out = np.zeros((self.w * self.h, 169), np.float32)
+        _check(lib().ctl_read_nlm_weights(self._ctx, _ptr(out)))
+        return out
 
     def readVarianceBuffer(self):
         """PixelVarianceBuffer contents (needs setParameter("PixelVarianceBuffer", 1) before the passes)."""

@@ -16,6 +16,7 @@
 #include "wavefront.cuh"
 #include "wavefront_pt.cuh"
 #include "image_pipeline.cuh"
+#include "nlm_filter.cuh"
 #include "bvh_build.cuh"
 
 using namespace ctld;
@@ -78,6 +79,7 @@ struct ctl_ctx {
     DevBuf<unsigned long long> stats; // [0] rays_last [1] rays_total [2..4] ext visits [5] ext rays [6..8] shadow visits [9] shadow rays
     DevBuf<float> own_accum; float* accum = nullptr; DevBuf<uchar4> resolve_tmp, pipe_rgbe; DevBuf<float4> pipe_partial; DevBuf<float> pipe_lum;
     DevBuf<ctl_pixel_variance_info> d_var; int variance_buffer = 0;
+    DevBuf<uchar4> nlm_cached; DevBuf<float> nlm_varh, nlm_weights; long long nlm_last_update = -1; size_t nlm_pixels = 0;   // NonLocalMeansFilter state (m_cachedImg, m_weightBuffer, last_iter_weight_update)
     unsigned captured_n = 0; DevBuf<unsigned> d_captured_n;
     uint32_t passes_done = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
@@ -347,7 +349,7 @@ void ctl_destroy(ctl_ctx* c) {
     if (c->h_tab1) cudaFreeHost(c->h_tab1); if (c->h_tab2) cudaFreeHost(c->h_tab2); if (c->h_tab_free) cudaEventDestroy(c->h_tab_free);
     c->cf.release(); c->cl.release(); c->nor.release(); c->px.release(); c->rays_a.release(); c->rays_b.release(); c->hit_a.release(); c->sh_rays.release();
     c->sh_payload.release(); c->capture.release(); c->path_a.release(); c->path_b.release(); c->path_c.release(); c->rays_c.release(); c->sort_keys.release(); c->sort_hist.release(); c->sort_offsets.release(); c->mat_hist.release(); c->mat_cls.release(); c->mat_order.release(); c->hit_node.release(); c->counters.release(); c->stats.release();
-    c->own_accum.release(); c->d_captured_n.release(); c->resolve_tmp.release(); c->pipe_rgbe.release(); c->pipe_partial.release(); c->pipe_lum.release(); c->d_var.release();
+    c->own_accum.release(); c->d_captured_n.release(); c->resolve_tmp.release(); c->pipe_rgbe.release(); c->pipe_partial.release(); c->pipe_lum.release(); c->d_var.release(); c->nlm_cached.release(); c->nlm_varh.release(); c->nlm_weights.release(); c->nlm_last_update = -1; c->nlm_pixels = 0;
     c->w_thr.release(); c->w_lxy.release(); c->w_df.release(); c->w_ray.release(); c->w_misc.release(); c->w_res.release(); c->w_desc.release();
     for (int k = 0; k < 2; k++) { c->w_sec[k].release(); c->w_sres[k].release(); }
     for (auto e : c->stage_ev) cudaEventDestroy(e);
@@ -362,6 +364,7 @@ int ctl_resize(ctl_ctx* c, int width, int height) {
     CK(cudaStreamSynchronize(c->stream));
     c->w = width; c->h = height; c->scene.img_w = width; c->scene.img_h = height;
     c->passes_done = 0;
+    c->nlm_pixels = 0; c->nlm_last_update = -1;   // NonLocalMeansFilter::Resize (NonLocalMeansFilter.h:131-137)
     return alloc_image(c);
 }
 
@@ -830,14 +833,48 @@ int ctl_read_accum(ctl_ctx* c, ctl_pixel_data* out) {
 // == applyImagePipeline (Kernel/ImagePipeline/ImagePipeline.cu:54-84): optional reconstruction filter, optional tone mapper, gamma
 int ctl_apply_image_pipeline(ctl_ctx* c, float splat_scale, const ctl_image_pipeline* P, void* d_rgba8, void* host_rgba8, float lum_info[6]) {
     if (!c || !P || (!d_rgba8 && !host_rgba8)) return set_err("null argument");
-    if (P->filter_type < -1 || P->filter_type > 4) return set_err("filter_type must be -1 (none), 0 (box), 1 (Gaussian), 2 (triangle), 3 (Mitchell) or 4 (Lanczos-sinc)");
-    if (P->filter_type >= 0 && (!(P->x_width > 0) || !(P->y_width > 0) || P->x_width > 16 || P->y_width > 16)) return set_err("filter widths out of range (0, 16]");
+    if (P->filter_type < -1 || P->filter_type > 5) return set_err("filter_type must be -1 (none), 0 (box), 1 (Gaussian), 2 (triangle), 3 (Mitchell), 4 (Lanczos-sinc) or 5 (non-local means)");
+    const bool nlm = P->filter_type == 5;
+    if (P->filter_type >= 0 && !nlm && (!(P->x_width > 0) || !(P->y_width > 0) || P->x_width > 16 || P->y_width > 16)) return set_err("filter widths out of range (0, 16]");
     if (P->tonemap < 0 || P->tonemap > 1) return set_err("tonemap must be 0 (none) or 1 (Reinhard05)");
+    if (nlm) {
+        if (!(P->param0 >= 0.0f) || !(P->param1 >= 0.0f)) return set_err("NonLocalMeansFilter: k (param0) and sigma2Scale (param1) must be >= 0");
+        if (!(P->x_width >= 1.0f) || P->x_width > 1e9f || P->x_width != floorf(P->x_width)) return set_err("NonLocalMeansFilter: UpdateWeightPeriodicity (x_width) must be an integer >= 1");
+        if (!c->variance_buffer || !c->d_var.p || c->d_var.n < (size_t)c->w * c->h) return set_err("NonLocalMeansFilter reads the PixelVarianceBuffer: ctl_set_param_i(ctx, \"PixelVarianceBuffer\", 1) before the passes");
+    }
     CK(cudaSetDevice(c->device));
     const int n = c->w * c->h;
     uchar4* dst = (uchar4*)d_rgba8;
     if (!dst) { CK(c->resolve_tmp.ensure((size_t)n)); dst = c->resolve_tmp.p; }
     const int grid = grid_for(c, 8);
+    if (nlm) { // NonLocalMeansFilter::Apply (Kernel/ImagePipeline/Filter/NonLocalMeansFilter.cu:184-228), then the rest of applyImagePipeline (ImagePipeline.cu:71-82)
+        const long long numPasses = (long long)c->passes_done; const int n_update = (int)P->x_width;
+        bool force_update = false;
+        if (c->nlm_pixels != (size_t)n) { // Resize / first use: new cache and weight buffer (adaptBuffer), last_iter_weight_update = -1
+            CK(c->nlm_cached.ensure((size_t)n)); CK(c->nlm_varh.ensure((size_t)n)); CK(c->nlm_weights.ensure((size_t)n * NLM_NW));
+            c->nlm_pixels = (size_t)n; c->nlm_last_update = -1; force_update = true;
+        }
+        k_nlm_prepare<<<grid, 256, 0, c->stream>>>(c->accum, c->d_var.p, n, splat_scale, c->nlm_cached.p, c->nlm_varh.p);
+        const dim3 nb((c->w + NLM_B - 1) / NLM_B, (c->h + NLM_B - 1) / NLM_B), nt(NLM_B, NLM_B);
+        if (c->nlm_last_update + 1 != numPasses || (numPasses % n_update) == 0 || force_update) {
+            CK(cudaMemsetAsync(c->nlm_weights.p, 0, (size_t)n * NLM_NW * sizeof(float), c->stream));   // m_weightBuffer.ClearBuffer()
+            k_nlm_weights<<<nb, nt, 0, c->stream>>>(c->nlm_cached.p, c->nlm_varh.p, c->w, c->h, P->param0, P->param1, c->nlm_weights.p);
+        }
+        c->nlm_last_update = numPasses;
+        if (!P->tonemap) k_nlm_apply<true><<<nb, nt, 0, c->stream>>>(c->nlm_cached.p, c->nlm_weights.p, c->w, c->h, dst);
+        else {
+            const int bx = (c->w + 15) / 16, by = (c->h + 15) / 16;
+            CK(c->pipe_rgbe.ensure((size_t)n)); CK(c->pipe_partial.ensure((size_t)bx * by)); CK(c->pipe_lum.ensure(8));
+            k_nlm_apply<false><<<nb, nt, 0, c->stream>>>(c->nlm_cached.p, c->nlm_weights.p, c->w, c->h, c->pipe_rgbe.p);
+            k_lum_blocks<<<bx * by, 256, 0, c->stream>>>(c->pipe_rgbe.p, c->w, c->h, bx, c->pipe_partial.p);
+            k_lum_final<<<1, 32, 0, c->stream>>>(c->pipe_partial.p, bx * by, n, P->key, P->burn, c->pipe_lum.p);
+            k_reinhard<<<grid, 256, 0, c->stream>>>(c->pipe_rgbe.p, n, c->pipe_lum.p, dst);
+            if (lum_info) { CK(cudaMemcpyAsync(lum_info, c->pipe_lum.p, 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+        }
+        CK(cudaGetLastError());
+        if (host_rgba8) { CK(cudaMemcpyAsync(host_rgba8, dst, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+        return 0;
+    }
     PipeFilter F = {P->filter_type, P->x_width, P->y_width, P->param0, P->param1, 1.f / P->x_width, 1.f / P->y_width,
                     expf(-P->param0 * P->x_width * P->x_width), expf(-P->param0 * P->y_width * P->y_width)}; // FilterBase / GaussianFilter ctor, SceneTypes/Filter.h:15-19, 60-66
     if (P->filter_type < 0 && !P->tonemap) k_pipe_direct<<<grid, 256, 0, c->stream>>>(c->accum, n, splat_scale, dst);
@@ -854,6 +891,19 @@ int ctl_apply_image_pipeline(ctl_ctx* c, float splat_scale, const ctl_image_pipe
     }
     CK(cudaGetLastError());
     if (host_rgba8) { CK(cudaMemcpyAsync(host_rgba8, dst, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+    return 0;
+}
+// NonLocalMeansFilter's weight buffer of the last ctl_apply_image_pipeline(filter_type 5), in the reference's layout [pixel][169] (slot (yo + 6) * 13 + xo + 6,
+// NonLocalMeansFilter.h:13-31, 63-66); kept on the device as [169][pixel]
+int ctl_read_nlm_weights(ctl_ctx* c, float* host_out) {
+    if (!c || !host_out) return set_err("null argument");
+    if (!c->nlm_pixels || c->nlm_pixels != (size_t)c->w * c->h || c->nlm_last_update < 0) return set_err("no NonLocalMeansFilter weights: apply a pipeline with filter_type 5 first");
+    CK(cudaSetDevice(c->device));
+    const size_t n = c->nlm_pixels;
+    std::vector<float> soa(n * NLM_NW);
+    CK(cudaMemcpyAsync(soa.data(), c->nlm_weights.p, n * NLM_NW * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (size_t p = 0; p < n; p++) for (int s = 0; s < NLM_NW; s++) host_out[p * NLM_NW + s] = soa[(size_t)s * n + p];
     return 0;
 }
 // == applyImagePipeline(tracer, img, 0, 0): the default resolve

@@ -125,9 +125,10 @@ typedef struct ctl_pixel_variance_info {
 /* applyImagePipeline's two optional stages (Kernel/ImagePipeline/ImagePipeline.h): an ImageSamplesFilter (CanonicalFilter over one of
  * the five filters of SceneTypes/Filter.h) and a PostProcess (ToneMapPostProcess = Reinhard05). */
 typedef struct ctl_image_pipeline {
-    int32_t filter_type; /* -1 none; 0 BoxFilter, 1 GaussianFilter, 2 TriangleFilter, 3 MitchellFilter, 4 LanczosSincFilter */
-    float x_width, y_width;
-    float param0, param1; /* Gaussian: alpha; Mitchell: B, C; LanczosSinc: tau */
+    int32_t filter_type; /* -1 none; 0 BoxFilter, 1 GaussianFilter, 2 TriangleFilter, 3 MitchellFilter, 4 LanczosSincFilter (CanonicalFilter);
+                          *  5 NonLocalMeansFilter (Kernel/ImagePipeline/Filter/NonLocalMeansFilter.h) */
+    float x_width, y_width; /* NonLocalMeansFilter: x_width = UpdateWeightPeriodicity (integer >= 1, reference default 25), y_width unused */
+    float param0, param1; /* Gaussian: alpha; Mitchell: B, C; LanczosSinc: tau; NonLocalMeans: k (0.45), sigma2Scale (0.005) */
     int32_t tonemap;     /* 0 none; 1 ToneMapPostProcess (Kernel/ImagePipeline/PostProcess/ToneMapPostProcess.h) */
     float key, burn;     /* m_key (0.18), m_burn (0) */
 } ctl_image_pipeline;
@@ -344,6 +345,12 @@ int ctl_resolve_filtered_srgb8(ctl_ctx*, float splat_scale, int filter_type, flo
  * + Reinhard05Kernel, ToneMapPostProcess.cu:6-39) and the gamma stage.  lum_info (may be NULL, filled when tonemap != 0, synchronises):
  * [0] min [1] max [2] average luminance, [3] log-average luminance, [4] scale, [5] invWp2. */
 int ctl_apply_image_pipeline(ctl_ctx*, float splat_scale, const ctl_image_pipeline*, void* d_rgba8, void* host_rgba8, float lum_info[6]);
+/* filter_type 5 == NonLocalMeansFilter::Apply (Kernel/ImagePipeline/Filter/NonLocalMeansFilter.cu:184-228) in the filter slot of the pipeline: variance-guided
+ * non-local means, 13x13 search window, 7x7 patches.  Needs "PixelVarianceBuffer"=1 during the passes.  Like the reference object, the context keeps the
+ * weight buffer (169 floats per pixel) between calls and recomputes it when the pass count did not advance by exactly one since the last call, when it is a
+ * multiple of UpdateWeightPeriodicity, or after a resize; otherwise the stored weights are applied to the new frame.  ctl_read_nlm_weights copies the
+ * weights of the last call to the host in the reference's layout: w*h*169 floats, slot (yo + 6) * 13 + (xo + 6) of pixel y*w + x. */
+int ctl_read_nlm_weights(ctl_ctx*, float* host_out);
 /* == PixelVarianceBuffer (Kernel/PixelVarianceBuffer.h, .cu:10-36; owned by TracerBase, updated after every pass of a progressive tracer,
  * Kernel/Tracer.h:233-237): "PixelVarianceBuffer"=1 (ctl_set_param_i) makes every single-pass render call (ctl_render_pass with the full
  * window, ctl_wavefront_pass) run PixelVarianceInfo::updateMoments on all pixels after the pass and clear the buffer on a new trace.
