@@ -58,10 +58,12 @@ __global__ void __launch_bounds__(NLM_B * NLM_B) k_nlm_weights(const uchar4* __r
         for (int yo = -NLM_R; yo <= NLM_R; yo++) {
             const int qx = x + xo, qy = y + yo;
             if (qx < 0 || qx >= w || qy < 0 || qy >= h) continue;
+            // patch offsets with p + d and q + d inside the image (the reference tests every tap, :75-77): a rectangle, visited in the same dx-major order
+            const int dx0 = max(-NLM_F, max(-x, -qx)), dx1 = min(NLM_F, min(w - 1 - x, w - 1 - qx));
+            const int dy0 = max(-NLM_F, max(-y, -qy)), dy1 = min(NLM_F, min(h - 1 - y, h - 1 - qy));
             float d_range = 0.0f, cnt = 0.0f;
-            for (int dx = -NLM_F; dx <= NLM_F; dx++)
-                for (int dy = -NLM_F; dy <= NLM_F; dy++) {
-                    if (x + dx < 0 || x + dx >= w || y + dy < 0 || y + dy >= h || qx + dx < 0 || qx + dx >= w || qy + dy < 0 || qy + dy >= h) continue;
+            for (int dx = dx0; dx <= dx1; dx++)
+                for (int dy = dy0; dy <= dy1; dy++) {
                     const int ip = (ly + dy) * NLM_TW + (lx + dx), iq = (ly + yo + dy) * NLM_TW + (lx + xo + dx);
                     const float var_p = s_v[ip], var_q = s_v[iq];
                     const float er = s_r[ip] - s_r[iq], eg = s_g[ip] - s_g[iq], eb = s_b[ip] - s_b[iq];
