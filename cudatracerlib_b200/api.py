@@ -91,6 +91,7 @@ class SceneView(C.Structure):
         ("num_lights", C.c_uint32),
         ("light_indices", C.c_uint32 * MAX_NUM_LIGHTS), ("light_cdf", C.c_float * MAX_NUM_LIGHTS),
         ("camera", Camera), ("box_min", C.c_float * 3), ("box_max", C.c_float * 3), ("ray_eps", C.c_float),
+        ("node_alias", C.POINTER(C.c_uint32)),
     ]
 
 
@@ -125,6 +126,7 @@ def lib():
     L.ctl_scene_create_from_files.argtypes = [C.POINTER(C.c_char_p), u32, vp, vp, vp, vp, C.c_float, i32, i32]
     L.ctl_scene_get_mesh_triangles.argtypes = [vp, u32, vp, C.POINTER(C.c_uint32)]
     L.ctl_scene_destroy.argtypes = [vp]; L.ctl_scene_destroy.restype = None
+    L.ctl_scene_set_rebraid.argtypes = [vp, C.c_uint32]; L.ctl_scene_set_rebraid.restype = C.c_int
     L.ctl_validate_scene_view.argtypes = [C.POINTER(SceneView)]; L.ctl_validate_scene_view.restype = C.c_int
     L.ctl_bvh_build_gpu.argtypes = [i32, vp, u32, vp, vp, vp, vp, vp]
     L.ctl_scene_rebuild_bvh_gpu.argtypes = [vp, i32, vp]
@@ -241,6 +243,11 @@ class Scene:
     def write_xmsh(self, path, mesh=0):
         """Mesh `mesh` as an .xmsh file (the output sequence of the reference's Mesh::CompileMesh)."""
         _check(lib().ctl_scene_write_xmsh(self._h, mesh, os.fsencode(path)))
+
+    def setRebraid(self, max_entries):
+        """ctl_scene_set_rebraid: open overlapping instances into up to max_entries scene-level leaves (0 = off); refreshes self.view."""
+        _check(lib().ctl_scene_set_rebraid(self._h, int(max_entries)))
+        _check(lib().ctl_scene_get_view(self._h, C.byref(self.view)))
 
     def validate(self):
         """ctl_validate_scene_view: raises RuntimeError naming the first structural problem of the view (index ranges, tree shape, stack depth)."""

@@ -182,6 +182,11 @@ int ctl_scene_set_node_transform(ctl_scene* s, uint32_t node, const float* xf16)
     try { memcpy(s->S.node_inputs[node].xf.m, xf16, 64); ctlb::assemble_nodes(s->S); return 0; }
     catch (const std::exception& e) { return set_err(e.what()); }
 }
+int ctl_scene_set_rebraid(ctl_scene* s, uint32_t max_entries) {
+    if (!s) return set_err("null argument");
+    try { s->S.rebraid_entries = max_entries; ctlb::assemble_nodes(s->S); return 0; }
+    catch (const std::exception& e) { return set_err(e.what()); }
+}
 int ctl_scene_get_view(const ctl_scene* s, ctl_scene_view* out) { if (!s || !out) return set_err("null argument"); s->S.fill_view(out); return 0; }
 void ctl_scene_destroy(ctl_scene* s) { delete s; }
 int ctl_validate_scene_view(const ctl_scene_view* v) {
@@ -446,6 +451,7 @@ int ctl_upload_scene(ctl_ctx* c, const ctl_scene_view* v) {
 int ctl_update_scene_nodes(ctl_ctx* c, const ctl_scene_view* v) {
     if (!c || !v) return set_err("null argument");
     if (!c->has_scene) return set_err("no scene uploaded");
+    if (v->node_alias) return set_err("re-braided view: its mesh-level arrays change with the node level, use ctl_upload_scene");
     if (v->n_bvh_nodes != c->d_bvh_nodes.n && v->n_bvh_nodes > c->d_bvh_nodes.n) return set_err("the view has other meshes than the uploaded scene: use ctl_upload_scene");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));

@@ -271,6 +271,8 @@ void assemble_scene(const std::vector<MeshInput>& meshes, const std::vector<Node
     assemble_nodes(S);
 }
 
+void rebraid(SceneStorage& S, const std::vector<Box>& node_box);
+
 void assemble_nodes(SceneStorage& S) {
     const std::vector<NodeInput>& nodes = S.node_inputs;
     const std::vector<Box>& mesh_box = S.mesh_boxes;
@@ -368,19 +370,102 @@ void assemble_nodes(SceneStorage& S) {
     }
     make_camera(S.cam_pos, S.cam_target, S.cam_up, S.cam_fov, S.cam_w, S.cam_h, &S.camera);
     S.ray_eps = 1e-4f * length(S.box.hi - S.box.lo); // DynamicScene.cpp:587
+    rebraid(S, node_box);
+}
+
+// Partial re-braiding (Benthin, Woop, Wald, Afra: "Improved two-level BVHs using partial re-braiding", HPG 2017) inside the reference's data
+// layout.  The reference's scene level has one leaf per instance (BVHRebuilder); where instance boxes overlap, a ray descends every overlapping
+// mesh tree from its root (config 4: 5.7 instance entries and 95 inner nodes per ray).  Here the instances with the largest world-space boxes are
+// opened, top-down, into entries (instance, sub-tree) until the budget of scene-level leaves is reached, and the scene-level tree is built over the
+// entries.  No kernel knows: an entry is an ordinary node record (a copy of the instance's: same transform, materials, lights) whose mesh record
+// points at a re-based copy of the sub-tree (same Woop / index / TriangleData offsets).  Hits are the same triangles at the same distances; the
+// node index a hit reports is the pseudo-node's, node_alias gives the instance.
+void rebraid(SceneStorage& S, const std::vector<Box>& node_box) {
+    S.rb_active = false;
+    S.rb_bvh_nodes.clear(); S.rb_scene_bvh.clear(); S.rb_meshes.clear(); S.rb_nodes.clear(); S.rb_node_xf.clear(); S.rb_node_inv_xf.clear(); S.rb_node_alias.clear();
+    size_t budget = S.rebraid_entries;
+    if (!budget) if (const char* e = getenv("CTL_REBRAID")) budget = (size_t)atoll(e);
+    const size_t n_real = S.nodes.size();
+    if (budget <= n_real || n_real < 2) return;
+    struct Entry { uint32_t node; int ref; Box world; float area; uint32_t out_node; };
+    auto mesh_node = [&](uint32_t ni, int ref) -> const ctl_bvh_node& { return S.bvh_nodes[S.meshes[S.nodes[ni].mesh_index].bvh_node_offset / 4 + (uint32_t)ref / 4]; };
+    auto inner = [](int c) { return c >= 0 && c != CTL_SENTINEL; };
+    auto openable = [&](const Entry& e) { const ctl_bvh_node& n = mesh_node(e.node, e.ref); return inner(n.child0) && inner(n.child1); };
+    auto world_of = [&](uint32_t ni, const Box& lb) {
+        Box b; const M4& xf = S.node_inputs[ni].xf;
+        for (int c = 0; c < 8; c++) b.grow(xf.transform_point(V3(c & 1 ? lb.hi.x : lb.lo.x, c & 2 ? lb.hi.y : lb.lo.y, c & 4 ? lb.hi.z : lb.lo.z)));
+        return b;
+    };
+    auto cmp = [](const Entry& a, const Entry& b) { return a.area != b.area ? a.area < b.area : (a.node != b.node ? a.node > b.node : a.ref > b.ref); }; // max-heap on area, ties by index
+    std::vector<Entry> heap, done;
+    auto place = [&](Entry e) { e.area = e.world.area(); if (openable(e)) { heap.push_back(e); std::push_heap(heap.begin(), heap.end(), cmp); } else done.push_back(e); };
+    for (uint32_t ni = 0; ni < n_real; ni++) place(Entry{ni, 0, node_box[ni], 0.0f, ni});
+    while (!heap.empty() && heap.size() + done.size() < budget) {
+        std::pop_heap(heap.begin(), heap.end(), cmp);
+        const Entry e = heap.back(); heap.pop_back();
+        const ctl_bvh_node& n = mesh_node(e.node, e.ref);
+        place(Entry{e.node, n.child0, world_of(e.node, Box(V3(n.a[0], n.a[2], n.c[0]), V3(n.a[1], n.a[3], n.c[1]))), 0.0f, 0});
+        place(Entry{e.node, n.child1, world_of(e.node, Box(V3(n.b[0], n.b[2], n.c[2]), V3(n.b[1], n.b[3], n.c[3]))), 0.0f, 0});
+    }
+    done.insert(done.end(), heap.begin(), heap.end());
+    std::sort(done.begin(), done.end(), [](const Entry& a, const Entry& b) { return a.node != b.node ? a.node < b.node : a.ref < b.ref; });
+    bool any_opened = false;
+    for (const Entry& e : done) any_opened |= e.ref != 0;
+    if (!any_opened) return;
+    S.rb_bvh_nodes = S.bvh_nodes; S.rb_meshes = S.meshes; S.rb_nodes = S.nodes; S.rb_node_xf = S.node_xf; S.rb_node_inv_xf = S.node_inv_xf;
+    S.rb_node_alias.resize(n_real); for (uint32_t i = 0; i < n_real; i++) S.rb_node_alias[i] = i;
+    std::vector<Box> entry_box;
+    for (Entry& e : done) {
+        entry_box.push_back(e.world);
+        if (e.ref == 0) { e.out_node = e.node; continue; }   // unopened instance: its own node record
+        // re-based copy of the sub-tree, pre-order; the copy's node 0 is the sub-tree root (traversal enters a mesh at its node 0)
+        const uint32_t base = S.meshes[S.nodes[e.node].mesh_index].bvh_node_offset / 4, first = (uint32_t)S.rb_bvh_nodes.size();
+        std::vector<std::pair<uint32_t, uint32_t>> todo;   // (old local index, new local index)
+        S.rb_bvh_nodes.push_back(S.bvh_nodes[base + (uint32_t)e.ref / 4]); S.rb_bvh_nodes.back().parent = 0xffffffffu;
+        todo.emplace_back((uint32_t)e.ref / 4, 0u);
+        while (!todo.empty()) {
+            const auto cur = todo.back(); todo.pop_back();
+            int ch[2] = {S.bvh_nodes[base + cur.first].child0, S.bvh_nodes[base + cur.first].child1};
+            for (int k = 1; k >= 0; k--) {
+                if (!inner(ch[k])) continue;
+                const uint32_t nu = (uint32_t)S.rb_bvh_nodes.size() - first;
+                S.rb_bvh_nodes.push_back(S.bvh_nodes[base + (uint32_t)ch[k] / 4]); S.rb_bvh_nodes.back().parent = cur.second * 4;
+                todo.emplace_back((uint32_t)ch[k] / 4, nu);
+                ch[k] = (int)(nu * 4);
+            }
+            S.rb_bvh_nodes[first + cur.second].child0 = ch[0]; S.rb_bvh_nodes[first + cur.second].child1 = ch[1];
+        }
+        ctl_mesh pm = S.meshes[S.nodes[e.node].mesh_index]; pm.bvh_node_offset = first * 4;
+        S.rb_meshes.push_back(pm);
+        ctl_node pn = S.nodes[e.node]; pn.mesh_index = (uint32_t)S.rb_meshes.size() - 1;
+        e.out_node = (uint32_t)S.rb_nodes.size();
+        S.rb_nodes.push_back(pn);
+        S.rb_node_xf.insert(S.rb_node_xf.end(), S.node_xf.begin() + 16 * e.node, S.node_xf.begin() + 16 * e.node + 16);
+        S.rb_node_inv_xf.insert(S.rb_node_inv_xf.end(), S.node_inv_xf.begin() + 16 * e.node, S.node_inv_xf.begin() + 16 * e.node + 16);
+        S.rb_node_alias.push_back(e.node);
+    }
+    std::vector<uint32_t> ord; std::vector<uint8_t> last;
+    build_bvh(entry_box, 1, S.rb_scene_bvh, ord, last);
+    for (auto& n : S.rb_scene_bvh) {
+        if (n.child0 < 0) n.child0 = ~(int)done[ord[~n.child0]].out_node;
+        if (n.child1 < 0) n.child1 = ~(int)done[ord[~n.child1]].out_node;
+    }
+    S.rb_active = true;
 }
 
 void SceneStorage::fill_view(ctl_scene_view* v) const {
     memset(v, 0, sizeof(*v));
-    v->bvh_nodes = bvh_nodes.data(); v->n_bvh_nodes = (uint32_t)bvh_nodes.size();
+    const bool rb = rb_active;
+    v->bvh_nodes = rb ? rb_bvh_nodes.data() : bvh_nodes.data(); v->n_bvh_nodes = (uint32_t)(rb ? rb_bvh_nodes.size() : bvh_nodes.size());
     v->woop = woop.data(); v->n_woop = (uint32_t)woop.size();
     v->tri_index = tri_index.data(); v->n_tri_index = (uint32_t)tri_index.size();
     v->tri_data = tri_data.data(); v->n_tri_data = (uint32_t)tri_data.size();
-    v->meshes = meshes.data(); v->n_meshes = (uint32_t)meshes.size();
-    v->nodes = nodes.data(); v->n_nodes = (uint32_t)nodes.size();
-    v->node_xf = node_xf.data(); v->node_inv_xf = node_inv_xf.data();
-    v->scene_bvh_nodes = scene_bvh.data(); v->n_scene_bvh_nodes = (uint32_t)scene_bvh.size();
-    v->scene_start_node = scene_start;
+    v->meshes = rb ? rb_meshes.data() : meshes.data(); v->n_meshes = (uint32_t)(rb ? rb_meshes.size() : meshes.size());
+    v->nodes = rb ? rb_nodes.data() : nodes.data(); v->n_nodes = (uint32_t)(rb ? rb_nodes.size() : nodes.size());
+    v->node_xf = rb ? rb_node_xf.data() : node_xf.data(); v->node_inv_xf = rb ? rb_node_inv_xf.data() : node_inv_xf.data();
+    v->scene_bvh_nodes = rb ? rb_scene_bvh.data() : scene_bvh.data(); v->n_scene_bvh_nodes = (uint32_t)(rb ? rb_scene_bvh.size() : scene_bvh.size());
+    v->scene_start_node = rb ? 0 : scene_start;
+    v->node_alias = rb ? rb_node_alias.data() : nullptr;
     v->materials = materials.data(); v->n_materials = (uint32_t)materials.size();
     v->lights = lights.data(); v->n_lights_buf = (uint32_t)lights.size();
     v->light_tris = light_tris.data(); v->n_light_tris = (uint32_t)light_tris.size();

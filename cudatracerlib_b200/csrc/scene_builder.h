@@ -76,6 +76,16 @@ struct SceneStorage {
     ctl_camera camera;
     Box box;
     float ray_eps = 0;
+    // Partial re-braiding of the scene level (opt-in, rebraid()): instances whose boxes overlap are opened into sub-tree entries.  The combined arrays
+    // (real + pseudo nodes / meshes / BVH nodes) live beside the real ones, which stay what every other function reads; fill_view hands out the
+    // combined set while rb_active.
+    uint32_t rebraid_entries = 0;                  // budget of scene-level leaves; 0 = off (or CTL_REBRAID in the environment)
+    bool rb_active = false;
+    std::vector<ctl_bvh_node> rb_bvh_nodes, rb_scene_bvh;
+    std::vector<ctl_mesh> rb_meshes;
+    std::vector<ctl_node> rb_nodes;
+    std::vector<float> rb_node_xf, rb_node_inv_xf;
+    std::vector<uint32_t> rb_node_alias;           // real node of every (pseudo-)node
     void fill_view(ctl_scene_view* v) const;
 };
 

@@ -196,6 +196,7 @@ typedef struct ctl_scene_view {
     ctl_camera camera;                                               /* m_Camera       */
     float box_min[3], box_max[3];                                    /* m_sBox         */
     float ray_eps;                                                   /* m_rayTraceEps  */
+    const uint32_t* node_alias; /* NULL, or n_nodes entries when the scene level was re-braided (ctl_scene_set_rebraid): the instance each (pseudo-)node stands for */
 } ctl_scene_view;
 
 /* ---- host-side scene construction (replaces DynamicScene + SplitBVHBuilder
@@ -240,6 +241,12 @@ int  ctl_scene_get_mesh_triangles(const ctl_scene*, uint32_t mesh, float* verts9
  * ray epsilon); mesh BVHs / Woop triangles / TriangleData are untouched.  Views obtained before the call are invalidated. */
 int  ctl_scene_set_node_transform(ctl_scene*, uint32_t node, const float* xf16);
 /* == DynamicScene::getKernelSceneData(false) (Engine/DynamicScene.cpp:567-589): the flat view of the host arrays; valid until the scene is changed or destroyed */
+/* Opt-in partial re-braiding of the scene level (no reference counterpart; its BVHRebuilder keeps one leaf per instance): instances with large,
+ * overlapping boxes are opened into up to max_entries (instance, sub-tree) leaves, each an ordinary node + mesh record over a re-based copy of the
+ * sub-tree, so the traversal kernels and the data layout are unchanged.  Same hits; the node index reported for a hit may be a pseudo-node, whose
+ * instance is view.node_alias[index].  0 = off (default).  Re-assembles the node level: obtain the view again, then ctl_upload_scene (a re-braided
+ * view cannot go through ctl_update_scene_nodes: mesh-level arrays change with it).  EXPERIMENTAL in round 1: measured on the CPU oracle only. */
+int  ctl_scene_set_rebraid(ctl_scene*, uint32_t max_entries);
 int  ctl_scene_get_view(const ctl_scene*, ctl_scene_view* out);
 /* == DynamicScene::~DynamicScene (Engine/DynamicScene.cpp:219) */
 void ctl_scene_destroy(ctl_scene*);
