@@ -300,6 +300,7 @@ int ctl_scene_rebuild_bvh_gpu(ctl_scene* s, int device, float* build_ms_total) {
         }
     }
     S.bvh_nodes.swap(all_nodes); S.woop.swap(all_woop); S.tri_index.swap(all_index); S.meshes = meshes;
+    if (S.rb_active) { try { ctlb::assemble_nodes(S); } catch (const std::exception& e) { return set_err(e.what()); } }   // re-braided entries are copies of the old sub-trees: redo them
     if (build_ms_total) *build_ms_total = total;
     return 0;
 }
