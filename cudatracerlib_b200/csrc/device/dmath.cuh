@@ -72,6 +72,10 @@ struct F8 { float4 lo, hi; };
 #endif
 CTL_DEV F8 ldg256(const void* p) {
     F8 r;
+#ifndef __CUDACC__   // host build of the kernel source (tests/traverse_emulate.cpp): a plain 32-byte read
+    r.lo = ((const float4*)p)[0]; r.hi = ((const float4*)p)[1];
+    return r;
+#endif
 #if CTL_NODE_EVICT_LAST
     asm("ld.global.nc.L1::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w) : "l"(p));
