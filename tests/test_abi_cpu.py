@@ -283,7 +283,7 @@ def test_scene_from_mesh_validates_and_survives_degenerate_geometry(built_lib, o
     """ctl_scene_create_from_mesh refuses indices outside the vertex / material arrays (the reference's Mesh::CompileMesh trusts its compilers;
     a C ABI cannot), and the mesh builder terminates with a valid tree on geometry SAH cannot separate: coincident, collinear and point
     triangles, one far outlier, sticks through one point."""
-    mat = api.Material(); mat.type = 1
+    mat = api.Material()                                               # zero-filled record = diffuse, black
     cam = ((0, 0, -5.0), (0, 0, 0), (0, 1, 0), 60.0, 16, 16)
     tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
     z1 = np.zeros((1, 3), np.float32)
