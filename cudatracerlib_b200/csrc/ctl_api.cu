@@ -79,6 +79,7 @@ struct ctl_ctx {
     DevBuf<unsigned long long> stats; // [0] rays_last [1] rays_total [2..4] ext visits [5] ext rays [6..8] shadow visits [9] shadow rays
     DevBuf<float> own_accum; float* accum = nullptr; DevBuf<uchar4> resolve_tmp, pipe_rgbe; DevBuf<float4> pipe_partial; DevBuf<float> pipe_lum;
     DevBuf<ctl_pixel_variance_info> d_var; int variance_buffer = 0;
+    DevBuf<uint32_t> d_node_alias; uint32_t n_alias = 0;   // re-braided scene: instance of every (pseudo-)node, for the node indices the API reports
     DevBuf<uchar4> nlm_cached; DevBuf<float> nlm_varh, nlm_weights; long long nlm_last_update = -1; size_t nlm_pixels = 0;   // NonLocalMeansFilter state (m_cachedImg, m_weightBuffer, last_iter_weight_update)
     unsigned captured_n = 0; DevBuf<unsigned> d_captured_n;
     uint32_t passes_done = 0;
@@ -355,7 +356,7 @@ void ctl_destroy(ctl_ctx* c) {
     if (c->h_tab1) cudaFreeHost(c->h_tab1); if (c->h_tab2) cudaFreeHost(c->h_tab2); if (c->h_tab_free) cudaEventDestroy(c->h_tab_free);
     c->cf.release(); c->cl.release(); c->nor.release(); c->px.release(); c->rays_a.release(); c->rays_b.release(); c->hit_a.release(); c->sh_rays.release();
     c->sh_payload.release(); c->capture.release(); c->path_a.release(); c->path_b.release(); c->path_c.release(); c->rays_c.release(); c->sort_keys.release(); c->sort_hist.release(); c->sort_offsets.release(); c->mat_hist.release(); c->mat_cls.release(); c->mat_order.release(); c->hit_node.release(); c->counters.release(); c->stats.release();
-    c->own_accum.release(); c->d_captured_n.release(); c->resolve_tmp.release(); c->pipe_rgbe.release(); c->pipe_partial.release(); c->pipe_lum.release(); c->d_var.release(); c->nlm_cached.release(); c->nlm_varh.release(); c->nlm_weights.release(); c->nlm_last_update = -1; c->nlm_pixels = 0;
+    c->own_accum.release(); c->d_captured_n.release(); c->resolve_tmp.release(); c->pipe_rgbe.release(); c->pipe_partial.release(); c->pipe_lum.release(); c->d_var.release(); c->nlm_cached.release(); c->nlm_varh.release(); c->nlm_weights.release(); c->nlm_last_update = -1; c->nlm_pixels = 0; c->d_node_alias.release();
     c->w_thr.release(); c->w_lxy.release(); c->w_df.release(); c->w_ray.release(); c->w_misc.release(); c->w_res.release(); c->w_desc.release();
     for (int k = 0; k < 2; k++) { c->w_sec[k].release(); c->w_sres[k].release(); }
     for (auto e : c->stage_ev) cudaEventDestroy(e);
@@ -420,6 +421,7 @@ int ctl_upload_scene(ctl_ctx* c, const ctl_scene_view* v) {
     CK(c->d_scene_nodes.upload(v->scene_bvh_nodes, v->n_scene_bvh_nodes)); CK(c->d_bvh_nodes.upload(v->bvh_nodes, v->n_bvh_nodes));
     CK(c->d_woop.upload(v->woop, v->n_woop)); CK(c->d_tri_index.upload(v->tri_index, v->n_tri_index)); CK(c->d_tri_data.upload(v->tri_data, v->n_tri_data));
     CK(c->d_meshes.upload(v->meshes, v->n_meshes)); CK(c->d_nodes.upload(v->nodes, v->n_nodes));
+    c->n_alias = 0; if (v->node_alias) { CK(c->d_node_alias.upload(v->node_alias, v->n_nodes)); c->n_alias = v->n_nodes; }
     CK(c->d_xf.upload(v->node_xf, (size_t)v->n_nodes * 16)); CK(c->d_inv_xf.upload(v->node_inv_xf, (size_t)v->n_nodes * 16));
     CK(c->d_materials.upload(v->materials, v->n_materials)); CK(c->d_lights.upload(v->lights, v->n_lights_buf));
     CK(c->d_light_tris.upload(v->light_tris, v->n_light_tris)); CK(c->d_light_cdf.upload(v->light_cdf_data, v->n_light_cdf_data));
@@ -541,6 +543,14 @@ int ctl_read_sample_tables(ctl_ctx* c, int table_set, float* d1, float* d2) {
 static int grid_for(const ctl_ctx* c, int per_sm) { return c->n_sm * per_sm; }
 
 
+// Re-braided scenes (ctl_scene_set_rebraid): the traversal reports the pseudo-node it hit; API results name the instance, as the reference's would.
+// res: n records of stride_words 32-bit words, node index at node_word; misses hold 0xffffffff and are left alone.
+__global__ void __launch_bounds__(256) k_alias_nodes(uint32_t* __restrict__ res, int n, int stride_words, int node_word, const uint32_t* __restrict__ alias, uint32_t n_alias) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t v = res[(size_t)i * stride_words + node_word];
+        if (v < n_alias) res[(size_t)i * stride_words + node_word] = alias[v];
+    }
+}
 int ctl_intersect(ctl_ctx* c, int n, const void* d_rays, void* d_results, int any_hit, void* stream) {
     if (!c || !c->has_scene) return set_err("no scene uploaded");
     if (n < 0) return set_err("negative ray count");
@@ -552,6 +562,7 @@ int ctl_intersect(ctl_ctx* c, int n, const void* d_rays, void* d_results, int an
     const int grid = grid_for(c, c->trav_blocks_per_sm);
     if (any_hit) launch_intersect<2, true, false>(c, grid, st, c->scene, (const float4*)d_rays, nullptr, n, work, nullptr, nullptr, nullptr, nullptr, d_results, nullptr);
     else launch_intersect<2, false, false>(c, grid, st, c->scene, (const float4*)d_rays, nullptr, n, work, nullptr, nullptr, nullptr, nullptr, d_results, nullptr);
+    if (c->n_alias) k_alias_nodes<<<grid, 256, 0, st>>>((uint32_t*)d_results, n, 4, 1, c->d_node_alias.p, c->n_alias);   // traversalResult: {dist, nodeIdx, triIdx, bary}
     CK(cudaGetLastError());
     return 0;
 }
@@ -584,6 +595,7 @@ int ctl_trace_rays_host(ctl_ctx* c, int n, const ctl_traversal_ray* rays, ctl_tr
     const int grid = grid_for(c, c->trav_blocks_per_sm);
     if (counts) launch_intersect<3, false, true>(c, grid, c->stream, c->scene, dr.p, nullptr, n, work, nullptr, nullptr, nullptr, nullptr, dres.p, dcnt.p);
     else launch_intersect<3, false, false>(c, grid, c->stream, c->scene, dr.p, nullptr, n, work, nullptr, nullptr, nullptr, nullptr, dres.p, nullptr);
+    if (c->n_alias) k_alias_nodes<<<grid, 256, 0, c->stream>>>((uint32_t*)dres.p, n, 5, 4, c->d_node_alias.p, c->n_alias);   // TraceResult: {dist, u, v, triIdx, nodeIdx}
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(results, dres.p, (size_t)n * 20, cudaMemcpyDeviceToHost, c->stream));
     unsigned long long hc[4] = {0, 0, 0, 0};

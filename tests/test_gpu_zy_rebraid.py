@@ -31,15 +31,19 @@ def test_rebraided_scene_on_gpu(built_lib, orc):
     t.InitializeScene(s)
     g, gc = t.trace_rays(rays, counts=True)
     o, oc = orc.trace_rays(s.view, rays, counts=True)
-    for f in ("tri_idx", "node_idx"):
-        assert np.array_equal(g[f], o[f]), f
+    alias = np.ctypeslib.as_array(s.view.node_alias, (s.view.n_nodes,))
+    hit = g["tri_idx"] != 0xffffffff
+    assert np.array_equal(g["tri_idx"], o["tri_idx"])
+    assert np.array_equal(g["node_idx"][hit], alias[o["node_idx"][hit]]) and (g["node_idx"][~hit] == 0xffffffff).all()   # the API names the instance, the oracle the pseudo-node it walked
     for f in ("dist", "u", "v"):
         assert np.array_equal(g[f].view(np.uint32), o[f].view(np.uint32)), f
     assert gc == oc
     assert np.array_equal(g["tri_idx"], g0["tri_idx"]) and np.array_equal(g["dist"].view(np.uint32), g0["dist"].view(np.uint32))   # same hits as the plain view
-    alias = np.ctypeslib.as_array(s.view.node_alias, (s.view.n_nodes,))
-    hit = g["tri_idx"] != 0xffffffff
-    assert np.array_equal(alias[g["node_idx"][hit]], g0["node_idx"][hit])
+    assert np.array_equal(g["node_idx"], g0["node_idx"])                      # ... which is the node the plain view reports
+    seg = rays.copy(); seg["tmin"] = 1e-3; seg["tmax"] = 4.0
+    r16, r16_plain_nodes = t.intersect(seg), orc.intersect(s.view, seg)
+    h16 = r16["tri_idx"] != -1
+    assert np.array_equal(r16["tri_idx"], r16_plain_nodes["tri_idx"]) and np.array_equal(r16["node_idx"][h16], alias[r16_plain_nodes["node_idx"][h16]].astype(np.int32))
     t.DoPass(True); img = t.readAccumulator()
     assert np.array_equal(img["weight_sum"], plain["weight_sum"])
     assert np.allclose(img["rgb"], plain["rgb"], rtol=1e-5, atol=1e-7)     # same paths; only the order of the float atomics into a pixel may differ
