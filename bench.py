@@ -388,6 +388,8 @@ def main():
             "gpu_launches": int((launches_per_batch + 1) * (spp // batch) * args.steps),
             "wall_s_timed_region": t_wall, "image_mean_srgb8": img_mean,
         }
+        if scene.view.node_alias:   # opt-in A/B (CTL_REBRAID=<entries>): the scene level was re-braided
+            line["config"]["rebraid_entries"] = int(os.environ.get("CTL_REBRAID", "0")); line["config"]["scene_nodes"] = int(scene.view.n_nodes)
         if roof:
             line["roofline"] = roof
         if cpu:
