@@ -61,7 +61,8 @@ class Camera(C.Structure):
 
 
 class ImagePipeline(C.Structure):
-    """ctl_image_pipeline: filter_type -1 none / 0 box / 1 gaussian / 2 triangle / 3 mitchell / 4 lanczos; tonemap 0 none / 1 Reinhard05."""
+    """ctl_image_pipeline: filter_type -1 none / 0 box / 1 gaussian / 2 triangle / 3 mitchell / 4 lanczos / 5 non-local means (x_width = UpdateWeightPeriodicity,
+    param0 = k, param1 = sigma2Scale; needs PixelVarianceBuffer=1); tonemap 0 none / 1 Reinhard05."""
     _fields_ = [("filter_type", C.c_int32), ("x_width", C.c_float), ("y_width", C.c_float), ("param0", C.c_float), ("param1", C.c_float),
                 ("tonemap", C.c_int32), ("key", C.c_float), ("burn", C.c_float)]
 
