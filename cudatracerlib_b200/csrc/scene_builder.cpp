@@ -5,6 +5,9 @@
 #include <algorithm>
 #include <cstdio>
 #include <stdexcept>
+#include <atomic>
+#include <exception>
+#include <thread>
 
 namespace ctlb {
 
@@ -207,35 +210,18 @@ void assemble_scene(const std::vector<MeshInput>& meshes, const std::vector<Node
                     V3 cam_up, float fov_deg, int width, int height, SceneStorage& S) {
     S = SceneStorage();
     std::vector<Box> mesh_box(meshes.size());
-    for (size_t mi = 0; mi < meshes.size(); mi++) {
-        const MeshInput& M = meshes[mi];
-        if (!M.pre_tri_data.empty()) { // pre-compiled mesh (.xmsh): reference-layout arrays appended as they are
-            ctl_mesh km;
-            km.tri_offset = (uint32_t)S.tri_data.size(); km.bvh_node_offset = (uint32_t)S.bvh_nodes.size() * 4; km.bvh_tri_offset = (uint32_t)S.woop.size() * 3;
-            km.bvh_idx_offset = (uint32_t)S.tri_index.size(); km.mat_offset = (uint32_t)S.materials.size();
-            for (auto m : M.materials) { m.node_light_index = 0xffffffffu; S.materials.push_back(m); }
-            S.tri_data.insert(S.tri_data.end(), M.pre_tri_data.begin(), M.pre_tri_data.end());
-            S.bvh_nodes.insert(S.bvh_nodes.end(), M.pre_nodes.begin(), M.pre_nodes.end());
-            S.woop.insert(S.woop.end(), M.pre_woop.begin(), M.pre_woop.end());
-            S.tri_index.insert(S.tri_index.end(), M.pre_index.begin(), M.pre_index.end());
-            S.mesh_verts9.emplace_back(); // no source vertices: GPU BVH rebuilds are not available for imported meshes
-            mesh_box[mi] = M.pre_box;
-            S.meshes.push_back(km);
-            continue;
-        }
-        uint32_t nt = (uint32_t)M.indices.size() / 3;
+    // Meshes that need compiling (TriangleData, BVH, Woop records) are independent: they are built concurrently into per-mesh arrays and appended in
+    // mesh order afterwards, so the scene arrays do not depend on the schedule.
+    struct Built { std::vector<ctl_tri_data> tri_data; std::vector<float> verts9; std::vector<ctl_bvh_node> nodes; std::vector<ctl_woop_tri> woop; std::vector<uint32_t> index; Box box; std::exception_ptr err; };
+    std::vector<Built> built(meshes.size());
+    auto build_one = [&](size_t mi) {
+        const MeshInput& M = meshes[mi]; Built& B = built[mi];
+        const uint32_t nt = (uint32_t)M.indices.size() / 3;
         if (M.materials.size() > 255) throw std::runtime_error("more than 255 materials in one mesh (8-bit index, TriangleData.h:24)");
-        ctl_mesh km;
-        km.tri_offset = (uint32_t)S.tri_data.size();
-        km.bvh_node_offset = (uint32_t)S.bvh_nodes.size() * 4;
-        km.bvh_tri_offset = (uint32_t)S.woop.size() * 3;
-        km.bvh_idx_offset = (uint32_t)S.tri_index.size();
-        km.mat_offset = (uint32_t)S.materials.size();
-        for (auto m : M.materials) { m.node_light_index = 0xffffffffu; S.materials.push_back(m); }
         std::vector<V3> vn;
         compute_vertex_normals(M.verts, M.indices, vn);
         std::vector<Box> pb(nt);
-        S.mesh_verts9.emplace_back(); S.mesh_verts9.back().reserve((size_t)nt * 9);
+        B.verts9.reserve((size_t)nt * 9); B.tri_data.reserve(nt);
         for (uint32_t t = 0; t < nt; t++) {
             V3 p[3], n[3];
             float uv[6] = {0, 0, 0, 0, 0, 0};
@@ -243,24 +229,58 @@ void assemble_scene(const std::vector<MeshInput>& meshes, const std::vector<Node
                 const uint32_t vi = M.indices[t * 3 + k];
                 p[k] = M.verts[vi]; n[k] = M.normals.empty() ? vn[vi] : normalize(M.normals[vi]); pb[t].grow(p[k]);
                 if (!M.uvs.empty()) { uv[2 * k] = M.uvs[2 * vi]; uv[2 * k + 1] = M.uvs[2 * vi + 1]; }
-                S.mesh_verts9.back().insert(S.mesh_verts9.back().end(), {p[k].x, p[k].y, p[k].z});
+                B.verts9.insert(B.verts9.end(), {p[k].x, p[k].y, p[k].z});
             }
             ctl_tri_data td;
             encode_tri_data(p, n, uv, M.mat_index[t], &td);
-            S.tri_data.push_back(td);
-            mesh_box[mi].grow(pb[t]);
+            B.tri_data.push_back(td);
+            B.box.grow(pb[t]);
         }
-        std::vector<ctl_bvh_node> bn; std::vector<uint32_t> ord; std::vector<uint8_t> last;
+        std::vector<uint32_t> ord; std::vector<uint8_t> last;
         const char* which = getenv("CTL_BVH_BUILDER");
-        if (which && std::string(which) == "sah") build_bvh(pb, 8, bn, ord, last);
-        else build_sbvh(S.mesh_verts9.back().data(), nt, 8, bn, ord, last); // maxLeafSize 8: BVHBuilderHelper.cpp:119
-        S.bvh_nodes.insert(S.bvh_nodes.end(), bn.begin(), bn.end());
+        if (which && std::string(which) == "sah") build_bvh(pb, 8, B.nodes, ord, last);
+        else build_sbvh(B.verts9.data(), nt, 8, B.nodes, ord, last); // maxLeafSize 8: BVHBuilderHelper.cpp:119
+        B.woop.resize(ord.size()); B.index.resize(ord.size());
         for (size_t s = 0; s < ord.size(); s++) {
-            uint32_t t = ord[s];
-            ctl_woop_tri w;
-            encode_woop(M.verts[M.indices[t * 3]], M.verts[M.indices[t * 3 + 1]], M.verts[M.indices[t * 3 + 2]], &w);
-            S.woop.push_back(w);
-            S.tri_index.push_back((t << 1) | (last[s] ? 1u : 0u));
+            const uint32_t t = ord[s];
+            encode_woop(M.verts[M.indices[t * 3]], M.verts[M.indices[t * 3 + 1]], M.verts[M.indices[t * 3 + 2]], &B.woop[s]);
+            B.index[s] = (t << 1) | (last[s] ? 1u : 0u);
+        }
+    };
+    {
+        std::vector<size_t> todo;
+        for (size_t mi = 0; mi < meshes.size(); mi++) if (meshes[mi].pre_tri_data.empty()) todo.push_back(mi);
+        std::atomic<size_t> next(0);
+        auto worker = [&]() { for (size_t k; (k = next.fetch_add(1)) < todo.size();) { try { build_one(todo[k]); } catch (...) { built[todo[k]].err = std::current_exception(); } } };
+        const size_t n_workers = std::min<size_t>(todo.size(), std::max(1u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < n_workers; t++) pool.emplace_back(worker);
+        worker();
+        for (auto& th : pool) th.join();
+        for (size_t mi : todo) if (built[mi].err) std::rethrow_exception(built[mi].err);
+    }
+    for (size_t mi = 0; mi < meshes.size(); mi++) {
+        const MeshInput& M = meshes[mi];
+        ctl_mesh km;
+        km.tri_offset = (uint32_t)S.tri_data.size(); km.bvh_node_offset = (uint32_t)S.bvh_nodes.size() * 4; km.bvh_tri_offset = (uint32_t)S.woop.size() * 3;
+        km.bvh_idx_offset = (uint32_t)S.tri_index.size(); km.mat_offset = (uint32_t)S.materials.size();
+        for (auto m : M.materials) { m.node_light_index = 0xffffffffu; S.materials.push_back(m); }
+        if (!M.pre_tri_data.empty()) { // pre-compiled mesh (.xmsh): reference-layout arrays appended as they are
+            S.tri_data.insert(S.tri_data.end(), M.pre_tri_data.begin(), M.pre_tri_data.end());
+            S.bvh_nodes.insert(S.bvh_nodes.end(), M.pre_nodes.begin(), M.pre_nodes.end());
+            S.woop.insert(S.woop.end(), M.pre_woop.begin(), M.pre_woop.end());
+            S.tri_index.insert(S.tri_index.end(), M.pre_index.begin(), M.pre_index.end());
+            S.mesh_verts9.emplace_back(); // no source vertices: GPU BVH rebuilds are not available for imported meshes
+            mesh_box[mi] = M.pre_box;
+        } else {
+            Built& B = built[mi];
+            S.tri_data.insert(S.tri_data.end(), B.tri_data.begin(), B.tri_data.end());
+            S.bvh_nodes.insert(S.bvh_nodes.end(), B.nodes.begin(), B.nodes.end());
+            S.woop.insert(S.woop.end(), B.woop.begin(), B.woop.end());
+            S.tri_index.insert(S.tri_index.end(), B.index.begin(), B.index.end());
+            S.mesh_verts9.emplace_back(std::move(B.verts9));
+            mesh_box[mi] = B.box;
+            B = Built();
         }
         S.meshes.push_back(km);
     }
