@@ -11,7 +11,9 @@
 //   * depth(scene tree) + 1 + depth(mesh tree) + 1 fits the 64-entry traversal stack for every instance;
 //   * mesh / material / light indices of nodes, triangles and lights are in range.
 // Box planes are not examined: NaN or inverted boxes only make rays miss.
+#include <algorithm>
 #include <cstring>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -50,15 +52,19 @@ template <typename LEAF> TreeInfo walk_tree(const ctl_bvh_node* nodes, uint32_t 
 } // namespace
 
 // Mesh level of one mesh: nodes [0, n_nodes), leaf words [0, n_refs) with triangle ids < n_tris.  Returns the tree depth.
-int validate_mesh_bvh(const ctl_bvh_node* nodes, uint32_t n_nodes, const uint32_t* index, uint32_t n_refs, uint32_t n_tris, const std::string& what) {
+static int validate_mesh_tree(const ctl_bvh_node* nodes, uint32_t n_nodes, const uint32_t* index, uint32_t n_refs, uint32_t n_tris, const std::string& what, bool check_words) {
     if (!n_nodes || !n_refs) throw std::runtime_error(what + ": empty BVH");
     // end_after[i]: a run starting at i meets an end flag before the array ends  <=>  some word in [i, n_refs) has bit 0; true for all i iff the last has
     if (!(index[n_refs - 1] & 1u)) throw std::runtime_error(what + ": the last leaf run has no end flag");
-    for (uint32_t i = 0; i < n_refs; i++) if ((index[i] >> 1) >= n_tris) throw std::runtime_error(what + ": leaf word " + std::to_string(i) + " references triangle " + std::to_string(index[i] >> 1) + " of " + std::to_string(n_tris));
+    if (check_words) for (uint32_t i = 0; i < n_refs; i++) if ((index[i] >> 1) >= n_tris) throw std::runtime_error(what + ": leaf word " + std::to_string(i) + " references triangle " + std::to_string(index[i] >> 1) + " of " + std::to_string(n_tris));
     const TreeInfo t = walk_tree(nodes, n_nodes, 0, what, [&](uint32_t ref) {
         if (ref >= n_refs) throw std::runtime_error(what + ": leaf reference " + std::to_string(ref) + " outside the reference array (" + std::to_string(n_refs) + ")");
     });
     return t.depth;
+}
+
+int validate_mesh_bvh(const ctl_bvh_node* nodes, uint32_t n_nodes, const uint32_t* index, uint32_t n_refs, uint32_t n_tris, const std::string& what) {
+    return validate_mesh_tree(nodes, n_nodes, index, n_refs, n_tris, what, true);
 }
 
 void validate_view(const ctl_scene_view& v) {
@@ -67,25 +73,26 @@ void validate_view(const ctl_scene_view& v) {
         throw std::runtime_error("scene view: null array");
     if (v.n_woop != v.n_tri_index) throw std::runtime_error("scene view: woop / index arrays differ in length");
     std::vector<int> mesh_depth(v.n_meshes, -1);
+    std::set<uint32_t> words_checked;
+    // arrays of a mesh end where the next larger offset of any mesh begins (re-braided views hold many mesh records over the same triangle / reference ranges)
+    std::vector<uint32_t> node_offs, ref_offs, tri_offs;
+    for (uint32_t o = 0; o < v.n_meshes; o++) { node_offs.push_back(v.meshes[o].bvh_node_offset / 4); ref_offs.push_back(v.meshes[o].bvh_idx_offset); tri_offs.push_back(v.meshes[o].tri_offset); }
+    std::sort(node_offs.begin(), node_offs.end()); std::sort(ref_offs.begin(), ref_offs.end()); std::sort(tri_offs.begin(), tri_offs.end());
+    auto next_after = [](const std::vector<uint32_t>& sorted, uint32_t x, uint32_t end) { auto it = std::upper_bound(sorted.begin(), sorted.end(), x); return it == sorted.end() || *it > end ? end : *it; };
     auto mesh_extent = [&](uint32_t m, uint32_t& node0, uint32_t& n_nodes, uint32_t& ref0, uint32_t& n_refs, uint32_t& n_tris) {
         const ctl_mesh& K = v.meshes[m];
-        // arrays of a mesh end where the next mesh (in array order of its offsets) begins; meshes are appended in order by every builder here
-        uint32_t node_end = v.n_bvh_nodes, ref_end = v.n_tri_index, tri_end = v.n_tri_data;
-        for (uint32_t o = 0; o < v.n_meshes; o++) {
-            const ctl_mesh& O = v.meshes[o];
-            if (O.bvh_node_offset / 4 > K.bvh_node_offset / 4 && O.bvh_node_offset / 4 < node_end) node_end = O.bvh_node_offset / 4;
-            if (O.bvh_idx_offset > K.bvh_idx_offset && O.bvh_idx_offset < ref_end) ref_end = O.bvh_idx_offset;
-            if (O.tri_offset > K.tri_offset && O.tri_offset < tri_end) tri_end = O.tri_offset;
-        }
         if ((K.bvh_node_offset & 3) || K.bvh_node_offset / 4 >= v.n_bvh_nodes || K.bvh_idx_offset >= v.n_tri_index || K.tri_offset >= v.n_tri_data)
             throw std::runtime_error("scene view: mesh " + std::to_string(m) + " offsets outside the arrays");
         if ((uint64_t)K.bvh_tri_offset != (uint64_t)K.bvh_idx_offset * 3) throw std::runtime_error("scene view: mesh " + std::to_string(m) + " woop offset is not 3 x its index offset");
-        node0 = K.bvh_node_offset / 4; n_nodes = node_end - node0; ref0 = K.bvh_idx_offset; n_refs = ref_end - ref0; n_tris = tri_end - K.tri_offset;
+        node0 = K.bvh_node_offset / 4; n_nodes = next_after(node_offs, node0, v.n_bvh_nodes) - node0;
+        ref0 = K.bvh_idx_offset; n_refs = next_after(ref_offs, ref0, v.n_tri_index) - ref0;
+        n_tris = next_after(tri_offs, K.tri_offset, v.n_tri_data) - K.tri_offset;
     };
     for (uint32_t m = 0; m < v.n_meshes; m++) {
         uint32_t node0, n_nodes, ref0, n_refs, n_tris;
         mesh_extent(m, node0, n_nodes, ref0, n_refs, n_tris);
-        mesh_depth[m] = validate_mesh_bvh(v.bvh_nodes + node0, n_nodes, v.tri_index + ref0, n_refs, n_tris, "mesh " + std::to_string(m));
+        const bool first_use = words_checked.insert(ref0).second;   // re-braided views: thousands of mesh records share one reference range -- its words are scanned once
+        mesh_depth[m] = validate_mesh_tree(v.bvh_nodes + node0, n_nodes, v.tri_index + ref0, n_refs, n_tris, "mesh " + std::to_string(m), first_use);
         const ctl_mesh& K = v.meshes[m];
         if (K.mat_offset > v.n_materials) throw std::runtime_error("scene view: mesh " + std::to_string(m) + " material offset out of range");
     }
