@@ -418,14 +418,27 @@ void rebraid(SceneStorage& S, const std::vector<Box>& node_box) {
     };
     auto cmp = [](const Entry& a, const Entry& b) { return a.area != b.area ? a.area < b.area : (a.node != b.node ? a.node > b.node : a.ref > b.ref); }; // max-heap on area, ties by index
     std::vector<Entry> heap, done;
-    auto place = [&](Entry e) { e.area = e.world.area(); if (openable(e)) { heap.push_back(e); std::push_heap(heap.begin(), heap.end(), cmp); } else done.push_back(e); };
+    // which entry to open next: the one whose box shrinks most when replaced by its two children (area - mean child area).  CTL_REBRAID_MODE=0 selects the
+    // plain "largest box first" of the paper for A/B; on config 4 at 1 024 entries the oracle counts 5 468 algorithmic bytes per ray against 5 682.
+    const int mode = getenv("CTL_REBRAID_MODE") ? atoi(getenv("CTL_REBRAID_MODE")) : 1;
+    auto child_boxes = [&](const Entry& e, Box& b0, Box& b1) {
+        const ctl_bvh_node& n = mesh_node(e.node, e.ref);
+        b0 = world_of(e.node, Box(V3(n.a[0], n.a[2], n.c[0]), V3(n.a[1], n.a[3], n.c[1]))); b1 = world_of(e.node, Box(V3(n.b[0], n.b[2], n.c[2]), V3(n.b[1], n.b[3], n.c[3])));
+    };
+    auto place = [&](Entry e) {
+        e.area = e.world.area();
+        if (!openable(e)) { done.push_back(e); return; }
+        if (mode == 1) { Box b0, b1; child_boxes(e, b0, b1); e.area = e.world.area() - 0.5f * (b0.area() + b1.area()); }
+        heap.push_back(e); std::push_heap(heap.begin(), heap.end(), cmp);
+    };
     for (uint32_t ni = 0; ni < n_real; ni++) place(Entry{ni, 0, node_box[ni], 0.0f, ni});
     while (!heap.empty() && heap.size() + done.size() < budget) {
         std::pop_heap(heap.begin(), heap.end(), cmp);
         const Entry e = heap.back(); heap.pop_back();
         const ctl_bvh_node& n = mesh_node(e.node, e.ref);
-        place(Entry{e.node, n.child0, world_of(e.node, Box(V3(n.a[0], n.a[2], n.c[0]), V3(n.a[1], n.a[3], n.c[1]))), 0.0f, 0});
-        place(Entry{e.node, n.child1, world_of(e.node, Box(V3(n.b[0], n.b[2], n.c[2]), V3(n.b[1], n.b[3], n.c[3]))), 0.0f, 0});
+        Box b0, b1; child_boxes(e, b0, b1);
+        place(Entry{e.node, n.child0, b0, 0.0f, 0});
+        place(Entry{e.node, n.child1, b1, 0.0f, 0});
     }
     done.insert(done.end(), heap.begin(), heap.end());
     std::sort(done.begin(), done.end(), [](const Entry& a, const Entry& b) { return a.node != b.node ? a.node < b.node : a.ref < b.ref; });
