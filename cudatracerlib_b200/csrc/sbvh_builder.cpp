@@ -363,10 +363,93 @@ double traversal_cost(const Tree& T, const std::vector<SampleRay>& rays) {
 
 static void build_sbvh_alpha(const float* verts9, uint32_t n_tris, int max_leaf, float alpha, std::vector<ctl_bvh_node>& nodes_out, std::vector<uint32_t>& ordered, std::vector<uint8_t>& last);
 
+// Post-pass: tree rotations (Kensler, "Tree rotations for improving bounding volume hierarchies",
+// 2008) on the finished node array.  For a node with children L, R the four exchanges "child <-> grandchild on the other side" are tried and the one
+// that shrinks the surface area of the rebuilt inner child most is kept; sweeps run children-first until nothing improves.  Leaves (index runs) are
+// never touched, so the reference set and the hits are unchanged; the array is re-laid out in pre-order at the end.
+namespace {
+inline Box child_box(const ctl_bvh_node& n, int w) { return w == 0 ? Box(V3(n.a[0], n.a[2], n.c[0]), V3(n.a[1], n.a[3], n.c[1])) : Box(V3(n.b[0], n.b[2], n.c[2]), V3(n.b[1], n.b[3], n.c[3])); }
+inline void put_box(ctl_bvh_node& n, int w, const Box& b) {
+    if (w == 0) { n.a[0] = b.lo.x; n.a[1] = b.hi.x; n.a[2] = b.lo.y; n.a[3] = b.hi.y; n.c[0] = b.lo.z; n.c[1] = b.hi.z; }
+    else { n.b[0] = b.lo.x; n.b[1] = b.hi.x; n.b[2] = b.lo.y; n.b[3] = b.hi.y; n.c[2] = b.lo.z; n.c[3] = b.hi.z; }
+}
+inline int& child_ref(ctl_bvh_node& n, int w) { return w == 0 ? n.child0 : n.child1; }
+inline bool is_inner(int c) { return c >= 0 && c != CTL_SENTINEL; }
+
+size_t rotate_tree(std::vector<ctl_bvh_node>& nodes, int max_sweeps) {
+    if (nodes.size() < 3) return 0;
+    size_t total = 0;
+    // children-first order: reverse of a pre-order walk from the root (recomputed every sweep: rotations move sub-trees)
+    for (int sweep = 0; sweep < max_sweeps; sweep++) {
+        std::vector<uint32_t> order; order.reserve(nodes.size());
+        std::vector<uint32_t> st = {0};
+        while (!st.empty()) { const uint32_t i = st.back(); st.pop_back(); order.push_back(i); if (is_inner(nodes[i].child0)) st.push_back((uint32_t)nodes[i].child0 / 4); if (is_inner(nodes[i].child1)) st.push_back((uint32_t)nodes[i].child1 / 4); }
+        size_t done = 0;
+        for (size_t k = order.size(); k-- > 0;) {
+            ctl_bvh_node& N = nodes[order[k]];
+            if (N.child1 == CTL_SENTINEL) continue;
+            float best = 0.0f; int best_side = -1, best_g = -1;   // exchange child (1 - side) with grandchild g of child `side`; best = most negative area change
+            for (int side = 0; side < 2; side++) {
+                const int c = child_ref(N, side);
+                if (!is_inner(c)) continue;
+                const ctl_bvh_node& C = nodes[(uint32_t)c / 4];
+                if (C.child1 == CTL_SENTINEL) continue;
+                const Box other = child_box(N, 1 - side);
+                const float old_area = child_box(N, side).area();
+                for (int g = 0; g < 2; g++) {   // g goes up, `other` takes its place next to grandchild 1 - g
+                    Box nb = other; nb.grow(child_box(C, 1 - g));
+                    const float delta = nb.area() - old_area;
+                    if (delta < -1e-5f * old_area && delta < best) { best = delta; best_side = side; best_g = g; }
+                }
+            }
+            if (best_side < 0) continue;
+            const int side = best_side, g = best_g;
+            ctl_bvh_node& C = nodes[(uint32_t)child_ref(N, side) / 4];
+            const int up = child_ref(C, g), down = child_ref(N, 1 - side);
+            const Box up_box = child_box(C, g), down_box = child_box(N, 1 - side);
+            child_ref(C, g) = down; put_box(C, g, down_box);
+            child_ref(N, 1 - side) = up; put_box(N, 1 - side, up_box);
+            Box cb = child_box(C, 0); cb.grow(child_box(C, 1)); put_box(N, side, cb);
+            done++;
+        }
+        total += done;
+        if (!done) break;
+    }
+    // pre-order re-layout, parents re-linked
+    std::vector<ctl_bvh_node> out; out.reserve(nodes.size());
+    std::vector<std::pair<uint32_t, uint32_t>> st;   // (old index, new index)
+    out.push_back(nodes[0]); out[0].parent = 0xffffffffu; st.emplace_back(0u, 0u);
+    while (!st.empty()) {
+        const auto cur = st.back(); st.pop_back();
+        int ch[2] = {nodes[cur.first].child0, nodes[cur.first].child1};
+        for (int k = 1; k >= 0; k--) {
+            if (!is_inner(ch[k])) continue;
+            const uint32_t nu = (uint32_t)out.size();
+            out.push_back(nodes[(uint32_t)ch[k] / 4]); out.back().parent = cur.second * 4;
+            st.emplace_back((uint32_t)ch[k] / 4, nu);
+            ch[k] = (int)(nu * 4);
+        }
+        out[cur.second].child0 = ch[0]; out[cur.second].child1 = ch[1];
+    }
+    nodes.swap(out);
+    return total;
+}
+} // namespace
+
+// Post-pass of every mesh tree: up to 8 sweeps of tree rotations (CTL_SBVH_ROTATE=<sweeps> overrides, 0 = off).  ~800 rotations on the 57 K-node tree of
+// config 2 take the oracle's path rays from 27.9 to 26.7 inner nodes per ray (-3.5 % algorithmic bytes); hits, images and ray counts are unchanged.
+static void finish_tree(std::vector<ctl_bvh_node>& nodes) {
+    const char* r = getenv("CTL_SBVH_ROTATE");
+    const int sweeps = r ? atoi(r) : 8;
+    if (sweeps <= 0) return;
+    const size_t n_rot = rotate_tree(nodes, sweeps);
+    if (getenv("CTL_SBVH_VERBOSE")) fprintf(stderr, "  tree rotations: %zu\n", n_rot);
+}
+
 void build_sbvh(const float* verts9, uint32_t n_tris, int max_leaf, std::vector<ctl_bvh_node>& nodes_out, std::vector<uint32_t>& ordered, std::vector<uint8_t>& last) {
-    if (getenv("CTL_SBVH_ALPHA")) { build_sbvh_alpha(verts9, n_tris, max_leaf, (float)atof(getenv("CTL_SBVH_ALPHA")), nodes_out, ordered, last); return; } // experiments: no selection
+    if (getenv("CTL_SBVH_ALPHA")) { build_sbvh_alpha(verts9, n_tris, max_leaf, (float)atof(getenv("CTL_SBVH_ALPHA")), nodes_out, ordered, last); finish_tree(nodes_out); return; } // experiments: no selection
     build_sbvh_alpha(verts9, n_tris, max_leaf, 1e-5f, nodes_out, ordered, last);   // the published default (and the reference's BuildParams::splitAlpha)
-    if (ordered.size() == n_tris || n_tris < 64) return;                           // no reference was split: nothing to choose
+    if (ordered.size() == n_tris || n_tris < 64) { finish_tree(nodes_out); return; } // no reference was split: nothing to choose
     std::vector<ctl_bvh_node> n2; std::vector<uint32_t> o2; std::vector<uint8_t> l2;
     build_sbvh_alpha(verts9, n_tris, max_leaf, 3.0e38f, n2, o2, l2);               // object splits only
     const Tree split{verts9, nodes_out, ordered, last}, plain{verts9, n2, o2, l2};
@@ -375,6 +458,7 @@ void build_sbvh(const float* verts9, uint32_t n_tris, int max_leaf, std::vector<
     const double c_split = traversal_cost(split, rays), c_plain = traversal_cost(plain, rays);
     if (getenv("CTL_SBVH_VERBOSE")) fprintf(stderr, "mesh %u tris: split tree %zu refs cost %.0f, plain tree cost %.0f over %zu walk rays -> %s\n", n_tris, ordered.size(), c_split, c_plain, rays.size(), c_plain < c_split ? "plain" : "split");
     if (c_plain < c_split) { nodes_out.swap(n2); ordered.swap(o2); last.swap(l2); }
+    finish_tree(nodes_out);
 }
 
 static void build_sbvh_alpha(const float* verts9, uint32_t n_tris, int max_leaf, float alpha, std::vector<ctl_bvh_node>& nodes_out, std::vector<uint32_t>& ordered, std::vector<uint8_t>& last) {
