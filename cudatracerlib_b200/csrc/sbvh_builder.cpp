@@ -566,9 +566,12 @@ static void finish_tree(std::vector<ctl_bvh_node>& nodes) {
     if (sweeps <= 0) return;   // CTL_SBVH_ROTATE=0: the builder's tree as it is (A/B)
     const char* q = getenv("CTL_SBVH_REINSERT");   // passes of sub-tree re-insertion before the rotations (0 = off); CTL_SBVH_REINSERT_FRAC = share of the nodes tried per pass
     const int ins_passes = q ? atoi(q) : 4;
+    const int rounds = getenv("CTL_SBVH_ROUNDS") ? atoi(getenv("CTL_SBVH_ROUNDS")) : 1;   // experiments: (re-insertion, rotations) repeated
+    for (int round = 0; round < rounds; round++) {
     const size_t n_ins = ins_passes > 0 ? reinsert_tree(nodes, ins_passes, getenv("CTL_SBVH_REINSERT_FRAC") ? (float)atof(getenv("CTL_SBVH_REINSERT_FRAC")) : 1.0f) : 0;
     const size_t n_rot = rotate_tree(nodes, sweeps);
     if (getenv("CTL_SBVH_VERBOSE")) fprintf(stderr, "  re-insertions: %zu, tree rotations: %zu\n", n_ins, n_rot);
+    }
 }
 
 void build_sbvh(const float* verts9, uint32_t n_tris, int max_leaf, std::vector<ctl_bvh_node>& nodes_out, std::vector<uint32_t>& ordered, std::vector<uint8_t>& last) {
