@@ -574,6 +574,8 @@ static void finish_tree(std::vector<ctl_bvh_node>& nodes) {
     }
 }
 
+void optimize_bvh(std::vector<ctl_bvh_node>& nodes) { finish_tree(nodes); }
+
 void build_sbvh(const float* verts9, uint32_t n_tris, int max_leaf, std::vector<ctl_bvh_node>& nodes_out, std::vector<uint32_t>& ordered, std::vector<uint8_t>& last) {
     if (getenv("CTL_SBVH_ALPHA")) { build_sbvh_alpha(verts9, n_tris, max_leaf, (float)atof(getenv("CTL_SBVH_ALPHA")), nodes_out, ordered, last); finish_tree(nodes_out); return; } // experiments: no selection
     build_sbvh_alpha(verts9, n_tris, max_leaf, 1e-5f, nodes_out, ordered, last);   // the published default (and the reference's BuildParams::splitAlpha)

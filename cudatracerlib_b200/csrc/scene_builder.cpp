@@ -483,6 +483,7 @@ void rebraid(SceneStorage& S, const std::vector<Box>& node_box) {
         if (n.child0 < 0) n.child0 = ~(int)done[ord[~n.child0]].out_node;
         if (n.child1 < 0) n.child1 = ~(int)done[ord[~n.child1]].out_node;
     }
+    // (the mesh trees' post-pass, optimize_bvh, was tried on this tree: -0.4 % algorithmic bytes at 1 024 entries, +7 % at 16: left out)
     S.rb_active = true;
 }
 

@@ -100,6 +100,9 @@ void build_bvh(const std::vector<Box>& prim_boxes, int max_leaf, std::vector<ctl
 void build_sbvh(const float* verts9, uint32_t n_tris, int max_leaf, std::vector<ctl_bvh_node>& nodes_out,
                 std::vector<uint32_t>& ordered_prims_out, std::vector<uint8_t>& last_in_leaf_out);
 
+// Post-build optimisation of a finished tree in the reference node layout (sub-tree re-insertion + rotations, sbvh_builder.cpp); leaves are untouched
+void optimize_bvh(std::vector<ctl_bvh_node>& nodes);
+
 // Woop unit-triangle transform (Engine/TriIntersectorData.cu:5-18); host + device (GPU BVH builder), same expressions
 CTLB_HD inline void encode_woop(V3 v0, V3 v1, V3 v2, ctl_woop_tri* out) {
     // M = [v0-v2 | v1-v2 | (v0-v2)x(v1-v2) | v2] (columns), inverted; store row2 (w negated), row0, row1.
