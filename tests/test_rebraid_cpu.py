@@ -49,7 +49,7 @@ def test_rebraided_view_same_hits_same_image_fewer_visits(built_lib, orc, kind, 
     assert rays_a == rays_b and img_a.tobytes() == img_b.tobytes()
     if kind == "c4":
         # fewer algorithmic bytes (node visits + instance entries); at this size (24 spheres + 3.4 K foliage triangles) the gain is small -- on the full 1 M-triangle config 4 the oracle
-        # counts 94.9 -> 70.3 inner nodes per ray (7 374 -> 5 468 algorithmic bytes) with 1 024 entries, 66.8 (5 425 bytes) with 4 096
+        # counts 90.4 -> 65.9 inner nodes per ray (7 089 -> 5 169 algorithmic bytes) with 1 024 entries
         assert api.traversal_bytes(cb, len(rays)) < api.traversal_bytes(ca, len(rays)), (ca, cb)
     s.setRebraid(0)
     assert (s.view.n_nodes, s.view.n_meshes, s.view.n_bvh_nodes) == (n_nodes, n_meshes, n_bvh) and not s.view.node_alias
