@@ -284,6 +284,7 @@ int ctl_scene_rebuild_bvh_gpu(ctl_scene* s, int device, float* build_ms_total) {
         uint32_t nn = 0; float ms = 0;
         if (ctl_bvh_build_gpu(device, S.mesh_verts9[mi].data(), nt, nodes.data(), &nn, woop.data(), index.data(), &ms)) return 1;
         total += ms;
+        if (getenv("CTL_LBVH_OPTIMIZE")) { nodes.resize(nn); ctlb::optimize_bvh(nodes); }   // experiment for round 2: the mesh trees' host post-pass (re-insertion + rotations) on the LBVH; node count unchanged
         meshes[mi].bvh_node_offset = (uint32_t)all_nodes.size() * 4;
         meshes[mi].bvh_tri_offset = (uint32_t)all_woop.size() * 3;
         meshes[mi].bvh_idx_offset = (uint32_t)all_index.size();

@@ -567,11 +567,21 @@ static void finish_tree(std::vector<ctl_bvh_node>& nodes) {
     const char* q = getenv("CTL_SBVH_REINSERT");   // passes of sub-tree re-insertion before the rotations (0 = off); CTL_SBVH_REINSERT_FRAC = share of the nodes tried per pass
     const int ins_passes = q ? atoi(q) : 4;
     const int rounds = getenv("CTL_SBVH_ROUNDS") ? atoi(getenv("CTL_SBVH_ROUNDS")) : 1;   // experiments: (re-insertion, rotations) repeated
+    const std::vector<ctl_bvh_node> before = nodes;
     for (int round = 0; round < rounds; round++) {
     const size_t n_ins = ins_passes > 0 ? reinsert_tree(nodes, ins_passes, getenv("CTL_SBVH_REINSERT_FRAC") ? (float)atof(getenv("CTL_SBVH_REINSERT_FRAC")) : 1.0f) : 0;
     const size_t n_rot = rotate_tree(nodes, sweeps);
     if (getenv("CTL_SBVH_VERBOSE")) fprintf(stderr, "  re-insertions: %zu, tree rotations: %zu\n", n_ins, n_rot);
     }
+    // the traversal stack holds 64 entries for the scene level and the mesh level together: an optimised tree deeper than 52 is not worth it
+    int max_depth = 0; std::vector<std::pair<uint32_t, int>> st = {{0u, 1}};
+    while (!st.empty()) {
+        const auto c = st.back(); st.pop_back();
+        if (c.second > max_depth) max_depth = c.second;
+        if (is_inner(nodes[c.first].child0)) st.emplace_back((uint32_t)nodes[c.first].child0 / 4, c.second + 1);
+        if (is_inner(nodes[c.first].child1)) st.emplace_back((uint32_t)nodes[c.first].child1 / 4, c.second + 1);
+    }
+    if (max_depth > 52) nodes = before;
 }
 
 void optimize_bvh(std::vector<ctl_bvh_node>& nodes) { finish_tree(nodes); }
