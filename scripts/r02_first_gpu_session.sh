@@ -23,6 +23,20 @@ except Exception as e:
 PY
   done
 done
+# 2b. post-build optimisation of the mesh trees (re-insertion + rotations, on by default): A/B against the builder's raw trees
+for wl in c2 c4; do
+  for rot in 0 8; do
+    CTL_SBVH_ROTATE=$rot timeout 400 python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > $O/r02a_treeopt_${wl}_$rot.json
+    python - $O/r02a_treeopt_${wl}_$rot.json $wl $rot <<'PY' >> $O/r02a_treeopt_summary.log
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read())
+    print(sys.argv[2], "CTL_SBVH_ROTATE", sys.argv[3], round(d["value"], 1), "Mrays/s", round(d["ms_per_step"], 2), "ms  roofline", round(d["roofline"]["frac"], 3), round(d["roofline"].get("bytes_per_ray", 0)), "B/ray")
+except Exception as e:
+    print(sys.argv[2], "CTL_SBVH_ROTATE", sys.argv[3], "FAILED", e)
+PY
+  done
+done
 # 3. ray-level micro-benchmark
 for wl in c2 c4; do timeout 300 python scripts/ray_microbench.py $wl > $O/r02a_ray_microbench_$wl.json 2> $O/r02a_ray_microbench_$wl.err; done
 # 4. NonLocalMeansFilter timing at 1920x1080 (CUDA events around the pipeline call) + launch list
