@@ -455,7 +455,7 @@ int ctl_upload_scene(ctl_ctx* c, const ctl_scene_view* v) {
 int ctl_update_scene_nodes(ctl_ctx* c, const ctl_scene_view* v) {
     if (!c || !v) return set_err("null argument");
     if (!c->has_scene) return set_err("no scene uploaded");
-    if (v->node_alias) return set_err("re-braided view: its mesh-level arrays change with the node level, use ctl_upload_scene");
+    if (v->node_alias || c->n_alias) return ctl_upload_scene(c, v);   // re-braided view (now or before): its mesh-level records follow the node level -> everything is uploaded
     if (v->n_bvh_nodes != c->d_bvh_nodes.n && v->n_bvh_nodes > c->d_bvh_nodes.n) return set_err("the view has other meshes than the uploaded scene: use ctl_upload_scene");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));

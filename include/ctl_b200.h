@@ -244,8 +244,8 @@ int  ctl_scene_set_node_transform(ctl_scene*, uint32_t node, const float* xf16);
 /* Opt-in partial re-braiding of the scene level (no reference counterpart; its BVHRebuilder keeps one leaf per instance): instances with large,
  * overlapping boxes are opened into up to max_entries (instance, sub-tree) leaves, each an ordinary node + mesh record over a re-based copy of the
  * sub-tree, so the traversal kernels and the data layout are unchanged.  Same hits; ctl_intersect / ctl_intersect_host / ctl_trace_rays_host report the
- * INSTANCE a hit belongs to (results pass through view.node_alias on the device), like the reference would.  0 = off (default).  Re-assembles the node level: obtain the view again, then ctl_upload_scene (a re-braided
- * view cannot go through ctl_update_scene_nodes: mesh-level arrays change with it).  EXPERIMENTAL in round 1: measured on the CPU oracle only. */
+ * INSTANCE a hit belongs to (results pass through view.node_alias on the device), like the reference would.  0 = off (default).  Re-assembles the node level: obtain the view again, then ctl_upload_scene
+ * (ctl_update_scene_nodes uploads everything for a re-braided view: its mesh-level records follow the node level).  EXPERIMENTAL in round 1: measured on the CPU oracle only. */
 int  ctl_scene_set_rebraid(ctl_scene*, uint32_t max_entries);
 int  ctl_scene_get_view(const ctl_scene*, ctl_scene_view* out);
 /* == DynamicScene::~DynamicScene (Engine/DynamicScene.cpp:219) */
