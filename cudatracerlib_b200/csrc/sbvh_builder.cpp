@@ -557,7 +557,7 @@ static size_t reinsert_tree(std::vector<ctl_bvh_node>& nodes, int passes, float 
     return moved;
 }
 
-// Post-pass of every mesh tree: sub-tree re-insertion (4 passes over all nodes), then up to 8 sweeps of tree rotations (CTL_SBVH_ROTATE=<sweeps> overrides,
+// Post-pass of every mesh tree: sub-tree re-insertion (2 passes over all nodes), then up to 8 sweeps of tree rotations (CTL_SBVH_ROTATE=<sweeps> overrides,
 // 0 = neither).  Together they take the oracle's path rays on config 2 from 27.9 to 25.1 inner nodes per ray (-7.4 % algorithmic bytes), config 4 -4.4 %.  ~1 700 rotations on the 57 K-node tree of
 // config 2 take the oracle's path rays from 27.9 to 26.2 inner nodes per ray (-4.8 % algorithmic bytes); hits, images and ray counts are unchanged.
 static void finish_tree(std::vector<ctl_bvh_node>& nodes) {
@@ -565,7 +565,7 @@ static void finish_tree(std::vector<ctl_bvh_node>& nodes) {
     const int sweeps = r ? atoi(r) : 8;
     if (sweeps <= 0) return;   // CTL_SBVH_ROTATE=0: the builder's tree as it is (A/B)
     const char* q = getenv("CTL_SBVH_REINSERT");   // passes of sub-tree re-insertion before the rotations (0 = off); CTL_SBVH_REINSERT_FRAC = share of the nodes tried per pass
-    const int ins_passes = q ? atoi(q) : 4;
+    const int ins_passes = q ? atoi(q) : 2;   // measured: 2 passes reach the result of 4 within 0.3 % (config 2: 2 060 vs 2 065 bytes per path ray)
     const int rounds = getenv("CTL_SBVH_ROUNDS") ? atoi(getenv("CTL_SBVH_ROUNDS")) : 1;   // experiments: (re-insertion, rotations) repeated
     const std::vector<ctl_bvh_node> before = nodes;
     for (int round = 0; round < rounds; round++) {
