@@ -565,11 +565,12 @@ static void finish_tree(std::vector<ctl_bvh_node>& nodes) {
     const int sweeps = r ? atoi(r) : 8;
     if (sweeps <= 0) return;   // CTL_SBVH_ROTATE=0: the builder's tree as it is (A/B)
     const char* q = getenv("CTL_SBVH_REINSERT");   // passes of sub-tree re-insertion before the rotations (0 = off); CTL_SBVH_REINSERT_FRAC = share of the nodes tried per pass
+    // (by default only for trees up to 4 M nodes: the searches of a heavily overlapping 235 K-reference mesh already take 8 s; rotations always run)
     const int ins_passes = q ? atoi(q) : 2;   // measured: 2 passes reach the result of 4 within 0.3 % (config 2: 2 060 vs 2 065 bytes per path ray)
     const int rounds = getenv("CTL_SBVH_ROUNDS") ? atoi(getenv("CTL_SBVH_ROUNDS")) : 1;   // experiments: (re-insertion, rotations) repeated
     const std::vector<ctl_bvh_node> before = nodes;
     for (int round = 0; round < rounds; round++) {
-    const size_t n_ins = ins_passes > 0 ? reinsert_tree(nodes, ins_passes, getenv("CTL_SBVH_REINSERT_FRAC") ? (float)atof(getenv("CTL_SBVH_REINSERT_FRAC")) : 1.0f) : 0;
+    const size_t n_ins = ins_passes > 0 && (q || nodes.size() <= 4000000) ? reinsert_tree(nodes, ins_passes, getenv("CTL_SBVH_REINSERT_FRAC") ? (float)atof(getenv("CTL_SBVH_REINSERT_FRAC")) : 1.0f) : 0;
     const size_t n_rot = rotate_tree(nodes, sweeps);
     if (getenv("CTL_SBVH_VERBOSE")) fprintf(stderr, "  re-insertions: %zu, tree rotations: %zu\n", n_ins, n_rot);
     }
