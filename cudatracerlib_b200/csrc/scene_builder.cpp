@@ -239,7 +239,7 @@ void assemble_scene(const std::vector<MeshInput>& meshes, const std::vector<Node
         std::vector<uint32_t> ord; std::vector<uint8_t> last;
         const char* which = getenv("CTL_BVH_BUILDER");
         if (which && std::string(which) == "sah") build_bvh(pb, 8, B.nodes, ord, last);
-        else build_sbvh(B.verts9.data(), nt, 8, B.nodes, ord, last); // maxLeafSize 8: BVHBuilderHelper.cpp:119
+        else build_sbvh(B.verts9.data(), nt, getenv("CTL_SBVH_MAXLEAF") ? atoi(getenv("CTL_SBVH_MAXLEAF")) : 8, B.nodes, ord, last); // maxLeafSize 8: BVHBuilderHelper.cpp:119 (env: experiments)
         B.woop.resize(ord.size()); B.index.resize(ord.size());
         for (size_t s = 0; s < ord.size(); s++) {
             const uint32_t t = ord[s];
