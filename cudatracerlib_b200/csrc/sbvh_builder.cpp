@@ -483,8 +483,9 @@ static size_t reinsert_tree(std::vector<ctl_bvh_node>& nodes, int passes, float 
         t[i].leafref = 0;
     }
     int root = 0; t[0].parent = -1; t[0].box = t[t[0].left].box; t[0].box.grow(t[t[0].right].box);
-    for (T& n : t) n.area = n.box.area();
-    auto refit_up = [&](int i) { for (; i >= 0; i = t[i].parent) { Box b = t[t[i].left].box; b.grow(t[t[i].right].box); const float a = b.area(); if (a == t[i].area && b.lo.x == t[i].box.lo.x && b.lo.y == t[i].box.lo.y && b.lo.z == t[i].box.lo.z && b.hi.x == t[i].box.hi.x && b.hi.y == t[i].box.hi.y && b.hi.z == t[i].box.hi.z) break; t[i].box = b; t[i].area = a; } };
+    auto finite_area = [](const Box& b) { const float a = b.area(); return a >= 0.0f && a < 3.0e38f ? a : 0.0f; };   // NaN / inf vertices must not poison the orderings
+    for (T& n : t) n.area = finite_area(n.box);
+    auto refit_up = [&](int i) { for (; i >= 0; i = t[i].parent) { Box b = t[t[i].left].box; b.grow(t[t[i].right].box); const float a = finite_area(b); if (a == t[i].area && b.lo.x == t[i].box.lo.x && b.lo.y == t[i].box.lo.y && b.lo.z == t[i].box.lo.z && b.hi.x == t[i].box.hi.x && b.hi.y == t[i].box.hi.y && b.hi.z == t[i].box.hi.z) break; t[i].box = b; t[i].area = a; } };
     size_t moved = 0;
     std::vector<int> cand;
     std::vector<std::pair<float, int>> heap;   // (-induced cost, node)
@@ -520,10 +521,11 @@ static size_t reinsert_tree(std::vector<ctl_bvh_node>& nodes, int passes, float 
                 }
             }
             // attach: P becomes the parent of (best, X) where best was
+            if (best < 0) best = S;   // only with non-finite boxes (every comparison false): back to where it was
             const int Y = best, YP = t[Y].parent;
             t[P].parent = YP; t[P].left = Y; t[P].right = X; t[Y].parent = P; t[X].parent = P;
             if (YP < 0) root = P; else (t[YP].left == Y ? t[YP].left : t[YP].right) = P;
-            t[P].box = t[Y].box; t[P].box.grow(t[X].box); t[P].area = t[P].box.area();
+            t[P].box = t[Y].box; t[P].box.grow(t[X].box); t[P].area = finite_area(t[P].box);
             refit_up(YP);
             if (Y != S) moved_pass++;
         }
