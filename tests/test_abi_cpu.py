@@ -298,7 +298,9 @@ def test_scene_from_mesh_validates_and_survives_degenerate_geometry(built_lib, o
         a = rng.normal(size=3) * 10
         sticks += [a, -a + rng.normal(size=3) * 0.01, a + rng.normal(size=3) * 0.001]
     outlier = rng.normal(size=(900, 3)); outlier[:3] *= 1e18
-    cases = {"identical": np.tile(tri, (300, 1)), "collinear": np.tile(np.array([[0, 0, 0], [1, 1, 1], [2, 2, 2]], np.float32), (60, 1)),
+    bad_nan = rng.normal(size=(300, 3)); bad_nan[7, 1] = np.nan
+    bad_inf = rng.normal(size=(300, 3)); bad_inf[11, 2] = np.inf
+    cases = {"nan vertex": bad_nan, "inf vertex": bad_inf, "identical": np.tile(tri, (300, 1)), "collinear": np.tile(np.array([[0, 0, 0], [1, 1, 1], [2, 2, 2]], np.float32), (60, 1)),
              "points": np.zeros((180, 3), np.float32), "outlier": outlier, "sticks": np.array(sticks)}
     for name, V in cases.items():
         nt = len(V) // 3
