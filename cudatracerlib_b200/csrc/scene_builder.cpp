@@ -429,6 +429,7 @@ void rebraid(SceneStorage& S, const std::vector<Box>& node_box) {
         e.area = e.world.area();
         if (!openable(e)) { done.push_back(e); return; }
         if (mode == 1) { Box b0, b1; child_boxes(e, b0, b1); e.area = e.world.area() - 0.5f * (b0.area() + b1.area()); }
+        if (!(e.area > -3.0e38f && e.area < 3.0e38f)) e.area = 0.0f;   // non-finite boxes must not poison the heap order
         heap.push_back(e); std::push_heap(heap.begin(), heap.end(), cmp);
     };
     for (uint32_t ni = 0; ni < n_real; ni++) place(Entry{ni, 0, node_box[ni], 0.0f, ni});
