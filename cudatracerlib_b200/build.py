@@ -17,7 +17,7 @@ NVCC_FLAGS = [
     "-fmad=false",
     "-shared", "-Xcompiler", "-fPIC,-O2,-ffp-contract=off",
 ]
-SOURCES = ["ctl_api.cu", "scene_builder.cpp", "sbvh_builder.cpp", "xmsh.cpp", "obj_import.cpp", "validate.cpp"]
+SOURCES = ["ctl_api.cu", "scene_builder.cpp", "sbvh_builder.cpp", "xmsh.cpp", "obj_import.cpp", "validate.cpp", "staging.cpp"]
 
 
 def _sources():

@@ -13,7 +13,9 @@
 #include "../../include/ctl_b200.h"
 #include "scene_builder.h"
 #include "sampler_tables.h"
+#include "staging.h"
 #include "wavefront.cuh"
+#include "device/traverse_staged.cuh"
 #include "wavefront_pt.cuh"
 #include "image_pipeline.cuh"
 #include "nlm_filter.cuh"
@@ -88,14 +90,40 @@ struct ctl_ctx {
     float stage_ms[5] = {0, 0, 0, 0, 0}; uint32_t n_launches = 0;
     bool instrumented = false;
     TravTune tune = {2, 8, 8, 4};
+    // staged traversal kernel (device/traverse_staged.cuh): derived records + launch shape
+    DevBuf<float4> d_tri64, d_inst, d_treelet; StagedScene staged = {nullptr, nullptr, nullptr, 0, 0, 16}; bool staged_ok = false; std::string staged_why;
+    int staged_threads = 512, staged_rows = 16, staged_treelet = 512;   // "StagedThreads", "StagedStackRows", "StagedTreeletNodes"
 };
 
 
-// "TraversalKernel": 0 = persistent phase-scheduled kernel (production), 1 = simple ray-batch kernel (A/B baseline)
-template <int MODE, bool ANY_HIT, bool COUNT, typename... Args>
-static void launch_intersect(const ctl_ctx* c, int grid, cudaStream_t st, const DScene& S, Args... args) {
-    if (c->trav_kernel == 1) k_intersect_simple<MODE, ANY_HIT, COUNT><<<grid, 128, 0, st>>>(S, args...);
-    else k_intersect<MODE, ANY_HIT, COUNT><<<grid, 128, 0, st>>>(S, c->tune, args...);
+// Launch shape of the staged kernel: blocks of `staged_threads`, as many per SM as 1024 resident threads and the shared memory allow
+static size_t staged_smem_bytes(const ctl_ctx* c) { return (size_t)c->staged.tl_nodes * 64 + 16 + (size_t)(c->staged.stack_rows + 1) * c->staged_threads * 4; }
+static int staged_grid(const ctl_ctx* c) {
+    const size_t smem = staged_smem_bytes(c);
+    int per_sm = 1024 / c->staged_threads;
+    const int fit = (int)((227u * 1024u) / (smem + 1024));
+    if (per_sm > fit) per_sm = fit;
+    if (per_sm < 1) per_sm = 1;
+    return c->n_sm * per_sm;
+}
+template <int MODE, bool ANY_HIT, bool COUNT>
+static void launch_staged(const ctl_ctx* c, cudaStream_t st, const float4* rays, const unsigned* n_ptr, const unsigned* n2_ptr, int n_fixed, unsigned* work, const TravOut& out, unsigned long long* visit) {
+    static size_t attr_set = 0; // per instantiation
+    const size_t smem = staged_smem_bytes(c);
+    if (smem > attr_set) { cudaFuncSetAttribute(k_intersect_staged<MODE, ANY_HIT, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = smem; }
+    k_intersect_staged<MODE, ANY_HIT, COUNT><<<staged_grid(c), c->staged_threads, smem, st>>>(c->scene, c->staged, c->tune, rays, n_ptr, n2_ptr, n_fixed, work, out, visit);
+}
+
+// "TraversalKernel": 0 = persistent phase-scheduled kernel, 1 = simple ray-batch kernel (A/B baseline), 2 = persistent kernel with shared-memory staging
+template <int MODE, bool ANY_HIT, bool COUNT>
+static void launch_intersect(const ctl_ctx* c, int grid, cudaStream_t st, const DScene& S, const float4* rays, const unsigned* n_ptr, int n_fixed, unsigned* work_ctr,
+                             float4* hit_a, uint32_t* hit_node, const float4* sh_payload, float4* cl, void* api_out, unsigned long long* visit_out) {
+    if (c->trav_kernel == 2 && c->staged_ok) {
+        const TravOut out = {hit_a, hit_node, sh_payload, cl, api_out, nullptr, 0, nullptr};
+        launch_staged<MODE, ANY_HIT, COUNT>(c, st, rays, n_ptr, nullptr, n_fixed, work_ctr, out, visit_out);
+    }
+    else if (c->trav_kernel == 1) k_intersect_simple<MODE, ANY_HIT, COUNT><<<grid, 128, 0, st>>>(S, rays, n_ptr, n_fixed, work_ctr, hit_a, hit_node, sh_payload, cl, api_out, visit_out);
+    else k_intersect<MODE, ANY_HIT, COUNT><<<grid, 128, 0, st>>>(S, c->tune, rays, n_ptr, n_fixed, work_ctr, hit_a, hit_node, sh_payload, cl, api_out, visit_out);
 }
 
 extern "C" {
@@ -352,7 +380,7 @@ void ctl_destroy(ctl_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->d_scene_nodes.release(); c->d_bvh_nodes.release(); c->d_woop.release(); c->d_tri_index.release(); c->d_tri_data.release(); c->d_meshes.release();
     c->d_nodes.release(); c->d_xf.release(); c->d_inv_xf.release(); c->d_materials.release(); c->d_lights.release(); c->d_light_tris.release();
-    c->d_light_cdf.release(); c->d_normal_lut.release();
+    c->d_light_cdf.release(); c->d_normal_lut.release(); c->d_tri64.release(); c->d_inst.release(); c->d_treelet.release();
     c->d_tab1.release(); c->d_tab2.release(); c->d_states.release(); c->d_states0.release(); c->d_jump.release();
     if (c->h_tab1) cudaFreeHost(c->h_tab1); if (c->h_tab2) cudaFreeHost(c->h_tab2); if (c->h_tab_free) cudaEventDestroy(c->h_tab_free);
     c->cf.release(); c->cl.release(); c->nor.release(); c->px.release(); c->rays_a.release(); c->rays_b.release(); c->hit_a.release(); c->sh_rays.release();
@@ -392,7 +420,10 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "WarpPixelBlocks") c->warp_blocks = v != 0;
     else if (k == "PassStride") { if (v < 1) return set_err("PassStride must be >= 1"); c->pass_stride = v; }   // multi-GPU by pass: this context renders passes PassPhase + k * PassStride
     else if (k == "PassPhase") { if (v < 0) return set_err("PassPhase must be >= 0"); c->pass_phase = v; }
-    else if (k == "TraversalKernel") { if (v < 0 || v > 1) return set_err("TraversalKernel must be 0 or 1"); c->trav_kernel = v; }
+    else if (k == "TraversalKernel") { if (v < 0 || v > 2) return set_err("TraversalKernel must be 0 (persistent), 1 (ray batch) or 2 (staged)"); c->trav_kernel = v; }
+    else if (k == "StagedThreads") { if (v < 32 || v > 1024 || (v & (v - 1))) return set_err("StagedThreads must be a power of two in [32,1024]"); c->staged_threads = v; }
+    else if (k == "StagedStackRows") { if (v < 0 || v > TP_STACK) return set_err("StagedStackRows out of range [0,64]"); c->staged_rows = v; c->staged.stack_rows = v; }
+    else if (k == "StagedTreeletNodes") { if (v < 0 || v > 2048) return set_err("StagedTreeletNodes out of range [0,2048]"); c->staged_treelet = v; }   // takes effect at the next ctl_upload_scene / ctl_update_scene_nodes
     else if (k == "TravThT") c->tune.th_t = v; else if (k == "TravThL") c->tune.th_l = v; else if (k == "TravThF") c->tune.th_f = v;
     else if (k == "TravThNExit") c->tune.th_n_exit = v;
     else if (k == "ShadeBlocksPerSM") { if (v < 1 || v > 16) return set_err("ShadeBlocksPerSM out of range [1,16]"); c->shade_blocks_per_sm = v; }
@@ -411,7 +442,25 @@ int ctl_get_param_i(ctl_ctx* c, const char* key, int* v) {
     if (k == "MaxPathLength") *v = c->max_path_length; else if (k == "RRStartDepth") *v = c->rr_start; else if (k == "Direct") *v = c->direct;
     else if (k == "Regularization") *v = c->regularization; else if (k == "SortMode") *v = c->sort_mode; else if (k == "StageTimers") *v = c->stage_timers;
     else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables; else if (k == "FuseTraversal") *v = c->fuse_traversal; else if (k == "PixelVarianceBuffer") *v = c->variance_buffer; else if (k == "PassStride") *v = c->pass_stride; else if (k == "PassPhase") *v = c->pass_phase;
-    else if (k == "TraversalBlocksPerSM") *v = c->trav_blocks_per_sm; else return set_err("unknown parameter key: " + k);
+    else if (k == "TraversalBlocksPerSM") *v = c->trav_blocks_per_sm; else if (k == "StagedThreads") *v = c->staged_threads; else if (k == "StagedStackRows") *v = c->staged_rows;
+    else if (k == "StagedTreeletNodes") *v = c->staged.tl_nodes; else if (k == "StagedUsable") *v = c->staged_ok ? 1 : 0; else return set_err("unknown parameter key: " + k);
+    return 0;
+}
+
+// Derived records of the staged traversal kernel (csrc/staging.cpp): leaf triangles (with_tris) and the node-level half (instance records, treelet).
+static int upload_staging(ctl_ctx* c, const ctl_scene_view* v, bool with_tris) {
+    ctlb::StagedHost H;
+    if (with_tris) {
+        ctlb::build_staging_tris(*v, H);
+        c->staged_ok = H.usable; c->staged_why = H.why;
+        if (H.usable) CK(c->d_tri64.upload((const float4*)H.tri64.data(), H.tri64.size() / 4));
+    }
+    if (!c->staged_ok) return 0;
+    ctlb::build_staging_nodes(*v, c->staged_treelet, H);
+    CK(c->d_inst.upload((const float4*)H.inst.data(), H.inst.size() / 4));
+    CK(c->d_treelet.upload((const float4*)H.treelet.data(), H.treelet.size() / 4));
+    c->staged.tri64 = c->d_tri64.p; c->staged.inst = c->d_inst.p; c->staged.treelet = c->d_treelet.p;
+    c->staged.tl_nodes = H.tl_nodes; c->staged.scene_root = H.scene_root; c->staged.stack_rows = c->staged_rows;
     return 0;
 }
 
@@ -447,7 +496,7 @@ int ctl_upload_scene(ctl_ctx* c, const ctl_scene_view* v) {
     S.camera = v->camera; S.ray_eps = v->ray_eps; S.scene_start = v->scene_start_node; S.n_nodes = v->n_nodes;
     S.img_w = c->w; S.img_h = c->h;
     c->has_scene = true;
-    return 0;
+    return upload_staging(c, v, true);
 }
 
 // Node-level half of ctl_upload_scene for a view whose meshes are the ones already uploaded: nodes, transforms, scene-level BVH, lights, box, epsilon,
@@ -470,7 +519,7 @@ int ctl_update_scene_nodes(ctl_ctx* c, const ctl_scene_view* v) {
     memcpy(S.light_indices, v->light_indices, sizeof(S.light_indices)); memcpy(S.light_cdf, v->light_cdf, sizeof(S.light_cdf));
     for (int k = 0; k < 3; k++) { S.box_min[k] = v->box_min[k]; const float e = v->box_max[k] - v->box_min[k]; S.box_inv_extent[k] = e > 0 ? 1.0f / e : 0.0f; }
     S.camera = v->camera; S.ray_eps = v->ray_eps; S.scene_start = v->scene_start_node; S.n_nodes = v->n_nodes;
-    return 0;
+    return upload_staging(c, v, false);
 }
 
 static const size_t TAB1 = (size_t)ctlb::kNumSeq * ctlb::kSeqLen, TAB2 = TAB1 * 2;
@@ -666,7 +715,7 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
     ShadeParams P = {c->max_path_length, c->rr_start, c->direct};
     float4* rin = c->rays_a.p; float4* rout = c->rays_b.p; uint32_t* pin = c->path_a.p; uint32_t* pout = c->path_b.p;
     float4* rspare = c->rays_c.p; uint32_t* pspare = c->path_c.p;
-    const bool fuse = c->fuse_traversal && c->direct && !c->instrumented && c->trav_kernel == 0;
+    const bool fuse = c->fuse_traversal && c->direct && !c->instrumented && (c->trav_kernel == 0 || (c->trav_kernel == 2 && c->staged_ok));
     for (int b = 0; b < c->max_path_length; b++) {
         stage_mark(c, 1);
         if (c->capture_bounce == b + 1) {
@@ -674,6 +723,10 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
             CK(cudaMemcpyAsync(c->d_captured_n.p, ctr + CTR_Q + b, sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
         }
         if (fuse && b > 0) { // shadow rays of bounce b-1 + extension rays of bounce b in one persistent launch
+            if (c->trav_kernel == 2 && c->staged_ok) {
+                const TravOut out = {c->hit_a.p, c->hit_node.p, c->sh_payload.p, c->cl.p, nullptr, c->sh_rays.p, 0, nullptr};
+                launch_staged<4, false, false>(c, c->stream, rin, ctr + CTR_Q + b, ctr + CTR_SH + b - 1, 0, ctr + CTR_WORK + 2 * b, out, nullptr);
+            } else
             k_intersect_fused<<<g_trav, 128, 0, c->stream>>>(c->scene, c->tune, rin, ctr + CTR_Q + b, c->sh_rays.p, ctr + CTR_SH + b - 1, ctr + CTR_WORK + 2 * b,
                                                               c->hit_a.p, c->hit_node.p, c->sh_payload.p, c->cl.p);
         }
@@ -802,6 +855,10 @@ int ctl_wavefront_pass(ctl_ctx* c, int new_trace) {
                                                 (void*)c->w_sres[(d - 1) & 1].p, c->stats.p + 6);
                 launches++;
             }
+        } else if (have_sec && c->fuse_traversal && c->trav_kernel == 2 && c->staged_ok) {
+            const TravOut out = {nullptr, nullptr, nullptr, nullptr, (void*)c->w_res.p, (const float4*)c->w_sec[(d - 1) & 1].p, 0, (void*)c->w_sres[(d - 1) & 1].p};
+            launch_staged<5, false, false>(c, c->stream, (const float4*)c->w_ray.p, ctr + CTR_Q + d, ctr + CTR_SH + d - 1, 0, ctr + CTR_WORK + 2 * d, out, nullptr);
+            launches++;
         } else if (have_sec && c->fuse_traversal && c->trav_kernel == 0) {
             k_intersect_fused_api<<<g_trav, 128, 0, c->stream>>>(c->scene, c->tune, (const float4*)c->w_ray.p, ctr + CTR_Q + d, (const float4*)c->w_sec[(d - 1) & 1].p, ctr + CTR_SH + d - 1,
                                                                   ctr + CTR_WORK + 2 * d, (void*)c->w_res.p, (void*)c->w_sres[(d - 1) & 1].p);
