@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cmath>
 #include <stdexcept>
+#include <memory>
 #include "../../include/ctl_b200.h"
 #include "scene_builder.h"
 #include "sampler_tables.h"
@@ -32,6 +33,7 @@ struct ctl_scene { ctlb::SceneStorage S; };
 
 namespace {
 const int MAX_BOUNCES = 256;
+const unsigned API_WORK_RING = 256;
 enum { CTR_Q = 0, CTR_SH = MAX_BOUNCES + 1, CTR_WORK = 2 * (MAX_BOUNCES + 1), CTR_TOTAL = 4 * (MAX_BOUNCES + 1) };
 
 template <typename T> struct DevBuf {
@@ -58,7 +60,7 @@ struct ctl_ctx {
     int n_sm = 148;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     // parameters (Integrators/PathTracer.h:10-20)
-    int max_path_length = 50, rr_start = 5, direct = 1, regularization = 0, sort_mode = 0, stage_timers = 0, capture_bounce = 0, trav_kernel = 0, trav_blocks_per_sm = 8, shade_blocks_per_sm = 8, smem_carveout = -1, fuse_traversal = 1, warp_blocks = 0, pass_stride = 1, pass_phase = 0;
+    int max_path_length = 50, rr_start = 5, direct = 1, regularization = 0, sort_mode = 0, stage_timers = 0, capture_bounce = 0, trav_kernel = 2, trav_blocks_per_sm = 8, shade_blocks_per_sm = 8, smem_carveout = -1, fuse_traversal = 1, warp_blocks = 0, pass_stride = 1, pass_phase = 0;
     // scene
     DevBuf<ctl_bvh_node> d_scene_nodes, d_bvh_nodes; DevBuf<ctl_woop_tri> d_woop; DevBuf<uint32_t> d_tri_index; DevBuf<ctl_tri_data> d_tri_data;
     DevBuf<ctl_mesh> d_meshes; DevBuf<ctl_node> d_nodes; DevBuf<float> d_xf, d_inv_xf; DevBuf<ctl_material> d_materials; DevBuf<ctl_light> d_lights;
@@ -76,6 +78,7 @@ struct ctl_ctx {
     DevBuf<float4> cf, cl, nor, px, rays_a, rays_b, hit_a, sh_rays, sh_payload, capture;
     DevBuf<uint32_t> path_a, path_b, path_c, hit_node, sort_keys; DevBuf<float4> rays_c; DevBuf<unsigned> sort_hist, sort_offsets, mat_hist; DevBuf<unsigned char> mat_cls; DevBuf<uint32_t> mat_order;
     DevBuf<unsigned> counters;
+    DevBuf<unsigned> api_work; unsigned api_seq = 0;   // ring of work counters of the API traversal launches: calls in flight on different streams never share one
     // WavefrontPathTracer queue (DoubleRayBuffer<WavefrontPTRayData>)
     DevBuf<float4> w_thr, w_lxy, w_df, w_ray, w_sec[2]; DevBuf<uint2> w_misc; DevBuf<uint4> w_res, w_sres[2]; DevBuf<unsigned long long> w_desc;
     DevBuf<unsigned long long> stats; // [0] rays_last [1] rays_total [2..4] ext visits [5] ext rays [6..8] shadow visits [9] shadow rays
@@ -85,14 +88,14 @@ struct ctl_ctx {
     DevBuf<uchar4> nlm_cached; DevBuf<float> nlm_varh, nlm_weights; long long nlm_last_update = -1; size_t nlm_pixels = 0;   // NonLocalMeansFilter state (m_cachedImg, m_weightBuffer, last_iter_weight_update)
     unsigned captured_n = 0; DevBuf<unsigned> d_captured_n;
     uint32_t passes_done = 0;
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr; bool events_recorded = false;
     std::vector<cudaEvent_t> stage_ev; std::vector<int> stage_kind;
     float stage_ms[5] = {0, 0, 0, 0, 0}; uint32_t n_launches = 0;
     bool instrumented = false;
-    TravTune tune = {2, 8, 8, 4};
+    TravTune tune = {2, 8, 8, 4, 1};
     // staged traversal kernel (device/traverse_staged.cuh): derived records + launch shape
     DevBuf<float4> d_tri64, d_inst, d_treelet; StagedScene staged = {nullptr, nullptr, nullptr, 0, 0, 16}; bool staged_ok = false; std::string staged_why;
-    int staged_threads = 512, staged_rows = 16, staged_treelet = 512;   // "StagedThreads", "StagedStackRows", "StagedTreeletNodes"
+    int staged_threads = 512, staged_rows = 16, staged_treelet = 0, staged_resident = 1024;   // "StagedThreads", "StagedStackRows", "StagedTreeletNodes", "StagedResidentThreads"
 };
 
 
@@ -100,7 +103,7 @@ struct ctl_ctx {
 static size_t staged_smem_bytes(const ctl_ctx* c) { return (size_t)c->staged.tl_nodes * 64 + 16 + (size_t)(c->staged.stack_rows + 1) * c->staged_threads * 4; }
 static int staged_grid(const ctl_ctx* c) {
     const size_t smem = staged_smem_bytes(c);
-    int per_sm = 1024 / c->staged_threads;
+    int per_sm = c->staged_resident / c->staged_threads;
     const int fit = (int)((227u * 1024u) / (smem + 1024));
     if (per_sm > fit) per_sm = fit;
     if (per_sm < 1) per_sm = 1;
@@ -132,7 +135,7 @@ const char* ctl_last_error(void) { return g_err.c_str(); }
 
 // ------------------------------------------------------------------ scenes (host)
 ctl_scene* ctl_scene_create(int kind, int width, int height, uint32_t seed, int n_hint) {
-    try { ctl_scene* s = new ctl_scene(); ctlb::make_scene(kind, width, height, seed, n_hint, s->S); return s; }
+    try { std::unique_ptr<ctl_scene> s(new ctl_scene()); ctlb::make_scene(kind, width, height, seed, n_hint, s->S); return s.release(); }
     catch (const std::exception& e) { set_err(e.what()); return nullptr; }
 }
 ctl_scene* ctl_scene_create_from_mesh(const float* verts, uint32_t nv, const uint32_t* indices, uint32_t nt, const uint8_t* mat_index,
@@ -150,12 +153,12 @@ ctl_scene* ctl_scene_create_from_mesh(const float* verts, uint32_t nv, const uin
         M.mat_index.assign(mat_index, mat_index + nt);
         M.materials.assign(materials, materials + nm);
         for (uint32_t i = 0; i < nm; i++) M.emissive.push_back(emissive ? ctlb::V3(emissive[3 * i], emissive[3 * i + 1], emissive[3 * i + 2]) : ctlb::V3(0.0f));
-        ctl_scene* s = new ctl_scene();
+        std::unique_ptr<ctl_scene> s(new ctl_scene());
         std::vector<ctlb::MeshInput> meshes = {M};
         std::vector<ctlb::NodeInput> nodes = {{0, ctlb::M4::identity(), -1}};
         ctlb::assemble_scene(meshes, nodes, ctlb::V3(cam_pos[0], cam_pos[1], cam_pos[2]), ctlb::V3(cam_target[0], cam_target[1], cam_target[2]),
                              ctlb::V3(cam_up[0], cam_up[1], cam_up[2]), fov_deg, width, height, s->S);
-        return s;
+        return s.release();
     } catch (const std::exception& e) { set_err(e.what()); return nullptr; }
 }
 // == DynamicScene::CreateNode(compiled mesh file) per file + the camera (Engine/DynamicScene.cpp:283-345; reader Engine/Mesh.cpp:46-98): SURVEY 8 f4
@@ -357,7 +360,7 @@ static int init_ctx(ctl_ctx* c) { // everything of ctl_create that can fail afte
         CK(c->d_states0.upload(st0.data(), st0.size())); CK(c->d_states.upload(st0.data(), st0.size()));
         CK(c->d_jump.upload(&J.row[0][0], 160 * 5));
     }
-    CK(c->counters.ensure(CTR_TOTAL)); CK(c->stats.ensure(16)); CK(c->d_captured_n.ensure(1));
+    CK(c->counters.ensure(CTR_TOTAL)); CK(c->api_work.ensure(API_WORK_RING)); CK(c->stats.ensure(16)); CK(c->d_captured_n.ensure(1));
     CK(cudaMemset(c->stats.p, 0, 16 * sizeof(unsigned long long)));
     return alloc_image(c);
 }
@@ -384,7 +387,7 @@ void ctl_destroy(ctl_ctx* c) {
     c->d_tab1.release(); c->d_tab2.release(); c->d_states.release(); c->d_states0.release(); c->d_jump.release();
     if (c->h_tab1) cudaFreeHost(c->h_tab1); if (c->h_tab2) cudaFreeHost(c->h_tab2); if (c->h_tab_free) cudaEventDestroy(c->h_tab_free);
     c->cf.release(); c->cl.release(); c->nor.release(); c->px.release(); c->rays_a.release(); c->rays_b.release(); c->hit_a.release(); c->sh_rays.release();
-    c->sh_payload.release(); c->capture.release(); c->path_a.release(); c->path_b.release(); c->path_c.release(); c->rays_c.release(); c->sort_keys.release(); c->sort_hist.release(); c->sort_offsets.release(); c->mat_hist.release(); c->mat_cls.release(); c->mat_order.release(); c->hit_node.release(); c->counters.release(); c->stats.release();
+    c->sh_payload.release(); c->capture.release(); c->path_a.release(); c->path_b.release(); c->path_c.release(); c->rays_c.release(); c->sort_keys.release(); c->sort_hist.release(); c->sort_offsets.release(); c->mat_hist.release(); c->mat_cls.release(); c->mat_order.release(); c->hit_node.release(); c->counters.release(); c->api_work.release(); c->stats.release();
     c->own_accum.release(); c->d_captured_n.release(); c->resolve_tmp.release(); c->pipe_rgbe.release(); c->pipe_partial.release(); c->pipe_lum.release(); c->d_var.release(); c->nlm_cached.release(); c->nlm_varh.release(); c->nlm_weights.release(); c->nlm_last_update = -1; c->nlm_pixels = 0; c->d_node_alias.release();
     c->w_thr.release(); c->w_lxy.release(); c->w_df.release(); c->w_ray.release(); c->w_misc.release(); c->w_res.release(); c->w_desc.release();
     for (int k = 0; k < 2; k++) { c->w_sec[k].release(); c->w_sres[k].release(); }
@@ -421,11 +424,13 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "PassStride") { if (v < 1) return set_err("PassStride must be >= 1"); c->pass_stride = v; }   // multi-GPU by pass: this context renders passes PassPhase + k * PassStride
     else if (k == "PassPhase") { if (v < 0) return set_err("PassPhase must be >= 0"); c->pass_phase = v; }
     else if (k == "TraversalKernel") { if (v < 0 || v > 2) return set_err("TraversalKernel must be 0 (persistent), 1 (ray batch) or 2 (staged)"); c->trav_kernel = v; }
-    else if (k == "StagedThreads") { if (v < 32 || v > 1024 || (v & (v - 1))) return set_err("StagedThreads must be a power of two in [32,1024]"); c->staged_threads = v; }
+    else if (k == "StagedThreads") { if (v < 32 || v > 1024 || (v & 31)) return set_err("StagedThreads must be a multiple of 32 in [32,1024]"); c->staged_threads = v; }
+    else if (k == "StagedResidentThreads") { if (v < 32 || v > 2048) return set_err("StagedResidentThreads out of range [32,2048]"); c->staged_resident = v; }
     else if (k == "StagedStackRows") { if (v < 0 || v > TP_STACK) return set_err("StagedStackRows out of range [0,64]"); c->staged_rows = v; c->staged.stack_rows = v; }
     else if (k == "StagedTreeletNodes") { if (v < 0 || v > 2048) return set_err("StagedTreeletNodes out of range [0,2048]"); c->staged_treelet = v; }   // takes effect at the next ctl_upload_scene / ctl_update_scene_nodes
     else if (k == "TravThT") c->tune.th_t = v; else if (k == "TravThL") c->tune.th_l = v; else if (k == "TravThF") c->tune.th_f = v;
     else if (k == "TravThNExit") c->tune.th_n_exit = v;
+    else if (k == "TravTSteps") { if (v < 1 || v > 8) return set_err("TravTSteps out of range [1,8]"); c->tune.t_steps = v; }
     else if (k == "ShadeBlocksPerSM") { if (v < 1 || v > 16) return set_err("ShadeBlocksPerSM out of range [1,16]"); c->shade_blocks_per_sm = v; }
     else if (k == "TravSmemCarveout") { // experiment: shared-memory carve-out (percent) of the traversal kernels = how much L1 they lose
         c->smem_carveout = v;
@@ -607,7 +612,7 @@ int ctl_intersect(ctl_ctx* c, int n, const void* d_rays, void* d_results, int an
     if (n == 0) return 0;
     CK(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    unsigned* work = c->counters.p + CTR_WORK + 2 * MAX_BOUNCES + 1;
+    unsigned* work = c->api_work.p + (c->api_seq++ % API_WORK_RING);
     CK(cudaMemsetAsync(work, 0, sizeof(unsigned), st));
     const int grid = grid_for(c, c->trav_blocks_per_sm);
     if (any_hit) launch_intersect<2, true, false>(c, grid, st, c->scene, (const float4*)d_rays, nullptr, n, work, nullptr, nullptr, nullptr, nullptr, d_results, nullptr);
@@ -640,7 +645,7 @@ int ctl_trace_rays_host(ctl_ctx* c, int n, const ctl_traversal_ray* rays, ctl_tr
     CK(dr.ensure((size_t)n * 2)); CK(dres.ensure((size_t)n * 5)); CK(dcnt.ensure(4));
     CK(cudaMemsetAsync(dcnt.p, 0, 32, c->stream));
     CK(cudaMemcpyAsync(dr.p, rays, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream));
-    unsigned* work = c->counters.p + CTR_WORK + 2 * MAX_BOUNCES + 1;
+    unsigned* work = c->api_work.p + (c->api_seq++ % API_WORK_RING);
     CK(cudaMemsetAsync(work, 0, sizeof(unsigned), c->stream));
     const int grid = grid_for(c, c->trav_blocks_per_sm);
     if (counts) launch_intersect<3, false, true>(c, grid, c->stream, c->scene, dr.p, nullptr, n, work, nullptr, nullptr, nullptr, nullptr, dres.p, dcnt.p);
@@ -767,6 +772,7 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
     CK(cudaGetLastError());
     if (variance_after_pass(c, new_trace != 0)) return 1;
     CK(cudaEventRecord(c->ev_stop, c->stream));
+    c->events_recorded = true;
     c->n_launches = launches;
     c->passes_done += W.n_passes;
     return 0;
@@ -794,7 +800,11 @@ int ctl_render_passes_tiled(ctl_ctx* c, int new_trace, int n_passes, int tile_w,
     if ((size_t)W.n_slots * n_passes > 0x7fffffffull / 2) return set_err("batch too large: reduce n_passes");
     if (W.n_slots == 0) { // nothing to trace on this part: still honour the clear and advance the pass counter / sample stream
         CK(cudaSetDevice(c->device));
+        CK(cudaEventRecord(c->ev_start, c->stream));
         if (new_trace) { CK(cudaMemsetAsync(c->accum, 0, (size_t)c->w * c->h * 7 * sizeof(float), c->stream)); c->passes_done = 0; }
+        CK(cudaMemsetAsync(c->stats.p, 0, sizeof(unsigned long long), c->stream));   // rays of the last pass: none
+        CK(cudaEventRecord(c->ev_stop, c->stream));
+        c->events_recorded = true; c->n_launches = 0;
         c->passes_done += n_passes;
         return 0;
     }
@@ -888,6 +898,7 @@ int ctl_wavefront_pass(ctl_ctx* c, int new_trace) {
     CK(cudaGetLastError());
     if (variance_after_pass(c, new_trace != 0)) return 1;
     CK(cudaEventRecord(c->ev_stop, c->stream));
+    c->events_recorded = true;
     c->n_launches = launches;
     c->passes_done += 1;
     return 0;
@@ -1037,7 +1048,7 @@ int ctl_stats(ctl_ctx* c, uint64_t* rays_last, float* seconds_last, uint64_t* ra
     unsigned long long h[2] = {0, 0};
     CK(cudaMemcpy(h, c->stats.p, sizeof(h), cudaMemcpyDeviceToHost));
     float ms = 0.0f;
-    if (c->passes_done) CK(cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop));
+    if (c->events_recorded) CK(cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop));
     if (rays_last) *rays_last = h[0];
     if (rays_total) *rays_total = h[1];
     if (seconds_last) *seconds_last = ms * 1e-3f;

@@ -31,7 +31,7 @@ struct TravOut { // where results go (MODE-dependent, see k_intersect)
     void* api_out2;
 };
 
-struct TravTune { int th_t, th_l, th_f, th_n_exit; }; // lane thresholds of the T / L / F blocks; th_n_exit = node steps per iteration
+struct TravTune { int th_t, th_l, th_f, th_n_exit, t_steps; }; // lane thresholds of the T / L / F blocks; th_n_exit = node steps per iteration; t_steps = triangle tests per iteration (staged kernel)
 
 template <int MODE, bool ANY_HIT, bool COUNT>
 __device__ __forceinline__ void trace_persistent(const DScene& S, const float4* __restrict__ rays, int n, unsigned* work_ctr, const TravOut& out,

@@ -63,7 +63,7 @@ CTL_DEV void tma_fill(void* dst_smem, const void* src_gmem, uint32_t bytes, void
 template <int MODE, bool ANY_HIT, bool COUNT>
 __device__ __forceinline__ void trace_staged(const DScene& S, const StagedScene& SS, const float4* __restrict__ rays, int n, unsigned* work_ctr, const TravOut& out,
                                              const TravTune& tune, VisitCounters<COUNT>& cnt, const float4* __restrict__ tl, int* __restrict__ ss, const int NT) {
-    const int TH_T = tune.th_t, TH_L = tune.th_l, TH_F = tune.th_f, N_STEPS = tune.th_n_exit > 0 ? tune.th_n_exit : 1;
+    const int TH_T = tune.th_t, TH_L = tune.th_l, TH_F = tune.th_f, N_STEPS = tune.th_n_exit > 0 ? tune.th_n_exit : 1, T_STEPS = tune.t_steps > 0 ? tune.t_steps : 1;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int SD = SS.stack_rows;
@@ -207,59 +207,66 @@ __device__ __forceinline__ void trace_staged(const DScene& S, const StagedScene&
             }
         }
 
-        // ---- N: inner-node step(s)
-        for (int ns = 0; ns < N_STEPS; ns++)
+        // ---- N: up to N_STEPS inner-node steps for every lane that has one.  Inside the block a lane only asks "still an inner node?"; its
+        // state is classified once, on leaving
         if (state == 0) {
-            F8 nA, nB;
-            if (nodeAddr & ST_TL) { // treelet node: four conflict-spread LDS.128
-                const int t = nodeAddr >> 2;
-                nA.lo = tl[tl_chunk(t, 0)]; nA.hi = tl[tl_chunk(t, 1)]; nB.lo = tl[tl_chunk(t, 2)]; nB.hi = tl[tl_chunk(t, 3)];
-            } else { nA = ldg256(nbase + nodeAddr); nB = ldg256(nbase + nodeAddr + 2); }
-            const float4 n0xy = nA.lo, n1xy = nA.hi, nz = nB.lo, cn = nB.hi;
-            if (COUNT) ((VisitCounters<true>&)cnt).inner++;
-            int c0 = __float_as_int(cn.x), c1 = __float_as_int(cn.y);
-            const float c0lox = fmaf(n0xy.x, idx, -oodx), c0hix = fmaf(n0xy.y, idx, -oodx);
-            const float c0loy = fmaf(n0xy.z, idy, -oody), c0hiy = fmaf(n0xy.w, idy, -oody);
-            const float c0loz = fmaf(nz.x, idz, -oodz), c0hiz = fmaf(nz.y, idz, -oodz);
-            const float c1loz = fmaf(nz.z, idz, -oodz), c1hiz = fmaf(nz.w, idz, -oodz);
-            const float c1lox = fmaf(n1xy.x, idx, -oodx), c1hix = fmaf(n1xy.y, idx, -oodx);
-            const float c1loy = fmaf(n1xy.z, idy, -oody), c1hiy = fmaf(n1xy.w, idy, -oody);
-            const float rayT = hit.dist;
-            const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), box_lo));
-            const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), rayT));
-            const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), box_lo));
-            const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), rayT));
-            const bool swp = (c1min < c0min), t0 = (c0max >= c0min), t1 = (c1max >= c1min);
-            if (!t0 && !t1) nodeAddr = pop();
-            else {
-                nodeAddr = t0 ? c0 : c1;
-                if (t0 && t1) {
-                    if (swp) { const int tmp = nodeAddr; nodeAddr = c1; c1 = tmp; }
-                    push(c1);
+            int ns = N_STEPS;
+            do {
+                F8 nA, nB;
+                if (nodeAddr & ST_TL) { // treelet node: four conflict-spread LDS.128
+                    const int t = nodeAddr >> 2;
+                    nA.lo = tl[tl_chunk(t, 0)]; nA.hi = tl[tl_chunk(t, 1)]; nB.lo = tl[tl_chunk(t, 2)]; nB.hi = tl[tl_chunk(t, 3)];
+                } else { nA = ldg256(nbase + nodeAddr); nB = ldg256(nbase + nodeAddr + 2); }
+                const float4 n0xy = nA.lo, n1xy = nA.hi, nz = nB.lo, cn = nB.hi;
+                if (COUNT) ((VisitCounters<true>&)cnt).inner++;
+                int c0 = __float_as_int(cn.x), c1 = __float_as_int(cn.y);
+                const float c0lox = fmaf(n0xy.x, idx, -oodx), c0hix = fmaf(n0xy.y, idx, -oodx);
+                const float c0loy = fmaf(n0xy.z, idy, -oody), c0hiy = fmaf(n0xy.w, idy, -oody);
+                const float c0loz = fmaf(nz.x, idz, -oodz), c0hiz = fmaf(nz.y, idz, -oodz);
+                const float c1loz = fmaf(nz.z, idz, -oodz), c1hiz = fmaf(nz.w, idz, -oodz);
+                const float c1lox = fmaf(n1xy.x, idx, -oodx), c1hix = fmaf(n1xy.y, idx, -oodx);
+                const float c1loy = fmaf(n1xy.z, idy, -oody), c1hiy = fmaf(n1xy.w, idy, -oody);
+                const float rayT = hit.dist;
+                const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), box_lo));
+                const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), rayT));
+                const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), box_lo));
+                const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), rayT));
+                const bool swp = (c1min < c0min), t0 = (c0max >= c0min), t1 = (c1max >= c1min);
+                if (!t0 && !t1) nodeAddr = pop();
+                else {
+                    nodeAddr = t0 ? c0 : c1;
+                    if (t0 && t1) {
+                        if (swp) { const int tmp = nodeAddr; nodeAddr = c1; c1 = tmp; }
+                        push(c1);
+                    }
                 }
-            }
+            } while (--ns > 0 && (unsigned)nodeAddr < (unsigned)SENT);
             if (nodeAddr < 0) triAddr = (int)tri_slot_base + ~nodeAddr;
             classify();
         }
 
-        // ---- T: one triangle test for every lane inside a mesh leaf
+        // ---- T: up to T_STEPS triangle tests for every lane inside a mesh leaf
         const unsigned mT2 = __ballot_sync(0xffffffffu, state == 1);
         if (mT2 && (__popc(mT2) >= TH_T || (mT2 | b1) == 0xffffffffu)) {
             if (state == 1) {
-                const float4* T = SS.tri64 + (size_t)triAddr * 4;
-                const F8 tA = ldg256(T), tB = ldg256(T + 2);
-                const uint32_t index = __float_as_uint(tB.hi.x);
-                if (COUNT) ((VisitCounters<true>&)cnt).tris++;
-                float t, u, v;
-                bool done = false;
-                if (woop_test(tA.lo, tA.hi, tB.lo, mk(ox, oy, oz), mk(dx, dy, dz), tri_lo, hit.dist, t, u, v)) {
-                    hit.node = (uint32_t)inst; hit.tri = (index >> 1) + tri_base; hit.u = u; hit.v = v; hit.dist = t;
-                    if ((MODE == 4 || MODE == 5) ? lane_any : ANY_HIT) { done = true; nodeAddr = SENT; inst = -1; } // first hit terminates the ray (TraceHelper.cu:675-679)
-                }
-                if (!done) {
-                    if (index & 1) { nodeAddr = pop(); if (nodeAddr < 0) triAddr = (int)tri_slot_base + ~nodeAddr; }
-                    else triAddr++;
-                }
+                int ts = T_STEPS;
+                bool more;
+                do {
+                    const float4* T = SS.tri64 + (size_t)triAddr * 4;
+                    const F8 tA = ldg256(T), tB = ldg256(T + 2);
+                    const uint32_t index = __float_as_uint(tB.hi.x);
+                    if (COUNT) ((VisitCounters<true>&)cnt).tris++;
+                    float t, u, v;
+                    more = true;
+                    if (woop_test(tA.lo, tA.hi, tB.lo, mk(ox, oy, oz), mk(dx, dy, dz), tri_lo, hit.dist, t, u, v)) {
+                        hit.node = (uint32_t)inst; hit.tri = (index >> 1) + tri_base; hit.u = u; hit.v = v; hit.dist = t;
+                        if ((MODE == 4 || MODE == 5) ? lane_any : ANY_HIT) { more = false; nodeAddr = SENT; inst = -1; } // first hit terminates the ray (TraceHelper.cu:675-679)
+                    }
+                    if (more) {
+                        if (index & 1) { nodeAddr = pop(); more = nodeAddr < 0; if (more) triAddr = (int)tri_slot_base + ~nodeAddr; } // end of the leaf: the next entry may be another leaf
+                        else triAddr++;
+                    }
+                } while (--ts > 0 && more);
                 classify();
             }
         }
@@ -272,10 +279,13 @@ CTL_DEV size_t staged_smem_bytes_dev(const StagedScene& SS, int nt) { return (si
 #ifndef CTL_STAGED_MAX_THREADS
 #define CTL_STAGED_MAX_THREADS 1024 // <= 64 registers per thread, so that any block size up to 1024 keeps 1024 threads per SM resident
 #endif
+#ifndef CTL_STAGED_MIN_BLOCKS
+#define CTL_STAGED_MIN_BLOCKS 1
+#endif
 
 // MODEs as k_intersect (wavefront.cuh).  MODE 4 / 5 (fused launches) take their second queue through `out`.
 template <int MODE, bool ANY_HIT, bool COUNT>
-__global__ void __launch_bounds__(CTL_STAGED_MAX_THREADS, 1) k_intersect_staged(const __grid_constant__ DScene S, const __grid_constant__ StagedScene SS, const __grid_constant__ TravTune tune,
+__global__ void __launch_bounds__(CTL_STAGED_MAX_THREADS, CTL_STAGED_MIN_BLOCKS) k_intersect_staged(const __grid_constant__ DScene S, const __grid_constant__ StagedScene SS, const __grid_constant__ TravTune tune,
         const float4* __restrict__ rays, const unsigned* __restrict__ n_ptr, const unsigned* __restrict__ n2_ptr, int n_fixed, unsigned* work_ctr,
         const __grid_constant__ TravOut out_in, unsigned long long* visit_out) {
     extern __shared__ __align__(128) unsigned char staged_smem[];

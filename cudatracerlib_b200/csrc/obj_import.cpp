@@ -199,6 +199,7 @@ void read_ply(const char* path_c, MeshInput& M) {
     std::string line;
     if (!getline(line) || line.substr(0, 3) != "ply") throw std::runtime_error("not a ply file: " + path);
     int format = -1, vertex_count = -1, face_count = -1, n_props = 0, pos_start = -1, uv_start = -1, has_pos = 0; bool has_uv = false, in_vertex = false;
+    int pos_col[3] = {-1, -1, -1}; bool pos_is_float32 = true;
     while (getline(line)) {
         const std::vector<std::string> w = words(line);
         if (w.empty()) continue;
@@ -208,7 +209,7 @@ void read_ply(const char* path_c, MeshInput& M) {
             if (w.size() < 3 || w[1] == "list") throw std::runtime_error("compileply: unsupported vertex property: " + path);
             const std::string &type = w[1], &name = w[2];
             const bool real = type == "float" || type == "double";
-            if (name.size() == 1 && name[0] >= 'x' && name[0] <= 'z' && real) { has_pos |= 1 << (name[0] - 'x'); if (name[0] == 'x') pos_start = n_props; }
+            if (name.size() == 1 && name[0] >= 'x' && name[0] <= 'z' && real) { has_pos |= 1 << (name[0] - 'x'); pos_col[name[0] - 'x'] = n_props; if (type != "float") pos_is_float32 = false; if (name[0] == 'x') pos_start = n_props; }
             else if (name[0] == 'u' || (name[0] == 'v' && name.size() == 1 && real)) { has_uv = true; if (name[0] == 'u') uv_start = n_props; }
             else if (name.find("material") != std::string::npos) throw std::runtime_error("compileply: per-vertex materials are not supported: " + path);
             n_props++;
@@ -216,6 +217,10 @@ void read_ply(const char* path_c, MeshInput& M) {
         else if (w[0] == "end_header") break;
     }
     if (has_pos != 7 || vertex_count <= 0 || face_count <= 0 || format < 0) throw std::runtime_error("compileply: header without float x y z vertices and faces: " + path);
+    // the reference reader takes x, y, z from three consecutive columns starting at x (PlyParser.cpp:262-283); anything else would read the wrong columns
+    if (pos_col[1] != pos_col[0] + 1 || pos_col[2] != pos_col[0] + 2) throw std::runtime_error("compileply: unsupported vertex layout (x y z must be consecutive properties): " + path);
+    if (format != 2 && (n_props != 3 || pos_start != 0 || !pos_is_float32)) throw std::runtime_error("compileply: unsupported vertex layout (binary files: exactly the float properties x y z): " + path);
+    if (has_uv && (uv_start < 0 || uv_start >= n_props)) has_uv = false;
     M = MeshInput();
     M.verts.resize(vertex_count);
     if (has_uv) M.uvs.assign((size_t)vertex_count * 2, 0.0f);

@@ -329,6 +329,17 @@ void assemble_nodes(SceneStorage& S) {
         if (nodes.size() == 1) S.scene_start = ~0; // single node: start at the leaf (TraceHelper.cu:417, BVHTraversal.h:11-12)
     }
     // area lights: one DiffuseLight per (node, emissive material), DynamicScene.cpp:689-711
+    std::vector<std::vector<uint32_t>> first_slot(S.meshes.size());   // per mesh with emitters: first leaf slot referencing each triangle (built on demand, one pass over the leaf words)
+    auto slot_table = [&](uint32_t mesh_id) -> const std::vector<uint32_t>& {
+        std::vector<uint32_t>& tab = first_slot[mesh_id];
+        if (!tab.empty()) return tab;
+        const ctl_mesh& km = S.meshes[mesh_id];
+        const uint32_t nt = (mesh_id + 1 < S.meshes.size() ? S.meshes[mesh_id + 1].tri_offset : (uint32_t)S.tri_data.size()) - km.tri_offset;
+        const uint32_t slot_end = (mesh_id + 1 < S.meshes.size()) ? S.meshes[mesh_id + 1].bvh_idx_offset : (uint32_t)S.tri_index.size();
+        tab.assign((size_t)nt + 1, 0xffffffffu);
+        for (uint32_t slot = km.bvh_idx_offset; slot < slot_end; slot++) { const uint32_t t = S.tri_index[slot] >> 1; if (t < nt && tab[t] == 0xffffffffu) tab[t] = slot; }
+        return tab;
+    };
     for (size_t ni = 0; ni < nodes.size(); ni++) {
         const uint32_t mesh_id = nodes[ni].mesh;
         const ctl_mesh& km = S.meshes[mesh_id];
@@ -352,9 +363,8 @@ void assemble_nodes(SceneStorage& S) {
                 if (tm != m) continue;
                 ctl_light_tri lt3; memset(&lt3, 0, sizeof(lt3));
                 // first woop slot referencing this triangle
-                uint32_t slot_end = (nodes[ni].mesh + 1 < S.meshes.size()) ? S.meshes[nodes[ni].mesh + 1].bvh_idx_offset : (uint32_t)S.tri_index.size();
-                uint32_t slot = km.bvh_idx_offset;
-                while (slot < slot_end && (S.tri_index[slot] >> 1) != t) slot++;
+                const uint32_t slot = slot_table(mesh_id)[t];
+                if (slot == 0xffffffffu || slot >= S.woop.size()) throw std::runtime_error("emissive triangle " + std::to_string(t) + " of mesh " + std::to_string(mesh_id) + " is not referenced by the BVH");
                 lt3.i_dat = slot; lt3.t_dat = km.tri_offset + t;
                 V3 p0, p1, p2;
                 decode_woop(S.woop[slot], p0, p1, p2);
@@ -391,6 +401,13 @@ void assemble_nodes(SceneStorage& S) {
     make_camera(S.cam_pos, S.cam_target, S.cam_up, S.cam_fov, S.cam_w, S.cam_h, &S.camera);
     S.ray_eps = 1e-4f * length(S.box.hi - S.box.lo); // DynamicScene.cpp:587
     rebraid(S, node_box);
+    // the traversal kernels keep 64 stack entries per ray (BVHTraversal.h: traversalStack[64]): trees built here are checked against that, a re-braided
+    // level that does not fit is dropped, a plain view that does not fit is refused
+    ctl_scene_view v; S.fill_view(&v);
+    if (view_stack_depth(v) > 64) {
+        if (S.rb_active) { S.rb_active = false; S.fill_view(&v); }
+        if (view_stack_depth(v) > 64) throw std::runtime_error("scene trees are deeper than the 64-entry traversal stack (scene level + mesh level)");
+    }
 }
 
 // Partial re-braiding (Benthin, Woop, Wald, Afra: "Improved two-level BVHs using partial re-braiding", HPG 2017) inside the reference's data
@@ -404,7 +421,12 @@ void rebraid(SceneStorage& S, const std::vector<Box>& node_box) {
     S.rb_active = false;
     S.rb_bvh_nodes.clear(); S.rb_scene_bvh.clear(); S.rb_meshes.clear(); S.rb_nodes.clear(); S.rb_node_xf.clear(); S.rb_node_inv_xf.clear(); S.rb_node_alias.clear();
     size_t budget = S.rebraid_entries;
-    if (!budget) if (const char* e = getenv("CTL_REBRAID")) budget = (size_t)atoll(e);
+    if (S.rebraid_entries == kRebraidAuto) {
+        // default: large multi-instance scenes get 1 024 scene-level leaves (measured on the 1 M-triangle configs, profiles/r02a_rebraid_summary.log: +11 % / +22 %
+        // Mrays/s at 1 024, nothing more at 4 096); small scenes keep the reference's one leaf per instance.  CTL_REBRAID=<n> overrides (0 = off).
+        if (const char* e = getenv("CTL_REBRAID")) budget = (size_t)atoll(e);
+        else budget = S.bvh_nodes.size() >= 32768 ? 1024 : 0;
+    }
     const size_t n_real = S.nodes.size();
     if (budget <= n_real || n_real < 2) return;
     struct Entry { uint32_t node; int ref; Box world; float area; uint32_t out_node; };

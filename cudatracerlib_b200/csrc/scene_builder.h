@@ -49,6 +49,7 @@ struct NodeInput {
     int material_override; // -1: use the mesh's material block; else global material offset
 };
 
+constexpr uint32_t kRebraidAuto = 0xffffffffu;
 struct SceneStorage {
     std::vector<ctl_bvh_node> bvh_nodes;
     std::vector<ctl_woop_tri> woop;
@@ -79,7 +80,7 @@ struct SceneStorage {
     // Partial re-braiding of the scene level (opt-in, rebraid()): instances whose boxes overlap are opened into sub-tree entries.  The combined arrays
     // (real + pseudo nodes / meshes / BVH nodes) live beside the real ones, which stay what every other function reads; fill_view hands out the
     // combined set while rb_active.
-    uint32_t rebraid_entries = 0;                  // budget of scene-level leaves; 0 = off (or CTL_REBRAID in the environment)
+    uint32_t rebraid_entries = 0xffffffffu;        // budget of scene-level leaves; 0 = off; kRebraidAuto = by scene size (or CTL_REBRAID in the environment)
     bool rb_active = false;
     std::vector<ctl_bvh_node> rb_bvh_nodes, rb_scene_bvh;
     std::vector<ctl_mesh> rb_meshes;
@@ -133,6 +134,7 @@ void assemble_nodes(SceneStorage& S);
 // csrc/validate.cpp: structural checks of externally supplied BVHs / views (index ranges, tree shape, leaf-run end flags, stack depth); throw std::runtime_error
 int validate_mesh_bvh(const ctl_bvh_node* nodes, uint32_t n_nodes, const uint32_t* index, uint32_t n_refs, uint32_t n_tris, const std::string& what);
 void validate_view(const ctl_scene_view& v);
+int view_stack_depth(const ctl_scene_view& v);   // depth(scene level) + 1 + depth(mesh) + 1, worst instance: must fit the kernels' 64-entry stack
 
 // synthetic scenes
 void make_scene(int kind, int width, int height, uint32_t seed, int n_hint, SceneStorage& out);

@@ -108,13 +108,61 @@ void validate_view(const ctl_scene_view& v) {
         if (node_in_tree[n] && top.depth + 1 + mesh_depth[N.mesh_index] + 1 > 64)
             throw std::runtime_error("scene view: node " + std::to_string(n) + ": tree depths " + std::to_string(top.depth) + " + " + std::to_string(mesh_depth[N.mesh_index]) + " exceed the 64-entry traversal stack");
     }
+    // every triangle's material byte (TriangleData::getMatIndex, Engine/TriangleData.h:40-44) + the node's material offset names an existing material
+    {
+        std::vector<int> mesh_max_mat(v.n_meshes, -1);
+        for (uint32_t n = 0; n < v.n_nodes; n++) {
+            const uint32_t m = v.nodes[n].mesh_index;
+            if (mesh_max_mat[m] < 0) {
+                uint32_t node0, n_nodes, ref0, n_refs, n_tris;
+                mesh_extent(m, node0, n_nodes, ref0, n_refs, n_tris);
+                int mx = 0;
+                for (uint32_t t = 0; t < n_tris; t++) mx = std::max(mx, (int)((v.tri_data[v.meshes[m].tri_offset + t].w[1] >> 16) & 0xffu));
+                mesh_max_mat[m] = mx;
+            }
+            if ((uint64_t)v.nodes[n].material_offset + (uint64_t)mesh_max_mat[m] >= v.n_materials)
+                throw std::runtime_error("scene view: node " + std::to_string(n) + ": a triangle names material " + std::to_string(mesh_max_mat[m]) + " + offset " + std::to_string(v.nodes[n].material_offset) + " of " + std::to_string(v.n_materials));
+        }
+    }
     if (v.num_lights > CTL_MAX_NUM_LIGHTS) throw std::runtime_error("scene view: too many lights");
+    if (v.num_lights && (!v.lights || !v.light_tris || !v.light_cdf_data)) throw std::runtime_error("scene view: null light array");
     for (uint32_t i = 0; i < v.num_lights; i++) {
         if (v.light_indices[i] >= v.n_lights_buf) throw std::runtime_error("scene view: light index out of range");
         const ctl_light& L = v.lights[v.light_indices[i]];
         if ((uint64_t)L.tri_offset + L.count > v.n_light_tris || (uint64_t)L.cdf_offset + L.count + 1 > v.n_light_cdf_data || L.node_idx >= v.n_nodes)
             throw std::runtime_error("scene view: light " + std::to_string(i) + " ranges outside the light arrays");
+        for (uint32_t k = 0; k < L.count; k++) {
+            const ctl_light_tri& T = v.light_tris[L.tri_offset + k];
+            if (T.i_dat >= v.n_woop || T.t_dat >= v.n_tri_data) throw std::runtime_error("scene view: light " + std::to_string(i) + " triangle " + std::to_string(k) + " points outside the triangle arrays");
+        }
     }
+}
+
+// Deepest traversal-stack use of a view built in this library (trees are trees): depth(scene level) + 1 + depth(mesh) + 1 over the instances.
+int view_stack_depth(const ctl_scene_view& v) {
+    auto depth_of = [](const ctl_bvh_node* nodes, uint32_t n_nodes, int start) {
+        if (start < 0 || start == CTL_SENTINEL || !n_nodes) return 0;
+        int deepest = 0; uint64_t visited = 0;
+        std::vector<std::pair<uint32_t, int>> todo; todo.emplace_back((uint32_t)start / 4, 1);
+        while (!todo.empty()) {
+            const auto cur = todo.back(); todo.pop_back();
+            if (cur.first >= n_nodes || ++visited > n_nodes) return 1 << 20;   // not a tree of this array
+            deepest = std::max(deepest, cur.second);
+            for (int c : {nodes[cur.first].child0, nodes[cur.first].child1}) if (c >= 0 && c != CTL_SENTINEL) todo.emplace_back((uint32_t)c / 4, cur.second + 1);
+        }
+        return deepest;
+    };
+    if (!v.n_nodes) return 0;
+    const int top = depth_of(v.scene_bvh_nodes, v.n_scene_bvh_nodes, v.scene_start_node);
+    int worst = 0;
+    std::vector<int> mesh_depth(v.n_meshes, -1);
+    for (uint32_t n = 0; n < v.n_nodes; n++) {
+        const uint32_t m = v.nodes[n].mesh_index;
+        if (m >= v.n_meshes) continue;
+        if (mesh_depth[m] < 0) { const uint32_t node0 = v.meshes[m].bvh_node_offset / 4; mesh_depth[m] = node0 < v.n_bvh_nodes ? depth_of(v.bvh_nodes + node0, v.n_bvh_nodes - node0, 0) : 0; }
+        worst = std::max(worst, top + 1 + mesh_depth[m] + 1);
+    }
+    return worst;
 }
 
 } // namespace ctlb

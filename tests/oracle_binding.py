@@ -145,15 +145,30 @@ def camera_ray(view, px, py):
     o = np.zeros(3, np.float32); d = np.zeros(3, np.float32); oracle().orc_camera_ray(C.byref(view), px, py, _p(o), _p(d)); return o, d
 
 
-def trace_rays(view, rays, counts=False):
+def _alias(view, node_idx, miss):
+    """Re-braided views (ctl_scene_set_rebraid; the default for large multi-instance scenes): the oracle walks the view and reports the pseudo-node it
+    hit; the API names the instance that pseudo-node stands for (view.node_alias), as the reference's own scene would."""
+    if not view.node_alias:
+        return
+    alias = np.ctypeslib.as_array(view.node_alias, shape=(view.n_nodes,))
+    hit = node_idx != miss
+    node_idx[hit] = alias[node_idx[hit]].astype(node_idx.dtype)
+
+
+def trace_rays(view, rays, counts=False, pseudo_nodes=False):
     rays = np.ascontiguousarray(rays, RAY_DTYPE); out = np.zeros(len(rays), TRACE_RESULT_DTYPE); cnt = np.zeros(3, np.uint64)
     oracle().orc_trace_rays(C.byref(view), len(rays), _p(rays), _p(out), _p(cnt) if counts else None)
+    if not pseudo_nodes:
+        _alias(view, out["node_idx"], 0xffffffff)
     return (out, [int(x) for x in cnt]) if counts else out
 
 
-def intersect(view, rays, any_hit=False):
+def intersect(view, rays, any_hit=False, pseudo_nodes=False):
     rays = np.ascontiguousarray(rays, RAY_DTYPE); out = np.zeros(len(rays), RESULT16_DTYPE)
-    oracle().orc_intersect(C.byref(view), len(rays), _p(rays), _p(out), int(any_hit)); return out
+    oracle().orc_intersect(C.byref(view), len(rays), _p(rays), _p(out), int(any_hit))
+    if not pseudo_nodes:
+        _alias(view, out["node_idx"], -1)
+    return out
 
 
 def render(view, w, h, n_passes=1, pass_first=0, max_path_length=8, rr_start=5, direct=1, window=None, n_threads=0, counts=False, img=None):

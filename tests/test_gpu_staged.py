@@ -30,10 +30,6 @@ def test_staged_trace_rays_bit_exact(built_lib, orc, kind, n, rebraid):
             rays = random_rays(s, n, seed=5, inside=inside)
             g, gc = t.trace_rays(rays, counts=True)
             o, oc = orc.trace_rays(s.view, rays, counts=True)
-            if rebraid:   # API results name the instance (k_alias_nodes); the oracle walks the same view and reports pseudo-nodes
-                alias = np.ctypeslib.as_array(s.view.node_alias, shape=(s.view.n_nodes,))
-                hit = o["node_idx"] != 0xffffffff
-                o["node_idx"][hit] = alias[o["node_idx"][hit]]
             assert g.tobytes() == o.tobytes(), shape
             assert gc == oc, shape
     t.close()
@@ -60,6 +56,7 @@ def test_staged_intersect_closest_and_any_hit(built_lib, orc, kind):
 def test_staged_render_equals_persistent_kernel(built_lib, kind, w, h, depth):
     """Same hits => the single-pass image, the ray count and the queue sizes are bit-identical between the two kernels, fused launches included."""
     s, t = make(kind, w, h, depth)
+    t.setParameter("TraversalKernel", 0)
     t.DoPass(True); t.synchronize()
     ref = t.readAccumulator(); ref_rays = t.getRaysInLastPass(); ref_q = t.queueSizes(depth)
     for shape in SHAPES[:3]:
@@ -79,7 +76,7 @@ def test_staged_render_equals_persistent_kernel(built_lib, kind, w, h, depth):
 def test_staged_wavefront_path_tracer_and_instrumented_counts(built_lib, orc):
     w = h = 64
     s = ctl.Scene("cornell7", w, h)
-    a = ctl.WavefrontPathTracer(w, h); a.InitializeScene(s); a.setParameter("MaxPathLength", 8)
+    a = ctl.WavefrontPathTracer(w, h); a.InitializeScene(s); a.setParameter("MaxPathLength", 8); a.setParameter("TraversalKernel", 0)
     a.DoPass(True); a.synchronize(); ref = a.readAccumulator(); ref_q = a.queueSizes(8)
     _staged(a, s, 512, 16, 512)
     a.DoPass(True); a.synchronize()
@@ -90,7 +87,7 @@ def test_staged_wavefront_path_tracer_and_instrumented_counts(built_lib, orc):
     a.close()
     # visit counts of an instrumented PathTracer pass: identical between the kernels (they feed the roofline of bench.py)
     s2, t = make("soup", 96, 96, 6)
-    t.setInstrumented(1); t.DoPass(True); t.synchronize(); c0 = t.visitCounts()
+    t.setParameter("TraversalKernel", 0); t.setInstrumented(1); t.DoPass(True); t.synchronize(); c0 = t.visitCounts()
     _staged(t, s2, 512, 16, 512)
     t.DoPass(True); t.synchronize(); c2 = t.visitCounts()
     assert c0 == c2

@@ -173,3 +173,22 @@ def test_xmsh_reader_survives_damaged_files(built_lib, tmp_path):
         except RuntimeError:
             outcomes["error"] += 1
     assert outcomes["ok"] > 0 and outcomes["error"] > 0
+
+
+def test_ply_vertex_layouts_outside_the_reference_reader(built_lib, tmp_path):
+    """x / y / z must be three consecutive columns starting at x (what the reference reader assumes); other layouts are refused by name instead of
+    indexing past the line (a header listing x last crashed the process), binary files must be position-only."""
+    face = "3 0 1 2\n"
+    def write(name, props, rows, fmt="ascii"):
+        p = str(tmp_path / name)
+        hdr = "ply\nformat %s 1.0\nelement vertex 3\n%selement face 1\nproperty list uchar int vertex_indices\nend_header\n" % (fmt, "".join("property float %s\n" % q for q in props))
+        open(p, "w").write(hdr + rows + face)
+        return p
+    for props, rows in ((["y", "z", "x"], "0 0 0\n1 0 0\n0 1 0\n"), (["x", "nx", "y", "z"], "0 9 0 0\n1 9 0 0\n0 9 1 0\n"), (["z", "y", "x"], "0 0 0\n1 0 0\n0 1 0\n")):
+        with pytest.raises(RuntimeError, match="unsupported vertex layout"):
+            ctl.Scene.from_files(write("bad.ply", props, rows), *CAM, 16, 16)
+    with pytest.raises(RuntimeError, match="unsupported vertex layout"):
+        ctl.Scene.from_files(write("bin.ply", ["x", "y", "z", "nx"], "", fmt="binary_little_endian"), *CAM, 16, 16)
+    # extra columns around a consecutive x y z block are fine in ascii files
+    s = ctl.Scene.from_files(write("ok.ply", ["quality", "x", "y", "z", "nx"], "5 0 0 0 1\n5 1 0 0 1\n5 0 1 0 1\n"), *CAM, 16, 16)
+    assert s.n_triangles == 1

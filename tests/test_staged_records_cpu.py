@@ -45,10 +45,10 @@ def test_staged_records_walk_equals_oracle(built_lib, orc, emu, kind, hint, rebr
     n = 5000
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     rays = _rays(s, n, 31)
-    o, oc = orc.trace_rays(s.view, rays, counts=True)
+    o, oc = orc.trace_rays(s.view, rays, counts=True, pseudo_nodes=True)
     diag = float(np.linalg.norm(np.array(list(s.view.box_max)) - np.array(list(s.view.box_min))))
     seg = _rays(s, n, 32, tmin=1e-3 * diag, tmax=0.35 * diag)
-    refs = [orc.intersect(s.view, seg, any_hit=bool(a)) for a in (0, 1)]
+    refs = [orc.intersect(s.view, seg, any_hit=bool(a), pseudo_nodes=True) for a in (0, 1)]
     seen_tl = set()
     for budget, rows in ((0, 64), (0, 0), (5, 2), (64, 3), (512, 16), (2048, 1)):
         out = np.zeros(n, api.TRACE_RESULT_DTYPE); cnt = np.zeros(3, np.uint64); info = np.zeros(4, np.int32)

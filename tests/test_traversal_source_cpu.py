@@ -47,7 +47,7 @@ def test_device_traversal_source_on_host_vs_oracle(built_lib, orc, emu, kind, hi
     rays = _rays(s, n, 21)
     out = np.zeros(n, api.TRACE_RESULT_DTYPE); cnt = np.zeros(3, np.uint64)
     emu.emu_trace_rays(C.byref(s.view), n, p(rays), p(out), p(cnt))
-    o, oc = orc.trace_rays(s.view, rays, counts=True)
+    o, oc = orc.trace_rays(s.view, rays, counts=True, pseudo_nodes=True)
     assert out.tobytes() == o.tobytes()
     assert [int(x) for x in cnt] == oc
     assert 0.05 < (o["tri_idx"] != 0xffffffff).mean()
@@ -56,6 +56,6 @@ def test_device_traversal_source_on_host_vs_oracle(built_lib, orc, emu, kind, hi
     for any_hit in (0, 1):
         res = np.zeros(n, api.RESULT16_DTYPE)
         emu.emu_intersect(C.byref(s.view), n, p(seg), p(res), any_hit)
-        ref = orc.intersect(s.view, seg, any_hit=bool(any_hit))
+        ref = orc.intersect(s.view, seg, any_hit=bool(any_hit), pseudo_nodes=True)
         assert res.tobytes() == ref.tobytes(), any_hit
         assert (ref["tri_idx"] == -1).any() and (ref["tri_idx"] != -1).any()
