@@ -160,17 +160,37 @@ def cpu_reference_run(view, w, h, depth, window, n_passes, threads):
     return kind, rays, dt
 
 
+def static_config(name, scene, world, tile):
+    """What both arms state identically about the workload (no measured values in here)."""
+    kind, w, h, spp, depth, desc = WORKLOADS[name]
+    return {"workload": desc, "width": w, "height": h, "spp": spp, "max_path_length": depth, "rr_start_depth": 5, "direct": True, "triangles": scene.n_triangles,
+            "partition": "whole image" if world == 1 else f"interleaved {tile}x{tile} tiles, tile % {world} == rank; one NCCL reduce of PixelData (7*w*h f32) per step",
+            "l2": "256 MiB buffer written between timed steps (L2 flush); per-pass queue/path-state working set ~0.5 GB > 126 MB L2"}
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref: its PathTrace / traceRay sources compiled here) on all host
+    cores, rank 0 only.  Same workload and config as the b200 arm; every step renders a bounded sample of the frame -- a centre crop, one pass -- sized by
+    a probe so that the whole run stays within a few minutes (a full 1 M-triangle frame is ~160 M rays, minutes per step on the host)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from cudatracerlib_b200 import Scene
+    from cudatracerlib_b200 import Scene, TILE
     kind, w, h, spp, depth, desc = WORKLOADS[args.workload]
     scene = Scene(kind, w, h)
+    if args.ref_own_tree:
+        if args.workload == "cornell":
+            raise SystemExit("--ref-own-tree: the 100 K / 1 M workloads only")
+        scene = scene_on_reference_tree(scene, w, h)
     threads = os.cpu_count() or 1
-    frac = args.cpu_frac if args.workload != "cornell" else 1.0
-    window = crop_window(w, h, frac)
+    if args.workload == "cornell":
+        window = (0, 0, w, h)
+    else:
+        probe = crop_window(w, h, 1.0 / 256)
+        _, prays, pdt = cpu_reference_run(scene.view, w, h, depth, probe, 1, threads)
+        budget_s = max(0.5, min(6.0, args.ref_seconds / max(1, args.warmup + args.steps)))   # seconds of host work per step
+        frac = min(1.0, (1.0 / 256) * budget_s / max(pdt, 1e-3))
+        window = crop_window(w, h, frac)
     times, rays_tot, impl_kind = [], 0, "port"
     for i in range(args.warmup + args.steps):
         impl_kind, rays, dt = cpu_reference_run(scene.view, w, h, depth, window, 1, threads)
@@ -178,66 +198,69 @@ def run_reference(args):
             times.append(dt); rays_tot += rays
     total = sum(times)
     v = rays_tot / total / 1e6
-    sample = f"{window[2]-window[0]}x{window[3]-window[1]} centre crop of the {w}x{h} image, 1 pass per step (of {spp}), depth {depth}"
+    sample = f"{window[2]-window[0]}x{window[3]-window[1]} centre crop of the {w}x{h} image, 1 pass per step (of {spp}), depth {depth}" + \
+             (", mesh trees built by the reference's own SplitBVHBuilder" if args.ref_own_tree else ", trees of this repo's builder (same arrays as the b200 arm)")
     line = {"impl": "reference", "metric": baseline_metric(), "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": desc, "width": w, "height": h, "spp": spp, "max_path_length": depth, "sample": sample},
+            "data": "synthetic", "config": static_config(args.workload, scene, max(1, args.gpus), args.tile or TILE),
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": threads, "kind": impl_kind, "sample": sample},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-frac", type=float, default=1.0 / 16, help="fraction of the image the CPU baseline renders per step")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sort-mode", type=int, default=None)
-    ap.add_argument("--set", action="append", default=[], metavar="KEY=INT", help="extra tracer parameter (ctl_set_param_i), for A/B runs")
-    ap.add_argument("--tile", type=int, default=0, help="tile edge for the multi-GPU partition (0 = package default)")
-    ap.add_argument("--batch", type=int, default=8, help="progressive passes fused into one wavefront (must divide spp)")
-    args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "b200":
-        args.warmup = 3  # timing rule: W >= 3
-    if args.impl == "reference":
-        return run_reference(args)
+def scene_on_reference_tree(scene, w, h):
+    """The same scene with every mesh BVH built by the reference's OWN SplitBVHBuilder (through oracle/_ref's Mesh::CompileMesh -> .xmsh writer, then the
+    .xmsh import): the CPU baseline as "the reference on its own tree".  Minutes for 1 M triangles (its builder is single-threaded)."""
+    import ctypes as C
+    import ref_binding as rb
+    from cudatracerlib_b200 import api, Scene
+    if not rb.available():
+        raise SystemExit("--ref-own-tree needs oracle/_ref (built where /root/reference is mounted)")
+    scene.setRebraid(0)
+    tmp = tempfile.mkdtemp()
+    tri_data = scene.array("tri_data"); meshes = scene.array("meshes"); nodes = scene.array("nodes")
+    v = scene.view
+    mats_all = (api.Material * v.n_materials).from_address(C.addressof(v.materials.contents))
+    lights = (api.Light * max(1, v.n_lights_buf)).from_address(C.addressof(v.lights.contents)) if v.n_lights_buf else []
+    paths = []
+    for mi in range(len(meshes)):
+        T = scene.mesh_triangles(mi)
+        toff, moff = int(meshes[mi][0]), int(meshes[mi][4])
+        mat_idx = ((tri_data[toff:toff + len(T), 1] >> 16) & 0xff).astype(np.int64)
+        order = np.argsort(mat_idx, kind="stable"); used = int(mat_idx.max()) + 1
+        V = T[order].reshape(-1, 3); I = np.arange(len(V), dtype=np.uint32)
+        node = next(n for n in range(len(nodes)) if int(nodes[n][0]) == mi)
+        em = np.zeros((used, 3), np.float32)
+        for k in range(used):
+            nli = mats_all[int(nodes[node][1]) + k].node_light_index
+            if nli != 0xffffffff:
+                em[k] = list(lights[int(nodes[node][4 + nli])].radiance)
+        pth = os.path.join(tmp, f"m{mi}.xmsh")
+        rb.write_xmsh(pth, V, I, np.bincount(mat_idx, minlength=used), [mats_all[moff + k] for k in range(used)], em)
+        paths.append(pth)
+    xf = scene.array("node_xf").reshape(-1, 16)
+    cam = ((0, 0, -9.5), (0, 0, 0), (0, 1, 0), 60.0)   # camera of the 100 K / 1 M scenes (csrc/scene_builder.cpp)
+    s2 = Scene.from_xmsh([paths[int(nodes[n][0])] for n in range(len(nodes))], *cam, w, h, node_xforms=xf)
+    s2.setRebraid(0)
+    return s2
 
-    import torch
-    import torch.distributed as dist
-    from cudatracerlib_b200 import Scene, PathTracer, DistributedFrame, traversal_bytes, build, TILE
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
-    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        args.gpus = world
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    if rank == 0:
-        build.build()
-    if world > 1:
-        dist.barrier()
 
-    kind, w, h, spp, depth, desc = WORKLOADS[args.workload]
-    if args.tile > 0:
-        TILE = args.tile
+def measure_workload(name, args, torch, dist, world, rank, local, dev, stream, steps, warmup, primary):
+    """One workload on this rank's share of the image.  Returns (line fields of rank 0, scene)."""
+    from cudatracerlib_b200 import Scene, PathTracer, DistributedFrame, traversal_bytes, TILE
+    kind, w, h, spp, depth, desc = WORKLOADS[name]
+    tile = args.tile if args.tile > 0 else TILE
     scene = Scene(kind, w, h)
     tracer = PathTracer(w, h, device=local)
     tracer.InitializeScene(scene)
     tracer.setParameter("MaxPathLength", depth)
     if args.sort_mode is not None:
         tracer.setParameter("SortMode", args.sort_mode)
+    reupload = False
     for kv in args.set:
-        k, v = kv.split("="); tracer.setParameter(k, int(v))
-    stream = torch.cuda.Stream(device=dev)  # a real (non-default) stream: the tracer, NCCL and the timing events all use it
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
+        k, v = kv.split("="); tracer.setParameter(k, int(v)); reupload |= k == "StagedTreeletNodes"
+    if reupload:
+        tracer.InitializeScene(scene)
     tracer.setStream(stream.cuda_stream)
     accum = torch.zeros(h * w * 7, dtype=torch.float32, device=dev)
     tracer.setAccumDevicePtr(accum.data_ptr())
@@ -245,12 +268,11 @@ def main():
     d_rgba = torch.empty(h * w * 4, dtype=torch.uint8, device=dev)
     host_rgba = torch.empty(h * w * 4, dtype=torch.uint8, pin_memory=True)
     table_bytes = 4096 * 30 * 12
-
     batch = min(spp, args.batch)
 
     def render_pass(p, new_trace):
         # `batch` progressive passes fused into one wavefront (ctl_render_passes_tiled) on this rank's tiles
-        tracer.DoPasses(batch, new_trace=new_trace, tile=(TILE, TILE), part=rank, n_parts=world)
+        tracer.DoPasses(batch, new_trace=new_trace, tile=(tile, tile), part=rank, n_parts=world)
 
     df = DistributedFrame(accum, render_pass, lambda: 0)
 
@@ -268,28 +290,29 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)
+    if primary:
+        clocks.start()   # before the warm-up: short timed regions (8 GPUs) still collect samples under load
     # ---- warm-up
     rays_per_frame_local = 0
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         r0 = tracer.getTotalRays()
         frame(False)
         rays_per_frame_local = tracer.getTotalRays() - r0  # frames are identical (new_trace restarts the sample stream)
     sync_all()
 
     # ---- device-timed steps (value)
-    clocks = ClockSampler(local); clocks.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    rays_steps = 0
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     sync_all()
     t_wall0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(steps):
         flush.zero_()  # L2 flush between timed iterations, outside the event bracket
         ev[i][0].record(stream)
         frame(False)
         ev[i][1].record(stream)
     sync_all()
     t_wall = time.perf_counter() - t_wall0
-    clk = clocks.stop()
+    clk = clocks.stop() if primary else None
     step_ms = [a.elapsed_time(b) for a, b in ev]
     dev_ms = float(sum(step_ms))
     t = torch.tensor([dev_ms, float(rays_per_frame_local)], dtype=torch.float64, device=dev)
@@ -299,11 +322,11 @@ def main():
         dev_ms, rays_frame = float(tmax[0]), float(tsum[1])
     else:
         rays_frame = float(t[1])
-    value = rays_frame * args.steps / (dev_ms * 1e-3) / 1e6
+    value = rays_frame * steps / (dev_ms * 1e-3) / 1e6
     launches_per_batch = tracer.stageTimes()[1]
 
     # ---- end-to-end steps through the public API with host buffers
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(2, min(steps, 10))
     tracer.setParameter("DeviceSampleTables", 0)   # e2e: the step's inputs (the pass sample tables) come from the host, like the reference's UpdateKernel
     frame(True)
     sync_all()
@@ -341,28 +364,34 @@ def main():
     n_trav_launches = depth + 1 if fused else 2 * depth   # fused: ext(0), [shadow(b-1)+ext(b)] x (depth-1), shadow(depth-1)
     peak, peak_src = hbm_peak()
     achieved = bytes_batch / (trav_ms_batch * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "k_intersect / k_intersect_fused (all traversal launches of a wavefront)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    tk = tracer.getParameter("TraversalKernel")
+    n_rays_b = max(1, e_cnt[3] + s_cnt[3])
+    roof = {"bound": "hbm", "kernel": {0: "k_intersect / k_intersect_fused", 1: "k_intersect_simple", 2: "k_intersect_staged"}.get(tk, "?") + " (all traversal launches of a wavefront)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
             "algorithmic_bytes_per_launch": bytes_batch / n_trav_launches, "avg_launch_ms": trav_ms_batch / n_trav_launches,
-            "bytes_per_ray": bytes_batch / max(1, e_cnt[3] + s_cnt[3]), "launches_per_batch": n_trav_launches, "passes_per_batch": batch,
+            "bytes_per_ray": bytes_batch / n_rays_b, "launches_per_batch": n_trav_launches, "passes_per_batch": batch,
+            "visits_per_ray": {"inner_nodes": (e_cnt[0] + s_cnt[0]) / n_rays_b, "triangle_tests": (e_cnt[1] + s_cnt[1]) / n_rays_b, "instance_entries": (e_cnt[2] + s_cnt[2]) / n_rays_b},
             "traversal_share_of_batch": (stage_last[1] + stage_last[3]) / max(1e-9, sum(stage_last)),
-            "stage_ms_last_batch": {"generate": stage_last[0], "extension": stage_last[1], "shade": stage_last[2], "shadow": stage_last[3], "finish": stage_last[4]}}
+            "stage_ms_last_batch": {"generate": stage_last[0], "extension": stage_last[1], "shade": stage_last[2], "shadow": stage_last[3], "finish": stage_last[4]},
+            "note": "algorithmic bytes in the reference's record sizes (SURVEY 8d); the BVH is L1/L2-resident, so this is a traversal rate in bytes, not DRAM utilisation -- `traffic` is the measured DRAM side"}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(tp) as f:
-            roof["traffic"] = json.load(f).get(args.workload, {}).get("dram_bytes_per_launch")
+            tj = json.load(f).get(name, {})
+        roof["traffic"] = tj.get("dram_bytes_per_launch"); roof["traffic_source"] = tj.get("source")
     except Exception:
         pass
 
-    # ---- CPU baseline (rank 0, N == 1 only): bounded crop on the host cores
+    # ---- CPU baseline (rank 0, N == 1, primary workload only): bounded crop on the host cores
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and primary and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        frac = args.cpu_frac if args.workload != "cornell" else 1.0
+        frac = args.cpu_frac if name != "cornell" else 1.0
         window = crop_window(w, h, frac)
         ckind, crays, cdt = cpu_reference_run(scene.view, w, h, depth, window, 1, threads)   # probe: 1 pass on the small crop
         n_p = 1
-        if args.workload != "cornell" and cdt < 8.0:
+        if name != "cornell" and cdt < 8.0:
             # size the sample for ~12 s of CPU work: all spp passes on a centre crop of the matching size
             target_rays = 12.0 * crays / max(cdt, 1e-3)
             frac2 = min(1.0, target_rays / (crays / frac * spp))
@@ -374,31 +403,84 @@ def main():
         cpu = {"value": crays / cdt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": ckind,
                "sample": f"{window[2]-window[0]}x{window[3]-window[1]} centre crop of the {w}x{h} image, {n_p} pass(es), depth {depth}, {crays} rays in {cdt:.2f} s"}
 
+    line = None
     if rank == 0:
         line = {
-            "metric": baseline_metric(), "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "width": w, "height": h, "spp": spp, "max_path_length": depth, "rr_start_depth": 5, "direct": True, "passes_per_wavefront": batch,
-                       "triangles": scene.n_triangles, "rays_per_step": rays_frame,
-                       "partition": "whole image" if world == 1 else f"interleaved {TILE}x{TILE} tiles, tile % {world} == rank; one NCCL reduce of PixelData (7*w*h f32) per step",
-                       "l2": "256 MiB buffer written between timed steps (L2 flush); per-pass queue/path-state working set ~0.5 GB > 126 MB L2"},
+            "metric": baseline_metric(), "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": static_config(name, scene, world, tile),
+            "rays_per_step": rays_frame, "passes_per_wavefront": batch,
+            "scene_level": {"leaves": int(scene.view.n_nodes), "re_braided": bool(scene.view.node_alias)},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": spp * table_bytes, "d2h_bytes_per_step": h * w * 4,
                     "steps": e2e_steps, "note": "wall clock; DeviceSampleTables=0: sample tables generated by the host XORWOW twin and copied H2D from pinned memory for every pass, the frame resolved by ctl_resolve_srgb8 (default image pipeline) and the RGBA8 image copied D2H to pinned memory every step"},
-            "gpu_launches": int((launches_per_batch + 1) * (spp // batch) * args.steps),
-            "wall_s_timed_region": t_wall, "image_mean_srgb8": img_mean,
+            "gpu_launches": int((launches_per_batch + 1) * (spp // batch) * steps),
+            "wall_s_timed_region": t_wall, "image_mean_srgb8": img_mean, "roofline": roof,
         }
-        if scene.view.node_alias:   # opt-in A/B (CTL_REBRAID=<entries>): the scene level was re-braided
-            line["config"]["rebraid_entries"] = int(os.environ.get("CTL_REBRAID", "0")); line["config"]["scene_nodes"] = int(scene.view.n_nodes)
-        if roof:
-            line["roofline"] = roof
         if cpu:
             line["cpu_baseline"] = cpu
+    tracer.close()
+    del accum, flush, d_rgba
+    torch.cuda.empty_cache()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS), help="default: configs[3], the 1 M-triangle scene the north star's targets are stated on")
+    ap.add_argument("--cpu-frac", type=float, default=1.0 / 16, help="fraction of the image the CPU baseline renders per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra.configs lines (configs[1], [2], [4] on one GPU)")
+    ap.add_argument("--ref-seconds", type=float, default=100.0, help="--impl reference: host seconds the whole run may take (sizes the per-step sample)")
+    ap.add_argument("--ref-own-tree", action="store_true", help="--impl reference: mesh trees from the reference's own SplitBVHBuilder")
+    ap.add_argument("--sort-mode", type=int, default=None)
+    ap.add_argument("--set", action="append", default=[], metavar="KEY=INT", help="extra tracer parameter (ctl_set_param_i), for A/B runs")
+    ap.add_argument("--tile", type=int, default=0, help="tile edge for the multi-GPU partition (0 = package default)")
+    ap.add_argument("--batch", type=int, default=8, help="progressive passes fused into one wavefront (must divide spp)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rule: W >= 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from cudatracerlib_b200 import build
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    stream = torch.cuda.Stream(device=dev)  # a real (non-default) stream: the tracer, NCCL and the timing events all use it
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+
+    line = measure_workload(args.workload, args, torch, dist, world, rank, local, dev, stream, args.steps, args.warmup, True)
+    # the other single-GPU configurations of BASELINE.json (configs[1], [2], [4]) next to the headline: shorter runs, same measurement
+    if world == 1 and not args.no_extra and args.workload == "c4":
+        extra = {}
+        for name, st in (("c2", 5), ("c3", 5), ("c5", 2)):
+            x = measure_workload(name, args, torch, dist, world, rank, local, dev, stream, st, 3, False)
+            extra[name] = {k: x[k] for k in ("value", "unit", "steps", "warmup", "ms_per_step", "config", "rays_per_step", "scene_level", "e2e", "roofline", "image_mean_srgb8")}
+        line["extra"] = {"configs": extra}
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    tracer.close()
 
 
 if __name__ == "__main__":

@@ -92,7 +92,7 @@ struct ctl_ctx {
     std::vector<cudaEvent_t> stage_ev; std::vector<int> stage_kind;
     float stage_ms[5] = {0, 0, 0, 0, 0}; uint32_t n_launches = 0;
     bool instrumented = false;
-    TravTune tune = {2, 8, 8, 4, 1};
+    TravTune tune = {2, 8, 8, 6, 2}, tune_p = {2, 8, 8, 4, 1};   // scheduler parameters of the staged kernel (swept on the device: profiles/r02c_tune_sweep.log) / of the persistent kernel (profiles/r01d_*)
     // staged traversal kernel (device/traverse_staged.cuh): derived records + launch shape
     DevBuf<float4> d_tri64, d_inst, d_treelet; StagedScene staged = {nullptr, nullptr, nullptr, 0, 0, 16}; bool staged_ok = false; std::string staged_why;
     int staged_threads = 512, staged_rows = 16, staged_treelet = 0, staged_resident = 1024;   // "StagedThreads", "StagedStackRows", "StagedTreeletNodes", "StagedResidentThreads"
@@ -126,7 +126,7 @@ static void launch_intersect(const ctl_ctx* c, int grid, cudaStream_t st, const 
         launch_staged<MODE, ANY_HIT, COUNT>(c, st, rays, n_ptr, nullptr, n_fixed, work_ctr, out, visit_out);
     }
     else if (c->trav_kernel == 1) k_intersect_simple<MODE, ANY_HIT, COUNT><<<grid, 128, 0, st>>>(S, rays, n_ptr, n_fixed, work_ctr, hit_a, hit_node, sh_payload, cl, api_out, visit_out);
-    else k_intersect<MODE, ANY_HIT, COUNT><<<grid, 128, 0, st>>>(S, c->tune, rays, n_ptr, n_fixed, work_ctr, hit_a, hit_node, sh_payload, cl, api_out, visit_out);
+    else k_intersect<MODE, ANY_HIT, COUNT><<<grid, 128, 0, st>>>(S, c->tune_p, rays, n_ptr, n_fixed, work_ctr, hit_a, hit_node, sh_payload, cl, api_out, visit_out);
 }
 
 extern "C" {
@@ -428,8 +428,8 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "StagedResidentThreads") { if (v < 32 || v > 2048) return set_err("StagedResidentThreads out of range [32,2048]"); c->staged_resident = v; }
     else if (k == "StagedStackRows") { if (v < 0 || v > TP_STACK) return set_err("StagedStackRows out of range [0,64]"); c->staged_rows = v; c->staged.stack_rows = v; }
     else if (k == "StagedTreeletNodes") { if (v < 0 || v > 2048) return set_err("StagedTreeletNodes out of range [0,2048]"); c->staged_treelet = v; }   // takes effect at the next ctl_upload_scene / ctl_update_scene_nodes
-    else if (k == "TravThT") c->tune.th_t = v; else if (k == "TravThL") c->tune.th_l = v; else if (k == "TravThF") c->tune.th_f = v;
-    else if (k == "TravThNExit") c->tune.th_n_exit = v;
+    else if (k == "TravThT") c->tune.th_t = c->tune_p.th_t = v; else if (k == "TravThL") c->tune.th_l = c->tune_p.th_l = v; else if (k == "TravThF") c->tune.th_f = c->tune_p.th_f = v;
+    else if (k == "TravThNExit") c->tune.th_n_exit = c->tune_p.th_n_exit = v;
     else if (k == "TravTSteps") { if (v < 1 || v > 8) return set_err("TravTSteps out of range [1,8]"); c->tune.t_steps = v; }
     else if (k == "ShadeBlocksPerSM") { if (v < 1 || v > 16) return set_err("ShadeBlocksPerSM out of range [1,16]"); c->shade_blocks_per_sm = v; }
     else if (k == "TravSmemCarveout") { // experiment: shared-memory carve-out (percent) of the traversal kernels = how much L1 they lose
@@ -732,7 +732,7 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
                 const TravOut out = {c->hit_a.p, c->hit_node.p, c->sh_payload.p, c->cl.p, nullptr, c->sh_rays.p, 0, nullptr};
                 launch_staged<4, false, false>(c, c->stream, rin, ctr + CTR_Q + b, ctr + CTR_SH + b - 1, 0, ctr + CTR_WORK + 2 * b, out, nullptr);
             } else
-            k_intersect_fused<<<g_trav, 128, 0, c->stream>>>(c->scene, c->tune, rin, ctr + CTR_Q + b, c->sh_rays.p, ctr + CTR_SH + b - 1, ctr + CTR_WORK + 2 * b,
+            k_intersect_fused<<<g_trav, 128, 0, c->stream>>>(c->scene, c->tune_p, rin, ctr + CTR_Q + b, c->sh_rays.p, ctr + CTR_SH + b - 1, ctr + CTR_WORK + 2 * b,
                                                               c->hit_a.p, c->hit_node.p, c->sh_payload.p, c->cl.p);
         }
         else if (c->instrumented) launch_intersect<0, false, true>(c, g_trav, c->stream, c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, c->stats.p + 2);
@@ -870,7 +870,7 @@ int ctl_wavefront_pass(ctl_ctx* c, int new_trace) {
             launch_staged<5, false, false>(c, c->stream, (const float4*)c->w_ray.p, ctr + CTR_Q + d, ctr + CTR_SH + d - 1, 0, ctr + CTR_WORK + 2 * d, out, nullptr);
             launches++;
         } else if (have_sec && c->fuse_traversal && c->trav_kernel == 0) {
-            k_intersect_fused_api<<<g_trav, 128, 0, c->stream>>>(c->scene, c->tune, (const float4*)c->w_ray.p, ctr + CTR_Q + d, (const float4*)c->w_sec[(d - 1) & 1].p, ctr + CTR_SH + d - 1,
+            k_intersect_fused_api<<<g_trav, 128, 0, c->stream>>>(c->scene, c->tune_p, (const float4*)c->w_ray.p, ctr + CTR_Q + d, (const float4*)c->w_sec[(d - 1) & 1].p, ctr + CTR_SH + d - 1,
                                                                   ctr + CTR_WORK + 2 * d, (void*)c->w_res.p, (void*)c->w_sres[(d - 1) & 1].p);
             launches++;
         } else {
