@@ -60,7 +60,7 @@ struct ctl_ctx {
     int n_sm = 148;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     // parameters (Integrators/PathTracer.h:10-20)
-    int max_path_length = 50, rr_start = 5, direct = 1, regularization = 0, sort_mode = 0, stage_timers = 0, capture_bounce = 0, trav_kernel = 2, trav_blocks_per_sm = 8, shade_blocks_per_sm = 8, smem_carveout = -1, fuse_traversal = 1, warp_blocks = 0, pass_stride = 1, pass_phase = 0;
+    int max_path_length = 50, rr_start = 5, direct = 1, regularization = 0, sort_mode = 0, stage_timers = 0, capture_bounce = 0, trav_kernel = 2, trav_blocks_per_sm = 8, shade_blocks_per_sm = 8, smem_carveout = -1, fuse_traversal = 1, warp_blocks = 0, pass_stride = 1, pass_phase = 0, stop_zero = 1;
     // scene
     DevBuf<ctl_bvh_node> d_scene_nodes, d_bvh_nodes; DevBuf<ctl_woop_tri> d_woop; DevBuf<uint32_t> d_tri_index; DevBuf<ctl_tri_data> d_tri_data;
     DevBuf<ctl_mesh> d_meshes; DevBuf<ctl_node> d_nodes; DevBuf<float> d_xf, d_inv_xf; DevBuf<ctl_material> d_materials; DevBuf<ctl_light> d_lights;
@@ -75,7 +75,7 @@ struct ctl_ctx {
     uint32_t gen_pos_host = 0, gen_pos_dev = 0;   // index of the next pass each generator would produce
     ctlb::SamplerTableGenerator gen;
     // wavefront state
-    DevBuf<float4> cf, cl, nor, px, rays_a, rays_b, hit_a, sh_rays, sh_payload, capture;
+    DevBuf<float4> wo_prev; DevBuf<float4> cf, cl, nor, px, rays_a, rays_b, hit_a, sh_rays, sh_payload, capture;
     DevBuf<uint32_t> path_a, path_b, path_c, hit_node, sort_keys; DevBuf<float4> rays_c; DevBuf<unsigned> sort_hist, sort_offsets, mat_hist; DevBuf<unsigned char> mat_cls; DevBuf<uint32_t> mat_order;
     DevBuf<unsigned> counters;
     DevBuf<unsigned> api_work; unsigned api_seq = 0;   // ring of work counters of the API traversal launches: calls in flight on different streams never share one
@@ -386,7 +386,7 @@ void ctl_destroy(ctl_ctx* c) {
     c->d_light_cdf.release(); c->d_normal_lut.release(); c->d_tri64.release(); c->d_inst.release(); c->d_treelet.release();
     c->d_tab1.release(); c->d_tab2.release(); c->d_states.release(); c->d_states0.release(); c->d_jump.release();
     if (c->h_tab1) cudaFreeHost(c->h_tab1); if (c->h_tab2) cudaFreeHost(c->h_tab2); if (c->h_tab_free) cudaEventDestroy(c->h_tab_free);
-    c->cf.release(); c->cl.release(); c->nor.release(); c->px.release(); c->rays_a.release(); c->rays_b.release(); c->hit_a.release(); c->sh_rays.release();
+    c->wo_prev.release(); c->cf.release(); c->cl.release(); c->nor.release(); c->px.release(); c->rays_a.release(); c->rays_b.release(); c->hit_a.release(); c->sh_rays.release();
     c->sh_payload.release(); c->capture.release(); c->path_a.release(); c->path_b.release(); c->path_c.release(); c->rays_c.release(); c->sort_keys.release(); c->sort_hist.release(); c->sort_offsets.release(); c->mat_hist.release(); c->mat_cls.release(); c->mat_order.release(); c->hit_node.release(); c->counters.release(); c->api_work.release(); c->stats.release();
     c->own_accum.release(); c->d_captured_n.release(); c->resolve_tmp.release(); c->pipe_rgbe.release(); c->pipe_partial.release(); c->pipe_lum.release(); c->d_var.release(); c->nlm_cached.release(); c->nlm_varh.release(); c->nlm_weights.release(); c->nlm_last_update = -1; c->nlm_pixels = 0; c->d_node_alias.release();
     c->w_thr.release(); c->w_lxy.release(); c->w_df.release(); c->w_ray.release(); c->w_misc.release(); c->w_res.release(); c->w_desc.release();
@@ -413,6 +413,7 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     if (k == "MaxPathLength") { if (v < 1 || v > MAX_BOUNCES) return set_err("MaxPathLength out of range [1,256]"); c->max_path_length = v; }
     else if (k == "RRStartDepth") { if (v < 0) return set_err("RRStartDepth must be >= 0"); c->rr_start = v; }
     else if (k == "Direct") c->direct = v != 0;
+    else if (k == "StopZeroThroughput") c->stop_zero = v != 0;   // 1 (default): a path whose throughput is exactly zero ends; 0: it is traced until Russian roulette ends it, the reference's ray count (Kernel/TraceHelper.cu:176)
     else if (k == "Regularization") { if (v != 0) return set_err("Regularization=true is not implemented (off by default in the reference)"); c->regularization = 0; }
     else if (k == "SortMode") c->sort_mode = v;
     else if (k == "StageTimers") c->stage_timers = v != 0;
@@ -445,7 +446,7 @@ int ctl_get_param_i(ctl_ctx* c, const char* key, int* v) {
     if (!c || !key || !v) return set_err("null argument");
     std::string k(key);
     if (k == "MaxPathLength") *v = c->max_path_length; else if (k == "RRStartDepth") *v = c->rr_start; else if (k == "Direct") *v = c->direct;
-    else if (k == "Regularization") *v = c->regularization; else if (k == "SortMode") *v = c->sort_mode; else if (k == "StageTimers") *v = c->stage_timers;
+    else if (k == "StopZeroThroughput") *v = c->stop_zero; else if (k == "Regularization") *v = c->regularization; else if (k == "SortMode") *v = c->sort_mode; else if (k == "StageTimers") *v = c->stage_timers;
     else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables; else if (k == "FuseTraversal") *v = c->fuse_traversal; else if (k == "PixelVarianceBuffer") *v = c->variance_buffer; else if (k == "PassStride") *v = c->pass_stride; else if (k == "PassPhase") *v = c->pass_phase;
     else if (k == "TraversalBlocksPerSM") *v = c->trav_blocks_per_sm; else if (k == "StagedThreads") *v = c->staged_threads; else if (k == "StagedStackRows") *v = c->staged_rows;
     else if (k == "StagedTreeletNodes") *v = c->staged.tl_nodes; else if (k == "StagedUsable") *v = c->staged_ok ? 1 : 0; else return set_err("unknown parameter key: " + k);
@@ -666,6 +667,7 @@ static int ensure_state(ctl_ctx* c, size_t n) {
     CK(c->cf.ensure(n)); CK(c->cl.ensure(n)); CK(c->nor.ensure(n)); CK(c->px.ensure(n));
     CK(c->rays_a.ensure(2 * n)); CK(c->rays_b.ensure(2 * n)); CK(c->hit_a.ensure(n)); CK(c->hit_node.ensure(n));
     CK(c->sh_rays.ensure(2 * n)); CK(c->sh_payload.ensure(n)); CK(c->path_a.ensure(n)); CK(c->path_b.ensure(n));
+    if (!c->stop_zero) CK(c->wo_prev.ensure(n));
     if (c->sort_mode == 2) { CK(c->mat_cls.ensure(n)); CK(c->mat_order.ensure(n)); CK(c->mat_hist.ensure(2 * MAT_CLASSES * (MAX_BOUNCES + 1))); }
     if (c->sort_mode == 1) {
         CK(c->rays_c.ensure(2 * n)); CK(c->path_c.ensure(n)); CK(c->sort_keys.ensure(n));
@@ -710,14 +712,14 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
     if (c->sort_mode == 2) CK(cudaMemsetAsync(c->mat_hist.p, 0, 2 * MAT_CLASSES * (MAX_BOUNCES + 1) * sizeof(unsigned), c->stream));
     if (c->instrumented) CK(cudaMemsetAsync(c->stats.p + 2, 0, 8 * sizeof(unsigned long long), c->stream));
     unsigned* ctr = c->counters.p;
-    PathState st = {c->cf.p, c->cl.p, c->nor.p, c->px.p};
+    PathState st = {c->cf.p, c->cl.p, c->nor.p, c->px.p, c->stop_zero ? nullptr : c->wo_prev.p};
     const int g_light = grid_for(c, c->shade_blocks_per_sm);
     const int g_trav = grid_for(c, c->trav_blocks_per_sm);
     uint32_t launches = 0;
     stage_mark(c, 0);
     k_generate<<<g_light, 256, 0, c->stream>>>(c->scene, W, st, c->rays_a.p, c->path_a.p, ctr + CTR_Q + 0);
     launches++;
-    ShadeParams P = {c->max_path_length, c->rr_start, c->direct};
+    ShadeParams P = {c->max_path_length, c->rr_start, c->direct, c->stop_zero};
     float4* rin = c->rays_a.p; float4* rout = c->rays_b.p; uint32_t* pin = c->path_a.p; uint32_t* pout = c->path_b.p;
     float4* rspare = c->rays_c.p; uint32_t* pspare = c->path_c.p;
     const bool fuse = c->fuse_traversal && c->direct && !c->instrumented && (c->trav_kernel == 0 || (c->trav_kernel == 2 && c->staged_ok));

@@ -27,6 +27,8 @@ struct PathState {
     float4* cl;   // radiance rgb, -
     float4* nor;  // last_nor xyz, packed (depth | specular<<8 | i1<<9 | i2<<19)
     float4* px;   // pX, pY, sampler index bits, (pass-in-batch + 1) as uint bits (0 = no path)
+    float4* wo;   // StopZeroThroughput=0 only (else null): the last sampled local direction -- the reference's BSDFSamplingRecord lives across the
+                  // loop, so a failed sample continues along the previous wo (PathTracer.cu:44, 80-93)
 };
 
 struct Queues {
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(256) k_matsort_scatter(const unsigned* __restr
 }
 
 // ---- shade: one path vertex (PathTracer.cu:58-96) ----------------------------------
-struct ShadeParams { int max_path_length, rr_start, direct; };
+struct ShadeParams { int max_path_length, rr_start, direct, stop_zero; };
 
 #ifndef CTL_SHADE_MIN_BLOCKS
 #define CTL_SHADE_MIN_BLOCKS 8 // 64 registers: 8 resident blocks per SM; measured -18% (diffuse) / -27% (microfacet) shade time vs 116 registers
@@ -374,6 +376,7 @@ __global__ void __launch_bounds__(128, CTL_SHADE_MIN_BLOCKS) k_shade(const __gri
                 const ctl_node* N = S.nodes + node;
                 const ctl_material mat = S.materials[mat_local + __ldg(&N->material_offset)];
                 BRec bRec; bRec.eta = 1.0f; bRec.sampledType = 0; bRec.typeMask = E_ALL; bRec.wo = mk(0, 0, 1);
+                if (st.wo && depth > 1) { const float4 w4 = st.wo[p]; bRec.wo = mk(w4.x, w4.y, w4.z); }
                 bRec.wi = to_local(dg.sys, -rd);
                 if ((mat.flags & CTL_MAT_TWO_SIDED) && bRec.wi.z < 0) { dg.n = -dg.n; dg.sys.n = -dg.sys.n; bRec.wi.z *= -1.0f; }
                 // emitter hit with MIS (PathTracer.cu:64-77)
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(128, CTL_SHADE_MIN_BLOCKS) k_shade(const __gri
                 specularBounce = (bRec.sampledType & E_DELTA) != 0;
                 cf = cf * f;
                 nd = to_world(dg.sys, bRec.wo); no = dg.P;
-                alive = !is_zero(cf);
+                alive = !P.stop_zero || !is_zero(cf);   // stop_zero: a path of zero throughput ends here (no image effect); off: it lives until Russian roulette, as in the reference
                 if (alive && depth > P.rr_start && !specularBounce) {
                     const float q = smax(cf);
                     if (rnd.f1(S) >= q) alive = false;
@@ -434,6 +437,7 @@ __global__ void __launch_bounds__(128, CTL_SHADE_MIN_BLOCKS) k_shade(const __gri
                 if (alive) {
                     st.cf[p] = make_float4(cf.r, cf.g, cf.b, brdf_pdf);
                     st.nor[p] = make_float4(last_nor.x, last_nor.y, last_nor.z, __uint_as_float(pack_ctl(depth, specularBounce, rnd.i1, rnd.i2)));
+                    if (st.wo) st.wo[p] = make_float4(bRec.wo.x, bRec.wo.y, bRec.wo.z, 0.0f);
                 }
             }
         }

@@ -703,6 +703,7 @@ void camera_ray(const ctl_camera& C, float px, float py, V3& o, V3& d) {
 }
 
 struct PTParams { int max_path_length, rr_start, direct; };
+static int g_stop_zero = 1;   // the product's default (StopZeroThroughput=1); 0 reproduces the reference's ray count exactly
 
 inline uint32_t mat_index_of(const ctl_scene_view& S, const Hit& h) { // TraceResult.cu:81-84
     return ((S.tri_data[h.tri].w[1] >> 16) & 0xff) + S.nodes[h.node].material_offset;
@@ -779,7 +780,7 @@ Spec path_trace(const ctl_scene_view& S, V3 ro, V3 rd, Sampler& rnd, const PTPar
         specularBounce = (bRec.sampledType & E_DELTA) != 0;
         cf = smul(cf, f);
         rd = to_world(bRec.dg.sys, bRec.wo); ro = bRec.dg.P;
-        if (sis_zero(cf)) break; // see deviation note above
+        if (g_stop_zero && sis_zero(cf)) break; // see deviation note above; orc_set_stop_zero_throughput(0) = the reference's own behaviour
         if (depth > P.rr_start && !specularBounce) {
             if (rnd.f1() >= smax(cf)) break;
             cf = sdivf(cf, smax(cf));
@@ -926,6 +927,8 @@ void orc_intersect(const ctl_scene_view* S, int n, const ctl_traversal_ray* rays
 // (accumulated, not cleared): the loop of pathKernel2's body (PathTracer.cu:184-193) over pixels.
 // Rows are distributed over n_threads; samples are splatted serially in pixel order so the result is
 // independent of the thread count. rays_out: traceRay calls (extension + shadow).
+// 1 (default) = the product's StopZeroThroughput=1; 0 = zero-throughput paths live until Russian roulette: the reference's own ray count (pinned against oracle/_ref)
+void orc_set_stop_zero_throughput(int on) { g_stop_zero = on != 0; }
 void orc_render(const ctl_scene_view* S, int w, int h, int x0, int y0, int x1, int y1, int pass_first, int n_passes,
                 int max_path_length, int rr_start, int direct, ctl_pixel_data* img, uint64_t* rays_out, int n_threads, uint64_t* counts) {
     std::vector<float> d1((size_t)N_SEQ * SEQ_LEN), d2((size_t)N_SEQ * SEQ_LEN * 2);

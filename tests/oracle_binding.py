@@ -171,6 +171,12 @@ def intersect(view, rays, any_hit=False, pseudo_nodes=False):
     return out
 
 
+def set_stop_zero_throughput(on):
+    """orc_set_stop_zero_throughput: 1 = the product default (a path of exactly zero throughput ends), 0 = the reference's behaviour (it lives until
+    Russian roulette; identical images, more rays).  Applies to both oracle builds when loaded."""
+    oracle().orc_set_stop_zero_throughput(int(on))
+
+
 def render(view, w, h, n_passes=1, pass_first=0, max_path_length=8, rr_start=5, direct=1, window=None, n_threads=0, counts=False, img=None):
     if img is None:
         img = np.zeros((h, w), PIXEL_DTYPE)
