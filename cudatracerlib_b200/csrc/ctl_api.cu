@@ -95,9 +95,20 @@ struct ctl_ctx {
     TravTune tune = {2, 8, 8, 6, 2}, tune_p = {2, 8, 8, 4, 1};   // scheduler parameters of the staged kernel (swept on the device: profiles/r02c_tune_sweep.log) / of the persistent kernel (profiles/r01d_*)
     // staged traversal kernel (device/traverse_staged.cuh): derived records + launch shape
     DevBuf<float4> d_tri64, d_inst, d_treelet; StagedScene staged = {nullptr, nullptr, nullptr, 0, 0, 16}; bool staged_ok = false; std::string staged_why;
+    int shade_mode = 1; uint32_t class_mask = 0; bool class_ok = false;   // "ShadeMode": 0 = one k_shade with the run-time BSDF dispatch, 1 = one launch per material class present (staged kernel only)
     int staged_threads = 512, staged_rows = 16, staged_treelet = 0, staged_resident = 1024;   // "StagedThreads", "StagedStackRows", "StagedTreeletNodes", "StagedResidentThreads"
 };
 
+
+static void launch_shade(int cls, int grid, cudaStream_t st, const DScene& S, const ShadeParams& P, const PathState& ps, const Queues& Q, const unsigned* n_in, unsigned* n_out, unsigned* n_shadow, const unsigned* seg_hist) {
+    switch (cls) {
+    case 0: k_shade<0><<<grid, 128, 0, st>>>(S, P, ps, Q, n_in, n_out, n_shadow, seg_hist); break;
+    case 1: k_shade<1><<<grid, 128, 0, st>>>(S, P, ps, Q, n_in, n_out, n_shadow, seg_hist); break;
+    case 2: k_shade<2><<<grid, 128, 0, st>>>(S, P, ps, Q, n_in, n_out, n_shadow, seg_hist); break;
+    case 3: k_shade<3><<<grid, 128, 0, st>>>(S, P, ps, Q, n_in, n_out, n_shadow, seg_hist); break;
+    default: k_shade<-1><<<grid, 128, 0, st>>>(S, P, ps, Q, n_in, n_out, n_shadow, nullptr); break;
+    }
+}
 
 // Launch shape of the staged kernel: blocks of `staged_threads`, as many per SM as 1024 resident threads and the shared memory allow
 static size_t staged_smem_bytes(const ctl_ctx* c) { return (size_t)c->staged.tl_nodes * 64 + 16 + (size_t)(c->staged.stack_rows + 1) * c->staged_threads * 4; }
@@ -120,9 +131,9 @@ static void launch_staged(const ctl_ctx* c, cudaStream_t st, const float4* rays,
 // "TraversalKernel": 0 = persistent phase-scheduled kernel, 1 = simple ray-batch kernel (A/B baseline), 2 = persistent kernel with shared-memory staging
 template <int MODE, bool ANY_HIT, bool COUNT>
 static void launch_intersect(const ctl_ctx* c, int grid, cudaStream_t st, const DScene& S, const float4* rays, const unsigned* n_ptr, int n_fixed, unsigned* work_ctr,
-                             float4* hit_a, uint32_t* hit_node, const float4* sh_payload, float4* cl, void* api_out, unsigned long long* visit_out) {
+                             float4* hit_a, uint32_t* hit_node, const float4* sh_payload, float4* cl, void* api_out, unsigned long long* visit_out, unsigned* cls_hist = nullptr) {
     if (c->trav_kernel == 2 && c->staged_ok) {
-        const TravOut out = {hit_a, hit_node, sh_payload, cl, api_out, nullptr, 0, nullptr};
+        const TravOut out = {hit_a, hit_node, sh_payload, cl, api_out, nullptr, 0, nullptr, cls_hist};
         launch_staged<MODE, ANY_HIT, COUNT>(c, st, rays, n_ptr, nullptr, n_fixed, work_ctr, out, visit_out);
     }
     else if (c->trav_kernel == 1) k_intersect_simple<MODE, ANY_HIT, COUNT><<<grid, 128, 0, st>>>(S, rays, n_ptr, n_fixed, work_ctr, hit_a, hit_node, sh_payload, cl, api_out, visit_out);
@@ -416,6 +427,7 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "StopZeroThroughput") c->stop_zero = v != 0;   // 1 (default): a path whose throughput is exactly zero ends; 0: it is traced until Russian roulette ends it, the reference's ray count (Kernel/TraceHelper.cu:176)
     else if (k == "Regularization") { if (v != 0) return set_err("Regularization=true is not implemented (off by default in the reference)"); c->regularization = 0; }
     else if (k == "SortMode") c->sort_mode = v;
+    else if (k == "ShadeMode") { if (v < 0 || v > 1) return set_err("ShadeMode must be 0 (run-time BSDF dispatch) or 1 (one launch per material class)"); c->shade_mode = v; }
     else if (k == "StageTimers") c->stage_timers = v != 0;
     else if (k == "CaptureBounce") c->capture_bounce = v;
     else if (k == "DeviceSampleTables") c->device_tables = v != 0;
@@ -449,6 +461,7 @@ int ctl_get_param_i(ctl_ctx* c, const char* key, int* v) {
     else if (k == "StopZeroThroughput") *v = c->stop_zero; else if (k == "Regularization") *v = c->regularization; else if (k == "SortMode") *v = c->sort_mode; else if (k == "StageTimers") *v = c->stage_timers;
     else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables; else if (k == "FuseTraversal") *v = c->fuse_traversal; else if (k == "PixelVarianceBuffer") *v = c->variance_buffer; else if (k == "PassStride") *v = c->pass_stride; else if (k == "PassPhase") *v = c->pass_phase;
     else if (k == "TraversalBlocksPerSM") *v = c->trav_blocks_per_sm; else if (k == "StagedThreads") *v = c->staged_threads; else if (k == "StagedStackRows") *v = c->staged_rows;
+    else if (k == "ShadeMode") *v = c->shade_mode; else if (k == "MaterialClassMask") *v = (int)c->class_mask;
     else if (k == "StagedTreeletNodes") *v = c->staged.tl_nodes; else if (k == "StagedUsable") *v = c->staged_ok ? 1 : 0; else return set_err("unknown parameter key: " + k);
     return 0;
 }
@@ -458,7 +471,7 @@ static int upload_staging(ctl_ctx* c, const ctl_scene_view* v, bool with_tris) {
     ctlb::StagedHost H;
     if (with_tris) {
         ctlb::build_staging_tris(*v, H);
-        c->staged_ok = H.usable; c->staged_why = H.why;
+        c->staged_ok = H.usable; c->staged_why = H.why; c->class_mask = H.class_mask;
         if (H.usable) CK(c->d_tri64.upload((const float4*)H.tri64.data(), H.tri64.size() / 4));
     }
     if (!c->staged_ok) return 0;
@@ -467,6 +480,7 @@ static int upload_staging(ctl_ctx* c, const ctl_scene_view* v, bool with_tris) {
     CK(c->d_treelet.upload((const float4*)H.treelet.data(), H.treelet.size() / 4));
     c->staged.tri64 = c->d_tri64.p; c->staged.inst = c->d_inst.p; c->staged.treelet = c->d_treelet.p;
     c->staged.tl_nodes = H.tl_nodes; c->staged.scene_root = H.scene_root; c->staged.stack_rows = c->staged_rows;
+    c->class_ok = H.class_ok;
     return 0;
 }
 
@@ -668,7 +682,8 @@ static int ensure_state(ctl_ctx* c, size_t n) {
     CK(c->rays_a.ensure(2 * n)); CK(c->rays_b.ensure(2 * n)); CK(c->hit_a.ensure(n)); CK(c->hit_node.ensure(n));
     CK(c->sh_rays.ensure(2 * n)); CK(c->sh_payload.ensure(n)); CK(c->path_a.ensure(n)); CK(c->path_b.ensure(n));
     if (!c->stop_zero) CK(c->wo_prev.ensure(n));
-    if (c->sort_mode == 2) { CK(c->mat_cls.ensure(n)); CK(c->mat_order.ensure(n)); CK(c->mat_hist.ensure(2 * MAT_CLASSES * (MAX_BOUNCES + 1))); }
+    if (c->sort_mode == 2) CK(c->mat_cls.ensure(n));
+    if (c->sort_mode == 2 || c->shade_mode == 1) { CK(c->mat_order.ensure(n)); CK(c->mat_hist.ensure(2 * MAT_CLASSES * (MAX_BOUNCES + 1))); }
     if (c->sort_mode == 1) {
         CK(c->rays_c.ensure(2 * n)); CK(c->path_c.ensure(n)); CK(c->sort_keys.ensure(n));
         if (!c->sort_hist.p) { CK(c->sort_hist.ensure(SORT_BUCKETS)); CK(c->sort_offsets.ensure(SORT_BUCKETS)); CK(cudaMemsetAsync(c->sort_hist.p, 0, SORT_BUCKETS * sizeof(unsigned), c->stream)); }
@@ -709,7 +724,12 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
 
     c->stage_kind.clear();
     CK(cudaMemsetAsync(c->counters.p, 0, CTR_TOTAL * sizeof(unsigned), c->stream));
-    if (c->sort_mode == 2) CK(cudaMemsetAsync(c->mat_hist.p, 0, 2 * MAT_CLASSES * (MAX_BOUNCES + 1) * sizeof(unsigned), c->stream));
+    // per-class shade launches: the staged kernel tags every hit with its material class; one launch per class present (a sort pass only when there are several)
+    const bool by_class = c->shade_mode == 1 && c->sort_mode != 2 && c->trav_kernel == 2 && c->staged_ok && c->class_ok && c->class_mask != 0;
+    int n_classes = 0, single_cls = -1;
+    for (int k = 0; k < 4; k++) if (c->class_mask & (1u << k)) { n_classes++; single_cls = k; }
+    const bool class_sort = by_class && n_classes > 1;
+    if (c->sort_mode == 2 || class_sort) CK(cudaMemsetAsync(c->mat_hist.p, 0, 2 * MAT_CLASSES * (MAX_BOUNCES + 1) * sizeof(unsigned), c->stream));
     if (c->instrumented) CK(cudaMemsetAsync(c->stats.p + 2, 0, 8 * sizeof(unsigned long long), c->stream));
     unsigned* ctr = c->counters.p;
     PathState st = {c->cf.p, c->cl.p, c->nor.p, c->px.p, c->stop_zero ? nullptr : c->wo_prev.p};
@@ -731,14 +751,16 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
         }
         if (fuse && b > 0) { // shadow rays of bounce b-1 + extension rays of bounce b in one persistent launch
             if (c->trav_kernel == 2 && c->staged_ok) {
-                const TravOut out = {c->hit_a.p, c->hit_node.p, c->sh_payload.p, c->cl.p, nullptr, c->sh_rays.p, 0, nullptr};
+                const TravOut out = {c->hit_a.p, c->hit_node.p, c->sh_payload.p, c->cl.p, nullptr, c->sh_rays.p, 0, nullptr, class_sort ? c->mat_hist.p + 2 * MAT_CLASSES * b : nullptr};
                 launch_staged<4, false, false>(c, c->stream, rin, ctr + CTR_Q + b, ctr + CTR_SH + b - 1, 0, ctr + CTR_WORK + 2 * b, out, nullptr);
             } else
             k_intersect_fused<<<g_trav, 128, 0, c->stream>>>(c->scene, c->tune_p, rin, ctr + CTR_Q + b, c->sh_rays.p, ctr + CTR_SH + b - 1, ctr + CTR_WORK + 2 * b,
                                                               c->hit_a.p, c->hit_node.p, c->sh_payload.p, c->cl.p);
         }
-        else if (c->instrumented) launch_intersect<0, false, true>(c, g_trav, c->stream, c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, c->stats.p + 2);
-        else launch_intersect<0, false, false>(c, g_trav, c->stream, c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, nullptr);
+        else if (c->instrumented) launch_intersect<0, false, true>(c, g_trav, c->stream, c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, c->stats.p + 2,
+                                                                   class_sort ? c->mat_hist.p + 2 * MAT_CLASSES * b : nullptr);
+        else launch_intersect<0, false, false>(c, g_trav, c->stream, c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, nullptr,
+                                               class_sort ? c->mat_hist.p + 2 * MAT_CLASSES * b : nullptr);
         stage_mark(c, 2);
         const bool sort_next = c->sort_mode == 1 && b + 1 < c->max_path_length;
         const uint32_t* order = nullptr;
@@ -748,8 +770,18 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
             k_matsort_scatter<<<g_light, 256, 0, c->stream>>>(ctr + CTR_Q + b, c->mat_cls.p, hist, hist + MAT_CLASSES, c->mat_order.p);
             order = c->mat_order.p; launches += 2;
         }
+        if (class_sort) { // group the hit records by the class bits the traversal kernel left in them
+            unsigned* hist = c->mat_hist.p + 2 * MAT_CLASSES * b;
+            k_class_scatter<<<g_light, 256, 0, c->stream>>>(ctr + CTR_Q + b, c->hit_a.p, hist, hist + MAT_CLASSES, c->mat_order.p);
+            order = c->mat_order.p; launches++;
+        }
         Queues Q = {rin, pin, rout, pout, c->hit_a.p, c->hit_node.p, c->sh_rays.p, c->sh_payload.p, sort_next ? c->sort_keys.p : nullptr, sort_next ? c->sort_hist.p : nullptr, order};
-        k_shade<<<g_light, 128, 0, c->stream>>>(c->scene, P, st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b);
+        if (class_sort) {
+            const unsigned* hist = c->mat_hist.p + 2 * MAT_CLASSES * b;
+            for (int k = 0; k < 4; k++) if (c->class_mask & (1u << k)) { launch_shade(k, g_light, c->stream, c->scene, P, st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b, hist); launches++; }
+            launches--;
+        }
+        else launch_shade(by_class ? single_cls : -1, g_light, c->stream, c->scene, P, st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b, nullptr);
         if (sort_next) { // counting sort of the next bounce's extension queue by (octant, origin cell)
             stage_mark(c, 4);
             k_sort_scan<<<1, 1024, 0, c->stream>>>(c->sort_hist.p, c->sort_offsets.p);

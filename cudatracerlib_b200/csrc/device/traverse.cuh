@@ -48,6 +48,8 @@ CTL_DEV float guard_inv(float d) { // BVHTraversal.h:16-19
 }
 
 constexpr int SENT = CTL_SENTINEL;
+constexpr int TRI_CLS_SHIFT = 29;                 // wavefront hit records written by the staged kernel carry the hit triangle's material class in the top 3 bits of the triangle word (7 = miss)
+constexpr uint32_t TRI_IDX_MASK = 0x1fffffffu;
 constexpr int STACK_N = 64;
 
 template <bool COUNT> struct VisitCounters { };

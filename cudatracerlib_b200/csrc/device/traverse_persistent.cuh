@@ -29,6 +29,7 @@ struct TravOut { // where results go (MODE-dependent, see k_intersect)
     // MODE 5 (fused API launch, WavefrontPathTracer): items [0, n_ext) are closest-hit queries from `rays` -> api_out, items [n_ext, n) are
     // any-hit queries from `sh_rays` -> api_out2; both with intersectKernel semantics (MODE 2: tmin / tmax from the ray, 16-byte results)
     void* api_out2;
+    unsigned* cls_hist;   // staged kernel, MODE 0 / 4: 8 counters of this bounce's hit records by material class (null = not wanted)
 };
 
 struct TravTune { int th_t, th_l, th_f, th_n_exit, t_steps; }; // lane thresholds of the T / L / F blocks; th_n_exit = node steps per iteration; t_steps = triangle tests per iteration (staged kernel)

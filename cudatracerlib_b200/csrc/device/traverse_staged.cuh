@@ -22,7 +22,7 @@
 namespace ctld {
 
 struct StagedScene {
-    const float4* tri64;     // 4 x float4 per leaf slot: Woop rows a, b, c, (leaf word bits, 0, 0, 0)
+    const float4* tri64;     // 4 x float4 per leaf slot: Woop rows a, b, c, (leaf word bits, material class, 0, 0)
     const float4* inst;      // 4 x float4 per (pseudo-)node: inverse transform rows 0..2, (bvh node base [float4 units], tri64 slot base, TriangleData base, root word)
     const float4* treelet;   // shared-memory image of the treelet: tl_nodes x 64 bytes, 16-byte chunks swizzled (see tl_chunk)
     int tl_nodes;            // 0 = no treelet
@@ -107,10 +107,19 @@ __device__ __forceinline__ void trace_staged(const DScene& S, const StagedScene&
 
         // ---- F: write finished results, fetch new rays
         if (runF) {
+            if ((MODE == 0 || MODE == 4) && out.cls_hist) { // class histogram of this bounce's hit records (the shade stage runs one launch per material class)
+                const bool wr = state == 3 && ray_i >= 0 && !(MODE == 4 && lane_any);
+                const unsigned mw = __ballot_sync(0xffffffffu, wr);
+                if (wr) {
+                    const unsigned cls = hit.tri >> TRI_CLS_SHIFT; // 7 = miss
+                    const unsigned peers = __match_any_sync(mw, cls);
+                    if (lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(out.cls_hist + cls, (unsigned)__popc(peers));
+                }
+            }
             if (state == 3 && ray_i >= 0) {
                 const int i = ray_i;
                 if (MODE == 0 || (MODE == 4 && !lane_any)) {
-                    out.hit_a[i] = make_float4(hit.dist, hit.u, hit.v, __uint_as_float(hit.tri));
+                    out.hit_a[i] = make_float4(hit.dist, hit.u, hit.v, __uint_as_float(hit.tri)); // tri word keeps the class bits: k_shade strips them
                     out.hit_node[i] = hit.node;
                 } else if (MODE == 1 || MODE == 4) {
                     if (hit.tri == 0xffffffffu) {
@@ -123,14 +132,14 @@ __device__ __forceinline__ void trace_staged(const DScene& S, const StagedScene&
                 } else if (MODE == 2 || MODE == 5) {
                     uint4 res = make_uint4(__float_as_uint(hit.dist), 0xffffffffu, 0xffffffffu, 0u);
                     if (hit.tri != 0xffffffffu) {
-                        res.y = hit.node; res.z = hit.tri;
+                        res.y = hit.node; res.z = hit.tri & TRI_IDX_MASK;
                         const unsigned short xd = (unsigned short)(hit.u * 65535), yd = (unsigned short)(hit.v * 65535); // TraceHelper.cu:726-727
                         res.w = ((uint32_t)yd << 16) | (uint32_t)xd;
                     }
                     ((uint4*)((MODE == 5 && lane_any) ? out.api_out2 : out.api_out))[i] = res;
                 } else {
                     float* o5 = (float*)out.api_out + (size_t)i * 5;
-                    o5[0] = hit.dist; o5[1] = hit.u; o5[2] = hit.v; o5[3] = __uint_as_float(hit.tri); o5[4] = __uint_as_float(hit.node);
+                    o5[0] = hit.dist; o5[1] = hit.u; o5[2] = hit.v; o5[3] = __uint_as_float(hit.tri == 0xffffffffu ? hit.tri : (hit.tri & TRI_IDX_MASK)); o5[4] = __uint_as_float(hit.node);
                 }
                 ray_i = -1;
             }
@@ -259,7 +268,7 @@ __device__ __forceinline__ void trace_staged(const DScene& S, const StagedScene&
                     float t, u, v;
                     more = true;
                     if (woop_test(tA.lo, tA.hi, tB.lo, mk(ox, oy, oz), mk(dx, dy, dz), tri_lo, hit.dist, t, u, v)) {
-                        hit.node = (uint32_t)inst; hit.tri = (index >> 1) + tri_base; hit.u = u; hit.v = v; hit.dist = t;
+                        hit.node = (uint32_t)inst; hit.tri = ((index >> 1) + tri_base) | (__float_as_uint(tB.hi.y) << TRI_CLS_SHIFT); hit.u = u; hit.v = v; hit.dist = t; // + the material class of the slot (staging.cpp)
                         if ((MODE == 4 || MODE == 5) ? lane_any : ANY_HIT) { more = false; nodeAddr = SENT; inst = -1; } // first hit terminates the ray (TraceHelper.cu:675-679)
                     }
                     if (more) {

@@ -7,6 +7,7 @@
 //   treelet : the inner nodes with the largest world-space boxes -- the top of the scene-level tree and of the mesh trees -- as a
 //             shared-memory image; children inside the image are re-addressed (slot * 4 | 1), children that leave it keep their address.
 #include "staging.h"
+#include <algorithm>
 #include <queue>
 #include <unordered_map>
 #include <cstring>
@@ -60,6 +61,27 @@ void build_staging_tris(const ctl_scene_view& v, StagedHost& out) {
         float* d = out.tri64.data() + (size_t)s * 16;
         memcpy(d, &v.woop[s], 48);
         d[12] = bitsf(v.tri_index[s]); d[13] = d[14] = d[15] = 0.0f;
+    }
+    // material class of every leaf slot (for the per-class shade launches): slot -> owning mesh (largest leaf-word offset <= slot) -> triangle -> material
+    out.class_mask = 0;
+    std::vector<std::pair<uint32_t, uint32_t>> owners; // (leaf-word offset, mesh); re-braided views hold many mesh records over one range, all with the same material block
+    for (uint32_t m = 0; m < v.n_meshes; m++) owners.emplace_back(v.meshes[m].bvh_idx_offset, m);
+    std::sort(owners.begin(), owners.end());
+    size_t oi = 0;
+    for (uint32_t s = 0; s < v.n_woop && !owners.empty(); s++) {
+        while (oi + 1 < owners.size() && owners[oi + 1].first <= s) oi++;
+        const ctl_mesh& M = v.meshes[owners[oi].second];
+        const uint64_t tri = (uint64_t)(v.tri_index[s] >> 1) + M.tri_offset;
+        uint32_t cls = 0;
+        if (tri < v.n_tri_data) {
+            const uint64_t mi = (uint64_t)((v.tri_data[tri].w[1] >> 16) & 0xffu) + M.mat_offset;
+            if (mi < v.n_materials) {
+                const ctl_material& mat = v.materials[mi];
+                cls = mat.bsdf_type == CTL_BSDF_ROUGHCONDUCTOR ? 1u + (mat.distr_type & 1u) : (mat.bsdf_type == CTL_BSDF_DIELECTRIC ? 3u : 0u);
+            }
+        }
+        out.class_mask |= 1u << cls;
+        out.tri64[(size_t)s * 16 + 13] = bitsf(cls);
     }
     out.usable = true;
 }
@@ -129,6 +151,8 @@ void build_staging_nodes(const ctl_scene_view& v, int treelet_budget, StagedHost
     }
     if (v.scene_start_node >= 0) { auto f = slot_of.find(key_of(-1, (uint32_t)v.scene_start_node / 4)); if (f != slot_of.end()) out.scene_root = f->second * 4 + 1; }
     // ---- instance records
+    out.class_ok = true;
+    for (uint32_t i = 0; i < v.n_nodes; i++) if (v.nodes[i].mesh_index < v.n_meshes && v.nodes[i].material_offset != v.meshes[v.nodes[i].mesh_index].mat_offset) out.class_ok = false;
     for (uint32_t i = 0; i < v.n_nodes; i++) {
         float* d = out.inst.data() + (size_t)i * 16;
         const float* inv = v.node_inv_xf + (size_t)i * 16;

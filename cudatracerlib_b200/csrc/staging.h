@@ -13,6 +13,8 @@ struct StagedHost {
     std::vector<float> treelet;  // 16 floats per treelet node: the shared-memory image (swizzled chunks)
     int tl_nodes = 0;
     int scene_root = 0;          // node address the scene-level walk starts at
+    uint32_t class_mask = 0;     // material classes present among the leaf slots (bit c = class c: 0 diffuse, 1 conductor / Beckmann, 2 conductor / GGX, 3 dielectric)
+    bool class_ok = false;       // the per-slot classes hold for every instance (no node overrides its mesh's material block)
     bool usable = false;         // false: the view's leaf arrays do not have the one-slot-one-Woop-record shape (why says so); the persistent kernel is used
     std::string why;
 };

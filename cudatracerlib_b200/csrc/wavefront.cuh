@@ -293,8 +293,9 @@ __global__ void __launch_bounds__(128, 8) k_intersect_fused_api(const __grid_con
 // histogram -> 8-entry scan (done by every block of the scatter) -> index scatter; only 4-byte indices move.
 constexpr int MAT_CLASSES = 8;
 CTL_DEV unsigned material_class(const DScene& S, float4 ha, uint32_t node) {
-    const uint32_t tri = __float_as_uint(ha.w);
-    if (tri == 0xffffffffu) return MAT_CLASSES - 1;
+    const uint32_t tri_word = __float_as_uint(ha.w);
+    if (tri_word == 0xffffffffu) return MAT_CLASSES - 1;
+    const uint32_t tri = tri_word & TRI_IDX_MASK;
     const uint32_t w1 = __ldg(&S.tri_data[(size_t)tri * 2].y);
     const ctl_material* m = S.materials + ((w1 >> 16) & 0xff) + __ldg(&S.nodes[node].material_offset);
     const uint32_t bt = __ldg(&m->bsdf_type);
@@ -333,15 +334,44 @@ __global__ void __launch_bounds__(256) k_matsort_scatter(const unsigned* __restr
     }
 }
 
+// Class-grouped order of a bounce's hit records for the per-class shade launches (ShadeMode 1).  The staged traversal kernel has already put the
+// material class of every hit into the top bits of its triangle word and counted the classes (TravOut::cls_hist), so this pass only reads the
+// 16-byte hit records and writes 4-byte indices; misses (class 7) need no shading and get no slot.
+__global__ void __launch_bounds__(256) k_class_scatter(const unsigned* __restrict__ n_ptr, const float4* __restrict__ hit_a, const unsigned* __restrict__ hist, unsigned* __restrict__ cursor /* MAT_CLASSES, zeroed */,
+                                                        uint32_t* __restrict__ order) {
+    const int n = (int)*n_ptr;
+    unsigned start[MAT_CLASSES]; unsigned run = 0;
+    for (int b = 0; b < MAT_CLASSES; b++) { start[b] = run; run += hist[b]; }
+    const int n_round = (n + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const unsigned c = i < n ? (__float_as_uint(__ldg(hit_a + i).w) >> TRI_CLS_SHIFT) : MAT_CLASSES;
+        const unsigned peers = __match_any_sync(0xffffffffu, c);
+        if (c < MAT_CLASSES - 1) {
+            const int leader = __ffs(peers) - 1;
+            unsigned base = 0;
+            if ((int)lane_id() == leader) base = atomicAdd(cursor + c, (unsigned)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            order[start[c] + base + __popc(peers & ((1u << lane_id()) - 1u))] = (uint32_t)i;
+        }
+    }
+}
+
 // ---- shade: one path vertex (PathTracer.cu:58-96) ----------------------------------
 struct ShadeParams { int max_path_length, rr_start, direct, stop_zero; };
 
 #ifndef CTL_SHADE_MIN_BLOCKS
 #define CTL_SHADE_MIN_BLOCKS 8 // 64 registers: 8 resident blocks per SM; measured -18% (diffuse) / -27% (microfacet) shade time vs 116 registers
 #endif
+// CLS = -1: any material (the reference's run-time BSDF dispatch, Base/VirtualFuncType.h:90-111).  CLS = 0..3: every work item of the launch is known to
+// hit that material class (0 diffuse, 1 rough conductor / Beckmann, 2 rough conductor / GGX, 3 dielectric), so one BSDF body is compiled in and a warp
+// never waits for another class's code (the Beckmann visible-normal Newton loop in particular).  With `seg_hist` the launch covers only its class's
+// segment of Q.order (k_class_scatter); without it the whole queue (single-class scenes).  Same per-path arithmetic either way.
+CTL_DEV constexpr uint32_t cls_bsdf_type(int cls) { return cls == 0 ? CTL_BSDF_DIFFUSE : (cls == 3 ? CTL_BSDF_DIELECTRIC : CTL_BSDF_ROUGHCONDUCTOR); }
+template <int CLS>
 __global__ void __launch_bounds__(128, CTL_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene S, const __grid_constant__ ShadeParams P, PathState st, Queues Q,
-                                                const unsigned* __restrict__ n_in, unsigned* n_out, unsigned* n_shadow) {
-    const int n = (int)*n_in;
+                                                const unsigned* __restrict__ n_in, unsigned* n_out, unsigned* n_shadow, const unsigned* __restrict__ seg_hist) {
+    int n = (int)*n_in, seg_start = 0;
+    if (CLS >= 0 && seg_hist) { for (int b = 0; b < CLS; b++) seg_start += (int)seg_hist[b]; n = (int)seg_hist[CLS]; }
     const int n_round = (n + 31) & ~31;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         bool alive = false, shadow = false;
@@ -351,11 +381,12 @@ __global__ void __launch_bounds__(128, CTL_SHADE_MIN_BLOCKS) k_shade(const __gri
         Spec pending = sp(0.0f);
         if (i < n) {
             const int i_unsorted = i;
-            const int i = Q.order ? (int)__ldg(Q.order + i_unsorted) : i_unsorted; // material-sorted shading: same work items, grouped
+            const int i = Q.order ? (int)__ldg(Q.order + seg_start + i_unsorted) : i_unsorted; // material-sorted shading: same work items, grouped
             p = Q.path_in[i];
             const float4 ha = Q.hit_a[i];
-            const uint32_t tri = __float_as_uint(ha.w);
-            if (tri != 0xffffffffu) {
+            const uint32_t tri_word = __float_as_uint(ha.w);
+            const uint32_t tri = tri_word & TRI_IDX_MASK;   // the staged traversal kernel leaves the material class in the top bits
+            if (tri_word != 0xffffffffu) {
                 const uint32_t node = Q.hit_node[i];
                 const float4 r0 = Q.rays_in[2 * i], r1 = Q.rays_in[2 * i + 1];
                 const V3 ro = mk(r0.x, r0.y, r0.z), rd = mk(r1.x, r1.y, r1.z);
@@ -374,7 +405,8 @@ __global__ void __launch_bounds__(128, CTL_SHADE_MIN_BLOCKS) k_shade(const __gri
                 dg.P = ro + rd * ha.x;
                 fill_dg(S, ha.y, ha.z, tri, node, dg, mat_local);
                 const ctl_node* N = S.nodes + node;
-                const ctl_material mat = S.materials[mat_local + __ldg(&N->material_offset)];
+                ctl_material mat = S.materials[mat_local + __ldg(&N->material_offset)];
+                if (CLS >= 0) { mat.bsdf_type = cls_bsdf_type(CLS); if (CLS == 1) mat.distr_type = CTL_DISTR_BECKMANN; if (CLS == 2) mat.distr_type = CTL_DISTR_GGX; } // known at compile time: the other bodies fold away
                 BRec bRec; bRec.eta = 1.0f; bRec.sampledType = 0; bRec.typeMask = E_ALL; bRec.wo = mk(0, 0, 1);
                 if (st.wo && depth > 1) { const float4 w4 = st.wo[p]; bRec.wo = mk(w4.x, w4.y, w4.z); }
                 bRec.wi = to_local(dg.sys, -rd);

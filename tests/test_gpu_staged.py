@@ -105,3 +105,33 @@ def test_staged_after_node_transform_update(built_lib, orc):
     g = t.trace_rays(rays); o = orc.trace_rays(s.view, rays)
     assert g.tobytes() == o.tobytes()
     t.close()
+
+
+@pytest.mark.parametrize("kind,w,h,depth", [("cornell", 96, 96, 8), ("soup", 128, 128, 8), ("c3", 160, 90, 8), ("c5", 64, 36, 12)])
+def test_per_class_shade_launches_equal_the_run_time_dispatch(built_lib, kind, w, h, depth):
+    """ShadeMode 1 (default): one k_shade launch per material class present, each with a single BSDF body compiled in, over the class bits the staged
+    kernel leaves in the hit records (single-class scenes: no sort pass).  Per-path arithmetic is unchanged, so images, ray counts and queue sizes
+    equal ShadeMode 0 (the reference's run-time dispatch, Base/VirtualFuncType.h:90-111) exactly."""
+    s, t = make(kind, w, h, depth)
+    mask = t.getParameter("MaterialClassMask")
+    assert mask != 0 and (bin(mask).count("1") > 1) == (kind != "cornell")
+    t.setParameter("ShadeMode", 0)
+    t.DoPass(True); t.synchronize()
+    ref = t.readAccumulator(); ref_rays = t.getRaysInLastPass(); ref_q = t.queueSizes(depth)
+    t.setParameter("ShadeMode", 1)
+    for fuse in (1, 0):
+        t.setParameter("FuseTraversal", fuse)
+        t.DoPass(True); t.synchronize()
+        img = t.readAccumulator()
+        assert np.array_equal(img["weight_sum"], ref["weight_sum"])
+        assert np.allclose(img["rgb"], ref["rgb"], rtol=1e-6, atol=0), fuse   # identical paths; only the order of the float atomics into a pixel may differ
+        assert t.getRaysInLastPass() == ref_rays
+        q = t.queueSizes(depth)
+        assert np.array_equal(q[0], ref_q[0]) and np.array_equal(q[1], ref_q[1])
+    # several passes fused into one wavefront (what bench.py runs)
+    t.setParameter("FuseTraversal", 1)
+    t.DoPasses(4, new_trace=True); t.synchronize(); a = t.readAccumulator(); ra = t.getRaysInLastPass()
+    t.setParameter("ShadeMode", 0)
+    t.DoPasses(4, new_trace=True); t.synchronize(); b = t.readAccumulator()
+    assert ra == t.getRaysInLastPass() and np.array_equal(a["weight_sum"], b["weight_sum"]) and np.allclose(a["rgb"], b["rgb"], rtol=1e-5, atol=1e-7)
+    t.close()
