@@ -22,7 +22,9 @@ def test_reference_arm_line(orc):
     assert d["e2e"] == {"value": d["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     c = d["cpu_baseline"]
     assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] == d["value"] and "crop" in c["sample"]
-    assert "100K" in d["config"]["workload"] and d["config"]["width"] == 1920 and d["config"]["height"] == 1080 and d["config"]["max_path_length"] == 8
+    assert "1M-triangle" in d["config"]["workload"] and "configs[3]" in d["config"]["workload"] and d["config"]["triangles"] == 999854   # the default workload is the north star's 1 M-triangle scene
+    assert set(d["config"]) == {"workload", "width", "height", "spp", "max_path_length", "rr_start_depth", "direct", "triangles", "partition", "l2"}   # the dict both arms print identically
+    assert d["config"]["width"] == 1920 and d["config"]["height"] == 1080 and d["config"]["max_path_length"] == 8
 
 
 def test_product_arm_has_no_cpu_fallback():
