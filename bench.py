@@ -247,7 +247,7 @@ def scene_on_reference_tree(scene, w, h):
 
 def measure_workload(name, args, torch, dist, world, rank, local, dev, stream, steps, warmup, primary):
     """One workload on this rank's share of the image.  Returns (line fields of rank 0, scene)."""
-    from cudatracerlib_b200 import Scene, PathTracer, DistributedFrame, traversal_bytes, TILE
+    from cudatracerlib_b200 import Scene, PathTracer, traversal_bytes, TILE
     kind, w, h, spp, depth, desc = WORKLOADS[name]
     tile = args.tile if args.tile > 0 else TILE
     scene = Scene(kind, w, h)
@@ -274,10 +274,15 @@ def measure_workload(name, args, torch, dist, world, rank, local, dev, stream, s
         # `batch` progressive passes fused into one wavefront (ctl_render_passes_tiled) on this rank's tiles
         tracer.DoPasses(batch, new_trace=new_trace, tile=(tile, tile), part=rank, n_parts=world)
 
-    df = DistributedFrame(accum, render_pass, lambda: 0)
+    if world > 1:
+        # the communicator lives behind the C ABI (csrc/ctl_comm.cu: NCCL loaded at run time); torch.distributed only carries the 128-byte id to the ranks
+        box = [PathTracer.commUniqueId() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        tracer.commInitRank(box[0], rank, world)
 
     def frame(read_back):
-        df.frame(spp // batch)  # spp passes on this rank's tiles + (N > 1) the one NCCL reduce of the accumulator, all on `stream`
+        # spp passes on this rank's tiles + (N > 1) the one NCCL reduce of the accumulator to rank 0, all on `stream`: ctl_comm_render_frame
+        tracer.commRenderFrame(spp, batch, tile, 0)
         if read_back and rank == 0:
             # what an application reads per frame: the image after the (default) image pipeline, as in the reference's
             # applyImagePipeline -> RGBCOL (Kernel/ImagePipeline/ImagePipeline.cu:54-63); PixelData stays on the device

@@ -166,6 +166,9 @@ def lib():
     L.ctl_get_visit_counts.argtypes = [vp, u64p, u64p]
     L.ctl_get_queue_sizes.argtypes = [vp, vp, vp, i32]
     L.ctl_get_captured_rays.argtypes = [vp, vp, i32]
+    L.ctl_comm_get_unique_id.argtypes = [vp]; L.ctl_comm_init_rank.argtypes = [vp, vp, i32, i32]; L.ctl_comm_init_all.argtypes = [vp, i32]
+    L.ctl_comm_rank.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]; L.ctl_comm_reduce_accum.argtypes = [vp, i32]; L.ctl_comm_reduce_accum_all.argtypes = [vp, i32, i32]
+    L.ctl_comm_allreduce_u64.argtypes = [vp, vp, i32]; L.ctl_comm_render_frame.argtypes = [vp, i32, i32, i32, i32]; L.ctl_comm_destroy.argtypes = [vp]
     _lib = L
     return L
 
@@ -464,6 +467,34 @@ class PathTracer:
         if n < 0:
             raise RuntimeError(lib().ctl_last_error().decode())
         return out[:n]
+
+    # -- multi-GPU (csrc/ctl_comm.cu): NCCL behind the C ABI
+    @staticmethod
+    def commUniqueId():
+        """ctl_comm_get_unique_id: 128 bytes for rank 0 to hand to the other ranks."""
+        buf = C.create_string_buffer(128); _check(lib().ctl_comm_get_unique_id(buf)); return buf.raw
+
+    def commInitRank(self, unique_id, rank, n_ranks):
+        _check(lib().ctl_comm_init_rank(self._ctx, C.c_char_p(unique_id), rank, n_ranks))
+
+    @staticmethod
+    def commInitAll(tracers):
+        """One process driving several GPUs: tracers[i] becomes rank i."""
+        arr = (C.c_void_p * len(tracers))(*[t._ctx for t in tracers]); _check(lib().ctl_comm_init_all(arr, len(tracers)))
+
+    def commReduceAccum(self, root=0):
+        _check(lib().ctl_comm_reduce_accum(self._ctx, root))
+
+    @staticmethod
+    def commReduceAccumAll(tracers, root=0):
+        arr = (C.c_void_p * len(tracers))(*[t._ctx for t in tracers]); _check(lib().ctl_comm_reduce_accum_all(arr, len(tracers), root))
+
+    def commRenderFrame(self, spp, batch=8, tile=64, root=0):
+        """ctl_comm_render_frame: this rank's tiles of a frame + the reduce to `root` (asynchronous)."""
+        _check(lib().ctl_comm_render_frame(self._ctx, spp, batch, tile, root))
+
+    def commAllReduce(self, values):
+        a = np.ascontiguousarray(values, np.uint64); _check(lib().ctl_comm_allreduce_u64(self._ctx, _ptr(a), len(a))); return a
 
     def close(self):
         if self._ctx and _lib is not None:

@@ -15,9 +15,11 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # no implicit FMA contraction: the only fused ops are the explicit fmaf() calls (see device/dmath.cuh)
     "-fmad=false",
-    "-shared", "-Xcompiler", "-fPIC,-O2,-ffp-contract=off",
+    "-shared", "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-pthread",
 ]
-SOURCES = ["ctl_api.cu", "scene_builder.cpp", "sbvh_builder.cpp", "xmsh.cpp", "obj_import.cpp", "validate.cpp", "staging.cpp"]
+SOURCES = ["ctl_api.cu", "ctl_pipeline.cu", "ctl_bvh_gpu.cu", "ctl_comm.cu", "ctl_scene_api.cpp", "scene_builder.cpp", "sbvh_builder.cpp", "xmsh.cpp", "obj_import.cpp", "validate.cpp",
+           "staging.cpp"]
+OBJ_DIR = os.path.join(HERE, "..", "build", "obj")
 
 
 def _sources():
@@ -37,17 +39,34 @@ def needs_build():
     return any(os.path.getmtime(s) > t for s in _sources())
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """Compile every translation unit (in parallel) and link the shared library.  extra_flags / out: A/B build variants (build_variants/)."""
+    out = out or LIB
+    if not force and out == LIB and not needs_build():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    obj_dir = OBJ_DIR if out == LIB else OBJ_DIR + "_" + os.path.basename(out)
+    os.makedirs(obj_dir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
+
+    def one(src):
+        obj = os.path.join(obj_dir, src + ".o")
+        r = subprocess.run([nvcc] + compile_flags + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        return src, obj, r
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(one, SOURCES))
+    log = ""
+    for src, obj, r in results:
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed on " + src + ":\n" + r.stdout + r.stderr)
+        log += r.stderr
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + [o for _, o, _ in results] + ["-ldl", "-o", out], capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     if verbose:
-        print(r.stderr)
-    return LIB
+        print(log)
+    return out
 
 
 if __name__ == "__main__":

@@ -1,103 +1,12 @@
-// ctl_api.cu -- C ABI (include/ctl_b200.h) over the sm_100a kernels.
+// ctl_api.cu -- C ABI (include/ctl_b200.h) over the sm_100a kernels: context, scene upload, traversal queries, the two integrators' host loops.
 //
 // Host orchestration replaces Tracer<true>::DoPass / UpdateKernel / __internal__IntersectBuffers
 // (Kernel/Tracer.h:209-289, Kernel/TraceHelper.cu:182-217, 736-746): one context per device, one
 // stream, no globals, no per-launch cudaDeviceSynchronize, queue sizes stay on the device.
-#include <cuda_runtime.h>
-#include <string>
-#include <vector>
-#include <cstring>
-#include <cstdio>
-#include <cmath>
-#include <stdexcept>
-#include <memory>
-#include "../../include/ctl_b200.h"
-#include "scene_builder.h"
-#include "sampler_tables.h"
-#include "staging.h"
+// (Scenes: ctl_scene_api.cpp; image pipeline: ctl_pipeline.cu; GPU BVH build: ctl_bvh_gpu.cu; NCCL: ctl_comm.cu.)
+#include "ctl_internal.h"
 #include "wavefront.cuh"
-#include "device/traverse_staged.cuh"
 #include "wavefront_pt.cuh"
-#include "image_pipeline.cuh"
-#include "nlm_filter.cuh"
-#include "bvh_build.cuh"
-
-using namespace ctld;
-
-static thread_local std::string g_err;
-static int set_err(const std::string& s) { g_err = s; return 1; }
-#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { char b_[512]; snprintf(b_, sizeof(b_), "In file %s at line %d : %s", __FILE__, __LINE__, cudaGetErrorString(e_)); return set_err(b_); } } while (0)
-#define CKP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { char b_[512]; snprintf(b_, sizeof(b_), "In file %s at line %d : %s", __FILE__, __LINE__, cudaGetErrorString(e_)); set_err(b_); return nullptr; } } while (0)
-
-struct ctl_scene { ctlb::SceneStorage S; };
-
-namespace {
-const int MAX_BOUNCES = 256;
-const unsigned API_WORK_RING = 256;
-enum { CTR_Q = 0, CTR_SH = MAX_BOUNCES + 1, CTR_WORK = 2 * (MAX_BOUNCES + 1), CTR_TOTAL = 4 * (MAX_BOUNCES + 1) };
-
-template <typename T> struct DevBuf {
-    T* p = nullptr; size_t n = 0;
-    cudaError_t ensure(size_t count) {
-        if (count <= n) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; n = 0;
-        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
-        if (e == cudaSuccess) n = count;
-        return e;
-    }
-    cudaError_t upload(const T* h, size_t count) {
-        cudaError_t e = ensure(count ? count : 1);
-        if (e != cudaSuccess || !count) return e;
-        return cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice);
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
-};
-} // namespace
-
-struct ctl_ctx {
-    int device = 0, w = 0, h = 0;
-    int n_sm = 148;
-    cudaStream_t stream = nullptr, own_stream = nullptr;
-    // parameters (Integrators/PathTracer.h:10-20)
-    int max_path_length = 50, rr_start = 5, direct = 1, regularization = 0, sort_mode = 0, stage_timers = 0, capture_bounce = 0, trav_kernel = 2, trav_blocks_per_sm = 8, shade_blocks_per_sm = 8, smem_carveout = -1, fuse_traversal = 1, warp_blocks = 0, pass_stride = 1, pass_phase = 0, stop_zero = 1;
-    // scene
-    DevBuf<ctl_bvh_node> d_scene_nodes, d_bvh_nodes; DevBuf<ctl_woop_tri> d_woop; DevBuf<uint32_t> d_tri_index; DevBuf<ctl_tri_data> d_tri_data;
-    DevBuf<ctl_mesh> d_meshes; DevBuf<ctl_node> d_nodes; DevBuf<float> d_xf, d_inv_xf; DevBuf<ctl_material> d_materials; DevBuf<ctl_light> d_lights;
-    DevBuf<ctl_light_tri> d_light_tris; DevBuf<float> d_light_cdf, d_normal_lut;
-    DScene scene; bool has_scene = false;
-    // sampler tables: `tab_cap` consecutive table sets (one per pass of a batch) on the device; generated there
-    // (k_gen_tables) or -- "DeviceSampleTables"=0, the reference's UpdateKernel behaviour -- on the host and copied H2D
-    int tab_cap = 0; DevBuf<float> d_tab1, d_tab2;
-    float* h_tab1 = nullptr; float* h_tab2 = nullptr; int h_tab_cap = 0; cudaEvent_t h_tab_free = nullptr;
-    DevBuf<uint32_t> d_states, d_states0, d_jump;
-    bool user_tables = false; int device_tables = 1;
-    uint32_t gen_pos_host = 0, gen_pos_dev = 0;   // index of the next pass each generator would produce
-    ctlb::SamplerTableGenerator gen;
-    // wavefront state
-    DevBuf<float4> wo_prev; DevBuf<float4> cf, cl, nor, px, rays_a, rays_b, hit_a, sh_rays, sh_payload, capture;
-    DevBuf<uint32_t> path_a, path_b, path_c, hit_node, sort_keys; DevBuf<float4> rays_c; DevBuf<unsigned> sort_hist, sort_offsets, mat_hist; DevBuf<unsigned char> mat_cls; DevBuf<uint32_t> mat_order;
-    DevBuf<unsigned> counters;
-    DevBuf<unsigned> api_work; unsigned api_seq = 0;   // ring of work counters of the API traversal launches: calls in flight on different streams never share one
-    // WavefrontPathTracer queue (DoubleRayBuffer<WavefrontPTRayData>)
-    DevBuf<float4> w_thr, w_lxy, w_df, w_ray, w_sec[2]; DevBuf<uint2> w_misc; DevBuf<uint4> w_res, w_sres[2]; DevBuf<unsigned long long> w_desc;
-    DevBuf<unsigned long long> stats; // [0] rays_last [1] rays_total [2..4] ext visits [5] ext rays [6..8] shadow visits [9] shadow rays
-    DevBuf<float> own_accum; float* accum = nullptr; DevBuf<uchar4> resolve_tmp, pipe_rgbe; DevBuf<float4> pipe_partial; DevBuf<float> pipe_lum;
-    DevBuf<ctl_pixel_variance_info> d_var; int variance_buffer = 0;
-    DevBuf<uint32_t> d_node_alias; uint32_t n_alias = 0;   // re-braided scene: instance of every (pseudo-)node, for the node indices the API reports
-    DevBuf<uchar4> nlm_cached; DevBuf<float> nlm_varh, nlm_weights; long long nlm_last_update = -1; size_t nlm_pixels = 0;   // NonLocalMeansFilter state (m_cachedImg, m_weightBuffer, last_iter_weight_update)
-    unsigned captured_n = 0; DevBuf<unsigned> d_captured_n;
-    uint32_t passes_done = 0;
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr; bool events_recorded = false;
-    std::vector<cudaEvent_t> stage_ev; std::vector<int> stage_kind;
-    float stage_ms[5] = {0, 0, 0, 0, 0}; uint32_t n_launches = 0;
-    bool instrumented = false;
-    TravTune tune = {2, 8, 8, 6, 2}, tune_p = {2, 8, 8, 4, 1};   // scheduler parameters of the staged kernel (swept on the device: profiles/r02c_tune_sweep.log) / of the persistent kernel (profiles/r01d_*)
-    // staged traversal kernel (device/traverse_staged.cuh): derived records + launch shape
-    DevBuf<float4> d_tri64, d_inst, d_treelet; StagedScene staged = {nullptr, nullptr, nullptr, 0, 0, 16}; bool staged_ok = false; std::string staged_why;
-    int shade_mode = 1; uint32_t class_mask = 0; bool class_ok = false;   // "ShadeMode": 0 = one k_shade with the run-time BSDF dispatch, 1 = one launch per material class present (staged kernel only)
-    int staged_threads = 512, staged_rows = 16, staged_treelet = 0, staged_resident = 1024;   // "StagedThreads", "StagedStackRows", "StagedTreeletNodes", "StagedResidentThreads"
-};
 
 
 static void launch_shade(int cls, int grid, cudaStream_t st, const DScene& S, const ShadeParams& P, const PathState& ps, const Queues& Q, const unsigned* n_in, unsigned* n_out, unsigned* n_shadow, const unsigned* seg_hist) {
@@ -142,213 +51,6 @@ static void launch_intersect(const ctl_ctx* c, int grid, cudaStream_t st, const 
 
 extern "C" {
 
-const char* ctl_last_error(void) { return g_err.c_str(); }
-
-// ------------------------------------------------------------------ scenes (host)
-ctl_scene* ctl_scene_create(int kind, int width, int height, uint32_t seed, int n_hint) {
-    try { std::unique_ptr<ctl_scene> s(new ctl_scene()); ctlb::make_scene(kind, width, height, seed, n_hint, s->S); return s.release(); }
-    catch (const std::exception& e) { set_err(e.what()); return nullptr; }
-}
-ctl_scene* ctl_scene_create_from_mesh(const float* verts, uint32_t nv, const uint32_t* indices, uint32_t nt, const uint8_t* mat_index,
-                                      const ctl_material* materials, uint32_t nm, const float* emissive, const float* cam_pos,
-                                      const float* cam_target, const float* cam_up, float fov_deg, int width, int height) {
-    if (!verts || !indices || !mat_index || !materials || !cam_pos || !cam_target || !cam_up) { set_err("null argument"); return nullptr; }
-    if (!nv || !nt || !nm) { set_err("empty mesh (no vertices, triangles or materials)"); return nullptr; }
-    if (width <= 0 || height <= 0) { set_err("bad image size"); return nullptr; }
-    for (size_t i = 0; i < 3 * (size_t)nt; i++) if (indices[i] >= nv) { set_err("triangle " + std::to_string(i / 3) + ": vertex index " + std::to_string(indices[i]) + " out of range (" + std::to_string(nv) + " vertices)"); return nullptr; }
-    for (uint32_t i = 0; i < nt; i++) if (mat_index[i] >= nm) { set_err("triangle " + std::to_string(i) + ": material index " + std::to_string((unsigned)mat_index[i]) + " out of range (" + std::to_string(nm) + " materials)"); return nullptr; }
-    try {
-        ctlb::MeshInput M;
-        for (uint32_t i = 0; i < nv; i++) M.verts.push_back(ctlb::V3(verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]));
-        M.indices.assign(indices, indices + 3 * (size_t)nt);
-        M.mat_index.assign(mat_index, mat_index + nt);
-        M.materials.assign(materials, materials + nm);
-        for (uint32_t i = 0; i < nm; i++) M.emissive.push_back(emissive ? ctlb::V3(emissive[3 * i], emissive[3 * i + 1], emissive[3 * i + 2]) : ctlb::V3(0.0f));
-        std::unique_ptr<ctl_scene> s(new ctl_scene());
-        std::vector<ctlb::MeshInput> meshes = {M};
-        std::vector<ctlb::NodeInput> nodes = {{0, ctlb::M4::identity(), -1}};
-        ctlb::assemble_scene(meshes, nodes, ctlb::V3(cam_pos[0], cam_pos[1], cam_pos[2]), ctlb::V3(cam_target[0], cam_target[1], cam_target[2]),
-                             ctlb::V3(cam_up[0], cam_up[1], cam_up[2]), fov_deg, width, height, s->S);
-        return s.release();
-    } catch (const std::exception& e) { set_err(e.what()); return nullptr; }
-}
-// == DynamicScene::CreateNode(compiled mesh file) per file + the camera (Engine/DynamicScene.cpp:283-345; reader Engine/Mesh.cpp:46-98): SURVEY 8 f4
-ctl_scene* ctl_scene_create_from_xmsh(const char* const* paths, uint32_t n_files, const float* node_xforms, const float* cam_pos, const float* cam_target,
-                                      const float* cam_up, float fov_deg, int width, int height) {
-    if (!paths || !n_files || !cam_pos || !cam_target || !cam_up) { set_err("null / empty argument"); return nullptr; }
-    try {
-        std::vector<ctlb::MeshInput> meshes(n_files); std::vector<ctlb::NodeInput> nodes;
-        for (uint32_t i = 0; i < n_files; i++) {
-            if (!paths[i]) throw std::runtime_error("null path");
-            const std::string pth(paths[i]);
-            if (pth.size() > 4 && (pth.substr(pth.size() - 4) == ".obj" || pth.substr(pth.size() - 4) == ".OBJ")) ctlb::read_obj(paths[i], meshes[i]); // MeshCompilerManager picks the compiler by extension (MeshCompiler.cpp:21-27)
-            else if (pth.size() > 4 && (pth.substr(pth.size() - 4) == ".ply" || pth.substr(pth.size() - 4) == ".PLY")) ctlb::read_ply(paths[i], meshes[i]);
-            else ctlb::read_xmsh(paths[i], meshes[i]);
-            ctlb::M4 xf = ctlb::M4::identity();
-            if (node_xforms) memcpy(xf.m, node_xforms + 16 * (size_t)i, 64);
-            nodes.push_back({i, xf, -1});
-        }
-        ctl_scene* s = new ctl_scene();
-        try {
-            ctlb::assemble_scene(meshes, nodes, ctlb::V3(cam_pos[0], cam_pos[1], cam_pos[2]), ctlb::V3(cam_target[0], cam_target[1], cam_target[2]),
-                                 ctlb::V3(cam_up[0], cam_up[1], cam_up[2]), fov_deg, width, height, s->S);
-        } catch (...) { delete s; throw; }
-        return s;
-    } catch (const std::exception& e) { set_err(e.what()); return nullptr; }
-}
-ctl_scene* ctl_scene_create_from_files(const char* const* paths, uint32_t n_files, const float* node_xforms, const float* cam_pos, const float* cam_target,
-                                       const float* cam_up, float fov_deg, int width, int height) {
-    return ctl_scene_create_from_xmsh(paths, n_files, node_xforms, cam_pos, cam_target, cam_up, fov_deg, width, height);
-}
-// == the output sequence of Mesh::CompileMesh (Engine/Mesh.cpp:278-289) for mesh `mesh` of a host scene
-int ctl_scene_write_xmsh(const ctl_scene* s, uint32_t mesh, const char* path) {
-    if (!s || !path) return set_err("null argument");
-    try { ctlb::write_xmsh(path, s->S, mesh); return 0; }
-    catch (const std::exception& e) { return set_err(e.what()); }
-}
-// Source triangles of mesh `mesh` (9 floats each, TriangleData order) for export / rebuild tooling; *n_tris receives the count (verts9_out may be NULL to size).
-int ctl_scene_get_mesh_triangles(const ctl_scene* s, uint32_t mesh, float* verts9_out, uint32_t* n_tris) {
-    if (!s || !n_tris) return set_err("null argument");
-    if (mesh >= s->S.mesh_verts9.size()) return set_err("no such mesh");
-    const std::vector<float>& v = s->S.mesh_verts9[mesh];
-    if (v.empty()) return set_err("mesh has no source triangles (imported from a compiled file)");
-    *n_tris = (uint32_t)(v.size() / 9);
-    if (verts9_out) memcpy(verts9_out, v.data(), v.size() * sizeof(float));
-    return 0;
-}
-// == DynamicScene::SetNodeTransform (Engine/DynamicScene.cpp:433-443): new local-to-world matrix of one instance; the node level is re-assembled (scene-level
-// BVH = BVHRebuilder's job, inverse matrix, the node's area lights -> RecomputeShape, scene box, ray epsilon).  Mesh BVHs, Woop triangles and TriangleData are
-// untouched.  Views obtained before are invalidated: call ctl_scene_get_view and ctl_upload_scene (or ctl_update_scene_nodes) again.
-int ctl_scene_set_node_transform(ctl_scene* s, uint32_t node, const float* xf16) {
-    if (!s || !xf16) return set_err("null argument");
-    if (node >= s->S.node_inputs.size()) return set_err("no such node");
-    try { memcpy(s->S.node_inputs[node].xf.m, xf16, 64); ctlb::assemble_nodes(s->S); return 0; }
-    catch (const std::exception& e) { return set_err(e.what()); }
-}
-int ctl_scene_set_rebraid(ctl_scene* s, uint32_t max_entries) {
-    if (!s) return set_err("null argument");
-    try { s->S.rebraid_entries = max_entries; ctlb::assemble_nodes(s->S); return 0; }
-    catch (const std::exception& e) { return set_err(e.what()); }
-}
-int ctl_scene_get_view(const ctl_scene* s, ctl_scene_view* out) { if (!s || !out) return set_err("null argument"); s->S.fill_view(out); return 0; }
-void ctl_scene_destroy(ctl_scene* s) { delete s; }
-int ctl_validate_scene_view(const ctl_scene_view* v) {
-    if (!v) return set_err("null argument");
-    try { ctlb::validate_view(*v); return 0; } catch (const std::exception& e) { return set_err(e.what()); }
-}
-void ctl_encode_woop(const float v0[3], const float v1[3], const float v2[3], ctl_woop_tri* out) {
-    ctlb::encode_woop(ctlb::V3(v0[0], v0[1], v0[2]), ctlb::V3(v1[0], v1[1], v1[2]), ctlb::V3(v2[0], v2[1], v2[2]), out);
-}
-void ctl_encode_tri_data(const float p[9], const float n[9], const float uv[6], uint32_t mat, ctl_tri_data* out) {
-    ctlb::V3 P[3], N[3];
-    for (int i = 0; i < 3; i++) { P[i] = ctlb::V3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); N[i] = ctlb::V3(n[3 * i], n[3 * i + 1], n[3 * i + 2]); }
-    ctlb::encode_tri_data(P, N, uv, mat, out);
-}
-int ctl_generate_sample_tables(uint32_t pass, float* d1, float* d2) {
-    ctlb::SamplerTableGenerator g;
-    for (uint32_t p = 0; p <= pass; p++) g.next_pass(d1, d2);
-    return 0;
-}
-
-
-// ------------------------------------------------------------------ GPU BVH build
-// LBVH of one triangle mesh in the reference layout; host arrays in, host arrays out (nodes_out: capacity >= max(1, n_tris) entries).
-int ctl_bvh_build_gpu(int device, const float* verts9, uint32_t n_tris, ctl_bvh_node* nodes_out, uint32_t* n_nodes_out, ctl_woop_tri* woop_out, uint32_t* index_out, float* build_ms) {
-    using namespace ctlbvh;
-    if (!verts9 || !n_tris || !nodes_out || !n_nodes_out || !woop_out || !index_out) return set_err("null / empty argument");
-    if (n_tris > 0x3fffffffu) return set_err("too many triangles");
-    CK(cudaSetDevice(device));
-    const int n = (int)n_tris;
-    const int nb_sort = (n + SORT_TILE - 1) / SORT_TILE;
-    DevBuf<float> d_verts; DevBuf<float4> d_boxes, d_nbox; DevBuf<unsigned> d_sbox, d_counts, d_flags, d_emit; DevBuf<uint32_t> d_k0, d_k1, d_v0, d_v1, d_index;
-    DevBuf<int> d_left, d_right, d_pint, d_pleaf, d_first, d_last; DevBuf<ctl_bvh_node> d_nodes; DevBuf<ctl_woop_tri> d_woop; DevBuf<unsigned char> d_lastflag, d_collapse; DevBuf<float> d_cost;
-    auto free_all = [&]() { d_verts.release(); d_boxes.release(); d_nbox.release(); d_sbox.release(); d_counts.release(); d_flags.release(); d_emit.release(); d_k0.release(); d_k1.release(); d_v0.release(); d_v1.release();
-                            d_index.release(); d_left.release(); d_right.release(); d_pint.release(); d_pleaf.release(); d_first.release(); d_last.release(); d_nodes.release(); d_woop.release(); d_lastflag.release(); d_collapse.release(); d_cost.release(); };
-#define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { free_all(); char b_[512]; snprintf(b_, sizeof(b_), "In file %s at line %d : %s", __FILE__, __LINE__, cudaGetErrorString(e_)); return set_err(b_); } } while (0)
-    CKF(d_verts.upload(verts9, (size_t)n * 9)); CKF(d_boxes.ensure((size_t)n * 2)); CKF(d_nbox.ensure((size_t)n * 2)); CKF(d_sbox.ensure(6)); CKF(d_counts.ensure((size_t)256 * nb_sort));
-    CKF(d_flags.ensure((size_t)n)); CKF(d_emit.ensure((size_t)n + 1)); CKF(d_k0.ensure(n)); CKF(d_k1.ensure(n)); CKF(d_v0.ensure(n)); CKF(d_v1.ensure(n)); CKF(d_index.ensure(n));
-    CKF(d_left.ensure(n)); CKF(d_right.ensure(n)); CKF(d_pint.ensure(n)); CKF(d_pleaf.ensure(n)); CKF(d_first.ensure(n)); CKF(d_last.ensure(n)); CKF(d_nodes.ensure((size_t)n)); CKF(d_woop.ensure(n)); CKF(d_lastflag.ensure(n)); CKF(d_collapse.ensure(n)); CKF(d_cost.ensure(n));
-    cudaEvent_t e0, e1; CKF(cudaEventCreate(&e0)); CKF(cudaEventCreate(&e1));
-    cudaStream_t st = nullptr;
-    CKF(cudaEventRecord(e0, st));
-    const unsigned sbox_init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
-    CKF(cudaMemcpyAsync(d_sbox.p, sbox_init, sizeof(sbox_init), cudaMemcpyHostToDevice, st));
-    CKF(cudaMemsetAsync(d_flags.p, 0, (size_t)n * 4, st)); CKF(cudaMemsetAsync(d_lastflag.p, 0, (size_t)n, st));
-    const int g = (n + 255) / 256;
-    k_tri_boxes<<<g, 256, 0, st>>>(d_verts.p, n_tris, d_boxes.p, d_sbox.p);
-    k_morton<<<g, 256, 0, st>>>(d_boxes.p, n_tris, d_sbox.p, d_k0.p, d_v0.p);
-    uint32_t *kin = d_k0.p, *kout = d_k1.p, *vin = d_v0.p, *vout = d_v1.p;
-    for (int pass = 0; pass < 4; pass++) {
-        k_sort_hist<<<nb_sort, SORT_THREADS, 0, st>>>(kin, n_tris, 8 * pass, d_counts.p, nb_sort);
-        k_scan_exclusive<<<1, 1024, 0, st>>>(d_counts.p, (uint32_t)(256 * nb_sort));
-        k_sort_scatter<<<nb_sort, SORT_THREADS, 0, st>>>(kin, vin, n_tris, 8 * pass, d_counts.p, nb_sort, kout, vout);
-        std::swap(kin, kout); std::swap(vin, vout);
-    }
-    uint32_t n_nodes = 1;
-    if (n > MAX_LEAF) {
-        k_radix_tree<<<g, 256, 0, st>>>(kin, n, d_left.p, d_right.p, d_pint.p, d_pleaf.p, d_first.p, d_last.p);
-        k_fit_boxes<<<g, 256, 0, st>>>(d_boxes.p, vin, n, d_left.p, d_right.p, d_pint.p, d_pleaf.p, d_first.p, d_last.p, d_flags.p, d_nbox.p, d_cost.p, d_collapse.p);
-        k_mark_emitted<<<g, 256, 0, st>>>(n, d_pint.p, d_first.p, d_last.p, d_collapse.p, d_emit.p);
-        k_scan_exclusive<<<1, 1024, 0, st>>>(d_emit.p, (uint32_t)n);
-        k_emit_nodes<<<g, 256, 0, st>>>(n, d_left.p, d_right.p, d_pint.p, d_first.p, d_last.p, d_emit.p, d_boxes.p, vin, d_nbox.p, d_collapse.p, d_nodes.p, d_lastflag.p);
-        CKF(cudaMemcpyAsync(&n_nodes, d_emit.p + (n - 1), 4, cudaMemcpyDeviceToHost, st));
-    } else {
-        k_single_leaf_root<<<1, 32, 0, st>>>(d_sbox.p, n, d_nodes.p, d_lastflag.p);
-    }
-    k_emit_tris<<<g, 256, 0, st>>>(d_verts.p, vin, n, d_lastflag.p, d_woop.p, d_index.p);
-    CKF(cudaGetLastError());
-    CKF(cudaEventRecord(e1, st));
-    CKF(cudaStreamSynchronize(st));
-    float ms = 0; CKF(cudaEventElapsedTime(&ms, e0, e1));
-    CKF(cudaMemcpy(nodes_out, d_nodes.p, (size_t)n_nodes * sizeof(ctl_bvh_node), cudaMemcpyDeviceToHost));
-    CKF(cudaMemcpy(woop_out, d_woop.p, (size_t)n * sizeof(ctl_woop_tri), cudaMemcpyDeviceToHost));
-    CKF(cudaMemcpy(index_out, d_index.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    free_all();
-#undef CKF
-    *n_nodes_out = n_nodes;
-    if (build_ms) *build_ms = ms;
-    return 0;
-}
-
-// Rebuild every mesh BVH of a host scene on the GPU (node / Woop / index arrays, mesh offsets, light-triangle slots).
-int ctl_scene_rebuild_bvh_gpu(ctl_scene* s, int device, float* build_ms_total) {
-    if (!s) return set_err("null scene");
-    ctlb::SceneStorage& S = s->S;
-    if (S.mesh_verts9.size() != S.meshes.size()) return set_err("scene has no triangle vertices (built by an older builder)");
-    std::vector<ctl_bvh_node> all_nodes; std::vector<ctl_woop_tri> all_woop; std::vector<uint32_t> all_index;
-    std::vector<ctl_mesh> meshes = S.meshes;
-    float total = 0;
-    std::vector<std::vector<uint32_t>> slot_of_tri(S.meshes.size());
-    for (size_t mi = 0; mi < S.meshes.size(); mi++) {
-        const uint32_t nt = (uint32_t)(S.mesh_verts9[mi].size() / 9);
-        std::vector<ctl_bvh_node> nodes(nt ? nt : 1); std::vector<ctl_woop_tri> woop(nt); std::vector<uint32_t> index(nt);
-        uint32_t nn = 0; float ms = 0;
-        if (ctl_bvh_build_gpu(device, S.mesh_verts9[mi].data(), nt, nodes.data(), &nn, woop.data(), index.data(), &ms)) return 1;
-        total += ms;
-        if (getenv("CTL_LBVH_OPTIMIZE")) { nodes.resize(nn); ctlb::optimize_bvh(nodes); }   // experiment for round 2: the mesh trees' host post-pass (re-insertion + rotations) on the LBVH; node count unchanged
-        meshes[mi].bvh_node_offset = (uint32_t)all_nodes.size() * 4;
-        meshes[mi].bvh_tri_offset = (uint32_t)all_woop.size() * 3;
-        meshes[mi].bvh_idx_offset = (uint32_t)all_index.size();
-        slot_of_tri[mi].assign(nt, 0);
-        for (uint32_t k = 0; k < nt; k++) slot_of_tri[mi][index[k] >> 1] = meshes[mi].bvh_idx_offset + k;
-        all_nodes.insert(all_nodes.end(), nodes.begin(), nodes.begin() + nn);
-        all_woop.insert(all_woop.end(), woop.begin(), woop.end());
-        all_index.insert(all_index.end(), index.begin(), index.end());
-    }
-    // light triangles point at Woop slots (ShapeSet::triData::iDat): remap through (mesh, triangle)
-    for (auto& lt : S.light_tris) {
-        for (size_t mi = 0; mi < S.meshes.size(); mi++) {
-            const uint32_t t0 = S.meshes[mi].tri_offset, nt = (uint32_t)slot_of_tri[mi].size();
-            if (lt.t_dat >= t0 && lt.t_dat < t0 + nt) { lt.i_dat = slot_of_tri[mi][lt.t_dat - t0]; break; }
-        }
-    }
-    S.bvh_nodes.swap(all_nodes); S.woop.swap(all_woop); S.tri_index.swap(all_index); S.meshes = meshes;
-    if (S.rb_active) { try { ctlb::assemble_nodes(S); } catch (const std::exception& e) { return set_err(e.what()); } }   // re-braided entries are copies of the old sub-trees: redo them
-    if (build_ms_total) *build_ms_total = total;
-    return 0;
-}
-
 // ------------------------------------------------------------------ context
 static int alloc_image(ctl_ctx* c) {
     CK(c->own_accum.ensure((size_t)c->w * c->h * 7));
@@ -384,7 +86,7 @@ ctl_ctx* ctl_create(int device, int width, int height) {
     CKP(cudaSetDevice(device));
     ctl_ctx* c = new ctl_ctx();
     c->device = device; c->w = width; c->h = height;
-    if (init_ctx(c)) { const std::string keep = g_err; ctl_destroy(c); g_err = keep; return nullptr; }
+    if (init_ctx(c)) { const std::string keep = ctl_last_error(); ctl_destroy(c); ctl_set_err(keep); return nullptr; }
     return c;
 }
 
@@ -392,6 +94,7 @@ void ctl_destroy(ctl_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    ctl_comm_release(c);
     c->d_scene_nodes.release(); c->d_bvh_nodes.release(); c->d_woop.release(); c->d_tri_index.release(); c->d_tri_data.release(); c->d_meshes.release();
     c->d_nodes.release(); c->d_xf.release(); c->d_inv_xf.release(); c->d_materials.release(); c->d_lights.release(); c->d_light_tris.release();
     c->d_light_cdf.release(); c->d_normal_lut.release(); c->d_tri64.release(); c->d_inst.release(); c->d_treelet.release();
@@ -610,7 +313,6 @@ int ctl_read_sample_tables(ctl_ctx* c, int table_set, float* d1, float* d2) {
 }
 
 // ------------------------------------------------------------------ intersect API
-static int grid_for(const ctl_ctx* c, int per_sm) { return c->n_sm * per_sm; }
 
 
 // Re-braided scenes (ctl_scene_set_rebraid): the traversal reports the pseudo-node it hit; API results name the instance, as the reference's would.
@@ -699,7 +401,6 @@ static void stage_mark(ctl_ctx* c, int kind) {
     c->stage_kind.push_back(kind);
 }
 
-static int variance_after_pass(ctl_ctx* c, bool new_trace);
 
 static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
     if (!c->has_scene) return set_err("no scene uploaded");
@@ -804,7 +505,7 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
     launches += 2;
     stage_mark(c, 5);
     CK(cudaGetLastError());
-    if (variance_after_pass(c, new_trace != 0)) return 1;
+    if (ctl_variance_after_pass(c, new_trace != 0)) return 1;
     CK(cudaEventRecord(c->ev_stop, c->stream));
     c->events_recorded = true;
     c->n_launches = launches;
@@ -930,7 +631,7 @@ int ctl_wavefront_pass(ctl_ctx* c, int new_trace) {
     launches++;
     stage_mark(c, 5);
     CK(cudaGetLastError());
-    if (variance_after_pass(c, new_trace != 0)) return 1;
+    if (ctl_variance_after_pass(c, new_trace != 0)) return 1;
     CK(cudaEventRecord(c->ev_stop, c->stream));
     c->events_recorded = true;
     c->n_launches = launches;
@@ -949,112 +650,6 @@ int ctl_read_accum(ctl_ctx* c, ctl_pixel_data* out) {
     if (!c || !out) return set_err("null argument");
     CK(cudaSetDevice(c->device));
     CK(cudaMemcpyAsync(out, c->accum, (size_t)c->w * c->h * 7 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    return 0;
-}
-// == applyImagePipeline (Kernel/ImagePipeline/ImagePipeline.cu:54-84): optional reconstruction filter, optional tone mapper, gamma
-int ctl_apply_image_pipeline(ctl_ctx* c, float splat_scale, const ctl_image_pipeline* P, void* d_rgba8, void* host_rgba8, float lum_info[6]) {
-    if (!c || !P || (!d_rgba8 && !host_rgba8)) return set_err("null argument");
-    if (P->filter_type < -1 || P->filter_type > 5) return set_err("filter_type must be -1 (none), 0 (box), 1 (Gaussian), 2 (triangle), 3 (Mitchell), 4 (Lanczos-sinc) or 5 (non-local means)");
-    const bool nlm = P->filter_type == 5;
-    if (P->filter_type >= 0 && !nlm && (!(P->x_width > 0) || !(P->y_width > 0) || P->x_width > 16 || P->y_width > 16)) return set_err("filter widths out of range (0, 16]");
-    if (P->tonemap < 0 || P->tonemap > 1) return set_err("tonemap must be 0 (none) or 1 (Reinhard05)");
-    if (nlm) {
-        if (!(P->param0 >= 0.0f) || !(P->param1 >= 0.0f)) return set_err("NonLocalMeansFilter: k (param0) and sigma2Scale (param1) must be >= 0");
-        if (!(P->x_width >= 1.0f) || P->x_width > 1e9f || P->x_width != floorf(P->x_width)) return set_err("NonLocalMeansFilter: UpdateWeightPeriodicity (x_width) must be an integer >= 1");
-        if (!c->variance_buffer || !c->d_var.p || c->d_var.n < (size_t)c->w * c->h) return set_err("NonLocalMeansFilter reads the PixelVarianceBuffer: ctl_set_param_i(ctx, \"PixelVarianceBuffer\", 1) before the passes");
-    }
-    CK(cudaSetDevice(c->device));
-    const int n = c->w * c->h;
-    uchar4* dst = (uchar4*)d_rgba8;
-    if (!dst) { CK(c->resolve_tmp.ensure((size_t)n)); dst = c->resolve_tmp.p; }
-    const int grid = grid_for(c, 8);
-    if (nlm) { // NonLocalMeansFilter::Apply (Kernel/ImagePipeline/Filter/NonLocalMeansFilter.cu:184-228), then the rest of applyImagePipeline (ImagePipeline.cu:71-82)
-        const long long numPasses = (long long)c->passes_done; const int n_update = (int)P->x_width;
-        bool force_update = false;
-        if (c->nlm_pixels != (size_t)n) { // Resize / first use: new cache and weight buffer (adaptBuffer), last_iter_weight_update = -1
-            CK(c->nlm_cached.ensure((size_t)n)); CK(c->nlm_varh.ensure((size_t)n)); CK(c->nlm_weights.ensure((size_t)n * NLM_NW));
-            c->nlm_pixels = (size_t)n; c->nlm_last_update = -1; force_update = true;
-        }
-        k_nlm_prepare<<<grid, 256, 0, c->stream>>>(c->accum, c->d_var.p, n, splat_scale, c->nlm_cached.p, c->nlm_varh.p);
-        const dim3 nb((c->w + NLM_B - 1) / NLM_B, (c->h + NLM_B - 1) / NLM_B), nt(NLM_B, NLM_B);
-        if (c->nlm_last_update + 1 != numPasses || (numPasses % n_update) == 0 || force_update) {
-            CK(cudaMemsetAsync(c->nlm_weights.p, 0, (size_t)n * NLM_NW * sizeof(float), c->stream));   // m_weightBuffer.ClearBuffer()
-            k_nlm_weights<<<nb, nt, 0, c->stream>>>(c->nlm_cached.p, c->nlm_varh.p, c->w, c->h, P->param0, P->param1, c->nlm_weights.p);
-        }
-        c->nlm_last_update = numPasses;
-        if (!P->tonemap) k_nlm_apply<true><<<nb, nt, 0, c->stream>>>(c->nlm_cached.p, c->nlm_weights.p, c->w, c->h, dst);
-        else {
-            const int bx = (c->w + 15) / 16, by = (c->h + 15) / 16;
-            CK(c->pipe_rgbe.ensure((size_t)n)); CK(c->pipe_partial.ensure((size_t)bx * by)); CK(c->pipe_lum.ensure(8));
-            k_nlm_apply<false><<<nb, nt, 0, c->stream>>>(c->nlm_cached.p, c->nlm_weights.p, c->w, c->h, c->pipe_rgbe.p);
-            k_lum_blocks<<<bx * by, 256, 0, c->stream>>>(c->pipe_rgbe.p, c->w, c->h, bx, c->pipe_partial.p);
-            k_lum_final<<<1, 32, 0, c->stream>>>(c->pipe_partial.p, bx * by, n, P->key, P->burn, c->pipe_lum.p);
-            k_reinhard<<<grid, 256, 0, c->stream>>>(c->pipe_rgbe.p, n, c->pipe_lum.p, dst);
-            if (lum_info) { CK(cudaMemcpyAsync(lum_info, c->pipe_lum.p, 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
-        }
-        CK(cudaGetLastError());
-        if (host_rgba8) { CK(cudaMemcpyAsync(host_rgba8, dst, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
-        return 0;
-    }
-    PipeFilter F = {P->filter_type, P->x_width, P->y_width, P->param0, P->param1, 1.f / P->x_width, 1.f / P->y_width,
-                    expf(-P->param0 * P->x_width * P->x_width), expf(-P->param0 * P->y_width * P->y_width)}; // FilterBase / GaussianFilter ctor, SceneTypes/Filter.h:15-19, 60-66
-    if (P->filter_type < 0 && !P->tonemap) k_pipe_direct<<<grid, 256, 0, c->stream>>>(c->accum, n, splat_scale, dst);
-    else if (!P->tonemap) k_pipe_stage2<true, true><<<grid, 256, 0, c->stream>>>(c->accum, c->w, c->h, splat_scale, F, dst);
-    else {
-        const int bx = (c->w + 15) / 16, by = (c->h + 15) / 16;
-        CK(c->pipe_rgbe.ensure((size_t)n)); CK(c->pipe_partial.ensure((size_t)bx * by)); CK(c->pipe_lum.ensure(8));
-        if (P->filter_type >= 0) k_pipe_stage2<true, false><<<grid, 256, 0, c->stream>>>(c->accum, c->w, c->h, splat_scale, F, c->pipe_rgbe.p);
-        else k_pipe_stage2<false, false><<<grid, 256, 0, c->stream>>>(c->accum, c->w, c->h, splat_scale, F, c->pipe_rgbe.p);
-        k_lum_blocks<<<bx * by, 256, 0, c->stream>>>(c->pipe_rgbe.p, c->w, c->h, bx, c->pipe_partial.p);
-        k_lum_final<<<1, 32, 0, c->stream>>>(c->pipe_partial.p, bx * by, n, P->key, P->burn, c->pipe_lum.p);
-        k_reinhard<<<grid, 256, 0, c->stream>>>(c->pipe_rgbe.p, n, c->pipe_lum.p, dst);
-        if (lum_info) { CK(cudaMemcpyAsync(lum_info, c->pipe_lum.p, 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
-    }
-    CK(cudaGetLastError());
-    if (host_rgba8) { CK(cudaMemcpyAsync(host_rgba8, dst, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
-    return 0;
-}
-// NonLocalMeansFilter's weight buffer of the last ctl_apply_image_pipeline(filter_type 5), in the reference's layout [pixel][169] (slot (yo + 6) * 13 + xo + 6,
-// NonLocalMeansFilter.h:13-31, 63-66); kept on the device as [169][pixel]
-int ctl_read_nlm_weights(ctl_ctx* c, float* host_out) {
-    if (!c || !host_out) return set_err("null argument");
-    if (!c->nlm_pixels || c->nlm_pixels != (size_t)c->w * c->h || c->nlm_last_update < 0) return set_err("no NonLocalMeansFilter weights: apply a pipeline with filter_type 5 first");
-    CK(cudaSetDevice(c->device));
-    const size_t n = c->nlm_pixels;
-    std::vector<float> soa(n * NLM_NW);
-    CK(cudaMemcpyAsync(soa.data(), c->nlm_weights.p, n * NLM_NW * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    for (size_t p = 0; p < n; p++) for (int s = 0; s < NLM_NW; s++) host_out[p * NLM_NW + s] = soa[(size_t)s * n + p];
-    return 0;
-}
-// == applyImagePipeline(tracer, img, 0, 0): the default resolve
-int ctl_resolve_srgb8(ctl_ctx* c, float splat_scale, void* d_rgba8, void* host_rgba8) {
-    ctl_image_pipeline P; memset(&P, 0, sizeof(P)); P.filter_type = -1;
-    return ctl_apply_image_pipeline(c, splat_scale, &P, d_rgba8, host_rgba8, nullptr);
-}
-// == applyImagePipeline(tracer, img, filter, 0) with box / Gaussian / triangle (kept for callers of the first f3 slice)
-int ctl_resolve_filtered_srgb8(ctl_ctx* c, float splat_scale, int filter_type, float x_width, float y_width, float alpha, void* d_rgba8, void* host_rgba8) {
-    if (filter_type < 0 || filter_type > 2) return set_err("filter_type must be 0 (box), 1 (Gaussian) or 2 (triangle)");
-    ctl_image_pipeline P; memset(&P, 0, sizeof(P)); P.filter_type = filter_type; P.x_width = x_width; P.y_width = y_width; P.param0 = alpha;
-    return ctl_apply_image_pipeline(c, splat_scale, &P, d_rgba8, host_rgba8, nullptr);
-}
-// == PixelVarianceBuffer (Kernel/PixelVarianceBuffer.h)
-static int variance_after_pass(ctl_ctx* c, bool new_trace) { // Tracer<true>::DoPass: Clear on a new trace (Tracer.h:222-226), AddPass after DoRender (:233-237)
-    if (!c->variance_buffer) return 0;
-    const size_t n = (size_t)c->w * c->h;
-    const bool fresh = c->d_var.n < n;
-    CK(c->d_var.ensure(n));
-    if (new_trace || fresh) CK(cudaMemsetAsync(c->d_var.p, 0, n * sizeof(ctl_pixel_variance_info), c->stream));
-    k_variance_update<<<grid_for(c, 8), 256, 0, c->stream>>>(c->d_var.p, c->accum, (int)n, 0.0f /* getSplatScale(): the path tracers never splat */);
-    CK(cudaGetLastError());
-    return 0;
-}
-int ctl_read_variance(ctl_ctx* c, ctl_pixel_variance_info* out) {
-    if (!c || !out) return set_err("null argument");
-    if (!c->variance_buffer || !c->d_var.p) return set_err("PixelVarianceBuffer is off: ctl_set_param_i(ctx, \"PixelVarianceBuffer\", 1) before the passes");
-    CK(cudaSetDevice(c->device));
-    CK(cudaMemcpyAsync(out, c->d_var.p, (size_t)c->w * c->h * sizeof(ctl_pixel_variance_info), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }

@@ -367,8 +367,11 @@ struct ShadeParams { int max_path_length, rr_start, direct, stop_zero; };
 // never waits for another class's code (the Beckmann visible-normal Newton loop in particular).  With `seg_hist` the launch covers only its class's
 // segment of Q.order (k_class_scatter); without it the whole queue (single-class scenes).  Same per-path arithmetic either way.
 CTL_DEV constexpr uint32_t cls_bsdf_type(int cls) { return cls == 0 ? CTL_BSDF_DIFFUSE : (cls == 3 ? CTL_BSDF_DIELECTRIC : CTL_BSDF_ROUGHCONDUCTOR); }
+#ifndef CTL_SHADE_MICRO_MIN_BLOCKS
+#define CTL_SHADE_MICRO_MIN_BLOCKS CTL_SHADE_MIN_BLOCKS // resident blocks per SM of the rough-conductor launches (their bodies spill ~150 B at 64 registers)
+#endif
 template <int CLS>
-__global__ void __launch_bounds__(128, CTL_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene S, const __grid_constant__ ShadeParams P, PathState st, Queues Q,
+__global__ void __launch_bounds__(128, (CLS == 1 || CLS == 2) ? CTL_SHADE_MICRO_MIN_BLOCKS : CTL_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene S, const __grid_constant__ ShadeParams P, PathState st, Queues Q,
                                                 const unsigned* __restrict__ n_in, unsigned* n_out, unsigned* n_shadow, const unsigned* __restrict__ seg_hist) {
     int n = (int)*n_in, seg_start = 0;
     if (CLS >= 0 && seg_hist) { for (int b = 0; b < CLS; b++) seg_start += (int)seg_hist[b]; n = (int)seg_hist[CLS]; }

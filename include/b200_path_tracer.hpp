@@ -15,6 +15,7 @@
 // "In file ... at line ... : msg" text (ThrowCudaErrors convention, Defines.cpp:15-29).  No CPU fallback exists.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -91,6 +92,11 @@ public:
         need_ctx(); std::vector<ctl_trace_result> out(rays.size());
         check(ctl_trace_rays_host(ctx_, (int)rays.size(), rays.data(), out.data(), nullptr)); return out;
     }
+    // n_passes DoPass calls fused into one wavefront on the tiles of `part` of `n_parts` (ctl_render_passes_tiled); asynchronous
+    void DoPassesTiled(int n_passes, bool a_NewTrace, int part = 0, int n_parts = 1, int tile = 64) {
+        need_ctx(); check(ctl_render_passes_tiled(ctx_, (a_NewTrace || new_trace_) ? 1 : 0, n_passes, tile, tile, part, n_parts)); new_trace_ = false;
+    }
+    void Synchronize() { need_ctx(); check(ctl_synchronize(ctx_)); }
     ctl_ctx* handle() { return ctx_; }
 protected:
     bool take_new_trace(bool a_NewTrace) { const bool nt = a_NewTrace || new_trace_; new_trace_ = false; return nt; }
@@ -117,6 +123,42 @@ public:
         check(ctl_wavefront_pass(handle(), take_new_trace(a_NewTrace) ? 1 : 0));
         finish_pass(image);
     }
+};
+
+// Several GPUs of one node driven by ONE host process (no reference counterpart: the reference is single-GPU).  One PathTracer per device, the same
+// scene uploaded to each, the image split in interleaved 64x64 tiles (tile index % devices == device), one NCCL reduce of the PixelData accumulators
+// to device 0 per frame (csrc/ctl_comm.cu).  Every path is the one a single device would trace, so the reduced image equals the single-GPU image up
+// to the order of float additions into a pixel.
+class MultiGpuPathTracer {
+public:
+    explicit MultiGpuPathTracer(int n_devices) { for (int d = 0; d < n_devices; d++) t_.emplace_back(new PathTracer(d)); }
+    int devices() const { return (int)t_.size(); }
+    PathTracer& device(int d) { return *t_[d]; }
+    void Resize(unsigned w, unsigned h) {
+        for (auto& t : t_) t->Resize(w, h);
+        std::vector<ctl_ctx*> c; for (auto& t : t_) c.push_back(t->handle());
+        if (c.size() > 1) check(ctl_comm_init_all(c.data(), (int)c.size()));
+        w_ = w; h_ = h;
+    }
+    void InitializeScene(const ctl_scene_view& view) { for (auto& t : t_) t->InitializeScene(view); }
+    void setParameter(const std::string& key, int value) { for (auto& t : t_) t->setParameter(key, value); }
+    // One progressive frame of `spp` passes (`batch` fused per wavefront): every device renders its tiles, then the one reduce to device 0.
+    // image (optional): the reduced PixelData accumulator.  Returns the rays traced by all devices.
+    unsigned long long RenderFrame(int spp, int batch, ctl_pixel_data* image = nullptr) {
+        if (spp < 1 || batch < 1 || spp % batch) throw std::runtime_error("spp must be a positive multiple of batch");
+        const int n = devices();
+        for (int p = 0; p < spp; p += batch)
+            for (int d = 0; d < n; d++) t_[d]->DoPassesTiled(batch, p == 0, d, n);     // asynchronous: the devices run concurrently
+        std::vector<ctl_ctx*> c; for (auto& t : t_) c.push_back(t->handle());
+        check(ctl_comm_reduce_accum_all(c.data(), n, 0));
+        unsigned long long rays = 0;
+        for (int d = 0; d < n; d++) { t_[d]->Synchronize(); rays += t_[d]->getAccRays(); }
+        const unsigned long long frame_rays = rays - rays_before_; rays_before_ = rays;
+        if (image) check(ctl_read_accum(t_[0]->handle(), image));
+        return frame_rays;
+    }
+private:
+    std::vector<std::unique_ptr<PathTracer>> t_; unsigned w_ = 0, h_ = 0; unsigned long long rays_before_ = 0;
 };
 
 } // namespace ctlb200

@@ -241,11 +241,11 @@ int  ctl_scene_get_mesh_triangles(const ctl_scene*, uint32_t mesh, float* verts9
  * ray epsilon); mesh BVHs / Woop triangles / TriangleData are untouched.  Views obtained before the call are invalidated. */
 int  ctl_scene_set_node_transform(ctl_scene*, uint32_t node, const float* xf16);
 /* == DynamicScene::getKernelSceneData(false) (Engine/DynamicScene.cpp:567-589): the flat view of the host arrays; valid until the scene is changed or destroyed */
-/* Opt-in partial re-braiding of the scene level (no reference counterpart; its BVHRebuilder keeps one leaf per instance): instances with large,
+/* Partial re-braiding of the scene level (no reference counterpart; its BVHRebuilder keeps one leaf per instance): instances with large,
  * overlapping boxes are opened into up to max_entries (instance, sub-tree) leaves, each an ordinary node + mesh record over a re-based copy of the
  * sub-tree, so the traversal kernels and the data layout are unchanged.  Same hits; ctl_intersect / ctl_intersect_host / ctl_trace_rays_host report the
- * INSTANCE a hit belongs to (results pass through view.node_alias on the device), like the reference would.  0 = off (default).  Re-assembles the node level: obtain the view again, then ctl_upload_scene
- * (ctl_update_scene_nodes uploads everything for a re-braided view: its mesh-level records follow the node level).  EXPERIMENTAL in round 1: measured on the CPU oracle only. */
+ * INSTANCE a hit belongs to (results pass through view.node_alias on the device), like the reference would.  0 = off; the default is by scene size (1 024 leaves when the meshes hold >= 32 768 BVH nodes, else off; CTL_REBRAID=<n> in the environment overrides).  Re-assembles the node level: obtain the view again, then ctl_upload_scene
+ * (ctl_update_scene_nodes uploads everything for a re-braided view: its mesh-level records follow the node level). */
 int  ctl_scene_set_rebraid(ctl_scene*, uint32_t max_entries);
 int  ctl_scene_get_view(const ctl_scene*, ctl_scene_view* out);
 /* == DynamicScene::~DynamicScene (Engine/DynamicScene.cpp:219) */
@@ -286,7 +286,10 @@ int      ctl_resize(ctl_ctx*, int width, int height);    /* == Tracer<true>::Res
  *    "Regularization" (0, only 0 supported)  (Integrators/PathTracer.h:10-20);
  *    extras: "SortMode" (0 none, 1 material), "StageTimers" (0/1), "CaptureBounce" (0 = off),
  *    "DeviceSampleTables" (1 = tables generated by a CUDA kernel, bit-identical to the host XORWOW generator; 0 = generated on the
- *    host and copied H2D every pass like the reference's UpdateKernel), "TraversalKernel" (0 persistent, 1 simple A/B baseline), "FuseTraversal" (1 = shadow rays of bounce b and
+ *    host and copied H2D every pass like the reference's UpdateKernel), "TraversalKernel" (2 = persistent warps with shared-memory staging [default], 0 = persistent warps, 1 = ray-batch A/B baseline), "StagedThreads" / "StagedStackRows" /
+ *    "StagedTreeletNodes" / "StagedResidentThreads" (launch shape of kernel 2; treelet nodes take effect at the next scene upload), "ShadeMode" (1 = one shade launch per
+ *    material class [default], 0 = run-time BSDF dispatch), "StopZeroThroughput" (1 = a path of exactly zero throughput ends [default]; 0 = it is traced until Russian
+ *    roulette, the reference's ray count), "TravTSteps", "FuseTraversal" (1 = shadow rays of bounce b and
  *    extension rays of bounce b+1 share one traversal launch),
  *    "TraversalBlocksPerSM", "TravThT/L/F", "TravThNExit" (tuning). */
 int ctl_set_param_i(ctl_ctx*, const char* key, int value);   /* == TracerParameterCollection::setValue<int> (Kernel/TracerSettings.h:277-283) */
@@ -389,6 +392,31 @@ void* ctl_stream(ctl_ctx*);
  * stream).  The reference is single-stream (default stream, Kernel/TraceHelper.cu:744); this lets a host
  * application order the passes with its own kernels / NCCL calls without extra synchronisation. */
 int ctl_set_stream(ctl_ctx*, void* stream);
+
+
+/* ---- multi-GPU: image tiles per rank + ONE NCCL reduce of the accumulator per frame (csrc/ctl_comm.cu) ---------------------------------
+ * No reference counterpart: the reference is single-GPU (Kernel/TraceHelper.cu:744 synchronises one device; no NCCL / MPI in its tree).
+ * Random numbers are a pure function of (pass, pixel index, dimension) (Kernel/Sampler_device.h:91-107), so disjoint tiles on different
+ * devices trace exactly the paths one device would, and summing the zero-initialised accumulators is exact.  NCCL is loaded at run time
+ * (dlopen of libnccl.so.2) and only by these calls. */
+#define CTL_COMM_ID_BYTES 128 /* == NCCL_UNIQUE_ID_BYTES */
+/* Rank 0 of a multi-process job: CTL_COMM_ID_BYTES bytes to hand to the other ranks (file, socket, MPI, environment ...). */
+int ctl_comm_get_unique_id(void* id_out);
+/* One process (or thread) per GPU: join the communicator described by `id` as `rank` of `n_ranks` (collective: every rank calls it). */
+int ctl_comm_init_rank(ctl_ctx*, const void* id, int rank, int n_ranks);
+/* One process driving n contexts on n distinct devices: contexts[i] becomes rank i.  Use the *_all collectives below with it. */
+int ctl_comm_init_all(ctl_ctx* const* contexts, int n);
+int ctl_comm_rank(const ctl_ctx*, int* rank, int* n_ranks);
+/* The one collective of the path: ncclReduce(sum) of the PixelData accumulator (7*w*h floats) to `root`, in place, on the context's stream
+ * (ordered after the frame's kernels); asynchronous.  Without a communicator (single GPU) it is a no-op. */
+int ctl_comm_reduce_accum(ctl_ctx*, int root);
+int ctl_comm_reduce_accum_all(ctl_ctx* const* contexts, int n, int root); /* the same for ctl_comm_init_all communicators (groups the per-device calls) */
+/* Sum of `count` (<= 64) host counters over the ranks, e.g. the ray counts of a frame; synchronous. */
+int ctl_comm_allreduce_u64(ctl_ctx*, uint64_t* host_inout, int count);
+/* One progressive frame shared by the ranks: `spp` passes (`batch` fused per wavefront) on this rank's interleaved tile x tile tiles
+ * (tile index % ranks == rank; tile <= 0 = 64), then ctl_comm_reduce_accum(root).  Asynchronous. */
+int ctl_comm_render_frame(ctl_ctx*, int spp, int batch, int tile, int root);
+int ctl_comm_destroy(ctl_ctx*);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ def test_full_resolution_windows_match_oracle(built_lib, orc, kind):
     t.DoPasses(SPP, new_trace=True); t.synchronize()             # == bench.py's frame at N = 1: ctl_render_passes_tiled(8 passes, 64x64 tiles, part 0 of 1)
     img = t.readAccumulator(); rays_stop = t.getRaysInLastPass()
     assert t.getNumPassesDone() == SPP
-    assert np.all(img["weight_sum"][2:-2, 2:-2] == SPP)
+    assert img["weight_sum"].sum() == SPP * W * H                # every path of every pass landed (a jittered sample may round into the neighbouring pixel)
     # the same frame with the reference's ray definition
     t.setParameter("StopZeroThroughput", 0)
     t.DoPasses(SPP, new_trace=True); t.synchronize()
