@@ -20,7 +20,9 @@ static void launch_shade(int cls, int grid, cudaStream_t st, const DScene& S, co
 }
 
 // Launch shape of the staged kernel: blocks of `staged_threads`, as many per SM as 1024 resident threads and the shared memory allow
-static size_t staged_smem_bytes(const ctl_ctx* c) { return (size_t)c->staged.tl_nodes * 64 + 16 + (size_t)(c->staged.stack_rows + 1) * c->staged_threads * 4; }
+static size_t staged_smem_bytes(const ctl_ctx* c) {
+    return (size_t)c->staged.tl_nodes * 64 + 16 + (size_t)(c->staged.stack_rows + 1) * c->staged_threads * 4 + (c->staged.ray_tma ? (size_t)(c->staged_threads / 32) * (1024 + 8) : 0);
+}
 static int staged_grid(const ctl_ctx* c) {
     const size_t smem = staged_smem_bytes(c);
     int per_sm = c->staged_resident / c->staged_threads;
@@ -31,10 +33,15 @@ static int staged_grid(const ctl_ctx* c) {
 }
 template <int MODE, bool ANY_HIT, bool COUNT>
 static void launch_staged(const ctl_ctx* c, cudaStream_t st, const float4* rays, const unsigned* n_ptr, const unsigned* n2_ptr, int n_fixed, unsigned* work, const TravOut& out, unsigned long long* visit) {
-    static size_t attr_set = 0; // per instantiation
+    static size_t attr_set[2] = {0, 0}; // per instantiation
     const size_t smem = staged_smem_bytes(c);
-    if (smem > attr_set) { cudaFuncSetAttribute(k_intersect_staged<MODE, ANY_HIT, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = smem; }
-    k_intersect_staged<MODE, ANY_HIT, COUNT><<<staged_grid(c), c->staged_threads, smem, st>>>(c->scene, c->staged, c->tune, rays, n_ptr, n2_ptr, n_fixed, work, out, visit);
+    if (c->staged.ray_tma) {
+        if (smem > attr_set[1]) { cudaFuncSetAttribute(k_intersect_staged<MODE, ANY_HIT, COUNT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[1] = smem; }
+        k_intersect_staged<MODE, ANY_HIT, COUNT, true><<<staged_grid(c), c->staged_threads, smem, st>>>(c->scene, c->staged, c->tune, rays, n_ptr, n2_ptr, n_fixed, work, out, visit);
+    } else {
+        if (smem > attr_set[0]) { cudaFuncSetAttribute(k_intersect_staged<MODE, ANY_HIT, COUNT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[0] = smem; }
+        k_intersect_staged<MODE, ANY_HIT, COUNT, false><<<staged_grid(c), c->staged_threads, smem, st>>>(c->scene, c->staged, c->tune, rays, n_ptr, n2_ptr, n_fixed, work, out, visit);
+    }
 }
 
 // "TraversalKernel": 0 = persistent phase-scheduled kernel, 1 = simple ray-batch kernel (A/B baseline), 2 = persistent kernel with shared-memory staging
@@ -142,6 +149,7 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "TraversalKernel") { if (v < 0 || v > 2) return set_err("TraversalKernel must be 0 (persistent), 1 (ray batch) or 2 (staged)"); c->trav_kernel = v; }
     else if (k == "StagedThreads") { if (v < 32 || v > 1024 || (v & 31)) return set_err("StagedThreads must be a multiple of 32 in [32,1024]"); c->staged_threads = v; }
     else if (k == "StagedResidentThreads") { if (v < 32 || v > 2048) return set_err("StagedResidentThreads out of range [32,2048]"); c->staged_resident = v; }
+    else if (k == "StagedRayTMA") c->staged.ray_tma = v != 0;   // ray-queue chunks through TMA bulk copies into per-warp shared-memory buffers
     else if (k == "StagedStackRows") { if (v < 0 || v > TP_STACK) return set_err("StagedStackRows out of range [0,64]"); c->staged_rows = v; c->staged.stack_rows = v; }
     else if (k == "StagedTreeletNodes") { if (v < 0 || v > 2048) return set_err("StagedTreeletNodes out of range [0,2048]"); c->staged_treelet = v; }   // takes effect at the next ctl_upload_scene / ctl_update_scene_nodes
     else if (k == "TravThT") c->tune.th_t = c->tune_p.th_t = v; else if (k == "TravThL") c->tune.th_l = c->tune_p.th_l = v; else if (k == "TravThF") c->tune.th_f = c->tune_p.th_f = v;
@@ -165,6 +173,7 @@ int ctl_get_param_i(ctl_ctx* c, const char* key, int* v) {
     else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables; else if (k == "FuseTraversal") *v = c->fuse_traversal; else if (k == "PixelVarianceBuffer") *v = c->variance_buffer; else if (k == "PassStride") *v = c->pass_stride; else if (k == "PassPhase") *v = c->pass_phase;
     else if (k == "TraversalBlocksPerSM") *v = c->trav_blocks_per_sm; else if (k == "StagedThreads") *v = c->staged_threads; else if (k == "StagedStackRows") *v = c->staged_rows;
     else if (k == "ShadeMode") *v = c->shade_mode; else if (k == "MaterialClassMask") *v = (int)c->class_mask;
+    else if (k == "StagedRayTMA") *v = c->staged.ray_tma;
     else if (k == "StagedTreeletNodes") *v = c->staged.tl_nodes; else if (k == "StagedUsable") *v = c->staged_ok ? 1 : 0; else return set_err("unknown parameter key: " + k);
     return 0;
 }

@@ -28,6 +28,7 @@ struct StagedScene {
     int tl_nodes;            // 0 = no treelet
     int scene_root;          // node address the scene-level walk starts at: the view's start node, or a treelet address
     int stack_rows;          // stack entries per lane kept in shared memory
+    int ray_tma;             // 1: ray-queue chunks reach the warp through TMA bulk copies into a per-warp shared-memory buffer (k_intersect_staged<.., RT = true>)
 };
 constexpr int ST_TL = 1;       // node address bit 0: treelet node, slot = address >> 2 (ordinary addresses are float4 units, multiples of 4)
 constexpr int ST_NEEDS_W = 2;  // root word bit 1: the instance's inverse transform has a projective last row -> divide by w like xf_point
@@ -60,9 +61,45 @@ CTL_DEV void tma_fill(void* dst_smem, const void* src_gmem, uint32_t bytes, void
 #endif
 }
 
-template <int MODE, bool ANY_HIT, bool COUNT>
+// Per-warp mbarrier helpers of the ray-queue staging (RT): the barrier is initialised with one arrival; every refill adds its bytes with expect_tx,
+// issues the bulk copies and arrives once, so a phase completes exactly when all bytes of that refill have landed.
+CTL_DEV void mbar_init1(uint32_t bar) {
+#ifdef __CUDACC__
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+}
+CTL_DEV void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+#ifdef __CUDACC__
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+#endif
+}
+CTL_DEV void mbar_arrive(uint32_t bar) {
+#ifdef __CUDACC__
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+#endif
+}
+CTL_DEV bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done = 1;
+#ifdef __CUDACC__
+    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+#endif
+    return done != 0;
+}
+CTL_DEV void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+#ifdef __CUDACC__
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+#endif
+}
+
+// RT: ray-queue staging.  A refill claims consecutive queue entries, so the rays of the lanes it feeds are one contiguous block (two when the claim
+// crosses the extension / shadow queue boundary of a fused launch): lane 0 sends it with cp.async.bulk into the warp's 1 KB buffer and the lanes pick
+// their ray up on the first iteration after the bytes have landed -- the DRAM latency of the queue read is hidden behind the node steps of the
+// warp's other lanes instead of stalling all 32 at the first use.
+template <int MODE, bool ANY_HIT, bool COUNT, bool RT>
 __device__ __forceinline__ void trace_staged(const DScene& S, const StagedScene& SS, const float4* __restrict__ rays, int n, unsigned* work_ctr, const TravOut& out,
-                                             const TravTune& tune, VisitCounters<COUNT>& cnt, const float4* __restrict__ tl, int* __restrict__ ss, const int NT) {
+                                             const TravTune& tune, VisitCounters<COUNT>& cnt, const float4* __restrict__ tl, int* __restrict__ ss, const int NT,
+                                             const float4* wbuf /* RT: this warp's 32-ray buffer */, const uint32_t wbar /* RT: this warp's mbarrier (shared address) */) {
     const int TH_T = tune.th_t, TH_L = tune.th_l, TH_F = tune.th_f, N_STEPS = tune.th_n_exit > 0 ? tune.th_n_exit : 1, T_STEPS = tune.t_steps > 0 ? tune.t_steps : 1;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -90,17 +127,43 @@ __device__ __forceinline__ void trace_staged(const DScene& S, const StagedScene&
     int pool_next = 0, pool_end = 0;
     bool exhausted = (n <= 0);
 
+    int pend_slot = -1;             // RT: >= 0 while this lane's ray is on its way into the warp buffer (the lane idles in state 3)
+    uint32_t wphase = 0;            // RT: parity of the warp barrier's current phase (warp-uniform)
+
+    auto start_ray = [&](const float4 ro, const float4 rd) { // a fetched ray enters the scene level
+        ox = ro.x; oy = ro.y; oz = ro.z; dx = rd.x; dy = rd.y; dz = rd.z;
+        hit.u = hit.v = 0.0f; hit.tri = 0xffffffffu; hit.node = 0xffffffffu;
+        if (MODE == 3) { tri_lo = S.ray_eps; box_lo = 0.0f; hit.dist = FLT_MAX; }
+        else if (MODE == 2 || MODE == 5) { tri_lo = ro.w; box_lo = ro.w; hit.dist = rd.w; }
+        else { tri_lo = ro.w; box_lo = 0.0f; hit.dist = rd.w; }
+        sp = 0; tos = SENT;
+        inst = -1; nbase = S.scene_nodes;
+        nodeAddr = S.n_nodes ? SS.scene_root : SENT;
+        if (nodeAddr >= 0) {
+            idx = guard_inv(dx); idy = guard_inv(dy); idz = guard_inv(dz);
+            oodx = ox * idx; oody = oy * idy; oodz = oz * idz;
+        }
+    };
+
     int state = 3;
     auto classify = [&]() { state = ((unsigned)nodeAddr < (unsigned)SENT) ? 0 : (nodeAddr < 0 ? (inst >= 0 ? 1 : 2) : (inst >= 0 ? 2 : 3)); };
 
     for (;;) {
+        unsigned mPend = 0;
+        if (RT) { // rays on their way: have the bytes landed?  (one test per iteration, warp-uniform)
+            mPend = __ballot_sync(0xffffffffu, pend_slot >= 0);
+            if (mPend && mbar_test(wbar, wphase)) {
+                wphase ^= 1u; mPend = 0u;
+                if (pend_slot >= 0) { start_ray(wbuf[2 * pend_slot], wbuf[2 * pend_slot + 1]); classify(); pend_slot = -1; }
+            }
+        }
         const unsigned b0 = __ballot_sync(0xffffffffu, state & 1), b1 = __ballot_sync(0xffffffffu, state & 2);
         const unsigned mNT = ~b1;
-        const unsigned mF = b0 & b1, mL = b1 & ~b0;
+        const unsigned mF = b0 & b1 & ~mPend, mL = b1 & ~b0;
         bool runF = false, runL = false;
         if (b1) {
             const int nF = exhausted ? __popc(mF & __ballot_sync(0xffffffffu, ray_i >= 0)) : __popc(mF);
-            if (mNT == 0u && mL == 0u && nF == 0) break;
+            if (mNT == 0u && mL == 0u && nF == 0 && mPend == 0u) break;
             runF = nF >= TH_F || (mNT == 0u && mL == 0u);
             runL = mL != 0u && (__popc(mL) >= TH_L || mNT == 0u);
         }
@@ -108,7 +171,7 @@ __device__ __forceinline__ void trace_staged(const DScene& S, const StagedScene&
         // ---- F: write finished results, fetch new rays
         if (runF) {
             if ((MODE == 0 || MODE == 4) && out.cls_hist) { // class histogram of this bounce's hit records (the shade stage runs one launch per material class)
-                const bool wr = state == 3 && ray_i >= 0 && !(MODE == 4 && lane_any);
+                const bool wr = state == 3 && ray_i >= 0 && !(MODE == 4 && lane_any) && (!RT || pend_slot < 0);
                 const unsigned mw = __ballot_sync(0xffffffffu, wr);
                 if (wr) {
                     const unsigned cls = hit.tri >> TRI_CLS_SHIFT; // 7 = miss
@@ -116,7 +179,7 @@ __device__ __forceinline__ void trace_staged(const DScene& S, const StagedScene&
                     if (lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(out.cls_hist + cls, (unsigned)__popc(peers));
                 }
             }
-            if (state == 3 && ray_i >= 0) {
+            if (state == 3 && ray_i >= 0 && (!RT || pend_slot < 0)) {
                 const int i = ray_i;
                 if (MODE == 0 || (MODE == 4 && !lane_any)) {
                     out.hit_a[i] = make_float4(hit.dist, hit.u, hit.v, __uint_as_float(hit.tri)); // tri word keeps the class bits: k_shade strips them
@@ -143,7 +206,7 @@ __device__ __forceinline__ void trace_staged(const DScene& S, const StagedScene&
                 }
                 ray_i = -1;
             }
-            if (!exhausted) {
+            if (!exhausted && (!RT || mPend == 0u)) { // RT: one refill in flight per warp (single buffer)
                 const unsigned mFree = mF;
                 int need = __popc(mFree);
                 const int my_rank = __popc(mFree & lt_mask);
@@ -159,28 +222,25 @@ __device__ __forceinline__ void trace_staged(const DScene& S, const StagedScene&
                     }
                     const int take = min(need, pool_end - pool_next);
                     const int r = my_rank - got_before;
+                    if (RT && lane == 0) { // the block [pool_next, pool_next + take) of the queue(s) -> warp buffer slots [got_before, got_before + take)
+                        int a = pool_next, cnt_a = take, cnt_b = 0;
+                        if (MODE == 4 || MODE == 5) { if (a >= out.n_ext) { cnt_b = take; cnt_a = 0; } else if (a + take > out.n_ext) { cnt_a = out.n_ext - a; cnt_b = take - cnt_a; } }
+                        const uint32_t dst = smem_u32(wbuf) + (uint32_t)got_before * 32u;
+                        mbar_expect_tx(wbar, (uint32_t)take * 32u);
+                        if (cnt_a) bulk_g2s(dst, rays + 2 * (size_t)a, (uint32_t)cnt_a * 32u, wbar);
+                        if (cnt_b) bulk_g2s(dst + (uint32_t)cnt_a * 32u, out.sh_rays + 2 * (size_t)(a + cnt_a - out.n_ext), (uint32_t)cnt_b * 32u, wbar);
+                    }
                     if (is_free && r >= 0 && r < take) {
                         int i = pool_next + r;
                         const float4* q = rays;
                         if (MODE == 4 || MODE == 5) { lane_any = i >= out.n_ext; if (lane_any) { i -= out.n_ext; q = out.sh_rays; } }
-                        const float4 ro = ldg_stream(q + 2 * i), rd = ldg_stream(q + 2 * i + 1);
                         ray_i = i;
-                        ox = ro.x; oy = ro.y; oz = ro.z; dx = rd.x; dy = rd.y; dz = rd.z;
-                        hit.u = hit.v = 0.0f; hit.tri = 0xffffffffu; hit.node = 0xffffffffu;
-                        if (MODE == 3) { tri_lo = S.ray_eps; box_lo = 0.0f; hit.dist = FLT_MAX; }
-                        else if (MODE == 2 || MODE == 5) { tri_lo = ro.w; box_lo = ro.w; hit.dist = rd.w; }
-                        else { tri_lo = ro.w; box_lo = 0.0f; hit.dist = rd.w; }
-                        sp = 0; tos = SENT;
-                        inst = -1; nbase = S.scene_nodes;
-                        nodeAddr = S.n_nodes ? SS.scene_root : SENT;
-                        if (nodeAddr >= 0) {
-                            idx = guard_inv(dx); idy = guard_inv(dy); idz = guard_inv(dz);
-                            oodx = ox * idx; oody = oy * idy; oodz = oz * idz;
-                        }
-                        classify();
+                        if (RT) pend_slot = my_rank; // == got_before + r: picked up when the refill's bytes have landed; the lane idles in state 3 until then
+                        else { start_ray(ldg_stream(q + 2 * i), ldg_stream(q + 2 * i + 1)); classify(); }
                     }
                     pool_next += take; need -= take; got_before += take;
                 }
+                if (RT && got_before > 0 && lane == 0) mbar_arrive(wbar); // closes the refill: the phase completes when its bytes are in
             }
         }
 
@@ -283,7 +343,7 @@ __device__ __forceinline__ void trace_staged(const DScene& S, const StagedScene&
 }
 
 // Shared-memory layout of one CTA: [treelet image: tl_nodes * 64 B][mbarrier: 16 B][stack: (stack_rows + 1) rows x blockDim ints]
-CTL_DEV size_t staged_smem_bytes_dev(const StagedScene& SS, int nt) { return (size_t)SS.tl_nodes * 64 + 16 + (size_t)(SS.stack_rows + 1) * nt * 4; }
+//                                  [RT: ray buffers, 1 KB per warp][RT: mbarriers, 8 B per warp]
 
 #ifndef CTL_STAGED_MAX_THREADS
 #define CTL_STAGED_MAX_THREADS 1024 // <= 64 registers per thread, so that any block size up to 1024 keeps 1024 threads per SM resident
@@ -293,7 +353,7 @@ CTL_DEV size_t staged_smem_bytes_dev(const StagedScene& SS, int nt) { return (si
 #endif
 
 // MODEs as k_intersect (wavefront.cuh).  MODE 4 / 5 (fused launches) take their second queue through `out`.
-template <int MODE, bool ANY_HIT, bool COUNT>
+template <int MODE, bool ANY_HIT, bool COUNT, bool RT>
 __global__ void __launch_bounds__(CTL_STAGED_MAX_THREADS, CTL_STAGED_MIN_BLOCKS) k_intersect_staged(const __grid_constant__ DScene S, const __grid_constant__ StagedScene SS, const __grid_constant__ TravTune tune,
         const float4* __restrict__ rays, const unsigned* __restrict__ n_ptr, const unsigned* __restrict__ n2_ptr, int n_fixed, unsigned* work_ctr,
         const __grid_constant__ TravOut out_in, unsigned long long* visit_out) {
@@ -302,12 +362,22 @@ __global__ void __launch_bounds__(CTL_STAGED_MAX_THREADS, CTL_STAGED_MIN_BLOCKS)
     const float4* tl = (const float4*)staged_smem;
     unsigned char* bar = staged_smem + (size_t)SS.tl_nodes * 64;
     int* ss = (int*)(bar + 16) + threadIdx.x;
+    // RT: after the stack rows, one 1 KB ray buffer per warp, then one 8-byte mbarrier per warp
+    const float4* wbuf = nullptr; uint32_t wbar = 0;
+    if (RT) {
+        unsigned char* rb = bar + 16 + (size_t)(SS.stack_rows + 1) * NT * 4;
+        const int warp = (int)(threadIdx.x >> 5);
+        wbuf = (const float4*)(rb + (size_t)warp * 1024);
+        wbar = smem_u32(rb + (size_t)(NT >> 5) * 1024 + (size_t)warp * 8);
+        if ((threadIdx.x & 31) == 0) mbar_init1(wbar);
+        __syncwarp();
+    }
     if (SS.tl_nodes) tma_fill(staged_smem, SS.treelet, (uint32_t)SS.tl_nodes * 64u, bar);
     TravOut out = out_in;
     int n = n_ptr ? (int)*n_ptr : n_fixed;
     if (MODE == 4 || MODE == 5) { out.n_ext = n; n += (int)*n2_ptr; }
     VisitCounters<COUNT> cnt;
-    trace_staged<MODE, ANY_HIT, COUNT>(S, SS, rays, n, work_ctr, out, tune, cnt, tl, ss, NT);
+    trace_staged<MODE, ANY_HIT, COUNT, RT>(S, SS, rays, n, work_ctr, out, tune, cnt, tl, ss, NT, wbuf, wbar);
     if (COUNT) {
         VisitCounters<true>& c = (VisitCounters<true>&)cnt;
         unsigned a = c.inner, b = c.tris, e = c.inst;

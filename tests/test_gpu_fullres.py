@@ -29,7 +29,8 @@ def test_full_resolution_windows_match_oracle(built_lib, orc, kind):
     t.DoPasses(SPP, new_trace=True); t.synchronize()             # == bench.py's frame at N = 1: ctl_render_passes_tiled(8 passes, 64x64 tiles, part 0 of 1)
     img = t.readAccumulator(); rays_stop = t.getRaysInLastPass()
     assert t.getNumPassesDone() == SPP
-    assert img["weight_sum"].sum() == SPP * W * H                # every path of every pass landed (a jittered sample may round into the neighbouring pixel)
+    landed = float(img["weight_sum"].astype(np.float64).sum())
+    assert SPP * W * H - 64 <= landed <= SPP * W * H             # every path of every pass landed (a jittered sample may round into the next pixel; past the image edge it is dropped, Image.cu:22-44)
     # the same frame with the reference's ray definition
     t.setParameter("StopZeroThroughput", 0)
     t.DoPasses(SPP, new_trace=True); t.synchronize()

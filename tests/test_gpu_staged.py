@@ -135,3 +135,40 @@ def test_per_class_shade_launches_equal_the_run_time_dispatch(built_lib, kind, w
     t.DoPasses(4, new_trace=True); t.synchronize(); b = t.readAccumulator()
     assert ra == t.getRaysInLastPass() and np.array_equal(a["weight_sum"], b["weight_sum"]) and np.allclose(a["rgb"], b["rgb"], rtol=1e-5, atol=1e-7)
     t.close()
+
+
+@pytest.mark.parametrize("kind,n", [("cornell", 3000), ("cornell7", 5000), ("soup", 5000), ("c2", 20000), ("c4", 6000)])
+def test_ray_queue_staging_through_tma_is_exact(built_lib, orc, kind, n):
+    """StagedRayTMA=1: refills reach the warp as cp.async.bulk copies into its shared-memory buffer (per-warp mbarrier).  Same rays, same results:
+    API queries against the oracle (ragged sizes: the last refill is a partial block), rendered frames against the direct-load kernel (fused launches:
+    a refill may cross the extension / shadow queue boundary)."""
+    s, t = make(kind, 96, 64, 8)
+    t.setParameter("StagedRayTMA", 1)
+    assert t.getParameter("StagedRayTMA") == 1
+    for threads in (512, 64, 1024):
+        t.setParameter("StagedThreads", threads)
+        for m in (n, 1, 33, 1000 + threads // 7):
+            rays = random_rays(s, m, seed=m)
+            g, gc = t.trace_rays(rays, counts=True); o, oc = orc.trace_rays(s.view, rays, counts=True)
+            assert g.tobytes() == o.tobytes() and gc == oc, (threads, m)
+        diag = float(np.linalg.norm(np.array(list(s.view.box_max)) - np.array(list(s.view.box_min))))
+        seg = random_rays(s, 4099, seed=9, tmin=1e-3 * diag, tmax=0.4 * diag)
+        assert np.array_equal(t.intersect(seg), orc.intersect(s.view, seg))
+        assert np.array_equal(t.intersect(seg, any_hit=True)["tri_idx"] >= 0, orc.intersect(s.view, seg, any_hit=True)["tri_idx"] >= 0)
+    t.setParameter("StagedThreads", 512)
+    t.setParameter("StagedRayTMA", 0)
+    t.DoPasses(3, new_trace=True); t.synchronize(); ref = t.readAccumulator(); ref_rays = t.getRaysInLastPass(); ref_q = t.queueSizes(8)
+    t.setParameter("StagedRayTMA", 1)
+    for fuse in (1, 0):
+        t.setParameter("FuseTraversal", fuse)
+        t.DoPasses(3, new_trace=True); t.synchronize(); img = t.readAccumulator()
+        assert np.array_equal(img["weight_sum"], ref["weight_sum"]) and np.allclose(img["rgb"], ref["rgb"], rtol=1e-5, atol=1e-7), fuse
+        assert t.getRaysInLastPass() == ref_rays
+        q = t.queueSizes(8)
+        assert np.array_equal(q[0], ref_q[0]) and np.array_equal(q[1], ref_q[1])
+    t.close()
+    w = ctl.WavefrontPathTracer(64, 64); w.InitializeScene(ctl.Scene("cornell7", 64, 64)); w.setParameter("MaxPathLength", 6)
+    w.DoPass(True); w.synchronize(); a = w.readAccumulator()
+    w.setParameter("StagedRayTMA", 1); w.DoPass(True); w.synchronize(); b = w.readAccumulator()
+    assert np.array_equal(a["weight_sum"], b["weight_sum"]) and np.allclose(a["rgb"], b["rgb"], rtol=1e-6, atol=0)
+    w.close()
