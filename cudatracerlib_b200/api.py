@@ -147,6 +147,7 @@ def lib():
     L.ctl_render_pass.argtypes = [vp, i32, i32, i32, i32, i32]
     L.ctl_render_pass_tiled.argtypes = [vp, i32, i32, i32, i32, i32]
     L.ctl_render_passes_tiled.argtypes = [vp, i32, i32, i32, i32, i32, i32]
+    L.ctl_render_frame_tiled.argtypes = [vp, i32, i32, i32, i32, i32, i32]
     L.ctl_wavefront_pass.argtypes = [vp, i32]
     L.ctl_read_sample_tables.argtypes = [vp, i32, vp, vp]
     L.ctl_synchronize.argtypes = [vp]
@@ -336,6 +337,10 @@ class PathTracer:
         """n_passes DoPass calls fused into one wavefront (ctl_render_passes_tiled); part/n_parts select interleaved tiles."""
         nt = self._new_trace if new_trace is None else bool(new_trace)
         _check(lib().ctl_render_passes_tiled(self._ctx, int(nt), int(n_passes), tile[0], tile[1], part, n_parts)); self._new_trace = False
+
+    def DoFrame(self, spp, batch=8, tile=(64, 64), part=0, n_parts=1):
+        """ctl_render_frame_tiled: a new trace of spp passes, `batch` per wavefront, the wavefronts overlapped on two streams ("OverlapWavefronts")."""
+        _check(lib().ctl_render_frame_tiled(self._ctx, spp, batch, tile[0], tile[1], part, n_parts)); self._new_trace = False
 
     def readSampleTables(self, table_set=0):
         d1 = np.zeros(4096 * 30, np.float32); d2 = np.zeros(4096 * 30 * 2, np.float32)

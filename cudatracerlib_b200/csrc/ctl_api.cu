@@ -80,7 +80,7 @@ static int init_ctx(ctl_ctx* c) { // everything of ctl_create that can fail afte
         CK(c->d_states0.upload(st0.data(), st0.size())); CK(c->d_states.upload(st0.data(), st0.size()));
         CK(c->d_jump.upload(&J.row[0][0], 160 * 5));
     }
-    CK(c->counters.ensure(CTR_TOTAL)); CK(c->api_work.ensure(API_WORK_RING)); CK(c->stats.ensure(16)); CK(c->d_captured_n.ensure(1));
+    CK(c->lanes[0].counters.ensure(CTR_TOTAL)); CK(c->api_work.ensure(API_WORK_RING)); CK(c->stats.ensure(16)); CK(c->d_captured_n.ensure(1));
     CK(cudaMemset(c->stats.p, 0, 16 * sizeof(unsigned long long)));
     return alloc_image(c);
 }
@@ -107,8 +107,10 @@ void ctl_destroy(ctl_ctx* c) {
     c->d_light_cdf.release(); c->d_normal_lut.release(); c->d_tri64.release(); c->d_inst.release(); c->d_treelet.release();
     c->d_tab1.release(); c->d_tab2.release(); c->d_states.release(); c->d_states0.release(); c->d_jump.release();
     if (c->h_tab1) cudaFreeHost(c->h_tab1); if (c->h_tab2) cudaFreeHost(c->h_tab2); if (c->h_tab_free) cudaEventDestroy(c->h_tab_free);
-    c->wo_prev.release(); c->cf.release(); c->cl.release(); c->nor.release(); c->px.release(); c->rays_a.release(); c->rays_b.release(); c->hit_a.release(); c->sh_rays.release();
-    c->sh_payload.release(); c->capture.release(); c->path_a.release(); c->path_b.release(); c->path_c.release(); c->rays_c.release(); c->sort_keys.release(); c->sort_hist.release(); c->sort_offsets.release(); c->mat_hist.release(); c->mat_cls.release(); c->mat_order.release(); c->hit_node.release(); c->counters.release(); c->api_work.release(); c->stats.release();
+    for (int k = 1; k < MAX_LANES; k++) { if (c->lane_stream[k]) { cudaStreamSynchronize(c->lane_stream[k]); cudaStreamDestroy(c->lane_stream[k]); } if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (int k = 0; k < MAX_LANES; k++) c->lanes[k].release();
+    c->capture.release(); c->api_work.release(); c->stats.release();
     c->own_accum.release(); c->d_captured_n.release(); c->resolve_tmp.release(); c->pipe_rgbe.release(); c->pipe_partial.release(); c->pipe_lum.release(); c->d_var.release(); c->nlm_cached.release(); c->nlm_varh.release(); c->nlm_weights.release(); c->nlm_last_update = -1; c->nlm_pixels = 0; c->d_node_alias.release();
     c->w_thr.release(); c->w_lxy.release(); c->w_df.release(); c->w_ray.release(); c->w_misc.release(); c->w_res.release(); c->w_desc.release();
     for (int k = 0; k < 2; k++) { c->w_sec[k].release(); c->w_sres[k].release(); }
@@ -142,6 +144,8 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "CaptureBounce") c->capture_bounce = v;
     else if (k == "DeviceSampleTables") c->device_tables = v != 0;
     else if (k == "FuseTraversal") c->fuse_traversal = v != 0;
+    else if (k == "OverlapWavefronts") c->overlap = v != 0;
+    else if (k == "OverlapLanes") { if (v < 1 || v > MAX_LANES) return set_err("OverlapLanes out of range [1,4]"); c->n_lanes = v; }   // wavefronts of a frame in flight at once   // ctl_render_frame_tiled / ctl_comm_render_frame: the frame's wavefronts alternate between two streams
     else if (k == "PixelVarianceBuffer") c->variance_buffer = v != 0;
     else if (k == "WarpPixelBlocks") c->warp_blocks = v != 0;
     else if (k == "PassStride") { if (v < 1) return set_err("PassStride must be >= 1"); c->pass_stride = v; }   // multi-GPU by pass: this context renders passes PassPhase + k * PassStride
@@ -170,7 +174,7 @@ int ctl_get_param_i(ctl_ctx* c, const char* key, int* v) {
     std::string k(key);
     if (k == "MaxPathLength") *v = c->max_path_length; else if (k == "RRStartDepth") *v = c->rr_start; else if (k == "Direct") *v = c->direct;
     else if (k == "StopZeroThroughput") *v = c->stop_zero; else if (k == "Regularization") *v = c->regularization; else if (k == "SortMode") *v = c->sort_mode; else if (k == "StageTimers") *v = c->stage_timers;
-    else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables; else if (k == "FuseTraversal") *v = c->fuse_traversal; else if (k == "PixelVarianceBuffer") *v = c->variance_buffer; else if (k == "PassStride") *v = c->pass_stride; else if (k == "PassPhase") *v = c->pass_phase;
+    else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables; else if (k == "FuseTraversal") *v = c->fuse_traversal; else if (k == "OverlapWavefronts") *v = c->overlap; else if (k == "OverlapLanes") *v = c->n_lanes; else if (k == "PixelVarianceBuffer") *v = c->variance_buffer; else if (k == "PassStride") *v = c->pass_stride; else if (k == "PassPhase") *v = c->pass_phase;
     else if (k == "TraversalBlocksPerSM") *v = c->trav_blocks_per_sm; else if (k == "StagedThreads") *v = c->staged_threads; else if (k == "StagedStackRows") *v = c->staged_rows;
     else if (k == "ShadeMode") *v = c->shade_mode; else if (k == "MaterialClassMask") *v = (int)c->class_mask;
     else if (k == "StagedRayTMA") *v = c->staged.ray_tma;
@@ -388,22 +392,23 @@ int ctl_trace_rays_host(ctl_ctx* c, int n, const ctl_traversal_ray* rays, ctl_tr
 }
 
 // ------------------------------------------------------------------ render pass
-static int ensure_state(ctl_ctx* c, size_t n) {
-    CK(c->cf.ensure(n)); CK(c->cl.ensure(n)); CK(c->nor.ensure(n)); CK(c->px.ensure(n));
-    CK(c->rays_a.ensure(2 * n)); CK(c->rays_b.ensure(2 * n)); CK(c->hit_a.ensure(n)); CK(c->hit_node.ensure(n));
-    CK(c->sh_rays.ensure(2 * n)); CK(c->sh_payload.ensure(n)); CK(c->path_a.ensure(n)); CK(c->path_b.ensure(n));
-    if (!c->stop_zero) CK(c->wo_prev.ensure(n));
-    if (c->sort_mode == 2) CK(c->mat_cls.ensure(n));
-    if (c->sort_mode == 2 || c->shade_mode == 1) { CK(c->mat_order.ensure(n)); CK(c->mat_hist.ensure(2 * MAT_CLASSES * (MAX_BOUNCES + 1))); }
+static int ensure_state(ctl_ctx* c, WaveLane& L, size_t n, cudaStream_t s) {
+    CK(L.cf.ensure(n)); CK(L.cl.ensure(n)); CK(L.nor.ensure(n)); CK(L.px.ensure(n));
+    CK(L.rays_a.ensure(2 * n)); CK(L.rays_b.ensure(2 * n)); CK(L.hit_a.ensure(n)); CK(L.hit_node.ensure(n));
+    CK(L.sh_rays.ensure(2 * n)); CK(L.sh_payload.ensure(n)); CK(L.path_a.ensure(n)); CK(L.path_b.ensure(n));
+    if (!c->stop_zero) CK(L.wo_prev.ensure(n));
+    if (c->sort_mode == 2) CK(L.mat_cls.ensure(n));
+    if (c->sort_mode == 2 || c->shade_mode == 1) { CK(L.mat_order.ensure(n)); CK(L.mat_hist.ensure(2 * MAT_CLASSES * (MAX_BOUNCES + 1))); }
     if (c->sort_mode == 1) {
-        CK(c->rays_c.ensure(2 * n)); CK(c->path_c.ensure(n)); CK(c->sort_keys.ensure(n));
-        if (!c->sort_hist.p) { CK(c->sort_hist.ensure(SORT_BUCKETS)); CK(c->sort_offsets.ensure(SORT_BUCKETS)); CK(cudaMemsetAsync(c->sort_hist.p, 0, SORT_BUCKETS * sizeof(unsigned), c->stream)); }
+        CK(L.rays_c.ensure(2 * n)); CK(L.path_c.ensure(n)); CK(L.sort_keys.ensure(n));
+        if (!L.sort_hist.p) { CK(L.sort_hist.ensure(SORT_BUCKETS)); CK(L.sort_offsets.ensure(SORT_BUCKETS)); CK(cudaMemsetAsync(L.sort_hist.p, 0, SORT_BUCKETS * sizeof(unsigned), s)); }
     }
+    CK(L.counters.ensure(CTR_TOTAL));
     return 0;
 }
 
 static void stage_mark(ctl_ctx* c, int kind) {
-    if (!c->stage_timers) return;
+    if (!c->stage_timers) return;   // (never on together with OverlapWavefronts lanes: see ctl_render_frame_tiled)
     size_t i = c->stage_kind.size();
     if (i >= c->stage_ev.size()) { cudaEvent_t e; cudaEventCreate(&e); c->stage_ev.push_back(e); }
     cudaEventRecord(c->stage_ev[i], c->stream);
@@ -411,113 +416,121 @@ static void stage_mark(ctl_ctx* c, int kind) {
 }
 
 
-static int render_window(ctl_ctx* c, int new_trace, const Window& W) {
+// lane / framed: ctl_comm_render_frame with "OverlapWavefronts" renders the wavefronts of a frame alternately on two lanes (two streams, two sets of
+// wavefront buffers) so that the tail of one persistent traversal launch is filled by the head of the other lane's; a framed call leaves the
+// accumulator clear, the sample tables (W.tab0) and the timing events to the frame.
+static int render_window(ctl_ctx* c, int new_trace, const Window& W, int lane = 0, bool framed = false) {
+    WaveLane& L = c->lanes[lane];
+    const cudaStream_t s = lane ? c->lane_stream[lane] : c->stream;
     if (!c->has_scene) return set_err("no scene uploaded");
     if (c->variance_buffer && (W.n_passes != 1 || W.mode != 0 || W.n_slots != c->w * c->h))
         return set_err("PixelVarianceBuffer=1 needs whole-image single-pass renders (ctl_render_pass with the full window, ctl_wavefront_pass)");
     if (W.n_slots <= 0) return 0;
     CK(cudaSetDevice(c->device));
-    CK(cudaEventRecord(c->ev_start, c->stream));
-    if (new_trace) {
-        CK(cudaMemsetAsync(c->accum, 0, (size_t)c->w * c->h * 7 * sizeof(float), c->stream));
-        c->passes_done = 0;
+    if (!framed) {
+        CK(cudaEventRecord(c->ev_start, s));
+        if (new_trace) {
+            CK(cudaMemsetAsync(c->accum, 0, (size_t)c->w * c->h * 7 * sizeof(float), s));
+            c->passes_done = 0;
+        }
+        // sample tables of these passes: caller-supplied (single pass), generated on the device, or host XORWOW + H2D
+        if (c->user_tables) { if (W.n_passes != 1) return set_err("caller-supplied sample tables cover exactly one pass"); }
+        else if (generate_tables(c, c->passes_done, W.n_passes)) return 1;
+        c->user_tables = false;
     }
-    // sample tables of these passes: caller-supplied (single pass), generated on the device, or host XORWOW + H2D
-    if (c->user_tables) { if (W.n_passes != 1) return set_err("caller-supplied sample tables cover exactly one pass"); }
-    else if (generate_tables(c, c->passes_done, W.n_passes)) return 1;
-    c->user_tables = false;
     c->scene.d1 = c->d_tab1.p; c->scene.d2 = (const float2*)c->d_tab2.p;
     c->scene.img_w = c->w; c->scene.img_h = c->h;
     const size_t n_paths = (size_t)W.n_slots * W.n_passes;
-    if (ensure_state(c, n_paths)) return 1;
+    if (ensure_state(c, L, n_paths, s)) return 1;
     if (c->capture_bounce > 0) CK(c->capture.ensure(2 * n_paths));
 
     c->stage_kind.clear();
-    CK(cudaMemsetAsync(c->counters.p, 0, CTR_TOTAL * sizeof(unsigned), c->stream));
+    CK(cudaMemsetAsync(L.counters.p, 0, CTR_TOTAL * sizeof(unsigned), s));
     // per-class shade launches: the staged kernel tags every hit with its material class; one launch per class present (a sort pass only when there are several)
     const bool by_class = c->shade_mode == 1 && c->sort_mode != 2 && c->trav_kernel == 2 && c->staged_ok && c->class_ok && c->class_mask != 0;
     int n_classes = 0, single_cls = -1;
     for (int k = 0; k < 4; k++) if (c->class_mask & (1u << k)) { n_classes++; single_cls = k; }
     const bool class_sort = by_class && n_classes > 1;
-    if (c->sort_mode == 2 || class_sort) CK(cudaMemsetAsync(c->mat_hist.p, 0, 2 * MAT_CLASSES * (MAX_BOUNCES + 1) * sizeof(unsigned), c->stream));
-    if (c->instrumented) CK(cudaMemsetAsync(c->stats.p + 2, 0, 8 * sizeof(unsigned long long), c->stream));
-    unsigned* ctr = c->counters.p;
-    PathState st = {c->cf.p, c->cl.p, c->nor.p, c->px.p, c->stop_zero ? nullptr : c->wo_prev.p};
+    if (c->sort_mode == 2 || class_sort) CK(cudaMemsetAsync(L.mat_hist.p, 0, 2 * MAT_CLASSES * (MAX_BOUNCES + 1) * sizeof(unsigned), s));
+    if (c->instrumented) CK(cudaMemsetAsync(c->stats.p + 2, 0, 8 * sizeof(unsigned long long), s));
+    unsigned* ctr = L.counters.p;
+    PathState st = {L.cf.p, L.cl.p, L.nor.p, L.px.p, c->stop_zero ? nullptr : L.wo_prev.p};
     const int g_light = grid_for(c, c->shade_blocks_per_sm);
     const int g_trav = grid_for(c, c->trav_blocks_per_sm);
     uint32_t launches = 0;
     stage_mark(c, 0);
-    k_generate<<<g_light, 256, 0, c->stream>>>(c->scene, W, st, c->rays_a.p, c->path_a.p, ctr + CTR_Q + 0);
+    k_generate<<<g_light, 256, 0, s>>>(c->scene, W, st, L.rays_a.p, L.path_a.p, ctr + CTR_Q + 0);
     launches++;
     ShadeParams P = {c->max_path_length, c->rr_start, c->direct, c->stop_zero};
-    float4* rin = c->rays_a.p; float4* rout = c->rays_b.p; uint32_t* pin = c->path_a.p; uint32_t* pout = c->path_b.p;
-    float4* rspare = c->rays_c.p; uint32_t* pspare = c->path_c.p;
+    float4* rin = L.rays_a.p; float4* rout = L.rays_b.p; uint32_t* pin = L.path_a.p; uint32_t* pout = L.path_b.p;
+    float4* rspare = L.rays_c.p; uint32_t* pspare = L.path_c.p;
     const bool fuse = c->fuse_traversal && c->direct && !c->instrumented && (c->trav_kernel == 0 || (c->trav_kernel == 2 && c->staged_ok));
     for (int b = 0; b < c->max_path_length; b++) {
         stage_mark(c, 1);
         if (c->capture_bounce == b + 1) {
-            CK(cudaMemcpyAsync(c->capture.p, rin, 32 * n_paths, cudaMemcpyDeviceToDevice, c->stream));
-            CK(cudaMemcpyAsync(c->d_captured_n.p, ctr + CTR_Q + b, sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
+            CK(cudaMemcpyAsync(c->capture.p, rin, 32 * n_paths, cudaMemcpyDeviceToDevice, s));
+            CK(cudaMemcpyAsync(c->d_captured_n.p, ctr + CTR_Q + b, sizeof(unsigned), cudaMemcpyDeviceToDevice, s));
         }
         if (fuse && b > 0) { // shadow rays of bounce b-1 + extension rays of bounce b in one persistent launch
             if (c->trav_kernel == 2 && c->staged_ok) {
-                const TravOut out = {c->hit_a.p, c->hit_node.p, c->sh_payload.p, c->cl.p, nullptr, c->sh_rays.p, 0, nullptr, class_sort ? c->mat_hist.p + 2 * MAT_CLASSES * b : nullptr};
-                launch_staged<4, false, false>(c, c->stream, rin, ctr + CTR_Q + b, ctr + CTR_SH + b - 1, 0, ctr + CTR_WORK + 2 * b, out, nullptr);
+                const TravOut out = {L.hit_a.p, L.hit_node.p, L.sh_payload.p, L.cl.p, nullptr, L.sh_rays.p, 0, nullptr, class_sort ? L.mat_hist.p + 2 * MAT_CLASSES * b : nullptr};
+                launch_staged<4, false, false>(c, s, rin, ctr + CTR_Q + b, ctr + CTR_SH + b - 1, 0, ctr + CTR_WORK + 2 * b, out, nullptr);
             } else
-            k_intersect_fused<<<g_trav, 128, 0, c->stream>>>(c->scene, c->tune_p, rin, ctr + CTR_Q + b, c->sh_rays.p, ctr + CTR_SH + b - 1, ctr + CTR_WORK + 2 * b,
-                                                              c->hit_a.p, c->hit_node.p, c->sh_payload.p, c->cl.p);
+            k_intersect_fused<<<g_trav, 128, 0, s>>>(c->scene, c->tune_p, rin, ctr + CTR_Q + b, L.sh_rays.p, ctr + CTR_SH + b - 1, ctr + CTR_WORK + 2 * b,
+                                                              L.hit_a.p, L.hit_node.p, L.sh_payload.p, L.cl.p);
         }
-        else if (c->instrumented) launch_intersect<0, false, true>(c, g_trav, c->stream, c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, c->stats.p + 2,
-                                                                   class_sort ? c->mat_hist.p + 2 * MAT_CLASSES * b : nullptr);
-        else launch_intersect<0, false, false>(c, g_trav, c->stream, c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, c->hit_a.p, c->hit_node.p, nullptr, nullptr, nullptr, nullptr,
-                                               class_sort ? c->mat_hist.p + 2 * MAT_CLASSES * b : nullptr);
+        else if (c->instrumented) launch_intersect<0, false, true>(c, g_trav, s, c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, L.hit_a.p, L.hit_node.p, nullptr, nullptr, nullptr, c->stats.p + 2,
+                                                                   class_sort ? L.mat_hist.p + 2 * MAT_CLASSES * b : nullptr);
+        else launch_intersect<0, false, false>(c, g_trav, s, c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, L.hit_a.p, L.hit_node.p, nullptr, nullptr, nullptr, nullptr,
+                                               class_sort ? L.mat_hist.p + 2 * MAT_CLASSES * b : nullptr);
         stage_mark(c, 2);
         const bool sort_next = c->sort_mode == 1 && b + 1 < c->max_path_length;
         const uint32_t* order = nullptr;
         if (c->sort_mode == 2) { // group this bounce's hits by material class before shading
-            unsigned* hist = c->mat_hist.p + 2 * MAT_CLASSES * b;
-            k_matsort_classify<<<g_light, 256, 0, c->stream>>>(c->scene, ctr + CTR_Q + b, c->hit_a.p, c->hit_node.p, c->mat_cls.p, hist);
-            k_matsort_scatter<<<g_light, 256, 0, c->stream>>>(ctr + CTR_Q + b, c->mat_cls.p, hist, hist + MAT_CLASSES, c->mat_order.p);
-            order = c->mat_order.p; launches += 2;
+            unsigned* hist = L.mat_hist.p + 2 * MAT_CLASSES * b;
+            k_matsort_classify<<<g_light, 256, 0, s>>>(c->scene, ctr + CTR_Q + b, L.hit_a.p, L.hit_node.p, L.mat_cls.p, hist);
+            k_matsort_scatter<<<g_light, 256, 0, s>>>(ctr + CTR_Q + b, L.mat_cls.p, hist, hist + MAT_CLASSES, L.mat_order.p);
+            order = L.mat_order.p; launches += 2;
         }
         if (class_sort) { // group the hit records by the class bits the traversal kernel left in them
-            unsigned* hist = c->mat_hist.p + 2 * MAT_CLASSES * b;
-            k_class_scatter<<<g_light, 256, 0, c->stream>>>(ctr + CTR_Q + b, c->hit_a.p, hist, hist + MAT_CLASSES, c->mat_order.p);
-            order = c->mat_order.p; launches++;
+            unsigned* hist = L.mat_hist.p + 2 * MAT_CLASSES * b;
+            k_class_scatter<<<g_light, 256, 0, s>>>(ctr + CTR_Q + b, L.hit_a.p, hist, hist + MAT_CLASSES, L.mat_order.p);
+            order = L.mat_order.p; launches++;
         }
-        Queues Q = {rin, pin, rout, pout, c->hit_a.p, c->hit_node.p, c->sh_rays.p, c->sh_payload.p, sort_next ? c->sort_keys.p : nullptr, sort_next ? c->sort_hist.p : nullptr, order};
+        Queues Q = {rin, pin, rout, pout, L.hit_a.p, L.hit_node.p, L.sh_rays.p, L.sh_payload.p, sort_next ? L.sort_keys.p : nullptr, sort_next ? L.sort_hist.p : nullptr, order};
         if (class_sort) {
-            const unsigned* hist = c->mat_hist.p + 2 * MAT_CLASSES * b;
-            for (int k = 0; k < 4; k++) if (c->class_mask & (1u << k)) { launch_shade(k, g_light, c->stream, c->scene, P, st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b, hist); launches++; }
+            const unsigned* hist = L.mat_hist.p + 2 * MAT_CLASSES * b;
+            for (int k = 0; k < 4; k++) if (c->class_mask & (1u << k)) { launch_shade(k, g_light, s, c->scene, P, st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b, hist); launches++; }
             launches--;
         }
-        else launch_shade(by_class ? single_cls : -1, g_light, c->stream, c->scene, P, st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b, nullptr);
+        else launch_shade(by_class ? single_cls : -1, g_light, s, c->scene, P, st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b, nullptr);
         if (sort_next) { // counting sort of the next bounce's extension queue by (octant, origin cell)
             stage_mark(c, 4);
-            k_sort_scan<<<1, 1024, 0, c->stream>>>(c->sort_hist.p, c->sort_offsets.p);
-            k_sort_scatter<<<g_light, 256, 0, c->stream>>>(ctr + CTR_Q + b + 1, c->sort_keys.p, rout, pout, c->sort_offsets.p, rspare, pspare);
+            k_sort_scan<<<1, 1024, 0, s>>>(L.sort_hist.p, L.sort_offsets.p);
+            k_sort_scatter<<<g_light, 256, 0, s>>>(ctr + CTR_Q + b + 1, L.sort_keys.p, rout, pout, L.sort_offsets.p, rspare, pspare);
             std::swap(rout, rspare); std::swap(pout, pspare);
             launches += 2;
         }
         stage_mark(c, 3);
         if (c->direct && (!fuse || b + 1 == c->max_path_length)) {
-            if (c->instrumented) launch_intersect<1, true, true>(c, g_trav, c->stream, c->scene, c->sh_rays.p, ctr + CTR_SH + b, 0, ctr + CTR_WORK + 2 * b + 1, nullptr, nullptr, c->sh_payload.p, c->cl.p, nullptr, c->stats.p + 6);
-            else launch_intersect<1, true, false>(c, g_trav, c->stream, c->scene, c->sh_rays.p, ctr + CTR_SH + b, 0, ctr + CTR_WORK + 2 * b + 1, nullptr, nullptr, c->sh_payload.p, c->cl.p, nullptr, nullptr);
+            if (c->instrumented) launch_intersect<1, true, true>(c, g_trav, s, c->scene, L.sh_rays.p, ctr + CTR_SH + b, 0, ctr + CTR_WORK + 2 * b + 1, nullptr, nullptr, L.sh_payload.p, L.cl.p, nullptr, c->stats.p + 6);
+            else launch_intersect<1, true, false>(c, g_trav, s, c->scene, L.sh_rays.p, ctr + CTR_SH + b, 0, ctr + CTR_WORK + 2 * b + 1, nullptr, nullptr, L.sh_payload.p, L.cl.p, nullptr, nullptr);
             launches++;
         }
         launches += 2;
         std::swap(rin, rout); std::swap(pin, pout);
     }
     stage_mark(c, 4);
-    k_finish<<<g_light, 256, 0, c->stream>>>((int)n_paths, st, c->accum, c->w, c->h);
-    k_tally<<<1, 32, 0, c->stream>>>(ctr + CTR_Q, ctr + CTR_SH, c->max_path_length, c->stats.p, c->stats.p + 1);
+    k_finish<<<g_light, 256, 0, s>>>((int)n_paths, st, c->accum, c->w, c->h);
+    k_tally<<<1, 32, 0, s>>>(ctr + CTR_Q, ctr + CTR_SH, c->max_path_length, c->stats.p, c->stats.p + 1);
     launches += 2;
     stage_mark(c, 5);
     CK(cudaGetLastError());
-    if (ctl_variance_after_pass(c, new_trace != 0)) return 1;
-    CK(cudaEventRecord(c->ev_stop, c->stream));
-    c->events_recorded = true;
     c->n_launches = launches;
+    if (framed) return 0;
+    if (ctl_variance_after_pass(c, new_trace != 0)) return 1;
+    CK(cudaEventRecord(c->ev_stop, s));
+    c->events_recorded = true;
     c->passes_done += W.n_passes;
     return 0;
 }
@@ -530,11 +543,10 @@ int ctl_render_pass(ctl_ctx* c, int new_trace, int x0, int y0, int x1, int y1) {
     return render_window(c, new_trace, W);
 }
 
-int ctl_render_passes_tiled(ctl_ctx* c, int new_trace, int n_passes, int tile_w, int tile_h, int part, int n_parts) {
-    if (!c) return set_err("null context");
+static int tiled_window(ctl_ctx* c, Window& W, int n_passes, int tile_w, int tile_h, int part, int n_parts) {
     if (n_passes < 1 || n_passes > 4096) return set_err("n_passes out of range [1,4096]");
     if (tile_w <= 0 || tile_h <= 0 || n_parts <= 0 || part < 0 || part >= n_parts) return set_err("invalid tiling");
-    Window W; memset(&W, 0, sizeof(W));
+    memset(&W, 0, sizeof(W));
     W.mode = 1; W.tile_w = tile_w; W.tile_h = tile_h; W.part = part; W.n_parts = n_parts; W.n_passes = n_passes;
     W.tiles_x = (c->w + tile_w - 1) / tile_w; W.tiles_y = (c->h + tile_h - 1) / tile_h;
     W.warp_blocks = c->warp_blocks && tile_w % 8 == 0 && tile_h % 4 == 0;
@@ -542,6 +554,13 @@ int ctl_render_passes_tiled(ctl_ctx* c, int new_trace, int n_passes, int tile_w,
     const int n_local = n_tiles > part ? (n_tiles - part + n_parts - 1) / n_parts : 0;
     W.n_slots = n_local * tile_w * tile_h;
     if ((size_t)W.n_slots * n_passes > 0x7fffffffull / 2) return set_err("batch too large: reduce n_passes");
+    return 0;
+}
+
+int ctl_render_passes_tiled(ctl_ctx* c, int new_trace, int n_passes, int tile_w, int tile_h, int part, int n_parts) {
+    if (!c) return set_err("null context");
+    Window W;
+    if (tiled_window(c, W, n_passes, tile_w, tile_h, part, n_parts)) return 1;
     if (W.n_slots == 0) { // nothing to trace on this part: still honour the clear and advance the pass counter / sample stream
         CK(cudaSetDevice(c->device));
         CK(cudaEventRecord(c->ev_start, c->stream));
@@ -553,6 +572,55 @@ int ctl_render_passes_tiled(ctl_ctx* c, int new_trace, int n_passes, int tile_w,
         return 0;
     }
     return render_window(c, new_trace, W);
+}
+
+// One progressive frame (a new trace): `spp` passes on the tiles of `part`, `batch` passes fused per wavefront.  With "OverlapWavefronts" (default) the
+// frame's wavefronts alternate between two lanes -- two streams with their own wavefront buffers -- and a frame that is ONE wavefront is cut into two
+// half-batches: every traversal launch is a persistent kernel whose last rays leave most of the SMs idle (nine tails per wavefront; at 1/8 of the image
+// per GPU they are ~10 % of the frame), and the other lane's launch moves into the blocks that drain first.  Paths are the same paths (a path only
+// depends on its pixel and pass); only the order of the float atomics into PixelData differs, as between any two runs.
+int ctl_render_frame_tiled(ctl_ctx* c, int spp, int batch, int tile_w, int tile_h, int part, int n_parts) {
+    if (!c) return set_err("null context");
+    if (spp < 1 || batch < 1 || spp % batch) return set_err("spp must be a positive multiple of batch");
+    const bool plain = !c->overlap || c->stage_timers || c->instrumented || c->capture_bounce > 0 || c->variance_buffer || c->user_tables || c->sort_mode != 0 || spp > 128 ||
+                       (spp == batch && (batch & 1)) || c->n_lanes < 2;
+    if (plain) {
+        for (int p = 0; p < spp; p += batch)
+            if (ctl_render_passes_tiled(c, p == 0, batch, tile_w, tile_h, part, n_parts)) return 1;
+        return 0;
+    }
+    const int n_lanes = c->n_lanes;
+    while (spp / batch < n_lanes && batch % 2 == 0) batch /= 2;   // fewer wavefronts than lanes: cut the batches
+    Window W;
+    if (tiled_window(c, W, batch, tile_w, tile_h, part, n_parts)) return 1;
+    if (!c->has_scene) return set_err("no scene uploaded");
+    CK(cudaSetDevice(c->device));
+    if (!c->ev_fork) CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for (int k = 1; k < n_lanes; k++) if (!c->lane_stream[k]) {
+        CK(cudaStreamCreateWithFlags(&c->lane_stream[k], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(c->ev_start, c->stream));
+    CK(cudaMemsetAsync(c->accum, 0, (size_t)c->w * c->h * 7 * sizeof(float), c->stream));
+    c->passes_done = 0;
+    if (W.n_slots == 0) CK(cudaMemsetAsync(c->stats.p, 0, sizeof(unsigned long long), c->stream));
+    else {
+        if (generate_tables(c, 0, spp)) return 1;   // the table sets of all passes of the frame, before the lanes fork
+        CK(cudaEventRecord(c->ev_fork, c->stream));
+        for (int k = 1; k < n_lanes; k++) CK(cudaStreamWaitEvent(c->lane_stream[k], c->ev_fork, 0));
+        uint32_t launches = 0;
+        for (int p = 0, i = 0; p < spp; p += batch, i++) {
+            W.tab0 = p;
+            if (render_window(c, 0, W, i % n_lanes, true)) return 1;
+            launches += c->n_launches;
+        }
+        c->n_launches = launches;
+        for (int k = 1; k < n_lanes; k++) { CK(cudaEventRecord(c->ev_join[k], c->lane_stream[k])); CK(cudaStreamWaitEvent(c->stream, c->ev_join[k], 0)); }
+    }
+    CK(cudaEventRecord(c->ev_stop, c->stream));
+    c->events_recorded = true;
+    c->passes_done = (uint32_t)spp;
+    return 0;
 }
 
 int ctl_render_pass_tiled(ctl_ctx* c, int new_trace, int tile_w, int tile_h, int part, int n_parts) {
@@ -585,7 +653,7 @@ int ctl_wavefront_pass(ctl_ctx* c, int new_trace) {
     for (int k = 0; k < 2; k++) { CK(c->w_sec[k].ensure(2 * n)); CK(c->w_sres[k].ensure(n)); }
     CK(c->w_desc.ensure((size_t)mpl * (n_tiles + 1)));
     c->stage_kind.clear();
-    unsigned* ctr = c->counters.p;
+    unsigned* ctr = c->lanes[0].counters.p;
     CK(cudaMemsetAsync(ctr, 0, CTR_TOTAL * sizeof(unsigned), c->stream));
     CK(cudaMemsetAsync(c->w_desc.p, 0, (size_t)mpl * (n_tiles + 1) * sizeof(unsigned long long), c->stream));
     if (c->instrumented) CK(cudaMemsetAsync(c->stats.p + 2, 0, 8 * sizeof(unsigned long long), c->stream));
@@ -715,7 +783,7 @@ int ctl_get_visit_counts(ctl_ctx* c, uint64_t ext[4], uint64_t sh[4]) {
     CK(cudaStreamSynchronize(c->stream));
     unsigned long long h[8]; std::vector<unsigned> ctr(CTR_TOTAL);
     CK(cudaMemcpy(h, c->stats.p + 2, sizeof(h), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(ctr.data(), c->counters.p, CTR_TOTAL * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ctr.data(), c->lanes[0].counters.p, CTR_TOTAL * sizeof(unsigned), cudaMemcpyDeviceToHost));
     unsigned long long ne = 0, ns = 0;
     for (int b = 0; b < c->max_path_length; b++) { ne += ctr[CTR_Q + b]; ns += ctr[CTR_SH + b]; }
     if (ext) { ext[0] = h[0]; ext[1] = h[1]; ext[2] = h[2]; ext[3] = ne; }
@@ -727,7 +795,7 @@ int ctl_get_queue_sizes(ctl_ctx* c, uint32_t* ext, uint32_t* sh, int n) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     std::vector<unsigned> ctr(CTR_TOTAL);
-    CK(cudaMemcpy(ctr.data(), c->counters.p, CTR_TOTAL * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ctr.data(), c->lanes[0].counters.p, CTR_TOTAL * sizeof(unsigned), cudaMemcpyDeviceToHost));
     for (int b = 0; b < n && b < MAX_BOUNCES; b++) { if (ext) ext[b] = ctr[CTR_Q + b]; if (sh) sh[b] = ctr[CTR_SH + b]; }
     return 0;
 }

@@ -142,10 +142,8 @@ int ctl_comm_allreduce_u64(ctl_ctx* c, uint64_t* host_inout, int count) {
 // fused per wavefront, then the reduce to `root`.  Asynchronous on the context's stream.  == what bench.py's step does at N GPUs.
 int ctl_comm_render_frame(ctl_ctx* c, int spp, int batch, int tile, int root) {
     if (!c) return ctl_set_err("null context");
-    if (spp < 1 || batch < 1 || spp % batch) return ctl_set_err("spp must be a positive multiple of batch");
     if (tile <= 0) tile = 64;
-    for (int p = 0; p < spp; p += batch)
-        if (ctl_render_passes_tiled(c, p == 0, batch, tile, tile, c->comm_rank, c->comm_size)) return 1;
+    if (ctl_render_frame_tiled(c, spp, batch, tile, tile, c->comm_rank, c->comm_size)) return 1;
     return ctl_comm_reduce_accum(c, root);
 }
 

@@ -27,6 +27,7 @@ int ctl_set_err(const std::string& s);
 struct ctl_scene { ctlb::SceneStorage S; };
 
 const int MAX_BOUNCES = 256;
+const int MAX_LANES = 4;   // wavefronts of a frame in flight at once (OverlapWavefronts / OverlapLanes)
 const unsigned API_WORK_RING = 256;
 enum { CTR_Q = 0, CTR_SH = MAX_BOUNCES + 1, CTR_WORK = 2 * (MAX_BOUNCES + 1), CTR_TOTAL = 4 * (MAX_BOUNCES + 1) };
 
@@ -50,6 +51,16 @@ template <typename T> struct DevBuf {
 
 struct ncclComm;   // ctl_comm.cu (NCCL is loaded at run time, only when a communicator is asked for)
 
+// Buffers of one wavefront in flight (SoA path state, rotating ray queues, hit records, shadow queue, per-bounce device counters).
+struct WaveLane {
+    DevBuf<float4> wo_prev, cf, cl, nor, px, rays_a, rays_b, rays_c, hit_a, sh_rays, sh_payload;
+    DevBuf<uint32_t> path_a, path_b, path_c, hit_node, sort_keys, mat_order; DevBuf<unsigned> sort_hist, sort_offsets, mat_hist, counters; DevBuf<unsigned char> mat_cls;
+    void release() {
+        wo_prev.release(); cf.release(); cl.release(); nor.release(); px.release(); rays_a.release(); rays_b.release(); rays_c.release(); hit_a.release(); sh_rays.release(); sh_payload.release();
+        path_a.release(); path_b.release(); path_c.release(); hit_node.release(); sort_keys.release(); mat_order.release(); sort_hist.release(); sort_offsets.release(); mat_hist.release(); counters.release(); mat_cls.release();
+    }
+};
+
 struct ctl_ctx {
     ncclComm* comm = nullptr; int comm_rank = 0, comm_size = 1; unsigned long long* comm_scratch = nullptr;   // ctl_comm_init_* (ctl_comm.cu)
     int device = 0, w = 0, h = 0;
@@ -70,10 +81,9 @@ struct ctl_ctx {
     bool user_tables = false; int device_tables = 1;
     uint32_t gen_pos_host = 0, gen_pos_dev = 0;   // index of the next pass each generator would produce
     ctlb::SamplerTableGenerator gen;
-    // wavefront state
-    DevBuf<float4> wo_prev; DevBuf<float4> cf, cl, nor, px, rays_a, rays_b, hit_a, sh_rays, sh_payload, capture;
-    DevBuf<uint32_t> path_a, path_b, path_c, hit_node, sort_keys; DevBuf<float4> rays_c; DevBuf<unsigned> sort_hist, sort_offsets, mat_hist; DevBuf<unsigned char> mat_cls; DevBuf<uint32_t> mat_order;
-    DevBuf<unsigned> counters;
+    // wavefront state: lane 0 runs on `stream`; lanes 1.. (own streams) hold the other wavefronts of a frame rendered with "OverlapWavefronts" (ctl_comm_render_frame)
+    WaveLane lanes[MAX_LANES]; DevBuf<float4> capture;
+    cudaStream_t lane_stream[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr}; int overlap = 1, n_lanes = 2;
     DevBuf<unsigned> api_work; unsigned api_seq = 0;   // ring of work counters of the API traversal launches: calls in flight on different streams never share one
     // WavefrontPathTracer queue (DoubleRayBuffer<WavefrontPTRayData>)
     DevBuf<float4> w_thr, w_lxy, w_df, w_ray, w_sec[2]; DevBuf<uint2> w_misc; DevBuf<uint4> w_res, w_sres[2]; DevBuf<unsigned long long> w_desc;

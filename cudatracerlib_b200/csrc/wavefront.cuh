@@ -19,6 +19,7 @@ struct Window { // which pixels a pass renders
     int n_slots;   // pixels of the window (paths per pass)
     int n_passes;  // passes rendered by this wavefront; path slot = pass * n_slots + pixel slot
     int warp_blocks; // mode 1: slots inside a tile run over 8x4 pixel blocks (tile_w % 8 == 0 and tile_h % 4 == 0) instead of rows
+    int tab0;      // sample-table set of this wavefront's first pass (pass k of the wavefront draws from set tab0 + k)
 };
 
 // SoA path state, indexed by path id (= window slot)
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_round; s += gridDim.x * blockDim.x) {
         int x = 0, y = 0;
         const bool in_range = s < n_total;
-        const unsigned pass = (unsigned)(s / W.n_slots);
+        const unsigned pass = (unsigned)(s / W.n_slots) + (unsigned)W.tab0;
         const bool valid = in_range && slot_to_pixel(W, s % W.n_slots, S.img_w, S.img_h, x, y);
         V3 o = mk(0, 0, 0), d = mk(0, 0, 1);
         if (valid) {
@@ -511,7 +512,7 @@ __global__ void k_tally(const unsigned* q_count, const unsigned* sh_count, int n
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         unsigned long long s = 0;
         for (int b = 0; b < n_bounces; b++) s += (unsigned long long)q_count[b] + (unsigned long long)sh_count[b];
-        *rays_last = s; *rays_total += s;
+        *rays_last = s; atomicAdd(rays_total, s);   // two wavefronts of a frame may tally concurrently (OverlapWavefronts)
     }
 }
 

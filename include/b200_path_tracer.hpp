@@ -96,6 +96,10 @@ public:
     void DoPassesTiled(int n_passes, bool a_NewTrace, int part = 0, int n_parts = 1, int tile = 64) {
         need_ctx(); check(ctl_render_passes_tiled(ctx_, (a_NewTrace || new_trace_) ? 1 : 0, n_passes, tile, tile, part, n_parts)); new_trace_ = false;
     }
+    // one progressive frame (a new trace of spp passes, `batch` fused per wavefront, the wavefronts overlapped on two streams: ctl_render_frame_tiled); asynchronous
+    void DoFrameTiled(int spp, int batch = 8, int part = 0, int n_parts = 1, int tile = 64) {
+        need_ctx(); check(ctl_render_frame_tiled(ctx_, spp, batch, tile, tile, part, n_parts)); new_trace_ = false;
+    }
     void Synchronize() { need_ctx(); check(ctl_synchronize(ctx_)); }
     ctl_ctx* handle() { return ctx_; }
 protected:

@@ -255,12 +255,19 @@ void ctl_scene_destroy(ctl_scene*);
  * 64-entry traversal stack.  The reference trusts its builders and would read out of bounds or spin in __traceRay_internal__ (Kernel/TraceHelper.cu:88-172)
  * on such data; the .xmsh reader runs the mesh part of this check on every file.  0 = consistent; otherwise ctl_last_error names the first problem. */
 int  ctl_validate_scene_view(const ctl_scene_view*);
-/* GPU construction of one mesh BVH in the reference layout (LBVH: Morton codes, hand-written radix sort, Karras radix tree,
- * bottom-up fit, <= 8-triangle leaves) -- replaces the CPU pre-process SplitBVHBuilder.cpp / BVHBuilderHelper.cpp:119 for
- * meshes that need (re)building at run time.  verts9: n_tris * 9 floats (host).  Outputs (host): nodes_out
- * (capacity max(1, n_tris)), woop_out / index_out (n_tris each, leaf order), *n_nodes_out, optional device build time. */
+/* GPU construction of one mesh BVH in the reference layout -- replaces the CPU pre-process SplitBVHBuilder.cpp:163-203 /
+ * BVHBuilderHelper.cpp:119 for meshes that need (re)building at run time.  Triangles are sorted by Morton code
+ * (hand-written radix sort); the tree over them is built by parallel locally-ordered clustering (every merge decided by surface
+ * area, the Morton order only bounds the search: csrc/bvh_ploc.cuh), then a bottom-up fit with the SAH leaf / split decision
+ * (<= 8-triangle leaves), leaves laid out in tree order, nodes in pre-order.  CTL_GPU_BUILDER=lbvh selects the Karras radix tree
+ * instead (fastest build, 1.1-1.3x slower traversal), CTL_PLOC_RADIUS the search window (default 16).  verts9: n_tris * 9 floats
+ * (host).  Outputs (host): nodes_out (capacity max(1, n_tris)), woop_out / index_out (n_tris each, leaf order), *n_nodes_out,
+ * optional device build time.  Deterministic. */
 int ctl_bvh_build_gpu(int device, const float* verts9, uint32_t n_tris, ctl_bvh_node* nodes_out, uint32_t* n_nodes_out,
                       ctl_woop_tri* woop_out, uint32_t* index_out, float* build_ms);
+/* The same with the builder named: algorithm 0 = LBVH, 1 = agglomerative (PLOC); radius <= 0 = default (16, at most 32). */
+int ctl_bvh_build_gpu_ex(int device, const float* verts9, uint32_t n_tris, int algorithm, int radius, ctl_bvh_node* nodes_out,
+                         uint32_t* n_nodes_out, ctl_woop_tri* woop_out, uint32_t* index_out, float* build_ms);
 /* Rebuild all mesh BVHs of a host scene with ctl_bvh_build_gpu (views obtained before the call are invalidated). */
 int ctl_scene_rebuild_bvh_gpu(ctl_scene*, int device, float* build_ms_total);
 /* encoders exposed for known-answer tests */
@@ -327,6 +334,11 @@ int ctl_render_pass_tiled(ctl_ctx*, int new_trace, int tile_w, int tile_h, int p
  * atomics into PixelData differs).  Keeps launches large when the image is split over many GPUs and amortises launch
  * overhead; path state is ~230 B x pixels x n_passes of HBM.  part=0, n_parts=1 renders the whole image. */
 int ctl_render_passes_tiled(ctl_ctx*, int new_trace, int n_passes, int tile_w, int tile_h, int part, int n_parts);
+/* One progressive FRAME (== StartNewTrace + spp DoPass calls, Kernel/Tracer.h:209-248) on the tiles of `part`, `batch` passes fused per wavefront
+ * (spp % batch == 0).  With "OverlapWavefronts" (default 1) the frame's wavefronts alternate between two streams with their own wavefront buffers (a
+ * frame of one wavefront is cut into two half-batches), so the draining tail of one persistent traversal launch overlaps the head of the other's;
+ * the paths traced are identical either way.  Asynchronous on the context's stream (the second stream is joined before the call returns work to it). */
+int ctl_render_frame_tiled(ctl_ctx*, int spp, int batch, int tile_w, int tile_h, int part, int n_parts);
 /* == WavefrontPathTracer: Tracer<true>::DoPass + WavefrontPathTracer::DoRender (Kernel/Tracer.h:209-248,
  *    Integrators/PseudoRealtime/WavefrontPathTracer.cu:166-191) over a DoubleRayBuffer-shaped device queue (Kernel/DoubleRayBuffer.h):
  *    the reference's own wavefront integrator, second consumer of the intersect kernel.  Same parameters as the reference

@@ -487,13 +487,16 @@ def _walk_reference_bvh(nodes_f32, tri_index, n_slots):
     return inner, leaves
 
 
+@pytest.mark.parametrize("builder", ["ploc", "lbvh"])
 @pytest.mark.parametrize("kind", ["cornell7", "soup", "c2"])
-def test_gpu_bvh_build_matches_cpu_bvh_results(built_lib, orc, kind):
-    """ctl_scene_rebuild_bvh_gpu: LBVH built on the device in the reference layout.  Different tree, same data surface:
-    every triangle referenced exactly once, leaves <= 8, and closest hits / images identical to the CPU-built (SAH) tree."""
+def test_gpu_bvh_build_matches_cpu_bvh_results(built_lib, orc, kind, builder, monkeypatch):
+    """ctl_scene_rebuild_bvh_gpu: the agglomerative builder (default) and the LBVH, built on the device in the reference layout.  Different trees,
+    same data surface: every triangle referenced exactly once, leaves <= 8, and closest hits / images identical to the CPU-built (SAH) tree."""
+    monkeypatch.setenv("CTL_GPU_BUILDER", builder)
     w, h = 192, 108
     s_cpu = ctl.Scene(kind, w, h); s_gpu = ctl.Scene(kind, w, h)
     ms = s_gpu.rebuildBVHOnGPU()
+    s_gpu.validate()                                                                  # child / leaf references, tree shape, depth within the traversal stack
     assert ms > 0 and s_gpu.view.n_woop == s_gpu.n_triangles == s_gpu.view.n_tri_index and s_cpu.view.n_woop >= s_cpu.n_triangles   # the CPU split BVH may duplicate references
     meshes = s_gpu.array("meshes"); tri_index = s_gpu.array("tri_index")[:, 0]; bvh = s_gpu.array("bvh_nodes")
     for mi, m in enumerate(meshes):
@@ -522,22 +525,52 @@ def test_gpu_bvh_build_matches_cpu_bvh_results(built_lib, orc, kind):
     t1.close(); t2.close()
 
 
-def test_gpu_bvh_build_api_edge_cases(built_lib, orc):
+def _depth(nodes):
+    d, st = 0, [(0, 1)]
+    u = nodes.view(np.int32)
+    while st:
+        i, k = st.pop(); d = max(d, k)
+        for c in (int(u[i, 12]), int(u[i, 13])):
+            if c >= 0 and c != 0x76543210: st.append((c // 4, k + 1))
+    return d
+
+
+@pytest.mark.parametrize("algorithm", [1, 0])
+def test_gpu_bvh_build_api_edge_cases(built_lib, orc, algorithm):
     L = built_lib
-    for n in (1, 2, 8, 9, 300):
+    L.ctl_bvh_build_gpu_ex.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    for n in (1, 2, 8, 9, 10, 17, 300, 5000):
         rng = np.random.default_rng(n)
         verts = rng.uniform(-1, 1, size=(n, 9)).astype(np.float32)
+        if n == 5000:   # duplicated / degenerate geometry: 2 000 copies of one triangle, 1 000 zero-area triangles at one point, the rest random
+            verts[:2000] = verts[0]; verts[2000:3000] = 0.25
         nodes = np.zeros((max(n, 1), 16), np.float32); woop = np.zeros((n, 12), np.float32); index = np.zeros(n, np.uint32)
         nn = C.c_uint32(0); ms = C.c_float(0)
-        assert L.ctl_bvh_build_gpu(0, verts.ctypes.data, n, nodes.ctypes.data, C.byref(nn), woop.ctypes.data, index.ctypes.data, C.byref(ms)) == 0
+        assert L.ctl_bvh_build_gpu_ex(0, verts.ctypes.data, n, algorithm, 0, nodes.ctypes.data, C.byref(nn), woop.ctypes.data, index.ctypes.data, C.byref(ms)) == 0
+        assert _depth(nodes[:nn.value]) <= 56                                           # equal boxes pair up (2k, 2k+1): no merge chains
         inner, leaves = _walk_reference_bvh(nodes[:nn.value], index, n)
         assert inner == nn.value and sum(c for _, c in leaves) == n and all(c <= 8 for _, c in leaves)
         if n <= 8:   # single-leaf mesh: root = {~0, sentinel} (SplitBVHBuilder.cpp:176-189)
             assert nn.value == 1 and nodes.view(np.uint32)[0, 12] == 0xffffffff and nodes.view(np.uint32)[0, 13] == 0x76543210
         for s_ in range(n):  # Woop data of every slot == the host encoder on that triangle's vertices, bit for bit
             t = index[s_] >> 1
-            assert np.array_equal(woop[s_].view(np.uint32), orc.encode_woop(verts[t, 0:3], verts[t, 3:6], verts[t, 6:9]).view(np.uint32))
+            ref = orc.encode_woop(verts[t, 0:3], verts[t, 3:6], verts[t, 6:9])
+            assert np.array_equal(woop[s_].view(np.uint32), ref.view(np.uint32)) or (np.isnan(ref).all() and np.isnan(woop[s_]).all())   # zero-area triangle: NaN both (payload bits differ host / device)
     assert L.ctl_bvh_build_gpu(0, None, 0, None, None, None, None, None) != 0
+    assert L.ctl_bvh_build_gpu_ex(0, verts.ctypes.data, 8, 2, 0, nodes.ctypes.data, C.byref(nn), woop.ctypes.data, index.ctypes.data, None) != 0   # unknown algorithm
+
+
+def test_gpu_bvh_build_is_deterministic(built_lib):
+    """The agglomerative builder hands out node ids by rank (scan), not by atomics: two builds of one mesh are byte-identical."""
+    L = built_lib
+    rng = np.random.default_rng(5); n = 20000
+    c = rng.uniform(-1, 1, size=(n, 1, 3)); verts = (c + rng.normal(scale=0.02, size=(n, 3, 3))).reshape(n, 9).astype(np.float32)
+    outs = []
+    for _ in range(2):
+        nodes = np.zeros((n, 16), np.float32); woop = np.zeros((n, 12), np.float32); index = np.zeros(n, np.uint32); nn = C.c_uint32(0)
+        assert L.ctl_bvh_build_gpu(0, verts.ctypes.data, n, nodes.ctypes.data, C.byref(nn), woop.ctypes.data, index.ctypes.data, None) == 0
+        outs.append((nn.value, nodes[:nn.value].tobytes(), index.tobytes()))
+    assert outs[0] == outs[1]
 
 
 def test_material_sort_preserves_results(built_lib):
