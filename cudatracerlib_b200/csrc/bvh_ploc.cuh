@@ -36,8 +36,11 @@ __device__ __forceinline__ bool pair_less(float a0, int i0, int j0, float a1, in
     if (m0 != m1) return m0 < m1;
     return max(i0, j0) < max(i1, j1);
 }
-__global__ void __launch_bounds__(256) k_ploc_nn(int nc, int radius, const float4* __restrict__ cbox, int* __restrict__ nn) {
+// Round state on the device: st[0] = clusters left, st[1] = next node id, st[2] = rounds that merged something.  The host launches rounds in groups
+// over grids sized for the last count it has seen (an upper bound) and looks at the state once per group.
+__global__ void __launch_bounds__(256) k_ploc_nn(const int* __restrict__ st, int radius, const float4* __restrict__ cbox, int* __restrict__ nn) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nc = st[0];
     if (i >= nc) return;
     const float4 lo = cbox[2 * i], hi = cbox[2 * i + 1];
     const int j0 = max(0, i - radius), j1 = min(nc - 1, i + radius);
@@ -51,17 +54,19 @@ __global__ void __launch_bounds__(256) k_ploc_nn(int nc, int radius, const float
     nn[i] = best;
 }
 // flags[i] = survives | merges << 32; slot nc = 0 (receives the totals after the exclusive scan)
-__global__ void k_ploc_flags(int nc, const int* __restrict__ nn, unsigned long long* __restrict__ flags) {
+__global__ void k_ploc_flags(const int* __restrict__ st, const int* __restrict__ nn, unsigned long long* __restrict__ flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nc = st[0];
     if (i > nc) return;
     if (i == nc) { flags[i] = 0ull; return; }
     const int j = nn[i];
     const bool mutual = j >= 0 && nn[j] == i;
     flags[i] = (mutual && i > j) ? 0ull : (1ull | ((mutual && i < j) ? (1ull << 32) : 0ull));
 }
-__global__ void __launch_bounds__(1024) k_scan_exclusive64(unsigned long long* __restrict__ data, uint32_t m) {
+__global__ void __launch_bounds__(1024) k_scan_exclusive64(unsigned long long* __restrict__ data, const int* __restrict__ st) {
     __shared__ unsigned long long warp_sums[32];
     const int t = threadIdx.x;
+    const uint32_t m = (uint32_t)st[0] + 1u;
     const uint32_t per = (m + 1023) / 1024, lo = (uint32_t)t * per, hi = min(lo + per, m);
     unsigned long long local = 0;
     for (uint32_t i = lo; i < hi; i++) local += data[i];
@@ -75,9 +80,10 @@ __global__ void __launch_bounds__(1024) k_scan_exclusive64(unsigned long long* _
     for (uint32_t i = lo; i < hi; i++) { const unsigned long long v = data[i]; data[i] = run; run += v; }
 }
 // survivors keep their order; a merge at position i (partner j > i) becomes inner node next_id - rank
-__global__ void k_ploc_merge(int nc, const int* __restrict__ nn, const unsigned long long* __restrict__ scan, int next_id, const int* __restrict__ cid_in, const float4* __restrict__ cbox_in,
+__global__ void k_ploc_merge(const int* __restrict__ st, const int* __restrict__ nn, const unsigned long long* __restrict__ scan, const int* __restrict__ cid_in, const float4* __restrict__ cbox_in,
                              int* __restrict__ cid_out, float4* __restrict__ cbox_out, int* __restrict__ left, int* __restrict__ right, int* __restrict__ parent_int, int* __restrict__ parent_leaf) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nc = st[0], next_id = st[1];
     if (i >= nc) return;
     const int j = nn[i];
     const bool mutual = j >= 0 && nn[j] == i;
@@ -98,6 +104,12 @@ __global__ void k_ploc_merge(int nc, const int* __restrict__ nn, const unsigned 
         if (id == 0) parent_int[0] = -1;
     }
     cid_out[p] = id; cbox_out[2 * p] = lo; cbox_out[2 * p + 1] = hi;
+}
+
+__global__ void k_ploc_advance(int* __restrict__ st, const unsigned long long* __restrict__ scan) {   // <<<1, 1>>> after the merge
+    const unsigned long long tot = scan[st[0]];
+    const int merges = (int)(uint32_t)(tot >> 32);
+    st[0] = (int)(uint32_t)tot; st[1] -= merges; st[2] += merges > 0 ? 1 : 0;
 }
 
 // ---- generic back end: any binary tree over the sorted triangles (children: >= 0 inner id, < 0 ~sorted position; root = inner 0) ------------------

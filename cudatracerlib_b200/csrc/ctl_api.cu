@@ -158,6 +158,8 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "StagedTreeletNodes") { if (v < 0 || v > 2048) return set_err("StagedTreeletNodes out of range [0,2048]"); c->staged_treelet = v; }   // takes effect at the next ctl_upload_scene / ctl_update_scene_nodes
     else if (k == "TravThT") c->tune.th_t = c->tune_p.th_t = v; else if (k == "TravThL") c->tune.th_l = c->tune_p.th_l = v; else if (k == "TravThF") c->tune.th_f = c->tune_p.th_f = v;
     else if (k == "TravThNExit") c->tune.th_n_exit = c->tune_p.th_n_exit = v;
+    else if (k == "TravChunk") { if (v < 0 || v > 4096 || (v & 31)) return set_err("TravChunk must be 0 (by queue size) or a multiple of 32 up to 4096"); c->tune.chunk = v; }   // rays a warp claims per atomic (staged kernel)
+    else if (k == "TravDrainPrefetch") c->tune.drain_prefetch = v != 0;   // staged kernel: prefetch both children per node step once the queue is exhausted
     else if (k == "TravTSteps") { if (v < 1 || v > 8) return set_err("TravTSteps out of range [1,8]"); c->tune.t_steps = v; }
     else if (k == "ShadeBlocksPerSM") { if (v < 1 || v > 16) return set_err("ShadeBlocksPerSM out of range [1,16]"); c->shade_blocks_per_sm = v; }
     else if (k == "TravSmemCarveout") { // experiment: shared-memory carve-out (percent) of the traversal kernels = how much L1 they lose

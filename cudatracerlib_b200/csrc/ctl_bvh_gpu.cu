@@ -22,11 +22,11 @@ static int tree_depth(const ctl_bvh_node* nodes, uint32_t n_nodes) {
     return depth;
 }
 
-int ctl_bvh_build_gpu_ex(int device, const float* verts9, uint32_t n_tris, int algorithm, int radius, ctl_bvh_node* nodes_out, uint32_t* n_nodes_out, ctl_woop_tri* woop_out, uint32_t* index_out, float* build_ms) {
+struct GpuBuildStats { float sah_cost = 0; int rounds = 0; };
+static int build_gpu(int device, const float* verts9, uint32_t n_tris, int algorithm, int radius, ctl_bvh_node* nodes_out, uint32_t* n_nodes_out, ctl_woop_tri* woop_out, uint32_t* index_out, float* build_ms, GpuBuildStats* stats) {
     using namespace ctlbvh;
     if (!verts9 || !n_tris || !nodes_out || !n_nodes_out || !woop_out || !index_out) return set_err("null / empty argument");
     if (n_tris > 0x3fffffffu) return set_err("too many triangles");
-    if (algorithm < 0 || algorithm > 1) return set_err("algorithm must be 0 (LBVH) or 1 (agglomerative, PLOC)");
     if (radius <= 0) radius = 16;
     if (radius > PLOC_MAX_RADIUS) radius = PLOC_MAX_RADIUS;
     CK(cudaSetDevice(device));
@@ -34,8 +34,8 @@ int ctl_bvh_build_gpu_ex(int device, const float* verts9, uint32_t n_tris, int a
     const int nb_sort = (n + SORT_TILE - 1) / SORT_TILE;
     DevBuf<float> d_verts; DevBuf<float4> d_boxes, d_nbox; DevBuf<unsigned> d_sbox, d_counts, d_flags, d_emit; DevBuf<uint32_t> d_k0, d_k1, d_v0, d_v1, d_index;
     DevBuf<int> d_left, d_right, d_pint, d_pleaf, d_first, d_last; DevBuf<ctl_bvh_node> d_nodes; DevBuf<ctl_woop_tri> d_woop; DevBuf<unsigned char> d_lastflag, d_collapse; DevBuf<float> d_cost;
-    DevBuf<int> d_cid0, d_cid1, d_nn, d_count, d_ecount, d_slot, d_pleaf2; DevBuf<float4> d_cb0, d_cb1; DevBuf<unsigned long long> d_scan; DevBuf<uint32_t> d_vals2;   // agglomerative builder
-    auto free_all = [&]() { d_cid0.release(); d_cid1.release(); d_nn.release(); d_count.release(); d_ecount.release(); d_slot.release(); d_pleaf2.release(); d_cb0.release(); d_cb1.release(); d_scan.release(); d_vals2.release(); d_verts.release(); d_boxes.release(); d_nbox.release(); d_sbox.release(); d_counts.release(); d_flags.release(); d_emit.release(); d_k0.release(); d_k1.release(); d_v0.release(); d_v1.release();
+    DevBuf<int> d_cid0, d_cid1, d_nn, d_count, d_ecount, d_slot, d_pleaf2, d_pst; DevBuf<float4> d_cb0, d_cb1; DevBuf<unsigned long long> d_scan; DevBuf<uint32_t> d_vals2;   // agglomerative builder
+    auto free_all = [&]() { d_pst.release(); d_cid0.release(); d_cid1.release(); d_nn.release(); d_count.release(); d_ecount.release(); d_slot.release(); d_pleaf2.release(); d_cb0.release(); d_cb1.release(); d_scan.release(); d_vals2.release(); d_verts.release(); d_boxes.release(); d_nbox.release(); d_sbox.release(); d_counts.release(); d_flags.release(); d_emit.release(); d_k0.release(); d_k1.release(); d_v0.release(); d_v1.release();
                             d_index.release(); d_left.release(); d_right.release(); d_pint.release(); d_pleaf.release(); d_first.release(); d_last.release(); d_nodes.release(); d_woop.release(); d_lastflag.release(); d_collapse.release(); d_cost.release(); };
 #define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { free_all(); char b_[512]; snprintf(b_, sizeof(b_), "In file %s at line %d : %s", __FILE__, __LINE__, cudaGetErrorString(e_)); return set_err(b_); } } while (0)
     CKF(d_verts.upload(verts9, (size_t)n * 9)); CKF(d_boxes.ensure((size_t)n * 2)); CKF(d_nbox.ensure((size_t)n * 2)); CKF(d_sbox.ensure(6)); CKF(d_counts.ensure((size_t)256 * nb_sort));
@@ -63,22 +63,31 @@ int ctl_bvh_build_gpu_ex(int device, const float* verts9, uint32_t n_tris, int a
         CKF(d_cb0.ensure((size_t)n * 2)); CKF(d_cb1.ensure((size_t)n * 2)); CKF(d_scan.ensure((size_t)n + 1)); CKF(d_vals2.ensure(n));
         k_ploc_init<<<g, 256, 0, st>>>(n, vin, d_boxes.p, d_cid0.p, d_cb0.p);
         int *cin = d_cid0.p, *cout = d_cid1.p; float4 *bin = d_cb0.p, *bout = d_cb1.p;
-        int nc = n, next_id = n - 2, rounds = 0;
-        while (nc > 1) {   // one round: nearest partner in the window, mutual pairs merge, survivors compact (order kept)
+        // rounds (nearest partner in the window, mutual pairs merge, survivors compact in order) in groups of 6 without a host round trip; a round on one
+        // cluster is a no-op, so overshooting the end is harmless
+        static int* h_st = nullptr;   // pinned
+        if (!h_st) CKF(cudaHostAlloc((void**)&h_st, 4 * sizeof(int), cudaHostAllocDefault));
+        CKF(d_pst.ensure(4));
+        h_st[0] = n; h_st[1] = n - 2; h_st[2] = 0; h_st[3] = 0;
+        CKF(cudaMemcpyAsync(d_pst.p, h_st, 4 * sizeof(int), cudaMemcpyHostToDevice, st));
+        int nc = n, rounds = 0;
+        while (nc > 1) {
             const int gc = (nc + 255) / 256;
-            k_ploc_nn<<<gc, 256, 0, st>>>(nc, radius, bin, d_nn.p);
-            k_ploc_flags<<<(nc + 256) / 256, 256, 0, st>>>(nc, d_nn.p, d_scan.p);
-            k_scan_exclusive64<<<1, 1024, 0, st>>>(d_scan.p, (uint32_t)nc + 1u);
-            k_ploc_merge<<<gc, 256, 0, st>>>(nc, d_nn.p, d_scan.p, next_id, cin, bin, cout, bout, d_left.p, d_right.p, d_pint.p, d_pleaf.p);
-            unsigned long long tot = 0;
-            CKF(cudaMemcpyAsync(&tot, d_scan.p + nc, sizeof(tot), cudaMemcpyDeviceToHost, st));
+            for (int k = 0; k < 6; k++) {
+                k_ploc_nn<<<gc, 256, 0, st>>>(d_pst.p, radius, bin, d_nn.p);
+                k_ploc_flags<<<(nc + 256) / 256, 256, 0, st>>>(d_pst.p, d_nn.p, d_scan.p);
+                k_scan_exclusive64<<<1, 1024, 0, st>>>(d_scan.p, d_pst.p);
+                k_ploc_merge<<<gc, 256, 0, st>>>(d_pst.p, d_nn.p, d_scan.p, cin, bin, cout, bout, d_left.p, d_right.p, d_pint.p, d_pleaf.p);
+                k_ploc_advance<<<1, 1, 0, st>>>(d_pst.p, d_scan.p);
+                std::swap(cin, cout); std::swap(bin, bout);
+            }
+            CKF(cudaMemcpyAsync(h_st, d_pst.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
             CKF(cudaStreamSynchronize(st));
-            const int merges = (int)(uint32_t)(tot >> 32), left_over = (int)(uint32_t)tot;
-            if (merges <= 0 || left_over != nc - merges) { free_all(); return set_err("agglomerative build made no progress (internal error)"); }
-            nc = left_over; next_id -= merges; rounds++;
-            std::swap(cin, cout); std::swap(bin, bout);
+            if (h_st[0] >= nc || h_st[0] < 1) { free_all(); return set_err("agglomerative build made no progress (internal error)"); }
+            nc = h_st[0]; rounds = h_st[2];
         }
-        (void)rounds;
+        if (h_st[1] != -1) { free_all(); return set_err("agglomerative build: node count mismatch (internal error)"); }
+        if (stats) stats->rounds = rounds;
         k_fit_counts<<<g, 256, 0, st>>>(d_boxes.p, vin, n, d_left.p, d_right.p, d_pint.p, d_pleaf.p, d_flags.p, d_nbox.p, d_cost.p, d_collapse.p, d_count.p, d_ecount.p);
         k_tree_order<<<(2 * n - 1 + 255) / 256, 256, 0, st>>>(n, d_left.p, d_right.p, d_pint.p, d_pleaf.p, d_count.p, d_ecount.p, d_first.p, d_last.p, d_emit.p, d_slot.p);
         k_leaf_remap<<<g, 256, 0, st>>>(n, d_slot.p, vin, d_pleaf.p, d_vals2.p, d_pleaf2.p, d_left.p, d_right.p);
@@ -96,6 +105,7 @@ int ctl_bvh_build_gpu_ex(int device, const float* verts9, uint32_t n_tris, int a
         k_single_leaf_root<<<1, 32, 0, st>>>(d_sbox.p, n, d_nodes.p, d_lastflag.p);
     }
     k_emit_tris<<<g, 256, 0, st>>>(d_verts.p, vin, n, d_lastflag.p, d_woop.p, d_index.p);
+    if (stats && n > MAX_LEAF) CKF(cudaMemcpyAsync(&stats->sah_cost, d_cost.p, sizeof(float), cudaMemcpyDeviceToHost, st));   // SAH cost of the root (C_inner 1.2, C_tri 1, unnormalised)
     CKF(cudaGetLastError());
     CKF(cudaEventRecord(e1, st));
     CKF(cudaStreamSynchronize(st));
@@ -108,19 +118,37 @@ int ctl_bvh_build_gpu_ex(int device, const float* verts9, uint32_t n_tris, int a
 #undef CKF
     *n_nodes_out = n_nodes;
     if (build_ms) *build_ms = ms;
-    if (algorithm == 1 && tree_depth(nodes_out, n_nodes) > 56) {   // pathological input (merge chains): the LBVH's depth is bounded by the key length
-        float ms2 = 0;
-        const int rc = ctl_bvh_build_gpu_ex(device, verts9, n_tris, 0, 0, nodes_out, n_nodes_out, woop_out, index_out, &ms2);
-        if (build_ms) *build_ms = ms + ms2;
-        return rc;
+    return 0;
+}
+
+// algorithm 0 = LBVH, 1 = agglomerative (PLOC), 2 = both, keep the tree with the lower SAH cost
+int ctl_bvh_build_gpu_ex(int device, const float* verts9, uint32_t n_tris, int algorithm, int radius, ctl_bvh_node* nodes_out, uint32_t* n_nodes_out, ctl_woop_tri* woop_out, uint32_t* index_out, float* build_ms) {
+    if (algorithm < 0 || algorithm > 2) return set_err("algorithm must be 0 (LBVH), 1 (agglomerative, PLOC) or 2 (both, lower SAH cost wins)");
+    const bool verbose = getenv("CTL_GPU_BUILDER_VERBOSE") != nullptr;
+    GpuBuildStats sa, sb; float ms_a = 0, ms_b = 0;
+    if (build_gpu(device, verts9, n_tris, algorithm == 0 ? 0 : 1, radius, nodes_out, n_nodes_out, woop_out, index_out, &ms_a, &sa)) return 1;
+    if (build_ms) *build_ms = ms_a;
+    if (algorithm == 0 || n_tris <= (uint32_t)ctlbvh::MAX_LEAF) return 0;
+    const int depth = tree_depth(nodes_out, *n_nodes_out);
+    if (verbose) fprintf(stderr, "[ctl gpu builder] PLOC: %u triangles, %d rounds, %u nodes, depth %d, SAH cost %.6g, %.2f ms\n", n_tris, sa.rounds, *n_nodes_out, depth, sa.sah_cost, ms_a);
+    if (algorithm == 1 && depth <= 56) return 0;   // (deeper: pathological input, merge chains -- the LBVH's depth is bounded by the key length)
+    std::vector<ctl_bvh_node> nodes2(n_tris); std::vector<ctl_woop_tri> woop2(n_tris); std::vector<uint32_t> index2(n_tris); uint32_t nn2 = 0;
+    if (build_gpu(device, verts9, n_tris, 0, 0, nodes2.data(), &nn2, woop2.data(), index2.data(), &ms_b, &sb)) return 1;
+    if (verbose) fprintf(stderr, "[ctl gpu builder] LBVH: %u nodes, SAH cost %.6g, %.2f ms\n", nn2, sb.sah_cost, ms_b);
+    if (build_ms) *build_ms = ms_a + ms_b;
+    if (depth > 56 || sb.sah_cost < sa.sah_cost) {
+        memcpy(nodes_out, nodes2.data(), (size_t)nn2 * sizeof(ctl_bvh_node)); memcpy(woop_out, woop2.data(), (size_t)n_tris * sizeof(ctl_woop_tri)); memcpy(index_out, index2.data(), (size_t)n_tris * 4);
+        *n_nodes_out = nn2;
     }
     return 0;
 }
 
-// Default builder: the agglomerative one; CTL_GPU_BUILDER=lbvh selects the LBVH, CTL_PLOC_RADIUS the search window (default 16).
+// Default builder: the agglomerative one; CTL_GPU_BUILDER=lbvh selects the LBVH, =auto builds both and keeps the tree with the lower SAH cost;
+// CTL_PLOC_RADIUS: the search window (default 16).
 int ctl_bvh_build_gpu(int device, const float* verts9, uint32_t n_tris, ctl_bvh_node* nodes_out, uint32_t* n_nodes_out, ctl_woop_tri* woop_out, uint32_t* index_out, float* build_ms) {
     const char* a = getenv("CTL_GPU_BUILDER"); const char* r = getenv("CTL_PLOC_RADIUS");
-    return ctl_bvh_build_gpu_ex(device, verts9, n_tris, (a && std::string(a) == "lbvh") ? 0 : 1, r ? atoi(r) : 0, nodes_out, n_nodes_out, woop_out, index_out, build_ms);
+    const std::string alg = a ? a : "ploc";
+    return ctl_bvh_build_gpu_ex(device, verts9, n_tris, alg == "lbvh" ? 0 : alg == "auto" ? 2 : 1, r ? atoi(r) : 0, nodes_out, n_nodes_out, woop_out, index_out, build_ms);
 }
 
 // Rebuild every mesh BVH of a host scene on the GPU (node / Woop / index arrays, mesh offsets, light-triangle slots).

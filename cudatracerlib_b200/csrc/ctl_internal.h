@@ -83,7 +83,7 @@ struct ctl_ctx {
     ctlb::SamplerTableGenerator gen;
     // wavefront state: lane 0 runs on `stream`; lanes 1.. (own streams) hold the other wavefronts of a frame rendered with "OverlapWavefronts" (ctl_comm_render_frame)
     WaveLane lanes[MAX_LANES]; DevBuf<float4> capture;
-    cudaStream_t lane_stream[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr}; int overlap = 1, n_lanes = 2;
+    cudaStream_t lane_stream[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr}; int overlap = 0, n_lanes = 2;   // off by default: measured (profiles/r02j-r02o_part_probe_*.log) -- the end-of-launch drain is the latency of the rays in flight, whose warps keep their slots until their last lane finishes, so a second lane's blocks cannot move in
     DevBuf<unsigned> api_work; unsigned api_seq = 0;   // ring of work counters of the API traversal launches: calls in flight on different streams never share one
     // WavefrontPathTracer queue (DoubleRayBuffer<WavefrontPTRayData>)
     DevBuf<float4> w_thr, w_lxy, w_df, w_ray, w_sec[2]; DevBuf<uint2> w_misc; DevBuf<uint4> w_res, w_sres[2]; DevBuf<unsigned long long> w_desc;
@@ -98,7 +98,7 @@ struct ctl_ctx {
     std::vector<cudaEvent_t> stage_ev; std::vector<int> stage_kind;
     float stage_ms[5] = {0, 0, 0, 0, 0}; uint32_t n_launches = 0;
     bool instrumented = false;
-    TravTune tune = {2, 8, 8, 6, 2}, tune_p = {2, 8, 8, 4, 1};   // scheduler parameters of the staged kernel (swept on the device: profiles/r02c_tune_sweep.log) / of the persistent kernel (profiles/r01d_*)
+    TravTune tune = {2, 8, 8, 6, 2, 32, 0}, tune_p = {2, 8, 8, 4, 1, 0, 0};   // scheduler parameters of the staged kernel (swept on the device: profiles/r02c_tune_sweep.log) / of the persistent kernel (profiles/r01d_*)
     // staged traversal kernel (device/traverse_staged.cuh): derived records + launch shape
     DevBuf<float4> d_tri64, d_inst, d_treelet; StagedScene staged = {nullptr, nullptr, nullptr, 0, 0, 16, 0}; bool staged_ok = false; std::string staged_why;
     int shade_mode = 1; uint32_t class_mask = 0; bool class_ok = false;   // "ShadeMode": 0 = one k_shade with the run-time BSDF dispatch, 1 = one launch per material class present (staged kernel only)

@@ -32,7 +32,7 @@ struct TravOut { // where results go (MODE-dependent, see k_intersect)
     unsigned* cls_hist;   // staged kernel, MODE 0 / 4: 8 counters of this bounce's hit records by material class (null = not wanted)
 };
 
-struct TravTune { int th_t, th_l, th_f, th_n_exit, t_steps; }; // lane thresholds of the T / L / F blocks; th_n_exit = node steps per iteration; t_steps = triangle tests per iteration (staged kernel)
+struct TravTune { int th_t, th_l, th_f, th_n_exit, t_steps, chunk, drain_prefetch; }; // lane thresholds of the T / L / F blocks; th_n_exit = node steps per iteration; t_steps = triangle tests per iteration (staged kernel); chunk = rays per claim (0 = by queue size); drain_prefetch = 1: once the queue is exhausted, every node step prefetches both children (staged kernel)
 
 template <int MODE, bool ANY_HIT, bool COUNT>
 __device__ __forceinline__ void trace_persistent(const DScene& S, const float4* __restrict__ rays, int n, unsigned* work_ctr, const TravOut& out,

@@ -38,6 +38,11 @@ constexpr int ST_NEEDS_W = 2;  // root word bit 1: the instance's inverse transf
 CTL_DEV int tl_chunk(int n, int j) { return n * 4 + (j ^ ((n >> 1) & 3)); }
 
 CTL_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+CTL_DEV void prefetch_l1(const void* p) {
+#ifdef __CUDACC__
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#endif
+}
 
 // One CTA-wide TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP + SYNCS).  Called by every thread of the CTA.
 CTL_DEV void tma_fill(void* dst_smem, const void* src_gmem, uint32_t bytes, void* bar_smem) {
@@ -123,7 +128,7 @@ __device__ __forceinline__ void trace_staged(const DScene& S, const StagedScene&
     auto pop = [&]() { const int r = tos; tos = sp <= SD ? ss[sp * NT] : ovf[sp - SD - 1]; sp--; return r; }; // row 0 is never written: read (and ignored) by the last pop of a ray
 
     const int n_warps = (int)(gridDim.x * (blockDim.x >> 5));
-    const int chunk = max(32, min(TP_CHUNK, (n / (n_warps * 8)) & ~31));
+    const int chunk = tune.chunk > 0 ? tune.chunk : max(32, min(TP_CHUNK, (n / (n_warps * 8)) & ~31));
     int pool_next = 0, pool_end = 0;
     bool exhausted = (n <= 0);
 
@@ -276,6 +281,7 @@ __device__ __forceinline__ void trace_staged(const DScene& S, const StagedScene&
             }
         }
 
+        const bool drain = exhausted && tune.drain_prefetch;
         // ---- N: up to N_STEPS inner-node steps for every lane that has one.  Inside the block a lane only asks "still an inner node?"; its
         // state is classified once, on leaving
         if (state == 0) {
@@ -301,6 +307,11 @@ __device__ __forceinline__ void trace_staged(const DScene& S, const StagedScene&
                 const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), box_lo));
                 const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), rayT));
                 const bool swp = (c1min < c0min), t0 = (c0max >= c0min), t1 = (c1max >= c1min);
+                if (drain) { // the launch is draining: what is left are its longest rays, each alone in its warp and paced by the node-fetch latency -- bring the
+                             // children that will be visited into L1 while the slab tests run (a loss in the throughput regime, profiles/r01k_*: hence only here)
+                    if (t0 && c0 >= 0 && !(c0 & ST_TL)) { prefetch_l1(nbase + c0); prefetch_l1(nbase + c0 + 2); }
+                    if (t1 && c1 >= 0 && !(c1 & ST_TL)) { prefetch_l1(nbase + c1); prefetch_l1(nbase + c1 + 2); }
+                }
                 if (!t0 && !t1) nodeAddr = pop();
                 else {
                     nodeAddr = t0 ? c0 : c1;

@@ -335,9 +335,11 @@ int ctl_render_pass_tiled(ctl_ctx*, int new_trace, int tile_w, int tile_h, int p
  * overhead; path state is ~230 B x pixels x n_passes of HBM.  part=0, n_parts=1 renders the whole image. */
 int ctl_render_passes_tiled(ctl_ctx*, int new_trace, int n_passes, int tile_w, int tile_h, int part, int n_parts);
 /* One progressive FRAME (== StartNewTrace + spp DoPass calls, Kernel/Tracer.h:209-248) on the tiles of `part`, `batch` passes fused per wavefront
- * (spp % batch == 0).  With "OverlapWavefronts" (default 1) the frame's wavefronts alternate between two streams with their own wavefront buffers (a
- * frame of one wavefront is cut into two half-batches), so the draining tail of one persistent traversal launch overlaps the head of the other's;
- * the paths traced are identical either way.  Asynchronous on the context's stream (the second stream is joined before the call returns work to it). */
+ * (spp % batch == 0).  With "OverlapWavefronts" = 1 (default 0; "OverlapLanes" 2..4 streams) the frame's wavefronts alternate between streams with
+ * their own wavefront buffers (a frame of fewer wavefronts than lanes is cut into smaller batches), so that the draining end of one persistent traversal
+ * launch can overlap the head of another's; the paths traced are identical either way.  Measured on the 1 M-triangle scene at 1/8 of the image per
+ * GPU: 37.6 ms per frame with or without, hence off.  Asynchronous on the context's stream (the other streams are joined before
+ * the call returns work to it). */
 int ctl_render_frame_tiled(ctl_ctx*, int spp, int batch, int tile_w, int tile_h, int part, int n_parts);
 /* == WavefrontPathTracer: Tracer<true>::DoPass + WavefrontPathTracer::DoRender (Kernel/Tracer.h:209-248,
  *    Integrators/PseudoRealtime/WavefrontPathTracer.cu:166-191) over a DoubleRayBuffer-shaped device queue (Kernel/DoubleRayBuffer.h):

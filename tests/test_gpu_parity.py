@@ -535,7 +535,7 @@ def _depth(nodes):
     return d
 
 
-@pytest.mark.parametrize("algorithm", [1, 0])
+@pytest.mark.parametrize("algorithm", [1, 0, 2])
 def test_gpu_bvh_build_api_edge_cases(built_lib, orc, algorithm):
     L = built_lib
     L.ctl_bvh_build_gpu_ex.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -557,7 +557,7 @@ def test_gpu_bvh_build_api_edge_cases(built_lib, orc, algorithm):
             ref = orc.encode_woop(verts[t, 0:3], verts[t, 3:6], verts[t, 6:9])
             assert np.array_equal(woop[s_].view(np.uint32), ref.view(np.uint32)) or (np.isnan(ref).all() and np.isnan(woop[s_]).all())   # zero-area triangle: NaN both (payload bits differ host / device)
     assert L.ctl_bvh_build_gpu(0, None, 0, None, None, None, None, None) != 0
-    assert L.ctl_bvh_build_gpu_ex(0, verts.ctypes.data, 8, 2, 0, nodes.ctypes.data, C.byref(nn), woop.ctypes.data, index.ctypes.data, None) != 0   # unknown algorithm
+    assert L.ctl_bvh_build_gpu_ex(0, verts.ctypes.data, 8, 3, 0, nodes.ctypes.data, C.byref(nn), woop.ctypes.data, index.ctypes.data, None) != 0   # unknown algorithm
 
 
 def test_gpu_bvh_build_is_deterministic(built_lib):
