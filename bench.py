@@ -268,7 +268,9 @@ def measure_workload(name, args, torch, dist, world, rank, local, dev, stream, s
     d_rgba = torch.empty(h * w * 4, dtype=torch.uint8, device=dev)
     host_rgba = torch.empty(h * w * 4, dtype=torch.uint8, pin_memory=True)
     table_bytes = 4096 * 30 * 12
-    batch = min(spp, args.batch)
+    batch = min(spp, args.batch if args.batch > 0 else (16 if spp >= 32 else 8))   # frames of many passes (configs[4]): 16 per wavefront, the wavefronts overlapped on lanes (ctl_render_frame_tiled)
+    if spp % batch:
+        raise SystemExit(f"--batch {batch} does not divide spp {spp}")
 
     def render_pass(p, new_trace):
         # `batch` progressive passes fused into one wavefront (ctl_render_passes_tiled) on this rank's tiles
@@ -414,7 +416,7 @@ def measure_workload(name, args, torch, dist, world, rank, local, dev, stream, s
             "metric": baseline_metric(), "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": static_config(name, scene, world, tile),
-            "rays_per_step": rays_frame, "passes_per_wavefront": batch,
+            "rays_per_step": rays_frame, "passes_per_wavefront": batch, "wavefront_lanes": (tracer.getParameter("OverlapLanes") if tracer.getParameter("OverlapWavefronts") and spp > batch else 1),
             "scene_level": {"leaves": int(scene.view.n_nodes), "re_braided": bool(scene.view.node_alias)},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": spp * table_bytes, "d2h_bytes_per_step": h * w * 4,
@@ -445,7 +447,7 @@ def main():
     ap.add_argument("--sort-mode", type=int, default=None)
     ap.add_argument("--set", action="append", default=[], metavar="KEY=INT", help="extra tracer parameter (ctl_set_param_i), for A/B runs")
     ap.add_argument("--tile", type=int, default=0, help="tile edge for the multi-GPU partition (0 = package default)")
-    ap.add_argument("--batch", type=int, default=8, help="progressive passes fused into one wavefront (must divide spp)")
+    ap.add_argument("--batch", type=int, default=0, help="progressive passes fused into one wavefront (must divide spp; 0 = 8, or 16 for frames of >= 32 passes)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: W >= 3

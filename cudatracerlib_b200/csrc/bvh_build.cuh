@@ -226,10 +226,12 @@ __global__ void k_emit_nodes(int n, const int* __restrict__ left, const int* __r
 }
 
 // one thread per sorted slot: Woop data + index word
-__global__ void k_emit_tris(const float* __restrict__ verts9, const uint32_t* __restrict__ vals, int n, const unsigned char* __restrict__ last_flag, ctl_woop_tri* __restrict__ woop, uint32_t* __restrict__ index) {
+// (ref_tri: triangle of every reference when the triangles were pre-split, bvh_presplit.cuh; nullptr = reference i is triangle i)
+__global__ void k_emit_tris(const float* __restrict__ verts9, const uint32_t* __restrict__ vals, int n, const unsigned char* __restrict__ last_flag, ctl_woop_tri* __restrict__ woop, uint32_t* __restrict__ index,
+                            const uint32_t* __restrict__ ref_tri = nullptr) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    const uint32_t p = vals[s];
+    const uint32_t p = ref_tri ? ref_tri[vals[s]] : vals[s];
     const float* v = verts9 + (size_t)p * 9;
     ctl_woop_tri w;
     ctlb::encode_woop(ctlb::V3(v[0], v[1], v[2]), ctlb::V3(v[3], v[4], v[5]), ctlb::V3(v[6], v[7], v[8]), &w);

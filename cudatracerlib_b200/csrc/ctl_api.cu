@@ -107,6 +107,7 @@ void ctl_destroy(ctl_ctx* c) {
     c->d_light_cdf.release(); c->d_normal_lut.release(); c->d_tri64.release(); c->d_inst.release(); c->d_treelet.release();
     c->d_tab1.release(); c->d_tab2.release(); c->d_states.release(); c->d_states0.release(); c->d_jump.release();
     if (c->h_tab1) cudaFreeHost(c->h_tab1); if (c->h_tab2) cudaFreeHost(c->h_tab2); if (c->h_tab_free) cudaEventDestroy(c->h_tab_free);
+    if (c->tab_stream) { cudaStreamSynchronize(c->tab_stream); cudaStreamDestroy(c->tab_stream); } if (c->ev_tab) cudaEventDestroy(c->ev_tab);
     for (int k = 1; k < MAX_LANES; k++) { if (c->lane_stream[k]) { cudaStreamSynchronize(c->lane_stream[k]); cudaStreamDestroy(c->lane_stream[k]); } if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (int k = 0; k < MAX_LANES; k++) c->lanes[k].release();
@@ -144,8 +145,8 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "CaptureBounce") c->capture_bounce = v;
     else if (k == "DeviceSampleTables") c->device_tables = v != 0;
     else if (k == "FuseTraversal") c->fuse_traversal = v != 0;
-    else if (k == "OverlapWavefronts") c->overlap = v != 0;
-    else if (k == "OverlapLanes") { if (v < 1 || v > MAX_LANES) return set_err("OverlapLanes out of range [1,4]"); c->n_lanes = v; }   // wavefronts of a frame in flight at once   // ctl_render_frame_tiled / ctl_comm_render_frame: the frame's wavefronts alternate between two streams
+    else if (k == "OverlapWavefronts") { if (v < 0 || v > 2) return set_err("OverlapWavefronts must be 0, 1 or 2"); c->overlap = v; }
+    else if (k == "OverlapLanes") { if (v < 1 || v > MAX_LANES) return set_err("OverlapLanes out of range [1,8]"); c->n_lanes = v; }   // wavefronts of a frame in flight at once   // ctl_render_frame_tiled / ctl_comm_render_frame: the frame's wavefronts alternate between two streams
     else if (k == "PixelVarianceBuffer") c->variance_buffer = v != 0;
     else if (k == "WarpPixelBlocks") c->warp_blocks = v != 0;
     else if (k == "PassStride") { if (v < 1) return set_err("PassStride must be >= 1"); c->pass_stride = v; }   // multi-GPU by pass: this context renders passes PassPhase + k * PassStride
@@ -292,26 +293,30 @@ int ctl_upload_samples(ctl_ctx* c, const float* d1, const float* d2) {
     return 0;
 }
 
-// Tables of passes [first, first + n) into the device table sets 0..n-1 (GenerateNewRandomSequences, Kernel/Sampler.h:36-55)
-static int generate_tables(ctl_ctx* c, uint32_t first, int n) {
-    if (ensure_tables(c, n)) return 1;
+// Tables of passes [first, first + n) into the device table sets set0 .. set0+n-1 (GenerateNewRandomSequences, Kernel/Sampler.h:36-55), on stream `st`.
+// Host mode: the caller has made sure the pinned sets it overwrites are free (h_tab_free).
+static int generate_tables(ctl_ctx* c, uint32_t first, int n, int set0 = 0, cudaStream_t st = nullptr, bool wait_free = true) {
+    if (!st) st = c->stream;
+    if (ensure_tables(c, set0 + n)) return 1;
+    float* d1 = c->d_tab1.p + TAB1 * set0; float* d2 = c->d_tab2.p + TAB2 * set0;
     if (c->device_tables) {
         if (c->gen_pos_dev != first) { // re-synchronise the device stream position (mode switch / user tables / strided passes): skip forward, or restart
             uint32_t from = c->gen_pos_dev;
-            if (from > first) { CK(cudaMemcpyAsync(c->d_states.p, c->d_states0.p, (size_t)ctlb::kNumSeq * 6 * 4, cudaMemcpyDeviceToDevice, c->stream)); from = 0; }
-            for (uint32_t p = from; p < first; p++) k_gen_tables<<<ctlb::kNumSeq / 128, 128, 0, c->stream>>>(c->d_states.p, c->d_jump.p, 1, c->d_tab1.p, (float2*)c->d_tab2.p);
+            if (from > first) { CK(cudaMemcpyAsync(c->d_states.p, c->d_states0.p, (size_t)ctlb::kNumSeq * 6 * 4, cudaMemcpyDeviceToDevice, st)); from = 0; }
+            for (uint32_t p = from; p < first; p++) k_gen_tables<<<ctlb::kNumSeq / 128, 128, 0, st>>>(c->d_states.p, c->d_jump.p, 1, d1, (float2*)d2);
         }
-        k_gen_tables<<<ctlb::kNumSeq / 128, 128, 0, c->stream>>>(c->d_states.p, c->d_jump.p, n, c->d_tab1.p, (float2*)c->d_tab2.p);
+        k_gen_tables<<<ctlb::kNumSeq / 128, 128, 0, st>>>(c->d_states.p, c->d_jump.p, n, d1, (float2*)d2);
         CK(cudaGetLastError());
         c->gen_pos_dev = first + n;
     } else {
-        if (ensure_host_tables(c, n)) return 1;
-        CK(cudaEventSynchronize(c->h_tab_free));
-        if (c->gen_pos_host != first) { uint32_t from = c->gen_pos_host; if (from > first) { c->gen.reset(); from = 0; } for (uint32_t p = from; p < first; p++) c->gen.next_pass(c->h_tab1, c->h_tab2); }
-        for (int p = 0; p < n; p++) c->gen.next_pass(c->h_tab1 + TAB1 * p, c->h_tab2 + TAB2 * p);
-        CK(cudaMemcpyAsync(c->d_tab1.p, c->h_tab1, TAB1 * 4 * n, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(c->d_tab2.p, c->h_tab2, TAB2 * 4 * n, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaEventRecord(c->h_tab_free, c->stream));
+        if (ensure_host_tables(c, set0 + n)) return 1;
+        if (wait_free) CK(cudaEventSynchronize(c->h_tab_free));
+        float* h1 = c->h_tab1 + TAB1 * set0; float* h2 = c->h_tab2 + TAB2 * set0;
+        if (c->gen_pos_host != first) { uint32_t from = c->gen_pos_host; if (from > first) { c->gen.reset(); from = 0; } for (uint32_t p = from; p < first; p++) c->gen.next_pass(h1, h2); }
+        for (int p = 0; p < n; p++) c->gen.next_pass(h1 + TAB1 * p, h2 + TAB2 * p);
+        CK(cudaMemcpyAsync(d1, h1, TAB1 * 4 * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d2, h2, TAB2 * 4 * n, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(c->h_tab_free, st));
         c->gen_pos_host = first + n;
     }
     return 0;
@@ -584,15 +589,17 @@ int ctl_render_passes_tiled(ctl_ctx* c, int new_trace, int n_passes, int tile_w,
 int ctl_render_frame_tiled(ctl_ctx* c, int spp, int batch, int tile_w, int tile_h, int part, int n_parts) {
     if (!c) return set_err("null context");
     if (spp < 1 || batch < 1 || spp % batch) return set_err("spp must be a positive multiple of batch");
+    // "OverlapWavefronts": 0 = never; 1 (default) = when the frame has several wavefronts anyway (spp > batch: the lanes come for free); 2 = also cut the batches
+    // of a frame with fewer wavefronts than lanes (measured: what the overlap gains, the extra launches lose)
     const bool plain = !c->overlap || c->stage_timers || c->instrumented || c->capture_bounce > 0 || c->variance_buffer || c->user_tables || c->sort_mode != 0 || spp > 128 ||
-                       (spp == batch && (batch & 1)) || c->n_lanes < 2;
+                       c->n_lanes < 2 || (c->overlap == 1 ? spp == batch : (spp == batch && (batch & 1)));
     if (plain) {
         for (int p = 0; p < spp; p += batch)
             if (ctl_render_passes_tiled(c, p == 0, batch, tile_w, tile_h, part, n_parts)) return 1;
         return 0;
     }
     const int n_lanes = c->n_lanes;
-    while (spp / batch < n_lanes && batch % 2 == 0) batch /= 2;   // fewer wavefronts than lanes: cut the batches
+    if (c->overlap >= 2) while (spp / batch < n_lanes && batch % 2 == 0) batch /= 2;   // fewer wavefronts than lanes: cut the batches
     Window W;
     if (tiled_window(c, W, batch, tile_w, tile_h, part, n_parts)) return 1;
     if (!c->has_scene) return set_err("no scene uploaded");
@@ -602,18 +609,27 @@ int ctl_render_frame_tiled(ctl_ctx* c, int spp, int batch, int tile_w, int tile_
         CK(cudaStreamCreateWithFlags(&c->lane_stream[k], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
     }
+    if (!c->tab_stream) { CK(cudaStreamCreateWithFlags(&c->tab_stream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->ev_tab, cudaEventDisableTiming)); }
     CK(cudaEventRecord(c->ev_start, c->stream));
     CK(cudaMemsetAsync(c->accum, 0, (size_t)c->w * c->h * 7 * sizeof(float), c->stream));
     c->passes_done = 0;
     if (W.n_slots == 0) CK(cudaMemsetAsync(c->stats.p, 0, sizeof(unsigned long long), c->stream));
     else {
-        if (generate_tables(c, 0, spp)) return 1;   // the table sets of all passes of the frame, before the lanes fork
+        // the frame keeps one table set per pass; each wavefront's sets are produced on the table stream just before the wavefront is enqueued, so that host-generated
+        // tables (DeviceSampleTables = 0) of wavefront k+1 are computed while the device renders wavefront k, and no lane waits for another lane's work
+        if (ensure_tables(c, spp)) return 1;
+        if (!c->device_tables) { if (ensure_host_tables(c, spp)) return 1; CK(cudaEventSynchronize(c->h_tab_free)); }   // the previous frame's copies have left the pinned sets
         CK(cudaEventRecord(c->ev_fork, c->stream));
+        CK(cudaStreamWaitEvent(c->tab_stream, c->ev_fork, 0));
         for (int k = 1; k < n_lanes; k++) CK(cudaStreamWaitEvent(c->lane_stream[k], c->ev_fork, 0));
         uint32_t launches = 0;
         for (int p = 0, i = 0; p < spp; p += batch, i++) {
+            const int lane = i % n_lanes;
+            if (generate_tables(c, (uint32_t)p, batch, p, c->tab_stream, false)) return 1;
+            CK(cudaEventRecord(c->ev_tab, c->tab_stream));
+            CK(cudaStreamWaitEvent(lane ? c->lane_stream[lane] : c->stream, c->ev_tab, 0));
             W.tab0 = p;
-            if (render_window(c, 0, W, i % n_lanes, true)) return 1;
+            if (render_window(c, 0, W, lane, true)) return 1;
             launches += c->n_launches;
         }
         c->n_launches = launches;

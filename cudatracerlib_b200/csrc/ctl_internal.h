@@ -27,7 +27,7 @@ int ctl_set_err(const std::string& s);
 struct ctl_scene { ctlb::SceneStorage S; };
 
 const int MAX_BOUNCES = 256;
-const int MAX_LANES = 4;   // wavefronts of a frame in flight at once (OverlapWavefronts / OverlapLanes)
+const int MAX_LANES = 8;   // wavefronts of a frame in flight at once (OverlapWavefronts / OverlapLanes)
 const unsigned API_WORK_RING = 256;
 enum { CTR_Q = 0, CTR_SH = MAX_BOUNCES + 1, CTR_WORK = 2 * (MAX_BOUNCES + 1), CTR_TOTAL = 4 * (MAX_BOUNCES + 1) };
 
@@ -83,7 +83,8 @@ struct ctl_ctx {
     ctlb::SamplerTableGenerator gen;
     // wavefront state: lane 0 runs on `stream`; lanes 1.. (own streams) hold the other wavefronts of a frame rendered with "OverlapWavefronts" (ctl_comm_render_frame)
     WaveLane lanes[MAX_LANES]; DevBuf<float4> capture;
-    cudaStream_t lane_stream[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr}; int overlap = 0, n_lanes = 2;   // off by default: measured (profiles/r02j-r02o_part_probe_*.log) -- the end-of-launch drain is the latency of the rays in flight, whose warps keep their slots until their last lane finishes, so a second lane's blocks cannot move in
+    cudaStream_t lane_stream[MAX_LANES] = {}; cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {}; cudaStream_t tab_stream = nullptr; cudaEvent_t ev_tab = nullptr;   // tab_stream: sample tables of a frame's wavefronts
+    int overlap = 1, n_lanes = 4;   // "OverlapWavefronts", "OverlapLanes": see ctl_render_frame_tiled
     DevBuf<unsigned> api_work; unsigned api_seq = 0;   // ring of work counters of the API traversal launches: calls in flight on different streams never share one
     // WavefrontPathTracer queue (DoubleRayBuffer<WavefrontPTRayData>)
     DevBuf<float4> w_thr, w_lxy, w_df, w_ray, w_sec[2]; DevBuf<uint2> w_misc; DevBuf<uint4> w_res, w_sres[2]; DevBuf<unsigned long long> w_desc;
@@ -102,7 +103,7 @@ struct ctl_ctx {
     // staged traversal kernel (device/traverse_staged.cuh): derived records + launch shape
     DevBuf<float4> d_tri64, d_inst, d_treelet; StagedScene staged = {nullptr, nullptr, nullptr, 0, 0, 16, 0}; bool staged_ok = false; std::string staged_why;
     int shade_mode = 1; uint32_t class_mask = 0; bool class_ok = false;   // "ShadeMode": 0 = one k_shade with the run-time BSDF dispatch, 1 = one launch per material class present (staged kernel only)
-    int staged_threads = 512, staged_rows = 16, staged_treelet = 0, staged_resident = 1024;   // "StagedThreads", "StagedStackRows", "StagedTreeletNodes", "StagedResidentThreads"
+    int staged_threads = 128, staged_rows = 16, staged_treelet = 0, staged_resident = 1024;   // "StagedThreads", "StagedStackRows", "StagedTreeletNodes", "StagedResidentThreads"
 };
 
 inline int grid_for(const ctl_ctx* c, int per_sm) { return c->n_sm * per_sm; }

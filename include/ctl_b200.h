@@ -265,10 +265,17 @@ int  ctl_validate_scene_view(const ctl_scene_view*);
  * optional device build time.  Deterministic. */
 int ctl_bvh_build_gpu(int device, const float* verts9, uint32_t n_tris, ctl_bvh_node* nodes_out, uint32_t* n_nodes_out,
                       ctl_woop_tri* woop_out, uint32_t* index_out, float* build_ms);
-/* The same with the builder named: algorithm 0 = LBVH, 1 = agglomerative (PLOC); radius <= 0 = default (16, at most 32). */
+/* The same with the builder named: algorithm 0 = LBVH, 1 = agglomerative (PLOC), 2 = both (the lower SAH cost wins); radius <= 0 = default (16, at most 32). */
 int ctl_bvh_build_gpu_ex(int device, const float* verts9, uint32_t n_tris, int algorithm, int radius, ctl_bvh_node* nodes_out,
                          uint32_t* n_nodes_out, ctl_woop_tri* woop_out, uint32_t* index_out, float* build_ms);
-/* Rebuild all mesh BVHs of a host scene with ctl_bvh_build_gpu (views obtained before the call are invalidated). */
+/* ... and with triangle pre-splitting (csrc/bvh_presplit.cuh): triangles whose box is much larger than the triangle -- long thin diagonals, where the
+ * reference's SplitBVHBuilder (SplitBVHBuilder.cpp:205-330) takes spatial splits -- are replaced by up to 16 references with the tight boxes of their
+ * clipped pieces before the tree is built; at most (1 + max_growth) * n_tris references in all (max_growth in [0, 8]; 0 = none).  The output arrays hold
+ * `capacity` (>= n_tris) entries each; *n_slots_out = references written to woop_out / index_out (a triangle may appear in several leaves). */
+int ctl_bvh_build_gpu_split(int device, const float* verts9, uint32_t n_tris, int algorithm, int radius, float max_growth, uint32_t capacity,
+                            ctl_bvh_node* nodes_out, uint32_t* n_nodes_out, ctl_woop_tri* woop_out, uint32_t* index_out, uint32_t* n_slots_out, float* build_ms);
+/* Rebuild all mesh BVHs of a host scene on the GPU (ctl_bvh_build_gpu_split; CTL_GPU_BUILDER, CTL_PLOC_RADIUS, CTL_GPU_SPLIT = reference growth budget,
+ * default 3, 0 = no pre-splitting).  Views obtained before the call are invalidated. */
 int ctl_scene_rebuild_bvh_gpu(ctl_scene*, int device, float* build_ms_total);
 /* encoders exposed for known-answer tests */
 void ctl_encode_woop(const float v0[3], const float v1[3], const float v2[3], ctl_woop_tri* out); /* TriIntersectorData.cu:5-18 */

@@ -9,6 +9,7 @@ from bench import WORKLOADS
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "c4"
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+parts_list = (1, 2, 4, 8)
 params = [a.split("=") for a in sys.argv[3:]]
 kind, w, h, spp, depth, _ = WORKLOADS[wl]
 scene = Scene(kind, w, h)
@@ -16,11 +17,13 @@ t = PathTracer(w, h); t.InitializeScene(scene); t.setParameter("MaxPathLength", 
 batch = 8
 for k, v in params:
     if k == "batch": batch = int(v)
+    elif k == "parts": parts_list = (int(v),)
+    elif k == "depth": t.setParameter("MaxPathLength", int(v))
     else: t.setParameter(k, int(v))
 stream = torch.cuda.Stream(); t.setStream(stream.cuda_stream)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 base = None
-for n_parts in (1, 2, 4, 8):
+for n_parts in parts_list:
     def frame(part=0):
         t.DoFrame(spp, batch, tile=(TILE, TILE), part=part, n_parts=n_parts)   # == what ctl_comm_render_frame runs on a rank before the reduce
     for _ in range(2): frame()
@@ -34,7 +37,7 @@ for n_parts in (1, 2, 4, 8):
     m = sorted(ms)[len(ms) // 2]
     if base is None: base = m
     rec = {"workload": wl, "params": dict(params), "n_parts": n_parts, "ms_part0": round(m, 3), "ideal_ms": round(base / n_parts, 3), "efficiency": round(base / n_parts / m, 4)}
-    if n_parts == 8:   # every part in turn: the slowest one is what an 8-GPU frame waits for
+    if n_parts == 8 and len(parts_list) > 1:   # every part in turn: the slowest one is what an 8-GPU frame waits for
         per = []
         for part in range(8):
             frame(part); torch.cuda.synchronize()

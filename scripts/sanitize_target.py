@@ -26,3 +26,27 @@ w.close()
 t = PathTracer(96, 64); t.InitializeScene(s); t.setParameter("MaxPathLength", 5); t.setParameter("SortMode", 2); t.DoPasses(2, new_trace=True); t.synchronize(); t.close()
 s2 = Scene("soup", 96, 64); s2.rebuildBVHOnGPU()
 print("all ok")
+# round-2 additions: staged traversal kernel variants (treelet through TMA, ray-queue TMA), per-class shade launches, frames on wavefront lanes,
+# re-braided scene level, the agglomerative GPU builder with and without triangle pre-splitting, NonLocalMeansFilter
+import ctypes as C
+from cudatracerlib_b200 import lib
+s3 = Scene("c3", 128, 72)
+t = PathTracer(128, 72); t.InitializeScene(s3); t.setParameter("MaxPathLength", 6)
+t.DoFrame(8, 2); t.setParameter("OverlapLanes", 8); t.DoFrame(8, 1); t.setParameter("OverlapWavefronts", 2); t.setParameter("OverlapLanes", 3); t.DoFrame(6, 6)
+t.setParameter("DeviceSampleTables", 0); t.DoFrame(4, 1); t.setParameter("DeviceSampleTables", 1)
+t.setParameter("StagedRayTMA", 1); t.DoPasses(2, new_trace=True); t.setParameter("StagedRayTMA", 0)
+t.setParameter("StagedTreeletNodes", 256); t.InitializeScene(s3); t.DoPasses(2, new_trace=True); t.setParameter("StagedTreeletNodes", 0); t.InitializeScene(s3)
+t.setParameter("ShadeMode", 0); t.DoPasses(2, new_trace=True); t.setParameter("TravDrainPrefetch", 1); t.DoPasses(1); t.setParameter("StopZeroThroughput", 0); t.DoPasses(1)
+t.synchronize(); out = t.applyImagePipeline(ImagePipeline(5)); print("round-2 frames ok", out.mean()); t.close()
+L = lib()
+L.ctl_bvh_build_gpu_split.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_float, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+rng = np.random.default_rng(3); n = 3000
+a = rng.uniform(-1, 1, size=(n, 3)); d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True); w3 = np.cross(d, rng.normal(size=(n, 3)))
+verts = np.concatenate([a, a + 0.8 * d, a + 0.4 * d + 0.02 * w3], axis=1).astype(np.float32); verts[:300] = verts[0]
+for alg, growth in ((1, 0.0), (1, 3.0), (0, 3.0), (2, 1.0)):
+    cap = int(n * (1 + growth)) + 1
+    nodes = np.zeros((cap, 16), np.float32); woop = np.zeros((cap, 12), np.float32); index = np.zeros(cap, np.uint32); nn = C.c_uint32(0); ns = C.c_uint32(0)
+    assert L.ctl_bvh_build_gpu_split(0, verts.ctypes.data, n, alg, 0, growth, cap, nodes.ctypes.data, C.byref(nn), woop.ctypes.data, index.ctypes.data, C.byref(ns), None) == 0
+s4 = Scene("soup", 96, 64); s4.setRebraid(64); s4.rebuildBVHOnGPU(); s4.validate()
+t = PathTracer(96, 64); t.InitializeScene(s4); t.DoPasses(2, new_trace=True); t.synchronize(); t.close()
+print("round-2 all ok")

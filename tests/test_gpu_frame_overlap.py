@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _frame(t, spp, batch, overlap, part=0, n_parts=1):
-    t.setParameter("OverlapWavefronts", overlap)
+    t.setParameter("OverlapWavefronts", 2 * overlap)
     r0 = t.getTotalRays()
     t.DoFrame(spp, batch, part=part, n_parts=n_parts); t.synchronize()
     return t.readAccumulator(), t.getTotalRays() - r0
@@ -20,7 +20,7 @@ def _frame(t, spp, batch, overlap, part=0, n_parts=1):
 def test_overlapped_frame_equals_sequential_frame(built_lib, kind, w, h, spp, batch, parts):
     s = ctl.Scene(kind, w, h)
     t = ctl.PathTracer(w, h); t.InitializeScene(s); t.setParameter("MaxPathLength", 8)
-    assert t.getParameter("OverlapWavefronts") == 0           # the default (measured: no gain)
+    assert t.getParameter("OverlapWavefronts") == 1           # the default: lanes when the frame has several wavefronts anyway; 2 also cuts the batches
     for part in range(min(parts, 2)):
         a, rays_a = _frame(t, spp, batch, 1, part, parts)
         assert t.getNumPassesDone() == spp
@@ -46,6 +46,24 @@ def test_overlapped_frame_matches_oracle(built_lib, orc):
     assert np.array_equal(img["weight_sum"], ref["weight_sum"])
     assert (rel <= 1e-3).mean() >= 0.99
     assert abs(rays - ref_rays) <= 5e-3 * ref_rays              # StopZeroThroughput=1 (default) ends zero-weight paths early
+    t.close()
+
+
+def test_frame_with_host_generated_tables_and_lanes(built_lib):
+    """DeviceSampleTables = 0 (tables from the host XORWOW twin, one set per pass of the frame, produced wavefront by wavefront on the table stream) renders the
+    frame the device generator renders; 1 .. 8 lanes render the same frame."""
+    w, h, spp, batch = 192, 128, 16, 2
+    s = ctl.Scene("soup", w, h)
+    t = ctl.PathTracer(w, h); t.InitializeScene(s); t.setParameter("MaxPathLength", 6)
+    ref = None
+    for lanes, dev in [(1, 1), (2, 1), (4, 0), (8, 1), (8, 0), (3, 0)]:
+        t.setParameter("OverlapLanes", lanes); t.setParameter("DeviceSampleTables", dev)
+        for _ in range(2):                                          # twice: the second frame restarts the sample stream and reuses the pinned sets
+            r0 = t.getTotalRays(); t.DoFrame(spp, batch); t.synchronize(); rays = t.getTotalRays() - r0
+            img = t.readAccumulator()
+            if ref is None: ref = (img, rays)
+            assert rays == ref[1] and np.array_equal(img["weight_sum"], ref[0]["weight_sum"])
+            assert np.allclose(img["rgb"], ref[0]["rgb"], rtol=2e-5, atol=1e-6)
     t.close()
 
 

@@ -497,7 +497,8 @@ def test_gpu_bvh_build_matches_cpu_bvh_results(built_lib, orc, kind, builder, mo
     s_cpu = ctl.Scene(kind, w, h); s_gpu = ctl.Scene(kind, w, h)
     ms = s_gpu.rebuildBVHOnGPU()
     s_gpu.validate()                                                                  # child / leaf references, tree shape, depth within the traversal stack
-    assert ms > 0 and s_gpu.view.n_woop == s_gpu.n_triangles == s_gpu.view.n_tri_index and s_cpu.view.n_woop >= s_cpu.n_triangles   # the CPU split BVH may duplicate references
+    assert ms > 0 and s_gpu.view.n_woop == s_gpu.view.n_tri_index >= s_gpu.n_triangles and s_cpu.view.n_woop >= s_cpu.n_triangles   # split trees (CPU: spatial splits, GPU: pre-split slivers) may reference a triangle from several leaves
+    assert s_gpu.view.n_woop <= 4 * s_gpu.n_triangles + 8                              # CTL_GPU_SPLIT budget (default: at most four times the triangles of a mesh)
     meshes = s_gpu.array("meshes"); tri_index = s_gpu.array("tri_index")[:, 0]; bvh = s_gpu.array("bvh_nodes")
     for mi, m in enumerate(meshes):
         node_off4, idx_off = int(m[1]), int(m[3])
@@ -508,7 +509,9 @@ def test_gpu_bvh_build_matches_cpu_bvh_results(built_lib, orc, kind, builder, mo
             assert 1 <= cnt <= 8
             covered[first:first + cnt] += 1
         assert np.all(covered == 1)                                                   # slots partitioned by the leaves
-        assert sorted((tri_index[idx_off:idx_off + n_slots] >> 1).tolist()) == list(range(n_slots))   # every triangle exactly once
+        tri_ids = np.unique(tri_index[idx_off:idx_off + n_slots] >> 1)
+        n_mesh_tris = (int(meshes[mi + 1][0]) if mi + 1 < len(meshes) else s_gpu.n_triangles) - int(m[0])
+        assert np.array_equal(tri_ids, np.arange(n_mesh_tris))                         # every triangle of the mesh is referenced (exactly once unless pre-split)
     # the oracle traverses the GPU-built tree and the CPU-built tree to the same hits
     rays = random_rays(s_cpu, 6000, seed=21)
     a = orc.trace_rays(s_cpu.view, rays); b = orc.trace_rays(s_gpu.view, rays)
@@ -558,6 +561,59 @@ def test_gpu_bvh_build_api_edge_cases(built_lib, orc, algorithm):
             assert np.array_equal(woop[s_].view(np.uint32), ref.view(np.uint32)) or (np.isnan(ref).all() and np.isnan(woop[s_]).all())   # zero-area triangle: NaN both (payload bits differ host / device)
     assert L.ctl_bvh_build_gpu(0, None, 0, None, None, None, None, None) != 0
     assert L.ctl_bvh_build_gpu_ex(0, verts.ctypes.data, 8, 3, 0, nodes.ctypes.data, C.byref(nn), woop.ctypes.data, index.ctypes.data, None) != 0   # unknown algorithm
+
+
+@pytest.mark.parametrize("algorithm", [1, 0])
+def test_gpu_bvh_presplit_slivers(built_lib, orc, algorithm):
+    """ctl_bvh_build_gpu_split on a mesh of long thin diagonal triangles (what the foliage of configs[3] is made of): references multiply within the budget,
+    every slot holds the Woop record of its triangle, every triangle is referenced, the tree is a valid reference-layout tree, and -- through a scene built
+    from the same mesh -- split and unsplit trees give the same hits on the device; the split tree needs fewer node visits."""
+    L = built_lib
+    L.ctl_bvh_build_gpu_split.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_float, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(11); n = 4000
+    a = rng.uniform(-1, 1, size=(n, 3)); d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    w = np.cross(d, rng.normal(size=(n, 3))); w /= np.linalg.norm(w, axis=1, keepdims=True)
+    verts = np.concatenate([a, a + 0.8 * d, a + 0.4 * d + 0.02 * w], axis=1).astype(np.float32)     # 40:1 slivers
+    verts[:50, 3:6] = verts[:50, 0:3] + np.float32(0.01); verts[:50, 6:9] = verts[:50, 0:3] + np.array([0.01, 0, 0], np.float32)   # and some small fat ones
+    out = {}
+    for growth in (0.0, 1.0, 3.0):
+        cap = int(n * (1 + growth)) + 1
+        nodes = np.zeros((cap, 16), np.float32); woop = np.zeros((cap, 12), np.float32); index = np.zeros(cap, np.uint32); nn = C.c_uint32(0); ns = C.c_uint32(0)
+        assert L.ctl_bvh_build_gpu_split(0, verts.ctypes.data, n, algorithm, 0, growth, cap, nodes.ctypes.data, C.byref(nn), woop.ctypes.data, index.ctypes.data, C.byref(ns), None) == 0, L.ctl_last_error()
+        assert n <= ns.value <= cap and (growth > 0) == (ns.value > n)
+        inner, leaves = _walk_reference_bvh(nodes[:nn.value], index[:ns.value], ns.value)
+        covered = np.zeros(ns.value, np.int32)
+        for first, cnt in leaves:
+            assert 1 <= cnt <= 8; covered[first:first + cnt] += 1
+        assert inner == nn.value and np.all(covered == 1) and _depth(nodes[:nn.value]) <= 60
+        assert np.array_equal(np.unique(index[:ns.value] >> 1), np.arange(n))
+        for s_ in rng.integers(0, ns.value, 300):
+            t = index[s_] >> 1
+            assert np.array_equal(woop[s_].view(np.uint32), orc.encode_woop(verts[t, 0:3], verts[t, 3:6], verts[t, 6:9]).view(np.uint32))
+        out[growth] = ns.value
+    assert out[3.0] >= out[1.0] > out[0.0] == n
+    assert L.ctl_bvh_build_gpu_split(0, verts.ctypes.data, n, algorithm, 0, 9.0, 10 * n, nodes.ctypes.data, C.byref(nn), woop.ctypes.data, index.ctypes.data, C.byref(ns), None) != 0   # growth out of range
+    assert L.ctl_bvh_build_gpu_split(0, verts.ctypes.data, n, algorithm, 0, 1.0, n - 1, nodes.ctypes.data, C.byref(nn), woop.ctypes.data, index.ctypes.data, C.byref(ns), None) != 0    # capacity below n_tris
+
+
+def test_gpu_bvh_presplit_scene_hits(built_lib, orc, monkeypatch):
+    """The 1 M-triangle scene's foliage mesh through ctl_scene_rebuild_bvh_gpu with and without pre-splitting: identical closest hits (the same Woop tests
+    decide them), fewer inner-node visits with the split tree."""
+    w, h = 96, 54
+    rays = None; res = {}
+    for split in ("0", "1"):
+        monkeypatch.setenv("CTL_GPU_SPLIT", "0" if split == "0" else "2")
+        s = ctl.Scene("c4", w, h); s.setRebraid(0); s.rebuildBVHOnGPU(); s.validate()
+        if rays is None: rays = random_rays(s, 20000, seed=5)
+        t = ctl.PathTracer(w, h); t.InitializeScene(s)
+        g, counts = t.trace_rays(rays, counts=True)
+        o = orc.trace_rays(s.view, rays)
+        assert np.array_equal(g["tri_idx"], o["tri_idx"]) and np.array_equal(g["dist"].view(np.uint32), o["dist"].view(np.uint32))
+        res[split] = (g, counts, s.view.n_woop); t.close()
+    same = (res["0"][0]["tri_idx"] == res["1"][0]["tri_idx"]) & (res["0"][0]["dist"].view(np.uint32) == res["1"][0]["dist"].view(np.uint32))
+    print("pre-split: slots", res["0"][2], "->", res["1"][2], "inner-node visits", res["0"][1][0], "->", res["1"][1][0], "agreement", same.mean())
+    assert same.mean() >= 0.9995 and res["1"][2] > res["0"][2]
+    assert res["1"][1][0] < res["0"][1][0]
 
 
 def test_gpu_bvh_build_is_deterministic(built_lib):
