@@ -9,14 +9,19 @@
 #include "wavefront_pt.cuh"
 
 
-static void launch_shade(int cls, int grid, cudaStream_t st, const DScene& S, const ShadeParams& P, const PathState& ps, const Queues& Q, const unsigned* n_in, unsigned* n_out, unsigned* n_shadow, const unsigned* seg_hist) {
+template <bool REGU>
+static void launch_shade_t(int cls, int grid, cudaStream_t st, const DScene& S, const ShadeParams& P, const PathState& ps, const Queues& Q, const unsigned* n_in, unsigned* n_out, unsigned* n_shadow, const unsigned* seg_hist) {
     switch (cls) {
-    case 0: k_shade<0><<<grid, 128, 0, st>>>(S, P, ps, Q, n_in, n_out, n_shadow, seg_hist); break;
-    case 1: k_shade<1><<<grid, 128, 0, st>>>(S, P, ps, Q, n_in, n_out, n_shadow, seg_hist); break;
-    case 2: k_shade<2><<<grid, 128, 0, st>>>(S, P, ps, Q, n_in, n_out, n_shadow, seg_hist); break;
-    case 3: k_shade<3><<<grid, 128, 0, st>>>(S, P, ps, Q, n_in, n_out, n_shadow, seg_hist); break;
-    default: k_shade<-1><<<grid, 128, 0, st>>>(S, P, ps, Q, n_in, n_out, n_shadow, nullptr); break;
+    case 0: k_shade<0, REGU><<<grid, 128, 0, st>>>(S, P, ps, Q, n_in, n_out, n_shadow, seg_hist); break;
+    case 1: k_shade<1, REGU><<<grid, 128, 0, st>>>(S, P, ps, Q, n_in, n_out, n_shadow, seg_hist); break;
+    case 2: k_shade<2, REGU><<<grid, 128, 0, st>>>(S, P, ps, Q, n_in, n_out, n_shadow, seg_hist); break;
+    case 3: k_shade<3, REGU><<<grid, 128, 0, st>>>(S, P, ps, Q, n_in, n_out, n_shadow, seg_hist); break;
+    default: k_shade<-1, REGU><<<grid, 128, 0, st>>>(S, P, ps, Q, n_in, n_out, n_shadow, nullptr); break;
     }
+}
+static void launch_shade(bool regu, int cls, int grid, cudaStream_t st, const DScene& S, const ShadeParams& P, const PathState& ps, const Queues& Q, const unsigned* n_in, unsigned* n_out, unsigned* n_shadow, const unsigned* seg_hist) {
+    if (regu) launch_shade_t<true>(cls, grid, st, S, P, ps, Q, n_in, n_out, n_shadow, seg_hist);   // KEY_Regularization: PathTraceRegularization's vertex (Integrators/PathTracer.cu:115-170)
+    else launch_shade_t<false>(cls, grid, st, S, P, ps, Q, n_in, n_out, n_shadow, seg_hist);
 }
 
 // Launch shape of the staged kernel: blocks of `staged_threads`, as many per SM as 1024 resident threads and the shared memory allow
@@ -138,7 +143,7 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "RRStartDepth") { if (v < 0) return set_err("RRStartDepth must be >= 0"); c->rr_start = v; }
     else if (k == "Direct") c->direct = v != 0;
     else if (k == "StopZeroThroughput") c->stop_zero = v != 0;   // 1 (default): a path whose throughput is exactly zero ends; 0: it is traced until Russian roulette ends it, the reference's ray count (Kernel/TraceHelper.cu:176)
-    else if (k == "Regularization") { if (v != 0) return set_err("Regularization=true is not implemented (off by default in the reference)"); c->regularization = 0; }
+    else if (k == "Regularization") c->regularization = v != 0;   // KEY_Regularization (Integrators/PathTracer.h:10-20): PathTraceRegularization instead of PathTrace; needs MaxPathLength <= 255
     else if (k == "SortMode") c->sort_mode = v;
     else if (k == "ShadeMode") { if (v < 0 || v > 1) return set_err("ShadeMode must be 0 (run-time BSDF dispatch) or 1 (one launch per material class)"); c->shade_mode = v; }
     else if (k == "StageTimers") c->stage_timers = v != 0;
@@ -402,7 +407,8 @@ int ctl_trace_rays_host(ctl_ctx* c, int n, const ctl_traversal_ray* rays, ctl_tr
 static int ensure_state(ctl_ctx* c, WaveLane& L, size_t n, cudaStream_t s) {
     CK(L.cf.ensure(n)); CK(L.cl.ensure(n)); CK(L.nor.ensure(n)); CK(L.px.ensure(n));
     CK(L.rays_a.ensure(2 * n)); CK(L.rays_b.ensure(2 * n)); CK(L.hit_a.ensure(n)); CK(L.hit_node.ensure(n));
-    CK(L.sh_rays.ensure(2 * n)); CK(L.sh_payload.ensure(n)); CK(L.path_a.ensure(n)); CK(L.path_b.ensure(n));
+    const size_t n_sh = n * (size_t)(c->regularization && c->scene.num_lights > 1 ? c->scene.num_lights : 1);   // Regularization: one shadow ray per light and vertex
+    CK(L.sh_rays.ensure(2 * n_sh)); CK(L.sh_payload.ensure(n_sh)); CK(L.path_a.ensure(n)); CK(L.path_b.ensure(n));
     if (!c->stop_zero) CK(L.wo_prev.ensure(n));
     if (c->sort_mode == 2) CK(L.mat_cls.ensure(n));
     if (c->sort_mode == 2 || c->shade_mode == 1) { CK(L.mat_order.ensure(n)); CK(L.mat_hist.ensure(2 * MAT_CLASSES * (MAX_BOUNCES + 1))); }
@@ -472,7 +478,12 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W, int lane = 
     float4* rin = L.rays_a.p; float4* rout = L.rays_b.p; uint32_t* pin = L.path_a.p; uint32_t* pout = L.path_b.p;
     float4* rspare = L.rays_c.p; uint32_t* pspare = L.path_c.p;
     const bool fuse = c->fuse_traversal && c->direct && !c->instrumented && (c->trav_kernel == 0 || (c->trav_kernel == 2 && c->staged_ok));
-    for (int b = 0; b < c->max_path_length; b++) {
+    const bool regu = c->regularization != 0;
+    if (regu && c->max_path_length > 255) return set_err("Regularization needs MaxPathLength <= 255");
+    if (regu && c->sort_mode != 0) return set_err("Regularization with SortMode != 0 is not supported");
+    const int n_iter = c->max_path_length + (regu ? 1 : 0);   // Regularization: the ray past the last vertex is traced (and counted), never shaded (Integrators/PathTracer.cu:125)
+    for (int b = 0; b < n_iter; b++) {
+        const bool shade_this = b < c->max_path_length;
         stage_mark(c, 1);
         if (c->capture_bounce == b + 1) {
             CK(cudaMemcpyAsync(c->capture.p, rin, 32 * n_paths, cudaMemcpyDeviceToDevice, s));
@@ -491,6 +502,7 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W, int lane = 
         else launch_intersect<0, false, false>(c, g_trav, s, c->scene, rin, ctr + CTR_Q + b, 0, ctr + CTR_WORK + 2 * b, L.hit_a.p, L.hit_node.p, nullptr, nullptr, nullptr, nullptr,
                                                class_sort ? L.mat_hist.p + 2 * MAT_CLASSES * b : nullptr);
         stage_mark(c, 2);
+        if (!shade_this) { stage_mark(c, 3); launches++; break; }   // (its shadow queue is empty: shade launch b-1 was the last)
         const bool sort_next = c->sort_mode == 1 && b + 1 < c->max_path_length;
         const uint32_t* order = nullptr;
         if (c->sort_mode == 2) { // group this bounce's hits by material class before shading
@@ -507,10 +519,10 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W, int lane = 
         Queues Q = {rin, pin, rout, pout, L.hit_a.p, L.hit_node.p, L.sh_rays.p, L.sh_payload.p, sort_next ? L.sort_keys.p : nullptr, sort_next ? L.sort_hist.p : nullptr, order};
         if (class_sort) {
             const unsigned* hist = L.mat_hist.p + 2 * MAT_CLASSES * b;
-            for (int k = 0; k < 4; k++) if (c->class_mask & (1u << k)) { launch_shade(k, g_light, s, c->scene, P, st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b, hist); launches++; }
+            for (int k = 0; k < 4; k++) if (c->class_mask & (1u << k)) { launch_shade(regu, k, g_light, s, c->scene, P, st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b, hist); launches++; }
             launches--;
         }
-        else launch_shade(by_class ? single_cls : -1, g_light, s, c->scene, P, st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b, nullptr);
+        else launch_shade(regu, by_class ? single_cls : -1, g_light, s, c->scene, P, st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b, nullptr);
         if (sort_next) { // counting sort of the next bounce's extension queue by (octant, origin cell)
             stage_mark(c, 4);
             k_sort_scan<<<1, 1024, 0, s>>>(L.sort_hist.p, L.sort_offsets.p);
@@ -519,7 +531,7 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W, int lane = 
             launches += 2;
         }
         stage_mark(c, 3);
-        if (c->direct && (!fuse || b + 1 == c->max_path_length)) {
+        if (c->direct && (!fuse || b + 1 == n_iter)) {
             if (c->instrumented) launch_intersect<1, true, true>(c, g_trav, s, c->scene, L.sh_rays.p, ctr + CTR_SH + b, 0, ctr + CTR_WORK + 2 * b + 1, nullptr, nullptr, L.sh_payload.p, L.cl.p, nullptr, c->stats.p + 6);
             else launch_intersect<1, true, false>(c, g_trav, s, c->scene, L.sh_rays.p, ctr + CTR_SH + b, 0, ctr + CTR_WORK + 2 * b + 1, nullptr, nullptr, L.sh_payload.p, L.cl.p, nullptr, nullptr);
             launches++;
@@ -529,7 +541,7 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W, int lane = 
     }
     stage_mark(c, 4);
     k_finish<<<g_light, 256, 0, s>>>((int)n_paths, st, c->accum, c->w, c->h);
-    k_tally<<<1, 32, 0, s>>>(ctr + CTR_Q, ctr + CTR_SH, c->max_path_length, c->stats.p, c->stats.p + 1);
+    k_tally<<<1, 32, 0, s>>>(ctr + CTR_Q, ctr + CTR_SH, n_iter, c->stats.p, c->stats.p + 1);
     launches += 2;
     stage_mark(c, 5);
     CK(cudaGetLastError());

@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(256) k_class_scatter(const unsigned* __restric
 }
 
 // ---- shade: one path vertex (PathTracer.cu:58-96) ----------------------------------
-struct ShadeParams { int max_path_length, rr_start, direct, stop_zero; };
+struct ShadeParams { int max_path_length, rr_start, direct, stop_zero; };   // (k_shade<CLS, REGU>: REGU = the reference's KEY_Regularization)
 
 #ifndef CTL_SHADE_MIN_BLOCKS
 #define CTL_SHADE_MIN_BLOCKS 8 // 64 registers: 8 resident blocks per SM; measured -18% (diffuse) / -27% (microfacet) shade time vs 116 registers
@@ -371,7 +371,12 @@ CTL_DEV constexpr uint32_t cls_bsdf_type(int cls) { return cls == 0 ? CTL_BSDF_D
 #ifndef CTL_SHADE_MICRO_MIN_BLOCKS
 #define CTL_SHADE_MICRO_MIN_BLOCKS CTL_SHADE_MIN_BLOCKS // resident blocks per SM of the rough-conductor launches (their bodies spill ~150 B at 64 registers)
 #endif
-template <int CLS>
+// REGU = true: one vertex of PathTraceRegularization<DIRECT> (Integrators/PathTracer.cu:115-170) instead of PathTrace<DIRECT>: emitted radiance only at
+// depth 1 / after a specular bounce / without direct lighting and without MIS weight; every non-delta vertex samples ALL lights (UniformSampleAllLights ->
+// EstimateDirect with light pdf 1: one shadow-queue entry per light, appended by the lane itself), a delta vertex draws sampleEmitterPosition's two numbers
+// and adds nothing (this path has DiffuseLights only, cu:138); Russian roulette also after specular bounces; a path that survives its last vertex still
+// emits its next ray (the reference traces before it tests the depth, cu:125) and the next shade launch leaves it alone.
+template <int CLS, bool REGU = false>
 __global__ void __launch_bounds__(128, (CLS == 1 || CLS == 2) ? CTL_SHADE_MICRO_MIN_BLOCKS : CTL_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene S, const __grid_constant__ ShadeParams P, PathState st, Queues Q,
                                                 const unsigned* __restrict__ n_in, unsigned* n_out, unsigned* n_shadow, const unsigned* __restrict__ seg_hist) {
     int n = (int)*n_in, seg_start = 0;
@@ -390,7 +395,7 @@ __global__ void __launch_bounds__(128, (CLS == 1 || CLS == 2) ? CTL_SHADE_MICRO_
             const float4 ha = Q.hit_a[i];
             const uint32_t tri_word = __float_as_uint(ha.w);
             const uint32_t tri = tri_word & TRI_IDX_MASK;   // the staged traversal kernel leaves the material class in the top bits
-            if (tri_word != 0xffffffffu) {
+            if (tri_word != 0xffffffffu && !(REGU && (int)(__float_as_uint(st.nor[p].w) & 0xff) >= P.max_path_length)) {   // (REGU: the ray past the last vertex is traced, not shaded)
                 const uint32_t node = Q.hit_node[i];
                 const float4 r0 = Q.rays_in[2 * i], r1 = Q.rays_in[2 * i + 1];
                 const V3 ro = mk(r0.x, r0.y, r0.z), rd = mk(r1.x, r1.y, r1.z);
@@ -416,11 +421,11 @@ __global__ void __launch_bounds__(128, (CLS == 1 || CLS == 2) ? CTL_SHADE_MICRO_
                 bRec.wi = to_local(dg.sys, -rd);
                 if ((mat.flags & CTL_MAT_TWO_SIDED) && bRec.wi.z < 0) { dg.n = -dg.n; dg.sys.n = -dg.sys.n; bRec.wi.z *= -1.0f; }
                 // emitter hit with MIS (PathTracer.cu:64-77)
-                if (mat.node_light_index != 0xffffffffu) {
+                if (mat.node_light_index != 0xffffffffu && (!REGU || !P.direct || depth == 1 || specularBounce)) {
                     const unsigned li = mat.node_light_index == 0 ? __ldg(&N->lights[0]) : __ldg(&N->lights[1]);
                     const ctl_light L = S.lights[li];
                     float misWeight = 1.0f;
-                    if (!(!P.direct || depth == 1 || specularBounce)) {
+                    if (!REGU && !(!P.direct || depth == 1 || specularBounce)) {
                         DRec dRec; dRec.ref = ro; dRec.refN = last_nor; dRec.p = dg.P; dRec.n = dg.n; dRec.d = rd; dRec.dist = ha.x;
                         const float direct_pdf = light_pdf_direct(L, dRec) * pdf_emitter(S, li);
                         misWeight = power_heuristic(brdf_pdf, direct_pdf);
@@ -431,8 +436,31 @@ __global__ void __launch_bounds__(128, (CLS == 1 || CLS == 2) ? CTL_SHADE_MICRO_
                 const float2 bs = rnd.f2(S);
                 const Spec f = bsdf_sample(mat, bRec, brdf_pdf, bs.x, bs.y);
                 last_nor = dg.sys.n;
+                if (REGU && P.direct) {
+                    if (bsdf_combined_type(mat.bsdf_type) & E_DELTA) rnd.f2(S);   // sampleEmitterPosition's sample (cu:136-137)
+                    else for (unsigned li = 0; li < S.num_lights; li++) {   // UniformSampleAllLights, one sample per light (TraceAlgorithms.cu:75-90)
+                        const ctl_light L = S.lights[S.light_indices[li]];
+                        DRec dRec; dRec.ref = dg.P; dRec.refN = dg.sys.n; dRec.p = dg.P; dRec.n = dg.sys.n; dRec.pdf = 0;
+                        const float2 es = rnd.f2(S);
+                        const Spec value = light_sample_direct(S, L, dRec, es.x, es.y);
+                        if (!is_zero(value)) {
+                            BRec b2 = bRec;
+                            b2.wo = to_local(dg.sys, dRec.d);
+                            b2.typeMask = E_ALL & ~E_DELTA;
+                            const Spec bsdfVal = bsdf_f(mat, b2);
+                            if (!is_zero(bsdfVal)) {
+                                const float weight = power_heuristic(dRec.pdf * 1.0f, bsdf_pdf(mat, b2));
+                                const Spec contrib = cf * ((value * bsdfVal) * weight);
+                                const unsigned ks = atomicAdd(n_shadow, 1u);
+                                Q.sh_rays[2 * ks] = make_float4(dg.P.x, dg.P.y, dg.P.z, S.ray_eps);
+                                Q.sh_rays[2 * ks + 1] = make_float4(dRec.d.x, dRec.d.y, dRec.d.z, dRec.dist - S.ray_eps);
+                                Q.sh_payload[ks] = make_float4(contrib.r, contrib.g, contrib.b, __uint_as_float(p));
+                            }
+                        }
+                    }
+                }
                 // next-event estimation (TraceAlgorithms.cu:44-101)
-                if (P.direct && (bsdf_combined_type(mat.bsdf_type) & E_SMOOTH) && S.num_lights) {
+                if (!REGU && P.direct && (bsdf_combined_type(mat.bsdf_type) & E_SMOOTH) && S.num_lights) {
                     const float2 ls = rnd.f2(S);
                     unsigned first = 0, count = S.num_lights; // STL_upper_bound, Base/STL.h:21-38
                     while (count > 0) { const unsigned c2 = count / 2, mid = first + c2; if (!(ls.x < S.light_cdf[mid])) { first = mid + 1; count -= c2 + 1; } else count = c2; }
@@ -462,12 +490,12 @@ __global__ void __launch_bounds__(128, (CLS == 1 || CLS == 2) ? CTL_SHADE_MICRO_
                 cf = cf * f;
                 nd = to_world(dg.sys, bRec.wo); no = dg.P;
                 alive = !P.stop_zero || !is_zero(cf);   // stop_zero: a path of zero throughput ends here (no image effect); off: it lives until Russian roulette, as in the reference
-                if (alive && depth > P.rr_start && !specularBounce) {
+                if (alive && depth > P.rr_start && (REGU || !specularBounce)) {
                     const float q = smax(cf);
                     if (rnd.f1(S) >= q) alive = false;
                     else cf = cf / q;
                 }
-                if (depth >= P.max_path_length) alive = false;
+                if (!REGU && depth >= P.max_path_length) alive = false;
                 cl4.x = cl.r; cl4.y = cl.g; cl4.z = cl.b;
                 st.cl[p] = cl4;
                 if (alive) {

@@ -297,7 +297,8 @@ ctl_ctx* ctl_create(int device, int width, int height);
 void     ctl_destroy(ctl_ctx*);                          /* == TracerBase::~TracerBase (Kernel/Tracer.h:101) + Image::Free (Engine/Image.cpp:25) */
 int      ctl_resize(ctl_ctx*, int width, int height);    /* == Tracer<true>::Resize (Kernel/Tracer.h:196-207): new PixelData / variance / queue storage, starts a new trace */
 /* == m_sParameters: "MaxPathLength" (50), "RRStartDepth" (5), "Direct" (1),
- *    "Regularization" (0, only 0 supported)  (Integrators/PathTracer.h:10-20);
+ *    "Regularization" (0; 1 = PathTraceRegularization<DIRECT> instead of PathTrace<DIRECT>, Integrators/PathTracer.cu:115-170: all lights per vertex, no emitter
+ *    MIS, one ray traced past the last vertex; needs MaxPathLength <= 255)  (Integrators/PathTracer.h:10-20);
  *    extras: "SortMode" (0 none, 1 material), "StageTimers" (0/1), "CaptureBounce" (0 = off),
  *    "DeviceSampleTables" (1 = tables generated by a CUDA kernel, bit-identical to the host XORWOW generator; 0 = generated on the
  *    host and copied H2D every pass like the reference's UpdateKernel), "TraversalKernel" (2 = persistent warps with shared-memory staging [default], 0 = persistent warps, 1 = ray-batch A/B baseline), "StagedThreads" / "StagedStackRows" /

@@ -789,6 +789,80 @@ Spec path_trace(const ctl_scene_view& S, V3 ro, V3 rd, Sampler& rnd, const PTPar
     return cl;
 }
 
+// PathTraceRegularization<DIRECT> (Integrators/PathTracer.cu:115-170; KEY_Regularization, off by default in the reference).  A different estimator, not a
+// variant of the one above: the ray is traced BEFORE the depth test (a path that survives its last vertex traces one more ray whose hit is never
+// shaded), emitted radiance is added only at depth 1 / after a specular bounce / without direct lighting (no MIS weight), every non-delta vertex samples
+// ALL lights (UniformSampleAllLights -> EstimateDirect with light_pdf 1, TraceAlgorithms.cu:44-90), a delta vertex draws the two numbers of
+// sampleEmitterPosition and adds nothing (the mollified connection is only taken for lights that are neither DiffuseLight nor InfiniteLight, cu:138; this
+// path has DiffuseLights only), and Russian roulette applies after specular bounces too.  No environment map, no volumes.
+Spec path_trace_regularized(const ctl_scene_view& S, V3 ro, V3 rd, Sampler& rnd, const PTParams& P, uint64_t& rays, Counters* cnt) {
+    Spec cl = sp(0.0f), cf = sp(1.0f);
+    int depth = 0; bool specularBounce = false;
+    BRec bRec; bRec.wo = mk(0, 0, 1);
+    for (;;) {
+        Hit r2; r2.dist = FLT_MAX; r2.tri = UINT_MAX; r2.node = UINT_MAX; r2.u = r2.v = 0;
+        rays++;
+        trace(S, ro, rd, S.ray_eps, 0.0f, r2, cnt, false);
+        if (r2.tri == UINT_MAX || !(depth++ < P.max_path_length)) break;   // while (traceRay(...) && depth++ < maxPathLength)
+        const ctl_material& mat = S.materials[mat_index_of(S, r2)];
+        bRec.eta = 1.0f; bRec.sampledType = 0; bRec.typeMask = E_ALL;
+        bRec.dg.P = add(ro, mul(rd, r2.dist));
+        fill_dg(S, r2.u, r2.v, r2.tri, r2.node, bRec.dg);
+        bRec.wi = to_local(bRec.dg.sys, neg(rd));
+        if ((mat.flags & CTL_MAT_TWO_SIDED) && bRec.wi.z < 0) { bRec.dg.n = neg(bRec.dg.n); bRec.dg.sys.n = neg(bRec.dg.sys.n); bRec.wi.z *= -1.0f; }
+        if ((!P.direct || depth == 1 || specularBounce) && mat.node_light_index != UINT_MAX) {   // cl += cf * r2.Le(...), cu:131-132
+            const ctl_light& L = S.lights[S.nodes[r2.node].lights[mat.node_light_index]];
+            Spec Le = dot(bRec.dg.sys.n, neg(rd)) <= 0 ? sp(0.0f) : sp3(L.radiance);
+            cl = sadd(cl, smul(cf, Le));
+        }
+        float sx, sy; rnd.f2(sx, sy);
+        float unused_pdf = 0;
+        Spec f = bsdf_sample(mat, bRec, unused_pdf, sx, sy);
+        if (P.direct) {
+            if (bsdf_combined_type(mat) & E_DELTA) { float ex, ey; rnd.f2(ex, ey); }   // sampleEmitterPosition's sample; DiffuseLights take no mollified connection
+            else {
+                Spec Lall = sp(0.0f);
+                for (unsigned li = 0; li < S.num_lights; li++) {   // UniformSampleAllLights, nSamples 1
+                    const ctl_light& L = S.lights[S.light_indices[li]];
+                    DRec dRec; dRec.ref = bRec.dg.P; dRec.refN = bRec.dg.sys.n; dRec.p = bRec.dg.P; dRec.n = bRec.dg.sys.n; dRec.pdf = 0;
+                    float ex, ey; rnd.f2(ex, ey);
+                    Spec value = light_sample_direct(S, L, dRec, ex, ey);
+                    Spec retVal = sp(0.0f);
+                    if (!sis_zero(value)) {
+                        BRec b2 = bRec;
+                        b2.wo = to_local(b2.dg.sys, dRec.d);
+                        b2.typeMask = E_ALL & ~E_DELTA;
+                        Spec bsdfVal = bsdf_f(mat, b2);
+                        if (!sis_zero(bsdfVal)) {
+                            Hit sh; sh.dist = FLT_MAX; sh.tri = UINT_MAX; sh.node = UINT_MAX;
+                            rays++;
+                            trace(S, dRec.ref, dRec.d, S.ray_eps, 0.0f, sh, cnt, false);
+                            bool end = sh.dist < dRec.dist - S.ray_eps;
+                            bool occluded = sh.dist > 0 + S.ray_eps && end;
+                            if (!occluded) {
+                                float bsdfPdf = bsdf_pdf(mat, b2);
+                                float directPdf = dRec.pdf * 1.0f;
+                                retVal = smulf(smul(value, bsdfVal), power_heuristic(directPdf, bsdfPdf));
+                            }
+                        }
+                    }
+                    Lall = sadd(Lall, sdivf(retVal, 1.0f));   // L += Ld / float(nSamples)
+                }
+                cl = sadd(cl, smul(cf, Lall));
+            }
+        }
+        specularBounce = (bRec.sampledType & E_DELTA) != 0;
+        cf = smul(cf, f);
+        if (depth > P.rr_start) {
+            if (rnd.f1() < smax(cf)) cf = sdivf(cf, smax(cf));
+            else break;
+        }
+        rd = to_world(bRec.dg.sys, bRec.wo); ro = bRec.dg.P;
+        if (g_stop_zero && sis_zero(cf)) break;   // the product's StopZeroThroughput (see path_trace)
+    }
+    return cl;
+}
+
 struct PixSample { float sx, sy; Spec L; };
 
 void add_sample(ctl_pixel_data* img, int w, int h, float sx, float sy, Spec L) { // Engine/Image.cu:22-44
@@ -934,7 +1008,8 @@ void orc_render(const ctl_scene_view* S, int w, int h, int x0, int y0, int x1, i
     std::vector<float> d1((size_t)N_SEQ * SEQ_LEN), d2((size_t)N_SEQ * SEQ_LEN * 2);
     Xorwow st; xorwow_init(1234, 7539414, 0, st);
     for (int p = 0; p < pass_first; p++) fill_tables(st, d1.data(), d2.data());
-    PTParams P = {max_path_length, rr_start, direct};
+    const bool regularization = (direct & 2) != 0;   // bit 1 of `direct`: PathTraceRegularization (KEY_Regularization)
+    PTParams P = {max_path_length, rr_start, direct & 1};
     uint64_t total_rays = 0; Counters total_cnt = {0, 0, 0};
     if (n_threads < 1) n_threads = 1;
     int bw = x1 - x0, bh = y1 - y0;
@@ -953,7 +1028,7 @@ void orc_render(const ctl_scene_view* S, int w, int h, int x0, int y0, int x1, i
                     float pX = (float)x + jx, pY = (float)y + jy;
                     float ax, ay; rng.f2(ax, ay); // aperture sample, unused by the pinhole
                     V3 o, d; camera_ray(S->camera, pX, pY, o, d);
-                    Spec col = path_trace(*S, o, d, rng, P, trays[tid], counts ? &tcnt[tid] : 0);
+                    Spec col = regularization ? path_trace_regularized(*S, o, d, rng, P, trays[tid], counts ? &tcnt[tid] : 0) : path_trace(*S, o, d, rng, P, trays[tid], counts ? &tcnt[tid] : 0);
                     PixSample ps = {pX, pY, col};
                     samples[(size_t)ry * bw + (x - x0)] = ps;
                 }

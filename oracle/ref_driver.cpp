@@ -254,6 +254,8 @@ unsigned long long ref_render(const ctl_scene_view* view, int w, int h, int x0, 
 {
 	std::lock_guard<std::mutex> lock(g_mutex);
 	pack_scene(*view);
+	const bool regularization = (direct & 2) != 0;   // bit 1 of `direct`: KEY_Regularization -> the reference's PathTraceRegularization<DIRECT> (Integrators/PathTracer.cu:115-170)
+	direct &= 1;
 	static bool sampler_init = false;
 	if (!sampler_init) { new (&(*g_SamplerDataHost)) SamplerData(4096, 30); sampler_init = true; } // Kernel/TraceHelper.cu:257
 	// fresh tracer: sample stream restarts; batches before pass_first are generated and discarded
@@ -280,7 +282,13 @@ unsigned long long ref_render(const ctl_scene_view* view, int w, int h, int x0, 
 					NormalizedT<Ray> r, rX, rY;
 					Vec2f pX = Vec2f((float)x, (float)y) + rng.randomFloat2();
 					Spectrum imp = g_SceneData.sampleSensorRay(r, rX, rY, pX, rng.randomFloat2());
-					Spectrum col = imp * (direct ? PathTrace<true>(r, rX, rY, rng, max_path_length, rr_start) : PathTrace<false>(r, rX, rY, rng, max_path_length, rr_start));
+					Spectrum col;
+					if (regularization) { // RenderBlock's mollifier radius (Integrators/PathTracer.cu:196-199); only read for lights this path does not have
+						AABB box = g_SceneData.m_sBox;
+						float r0 = (box.maxV - box.minV).sum() / 100, m = math::pow(math::pow(r0, float(2)) / math::pow(float(pass_first + p + 1), 0.5f * (1 - 0.75f)), 1.0f / 2.0f);
+						col = imp * (direct ? PathTraceRegularization<true>(r, rX, rY, rng, m, max_path_length, rr_start) : PathTraceRegularization<false>(r, rX, rY, rng, m, max_path_length, rr_start));
+					} else
+						col = imp * (direct ? PathTrace<true>(r, rX, rY, rng, max_path_length, rr_start) : PathTrace<false>(r, rX, rY, rng, max_path_length, rr_start));
 					out.push_back({pX.x, pX.y, col});
 				}
 			}

@@ -37,7 +37,8 @@ t.setParameter("DeviceSampleTables", 0); t.DoFrame(4, 1); t.setParameter("Device
 t.setParameter("StagedRayTMA", 1); t.DoPasses(2, new_trace=True); t.setParameter("StagedRayTMA", 0)
 t.setParameter("StagedTreeletNodes", 256); t.InitializeScene(s3); t.DoPasses(2, new_trace=True); t.setParameter("StagedTreeletNodes", 0); t.InitializeScene(s3)
 t.setParameter("ShadeMode", 0); t.DoPasses(2, new_trace=True); t.setParameter("TravDrainPrefetch", 1); t.DoPasses(1); t.setParameter("StopZeroThroughput", 0); t.DoPasses(1)
-t.synchronize(); out = t.applyImagePipeline(ImagePipeline(5)); print("round-2 frames ok", out.mean()); t.close()
+t.setParameter("PixelVarianceBuffer", 1); t.DoPass(True); t.DoPass(False)
+t.synchronize(); out = t.applyImagePipeline(ImagePipeline(5, 1.0, 0.0, 0.45, 1.0)); print("round-2 frames ok", out.mean()); t.close()
 L = lib()
 L.ctl_bvh_build_gpu_split.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_float, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 rng = np.random.default_rng(3); n = 3000
