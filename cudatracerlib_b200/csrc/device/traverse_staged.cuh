@@ -292,9 +292,16 @@ __device__ __forceinline__ void trace_staged(const DScene& S, const StagedScene&
                     const int t = nodeAddr >> 2;
                     nA.lo = tl[tl_chunk(t, 0)]; nA.hi = tl[tl_chunk(t, 1)]; nB.lo = tl[tl_chunk(t, 2)]; nB.hi = tl[tl_chunk(t, 3)];
                 } else { nA = ldg256(nbase + nodeAddr); nB = ldg256(nbase + nodeAddr + 2); }
+#if defined(CTL_EXP_EXTRA_NODE_LOADS) && defined(__CUDACC__)   // experiment (build variant only): what one more L1 wavefront per lane and node step costs -- the result is not used
+                bool x_never = false;   // (a box coordinate never has this NaN payload: the load cannot be eliminated, the walk is unchanged)
+                for (int xk = 0; xk < CTL_EXP_EXTRA_NODE_LOADS; xk++) { float xd; asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(xd) : "l"(nbase + nodeAddr + (xk & 3))); x_never |= __float_as_uint(xd) == 0x7fc12345u; }
+#endif
                 const float4 n0xy = nA.lo, n1xy = nA.hi, nz = nB.lo, cn = nB.hi;
                 if (COUNT) ((VisitCounters<true>&)cnt).inner++;
                 int c0 = __float_as_int(cn.x), c1 = __float_as_int(cn.y);
+#if defined(CTL_EXP_EXTRA_NODE_LOADS) && defined(__CUDACC__)
+                if (x_never) c0 = c1;
+#endif
                 const float c0lox = fmaf(n0xy.x, idx, -oodx), c0hix = fmaf(n0xy.y, idx, -oodx);
                 const float c0loy = fmaf(n0xy.z, idy, -oody), c0hiy = fmaf(n0xy.w, idy, -oody);
                 const float c0loz = fmaf(nz.x, idz, -oodz), c0hiz = fmaf(nz.y, idz, -oodz);

@@ -3,7 +3,7 @@
 CUDA events on the launch stream.  Algorithmic bytes per ray from the instrumented traversal of the same rays (ctl_trace_rays_host counts:
 48 + 64 inner + 52 tris + 108 instances), reported against the HBM peak bench.py uses.
     python scripts/ray_microbench.py c2 > gpurun_out/ray_microbench_c2.json        (GPU; one JSON line per bounce)
-Prepared at the end of round 1 after the GPU budget was spent: not yet run on a device (round-2 item)."""
+Results: profiles/r02a_ray_microbench_*.json (round-2 start), profiles/r03a_ray_microbench_*.json (shipping kernel and trees)."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
