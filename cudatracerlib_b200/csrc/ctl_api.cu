@@ -38,7 +38,8 @@ static int staged_grid(const ctl_ctx* c) {
 }
 template <int MODE, bool ANY_HIT, bool COUNT>
 static void launch_staged(const ctl_ctx* c, cudaStream_t st, const float4* rays, const unsigned* n_ptr, const unsigned* n2_ptr, int n_fixed, unsigned* work, const TravOut& out, unsigned long long* visit) {
-    static size_t attr_set[2] = {0, 0}; // per instantiation
+    static size_t attr_set_dev[64][2] = {}; // per instantiation and device (the attribute is a per-device property of the function)
+    size_t* attr_set = attr_set_dev[c->device & 63];
     const size_t smem = staged_smem_bytes(c);
     if (c->staged.ray_tma) {
         if (smem > attr_set[1]) { cudaFuncSetAttribute(k_intersect_staged<MODE, ANY_HIT, COUNT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[1] = smem; }
@@ -116,6 +117,7 @@ void ctl_destroy(ctl_ctx* c) {
     for (int k = 1; k < MAX_LANES; k++) { if (c->lane_stream[k]) { cudaStreamSynchronize(c->lane_stream[k]); cudaStreamDestroy(c->lane_stream[k]); } if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (int k = 0; k < MAX_LANES; k++) c->lanes[k].release();
+    c->ho_buf[0].release(); c->ho_buf[1].release(); c->ho_cnt.release();
     c->capture.release(); c->api_work.release(); c->stats.release();
     c->own_accum.release(); c->d_captured_n.release(); c->resolve_tmp.release(); c->pipe_rgbe.release(); c->pipe_partial.release(); c->pipe_lum.release(); c->d_var.release(); c->nlm_cached.release(); c->nlm_varh.release(); c->nlm_weights.release(); c->nlm_last_update = -1; c->nlm_pixels = 0; c->d_node_alias.release();
     c->w_thr.release(); c->w_lxy.release(); c->w_df.release(); c->w_ray.release(); c->w_misc.release(); c->w_res.release(); c->w_desc.release();
@@ -151,6 +153,8 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "DeviceSampleTables") c->device_tables = v != 0;
     else if (k == "FuseTraversal") c->fuse_traversal = v != 0;
     else if (k == "OverlapWavefronts") { if (v < 0 || v > 2) return set_err("OverlapWavefronts must be 0, 1 or 2"); c->overlap = v; }
+    else if (k == "HandOver") c->handover = v != 0;   // ctl_render_frame_tiled: one-wavefront frames as two half-wavefronts with ray hand-over between their launches
+    else if (k == "HandOverDrain") { if (v < 1 || v > 4096) return set_err("HandOverDrain out of range [1,4096]"); c->handover_drain = v; }
     else if (k == "OverlapLanes") { if (v < 1 || v > MAX_LANES) return set_err("OverlapLanes out of range [1,8]"); c->n_lanes = v; }   // wavefronts of a frame in flight at once   // ctl_render_frame_tiled / ctl_comm_render_frame: the frame's wavefronts alternate between two streams
     else if (k == "PixelVarianceBuffer") c->variance_buffer = v != 0;
     else if (k == "WarpPixelBlocks") c->warp_blocks = v != 0;
@@ -182,7 +186,7 @@ int ctl_get_param_i(ctl_ctx* c, const char* key, int* v) {
     std::string k(key);
     if (k == "MaxPathLength") *v = c->max_path_length; else if (k == "RRStartDepth") *v = c->rr_start; else if (k == "Direct") *v = c->direct;
     else if (k == "StopZeroThroughput") *v = c->stop_zero; else if (k == "Regularization") *v = c->regularization; else if (k == "SortMode") *v = c->sort_mode; else if (k == "StageTimers") *v = c->stage_timers;
-    else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables; else if (k == "FuseTraversal") *v = c->fuse_traversal; else if (k == "OverlapWavefronts") *v = c->overlap; else if (k == "OverlapLanes") *v = c->n_lanes; else if (k == "PixelVarianceBuffer") *v = c->variance_buffer; else if (k == "PassStride") *v = c->pass_stride; else if (k == "PassPhase") *v = c->pass_phase;
+    else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables; else if (k == "FuseTraversal") *v = c->fuse_traversal; else if (k == "OverlapWavefronts") *v = c->overlap; else if (k == "OverlapLanes") *v = c->n_lanes; else if (k == "HandOver") *v = c->handover; else if (k == "HandOverDrain") *v = c->handover_drain; else if (k == "PixelVarianceBuffer") *v = c->variance_buffer; else if (k == "PassStride") *v = c->pass_stride; else if (k == "PassPhase") *v = c->pass_phase;
     else if (k == "TraversalBlocksPerSM") *v = c->trav_blocks_per_sm; else if (k == "StagedThreads") *v = c->staged_threads; else if (k == "StagedStackRows") *v = c->staged_rows;
     else if (k == "ShadeMode") *v = c->shade_mode; else if (k == "MaterialClassMask") *v = (int)c->class_mask;
     else if (k == "StagedRayTMA") *v = c->staged.ray_tma;
@@ -593,6 +597,89 @@ int ctl_render_passes_tiled(ctl_ctx* c, int new_trace, int n_passes, int tile_w,
     return render_window(c, new_trace, W);
 }
 
+// A frame that is ONE wavefront, rendered as two interleaved half-wavefronts A and B (half the passes each, lanes[0] / lanes[1]) on the context's stream:
+//     T(A,0) T(B,0) S(A,0) T(A,1) S(B,0) T(B,1) S(A,1) ... T(B,last) S(A,last) Tsh(A) S(B,last) Tsh(B) finish
+// Every traversal launch first finishes the rays its predecessor suspended when its queue ran dry (device/traverse_handover.cuh), so no launch drains
+// except the last.  Same paths, same hits, same ray counts as the one-wavefront frame.
+static int render_frame_handover(ctl_ctx* c, Window W, int n_half) {
+    const cudaStream_t s = c->stream;
+    const int mpl = c->max_path_length;
+    const size_t n_paths = (size_t)W.n_slots * n_half;
+    const size_t smem = staged_smem_bytes(c);
+    const int grid = staged_grid(c), lanes_resident = grid * c->staged_threads;
+    for (int h = 0; h < 2; h++) { if (ensure_state(c, c->lanes[h], n_paths, s)) return 1; CK(c->ho_buf[h].ensure((size_t)lanes_resident * HO_WORDS)); }
+    CK(c->ho_cnt.ensure(2 * (size_t)MAX_BOUNCES + 8));
+    static size_t attr_set_dev[64] = {};
+    if (smem > attr_set_dev[c->device & 63]) { CK(cudaFuncSetAttribute(k_intersect_handover<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set_dev[c->device & 63] = smem; }
+    CK(cudaMemsetAsync(c->ho_cnt.p, 0, (2 * (size_t)MAX_BOUNCES + 8) * sizeof(unsigned), s));
+    c->scene.d1 = c->d_tab1.p; c->scene.d2 = (const float2*)c->d_tab2.p; c->scene.img_w = c->w; c->scene.img_h = c->h;
+    const bool by_class = c->shade_mode == 1 && c->class_ok && c->class_mask != 0;
+    int n_classes = 0, single_cls = -1;
+    for (int k = 0; k < 4; k++) if (c->class_mask & (1u << k)) { n_classes++; single_cls = k; }
+    const bool class_sort = by_class && n_classes > 1;
+    const int g_light = grid_for(c, c->shade_blocks_per_sm);
+    const ShadeParams P = {c->max_path_length, c->rr_start, c->direct, c->stop_zero};
+    struct Half { WaveLane* L; unsigned* ctr; PathState st; float4 *rin, *rout; uint32_t *pin, *pout; } H2[2];
+    uint32_t launches = 0;
+    for (int h = 0; h < 2; h++) {
+        WaveLane& L = c->lanes[h];
+        CK(cudaMemsetAsync(L.counters.p, 0, CTR_TOTAL * sizeof(unsigned), s));
+        if (class_sort) CK(cudaMemsetAsync(L.mat_hist.p, 0, 2 * MAT_CLASSES * (MAX_BOUNCES + 1) * sizeof(unsigned), s));
+        H2[h] = {&L, L.counters.p, {L.cf.p, L.cl.p, L.nor.p, L.px.p, c->stop_zero ? nullptr : L.wo_prev.p}, L.rays_a.p, L.rays_b.p, L.path_a.p, L.path_b.p};
+        Window Wh = W; Wh.n_passes = n_half; Wh.tab0 = h * n_half;
+        k_generate<<<g_light, 256, 0, s>>>(c->scene, Wh, H2[h].st, H2[h].rin, H2[h].pin, H2[h].ctr + CTR_Q + 0);
+        launches++;
+    }
+    auto shade = [&](int h, int b) {   // S(h, b): the bounce's hit records -> next extension queue + shadow queue
+        Half& X = H2[h]; unsigned* ctr = X.ctr; WaveLane& L = *X.L;
+        const uint32_t* order = nullptr;
+        if (class_sort) {
+            unsigned* hist = L.mat_hist.p + 2 * MAT_CLASSES * b;
+            k_class_scatter<<<g_light, 256, 0, s>>>(ctr + CTR_Q + b, L.hit_a.p, hist, hist + MAT_CLASSES, L.mat_order.p);
+            order = L.mat_order.p; launches++;
+        }
+        Queues Q = {X.rin, X.pin, X.rout, X.pout, L.hit_a.p, L.hit_node.p, L.sh_rays.p, L.sh_payload.p, nullptr, nullptr, order};
+        if (class_sort) {
+            const unsigned* hist = L.mat_hist.p + 2 * MAT_CLASSES * b;
+            for (int k = 0; k < 4; k++) if (c->class_mask & (1u << k)) { launch_shade(false, k, g_light, s, c->scene, P, X.st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b, hist); launches++; }
+        } else { launch_shade(false, by_class ? single_cls : -1, g_light, s, c->scene, P, X.st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b, nullptr); launches++; }
+        std::swap(X.rin, X.rout); std::swap(X.pin, X.pout);
+    };
+    TravOut prev_out = {}; const float4* prev_rays = nullptr;
+    int seq = 0;
+    auto trav = [&](int h, int b, bool ext, bool last) {   // T(h, b): [extension rays of bounce b] + [shadow rays of bounce b-1]; resumes launch seq-1's suspended rays
+        Half& X = H2[h]; unsigned* ctr = X.ctr; WaveLane& L = *X.L;
+        const TravOut out = {L.hit_a.p, L.hit_node.p, L.sh_payload.p, L.cl.p, nullptr, L.sh_rays.p, 0, nullptr, (class_sort && ext) ? L.mat_hist.p + 2 * MAT_CLASSES * b : nullptr};
+        HandOver HO;
+        HO.resume = seq > 0 ? c->ho_buf[(seq - 1) & 1].p : nullptr; HO.n_resume = seq > 0 ? c->ho_cnt.p + (seq - 1) : nullptr;
+        HO.alt = prev_out; HO.alt_rays = prev_rays;
+        HO.suspend = last ? nullptr : c->ho_buf[seq & 1].p; HO.n_suspend = last ? nullptr : c->ho_cnt.p + seq; HO.drain_iters = c->handover_drain;
+        const unsigned* n_ext_ptr = ext ? ctr + CTR_Q + b : nullptr;
+        const unsigned* n_sh_ptr = ext ? (b > 0 ? ctr + CTR_SH + b - 1 : nullptr) : ctr + CTR_SH + b;
+        unsigned* work = ext ? ctr + CTR_WORK + 2 * b : ctr + CTR_WORK + 2 * b + 1;
+        k_intersect_handover<true><<<grid, c->staged_threads, smem, s>>>(c->scene, c->staged, c->tune, X.rin, n_ext_ptr, n_sh_ptr, work, out, HO);
+        prev_out = out; prev_rays = X.rin; seq++; launches++;
+    };
+    int item_h = -1, item_b = -1;   // the (half, bounce) of the previous traversal launch: shaded after the current one
+    for (int b = 0; b < mpl; b++) for (int h = 0; h < 2; h++) {
+        trav(h, b, true, false);
+        if (item_h >= 0) shade(item_h, item_b);
+        item_h = h; item_b = b;
+    }
+    // item = (B, mpl-1) is still to be shaded; the shadow rays of the last bounce remain: Tsh(A) resumes B's last stragglers, Tsh(B) resumes A's and drains
+    trav(0, mpl - 1, false, false);
+    shade(item_h, item_b);
+    trav(1, mpl - 1, false, true);
+    for (int h = 0; h < 2; h++) {
+        k_finish<<<g_light, 256, 0, s>>>((int)n_paths, H2[h].st, c->accum, c->w, c->h);
+        k_tally<<<1, 32, 0, s>>>(H2[h].ctr + CTR_Q, H2[h].ctr + CTR_SH, mpl, c->stats.p, c->stats.p + 1, h);
+        launches += 2;
+    }
+    CK(cudaGetLastError());
+    c->n_launches = launches;
+    return 0;
+}
+
 // One progressive frame (a new trace): `spp` passes on the tiles of `part`, `batch` passes fused per wavefront.  With "OverlapWavefronts" (default) the
 // frame's wavefronts alternate between two lanes -- two streams with their own wavefront buffers -- and a frame that is ONE wavefront is cut into two
 // half-batches: every traversal launch is a persistent kernel whose last rays leave most of the SMs idle (nine tails per wavefront; at 1/8 of the image
@@ -605,6 +692,23 @@ int ctl_render_frame_tiled(ctl_ctx* c, int spp, int batch, int tile_w, int tile_
     // of a frame with fewer wavefronts than lanes (measured: what the overlap gains, the extra launches lose)
     const bool plain = !c->overlap || c->stage_timers || c->instrumented || c->capture_bounce > 0 || c->variance_buffer || c->user_tables || c->sort_mode != 0 || spp > 128 ||
                        c->n_lanes < 2 || (c->overlap == 1 ? spp == batch : (spp == batch && (batch & 1)));
+    const bool ho = c->handover && spp == batch && !(batch & 1) && c->has_scene && c->direct && c->fuse_traversal && c->trav_kernel == 2 && c->staged_ok && !c->staged.tl_nodes && !c->staged.ray_tma &&
+                    !c->regularization && !c->stage_timers && !c->instrumented && c->capture_bounce <= 0 && !c->variance_buffer && !c->user_tables && c->sort_mode == 0 && c->max_path_length < MAX_BOUNCES;
+    if (ho) {   // a one-wavefront frame as two half-wavefronts whose traversal launches hand their unfinished rays over
+        Window W;
+        if (tiled_window(c, W, batch / 2, tile_w, tile_h, part, n_parts)) return 1;
+        if (W.n_slots > 0) {
+            CK(cudaSetDevice(c->device));
+            CK(cudaEventRecord(c->ev_start, c->stream));
+            CK(cudaMemsetAsync(c->accum, 0, (size_t)c->w * c->h * 7 * sizeof(float), c->stream));
+            c->passes_done = 0;
+            if (generate_tables(c, 0, spp)) return 1;
+            if (render_frame_handover(c, W, batch / 2)) return 1;
+            CK(cudaEventRecord(c->ev_stop, c->stream));
+            c->events_recorded = true; c->passes_done = (uint32_t)spp;
+            return 0;
+        }
+    }
     if (plain) {
         for (int p = 0; p < spp; p += batch)
             if (ctl_render_passes_tiled(c, p == 0, batch, tile_w, tile_h, part, n_parts)) return 1;
@@ -829,6 +933,14 @@ int ctl_get_queue_sizes(ctl_ctx* c, uint32_t* ext, uint32_t* sh, int n) {
     for (int b = 0; b < n && b < MAX_BOUNCES; b++) { if (ext) ext[b] = ctr[CTR_Q + b]; if (sh) sh[b] = ctr[CTR_SH + b]; }
     return 0;
 }
+#ifdef CTL_EXP_DROP_STRAGGLERS
+int ctl_debug_counters(ctl_ctx* c, unsigned* out, int n) {   // experiment builds only: the raw per-bounce counter array of lane 0
+    if (!c || !out) return set_err("null argument");
+    CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(out, c->lanes[0].counters.p, (size_t)(n < CTR_TOTAL ? n : CTR_TOTAL) * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    return 0;
+}
+#endif
 int ctl_get_captured_rays(ctl_ctx* c, ctl_traversal_ray* host_out, int capacity) {
     if (!c) { set_err("null context"); return -1; }
     if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) { set_err("cuda error"); return -1; }

@@ -81,7 +81,8 @@ static int build_gpu(int device, const float* verts9, uint32_t n_tris, int algor
     struct { float4* p; } d_boxes = {split ? d_rboxes.p : d_tboxes.p};   // boxes of the references the builders work on
     DevBuf<int> d_left, d_right, d_pint, d_pleaf, d_first, d_last; DevBuf<ctl_bvh_node> d_nodes; DevBuf<ctl_woop_tri> d_woop; DevBuf<unsigned char> d_lastflag, d_collapse; DevBuf<float> d_cost;
     DevBuf<int> d_cid0, d_cid1, d_nn, d_count, d_ecount, d_slot, d_pleaf2, d_pst; DevBuf<float4> d_cb0, d_cb1; DevBuf<unsigned long long> d_scan; DevBuf<uint32_t> d_vals2;   // agglomerative builder
-    auto free_all = [&]() { free_pre(); d_pst.release(); d_cid0.release(); d_cid1.release(); d_nn.release(); d_count.release(); d_ecount.release(); d_slot.release(); d_pleaf2.release(); d_cb0.release(); d_cb1.release(); d_scan.release(); d_vals2.release(); d_nbox.release(); d_counts.release(); d_flags.release(); d_emit.release(); d_k0.release(); d_k1.release(); d_v0.release(); d_v1.release();
+    int* h_st_owned = nullptr;
+    auto free_all = [&]() { if (h_st_owned) cudaFreeHost(h_st_owned); h_st_owned = nullptr; free_pre(); d_pst.release(); d_cid0.release(); d_cid1.release(); d_nn.release(); d_count.release(); d_ecount.release(); d_slot.release(); d_pleaf2.release(); d_cb0.release(); d_cb1.release(); d_scan.release(); d_vals2.release(); d_nbox.release(); d_counts.release(); d_flags.release(); d_emit.release(); d_k0.release(); d_k1.release(); d_v0.release(); d_v1.release();
                             d_index.release(); d_left.release(); d_right.release(); d_pint.release(); d_pleaf.release(); d_first.release(); d_last.release(); d_nodes.release(); d_woop.release(); d_lastflag.release(); d_collapse.release(); d_cost.release(); };
 #define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { free_all(); char b_[512]; snprintf(b_, sizeof(b_), "In file %s at line %d : %s", __FILE__, __LINE__, cudaGetErrorString(e_)); return set_err(b_); } } while (0)
     CKF(d_nbox.ensure((size_t)n * 2)); CKF(d_counts.ensure((size_t)256 * nb_sort));
@@ -92,8 +93,8 @@ static int build_gpu(int device, const float* verts9, uint32_t n_tris, int algor
         CKF(d_cb0.ensure((size_t)n * 2)); CKF(d_cb1.ensure((size_t)n * 2)); CKF(d_scan.ensure((size_t)n + 1)); CKF(d_vals2.ensure(n));
         CKF(d_pst.ensure(4));
     }
-    static int* h_st = nullptr;   // pinned: round state of the agglomerative builder
-    if (!h_st) CKF(cudaHostAlloc((void**)&h_st, 4 * sizeof(int), cudaHostAllocDefault));
+    int* h_st = nullptr;   // pinned: round state of the agglomerative builder (per call: builds may run concurrently on several devices)
+    CKF(cudaHostAlloc((void**)&h_st, 4 * sizeof(int), cudaHostAllocDefault)); h_st_owned = h_st;
     CKF(cudaEventRecord(eB, st));
     CKF(cudaMemsetAsync(d_flags.p, 0, (size_t)n * 4, st)); CKF(cudaMemsetAsync(d_lastflag.p, 0, (size_t)n, st));
     const int g = (n + 255) / 256;

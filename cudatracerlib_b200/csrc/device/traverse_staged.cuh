@@ -153,7 +153,18 @@ __device__ __forceinline__ void trace_staged(const DScene& S, const StagedScene&
     int state = 3;
     auto classify = [&]() { state = ((unsigned)nodeAddr < (unsigned)SENT) ? 0 : (nodeAddr < 0 ? (inst >= 0 ? 1 : 2) : (inst >= 0 ? 2 : 3)); };
 
+#if defined(CTL_EXP_DROP_STRAGGLERS) && defined(__CUDACC__)
+    int x_drain_iters = 0;   // experiment (build variant only, WRONG results): upper bound of what deferring a draining launch's last rays could gain
+#endif
     for (;;) {
+#if defined(CTL_EXP_DROP_STRAGGLERS) && defined(__CUDACC__)
+        if (exhausted && (MODE == 0 || MODE == 4)) {
+            const unsigned x_live = __ballot_sync(0xffffffffu, state != 3);
+            if (x_live && __popc(x_live) <= CTL_EXP_DROP_LANES && ++x_drain_iters > CTL_EXP_DROP_STRAGGLERS) {
+                if (state != 3) { atomicAdd(work_ctr + 1, 1u); hit.tri = 0xffffffffu; nodeAddr = SENT; inst = -1; sp = 0; tos = SENT; state = 3; }   // abandoned: written out as a miss
+            }
+        }
+#endif
         unsigned mPend = 0;
         if (RT) { // rays on their way: have the bytes landed?  (one test per iteration, warp-uniform)
             mPend = __ballot_sync(0xffffffffu, pend_slot >= 0);

@@ -536,11 +536,11 @@ __global__ void __launch_bounds__(256) k_finish(int n_slots /* all passes */, Pa
 }
 
 // rays of the pass = sum of extension + shadow queue sizes (every traceRay call counts, TraceHelper.cu:176)
-__global__ void k_tally(const unsigned* q_count, const unsigned* sh_count, int n_bounces, unsigned long long* rays_last, unsigned long long* rays_total) {
+__global__ void k_tally(const unsigned* q_count, const unsigned* sh_count, int n_bounces, unsigned long long* rays_last, unsigned long long* rays_total, int add_to_last = 0) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         unsigned long long s = 0;
         for (int b = 0; b < n_bounces; b++) s += (unsigned long long)q_count[b] + (unsigned long long)sh_count[b];
-        *rays_last = s; atomicAdd(rays_total, s);   // two wavefronts of a frame may tally concurrently (OverlapWavefronts)
+        *rays_last = add_to_last ? *rays_last + s : s; atomicAdd(rays_total, s);   // two wavefronts of a frame may tally concurrently (OverlapWavefronts)
     }
 }
 
