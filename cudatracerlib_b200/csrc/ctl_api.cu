@@ -113,6 +113,7 @@ void ctl_destroy(ctl_ctx* c) {
     c->d_light_cdf.release(); c->d_normal_lut.release(); c->d_tri64.release(); c->d_inst.release(); c->d_treelet.release();
     c->d_tab1.release(); c->d_tab2.release(); c->d_states.release(); c->d_states0.release(); c->d_jump.release();
     if (c->h_tab1) cudaFreeHost(c->h_tab1); if (c->h_tab2) cudaFreeHost(c->h_tab2); if (c->h_tab_free) cudaEventDestroy(c->h_tab_free);
+    for (int k = 0; k < MAX_LANES; k++) { if (c->ev_cls_fork[k]) cudaEventDestroy(c->ev_cls_fork[k]); for (int j = 0; j < 3; j++) { if (c->cls_stream[k][j]) { cudaStreamSynchronize(c->cls_stream[k][j]); cudaStreamDestroy(c->cls_stream[k][j]); } if (c->ev_cls_done[k][j]) cudaEventDestroy(c->ev_cls_done[k][j]); } }
     if (c->tab_stream) { cudaStreamSynchronize(c->tab_stream); cudaStreamDestroy(c->tab_stream); } if (c->ev_tab) cudaEventDestroy(c->ev_tab);
     for (int k = 1; k < MAX_LANES; k++) { if (c->lane_stream[k]) { cudaStreamSynchronize(c->lane_stream[k]); cudaStreamDestroy(c->lane_stream[k]); } if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -153,6 +154,7 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "DeviceSampleTables") c->device_tables = v != 0;
     else if (k == "FuseTraversal") c->fuse_traversal = v != 0;
     else if (k == "OverlapWavefronts") { if (v < 0 || v > 2) return set_err("OverlapWavefronts must be 0, 1 or 2"); c->overlap = v; }
+    else if (k == "ShadeConcurrent") c->shade_concurrent = v != 0;   // the per-class shade launches of a bounce on their own streams
     else if (k == "HandOver") c->handover = v != 0;   // ctl_render_frame_tiled: one-wavefront frames as two half-wavefronts with ray hand-over between their launches
     else if (k == "HandOverDrain") { if (v < 1 || v > 4096) return set_err("HandOverDrain out of range [1,4096]"); c->handover_drain = v; }
     else if (k == "OverlapLanes") { if (v < 1 || v > MAX_LANES) return set_err("OverlapLanes out of range [1,8]"); c->n_lanes = v; }   // wavefronts of a frame in flight at once   // ctl_render_frame_tiled / ctl_comm_render_frame: the frame's wavefronts alternate between two streams
@@ -186,7 +188,7 @@ int ctl_get_param_i(ctl_ctx* c, const char* key, int* v) {
     std::string k(key);
     if (k == "MaxPathLength") *v = c->max_path_length; else if (k == "RRStartDepth") *v = c->rr_start; else if (k == "Direct") *v = c->direct;
     else if (k == "StopZeroThroughput") *v = c->stop_zero; else if (k == "Regularization") *v = c->regularization; else if (k == "SortMode") *v = c->sort_mode; else if (k == "StageTimers") *v = c->stage_timers;
-    else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables; else if (k == "FuseTraversal") *v = c->fuse_traversal; else if (k == "OverlapWavefronts") *v = c->overlap; else if (k == "OverlapLanes") *v = c->n_lanes; else if (k == "HandOver") *v = c->handover; else if (k == "HandOverDrain") *v = c->handover_drain; else if (k == "PixelVarianceBuffer") *v = c->variance_buffer; else if (k == "PassStride") *v = c->pass_stride; else if (k == "PassPhase") *v = c->pass_phase;
+    else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables; else if (k == "FuseTraversal") *v = c->fuse_traversal; else if (k == "OverlapWavefronts") *v = c->overlap; else if (k == "OverlapLanes") *v = c->n_lanes; else if (k == "HandOver") *v = c->handover; else if (k == "ShadeConcurrent") *v = c->shade_concurrent; else if (k == "HandOverDrain") *v = c->handover_drain; else if (k == "PixelVarianceBuffer") *v = c->variance_buffer; else if (k == "PassStride") *v = c->pass_stride; else if (k == "PassPhase") *v = c->pass_phase;
     else if (k == "TraversalBlocksPerSM") *v = c->trav_blocks_per_sm; else if (k == "StagedThreads") *v = c->staged_threads; else if (k == "StagedStackRows") *v = c->staged_rows;
     else if (k == "ShadeMode") *v = c->shade_mode; else if (k == "MaterialClassMask") *v = (int)c->class_mask;
     else if (k == "StagedRayTMA") *v = c->staged.ray_tma;
@@ -523,6 +525,21 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W, int lane = 
         Queues Q = {rin, pin, rout, pout, L.hit_a.p, L.hit_node.p, L.sh_rays.p, L.sh_payload.p, sort_next ? L.sort_keys.p : nullptr, sort_next ? L.sort_hist.p : nullptr, order};
         if (class_sort) {
             const unsigned* hist = L.mat_hist.p + 2 * MAT_CLASSES * b;
+            if (c->shade_concurrent) {   // the class launches are independent (disjoint segments of the hit queue, atomic appends): each on its own stream, joined before the next stage
+                if (!c->ev_cls_fork[lane]) {
+                    CK(cudaEventCreateWithFlags(&c->ev_cls_fork[lane], cudaEventDisableTiming));
+                    for (int j = 0; j < 3; j++) { CK(cudaStreamCreateWithFlags(&c->cls_stream[lane][j], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->ev_cls_done[lane][j], cudaEventDisableTiming)); }
+                }
+                CK(cudaEventRecord(c->ev_cls_fork[lane], s));
+                int j = -1;
+                for (int k = 0; k < 4; k++) if (c->class_mask & (1u << k)) {
+                    const cudaStream_t cs = j < 0 ? s : c->cls_stream[lane][j];
+                    if (j >= 0) CK(cudaStreamWaitEvent(cs, c->ev_cls_fork[lane], 0));
+                    launch_shade(regu, k, g_light, cs, c->scene, P, st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b, hist); launches++;
+                    if (j >= 0) { CK(cudaEventRecord(c->ev_cls_done[lane][j], cs)); CK(cudaStreamWaitEvent(s, c->ev_cls_done[lane][j], 0)); }
+                    j++;
+                }
+            } else
             for (int k = 0; k < 4; k++) if (c->class_mask & (1u << k)) { launch_shade(regu, k, g_light, s, c->scene, P, st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b, hist); launches++; }
             launches--;
         }

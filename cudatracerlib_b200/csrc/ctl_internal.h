@@ -84,6 +84,7 @@ struct ctl_ctx {
     // wavefront state: lane 0 runs on `stream`; lanes 1.. (own streams) hold the other wavefronts of a frame rendered with "OverlapWavefronts" (ctl_comm_render_frame)
     WaveLane lanes[MAX_LANES]; DevBuf<float4> capture;
     cudaStream_t lane_stream[MAX_LANES] = {}; cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {}; cudaStream_t tab_stream = nullptr; cudaEvent_t ev_tab = nullptr;   // tab_stream: sample tables of a frame's wavefronts
+    int shade_concurrent = 0; cudaStream_t cls_stream[MAX_LANES][3] = {}; cudaEvent_t ev_cls_fork[MAX_LANES] = {}, ev_cls_done[MAX_LANES][3] = {};   // "ShadeConcurrent": the per-class shade launches of a bounce on their own streams
     int handover = 0, handover_drain = 16; DevBuf<uint32_t> ho_buf[2]; DevBuf<unsigned> ho_cnt;   // "HandOver": one-wavefront frames as two interleaved half-wavefronts whose traversal launches hand their unfinished rays over (device/traverse_handover.cuh)
     int overlap = 1, n_lanes = 4;   // "OverlapWavefronts", "OverlapLanes": see ctl_render_frame_tiled
     DevBuf<unsigned> api_work; unsigned api_seq = 0;   // ring of work counters of the API traversal launches: calls in flight on different streams never share one

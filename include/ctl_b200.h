@@ -310,7 +310,8 @@ int      ctl_resize(ctl_ctx*, int width, int height);    /* == Tracer<true>::Res
  *    frames (ctl_render_frame_tiled / ctl_comm_render_frame): "OverlapWavefronts" (0 / 1 [default: wavefronts of a frame on several streams when the frame has
  *    several] / 2 [also cut the batches of a one-wavefront frame]), "OverlapLanes" (1..8, default 4), "HandOver" (0 [default] / 1: a one-wavefront frame as two
  *    interleaved half-wavefronts whose traversal launches hand their unfinished rays over instead of draining; measured: correct, not faster -- DESIGN.md
- *    section 5), "HandOverDrain" (loop iterations a warp keeps going after the queue ran dry, default 16). */
+ *    section 5), "HandOverDrain" (loop iterations a warp keeps going after the queue ran dry, default 16), "ShadeConcurrent" (0 [default] / 1: the per-class
+ *    shade launches of a bounce on their own streams; measured: -2 % on configs[2], a loss with lanes). */
 int ctl_set_param_i(ctl_ctx*, const char* key, int value);   /* == TracerParameterCollection::setValue<int> (Kernel/TracerSettings.h:277-283) */
 int ctl_get_param_i(ctl_ctx*, const char* key, int* value);  /* == getValue<int> (Kernel/TracerSettings.h:266-272) */
 /* == UpdateKernel scene half (Kernel/TraceHelper.cu:182-217): host view copied to HBM */

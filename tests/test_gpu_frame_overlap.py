@@ -67,6 +67,25 @@ def test_frame_with_host_generated_tables_and_lanes(built_lib):
     t.close()
 
 
+def test_concurrent_class_shade_launches(built_lib):
+    """ShadeConcurrent = 1: the per-class shade launches of a bounce run on their own streams (disjoint queue segments, atomic appends) -- same paths."""
+    w, h = 320, 180
+    s = ctl.Scene("c3", w, h)
+    t = ctl.PathTracer(w, h); t.InitializeScene(s); t.setParameter("MaxPathLength", 8)
+    out = {}
+    for conc in (0, 1, 0):
+        t.setParameter("ShadeConcurrent", conc)
+        r0 = t.getTotalRays(); t.DoPasses(4, new_trace=True); t.synchronize()
+        out[conc] = (t.readAccumulator(), t.getTotalRays() - r0)
+    assert out[0][1] == out[1][1] and np.array_equal(out[0][0]["weight_sum"], out[1][0]["weight_sum"])
+    assert np.allclose(out[0][0]["rgb"], out[1][0]["rgb"], rtol=2e-5, atol=1e-6)
+    t.setParameter("ShadeConcurrent", 1); t.setParameter("OverlapLanes", 3)
+    t.DoFrame(8, 2); t.synchronize(); a = t.readAccumulator()
+    t.setParameter("ShadeConcurrent", 0); t.DoFrame(8, 2); t.synchronize(); b = t.readAccumulator()
+    assert np.array_equal(a["weight_sum"], b["weight_sum"]) and np.allclose(a["rgb"], b["rgb"], rtol=2e-5, atol=1e-6)
+    t.close()
+
+
 def test_frame_argument_errors(built_lib):
     t = ctl.PathTracer(64, 64)
     with pytest.raises(RuntimeError, match="multiple of batch"):
