@@ -149,6 +149,7 @@ def lib():
     L.ctl_render_passes_tiled.argtypes = [vp, i32, i32, i32, i32, i32, i32]
     L.ctl_render_frame_tiled.argtypes = [vp, i32, i32, i32, i32, i32, i32]
     L.ctl_wavefront_pass.argtypes = [vp, i32]
+    L.ctl_wavefront_frame.argtypes = [vp, i32]
     L.ctl_read_sample_tables.argtypes = [vp, i32, vp, vp]
     L.ctl_synchronize.argtypes = [vp]
     L.ctl_read_accum.argtypes = [vp, vp]
@@ -533,6 +534,10 @@ class WavefrontPathTracer(PathTracer):
 
     def DoPassTiled(self, *a, **k):
         raise NotImplementedError("WavefrontPathTracer renders whole frames")
+
+    def DoFrame(self, spp, *a, **k):
+        """ctl_wavefront_frame: a new trace of spp passes, the passes overlapped on up to "OverlapLanes" streams."""
+        _check(lib().ctl_wavefront_frame(self._ctx, int(spp))); self._new_trace = False
 
     DoPasses = DoPassTiled
 

@@ -121,8 +121,7 @@ void ctl_destroy(ctl_ctx* c) {
     c->ho_buf[0].release(); c->ho_buf[1].release(); c->ho_cnt.release();
     c->capture.release(); c->api_work.release(); c->stats.release();
     c->own_accum.release(); c->d_captured_n.release(); c->resolve_tmp.release(); c->pipe_rgbe.release(); c->pipe_partial.release(); c->pipe_lum.release(); c->d_var.release(); c->nlm_cached.release(); c->nlm_varh.release(); c->nlm_weights.release(); c->nlm_last_update = -1; c->nlm_pixels = 0; c->d_node_alias.release();
-    c->w_thr.release(); c->w_lxy.release(); c->w_df.release(); c->w_ray.release(); c->w_misc.release(); c->w_res.release(); c->w_desc.release();
-    for (int k = 0; k < 2; k++) { c->w_sec[k].release(); c->w_sres[k].release(); }
+    for (int k = 0; k < MAX_LANES; k++) c->wl[k].release();
     for (auto e : c->stage_ev) cudaEventDestroy(e);
     if (c->ev_start) cudaEventDestroy(c->ev_start); if (c->ev_stop) cudaEventDestroy(c->ev_stop);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -785,85 +784,141 @@ __global__ void k_set_u32(unsigned* p, unsigned v) { *p = v; }
 // One pass = one path per pixel through the DoubleRayBuffer-shaped queue: create -> { intersect primaries (+ last iteration's secondaries),
 // iterate } x MaxPathLength.  Unlike the reference nothing crosses the host per bounce (it copies the queue struct to and from the device
 // around every kernel, cu:175-188): the queue sizes stay in device counters and an empty iteration costs three empty launches.
-int ctl_wavefront_pass(ctl_ctx* c, int new_trace) {
-    if (!c) return set_err("null context");
-    if (!c->has_scene) return set_err("no scene uploaded");
-    CK(cudaSetDevice(c->device));
-    CK(cudaEventRecord(c->ev_start, c->stream));
-    if (new_trace) { CK(cudaMemsetAsync(c->accum, 0, (size_t)c->w * c->h * 7 * sizeof(float), c->stream)); c->passes_done = 0; }
-    const uint32_t pass_index = (uint32_t)c->pass_phase + (uint32_t)c->pass_stride * c->passes_done;   // which pass of the (possibly shared) frame this is
-    if (c->user_tables) c->user_tables = false;
-    else if (generate_tables(c, pass_index, 1)) return 1;
-    c->scene.d1 = c->d_tab1.p; c->scene.d2 = (const float2*)c->d_tab2.p;
+// One WavefrontPathTracer pass on lane `lane` (stream st), drawing from sample-table set `table_set`.  framed: part of ctl_wavefront_frame (the frame owns the
+// accumulator clear, the tables, the timing events and the pass counter).
+static int wavefront_pass_on(ctl_ctx* c, int new_trace, int lane, cudaStream_t st, uint32_t pass_index, int table_set, bool framed) {
+    WptLane& WL = c->wl[lane];
+    if (!framed) {
+        CK(cudaEventRecord(c->ev_start, st));
+        if (new_trace) { CK(cudaMemsetAsync(c->accum, 0, (size_t)c->w * c->h * 7 * sizeof(float), st)); c->passes_done = 0; }
+        if (c->user_tables) c->user_tables = false;
+        else if (generate_tables(c, pass_index, 1)) return 1;
+    }
     c->scene.img_w = c->w; c->scene.img_h = c->h;
+    DScene scene = c->scene;   // this pass's view of the scene: its own sample-table set
+    scene.d1 = c->d_tab1.p + TAB1 * table_set; scene.d2 = (const float2*)(c->d_tab2.p + TAB2 * table_set);
     const size_t n = (size_t)c->w * c->h;
     if (n > 0x3fffffffull) return set_err("image too large for the wavefront queue");
     const int n_tiles = (int)((n + WPT_TILE - 1) / WPT_TILE);
     const int mpl = c->max_path_length;
-    CK(c->w_thr.ensure(n)); CK(c->w_lxy.ensure(n)); CK(c->w_df.ensure(n)); CK(c->w_misc.ensure(n)); CK(c->w_ray.ensure(2 * n)); CK(c->w_res.ensure(n));
-    for (int k = 0; k < 2; k++) { CK(c->w_sec[k].ensure(2 * n)); CK(c->w_sres[k].ensure(n)); }
-    CK(c->w_desc.ensure((size_t)mpl * (n_tiles + 1)));
+    CK(WL.w_thr.ensure(n)); CK(WL.w_lxy.ensure(n)); CK(WL.w_df.ensure(n)); CK(WL.w_misc.ensure(n)); CK(WL.w_ray.ensure(2 * n)); CK(WL.w_res.ensure(n));
+    for (int k = 0; k < 2; k++) { CK(WL.w_sec[k].ensure(2 * n)); CK(WL.w_sres[k].ensure(n)); }
+    CK(WL.w_desc.ensure((size_t)mpl * (n_tiles + 1)));
     c->stage_kind.clear();
-    unsigned* ctr = c->lanes[0].counters.p;
-    CK(cudaMemsetAsync(ctr, 0, CTR_TOTAL * sizeof(unsigned), c->stream));
-    CK(cudaMemsetAsync(c->w_desc.p, 0, (size_t)mpl * (n_tiles + 1) * sizeof(unsigned long long), c->stream));
-    if (c->instrumented) CK(cudaMemsetAsync(c->stats.p + 2, 0, 8 * sizeof(unsigned long long), c->stream));
+    CK(c->lanes[lane].counters.ensure(CTR_TOTAL));
+    unsigned* ctr = c->lanes[lane].counters.p;
+    CK(cudaMemsetAsync(ctr, 0, CTR_TOTAL * sizeof(unsigned), st));
+    CK(cudaMemsetAsync(WL.w_desc.p, 0, (size_t)mpl * (n_tiles + 1) * sizeof(unsigned long long), st));
+    if (c->instrumented) CK(cudaMemsetAsync(c->stats.p + 2, 0, 8 * sizeof(unsigned long long), st));
     const int g_light = grid_for(c, c->shade_blocks_per_sm), g_trav = grid_for(c, c->trav_blocks_per_sm);
     uint32_t launches = 0;
     stage_mark(c, 0);
-    k_set_u32<<<1, 1, 0, c->stream>>>(ctr + CTR_Q, (unsigned)n);
-    WptBuf B = {c->w_thr.p, c->w_lxy.p, c->w_df.p, c->w_misc.p, c->w_ray.p, c->w_res.p, nullptr, nullptr};
-    k_wpt_create<<<g_light, 256, 0, c->stream>>>(c->scene, B, (int)n);
+    k_set_u32<<<1, 1, 0, st>>>(ctr + CTR_Q, (unsigned)n);
+    WptBuf B = {WL.w_thr.p, WL.w_lxy.p, WL.w_df.p, WL.w_misc.p, WL.w_ray.p, WL.w_res.p, nullptr, nullptr};
+    k_wpt_create<<<g_light, 256, 0, st>>>(scene, B, (int)n);
     launches += 2;
     for (int d = 0; d < mpl; d++) {
         stage_mark(c, 1);
         // FinishIteration (DoubleRayBuffer.h:84-112): the primaries and the secondary rays pushed by iteration d-1
         const bool have_sec = d > 0 && c->direct;
         if (c->instrumented) { // visit counts for the roofline (ctl_get_visit_counts: "extension" = primaries, "shadow" = secondaries): unfused, counting builds
-            launch_intersect<2, false, true>(c, g_trav, c->stream, c->scene, (const float4*)c->w_ray.p, ctr + CTR_Q + d, 0, ctr + CTR_WORK + 2 * d, nullptr, nullptr, nullptr, nullptr, (void*)c->w_res.p, c->stats.p + 2);
+            launch_intersect<2, false, true>(c, g_trav, st, scene, (const float4*)WL.w_ray.p, ctr + CTR_Q + d, 0, ctr + CTR_WORK + 2 * d, nullptr, nullptr, nullptr, nullptr, (void*)WL.w_res.p, c->stats.p + 2);
             launches++;
             if (have_sec) {
                 stage_mark(c, 3);
-                launch_intersect<2, true, true>(c, g_trav, c->stream, c->scene, (const float4*)c->w_sec[(d - 1) & 1].p, ctr + CTR_SH + d - 1, 0, ctr + CTR_WORK + 2 * d + 1, nullptr, nullptr, nullptr, nullptr,
-                                                (void*)c->w_sres[(d - 1) & 1].p, c->stats.p + 6);
+                launch_intersect<2, true, true>(c, g_trav, st, scene, (const float4*)WL.w_sec[(d - 1) & 1].p, ctr + CTR_SH + d - 1, 0, ctr + CTR_WORK + 2 * d + 1, nullptr, nullptr, nullptr, nullptr,
+                                                (void*)WL.w_sres[(d - 1) & 1].p, c->stats.p + 6);
                 launches++;
             }
         } else if (have_sec && c->fuse_traversal && c->trav_kernel == 2 && c->staged_ok) {
-            const TravOut out = {nullptr, nullptr, nullptr, nullptr, (void*)c->w_res.p, (const float4*)c->w_sec[(d - 1) & 1].p, 0, (void*)c->w_sres[(d - 1) & 1].p};
-            launch_staged<5, false, false>(c, c->stream, (const float4*)c->w_ray.p, ctr + CTR_Q + d, ctr + CTR_SH + d - 1, 0, ctr + CTR_WORK + 2 * d, out, nullptr);
+            const TravOut out = {nullptr, nullptr, nullptr, nullptr, (void*)WL.w_res.p, (const float4*)WL.w_sec[(d - 1) & 1].p, 0, (void*)WL.w_sres[(d - 1) & 1].p};
+            launch_staged<5, false, false>(c, st, (const float4*)WL.w_ray.p, ctr + CTR_Q + d, ctr + CTR_SH + d - 1, 0, ctr + CTR_WORK + 2 * d, out, nullptr);
             launches++;
         } else if (have_sec && c->fuse_traversal && c->trav_kernel == 0) {
-            k_intersect_fused_api<<<g_trav, 128, 0, c->stream>>>(c->scene, c->tune_p, (const float4*)c->w_ray.p, ctr + CTR_Q + d, (const float4*)c->w_sec[(d - 1) & 1].p, ctr + CTR_SH + d - 1,
-                                                                  ctr + CTR_WORK + 2 * d, (void*)c->w_res.p, (void*)c->w_sres[(d - 1) & 1].p);
+            k_intersect_fused_api<<<g_trav, 128, 0, st>>>(scene, c->tune_p, (const float4*)WL.w_ray.p, ctr + CTR_Q + d, (const float4*)WL.w_sec[(d - 1) & 1].p, ctr + CTR_SH + d - 1,
+                                                                  ctr + CTR_WORK + 2 * d, (void*)WL.w_res.p, (void*)WL.w_sres[(d - 1) & 1].p);
             launches++;
         } else {
-            launch_intersect<2, false, false>(c, g_trav, c->stream, c->scene, (const float4*)c->w_ray.p, ctr + CTR_Q + d, 0, ctr + CTR_WORK + 2 * d, nullptr, nullptr, nullptr, nullptr, (void*)c->w_res.p, nullptr);
+            launch_intersect<2, false, false>(c, g_trav, st, scene, (const float4*)WL.w_ray.p, ctr + CTR_Q + d, 0, ctr + CTR_WORK + 2 * d, nullptr, nullptr, nullptr, nullptr, (void*)WL.w_res.p, nullptr);
             launches++;
             if (have_sec) {
                 stage_mark(c, 3);
-                launch_intersect<2, true, false>(c, g_trav, c->stream, c->scene, (const float4*)c->w_sec[(d - 1) & 1].p, ctr + CTR_SH + d - 1, 0, ctr + CTR_WORK + 2 * d + 1, nullptr, nullptr, nullptr, nullptr,
-                                                 (void*)c->w_sres[(d - 1) & 1].p, nullptr);
+                launch_intersect<2, true, false>(c, g_trav, st, scene, (const float4*)WL.w_sec[(d - 1) & 1].p, ctr + CTR_SH + d - 1, 0, ctr + CTR_WORK + 2 * d + 1, nullptr, nullptr, nullptr, nullptr,
+                                                 (void*)WL.w_sres[(d - 1) & 1].p, nullptr);
                 launches++;
             }
         }
         stage_mark(c, 2);
-        B.sec_out = c->w_sec[d & 1].p; B.sec_res = c->w_sres[(d - 1) & 1].p;
+        B.sec_out = WL.w_sec[d & 1].p; B.sec_res = WL.w_sres[(d - 1) & 1].p;
         const WptParams P = {d, (int)pass_index + 1, mpl, c->rr_start}; // m_uPassesDone++ precedes DoRender (Kernel/Tracer.h:231-232)
-        unsigned long long* desc = c->w_desc.p + (size_t)d * (n_tiles + 1);
-        if (c->direct) k_wpt_iterate<true><<<n_tiles, WPT_TILE, 0, c->stream>>>(c->scene, P, B, ctr + CTR_Q + d, ctr + CTR_Q + d + 1, ctr + CTR_SH + d, desc, n_tiles, c->accum);
-        else k_wpt_iterate<false><<<n_tiles, WPT_TILE, 0, c->stream>>>(c->scene, P, B, ctr + CTR_Q + d, ctr + CTR_Q + d + 1, ctr + CTR_SH + d, desc, n_tiles, c->accum);
+        unsigned long long* desc = WL.w_desc.p + (size_t)d * (n_tiles + 1);
+        if (c->direct) k_wpt_iterate<true><<<n_tiles, WPT_TILE, 0, st>>>(scene, P, B, ctr + CTR_Q + d, ctr + CTR_Q + d + 1, ctr + CTR_SH + d, desc, n_tiles, c->accum);
+        else k_wpt_iterate<false><<<n_tiles, WPT_TILE, 0, st>>>(scene, P, B, ctr + CTR_Q + d, ctr + CTR_Q + d + 1, ctr + CTR_SH + d, desc, n_tiles, c->accum);
         launches++;
     }
     stage_mark(c, 4);
-    k_tally<<<1, 32, 0, c->stream>>>(ctr + CTR_Q, ctr + CTR_SH, mpl, c->stats.p, c->stats.p + 1);
+    k_tally<<<1, 32, 0, st>>>(ctr + CTR_Q, ctr + CTR_SH, mpl, c->stats.p, c->stats.p + 1);
     launches++;
     stage_mark(c, 5);
     CK(cudaGetLastError());
+    c->n_launches = launches;
+    if (framed) return 0;
     if (ctl_variance_after_pass(c, new_trace != 0)) return 1;
+    CK(cudaEventRecord(c->ev_stop, st));
+    c->events_recorded = true;
+    c->passes_done += 1;
+    return 0;
+}
+
+int ctl_wavefront_pass(ctl_ctx* c, int new_trace) {
+    if (!c) return set_err("null context");
+    if (!c->has_scene) return set_err("no scene uploaded");
+    CK(cudaSetDevice(c->device));
+    const uint32_t pass_index = (uint32_t)c->pass_phase + (uint32_t)c->pass_stride * (new_trace ? 0u : c->passes_done);   // which pass of the (possibly shared) frame this is
+    return wavefront_pass_on(c, new_trace, 0, c->stream, pass_index, 0, false);
+}
+
+// One progressive frame of the WavefrontPathTracer: a new trace of `spp` passes.  Its passes are independent given their index (random numbers are keyed by
+// pass and queue slot, results go to the accumulator by atomics), so with "OverlapWavefronts" they run on up to "OverlapLanes" streams with their own
+// queues -- the drain of one pass's traversal launches is filled by another pass's.  Same passes, same paths as spp ctl_wavefront_pass calls.
+int ctl_wavefront_frame(ctl_ctx* c, int spp) {
+    if (!c) return set_err("null context");
+    if (!c->has_scene) return set_err("no scene uploaded");
+    if (spp < 1 || spp > 4096) return set_err("spp out of range [1,4096]");
+    CK(cudaSetDevice(c->device));
+    const int n_lanes = c->n_lanes < spp ? c->n_lanes : spp;
+    const bool plain = !c->overlap || n_lanes < 2 || spp > 128 || c->stage_timers || c->instrumented || c->variance_buffer || c->user_tables;
+    if (plain) { for (int p = 0; p < spp; p++) if (ctl_wavefront_pass(c, p == 0)) return 1; return 0; }
+    if (!c->ev_fork) CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for (int k = 1; k < n_lanes; k++) if (!c->lane_stream[k]) {
+        CK(cudaStreamCreateWithFlags(&c->lane_stream[k], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
+    }
+    if (!c->tab_stream) { CK(cudaStreamCreateWithFlags(&c->tab_stream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->ev_tab, cudaEventDisableTiming)); }
+    CK(cudaEventRecord(c->ev_start, c->stream));
+    CK(cudaMemsetAsync(c->accum, 0, (size_t)c->w * c->h * 7 * sizeof(float), c->stream));
+    c->passes_done = 0;
+    if (ensure_tables(c, spp)) return 1;
+    if (!c->device_tables) { if (ensure_host_tables(c, spp)) return 1; CK(cudaEventSynchronize(c->h_tab_free)); }
+    CK(cudaEventRecord(c->ev_fork, c->stream));
+    CK(cudaStreamWaitEvent(c->tab_stream, c->ev_fork, 0));
+    for (int k = 1; k < n_lanes; k++) CK(cudaStreamWaitEvent(c->lane_stream[k], c->ev_fork, 0));
+    uint32_t launches = 0;
+    for (int p = 0; p < spp; p++) {
+        const int lane = p % n_lanes;
+        const cudaStream_t st = lane ? c->lane_stream[lane] : c->stream;
+        const uint32_t pass_index = (uint32_t)c->pass_phase + (uint32_t)c->pass_stride * (uint32_t)p;
+        if (generate_tables(c, pass_index, 1, p, c->tab_stream, false)) return 1;
+        CK(cudaEventRecord(c->ev_tab, c->tab_stream));
+        CK(cudaStreamWaitEvent(st, c->ev_tab, 0));
+        if (wavefront_pass_on(c, 0, lane, st, pass_index, p, true)) return 1;
+        launches += c->n_launches;
+    }
+    c->n_launches = launches;
+    for (int k = 1; k < n_lanes; k++) { CK(cudaEventRecord(c->ev_join[k], c->lane_stream[k])); CK(cudaStreamWaitEvent(c->stream, c->ev_join[k], 0)); }
     CK(cudaEventRecord(c->ev_stop, c->stream));
     c->events_recorded = true;
-    c->n_launches = launches;
-    c->passes_done += 1;
+    c->passes_done = (uint32_t)spp;
     return 0;
 }
 

@@ -61,6 +61,12 @@ struct WaveLane {
     }
 };
 
+// Queue of one WavefrontPathTracer pass in flight (DoubleRayBuffer<WavefrontPTRayData>)
+struct WptLane {
+    DevBuf<float4> w_thr, w_lxy, w_df, w_ray, w_sec[2]; DevBuf<uint2> w_misc; DevBuf<uint4> w_res, w_sres[2]; DevBuf<unsigned long long> w_desc;
+    void release() { w_thr.release(); w_lxy.release(); w_df.release(); w_ray.release(); w_misc.release(); w_res.release(); w_desc.release(); for (int k = 0; k < 2; k++) { w_sec[k].release(); w_sres[k].release(); } }
+};
+
 struct ctl_ctx {
     ncclComm* comm = nullptr; int comm_rank = 0, comm_size = 1; unsigned long long* comm_scratch = nullptr;   // ctl_comm_init_* (ctl_comm.cu)
     int device = 0, w = 0, h = 0;
@@ -89,7 +95,7 @@ struct ctl_ctx {
     int overlap = 1, n_lanes = 4;   // "OverlapWavefronts", "OverlapLanes": see ctl_render_frame_tiled
     DevBuf<unsigned> api_work; unsigned api_seq = 0;   // ring of work counters of the API traversal launches: calls in flight on different streams never share one
     // WavefrontPathTracer queue (DoubleRayBuffer<WavefrontPTRayData>)
-    DevBuf<float4> w_thr, w_lxy, w_df, w_ray, w_sec[2]; DevBuf<uint2> w_misc; DevBuf<uint4> w_res, w_sres[2]; DevBuf<unsigned long long> w_desc;
+    WptLane wl[MAX_LANES];   // lane 0: ctl_wavefront_pass; lanes 1..: the other passes of a ctl_wavefront_frame in flight
     DevBuf<unsigned long long> stats; // [0] rays_last [1] rays_total [2..4] ext visits [5] ext rays [6..8] shadow visits [9] shadow rays
     DevBuf<float> own_accum; float* accum = nullptr; DevBuf<uchar4> resolve_tmp, pipe_rgbe; DevBuf<float4> pipe_partial; DevBuf<float> pipe_lum;
     DevBuf<ctl_pixel_variance_info> d_var; int variance_buffer = 0;

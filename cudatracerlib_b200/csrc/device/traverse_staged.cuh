@@ -135,7 +135,13 @@ __device__ __forceinline__ void trace_staged(const DScene& S, const StagedScene&
     int pend_slot = -1;             // RT: >= 0 while this lane's ray is on its way into the warp buffer (the lane idles in state 3)
     uint32_t wphase = 0;            // RT: parity of the warp barrier's current phase (warp-uniform)
 
+#if defined(CTL_EXP_OLD_RAY_BOOST) && defined(__CUDACC__)
+    int x_age = 0;
+#endif
     auto start_ray = [&](const float4 ro, const float4 rd) { // a fetched ray enters the scene level
+#if defined(CTL_EXP_OLD_RAY_BOOST) && defined(__CUDACC__)
+        x_age = 0;
+#endif
         ox = ro.x; oy = ro.y; oz = ro.z; dx = rd.x; dy = rd.y; dz = rd.z;
         hit.u = hit.v = 0.0f; hit.tri = 0xffffffffu; hit.node = 0xffffffffu;
         if (MODE == 3) { tri_lo = S.ray_eps; box_lo = 0.0f; hit.dist = FLT_MAX; }
@@ -297,6 +303,9 @@ __device__ __forceinline__ void trace_staged(const DScene& S, const StagedScene&
         // state is classified once, on leaving
         if (state == 0) {
             int ns = N_STEPS;
+#if defined(CTL_EXP_OLD_RAY_BOOST) && defined(__CUDACC__)   // experiment (build variant): a ray that has been in its lane for many iterations takes more node steps per iteration
+            if (++x_age > CTL_EXP_OLD_RAY_AGE) ns *= CTL_EXP_OLD_RAY_BOOST;
+#endif
             do {
                 F8 nA, nB;
                 if (nodeAddr & ST_TL) { // treelet node: four conflict-spread LDS.128

@@ -127,6 +127,12 @@ public:
         check(ctl_wavefront_pass(handle(), take_new_trace(a_NewTrace) ? 1 : 0));
         finish_pass(image);
     }
+    // a whole progressive frame: StartNewTrace + spp DoPass calls, the passes overlapped on several streams (ctl_wavefront_frame)
+    void DoFrame(ctl_pixel_data* image, int spp) {
+        require_ctx();
+        check(ctl_wavefront_frame(handle(), spp)); take_new_trace(false);
+        finish_pass(image);
+    }
 };
 
 // Several GPUs of one node driven by ONE host process (no reference counterpart: the reference is single-GPU).  One PathTracer per device, the same

@@ -363,6 +363,10 @@ int ctl_render_frame_tiled(ctl_ctx*, int spp, int batch, int tile_w, int tile_h,
  *    "PassStride" / "PassPhase" (ctl_set_param_i, default 1 / 0): the k-th pass since the last new trace is pass PassPhase + k * PassStride
  *    of the frame (sample tables, sampler skip) -- several devices share a frame by pass index and sum their accumulators. */
 int ctl_wavefront_pass(ctl_ctx*, int new_trace);
+/* One progressive frame of the WavefrontPathTracer: a new trace of `spp` passes (== StartNewTrace + spp DoPass calls).  The passes are independent given
+ * their index, so with "OverlapWavefronts" they run on up to "OverlapLanes" streams with their own queue buffers and the drain of one pass's traversal
+ * launches is filled by another pass's; same passes, same paths, PixelData equal up to the order of the float atomics.  Asynchronous. */
+int ctl_wavefront_frame(ctl_ctx*, int spp);
 /* Device copy-back of sample-table set `table_set` (0 .. passes of the last batch - 1) for verification. */
 int ctl_read_sample_tables(ctl_ctx*, int table_set, float* d1, float* d2);
 /* == the ThrowCudaErrors(cudaDeviceSynchronize()) the reference ends every launch with (Kernel/TraceHelper.cu:745), on this context's stream only */

@@ -27,6 +27,20 @@ st.synchronize()
 ms = e0.elapsed_time(e1) / frames
 rays = t.getTotalRays() // (frames + 3)
 out["wavefront_pt"] = {"ms_per_frame": ms, "rays_per_frame": int(rays), "mrays_s": rays / ms / 1e3}
+# the same frames through ctl_wavefront_frame: the passes of a frame on 1 .. 8 lanes (streams with their own queue buffers)
+out["wavefront_pt_frame"] = {}
+for lanes in (1, 2, 4, 8):
+    t.setParameter("OverlapLanes", lanes)
+    for rep in range(2): t.DoFrame(spp)
+    t.synchronize(); r0 = t.getTotalRays()
+    with torch.cuda.stream(st):
+        e0.record(st)
+        for f in range(frames): t.DoFrame(spp)
+        e1.record(st)
+    st.synchronize()
+    msf = e0.elapsed_time(e1) / frames; rf = (t.getTotalRays() - r0) // frames
+    out["wavefront_pt_frame"][str(lanes)] = {"ms_per_frame": msf, "mrays_s": rf / msf / 1e3}
+t.setParameter("OverlapLanes", 4)
 t.setParameter("StageTimers", 1); t.DoPass(True); t.synchronize()
 sm, nl = t.stageTimes(); out["wavefront_pt"]["stage_ms_one_pass"] = dict(zip(["create", "primary_trav", "iterate", "secondary_trav", "tally"], [round(x, 3) for x in sm])); out["wavefront_pt"]["launches_per_pass"] = nl
 e, sh = t.queueSizes(mpl); out["wavefront_pt"]["queues"] = [e.tolist(), sh.tolist()]

@@ -257,3 +257,23 @@ def test_double_ray_buffer_header(built_lib, orc, tmp_path):
         b, sh = orc.intersect(s.view, bounce), orc.intersect(s.view, sec)
         assert np.array_equal(out[hit, 2].view(np.uint32), b["dist"].view(np.uint32)) and np.array_equal(out[hit, 3].view(np.uint32), sh["dist"].view(np.uint32))
         assert (out[~hit, 2:] == 0).all()
+
+
+def test_wavefront_frame_equals_sequential_passes(built_lib):
+    """ctl_wavefront_frame: the passes of a frame on several streams with their own queues -- same passes, same paths: weights and ray totals equal, radiance
+    equal up to the order of the float atomics; also with host-generated tables and with one lane (= the plain loop)."""
+    w, h, spp = 160, 120, 6
+    s = ctl.Scene("soup", w, h)
+    t = ctl.WavefrontPathTracer(w, h); t.InitializeScene(s); t.setParameter("MaxPathLength", 6)
+    r0 = t.getTotalRays()
+    for p in range(spp): t.DoPass(p == 0)
+    t.synchronize(); ref = t.readAccumulator(); ref_rays = t.getTotalRays() - r0
+    for lanes, dev in ((4, 1), (8, 1), (3, 0), (1, 1)):
+        t.setParameter("OverlapLanes", lanes); t.setParameter("DeviceSampleTables", dev)
+        for _ in range(2):
+            r0 = t.getTotalRays(); t.DoFrame(spp); t.synchronize()
+            img = t.readAccumulator()
+            assert t.getTotalRays() - r0 == ref_rays and t.getNumPassesDone() == spp
+            assert np.array_equal(img["weight_sum"], ref["weight_sum"]) and np.allclose(img["rgb"], ref["rgb"], rtol=2e-5, atol=1e-6)
+    t.DoPass(False); t.synchronize(); assert t.getNumPassesDone() == spp + 1   # and single passes continue the trace
+    t.close()
