@@ -118,7 +118,8 @@ void ctl_destroy(ctl_ctx* c) {
     for (int k = 1; k < MAX_LANES; k++) { if (c->lane_stream[k]) { cudaStreamSynchronize(c->lane_stream[k]); cudaStreamDestroy(c->lane_stream[k]); } if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (int k = 0; k < MAX_LANES; k++) c->lanes[k].release();
-    c->ho_buf[0].release(); c->ho_buf[1].release(); c->ho_cnt.release();
+    c->ho_buf[0].release(); c->ho_buf[1].release(); c->ho_cnt.release(); c->df_cnt.release();
+    for (int k = 0; k < MAX_LANES; k++) { c->df_sh_rays[k].release(); c->df_sh_payload[k].release(); }
     c->capture.release(); c->api_work.release(); c->stats.release();
     c->own_accum.release(); c->d_captured_n.release(); c->resolve_tmp.release(); c->pipe_rgbe.release(); c->pipe_partial.release(); c->pipe_lum.release(); c->d_var.release(); c->nlm_cached.release(); c->nlm_varh.release(); c->nlm_weights.release(); c->nlm_last_update = -1; c->nlm_pixels = 0; c->d_node_alias.release();
     for (int k = 0; k < MAX_LANES; k++) c->wl[k].release();
@@ -154,6 +155,8 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "FuseTraversal") c->fuse_traversal = v != 0;
     else if (k == "OverlapWavefronts") { if (v < 0 || v > 2) return set_err("OverlapWavefronts must be 0, 1 or 2"); c->overlap = v; }
     else if (k == "ShadeConcurrent") c->shade_concurrent = v != 0;   // the per-class shade launches of a bounce on their own streams
+    else if (k == "DeferStragglers") c->defer = v != 0;   // frames: traversal launches move their unfinished rays into the wavefront's next launch (paths may lag DeferMaxLag bounces)
+    else if (k == "DeferMaxLag") { if (v < 1 || v > 3) return set_err("DeferMaxLag out of range [1,3]"); c->defer_max_lag = v; }
     else if (k == "HandOver") c->handover = v != 0;   // ctl_render_frame_tiled: one-wavefront frames as two half-wavefronts with ray hand-over between their launches
     else if (k == "HandOverDrain") { if (v < 1 || v > 4096) return set_err("HandOverDrain out of range [1,4096]"); c->handover_drain = v; }
     else if (k == "OverlapLanes") { if (v < 1 || v > MAX_LANES) return set_err("OverlapLanes out of range [1,8]"); c->n_lanes = v; }   // wavefronts of a frame in flight at once   // ctl_render_frame_tiled / ctl_comm_render_frame: the frame's wavefronts alternate between two streams
@@ -187,7 +190,7 @@ int ctl_get_param_i(ctl_ctx* c, const char* key, int* v) {
     std::string k(key);
     if (k == "MaxPathLength") *v = c->max_path_length; else if (k == "RRStartDepth") *v = c->rr_start; else if (k == "Direct") *v = c->direct;
     else if (k == "StopZeroThroughput") *v = c->stop_zero; else if (k == "Regularization") *v = c->regularization; else if (k == "SortMode") *v = c->sort_mode; else if (k == "StageTimers") *v = c->stage_timers;
-    else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables; else if (k == "FuseTraversal") *v = c->fuse_traversal; else if (k == "OverlapWavefronts") *v = c->overlap; else if (k == "OverlapLanes") *v = c->n_lanes; else if (k == "HandOver") *v = c->handover; else if (k == "ShadeConcurrent") *v = c->shade_concurrent; else if (k == "HandOverDrain") *v = c->handover_drain; else if (k == "PixelVarianceBuffer") *v = c->variance_buffer; else if (k == "PassStride") *v = c->pass_stride; else if (k == "PassPhase") *v = c->pass_phase;
+    else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables; else if (k == "FuseTraversal") *v = c->fuse_traversal; else if (k == "OverlapWavefronts") *v = c->overlap; else if (k == "OverlapLanes") *v = c->n_lanes; else if (k == "HandOver") *v = c->handover; else if (k == "DeferStragglers") *v = c->defer; else if (k == "DeferMaxLag") *v = c->defer_max_lag; else if (k == "ShadeConcurrent") *v = c->shade_concurrent; else if (k == "HandOverDrain") *v = c->handover_drain; else if (k == "PixelVarianceBuffer") *v = c->variance_buffer; else if (k == "PassStride") *v = c->pass_stride; else if (k == "PassPhase") *v = c->pass_phase;
     else if (k == "TraversalBlocksPerSM") *v = c->trav_blocks_per_sm; else if (k == "StagedThreads") *v = c->staged_threads; else if (k == "StagedStackRows") *v = c->staged_rows;
     else if (k == "ShadeMode") *v = c->shade_mode; else if (k == "MaterialClassMask") *v = (int)c->class_mask;
     else if (k == "StagedRayTMA") *v = c->staged.ray_tma;
@@ -696,6 +699,81 @@ static int render_frame_handover(ctl_ctx* c, Window W, int n_half) {
     return 0;
 }
 
+// One wavefront of a frame with straggler deferral ("DeferStragglers", device/traverse_handover.cuh: k_intersect_defer): every traversal launch moves the
+// rays it has not finished a few iterations after its queue ran dry into the next launch (front of the next bounce's queues + a record of the lane state);
+// their paths run up to max_lag bounces behind, the shade launches skip deferred hit records, and max_lag extra iterations at the end serve the paths that
+// lag.  Counters: DC[2b] = deferred entries at the front of extension queue b, DC[2b+1] = at the front of the shadow queue traced by launch b.
+__global__ void k_copy2_u32(unsigned* d0, const unsigned* s0, unsigned* d1, const unsigned* s1) { *d0 = *s0; *d1 = *s1; }
+static int render_wavefront_deferred(ctl_ctx* c, const Window& W, int lane) {
+    WaveLane& L = c->lanes[lane];
+    const cudaStream_t s = lane ? c->lane_stream[lane] : c->stream;
+    const int mpl = c->max_path_length, n_iter = mpl + c->defer_max_lag;
+    const size_t n_paths = (size_t)W.n_slots * W.n_passes;
+    if (ensure_state(c, L, n_paths, s)) return 1;
+    CK(c->df_sh_rays[lane].ensure(2 * n_paths)); CK(c->df_sh_payload[lane].ensure(n_paths));
+    const size_t smem = staged_smem_bytes(c);
+    const int grid = staged_grid(c), lanes_resident = grid * c->staged_threads;
+    const int rec_lanes = c->n_lanes > 1 ? c->n_lanes : 1;
+    CK(c->ho_buf[0].ensure((size_t)lanes_resident * HO_WORDS * rec_lanes)); CK(c->ho_buf[1].ensure((size_t)lanes_resident * HO_WORDS * rec_lanes));
+    const size_t DC_LANE = 4 * (size_t)MAX_BOUNCES + 16;   // per lane: [0, 2 MAX_BOUNCES + 8): DC; then n_suspend per launch
+    CK(c->df_cnt.ensure(DC_LANE * MAX_LANES));
+    uint32_t* rec[2] = {c->ho_buf[0].p + (size_t)lane * lanes_resident * HO_WORDS, c->ho_buf[1].p + (size_t)lane * lanes_resident * HO_WORDS};
+    unsigned* DC = c->df_cnt.p + DC_LANE * lane; unsigned* NS = DC + 2 * MAX_BOUNCES + 8;
+    static size_t attr_set_dev[64] = {};
+    if (smem > attr_set_dev[c->device & 63]) { CK(cudaFuncSetAttribute(k_intersect_defer<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set_dev[c->device & 63] = smem; }
+    CK(cudaMemsetAsync(DC, 0, DC_LANE * sizeof(unsigned), s));
+    c->scene.d1 = c->d_tab1.p; c->scene.d2 = (const float2*)c->d_tab2.p; c->scene.img_w = c->w; c->scene.img_h = c->h;
+    const bool by_class = c->shade_mode == 1 && c->class_ok && c->class_mask != 0;
+    int n_classes = 0, single_cls = -1;
+    for (int k = 0; k < 4; k++) if (c->class_mask & (1u << k)) { n_classes++; single_cls = k; }
+    const bool class_sort = by_class && n_classes > 1;
+    const int g_light = grid_for(c, c->shade_blocks_per_sm);
+    const ShadeParams P = {mpl, c->rr_start, c->direct, c->stop_zero};
+    unsigned* ctr = L.counters.p;
+    CK(cudaMemsetAsync(ctr, 0, CTR_TOTAL * sizeof(unsigned), s));
+    if (class_sort) CK(cudaMemsetAsync(L.mat_hist.p, 0, 2 * MAT_CLASSES * (MAX_BOUNCES + 1) * sizeof(unsigned), s));
+    PathState st = {L.cf.p, L.cl.p, L.nor.p, L.px.p, c->stop_zero ? nullptr : L.wo_prev.p};
+    float4 *rin = L.rays_a.p, *rout = L.rays_b.p; uint32_t *pin = L.path_a.p, *pout = L.path_b.p;
+    float4* shr[2] = {L.sh_rays.p, c->df_sh_rays[lane].p}; float4* shp[2] = {L.sh_payload.p, c->df_sh_payload[lane].p};   // shadow queue of bounce b lives in buffer b & 1
+    uint32_t launches = 0;
+    k_generate<<<g_light, 256, 0, s>>>(c->scene, W, st, rin, pin, ctr + CTR_Q + 0);
+    launches++;
+    for (int b = 0; b <= n_iter; b++) {   // launch b: extension queue b (none at b == n_iter) + shadow queue b-1; the last launch finishes everything
+        const bool ext = b < n_iter, last = b == n_iter;
+        const TravOut out = {L.hit_a.p, L.hit_node.p, b > 0 ? shp[(b - 1) & 1] : nullptr, L.cl.p, nullptr, b > 0 ? shr[(b - 1) & 1] : nullptr, 0, nullptr, (class_sort && ext) ? L.mat_hist.p + 2 * MAT_CLASSES * b : nullptr};
+        Defer D;
+        D.resume = rec[(b + 1) & 1]; D.n_resume = b > 0 ? NS + (b - 1) : nullptr; D.k_ext = ext ? DC + 2 * b : nullptr; D.k_sh = b > 0 ? DC + 2 * b + 1 : nullptr;
+        D.suspend = last ? nullptr : rec[b & 1]; D.n_suspend = last ? nullptr : NS + b;
+        D.paths_in = pin; D.next_rays = rout; D.next_paths = pout; D.next_ext_ctr = ctr + CTR_Q + b + 1;
+        D.next_sh_rays = shr[b & 1]; D.next_sh_payload = shp[b & 1]; D.next_sh_ctr = ctr + CTR_SH + b;
+        D.drain_iters = c->handover_drain; D.max_lag = (b + 1 < n_iter) ? c->defer_max_lag : 0;   // (an extension ray deferred by launch b is traced by launch b + 1: the last one that takes extension rays is n_iter - 1)
+        k_intersect_defer<true><<<grid, c->staged_threads, smem, s>>>(c->scene, c->staged, c->tune, rin, ext ? ctr + CTR_Q + b : nullptr, b > 0 ? ctr + CTR_SH + b - 1 : nullptr, ctr + CTR_WORK + 2 * b, out, D);
+        launches++;
+        if (last) break;
+        // what the launch deferred sits at the front of the next queues: remember how many before the shade launches append behind them
+        k_copy2_u32<<<1, 1, 0, s>>>(DC + 2 * (b + 1), ctr + CTR_Q + b + 1, DC + 2 * (b + 1) + 1, ctr + CTR_SH + b);
+        launches++;
+        const uint32_t* order = nullptr;
+        if (class_sort) {
+            unsigned* hist = L.mat_hist.p + 2 * MAT_CLASSES * b;
+            k_class_scatter<<<g_light, 256, 0, s>>>(ctr + CTR_Q + b, L.hit_a.p, hist, hist + MAT_CLASSES, L.mat_order.p);
+            order = L.mat_order.p; launches++;
+        }
+        Queues Q = {rin, pin, rout, pout, L.hit_a.p, L.hit_node.p, shr[b & 1], shp[b & 1], nullptr, nullptr, order};
+        if (class_sort) {
+            const unsigned* hist = L.mat_hist.p + 2 * MAT_CLASSES * b;
+            for (int k = 0; k < 4; k++) if (c->class_mask & (1u << k)) { launch_shade(false, k, g_light, s, c->scene, P, st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b, hist); launches++; }
+        } else { launch_shade(false, by_class ? single_cls : -1, g_light, s, c->scene, P, st, Q, ctr + CTR_Q + b, ctr + CTR_Q + b + 1, ctr + CTR_SH + b, nullptr); launches++; }
+        std::swap(rin, rout); std::swap(pin, pout);
+    }
+    k_finish<<<g_light, 256, 0, s>>>((int)n_paths, st, c->accum, c->w, c->h);
+    k_tally<<<1, 32, 0, s>>>(ctr + CTR_Q, ctr + CTR_SH, n_iter, c->stats.p, c->stats.p + 1, 0, DC);
+    launches += 2;
+    CK(cudaGetLastError());
+    c->n_launches = launches;
+    return 0;
+}
+
 // One progressive frame (a new trace): `spp` passes on the tiles of `part`, `batch` passes fused per wavefront.  With "OverlapWavefronts" (default) the
 // frame's wavefronts alternate between two lanes -- two streams with their own wavefront buffers -- and a frame that is ONE wavefront is cut into two
 // half-batches: every traversal launch is a persistent kernel whose last rays leave most of the SMs idle (nine tails per wavefront; at 1/8 of the image
@@ -710,6 +788,25 @@ int ctl_render_frame_tiled(ctl_ctx* c, int spp, int batch, int tile_w, int tile_
                        c->n_lanes < 2 || (c->overlap == 1 ? spp == batch : (spp == batch && (batch & 1)));
     const bool ho = c->handover && spp == batch && !(batch & 1) && c->has_scene && c->direct && c->fuse_traversal && c->trav_kernel == 2 && c->staged_ok && !c->staged.tl_nodes && !c->staged.ray_tma &&
                     !c->regularization && !c->stage_timers && !c->instrumented && c->capture_bounce <= 0 && !c->variance_buffer && !c->user_tables && c->sort_mode == 0 && c->max_path_length < MAX_BOUNCES;
+    const bool df = c->defer && c->has_scene && c->direct && c->fuse_traversal && c->trav_kernel == 2 && c->staged_ok && !c->staged.tl_nodes && !c->staged.ray_tma && !c->regularization &&
+                    !c->stage_timers && !c->instrumented && c->capture_bounce <= 0 && !c->variance_buffer && !c->user_tables && c->sort_mode == 0 && c->max_path_length + c->defer_max_lag + 2 < MAX_BOUNCES;
+    if (df && plain) {   // the frame's wavefronts one after the other, each with straggler deferral between its traversal launches
+        Window W;
+        if (tiled_window(c, W, batch, tile_w, tile_h, part, n_parts)) return 1;
+        if (W.n_slots > 0) {
+            CK(cudaSetDevice(c->device));
+            CK(cudaEventRecord(c->ev_start, c->stream));
+            CK(cudaMemsetAsync(c->accum, 0, (size_t)c->w * c->h * 7 * sizeof(float), c->stream));
+            c->passes_done = 0;
+            if (generate_tables(c, 0, spp)) return 1;
+            uint32_t launches = 0;
+            for (int p = 0; p < spp; p += batch) { W.tab0 = p; if (render_wavefront_deferred(c, W, 0)) return 1; launches += c->n_launches; }
+            c->n_launches = launches;
+            CK(cudaEventRecord(c->ev_stop, c->stream));
+            c->events_recorded = true; c->passes_done = (uint32_t)spp;
+            return 0;
+        }
+    }
     if (ho) {   // a one-wavefront frame as two half-wavefronts whose traversal launches hand their unfinished rays over
         Window W;
         if (tiled_window(c, W, batch / 2, tile_w, tile_h, part, n_parts)) return 1;
@@ -761,7 +858,7 @@ int ctl_render_frame_tiled(ctl_ctx* c, int spp, int batch, int tile_w, int tile_
             CK(cudaEventRecord(c->ev_tab, c->tab_stream));
             CK(cudaStreamWaitEvent(lane ? c->lane_stream[lane] : c->stream, c->ev_tab, 0));
             W.tab0 = p;
-            if (render_window(c, 0, W, lane, true)) return 1;
+            if (df ? render_wavefront_deferred(c, W, lane) : render_window(c, 0, W, lane, true)) return 1;
             launches += c->n_launches;
         }
         c->n_launches = launches;

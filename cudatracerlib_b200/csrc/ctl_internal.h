@@ -91,6 +91,7 @@ struct ctl_ctx {
     WaveLane lanes[MAX_LANES]; DevBuf<float4> capture;
     cudaStream_t lane_stream[MAX_LANES] = {}; cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {}; cudaStream_t tab_stream = nullptr; cudaEvent_t ev_tab = nullptr;   // tab_stream: sample tables of a frame's wavefronts
     int shade_concurrent = 0; cudaStream_t cls_stream[MAX_LANES][3] = {}; cudaEvent_t ev_cls_fork[MAX_LANES] = {}, ev_cls_done[MAX_LANES][3] = {};   // "ShadeConcurrent": the per-class shade launches of a bounce on their own streams
+    int defer = 0, defer_max_lag = 3; DevBuf<float4> df_sh_rays[MAX_LANES], df_sh_payload[MAX_LANES]; DevBuf<unsigned> df_cnt;   // "DeferStragglers": second shadow-queue buffer per lane, deferral counters
     int handover = 0, handover_drain = 16; DevBuf<uint32_t> ho_buf[2]; DevBuf<unsigned> ho_cnt;   // "HandOver": one-wavefront frames as two interleaved half-wavefronts whose traversal launches hand their unfinished rays over (device/traverse_handover.cuh)
     int overlap = 1, n_lanes = 4;   // "OverlapWavefronts", "OverlapLanes": see ctl_render_frame_tiled
     DevBuf<unsigned> api_work; unsigned api_seq = 0;   // ring of work counters of the API traversal launches: calls in flight on different streams never share one

@@ -384,18 +384,18 @@ __global__ void __launch_bounds__(128, (CLS == 1 || CLS == 2) ? CTL_SHADE_MICRO_
     const int n_round = (n + 31) & ~31;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         bool alive = false, shadow = false;
-        uint32_t p = 0;
+        uint32_t p = 0, p_lag = 0;   // path id; its lag bits (frames with DeferStragglers: the path runs behind the wavefront's bounce, device/traverse_handover.cuh)
         V3 no = mk(0, 0, 0), nd = mk(0, 0, 1), sd = mk(0, 0, 1);
         float sh_tmax = 0.0f;
         Spec pending = sp(0.0f);
         if (i < n) {
             const int i_unsorted = i;
             const int i = Q.order ? (int)__ldg(Q.order + seg_start + i_unsorted) : i_unsorted; // material-sorted shading: same work items, grouped
-            p = Q.path_in[i];
+            p = Q.path_in[i]; p_lag = p & ~PATH_ID_MASK; p &= PATH_ID_MASK;
             const float4 ha = Q.hit_a[i];
             const uint32_t tri_word = __float_as_uint(ha.w);
             const uint32_t tri = tri_word & TRI_IDX_MASK;   // the staged traversal kernel leaves the material class in the top bits
-            if (tri_word != 0xffffffffu && !(REGU && (int)(__float_as_uint(st.nor[p].w) & 0xff) >= P.max_path_length)) {   // (REGU: the ray past the last vertex is traced, not shaded)
+            if (tri_word != 0xffffffffu && tri_word != TRI_DEFERRED && !(REGU && (int)(__float_as_uint(st.nor[p].w) & 0xff) >= P.max_path_length)) {   // (REGU: the ray past the last vertex is traced, not shaded)
                 const uint32_t node = Q.hit_node[i];
                 const float4 r0 = Q.rays_in[2 * i], r1 = Q.rays_in[2 * i + 1];
                 const V3 ro = mk(r0.x, r0.y, r0.z), rd = mk(r1.x, r1.y, r1.z);
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(128, (CLS == 1 || CLS == 2) ? CTL_SHADE_MICRO_
         if (alive) {
             Q.rays_out[2 * jq] = make_float4(no.x, no.y, no.z, S.ray_eps);
             Q.rays_out[2 * jq + 1] = make_float4(nd.x, nd.y, nd.z, FLT_MAX);
-            Q.path_out[jq] = p;
+            Q.path_out[jq] = p | p_lag;
             if (Q.keys_out) { const uint32_t key = ray_sort_key(S, no, nd); Q.keys_out[jq] = key; atomicAdd(Q.hist + key, 1u); }
         }
         const int ks = warp_append(shadow, n_shadow);
@@ -536,10 +536,12 @@ __global__ void __launch_bounds__(256) k_finish(int n_slots /* all passes */, Pa
 }
 
 // rays of the pass = sum of extension + shadow queue sizes (every traceRay call counts, TraceHelper.cu:176)
-__global__ void k_tally(const unsigned* q_count, const unsigned* sh_count, int n_bounces, unsigned long long* rays_last, unsigned long long* rays_total, int add_to_last = 0) {
+// (deferred: 2 * n_bounces + 2 counters of queue entries that were deferred rays re-queued by the traversal launches -- counted once, where they were first queued)
+__global__ void k_tally(const unsigned* q_count, const unsigned* sh_count, int n_bounces, unsigned long long* rays_last, unsigned long long* rays_total, int add_to_last = 0, const unsigned* deferred = nullptr) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         unsigned long long s = 0;
         for (int b = 0; b < n_bounces; b++) s += (unsigned long long)q_count[b] + (unsigned long long)sh_count[b];
+        if (deferred) for (int k = 0; k < 2 * n_bounces + 2; k++) s -= (unsigned long long)deferred[k];
         *rays_last = add_to_last ? *rays_last + s : s; atomicAdd(rays_total, s);   // two wavefronts of a frame may tally concurrently (OverlapWavefronts)
     }
 }

@@ -310,7 +310,8 @@ int      ctl_resize(ctl_ctx*, int width, int height);    /* == Tracer<true>::Res
  *    frames (ctl_render_frame_tiled / ctl_comm_render_frame): "OverlapWavefronts" (0 / 1 [default: wavefronts of a frame on several streams when the frame has
  *    several] / 2 [also cut the batches of a one-wavefront frame]), "OverlapLanes" (1..8, default 4), "HandOver" (0 [default] / 1: a one-wavefront frame as two
  *    interleaved half-wavefronts whose traversal launches hand their unfinished rays over instead of draining; measured: correct, not faster -- DESIGN.md
- *    section 5), "HandOverDrain" (loop iterations a warp keeps going after the queue ran dry, default 16), "ShadeConcurrent" (0 [default] / 1: the per-class
+ *    section 5), "HandOverDrain" (loop iterations a warp keeps going after the queue ran dry, default 16), "DeferStragglers" (0 [default] / 1: traversal launches move their unfinished rays into the
+ *    wavefront's next launch, the paths lag up to "DeferMaxLag" = 1..3 bounces; measured: +2 % at 1/8 of the image, -2 % on the whole image), "ShadeConcurrent" (0 [default] / 1: the per-class
  *    shade launches of a bounce on their own streams; measured: -2 % on configs[2], a loss with lanes). */
 int ctl_set_param_i(ctl_ctx*, const char* key, int value);   /* == TracerParameterCollection::setValue<int> (Kernel/TracerSettings.h:277-283) */
 int ctl_get_param_i(ctl_ctx*, const char* key, int* value);  /* == getValue<int> (Kernel/TracerSettings.h:266-272) */
