@@ -50,4 +50,11 @@ for alg, growth in ((1, 0.0), (1, 3.0), (0, 3.0), (2, 1.0)):
     assert L.ctl_bvh_build_gpu_split(0, verts.ctypes.data, n, alg, 0, growth, cap, nodes.ctypes.data, C.byref(nn), woop.ctypes.data, index.ctypes.data, C.byref(ns), None) == 0
 s4 = Scene("soup", 96, 64); s4.setRebraid(64); s4.rebuildBVHOnGPU(); s4.validate()
 t = PathTracer(96, 64); t.InitializeScene(s4); t.DoPasses(2, new_trace=True); t.synchronize(); t.close()
+# ray hand-over between half-wavefronts, straggler deferral with lagging paths, WavefrontPathTracer frames on lanes, Regularization
+t = PathTracer(128, 72); t.InitializeScene(s3); t.setParameter("MaxPathLength", 6)
+t.setParameter("HandOver", 1); t.setParameter("HandOverDrain", 1); t.DoFrame(4, 4); t.setParameter("HandOver", 0)
+t.setParameter("DeferStragglers", 1); t.DoFrame(4, 4); t.setParameter("DeferMaxLag", 1); t.DoFrame(8, 2); t.setParameter("DeferStragglers", 0)
+t.setParameter("Regularization", 1); t.DoPasses(2, new_trace=True); t.setParameter("Regularization", 0); t.setParameter("ShadeConcurrent", 1); t.DoPasses(2, new_trace=True)
+t.synchronize(); t.close()
+w = WavefrontPathTracer(96, 64); w.InitializeScene(s); w.setParameter("MaxPathLength", 5); w.DoFrame(6); w.synchronize(); w.close()
 print("round-2 all ok")
