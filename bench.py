@@ -282,14 +282,43 @@ def measure_workload(name, args, torch, dist, world, rank, local, dev, stream, s
         dist.broadcast_object_list(box, src=0)
         tracer.commInitRank(box[0], rank, world)
 
-    def frame(read_back):
-        # spp passes on this rank's tiles + (N > 1) the one NCCL reduce of the accumulator to rank 0, all on `stream`: ctl_comm_render_frame
-        tracer.commRenderFrame(spp, batch, tile, 0)
-        if read_back and rank == 0:
+    # Frames in flight: a frame that is ONE wavefront (spp == batch) cannot hide the drain of its own persistent traversal launches, the next frame's launches can
+    # (ctl_comm_submit_frame / ctl_acquire_frame: every frame on a lane of its own -- stream, wavefront buffers, accumulator, sample tables -- its reduce on the
+    # communication stream; frames are handed back in order).  Frames of several wavefronts (configs[4]) overlap their own wavefronts instead (ctl_comm_render_frame).
+    fif = max(1, min(7, args.frames_in_flight)) if spp == batch else 1
+    tracer.setParameter("FramesInFlight", fif)
+
+    def read_back_frame():
+        if rank == 0:
             # what an application reads per frame: the image after the (default) image pipeline, as in the reference's
             # applyImagePipeline -> RGBCOL (Kernel/ImagePipeline/ImagePipeline.cu:54-63); PixelData stays on the device
             tracer.resolveSRGB8Device(d_rgba.data_ptr())
             host_rgba.copy_(d_rgba, non_blocking=True)
+
+    def frame(read_back):
+        # spp passes on this rank's tiles + (N > 1) the one NCCL reduce of the accumulator to rank 0, all on `stream`: ctl_comm_render_frame
+        tracer.commRenderFrame(spp, batch, tile, 0)
+        if read_back:
+            read_back_frame()
+
+    def frames(n, read_back, flush_l2):
+        """n steps.  fif == 1: one after the other; else as a pipeline with `fif` frames in flight -- every step submits one frame and (once the pipeline is full)
+        acquires the oldest one (and reads it back); the pipeline is drained before returning, so all n frames are complete inside the caller's bracket."""
+        for i in range(n):
+            if flush_l2:
+                flush.zero_()   # L2 flush between timed iterations (on `stream`; lanes fork from it)
+            if fif == 1:
+                frame(read_back)
+                continue
+            tracer.commSubmitFrame(spp, batch, tile, 0)
+            if i >= fif - 1:
+                tracer.acquireFrame()
+                if read_back:
+                    read_back_frame()
+        while fif > 1 and tracer.framesInFlight():
+            tracer.acquireFrame()
+            if read_back:
+                read_back_frame()
 
     def sync_all():
         torch.cuda.synchronize()
@@ -301,22 +330,25 @@ def measure_workload(name, args, torch, dist, world, rank, local, dev, stream, s
     if primary:
         clocks.start()   # before the warm-up: short timed regions (8 GPUs) still collect samples under load
     # ---- warm-up
-    rays_per_frame_local = 0
-    for _ in range(warmup):
-        r0 = tracer.getTotalRays()
-        frame(False)
-        rays_per_frame_local = tracer.getTotalRays() - r0  # frames are identical (new_trace restarts the sample stream)
+    r0 = tracer.getTotalRays()
+    frames(warmup, False, False)
+    rays_per_frame_local = (tracer.getTotalRays() - r0) // max(1, warmup)  # frames are identical (a new trace restarts the sample stream)
     sync_all()
 
     # ---- device-timed steps (value)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps if fif == 1 else 1)]
     sync_all()
     t_wall0 = time.perf_counter()
-    for i in range(steps):
-        flush.zero_()  # L2 flush between timed iterations, outside the event bracket
-        ev[i][0].record(stream)
-        frame(False)
-        ev[i][1].record(stream)
+    if fif == 1:
+        for i in range(steps):
+            flush.zero_()  # L2 flush between timed iterations, outside the event bracket
+            ev[i][0].record(stream)
+            frame(False)
+            ev[i][1].record(stream)
+    else:   # the pipeline: ONE event bracket over exactly `steps` frames, fill and drain (and the L2 flushes) inside it
+        ev[0][0].record(stream)
+        frames(steps, False, True)
+        ev[0][1].record(stream)
     sync_all()
     t_wall = time.perf_counter() - t_wall0
     clk = clocks.stop() if primary else None
@@ -335,11 +367,10 @@ def measure_workload(name, args, torch, dist, world, rank, local, dev, stream, s
     # ---- end-to-end steps through the public API with host buffers
     e2e_steps = max(2, min(steps, 10))
     tracer.setParameter("DeviceSampleTables", 0)   # e2e: the step's inputs (the pass sample tables) come from the host, like the reference's UpdateKernel
-    frame(True)
+    frames(1, True, False)
     sync_all()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        frame(True)
+    frames(e2e_steps, True, False)
     sync_all()
     e2e_s = time.perf_counter() - t0
     tracer.setParameter("DeviceSampleTables", 1)
@@ -416,11 +447,14 @@ def measure_workload(name, args, torch, dist, world, rank, local, dev, stream, s
             "metric": baseline_metric(), "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": static_config(name, scene, world, tile),
-            "rays_per_step": rays_frame, "passes_per_wavefront": batch, "wavefront_lanes": (tracer.getParameter("OverlapLanes") if tracer.getParameter("OverlapWavefronts") and spp > batch else 1),
+            "rays_per_step": rays_frame, "frames_in_flight": fif,
+            "timing": ("CUDA events on the launching stream around each step, summed" if fif == 1 else
+                       f"one CUDA-event bracket on the launching stream over all {steps} steps: the steps run as a pipeline of {fif} frames in flight (fill and drain inside the bracket); ms_per_step = bracket / steps"),
+            "passes_per_wavefront": batch, "wavefront_lanes": (tracer.getParameter("OverlapLanes") if tracer.getParameter("OverlapWavefronts") and spp > batch else 1),
             "scene_level": {"leaves": int(scene.view.n_nodes), "re_braided": bool(scene.view.node_alias)},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": spp * table_bytes, "d2h_bytes_per_step": h * w * 4,
-                    "steps": e2e_steps, "note": "wall clock; DeviceSampleTables=0: sample tables generated by the host XORWOW twin and copied H2D from pinned memory for every pass, the frame resolved by ctl_resolve_srgb8 (default image pipeline) and the RGBA8 image copied D2H to pinned memory every step"},
+                    "steps": e2e_steps, "note": "wall clock, the same pipeline of frames in flight as `value`; DeviceSampleTables=0: sample tables generated by the host XORWOW twin and copied H2D from pinned memory for every pass, the frame resolved by ctl_resolve_srgb8 (default image pipeline) and the RGBA8 image copied D2H to pinned memory every step"},
             "gpu_launches": int((launches_per_batch + 1) * (spp // batch) * steps),
             "wall_s_timed_region": t_wall, "image_mean_srgb8": img_mean, "roofline": roof,
         }
@@ -447,6 +481,7 @@ def main():
     ap.add_argument("--sort-mode", type=int, default=None)
     ap.add_argument("--set", action="append", default=[], metavar="KEY=INT", help="extra tracer parameter (ctl_set_param_i), for A/B runs")
     ap.add_argument("--tile", type=int, default=0, help="tile edge for the multi-GPU partition (0 = package default)")
+    ap.add_argument("--frames-in-flight", type=int, default=3, help="one-wavefront frames (spp == batch): steps in flight at once (1 = every step finishes before the next starts)")
     ap.add_argument("--batch", type=int, default=0, help="progressive passes fused into one wavefront (must divide spp; 0 = 8, or 16 for frames of >= 32 passes)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -481,7 +516,7 @@ def main():
         extra = {}
         for name, st in (("c2", 5), ("c3", 5), ("c5", 2)):
             x = measure_workload(name, args, torch, dist, world, rank, local, dev, stream, st, 3, False)
-            extra[name] = {k: x[k] for k in ("value", "unit", "steps", "warmup", "ms_per_step", "config", "rays_per_step", "scene_level", "e2e", "roofline", "image_mean_srgb8")}
+            extra[name] = {k: x[k] for k in ("value", "unit", "steps", "warmup", "ms_per_step", "config", "rays_per_step", "frames_in_flight", "scene_level", "e2e", "roofline", "image_mean_srgb8")}
         line["extra"] = {"configs": extra}
     if rank == 0:
         print(json.dumps(line))

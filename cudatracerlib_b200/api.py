@@ -148,6 +148,8 @@ def lib():
     L.ctl_render_pass_tiled.argtypes = [vp, i32, i32, i32, i32, i32]
     L.ctl_render_passes_tiled.argtypes = [vp, i32, i32, i32, i32, i32, i32]
     L.ctl_render_frame_tiled.argtypes = [vp, i32, i32, i32, i32, i32, i32]
+    L.ctl_submit_frame_tiled.argtypes = [vp, i32, i32, i32, i32, i32, i32]; L.ctl_acquire_frame.argtypes = [vp]; L.ctl_frames_in_flight.argtypes = [vp]
+    L.ctl_comm_submit_frame.argtypes = [vp, i32, i32, i32, i32]; L.ctl_comm_submit_frame_all.argtypes = [vp, i32, i32, i32, i32, i32]
     L.ctl_wavefront_pass.argtypes = [vp, i32]
     L.ctl_wavefront_frame.argtypes = [vp, i32]
     L.ctl_read_sample_tables.argtypes = [vp, i32, vp, vp]
@@ -498,6 +500,26 @@ class PathTracer:
     def commRenderFrame(self, spp, batch=8, tile=64, root=0):
         """ctl_comm_render_frame: this rank's tiles of a frame + the reduce to `root` (asynchronous)."""
         _check(lib().ctl_comm_render_frame(self._ctx, spp, batch, tile, root))
+
+    # -- frames in flight (ctl_submit_frame_tiled / ctl_acquire_frame): a sequence of frames as a pipeline
+    def submitFrame(self, spp, batch=8, tile=(64, 64), part=0, n_parts=1):
+        """One more frame on a lane of its own (asynchronous); up to "FramesInFlight" may be outstanding."""
+        _check(lib().ctl_submit_frame_tiled(self._ctx, spp, batch, tile[0], tile[1], part, n_parts))
+
+    def acquireFrame(self):
+        """The context's stream waits for the oldest outstanding frame; its accumulator becomes the context's (resolve / read-back calls see it)."""
+        _check(lib().ctl_acquire_frame(self._ctx))
+
+    def framesInFlight(self):
+        return lib().ctl_frames_in_flight(self._ctx)
+
+    def commSubmitFrame(self, spp, batch=8, tile=64, root=0):
+        """ctl_comm_submit_frame: this rank's tiles of one more frame; its reduce to `root` runs on the communication stream."""
+        _check(lib().ctl_comm_submit_frame(self._ctx, spp, batch, tile, root))
+
+    @staticmethod
+    def commSubmitFrameAll(tracers, spp, batch=8, tile=64, root=0):
+        arr = (C.c_void_p * len(tracers))(*[t._ctx for t in tracers]); _check(lib().ctl_comm_submit_frame_all(arr, len(tracers), spp, batch, tile, root))
 
     def commAllReduce(self, values):
         a = np.ascontiguousarray(values, np.uint64); _check(lib().ctl_comm_allreduce_u64(self._ctx, _ptr(a), len(a))); return a

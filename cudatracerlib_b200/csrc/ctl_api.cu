@@ -65,6 +65,16 @@ static void launch_intersect(const ctl_ctx* c, int grid, cudaStream_t st, const 
 extern "C" {
 
 // ------------------------------------------------------------------ context
+static void release_frame_slots(ctl_ctx* c) {   // (every stream idle) the accumulators / table state of the frames-in-flight slots
+    for (FrameSlot& F : c->fslot) {
+        F.accum.release(); F.states.release();
+        if (F.h1) cudaFreeHost(F.h1); if (F.h2) cudaFreeHost(F.h2); F.h1 = F.h2 = nullptr; F.h_cap = 0;
+        for (cudaEvent_t* e : {&F.begin, &F.done, &F.ready, &F.h_free}) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
+    }
+    for (int k = 0; k < MAX_LANES; k++) c->lane_accum[k] = nullptr;
+    c->f_submitted = c->f_acquired = 0;
+}
+
 static int alloc_image(ctl_ctx* c) {
     CK(c->own_accum.ensure((size_t)c->w * c->h * 7));
     c->accum = c->own_accum.p;
@@ -117,6 +127,8 @@ void ctl_destroy(ctl_ctx* c) {
     if (c->tab_stream) { cudaStreamSynchronize(c->tab_stream); cudaStreamDestroy(c->tab_stream); } if (c->ev_tab) cudaEventDestroy(c->ev_tab);
     for (int k = 1; k < MAX_LANES; k++) { if (c->lane_stream[k]) { cudaStreamSynchronize(c->lane_stream[k]); cudaStreamDestroy(c->lane_stream[k]); } if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->comm_stream) { cudaStreamSynchronize(c->comm_stream); cudaStreamDestroy(c->comm_stream); }
+    release_frame_slots(c);
     for (int k = 0; k < MAX_LANES; k++) c->lanes[k].release();
     c->ho_buf[0].release(); c->ho_buf[1].release(); c->ho_cnt.release(); c->df_cnt.release();
     for (int k = 0; k < MAX_LANES; k++) { c->df_sh_rays[k].release(); c->df_sh_payload[k].release(); }
@@ -133,6 +145,9 @@ int ctl_resize(ctl_ctx* c, int width, int height) {
     if (!c || width <= 0 || height <= 0) return set_err("invalid argument");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
+    if (c->f_submitted != c->f_acquired) return set_err("ctl_resize: frames are in flight (ctl_acquire_frame them first)");
+    for (int k = 1; k < MAX_LANES; k++) if (c->lane_stream[k]) CK(cudaStreamSynchronize(c->lane_stream[k]));
+    release_frame_slots(c);
     c->w = width; c->h = height; c->scene.img_w = width; c->scene.img_h = height;
     c->passes_done = 0;
     c->nlm_pixels = 0; c->nlm_last_update = -1;   // NonLocalMeansFilter::Resize (NonLocalMeansFilter.h:131-137)
@@ -160,6 +175,11 @@ int ctl_set_param_i(ctl_ctx* c, const char* key, int v) {
     else if (k == "HandOver") c->handover = v != 0;   // ctl_render_frame_tiled: one-wavefront frames as two half-wavefronts with ray hand-over between their launches
     else if (k == "HandOverDrain") { if (v < 1 || v > 4096) return set_err("HandOverDrain out of range [1,4096]"); c->handover_drain = v; }
     else if (k == "OverlapLanes") { if (v < 1 || v > MAX_LANES) return set_err("OverlapLanes out of range [1,8]"); c->n_lanes = v; }   // wavefronts of a frame in flight at once   // ctl_render_frame_tiled / ctl_comm_render_frame: the frame's wavefronts alternate between two streams
+    else if (k == "FramesInFlight") {   // ctl_submit_frame_tiled / ctl_acquire_frame: how many frames may be outstanding
+        if (v < 1 || v > MAX_LANES - 1) return set_err("FramesInFlight out of range [1,7]");
+        if (c->f_submitted != c->f_acquired) return set_err("FramesInFlight cannot change while frames are in flight");
+        c->fif = v; c->f_submitted = c->f_acquired = 0;
+    }
     else if (k == "PixelVarianceBuffer") c->variance_buffer = v != 0;
     else if (k == "WarpPixelBlocks") c->warp_blocks = v != 0;
     else if (k == "PassStride") { if (v < 1) return set_err("PassStride must be >= 1"); c->pass_stride = v; }   // multi-GPU by pass: this context renders passes PassPhase + k * PassStride
@@ -190,7 +210,7 @@ int ctl_get_param_i(ctl_ctx* c, const char* key, int* v) {
     std::string k(key);
     if (k == "MaxPathLength") *v = c->max_path_length; else if (k == "RRStartDepth") *v = c->rr_start; else if (k == "Direct") *v = c->direct;
     else if (k == "StopZeroThroughput") *v = c->stop_zero; else if (k == "Regularization") *v = c->regularization; else if (k == "SortMode") *v = c->sort_mode; else if (k == "StageTimers") *v = c->stage_timers;
-    else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables; else if (k == "FuseTraversal") *v = c->fuse_traversal; else if (k == "OverlapWavefronts") *v = c->overlap; else if (k == "OverlapLanes") *v = c->n_lanes; else if (k == "HandOver") *v = c->handover; else if (k == "DeferStragglers") *v = c->defer; else if (k == "DeferMaxLag") *v = c->defer_max_lag; else if (k == "ShadeConcurrent") *v = c->shade_concurrent; else if (k == "HandOverDrain") *v = c->handover_drain; else if (k == "PixelVarianceBuffer") *v = c->variance_buffer; else if (k == "PassStride") *v = c->pass_stride; else if (k == "PassPhase") *v = c->pass_phase;
+    else if (k == "CaptureBounce") *v = c->capture_bounce; else if (k == "TraversalKernel") *v = c->trav_kernel; else if (k == "DeviceSampleTables") *v = c->device_tables; else if (k == "FuseTraversal") *v = c->fuse_traversal; else if (k == "OverlapWavefronts") *v = c->overlap; else if (k == "OverlapLanes") *v = c->n_lanes; else if (k == "HandOver") *v = c->handover; else if (k == "DeferStragglers") *v = c->defer; else if (k == "DeferMaxLag") *v = c->defer_max_lag; else if (k == "ShadeConcurrent") *v = c->shade_concurrent; else if (k == "HandOverDrain") *v = c->handover_drain; else if (k == "PixelVarianceBuffer") *v = c->variance_buffer; else if (k == "PassStride") *v = c->pass_stride; else if (k == "PassPhase") *v = c->pass_phase; else if (k == "FramesInFlight") *v = c->fif;
     else if (k == "TraversalBlocksPerSM") *v = c->trav_blocks_per_sm; else if (k == "StagedThreads") *v = c->staged_threads; else if (k == "StagedStackRows") *v = c->staged_rows;
     else if (k == "ShadeMode") *v = c->shade_mode; else if (k == "MaterialClassMask") *v = (int)c->class_mask;
     else if (k == "StagedRayTMA") *v = c->staged.ray_tma;
@@ -444,6 +464,7 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W, int lane = 
     WaveLane& L = c->lanes[lane];
     const cudaStream_t s = lane ? c->lane_stream[lane] : c->stream;
     if (!c->has_scene) return set_err("no scene uploaded");
+    if (!framed && c->f_submitted != c->f_acquired) return set_err("frames are in flight (ctl_submit_frame_tiled): ctl_acquire_frame them before other render calls");
     if (c->variance_buffer && (W.n_passes != 1 || W.mode != 0 || W.n_slots != c->w * c->h))
         return set_err("PixelVarianceBuffer=1 needs whole-image single-pass renders (ctl_render_pass with the full window, ctl_wavefront_pass)");
     if (W.n_slots <= 0) return 0;
@@ -563,7 +584,7 @@ static int render_window(ctl_ctx* c, int new_trace, const Window& W, int lane = 
         std::swap(rin, rout); std::swap(pin, pout);
     }
     stage_mark(c, 4);
-    k_finish<<<g_light, 256, 0, s>>>((int)n_paths, st, c->accum, c->w, c->h);
+    k_finish<<<g_light, 256, 0, s>>>((int)n_paths, st, c->lane_accum[lane] ? c->lane_accum[lane] : c->accum, c->w, c->h);   // (lane_accum: a frame in flight owns its accumulator)
     k_tally<<<1, 32, 0, s>>>(ctr + CTR_Q, ctr + CTR_SH, n_iter, c->stats.p, c->stats.p + 1);
     launches += 2;
     stage_mark(c, 5);
@@ -782,6 +803,7 @@ static int render_wavefront_deferred(ctl_ctx* c, const Window& W, int lane) {
 int ctl_render_frame_tiled(ctl_ctx* c, int spp, int batch, int tile_w, int tile_h, int part, int n_parts) {
     if (!c) return set_err("null context");
     if (spp < 1 || batch < 1 || spp % batch) return set_err("spp must be a positive multiple of batch");
+    if (c->f_submitted != c->f_acquired) return set_err("frames are in flight (ctl_submit_frame_tiled): ctl_acquire_frame them before other render calls");
     // "OverlapWavefronts": 0 = never; 1 (default) = when the frame has several wavefronts anyway (spp > batch: the lanes come for free); 2 = also cut the batches
     // of a frame with fewer wavefronts than lanes (measured: what the overlap gains, the extra launches lose)
     const bool plain = !c->overlap || c->stage_timers || c->instrumented || c->capture_bounce > 0 || c->variance_buffer || c->user_tables || c->sort_mode != 0 || spp > 128 ||
@@ -869,6 +891,98 @@ int ctl_render_frame_tiled(ctl_ctx* c, int spp, int batch, int tile_w, int tile_
     c->passes_done = (uint32_t)spp;
     return 0;
 }
+
+// ------------------------------------------------------------------ frames in flight
+// A renderer that produces a SEQUENCE of frames (animation, interactive progressive display, a render farm's queue) does not have to finish frame k before
+// frame k+1 starts: the frames are independent.  ctl_submit_frame_tiled enqueues a whole frame -- accumulator clear, sample tables, every wavefront, and the
+// reduce when there is a communicator -- on wavefront lane 1 + k % FramesInFlight (its own stream, wavefront buffers, accumulator, table sets and generator
+// state); ctl_acquire_frame makes the context's stream wait for the OLDEST outstanding frame and makes its accumulator the context's.  Why: every traversal
+// launch is a persistent kernel that ends with a drain (the scene's longest rays, ~0.45 ms whatever the launch size: DESIGN.md section 5); a frame that is
+// one wavefront cannot hide its own drains (cutting it in two doubles the launches), but the NEXT frame's launches fill them -- the launches per frame stay
+// the same.  Same paths, same images as ctl_render_frame_tiled (only the order of the float atomics differs, as between any two runs).
+static int frame_tables(ctl_ctx* c, FrameSlot& F, int set0, int spp, cudaStream_t st) {
+    float* d1 = c->d_tab1.p + TAB1 * set0; float* d2 = c->d_tab2.p + TAB2 * set0;
+    if (c->device_tables) {   // a new trace: passes 0 .. spp-1 from the generator's start states, on this slot's own copy of the state
+        CK(F.states.ensure((size_t)ctlb::kNumSeq * 6));
+        CK(cudaMemcpyAsync(F.states.p, c->d_states0.p, (size_t)ctlb::kNumSeq * 6 * 4, cudaMemcpyDeviceToDevice, st));
+        k_gen_tables<<<ctlb::kNumSeq / 128, 128, 0, st>>>(F.states.p, c->d_jump.p, spp, d1, (float2*)d2);
+        CK(cudaGetLastError());
+    } else {                  // the reference's UpdateKernel behaviour: host XORWOW, pinned sets of this slot, H2D on the lane's stream
+        if (F.h_cap < spp) {
+            if (F.h_free) CK(cudaEventSynchronize(F.h_free));
+            if (F.h1) cudaFreeHost(F.h1); if (F.h2) cudaFreeHost(F.h2); F.h1 = F.h2 = nullptr; F.h_cap = 0;
+            CK(cudaMallocHost((void**)&F.h1, TAB1 * 4 * spp)); CK(cudaMallocHost((void**)&F.h2, TAB2 * 4 * spp));
+            F.h_cap = spp;
+        }
+        CK(cudaEventSynchronize(F.h_free));   // the copies of the frame that used this slot last have left the pinned sets
+        c->gen.reset();
+        for (int p = 0; p < spp; p++) c->gen.next_pass(F.h1 + TAB1 * p, F.h2 + TAB2 * p);
+        c->gen_pos_host = (uint32_t)spp;
+        CK(cudaMemcpyAsync(d1, F.h1, TAB1 * 4 * spp, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d2, F.h2, TAB2 * 4 * spp, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(F.h_free, st));
+    }
+    return 0;
+}
+
+int ctl_submit_frame_tiled(ctl_ctx* c, int spp, int batch, int tile_w, int tile_h, int part, int n_parts) {
+    if (!c) return set_err("null context");
+    if (spp < 1 || batch < 1 || spp % batch || spp > 128) return set_err("spp must be a positive multiple of batch (<= 128)");
+    if (!c->has_scene) return set_err("no scene uploaded");
+    if (c->stage_timers || c->instrumented || c->capture_bounce > 0 || c->variance_buffer || c->user_tables || c->sort_mode != 0)
+        return set_err("ctl_submit_frame_tiled: StageTimers / instrumentation / CaptureBounce / PixelVarianceBuffer / caller-supplied tables / SortMode need ctl_render_frame_tiled");
+    if (c->f_submitted - c->f_acquired >= (unsigned long long)c->fif) return set_err("FramesInFlight frames are outstanding: ctl_acquire_frame first");
+    Window W;
+    if (tiled_window(c, W, batch, tile_w, tile_h, part, n_parts)) return 1;
+    CK(cudaSetDevice(c->device));
+    const int slot = (int)(c->f_submitted % (unsigned long long)c->fif), lane = slot + 1;
+    FrameSlot& F = c->fslot[slot];
+    if (!c->ev_fork) CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    if (!c->lane_stream[lane]) { CK(cudaStreamCreateWithFlags(&c->lane_stream[lane], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->ev_join[lane], cudaEventDisableTiming)); }
+    if (!F.begin) { CK(cudaEventCreate(&F.begin)); CK(cudaEventCreate(&F.done)); CK(cudaEventCreateWithFlags(&F.ready, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&F.h_free, cudaEventDisableTiming)); }
+    const cudaStream_t s = c->lane_stream[lane];
+    if (c->fif * spp > c->tab_cap) {   // the table sets of every slot: grown only while no lane reads them
+        for (int k = 1; k < MAX_LANES; k++) if (c->lane_stream[k]) CK(cudaStreamSynchronize(c->lane_stream[k]));
+        if (ensure_tables(c, c->fif * spp)) return 1;
+    }
+    CK(F.accum.ensure((size_t)c->w * c->h * 7));
+    // the lane starts after what the context's stream holds so far (the consumer of the frame that used this slot last, scene updates, ...)
+    CK(cudaEventRecord(c->ev_fork, c->stream));
+    CK(cudaStreamWaitEvent(s, c->ev_fork, 0));
+    CK(cudaEventRecord(F.begin, s));
+    CK(cudaMemsetAsync(F.accum.p, 0, (size_t)c->w * c->h * 7 * sizeof(float), s));
+    c->lane_accum[lane] = F.accum.p;
+    F.launches = 0; F.spp = (uint32_t)spp;
+    if (W.n_slots > 0) {
+        if (frame_tables(c, F, slot * spp, spp, s)) return 1;
+        for (int p = 0; p < spp; p += batch) {
+            W.tab0 = slot * spp + p;
+            if (render_window(c, 0, W, lane, true)) { c->lane_accum[lane] = nullptr; return 1; }
+            F.launches += c->n_launches;
+        }
+    }
+    c->lane_accum[lane] = nullptr;   // (read at launch time only: the lanes of ctl_render_frame_tiled share the context's accumulator again)
+    CK(cudaEventRecord(F.done, s));
+    F.reduced = false;
+    if (ctl_comm_reduce_slot(c, F)) return 1;   // with a communicator: ncclReduce of this frame's accumulator on the communication stream, after F.done
+    c->f_submitted++;
+    return 0;
+}
+
+int ctl_acquire_frame(ctl_ctx* c) {
+    if (!c) return set_err("null context");
+    if (c->f_acquired == c->f_submitted) return set_err("ctl_acquire_frame: no frame in flight");
+    CK(cudaSetDevice(c->device));
+    FrameSlot& F = c->fslot[(int)(c->f_acquired % (unsigned long long)c->fif)];
+    CK(cudaStreamWaitEvent(c->stream, F.reduced ? F.ready : F.done, 0));
+    c->accum = F.accum.p;                                                  // resolve / image pipeline / read-back calls now see this frame
+    std::swap(c->ev_start, F.begin); std::swap(c->ev_stop, F.done);        // ctl_stats: device time of this frame on its lane (its wait on F.done is already enqueued)
+    c->events_recorded = true; c->n_launches = F.launches; c->passes_done = F.spp;
+    c->f_acquired++;
+    return 0;
+}
+
+int ctl_frames_in_flight(ctl_ctx* c) { return c ? (int)(c->f_submitted - c->f_acquired) : 0; }
 
 int ctl_render_pass_tiled(ctl_ctx* c, int new_trace, int tile_w, int tile_h, int part, int n_parts) {
     return ctl_render_passes_tiled(c, new_trace, 1, tile_w, tile_h, part, n_parts);
@@ -970,6 +1084,7 @@ static int wavefront_pass_on(ctl_ctx* c, int new_trace, int lane, cudaStream_t s
 int ctl_wavefront_pass(ctl_ctx* c, int new_trace) {
     if (!c) return set_err("null context");
     if (!c->has_scene) return set_err("no scene uploaded");
+    if (c->f_submitted != c->f_acquired) return set_err("frames are in flight (ctl_submit_frame_tiled): ctl_acquire_frame them before other render calls");
     CK(cudaSetDevice(c->device));
     const uint32_t pass_index = (uint32_t)c->pass_phase + (uint32_t)c->pass_stride * (new_trace ? 0u : c->passes_done);   // which pass of the (possibly shared) frame this is
     return wavefront_pass_on(c, new_trace, 0, c->stream, pass_index, 0, false);
@@ -981,6 +1096,7 @@ int ctl_wavefront_pass(ctl_ctx* c, int new_trace) {
 int ctl_wavefront_frame(ctl_ctx* c, int spp) {
     if (!c) return set_err("null context");
     if (!c->has_scene) return set_err("no scene uploaded");
+    if (c->f_submitted != c->f_acquired) return set_err("frames are in flight (ctl_submit_frame_tiled): ctl_acquire_frame them before other render calls");
     if (spp < 1 || spp > 4096) return set_err("spp out of range [1,4096]");
     CK(cudaSetDevice(c->device));
     const int n_lanes = c->n_lanes < spp ? c->n_lanes : spp;

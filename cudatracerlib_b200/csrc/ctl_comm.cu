@@ -55,6 +55,28 @@ void ctl_comm_release(ctl_ctx* c) {
     c->comm_scratch = nullptr;
 }
 
+// The reduce of a frame in flight: after the frame's last kernel (F.done), on the communication stream -- a stream of its own (highest priority) so that
+// neither the lane that rendered the frame nor the context's stream waits for the other ranks; F.ready marks the accumulator final.
+static int reduce_enqueue(ctl_ctx* c, FrameSlot& F) {
+    NEED_NCCL();
+    CK(cudaSetDevice(c->device));
+    if (!c->comm_stream) { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CK(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi)); }
+    CK(cudaStreamWaitEvent(c->comm_stream, F.done, 0));
+    NK("ncclReduce", N->Reduce(F.accum.p, F.accum.p, (size_t)c->w * c->h * 7, NCCL_FLOAT32, NCCL_SUM, c->frame_root, c->comm, c->comm_stream));
+    return 0;
+}
+static int reduce_mark(ctl_ctx* c, FrameSlot& F) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(F.ready, c->comm_stream));
+    F.reduced = true;
+    return 0;
+}
+int ctl_comm_reduce_slot(ctl_ctx* c, FrameSlot& F) {
+    if (!c->comm) { if (c->comm_size != 1) return ctl_set_err("no communicator: ctl_comm_init_rank / ctl_comm_init_all first"); return 0; }
+    if (c->comm_defer) { c->comm_pending = &F; return 0; }   // ctl_comm_submit_frame_all: one process, several devices -> the reduces are grouped by the caller
+    return reduce_enqueue(c, F) || reduce_mark(c, F);
+}
+
 extern "C" {
 
 int ctl_comm_get_unique_id(void* id_out) {
@@ -145,6 +167,37 @@ int ctl_comm_render_frame(ctl_ctx* c, int spp, int batch, int tile, int root) {
     if (tile <= 0) tile = 64;
     if (ctl_render_frame_tiled(c, spp, batch, tile, tile, c->comm_rank, c->comm_size)) return 1;
     return ctl_comm_reduce_accum(c, root);
+}
+
+// Frames in flight across the ranks: ctl_submit_frame_tiled on this rank's tiles; the reduce of every frame runs on the context's communication stream
+// (ctl_comm_reduce_slot), in submission order on every rank, while the lanes render the next frames.  ctl_acquire_frame returns them in order; on the
+// root the acquired accumulator holds the whole image.
+int ctl_comm_submit_frame(ctl_ctx* c, int spp, int batch, int tile, int root) {
+    if (!c) return ctl_set_err("null context");
+    if (tile <= 0) tile = 64;
+    if (root < 0 || root >= c->comm_size) return ctl_set_err("root out of range");
+    c->frame_root = root;
+    return ctl_submit_frame_tiled(c, spp, batch, tile, tile, c->comm_rank, c->comm_size);
+}
+
+int ctl_comm_submit_frame_all(ctl_ctx* const* ctxs, int n, int spp, int batch, int tile, int root) {   // the same for ctl_comm_init_all communicators
+    if (!ctxs || n < 1) return ctl_set_err("null / empty argument");
+    int rc = 0;
+    for (int i = 0; i < n && !rc; i++) {
+        if (!ctxs[i]) return ctl_set_err("null context");
+        ctxs[i]->comm_defer = true; ctxs[i]->comm_pending = nullptr;
+        rc = ctl_comm_submit_frame(ctxs[i], spp, batch, tile, root);
+        ctxs[i]->comm_defer = false;
+    }
+    if (rc || n == 1 || !ctxs[0]->comm) return rc;
+    NEED_NCCL();
+    NK("ncclGroupStart", N->GroupStart());
+    for (int i = 0; i < n && !rc; i++) rc = ctxs[i]->comm_pending ? reduce_enqueue(ctxs[i], *ctxs[i]->comm_pending) : ctl_set_err("ctl_comm_submit_frame_all: context without a communicator");
+    const int rg = N->GroupEnd();
+    if (rc) return rc;
+    NK("ncclGroupEnd", rg);
+    for (int i = 0; i < n && !rc; i++) { rc = reduce_mark(ctxs[i], *ctxs[i]->comm_pending); ctxs[i]->comm_pending = nullptr; }
+    return rc;
 }
 
 int ctl_comm_destroy(ctl_ctx* c) {

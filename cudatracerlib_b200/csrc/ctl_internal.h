@@ -67,6 +67,14 @@ struct WptLane {
     void release() { w_thr.release(); w_lxy.release(); w_df.release(); w_ray.release(); w_misc.release(); w_res.release(); w_desc.release(); for (int k = 0; k < 2; k++) { w_sec[k].release(); w_sres[k].release(); } }
 };
 
+// One frame in flight ("FramesInFlight", ctl_submit_frame_tiled / ctl_acquire_frame): its own PixelData accumulator, sample-table generator state and
+// pinned table sets; rendered on wavefront lane slot + 1 (own stream, own wavefront buffers).
+struct FrameSlot {
+    DevBuf<float> accum; DevBuf<uint32_t> states; float* h1 = nullptr; float* h2 = nullptr; int h_cap = 0;
+    cudaEvent_t begin = nullptr, done = nullptr, ready = nullptr, h_free = nullptr;   // begin / done: the lane's kernels (timed); ready: accumulator final (after the reduce, if any)
+    uint32_t launches = 0, spp = 0; bool reduced = false;
+};
+
 struct ctl_ctx {
     ncclComm* comm = nullptr; int comm_rank = 0, comm_size = 1; unsigned long long* comm_scratch = nullptr;   // ctl_comm_init_* (ctl_comm.cu)
     int device = 0, w = 0, h = 0;
@@ -94,6 +102,8 @@ struct ctl_ctx {
     int defer = 0, defer_max_lag = 3; DevBuf<float4> df_sh_rays[MAX_LANES], df_sh_payload[MAX_LANES]; DevBuf<unsigned> df_cnt;   // "DeferStragglers": second shadow-queue buffer per lane, deferral counters
     int handover = 0, handover_drain = 16; DevBuf<uint32_t> ho_buf[2]; DevBuf<unsigned> ho_cnt;   // "HandOver": one-wavefront frames as two interleaved half-wavefronts whose traversal launches hand their unfinished rays over (device/traverse_handover.cuh)
     int overlap = 1, n_lanes = 4;   // "OverlapWavefronts", "OverlapLanes": see ctl_render_frame_tiled
+    // frames in flight: frame k renders on lane 1 + k % fif into fslot[k % fif] while the frames before it drain; ctl_acquire_frame hands them back in order
+    int fif = 2; FrameSlot fslot[MAX_LANES - 1]; unsigned long long f_submitted = 0, f_acquired = 0; float* lane_accum[MAX_LANES] = {}; cudaStream_t comm_stream = nullptr; int frame_root = 0; bool comm_defer = false; FrameSlot* comm_pending = nullptr;   // comm_defer: ctl_comm_submit_frame_all groups the reduces itself
     DevBuf<unsigned> api_work; unsigned api_seq = 0;   // ring of work counters of the API traversal launches: calls in flight on different streams never share one
     // WavefrontPathTracer queue (DoubleRayBuffer<WavefrontPTRayData>)
     WptLane wl[MAX_LANES];   // lane 0: ctl_wavefront_pass; lanes 1..: the other passes of a ctl_wavefront_frame in flight
@@ -118,3 +128,4 @@ struct ctl_ctx {
 inline int grid_for(const ctl_ctx* c, int per_sm) { return c->n_sm * per_sm; }
 int ctl_variance_after_pass(ctl_ctx* c, bool new_trace);   // ctl_pipeline.cu: PixelVarianceBuffer::AddPass after a whole-image pass
 void ctl_comm_release(ctl_ctx* c);                          // ctl_comm.cu: called by ctl_destroy
+int ctl_comm_reduce_slot(ctl_ctx* c, FrameSlot& F);         // ctl_comm.cu: the reduce of a frame in flight on the communication stream (no-op without a communicator)

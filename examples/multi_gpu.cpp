@@ -1,7 +1,8 @@
 // examples/multi_gpu.cpp -- the north star's multi-GPU step without Python: C++ host code over the C ABI, one process driving N GPUs of one node,
 // image tiled across them, a single NCCL reduce of the Spectrum accumulation buffer per frame (csrc/ctl_comm.cu; NCCL is loaded at run time).
 // Build:  g++ -std=c++17 -O2 examples/multi_gpu.cpp -Iinclude -Lcudatracerlib_b200 -lctl_b200 -Wl,-rpath,$PWD/cudatracerlib_b200 -o examples/ctl_multi_gpu
-// Usage:  examples/ctl_multi_gpu [scene=c4] [gpus=all] [frames=5] [spp=8] [WxH=1920x1080] [check]
+// Usage:  examples/ctl_multi_gpu [scene=c4] [gpus=all] [frames=5] [spp=8] [WxH=1920x1080] [inflight=1] [check]
+//         inflight=L > 1: the frames as a pipeline with L frames in flight (SubmitFrame / AcquireFrame: ctl_comm_submit_frame_all, ctl_acquire_frame).
 //         `check` also renders the frame on device 0 alone and compares the images (same paths => equal up to float summation order).
 #include <chrono>
 #include <cmath>
@@ -14,7 +15,7 @@
 
 int main(int ac, char** av) {
     const char* kinds[] = {"cornell", "cornell7", "c2", "c3", "c4", "c5", "soup"};
-    int kind = 4, gpus = 0, frames = 5, spp = 8, width = 1920, height = 1080, depth = 8; bool check_single = false;
+    int kind = 4, gpus = 0, frames = 5, spp = 8, width = 1920, height = 1080, depth = 8, inflight = 1; bool check_single = false;
     for (int i = 1; i < ac; i++) {
         const std::string a = av[i]; unsigned w2 = 0, h2 = 0; int k = -1;
         for (int j = 0; j < 7; j++) if (a == kinds[j]) k = j;
@@ -25,7 +26,8 @@ int main(int ac, char** av) {
         else if (a.rfind("frames=", 0) == 0) frames = atoi(a.c_str() + 7);
         else if (a.rfind("spp=", 0) == 0) spp = atoi(a.c_str() + 4);
         else if (a.rfind("depth=", 0) == 0) depth = atoi(a.c_str() + 6);
-        else { fprintf(stderr, "accepts: scene name, gpus=N, frames=N, spp=N, depth=N, WxH, check\n"); return 2; }
+        else if (a.rfind("inflight=", 0) == 0) inflight = atoi(a.c_str() + 9);
+        else { fprintf(stderr, "accepts: scene name, gpus=N, frames=N, spp=N, depth=N, inflight=N, WxH, check\n"); return 2; }
     }
     try {
         if (gpus <= 0) { // all devices: probe by creating contexts until it fails
@@ -41,12 +43,22 @@ int main(int ac, char** av) {
         std::vector<ctl_pixel_data> img((size_t)width * height);
         unsigned long long rays = mt.RenderFrame(spp, batch, nullptr);   // warm-up
         const auto t0 = std::chrono::steady_clock::now();
+        if (inflight > 1) {   // the pipeline: frame f is submitted while frames f-1 .. f-inflight+1 render; images come back in order
+            mt.setParameter("FramesInFlight", inflight);
+            int got = 0;
+            for (int f = 0; f < frames; f++) {
+                mt.SubmitFrame(spp, batch);
+                if (f >= inflight - 1) { got++; mt.AcquireFrame(got == frames ? img.data() : nullptr); }
+            }
+            while (mt.FramesInFlight()) { got++; mt.AcquireFrame(got == frames ? img.data() : nullptr); }
+            for (int d = 0; d < gpus; d++) mt.device(d).Synchronize();
+        } else
         for (int f = 0; f < frames; f++) rays = mt.RenderFrame(spp, batch, f + 1 == frames ? img.data() : nullptr);
         const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         double mean = 0; for (auto& p : img) mean += (p.rgb[0] + p.rgb[1] + p.rgb[2]) / (3.0 * (p.weight_sum > 0 ? p.weight_sum : 1));
         mean /= (double)img.size();
-        printf("{\"scene\": \"%s\", \"gpus\": %d, \"frames\": %d, \"spp\": %d, \"width\": %d, \"height\": %d, \"rays_per_frame\": %llu, \"ms_per_frame\": %.3f, \"mrays_s\": %.1f, \"image_mean\": %.6f",
-               kinds[kind], gpus, frames, spp, width, height, rays, 1e3 * s / frames, rays * (double)frames / s / 1e6, mean);
+        printf("{\"scene\": \"%s\", \"gpus\": %d, \"frames\": %d, \"spp\": %d, \"width\": %d, \"height\": %d, \"rays_per_frame\": %llu, \"ms_per_frame\": %.3f, \"mrays_s\": %.1f, \"image_mean\": %.6f, \"frames_in_flight\": %d",
+               kinds[kind], gpus, frames, spp, width, height, rays, 1e3 * s / frames, rays * (double)frames / s / 1e6, mean, inflight);
         if (check_single) {
             ctlb200::PathTracer one(0);
             one.setParameter("MaxPathLength", depth); one.Resize(width, height); one.InitializeScene(scene.view());

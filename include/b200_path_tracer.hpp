@@ -167,6 +167,17 @@ public:
         if (image) check(ctl_read_accum(t_[0]->handle(), image));
         return frame_rays;
     }
+    // A sequence of frames as a pipeline (ctl_comm_submit_frame_all / ctl_acquire_frame, "FramesInFlight"): SubmitFrame enqueues one more frame on every device
+    // (its own lane and accumulator; the reduce on the communication streams); AcquireFrame waits for the oldest one and, optionally, reads its image.
+    void SubmitFrame(int spp, int batch, int tile = 64) {
+        std::vector<ctl_ctx*> c; for (auto& t : t_) c.push_back(t->handle());
+        check(ctl_comm_submit_frame_all(c.data(), devices(), spp, batch, tile, 0));
+    }
+    void AcquireFrame(ctl_pixel_data* image = nullptr) {
+        for (auto& t : t_) check(ctl_acquire_frame(t->handle()));
+        if (image) check(ctl_read_accum(t_[0]->handle(), image));
+    }
+    int FramesInFlight() const { return ctl_frames_in_flight(t_[0]->handle()); }
 private:
     std::vector<std::unique_ptr<PathTracer>> t_; unsigned w_ = 0, h_ = 0; unsigned long long rays_before_ = 0;
 };

@@ -355,6 +355,18 @@ int ctl_render_passes_tiled(ctl_ctx*, int new_trace, int n_passes, int tile_w, i
  * GPU: 37.6 ms per frame with or without, hence off.  Asynchronous on the context's stream (the other streams are joined before
  * the call returns work to it). */
 int ctl_render_frame_tiled(ctl_ctx*, int spp, int batch, int tile_w, int tile_h, int part, int n_parts);
+/* FRAMES IN FLIGHT -- a sequence of frames (== repeated StartNewTrace + spp DoPass calls, Kernel/Tracer.h:209-248; the reference finishes every pass with a
+ * device synchronise, Kernel/TraceHelper.cu:744-745) as a pipeline.  ctl_submit_frame_tiled enqueues one whole frame -- accumulator clear, sample tables,
+ * all wavefronts -- on a wavefront lane of its own (stream, wavefront buffers, PixelData accumulator, table sets); up to "FramesInFlight" (ctl_set_param_i,
+ * 1..7, default 2) frames may be outstanding.  ctl_acquire_frame makes the context's stream wait for the OLDEST outstanding frame and makes that frame's
+ * accumulator the context's accumulator (ctl_accum_device_ptr, ctl_resolve_*, ctl_apply_image_pipeline, ctl_read_accum then see it; it stays valid until
+ * FramesInFlight further frames have been submitted); ctl_stats afterwards reports that frame's device time on its lane.  A lane starts after the work
+ * the context's stream held when the frame was submitted.  The frames are the frames ctl_render_frame_tiled renders (same paths; only the order of the float
+ * atomics differs); what the pipeline buys is that the drain of every persistent traversal launch -- the scene's longest rays, ~0.45 ms per launch whatever
+ * its size -- is filled by the other frames' launches.  Other render calls fail while frames are outstanding.  Asynchronous. */
+int ctl_submit_frame_tiled(ctl_ctx*, int spp, int batch, int tile_w, int tile_h, int part, int n_parts);
+int ctl_acquire_frame(ctl_ctx*);
+int ctl_frames_in_flight(ctl_ctx*);   /* frames submitted and not yet acquired */
 /* == WavefrontPathTracer: Tracer<true>::DoPass + WavefrontPathTracer::DoRender (Kernel/Tracer.h:209-248,
  *    Integrators/PseudoRealtime/WavefrontPathTracer.cu:166-191) over a DoubleRayBuffer-shaped device queue (Kernel/DoubleRayBuffer.h):
  *    the reference's own wavefront integrator, second consumer of the intersect kernel.  Same parameters as the reference
@@ -448,6 +460,11 @@ int ctl_comm_allreduce_u64(ctl_ctx*, uint64_t* host_inout, int count);
 /* One progressive frame shared by the ranks: `spp` passes (`batch` fused per wavefront) on this rank's interleaved tile x tile tiles
  * (tile index % ranks == rank; tile <= 0 = 64), then ctl_comm_reduce_accum(root).  Asynchronous. */
 int ctl_comm_render_frame(ctl_ctx*, int spp, int batch, int tile, int root);
+/* The pipelined form (frames in flight, see ctl_submit_frame_tiled): this rank's tiles of one more frame on its own lane, and the frame's ncclReduce to `root`
+ * on the context's communication stream (its own high-priority stream: every rank enqueues the reduces in submission order, and neither the rendering lanes nor
+ * the context's stream wait for the other ranks).  ctl_acquire_frame returns the frames in order; on the root the acquired accumulator is the whole image. */
+int ctl_comm_submit_frame(ctl_ctx*, int spp, int batch, int tile, int root);
+int ctl_comm_submit_frame_all(ctl_ctx* const* contexts, int n, int spp, int batch, int tile, int root); /* for ctl_comm_init_all communicators */
 int ctl_comm_destroy(ctl_ctx*);
 
 #ifdef __cplusplus
