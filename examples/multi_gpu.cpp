@@ -42,9 +42,14 @@ int main(int ac, char** av) {
         mt.InitializeScene(scene.view());
         std::vector<ctl_pixel_data> img((size_t)width * height);
         unsigned long long rays = mt.RenderFrame(spp, batch, nullptr);   // warm-up
+        if (inflight > 1) {   // warm-up of the pipeline's lanes (their buffers are allocated on first use)
+            mt.setParameter("FramesInFlight", inflight);
+            for (int f = 0; f < inflight; f++) mt.SubmitFrame(spp, batch);
+            while (mt.FramesInFlight()) mt.AcquireFrame();
+            for (int d = 0; d < gpus; d++) mt.device(d).Synchronize();
+        }
         const auto t0 = std::chrono::steady_clock::now();
         if (inflight > 1) {   // the pipeline: frame f is submitted while frames f-1 .. f-inflight+1 render; images come back in order
-            mt.setParameter("FramesInFlight", inflight);
             int got = 0;
             for (int f = 0; f < frames; f++) {
                 mt.SubmitFrame(spp, batch);
