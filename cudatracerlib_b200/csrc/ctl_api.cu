@@ -117,6 +117,8 @@ void ctl_destroy(ctl_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int k = 1; k < MAX_LANES; k++) if (c->lane_stream[k]) cudaStreamSynchronize(c->lane_stream[k]);   // frames still in flight: their kernels and reduces end first
+    if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
     ctl_comm_release(c);
     c->d_scene_nodes.release(); c->d_bvh_nodes.release(); c->d_woop.release(); c->d_tri_index.release(); c->d_tri_data.release(); c->d_meshes.release();
     c->d_nodes.release(); c->d_xf.release(); c->d_inv_xf.release(); c->d_materials.release(); c->d_lights.release(); c->d_light_tris.release();
@@ -238,6 +240,7 @@ static int upload_staging(ctl_ctx* c, const ctl_scene_view* v, bool with_tris) {
 
 int ctl_upload_scene(ctl_ctx* c, const ctl_scene_view* v) {
     if (!c || !v) return set_err("null argument");
+    if (c->f_submitted != c->f_acquired) return set_err("ctl_upload_scene: frames are in flight (ctl_acquire_frame them first)");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     CK(c->d_scene_nodes.upload(v->scene_bvh_nodes, v->n_scene_bvh_nodes)); CK(c->d_bvh_nodes.upload(v->bvh_nodes, v->n_bvh_nodes));
@@ -276,6 +279,7 @@ int ctl_upload_scene(ctl_ctx* c, const ctl_scene_view* v) {
 int ctl_update_scene_nodes(ctl_ctx* c, const ctl_scene_view* v) {
     if (!c || !v) return set_err("null argument");
     if (!c->has_scene) return set_err("no scene uploaded");
+    if (c->f_submitted != c->f_acquired) return set_err("ctl_update_scene_nodes: frames are in flight (ctl_acquire_frame them first)");
     if (v->node_alias || c->n_alias) return ctl_upload_scene(c, v);   // re-braided view (now or before): its mesh-level records follow the node level -> everything is uploaded
     if (v->n_bvh_nodes != c->d_bvh_nodes.n && v->n_bvh_nodes > c->d_bvh_nodes.n) return set_err("the view has other meshes than the uploaded scene: use ctl_upload_scene");
     CK(cudaSetDevice(c->device));

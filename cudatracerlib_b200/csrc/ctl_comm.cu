@@ -49,6 +49,7 @@ int nccl_fail(const char* what, int rc) { return ctl_set_err(std::string(what) +
 } // namespace
 
 void ctl_comm_release(ctl_ctx* c) {
+    if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);   // reduces of frames in flight
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     c->comm = nullptr; c->comm_rank = 0; c->comm_size = 1;
     if (c->comm_scratch) cudaFree(c->comm_scratch);

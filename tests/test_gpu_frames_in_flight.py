@@ -82,7 +82,7 @@ def test_pipeline_errors(built_lib):
     t.submitFrame(2, 2); t.submitFrame(2, 2)
     with pytest.raises(RuntimeError, match="outstanding"):
         t.submitFrame(2, 2)
-    for call in (lambda: t.DoPass(), lambda: t.DoFrame(2, 2), lambda: t.DoPasses(2, new_trace=True), lambda: t.setParameter("FramesInFlight", 3), lambda: t.Resize(32, 32)):
+    for call in (lambda: t.DoPass(), lambda: t.DoFrame(2, 2), lambda: t.DoPasses(2, new_trace=True), lambda: t.setParameter("FramesInFlight", 3), lambda: t.Resize(32, 32), lambda: t.InitializeScene(s)):
         with pytest.raises(RuntimeError, match="in flight"):
             call()
     t.acquireFrame(); t.acquireFrame(); t.synchronize()
