@@ -100,6 +100,13 @@ public:
     void DoFrameTiled(int spp, int batch = 8, int part = 0, int n_parts = 1, int tile = 64) {
         need_ctx(); check(ctl_render_frame_tiled(ctx_, spp, batch, tile, tile, part, n_parts)); new_trace_ = false;
     }
+    // a sequence of frames as a pipeline ("FramesInFlight"): SubmitFrame enqueues one more frame on a lane of its own, AcquireFrame hands back the oldest one
+    // (ctl_submit_frame_tiled / ctl_acquire_frame); asynchronous, `image` (optional) reads the acquired frame's PixelData
+    void SubmitFrame(int spp, int batch = 8, int part = 0, int n_parts = 1, int tile = 64) {
+        need_ctx(); check(ctl_submit_frame_tiled(ctx_, spp, batch, tile, tile, part, n_parts)); new_trace_ = true;
+    }
+    void AcquireFrame(ctl_pixel_data* image = nullptr) { need_ctx(); check(ctl_acquire_frame(ctx_)); if (image) check(ctl_read_accum(ctx_, image)); }
+    int FramesInFlight() const { return ctx_ ? ctl_frames_in_flight(ctx_) : 0; }
     void Synchronize() { need_ctx(); check(ctl_synchronize(ctx_)); }
     ctl_ctx* handle() { return ctx_; }
 protected:
