@@ -1,5 +1,5 @@
-"""Parity where the benchmark runs: 1920x1080, 8 passes fused into one wavefront through ctl_render_passes_tiled -- the exact call bench.py makes --
-compared with the oracle on fixed windows of the frame: the bottom-right corner (sampler indices up to 2 073 599, far beyond the 65 536 the small test
+"""Parity where the benchmark runs: 1920x1080, 8 passes fused into one wavefront through ctl_render_passes_tiled and through the frames-in-flight
+pipeline (ctl_submit_frame_tiled / ctl_acquire_frame) -- the exact calls bench.py makes -- compared with the oracle on fixed windows of the frame: the bottom-right corner (sampler indices up to 2 073 599, far beyond the 65 536 the small test
 images reach: (idx / 4096) % 4096 > 15, Kernel/Sampler_device.h:91-107) and a window straddling several 64x64 tile boundaries.
 
 Tolerances: same seed, same passes; per-pixel relative L2 <= 1e-3 on >= 99 % of the pixels, image relative RMSE <= 3e-3 at 8 spp, mean
@@ -31,6 +31,16 @@ def test_full_resolution_windows_match_oracle(built_lib, orc, kind):
     assert t.getNumPassesDone() == SPP
     landed = float(img["weight_sum"].astype(np.float64).sum())
     assert SPP * W * H - 64 <= landed <= SPP * W * H             # every path of every pass landed (a jittered sample may round into the next pixel; past the image edge it is dropped, Image.cu:22-44)
+    # the same frame as bench.py renders it since the frames-in-flight pipeline: ctl_submit_frame_tiled / ctl_acquire_frame, 3 frames in flight, whole image
+    t.setParameter("FramesInFlight", 3)
+    r0 = t.getTotalRays()
+    for _ in range(3):
+        t.submitFrame(SPP, SPP)
+    for _ in range(3):
+        t.acquireFrame(); piped = t.readAccumulator()
+        assert np.array_equal(piped["weight_sum"], img["weight_sum"])
+        assert np.allclose(piped["rgb"], img["rgb"], rtol=2e-5, atol=1e-6)    # same paths; only the order of the float atomics into a pixel differs
+    assert t.getTotalRays() - r0 == 3 * rays_stop
     # the same frame with the reference's ray definition
     t.setParameter("StopZeroThroughput", 0)
     t.DoPasses(SPP, new_trace=True); t.synchronize()
