@@ -128,6 +128,7 @@ int ctl_comm_reduce_accum(ctl_ctx* c, int root) {
     if (!c) return ctl_set_err("null context");
     if (!c->comm) return c->comm_size == 1 ? 0 : ctl_set_err("no communicator: ctl_comm_init_rank / ctl_comm_init_all first");
     if (root < 0 || root >= c->comm_size) return ctl_set_err("root out of range");
+    if (c->f_submitted != c->f_acquired) return ctl_set_err("ctl_comm_reduce_accum: frames are in flight (their reduces run on the communication stream; ctl_acquire_frame them first)");
     NEED_NCCL();
     CK(cudaSetDevice(c->device));
     NK("ncclReduce", N->Reduce(c->accum, c->accum, (size_t)c->w * c->h * 7, NCCL_FLOAT32, NCCL_SUM, root, c->comm, c->stream));
