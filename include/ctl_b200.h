@@ -349,11 +349,12 @@ int ctl_render_pass_tiled(ctl_ctx*, int new_trace, int tile_w, int tile_h, int p
  * overhead; path state is ~230 B x pixels x n_passes of HBM.  part=0, n_parts=1 renders the whole image. */
 int ctl_render_passes_tiled(ctl_ctx*, int new_trace, int n_passes, int tile_w, int tile_h, int part, int n_parts);
 /* One progressive FRAME (== StartNewTrace + spp DoPass calls, Kernel/Tracer.h:209-248) on the tiles of `part`, `batch` passes fused per wavefront
- * (spp % batch == 0).  With "OverlapWavefronts" = 1 (default 0; "OverlapLanes" 2..4 streams) the frame's wavefronts alternate between streams with
- * their own wavefront buffers (a frame of fewer wavefronts than lanes is cut into smaller batches), so that the draining end of one persistent traversal
- * launch can overlap the head of another's; the paths traced are identical either way.  Measured on the 1 M-triangle scene at 1/8 of the image per
- * GPU: 37.6 ms per frame with or without, hence off.  Asynchronous on the context's stream (the other streams are joined before
- * the call returns work to it). */
+ * (spp % batch == 0).  With "OverlapWavefronts" = 1 (the default) a frame of SEVERAL wavefronts runs them on up to "OverlapLanes" (default 4) streams with
+ * their own wavefront buffers, so that the draining end of one persistent traversal launch overlaps the head of another lane's (configs[4] at 1/8 of the
+ * image per GPU: 457.9 -> 331.9 ms per frame); = 2 also cuts a frame of fewer wavefronts than lanes into smaller batches (measured on the 1 M-triangle
+ * scene at 1/8 of the image: 37.6 ms per frame with or without -- what the overlap gains the extra launches lose, DESIGN.md section 5 -- hence not the
+ * default; one-wavefront frames overlap with the NEXT frame instead: ctl_submit_frame_tiled below); = 0 never.  The paths traced are identical either way.
+ * Asynchronous on the context's stream (the other streams are joined before the call returns work to it). */
 int ctl_render_frame_tiled(ctl_ctx*, int spp, int batch, int tile_w, int tile_h, int part, int n_parts);
 /* FRAMES IN FLIGHT -- a sequence of frames (== repeated StartNewTrace + spp DoPass calls, Kernel/Tracer.h:209-248; the reference finishes every pass with a
  * device synchronise, Kernel/TraceHelper.cu:744-745) as a pipeline.  ctl_submit_frame_tiled enqueues one whole frame -- accumulator clear, sample tables,
