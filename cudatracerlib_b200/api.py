@@ -134,6 +134,7 @@ def lib():
     L.ctl_encode_woop.argtypes = [vp, vp, vp, vp]; L.ctl_encode_woop.restype = None
     L.ctl_encode_tri_data.argtypes = [vp, vp, vp, u32, vp]; L.ctl_encode_tri_data.restype = None
     L.ctl_generate_sample_tables.argtypes = [u32, vp, vp]
+    L.ctl_generate_sample_tables_n.argtypes = [u32, i32, vp, vp]
     L.ctl_create.restype = vp; L.ctl_create.argtypes = [i32, i32, i32]
     L.ctl_destroy.argtypes = [vp]; L.ctl_destroy.restype = None
     L.ctl_resize.argtypes = [vp, i32, i32]
@@ -567,6 +568,13 @@ class WavefrontPathTracer(PathTracer):
 def generate_sample_tables(pass_index):
     d1 = np.zeros(4096 * 30, np.float32); d2 = np.zeros(4096 * 30 * 2, np.float32)
     _check(lib().ctl_generate_sample_tables(pass_index, _ptr(d1), _ptr(d2)))
+    return d1, d2
+
+
+def generate_sample_tables_n(first_pass, n):
+    """ctl_generate_sample_tables_n: passes first_pass .. first_pass+n-1 produced concurrently (jump-ahead start states); returns [n, 4096*30] and [n, 4096*60]."""
+    d1 = np.zeros((n, 4096 * 30), np.float32); d2 = np.zeros((n, 4096 * 30 * 2), np.float32)
+    _check(lib().ctl_generate_sample_tables_n(first_pass, n, _ptr(d1), _ptr(d2)))
     return d1, d2
 
 

@@ -350,7 +350,7 @@ static int generate_tables(ctl_ctx* c, uint32_t first, int n, int set0 = 0, cuda
         if (wait_free) CK(cudaEventSynchronize(c->h_tab_free));
         float* h1 = c->h_tab1 + TAB1 * set0; float* h2 = c->h_tab2 + TAB2 * set0;
         if (c->gen_pos_host != first) { uint32_t from = c->gen_pos_host; if (from > first) { c->gen.reset(); from = 0; } for (uint32_t p = from; p < first; p++) c->gen.next_pass(h1, h2); }
-        for (int p = 0; p < n; p++) c->gen.next_pass(h1 + TAB1 * p, h2 + TAB2 * p);
+        ctlb::generate_passes_threaded(c->gen, n, h1, h2, TAB1, TAB2);   // the n passes concurrently (start states by jump-ahead): bit-identical to n next_pass calls
         CK(cudaMemcpyAsync(d1, h1, TAB1 * 4 * n, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d2, h2, TAB2 * 4 * n, cudaMemcpyHostToDevice, st));
         CK(cudaEventRecord(c->h_tab_free, st));
@@ -920,7 +920,7 @@ static int frame_tables(ctl_ctx* c, FrameSlot& F, int set0, int spp, cudaStream_
         }
         CK(cudaEventSynchronize(F.h_free));   // the copies of the frame that used this slot last have left the pinned sets
         c->gen.reset();
-        for (int p = 0; p < spp; p++) c->gen.next_pass(F.h1 + TAB1 * p, F.h2 + TAB2 * p);
+        ctlb::generate_passes_threaded(c->gen, spp, F.h1, F.h2, TAB1, TAB2);
         c->gen_pos_host = (uint32_t)spp;
         CK(cudaMemcpyAsync(d1, F.h1, TAB1 * 4 * spp, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d2, F.h2, TAB2 * 4 * spp, cudaMemcpyHostToDevice, st));

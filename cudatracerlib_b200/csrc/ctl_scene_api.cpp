@@ -123,6 +123,16 @@ int ctl_generate_sample_tables(uint32_t pass, float* d1, float* d2) {
     for (uint32_t p = 0; p <= pass; p++) g.next_pass(d1, d2);
     return 0;
 }
+// Passes first .. first+n-1 into n consecutive table sets, the passes produced concurrently (ctlb::generate_passes: start states by jump-ahead); what
+// the context does for the frames it renders with host-generated tables.  Bit-identical to n ctl_generate_sample_tables calls (tests/test_golden_cpu.py).
+int ctl_generate_sample_tables_n(uint32_t first, int n, float* d1, float* d2) {
+    if (!d1 || !d2 || n < 1) return 1;
+    ctlb::SamplerTableGenerator g;
+    const size_t T1 = (size_t)ctlb::kNumSeq * ctlb::kSeqLen;
+    for (uint32_t p = 0; p < first; p++) { ctlb::pass_jump().apply(g.v, g.v); g.d += 362437u * (uint32_t)ctlb::kDrawsPerPass; }   // skip whole passes by jump-ahead
+    ctlb::generate_passes_threaded(g, n, d1, d2, T1, 2 * T1);
+    return 0;
+}
 
 
 } // extern "C"

@@ -8,6 +8,9 @@
 // draw is the y component (g++ evaluates Vec2f(rng.randomFloat(), rng.randomFloat()) right to left).
 #pragma once
 #include <cstdint>
+#include <cstddef>
+#include <thread>
+#include <vector>
 
 namespace ctlb {
 
@@ -83,6 +86,43 @@ inline void device_generator_data(uint32_t* states0, XorwowJump* jump_to_next_pa
         for (int i = 0; i < kDrawsPerSeq; i++) g.next();
     }
     *jump_to_next_pass = XorwowJump::power((unsigned long long)(kDrawsPerPass - kDrawsPerSeq));
+}
+
+// ---- several passes at once on the host ------------------------------------------------------------------------
+// The passes of a frame are consecutive slices of ONE stream, but the start state of pass p+1 is the start state of pass p jumped kDrawsPerPass draws
+// ahead (the same GF(2) matrix trick as the device generator, plus the Weyl counter's closed form), so the n passes of a frame can be produced by n
+// threads, each running the plain sequential generator over its own pass: bit-identical tables, 1/n of the 1.3 ms per pass of host time per frame.
+// `g` is the generator at the start of the first pass and is left at the start of the pass after the last one, as n next_pass calls would leave it.
+inline const XorwowJump& pass_jump() { static const XorwowJump J = XorwowJump::power((unsigned long long)kDrawsPerPass); return J; }
+template <typename Launch>   // Launch(fn): runs fn(k) for k = 0 .. n-1, possibly concurrently (std::thread in the library, a plain loop in tests)
+inline void generate_passes(SamplerTableGenerator& g, int n, float* d1, float* d2, size_t stride1, size_t stride2, Launch&& launch) {
+    if (n <= 0) return;
+    SamplerTableGenerator* start = new SamplerTableGenerator[n + 1];
+    start[0] = g;
+    for (int p = 1; p <= n; p++) {
+        start[p] = start[p - 1];
+        pass_jump().apply(start[p - 1].v, start[p].v);
+        start[p].d = start[p - 1].d + 362437u * (uint32_t)kDrawsPerPass;
+    }
+    launch([&](int k) { SamplerTableGenerator local = start[k]; local.next_pass(d1 + stride1 * k, d2 + stride2 * k); });
+    g = start[n];
+    delete[] start;
+}
+
+// The library's launcher: one thread per pass, at most 8 and at most the host's cores at a time (a frame of 8 passes: 10.3 ms -> ~1.5 ms of host time).
+inline void generate_passes_threaded(SamplerTableGenerator& g, int n, float* d1, float* d2, size_t stride1, size_t stride2) {
+    generate_passes(g, n, d1, d2, stride1, stride2, [n](auto&& fn) {
+        unsigned hw = std::thread::hardware_concurrency(); if (hw == 0) hw = 1;
+        const int width = n < 2 ? 1 : (int)(hw < 8u ? hw : 8u);
+        if (width <= 1) { for (int k = 0; k < n; k++) fn(k); return; }
+        for (int k0 = 0; k0 < n; k0 += width) {
+            std::vector<std::thread> th;
+            const int k1 = k0 + width < n ? k0 + width : n;
+            for (int k = k0 + 1; k < k1; k++) th.emplace_back([&fn, k] { fn(k); });
+            fn(k0);
+            for (auto& t : th) t.join();
+        }
+    });
 }
 
 } // namespace ctlb

@@ -286,6 +286,9 @@ void ctl_encode_tri_data(const float p[9], const float n[9], const float uv[6], 
  * tracer: XORWOW curand_init(1234, 7539414, 0), 4096*(30+60) draws per pass.
  * d1: n_seq*seq_len floats, d2: n_seq*seq_len*2 floats, element (seq,dim) at dim*n_seq+seq. */
 int ctl_generate_sample_tables(uint32_t pass, float* d1, float* d2);
+/* Passes first .. first+n-1 into n consecutive table sets (set k at d1 + k*4096*30, d2 + k*4096*60), produced concurrently on host threads: the start
+ * state of every pass comes from a GF(2) jump-ahead of 4096*90 draws, each thread then runs the sequential generator.  Bit-identical to n calls above. */
+int ctl_generate_sample_tables_n(uint32_t first_pass, int n, float* d1, float* d2);
 
 /* ---- tracer context (Kernel/Tracer.h:67-294, Integrators/PathTracer.h:7-24) --- */
 

@@ -35,6 +35,22 @@ def test_product_table_generator_matches_reference(built_lib):
         assert d2.astype(np.float64).sum() == GOLD[f"tables_p{p}_sums"][1]
 
 
+def test_concurrent_table_generator_matches_sequential_and_reference(built_lib):
+    """ctl_generate_sample_tables_n (what the context runs for frames with host-generated tables): the passes of a frame produced by concurrent host threads from
+    jump-ahead start states are the tables of the sequential generator, bit for bit -- and therefore the reference generator's (goldens of passes 0 and 5)."""
+    d1, d2 = ctl.generate_sample_tables_n(0, 8)
+    for p in (0, 5):
+        assert np.array_equal(d1[p][:8192].view(np.uint32), GOLD[f"tables_p{p}_d1_head"].view(np.uint32))
+        assert np.array_equal(d2[p][:16384].view(np.uint32), GOLD[f"tables_p{p}_d2_head"].view(np.uint32))
+        s = GOLD[f"tables_p{p}_sums"]
+        assert d1[p].astype(np.float64).sum() == s[0] and d2[p].astype(np.float64).sum() == s[1] and d1[p][-1] == np.float32(s[2]) and d2[p][-1] == np.float32(s[3])
+    for first, n in ((0, 8), (3, 5), (6, 1), (2, 19)):
+        e1, e2 = ctl.generate_sample_tables_n(first, n)
+        for k in (0, n // 2, n - 1):
+            a, b = ctl.generate_sample_tables(first + k)
+            assert np.array_equal(a.view(np.uint32), e1[k].view(np.uint32)) and np.array_equal(b.view(np.uint32), e2[k].view(np.uint32))
+
+
 def test_woop_encoding(orc, built_lib):
     for t, w in zip(GOLD["woop_tris"], GOLD["woop_data"]):
         assert np.array_equal(orc.encode_woop(t[0], t[1], t[2]).view(np.uint32), w.view(np.uint32))
